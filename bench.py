@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py - distillation-loss fwd+bwd throughput on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[4], weak scaling): per GPU logits 16x150x128x128 fp32
+(= global B=128 on 8 GPUs), one step = CGDLoss(g=10, tau=2, alpha=3) + CDLoss forward AND
+backward on that batch through the loss modules (the reference-facing plugin API).  `value` =
+Mpixel/s with the maps resident in HBM; `e2e` = same through the modules from pinned HOST
+buffers (H2D of S and T and D2H of the loss scalars inside the timed region).  Inputs
+(2 x 157 MB per GPU) exceed the 126 MB L2, so no L2 flush is needed between iterations.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B_PER_GPU, C, H, W = 16, 150, 128, 128
+CGD = dict(group_size=10, alpha=3, tau=2)
+METRIC = 'distill-loss fwd+bwd Mpixel/s'
+UNIT = 'Mpixel/s'
+WORKLOAD = ('cfg5 shard: CGDLoss(g=10,tau=2,alpha=3)+CDLoss fwd+bwd on logits %dx%dx%dx%d fp32 per GPU '
+            '(global B=128 at 8 GPUs)' % (B_PER_GPU, C, H, W))
+FALLBACK_HBM_GBS = 6650.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU oracle leg (profiling runs)')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--extra', action='store_true', help='also time the other BASELINE configs (N=1 only)')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], None, set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': smax,
+                'reasons': sorted(reasons), 'samples': len(sm), 'power_w_max': max(power) if power else None}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs, copy burst)'
+    except Exception:
+        return FALLBACK_HBM_GBS, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def profiled_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            return json.load(f).get('kl_rows_tma_kernel_cd_bytes_per_launch')
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------ CPU oracle legs
+def cpu_oracle_step_time(batch, steps, warmup, threads=None):
+    """Reference algorithm (oracle port of losses.py) on the host cores: CGD+CD fwd+bwd on `batch` samples."""
+    import torch
+    import oracle
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    s = torch.randn(batch, C, H, W)
+    t = torch.randn(batch, C, H, W)
+    gt = torch.zeros(batch, 1, H, W, dtype=torch.long)
+    crits = [oracle.make_preset('CGDLoss', **CGD), oracle.make_preset('CDLoss')]
+    times = []
+    for i in range(warmup + steps):
+        x = s.clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        loss = crits[0](x, t, gt, 1) + crits[1](x, t, gt, 1)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times, float(loss.detach())
+
+
+def run_reference_arm(args, rank):
+    """--impl reference: the reference's own algorithm on the host CPU (oracle port; the reference is a
+    Python package that cannot travel to the GPU box), every host thread, bounded sample per step."""
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_b = 2
+    times, _ = cpu_oracle_step_time(sample_b, args.steps, args.warmup)
+    total = sum(times)
+    value = sample_b * H * W * len(times) / total / 1e6
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'timing': 'host perf_counter, CPU only'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                         'sample': f'each step = CGD+CD fwd+bwd on {sample_b} of the {B_PER_GPU} samples '
+                                   f'({sample_b}x{C}x{H}x{W} fp32), oracle port of losses.py on torch CPU'},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import segdistill_b200 as sd
+    from segdistill_b200 import _cabi
+    from segdistill_b200 import dist as sdist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    assert _cabi.load().sd_device_check() == 0, 'not an sm_100 device'
+
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    S = torch.randn(B_PER_GPU, C, H, W, device=dev, generator=g).requires_grad_(True)
+    T = torch.randn(B_PER_GPU, C, H, W, device=dev, generator=g)
+    gt = torch.zeros(B_PER_GPU, 1, H, W, dtype=torch.long, device=dev)
+    cgd, cd = sd.CGDLoss(**CGD), sd.CDLoss()
+    numel = S.numel()
+    packed = torch.zeros(3, device=dev)
+
+    def step(record=None):
+        S.grad = None
+        if record:
+            record[0].record()
+        l1 = cgd(S, T, gt, 1)
+        if record:
+            record[1].record()
+        l2 = cd(S, T, gt, 1)
+        if record:
+            record[2].record()
+        (l1 + l2).backward()
+        if world > 1:                      # the path's only collective: packed loss scalars, async
+            packed[0], packed[1] = l1.detach(), l2.detach()
+            dist.all_reduce(packed)
+        return l1, l2
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---- timed region: exactly K steps, device time
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _cabi.launch_count()
+    sync_all()
+    t_begin.record()
+    for i in range(args.steps):
+        l1, l2 = step(evs[i])
+    t_end.record()
+    sync_all()
+    launches = _cabi.launch_count() - launches0
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms = tt.item()
+    assert _cabi.workspace_error_flag() == 0
+    cgd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
+    cd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+    ms_per_step = elapsed_ms / args.steps
+    value = world * B_PER_GPU * H * W / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: pinned host buffers -> H2D -> modules -> D2H of the loss scalars, every step
+    e2e = None
+    if not args.no_e2e:
+        hS = torch.randn(B_PER_GPU, C, H, W).pin_memory()
+        hT = torch.randn(B_PER_GPU, C, H, W).pin_memory()
+        dS_in = torch.empty_like(S).requires_grad_(True)
+        dT_in = torch.empty_like(T)
+
+        def e2e_step():
+            dS_in.grad = None
+            with torch.no_grad():
+                dS_in.copy_(hS, non_blocking=True)
+                dT_in.copy_(hT, non_blocking=True)
+            losses = {'loss_cgd': cgd(dS_in, dT_in, gt, 1), 'loss_cd': cd(dS_in, dT_in, gt, 1)}
+            total, logs = sdist.parse_losses(losses)     # one packed all-reduce + ONE D2H read per step
+            total.backward()
+            return logs
+
+        n_e2e = max(3, min(args.steps, 10))
+        for _ in range(2):
+            e2e_step()
+        sync_all()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        b.record()
+        sync_all()
+        ems = a.elapsed_time(b)
+        if world > 1:
+            tt = torch.tensor([ems], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ems = tt.item()
+        e2e = {'value': world * B_PER_GPU * H * W / (ems / n_e2e * 1e-3) / 1e6, 'unit': UNIT,
+               'h2d_bytes_per_step': 2 * numel * 4, 'd2h_bytes_per_step': 3 * 4, 'steps': n_e2e,
+               'ms_per_step': ems / n_e2e}
+        del hS, hT, dS_in, dT_in
+
+    extra = None
+    if args.extra and world == 1:
+        extra = extra_configs(dev)
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample_b = 4
+        times, _ = cpu_oracle_step_time(sample_b, steps=2, warmup=1, threads=cores)
+        best = min(times)
+        cpu = {'value': sample_b * H * W / best / 1e6, 'unit': UNIT, 'cores': torch.get_num_threads(),
+               'kind': 'port',
+               'sample': f'CGD+CD fwd+bwd on {sample_b} of the {B_PER_GPU} samples ({sample_b}x{C}x{H}x{W} fp32), '
+                         f'best of 2 after 1 warm-up, oracle port of losses.py on torch CPU'}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        cd_bytes = 12.0 * numel                      # read S + read T + write dS, fp32
+        achieved = cd_bytes / (cd_ms * 1e-3) / 1e9
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'per_gpu_shape': [B_PER_GPU, C, H, W], 'losses': ['CGDLoss', 'CDLoss'],
+                       'l2': 'inputs (2 x 157 MB per GPU) exceed the 126 MB L2; no flush',
+                       'timing': 'CUDA events on the launch stream, max over ranks',
+                       'parallelism': f'batch-sharded x{world}, one scalar all-reduce per step'},
+            'melem_per_s': world * numel / (ms_per_step * 1e-3) / 1e6,
+            'hbm_gbs_step': world * 2 * cd_bytes / (ms_per_step * 1e-3) / 1e9,
+            'kernel_ms': {'cgd_fwd': cgd_ms, 'cd_fwd': cd_ms,
+                          'backward_and_rest': ms_per_step - cgd_ms - cd_ms},
+            'roofline': {'bound': 'hbm', 'kernel': 'kl_rows_tma_kernel<float> (CDLoss launch)',
+                         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'peak_source': peak_src, 'frac_of_8TBs_nominal': achieved / 8000.0,
+                         'algorithmic_bytes_per_launch': cd_bytes, 'traffic': profiled_traffic(),
+                         'cgd_kernel': {'achieved': cd_bytes / (cgd_ms * 1e-3) / 1e9,
+                                        'frac': cd_bytes / (cgd_ms * 1e-3) / 1e9 / peak}},
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'cpu_baseline': cpu,
+            'loss_values': {'cgd': float(l1), 'cd': float(l2)},
+        }
+        if extra:
+            line['extra'] = extra
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extra_configs(dev):
+    """Other BASELINE configs (parity-test cases, timed for information only)."""
+    import torch
+    import segdistill_b200 as sd
+    out = {}
+
+    def timeit(fn, n=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    def fwd_bwd(crit, s, t):
+        def f():
+            s.grad = None
+            crit(s, t, None, 1).backward()
+        return f
+
+    def pair(shape, dtype):
+        s = torch.randn(shape, device=dev).to(dtype).requires_grad_(True)
+        t = torch.randn(shape, device=dev).to(dtype)
+        return s, t
+
+    peak, _ = measured_peak()
+    for name, crit, shape, dtype in (
+            ('cfg1_cd_2x150x64x64_f32', sd.CDLoss(), (2, 150, 64, 64), torch.float32),
+            ('cfg3_cd_16x150x128x128_bf16', sd.CDLoss(), (16, 150, 128, 128), torch.bfloat16),
+            ('cfg3_pd_16x150x128x128_bf16', sd.PDLoss(), (16, 150, 128, 128), torch.bfloat16),
+            ('cfg3_pd_16x150x128x128_f32', sd.PDLoss(), (16, 150, 128, 128), torch.float32),
+            ('cfg4_cd+mse_fused_16x512x64x64_f32', sd.CDMSELoss(alpha=1, tau=4), (16, 512, 64, 64), torch.float32),
+            ('cfg4_mse_16x512x64x64_f32', sd.FeatureMSELoss(), (16, 512, 64, 64), torch.float32)):
+        s, t = pair(shape, dtype)
+        ms = timeit(fwd_bwd(crit, s, t))
+        nbytes = 3 * s.numel() * s.element_size()
+        out[name] = {'ms': ms, 'mpixel_s': shape[0] * shape[2] * shape[3] / ms / 1e3,
+                     'gbs': nbytes / ms / 1e6, 'frac_of_measured_peak': nbytes / ms / 1e6 / peak}
+    stages = [(16, 32, 128, 128), (16, 64, 64, 64), (16, 160, 32, 32), (16, 256, 16, 16)]
+    pairs = [pair(sh, torch.float32) for sh in stages]
+    crit = sd.CGDLoss()
+
+    def cfg2():
+        for s, t in pairs:
+            s.grad = None
+            crit(s, t, None, 1).backward()
+    ms = timeit(cfg2)
+    nbytes = sum(3 * s.numel() * 4 for s, _ in pairs)
+    out['cfg2_cgd_4stages_b16_f32'] = {'ms': ms, 'gbs': nbytes / ms / 1e6, 'frac_of_measured_peak': nbytes / ms / 1e6 / peak}
+    return out
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.gpus > 1 and world == 1 and args.impl == 'ours':
+        # launched without torchrun: re-exec under it (one rank per GPU, NCCL)
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
+               '--master-addr', '127.0.0.1', '--master-port', str(29500 + os.getpid() % 1000),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if args.impl == 'reference':
+        run_reference_arm(args, rank)
+        return
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == '__main__':
+    main()

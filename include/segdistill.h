@@ -1,0 +1,157 @@
+/*
+ * segdistill.h - C ABI of libsegdistill_sm100.so (B200 / sm_100a only).
+ *
+ * Drop-in boundary for SegDistill's dense distillation-loss hot path.  The
+ * reference has NO native interface for this path (0 native source files,
+ * setup.py:125 ext_modules=[]): its loss modules call ATen directly.  Each entry
+ * point below therefore replaces a *chain of ATen calls* in the reference and
+ * cites it (paths relative to the reference root):
+ *
+ *   sd_kl_rows_fwd_bwd    mmseg/models/distillation/losses.py:35-42 (channel gather),
+ *                         :50-58 (group reshape / -1e9 pad), :108-112 (softmax-KL, alpha)
+ *                         - CDLoss :130-143, CGDLoss :145-158, CGDLossWS :160-173,
+ *                         plain KLDLoss (softmax over the last dim) :9-113
+ *   sd_kl_pixels_fwd_bwd  losses.py:47-49 (permute to NHWC rows) + :108-112 - PDLoss :115-128;
+ *                         with at_weight != 0 also ATLoss :175-197 (channel-mean MSE :190
+ *                         + per-pixel KL :192-195)
+ *   sd_mse_fwd_bwd        losses.py:178,190 / :202,235 (nn.MSELoss), :812-830 (feature MSE)
+ *   sd_scale_grad         the autograd multiply by grad_output that torch would run in
+ *                         backward (loss enters the total as a plain sum,
+ *                         mmseg/models/segmentors/SD_structure.py:121-122; 512 under fp16
+ *                         loss scaling)
+ *   sd_cgd_corr_fwd_bwd   NOT in the reference: builder-defined per-group
+ *                         Gram-matrix loss; tcgen05 tensor-core GEMM.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named *_host.
+ *   - the library never allocates, frees or synchronises: outputs and workspace are
+ *     caller-owned; all work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - feature maps are contiguous NCHW: element (b,c,p) at ((b*C + c)*HW + p).
+ *   - return value: 0 = ok, negative = SD_ERR_* argument error, positive = cudaError_t.
+ *     No C++ exception crosses the boundary.  sd_strerror() names any of them.
+ *   - `workspace` must be zero-filled once when it is allocated (the kernels keep their
+ *     counters self-resetting); one workspace must not be shared by concurrent streams.
+ *   - fp32 accumulation regardless of `dtype`; dS has the dtype of S.
+ *   - deterministic: no floating-point atomics; reductions run in a fixed order for a
+ *     given shape and device.
+ */
+#ifndef SEGDISTILL_H_
+#define SEGDISTILL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SD_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SD_API __attribute__((visibility("default")))
+#else
+#define SD_API
+#endif
+
+/* dtype */
+#define SD_F32  0
+#define SD_BF16 1
+
+/* algo: AUTO picks the TMA-staged register-resident kernel when the layout allows it
+ * (16-byte aligned rows) and the plain multi-pass kernel otherwise. */
+#define SD_ALGO_AUTO    0
+#define SD_ALGO_GENERIC 1
+#define SD_ALGO_TMA     2
+
+/* argument errors */
+#define SD_OK               0
+#define SD_ERR_NULL        -1   /* a required pointer is NULL */
+#define SD_ERR_SHAPE       -2   /* non-positive or overflowing shape */
+#define SD_ERR_DTYPE       -3
+#define SD_ERR_ALIGN       -4   /* a base pointer is not 16-byte aligned */
+#define SD_ERR_WORKSPACE   -5   /* workspace too small */
+#define SD_ERR_UNSUPPORTED -6   /* forced algo cannot run this layout */
+#define SD_ERR_DEVICE      -7   /* not an sm_100 device */
+#define SD_ERR_VALUE       -8   /* tau <= 0, group < 1, ... */
+
+SD_API int         sd_abi_version(void);
+SD_API const char* sd_strerror(int rc);
+/* SD_OK when the current device can run the kernels (compute capability 10.x). */
+SD_API int         sd_device_check(void);
+
+/* ------------------------------------------------------------------ rows (CD / CGD) */
+SD_API size_t sd_kl_rows_workspace_bytes(int B, int C, int HW, int group);
+
+/*
+ * Softmax-KL over rows made of `group` consecutive channels (after the optional
+ * channel gather `chan_perm`), forward and backward fused.
+ *   rows R = B*ceil(C/group); a ragged last group counts as a row whose missing
+ *   channels contribute nothing (the reference pads them with -1e9).
+ *   row_kl[r] = sum_i p_i (log p_i - log q_i),  p = softmax(T_row/tau), q = softmax(S_row/tau)
+ *   *loss     = alpha/R * sum_r row_kl[r]
+ *   dS        = grad_scale*alpha/(R*tau) * (q - p), written in the ORIGINAL channel order
+ *   mse_weight != 0 additionally adds the feature MSE on the same pair:
+ *   *mse_loss = mse_weight*mean((S-T)^2), dS += grad_scale*2*mse_weight*(S-T)/numel
+ * chan_perm: int32[C] or NULL; row_kl: float[R] or NULL; mse_loss: NULL iff mse_weight == 0.
+ */
+SD_API int sd_kl_rows_fwd_bwd(const void* S, const void* T, void* dS,
+                       float* row_kl, float* loss,
+                       const int32_t* chan_perm,
+                       int B, int C, int HW, int group, int dtype,
+                       float tau, float alpha, float grad_scale,
+                       float mse_weight, float* mse_loss,
+                       void* workspace, size_t workspace_bytes,
+                       int algo, void* stream);
+
+/* ------------------------------------------------------------------ pixels (PD / AT) */
+SD_API size_t sd_kl_pixels_workspace_bytes(int B, int C, int HW);
+
+/*
+ * Softmax-KL over the channel axis of every pixel (rows R = B*HW, length C, stride HW).
+ *   row_kl[b*HW + p], *loss = alpha/R * sum, dS = grad_scale*alpha/(R*tau)*(q - p).
+ *   at_weight != 0 adds ATLoss' attention term: with m = mean over channels,
+ *   *at_loss = at_weight*mean_{b,p}((m_S - m_T)^2),
+ *   dS += grad_scale*2*at_weight*(m_S - m_T)/(C*B*HW).
+ */
+SD_API int sd_kl_pixels_fwd_bwd(const void* S, const void* T, void* dS,
+                         float* row_kl, float* loss,
+                         int B, int C, int HW, int dtype,
+                         float tau, float alpha, float grad_scale,
+                         float at_weight, float* at_loss,
+                         void* workspace, size_t workspace_bytes,
+                         int algo, void* stream);
+
+/* ------------------------------------------------------------------ feature MSE */
+SD_API size_t sd_mse_workspace_bytes(int64_t numel);
+/* *loss = weight*mean((S-T)^2); dS = grad_scale*2*weight*(S-T)/numel. */
+SD_API int sd_mse_fwd_bwd(const void* S, const void* T, void* dS, float* loss,
+                   int64_t numel, int dtype, float weight, float grad_scale,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ backward helper */
+/* dS *= *grad_output (a device scalar); exits without touching dS when it equals 1. */
+SD_API int sd_scale_grad(void* dS, int64_t numel, int dtype, const float* grad_output, void* stream);
+
+/* ------------------------------------------------------------------ CGD correlation (extension) */
+SD_API size_t sd_cgd_corr_workspace_bytes(int B, int C, int HW, int group);
+/*
+ * Builder-defined (no reference counterpart): per (sample, channel group) Gram matrix
+ * G = X X^T / HW with X in R^{group x HW};  *loss = alpha*mean((G_S - G_T)^2) over
+ * B*ceil(C/group)*group^2 entries;  dS = grad_scale*4*alpha/(N*HW) * (G_S - G_T) X_S.
+ * tcgen05 (TMEM accumulators) fed by TMA; bf16 inputs use kind::f16, fp32 inputs kind::tf32.
+ */
+SD_API int sd_cgd_corr_fwd_bwd(const void* S, const void* T, void* dS, float* loss,
+                        int B, int C, int HW, int group, int dtype,
+                        float alpha, float grad_scale,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ introspection */
+/* Number of kernel launches the library has enqueued since load (bench.py's gpu_launches). */
+SD_API uint64_t sd_launch_count(void);
+/* Name of the kernel variant the last call on this thread dispatched to ("" if none). */
+SD_API const char* sd_last_kernel(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEGDISTILL_H_ */

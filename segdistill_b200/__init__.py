@@ -1,0 +1,11 @@
+"""segdistill_b200 - B200-native (sm_100a) kernels for SegDistill's dense distillation losses.
+
+Only the hot path lives here: the CUDA kernels + C ABI (``csrc/``, ``include/segdistill.h``),
+the ctypes binding (``_cabi``), the autograd bridges (``functional``) and the host-side mirror of
+the reference's loss-module / dispatcher interface (``losses``, ``opts``, ``dist``).
+"""
+from .losses import (ATLoss, CDLoss, CDMSELoss, CGDCorrLoss, CGDLoss, CGDLossWS, FeatureMSELoss,  # noqa: F401
+                     KLDLoss, PDLoss)
+from .opts import DistillationLoss, Extractor, LOSS_CLASSES, build_criterion  # noqa: F401
+
+__version__ = '0.1.0'

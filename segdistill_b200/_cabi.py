@@ -1,0 +1,254 @@
+"""ctypes binding of ``libsegdistill_sm100.so`` (C ABI in ``include/segdistill.h``).
+
+PyTorch is plumbing here: it owns device memory and streams; every argument that
+crosses the boundary is a raw pointer, a size or a scalar.  There is NO fallback:
+if the library is missing, or the device is not sm_100, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import Optional
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, 'libsegdistill_sm100.so')
+
+SD_F32, SD_BF16 = 0, 1
+ALGO_AUTO, ALGO_GENERIC, ALGO_TMA = 0, 1, 2
+ALGOS = {'auto': ALGO_AUTO, 'generic': ALGO_GENERIC, 'tma': ALGO_TMA}
+
+# every symbol include/segdistill.h declares (tests check the library exports all of them)
+EXPORTS = (
+    'sd_abi_version', 'sd_strerror', 'sd_device_check',
+    'sd_kl_rows_workspace_bytes', 'sd_kl_rows_fwd_bwd',
+    'sd_kl_pixels_workspace_bytes', 'sd_kl_pixels_fwd_bwd',
+    'sd_mse_workspace_bytes', 'sd_mse_fwd_bwd', 'sd_scale_grad',
+    'sd_cgd_corr_workspace_bytes', 'sd_cgd_corr_fwd_bwd',
+    'sd_launch_count', 'sd_last_kernel',
+)
+
+_lib = None
+_lock = threading.Lock()
+
+
+class SegDistillError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA extension; raises (never falls back) when it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise SegDistillError(
+                f'{LIB_PATH} is missing: build it with `python -m segdistill_b200.build` '
+                '(nvcc, sm_100a). segdistill_b200 has no CPU or PyTorch fallback.')
+        lib = ctypes.CDLL(LIB_PATH)
+        c = ctypes
+        vp, i32, f32, sz, i64 = c.c_void_p, c.c_int, c.c_float, c.c_size_t, c.c_int64
+        lib.sd_abi_version.restype = i32
+        lib.sd_strerror.restype = c.c_char_p
+        lib.sd_strerror.argtypes = [i32]
+        lib.sd_device_check.restype = i32
+        lib.sd_kl_rows_workspace_bytes.restype = sz
+        lib.sd_kl_rows_workspace_bytes.argtypes = [i32, i32, i32, i32]
+        lib.sd_kl_rows_fwd_bwd.restype = i32
+        lib.sd_kl_rows_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
+                                           f32, f32, f32, f32, vp, vp, sz, i32, vp]
+        lib.sd_kl_pixels_workspace_bytes.restype = sz
+        lib.sd_kl_pixels_workspace_bytes.argtypes = [i32, i32, i32]
+        lib.sd_kl_pixels_fwd_bwd.restype = i32
+        lib.sd_kl_pixels_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32,
+                                             f32, f32, f32, f32, vp, vp, sz, i32, vp]
+        lib.sd_mse_workspace_bytes.restype = sz
+        lib.sd_mse_workspace_bytes.argtypes = [i64]
+        lib.sd_mse_fwd_bwd.restype = i32
+        lib.sd_mse_fwd_bwd.argtypes = [vp, vp, vp, vp, i64, i32, f32, f32, vp, sz, vp]
+        lib.sd_scale_grad.restype = i32
+        lib.sd_scale_grad.argtypes = [vp, i64, i32, vp, vp]
+        lib.sd_cgd_corr_workspace_bytes.restype = sz
+        lib.sd_cgd_corr_workspace_bytes.argtypes = [i32, i32, i32, i32]
+        lib.sd_cgd_corr_fwd_bwd.restype = i32
+        lib.sd_cgd_corr_fwd_bwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp, sz, vp]
+        lib.sd_launch_count.restype = c.c_uint64
+        lib.sd_last_kernel.restype = c.c_char_p
+        if lib.sd_abi_version() != 1:
+            raise SegDistillError('libsegdistill_sm100.so: ABI version mismatch, rebuild it')
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise SegDistillError(f'{load().sd_strerror(rc).decode()} (rc={rc})')
+
+
+def launch_count() -> int:
+    return int(load().sd_launch_count())
+
+
+def last_kernel() -> str:
+    return load().sd_last_kernel().decode()
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return SD_F32
+    if t.dtype == torch.bfloat16:
+        return SD_BF16
+    raise SegDistillError(f'unsupported dtype {t.dtype}: float32 or bfloat16 (fp32 accumulation either way)')
+
+
+def _prep_pair(x_student: torch.Tensor, x_teacher: torch.Tensor):
+    if x_student.shape != x_teacher.shape:
+        raise SegDistillError(f'student {tuple(x_student.shape)} and teacher {tuple(x_teacher.shape)} '
+                              'maps must have the same shape')
+    if not x_student.is_cuda or x_teacher.device != x_student.device:
+        raise SegDistillError('segdistill_b200 runs on CUDA tensors only (no CPU fallback)')
+    if x_student.dtype == torch.float16:      # fp16 features (Fp16OptimizerHook): compute in fp32
+        x_student = x_student.float()
+    if x_teacher.dtype != x_student.dtype:
+        x_teacher = x_teacher.to(x_student.dtype)
+    s = x_student.detach().contiguous()
+    t = x_teacher.detach().contiguous()
+    return s, t, _dtype_code(s)
+
+
+# ---------------------------------------------------------------- workspaces
+_workspaces = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Zero-initialised scratch, one per (device, stream); grown on demand, never shared across streams."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def workspace_error_flag(device=None) -> int:
+    """Spin time-out flag of the split-row kernel (0 = never fired); synchronises. Tests only."""
+    device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        return 0
+    return int(ws[:8].view(torch.int32)[1].item())
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+# ---------------------------------------------------------------- entry points
+def kl_rows(x_student, x_teacher, group=1, tau=1.0, alpha=1.0, perm: Optional[torch.Tensor] = None,
+            grad_scale=1.0, mse_weight=0.0, algo=ALGO_AUTO, want_row_kl=False, bchw=None):
+    """Row-wise softmax-KL (rows = ``group`` channels x HW). Returns (loss, dS, row_kl|None, mse|None).
+
+    ``bchw``: optional (B, C, HW) override to treat the tensor as that 3-D view.
+    """
+    lib = load()
+    s, t, code = _prep_pair(x_student, x_teacher)
+    if bchw is None:
+        B, C = s.shape[0], s.shape[1]
+        HW = s[0, 0].numel()
+    else:
+        B, C, HW = bchw
+    dev = s.device
+    with torch.cuda.device(dev):
+        ds = torch.empty_like(s)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        G = (C + min(group, C) - 1) // min(group, C)
+        row_kl = torch.empty(B * G, dtype=torch.float32, device=dev) if want_row_kl else None
+        perm_dev = None
+        if perm is not None:
+            perm_dev = perm.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
+            if perm_dev.numel() != C:
+                raise SegDistillError('chan_perm must have C entries')
+        nbytes = lib.sd_kl_rows_workspace_bytes(B, C, HW, group)
+        ws = _workspace(dev, nbytes)
+        rc = lib.sd_kl_rows_fwd_bwd(
+            s.data_ptr(), t.data_ptr(), ds.data_ptr(),
+            row_kl.data_ptr() if row_kl is not None else None, out.data_ptr(),
+            perm_dev.data_ptr() if perm_dev is not None else None,
+            B, C, HW, group, code, float(tau), float(alpha), float(grad_scale),
+            float(mse_weight), out[1:].data_ptr() if mse_weight != 0 else None,
+            ws.data_ptr(), ws.numel(), int(algo), _stream_ptr(dev))
+        _check(rc)
+    return out[0], ds, row_kl, (out[1] if mse_weight != 0 else None)
+
+
+def kl_pixels(x_student, x_teacher, tau=1.0, alpha=1.0, grad_scale=1.0, at_weight=0.0,
+              algo=ALGO_AUTO, want_row_kl=False):
+    """Per-pixel softmax-KL over channels. Returns (loss, dS, row_kl|None, at_loss|None)."""
+    lib = load()
+    s, t, code = _prep_pair(x_student, x_teacher)
+    B, C = s.shape[0], s.shape[1]
+    HW = s[0, 0].numel()
+    dev = s.device
+    with torch.cuda.device(dev):
+        ds = torch.empty_like(s)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        row_kl = torch.empty(B * HW, dtype=torch.float32, device=dev) if want_row_kl else None
+        nbytes = lib.sd_kl_pixels_workspace_bytes(B, C, HW)
+        ws = _workspace(dev, nbytes)
+        rc = lib.sd_kl_pixels_fwd_bwd(
+            s.data_ptr(), t.data_ptr(), ds.data_ptr(),
+            row_kl.data_ptr() if row_kl is not None else None, out.data_ptr(),
+            B, C, HW, code, float(tau), float(alpha), float(grad_scale),
+            float(at_weight), out[1:].data_ptr() if at_weight != 0 else None,
+            ws.data_ptr(), ws.numel(), int(algo), _stream_ptr(dev))
+        _check(rc)
+    return out[0], ds, row_kl, (out[1] if at_weight != 0 else None)
+
+
+def mse(x_student, x_teacher, weight=1.0, grad_scale=1.0):
+    """``weight * mean((s - t)^2)``. Returns (loss, dS)."""
+    lib = load()
+    s, t, code = _prep_pair(x_student, x_teacher)
+    dev = s.device
+    with torch.cuda.device(dev):
+        ds = torch.empty_like(s)
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        ws = _workspace(dev, lib.sd_mse_workspace_bytes(s.numel()))
+        rc = lib.sd_mse_fwd_bwd(s.data_ptr(), t.data_ptr(), ds.data_ptr(), out.data_ptr(), s.numel(), code,
+                                float(weight), float(grad_scale), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        _check(rc)
+    return out[0], ds
+
+
+def cgd_corr(x_student, x_teacher, group=10, alpha=1.0, grad_scale=1.0):
+    """Per-group Gram-matrix loss (tcgen05). Returns (loss, dS)."""
+    lib = load()
+    s, t, code = _prep_pair(x_student, x_teacher)
+    B, C = s.shape[0], s.shape[1]
+    HW = s[0, 0].numel()
+    dev = s.device
+    with torch.cuda.device(dev):
+        ds = torch.empty_like(s)
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        ws = _workspace(dev, lib.sd_cgd_corr_workspace_bytes(B, C, HW, group))
+        rc = lib.sd_cgd_corr_fwd_bwd(s.data_ptr(), t.data_ptr(), ds.data_ptr(), out.data_ptr(), B, C, HW, group,
+                                     code, float(alpha), float(grad_scale), ws.data_ptr(), ws.numel(),
+                                     _stream_ptr(dev))
+        _check(rc)
+    return out[0], ds
+
+
+def scale_grad_(ds: torch.Tensor, grad_output: torch.Tensor):
+    """In place ``ds *= grad_output`` on the device; a no-op launch when grad_output == 1."""
+    lib = load()
+    g = grad_output.detach().to(device=ds.device, dtype=torch.float32).reshape(1)
+    with torch.cuda.device(ds.device):
+        rc = lib.sd_scale_grad(ds.data_ptr(), ds.numel(), _dtype_code(ds), g.data_ptr(), _stream_ptr(ds.device))
+        _check(rc)
+    return ds

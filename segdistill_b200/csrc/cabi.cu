@@ -1,0 +1,347 @@
+// extern "C" entry points of libsegdistill_sm100.so (see include/segdistill.h).
+// Argument validation, work decomposition, workspace carving, kernel selection.  No allocation,
+// no synchronisation, no exceptions.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstring>
+
+#include "../../include/segdistill.h"
+#include "launch.h"
+#include "params.h"
+
+namespace {
+
+std::atomic<uint64_t> g_launches{0};
+thread_local const char* t_last_kernel = "";
+
+struct DeviceInfo {
+    int sms = 0;
+    int cc_major = 0;
+    bool ok = false;
+};
+// one process drives one GPU (torchrun, one rank per device); keep a small per-device cache anyway
+DeviceInfo& device_info() {
+    static DeviceInfo info[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    DeviceInfo& d = info[dev];
+    if (!d.ok) {
+        cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+        d.ok = d.sms > 0;
+    }
+    return d;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int elem_size(int dtype) { return dtype == SD_BF16 ? 2 : 4; }
+
+PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
+    }
+    return fn;
+}
+
+// (B, C, HW) view of an NCHW map; box = (tile pixels, C, 1); out-of-range pixels read as zero
+bool encode_pixel_map(CUtensorMap* m, const void* base, int B, int C, int HW, int dtype, int tile_px) {
+    auto enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t es = (cuuint64_t)elem_size(dtype);
+    cuuint64_t gdim[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
+    cuuint64_t gstr[2] = {(cuuint64_t)HW * es, (cuuint64_t)HW * es * (cuuint64_t)C};
+    cuuint32_t box[3] = {(cuuint32_t)tile_px, (cuuint32_t)C, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = enc(m, dtype == SD_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                           const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sd_abi_version(void) { return SD_ABI_VERSION; }
+
+const char* sd_strerror(int rc) {
+    switch (rc) {
+        case SD_OK: return "ok";
+        case SD_ERR_NULL: return "segdistill: a required pointer is NULL";
+        case SD_ERR_SHAPE: return "segdistill: invalid shape (non-positive or too large)";
+        case SD_ERR_DTYPE: return "segdistill: unsupported dtype (SD_F32 or SD_BF16)";
+        case SD_ERR_ALIGN: return "segdistill: base pointers must be 16-byte aligned";
+        case SD_ERR_WORKSPACE: return "segdistill: workspace too small";
+        case SD_ERR_UNSUPPORTED: return "segdistill: the requested algorithm cannot run this layout";
+        case SD_ERR_DEVICE: return "segdistill: kernels are built for sm_100a (B200) only";
+        case SD_ERR_VALUE: return "segdistill: invalid scalar argument (tau must be > 0, group >= 1)";
+        default: break;
+    }
+    if (rc > 0) return cudaGetErrorString(static_cast<cudaError_t>(rc));
+    return "segdistill: unknown error";
+}
+
+int sd_device_check(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return SD_ERR_DEVICE;
+    }
+    return device_info().cc_major == 10 ? SD_OK : SD_ERR_DEVICE;
+}
+
+uint64_t sd_launch_count(void) { return g_launches.load(); }
+const char* sd_last_kernel(void) { return t_last_kernel; }
+
+// ============================================================================ rows
+size_t sd_kl_rows_workspace_bytes(int B, int C, int HW, int group) {
+    if (B <= 0 || C <= 0 || HW <= 0 || group <= 0) return 0;
+    return sd::rows_workspace_layout(B, C, HW, group).bytes;
+}
+
+int sd_kl_rows_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl, float* loss, const int32_t* chan_perm,
+                       int B, int C, int HW, int group, int dtype, float tau, float alpha, float grad_scale,
+                       float mse_weight, float* mse_loss, void* workspace, size_t workspace_bytes, int algo,
+                       void* stream) {
+    if (!S || !T || !dS || !loss || !workspace) return SD_ERR_NULL;
+    if (mse_weight != 0.f && !mse_loss) return SD_ERR_NULL;
+    if (dtype != SD_F32 && dtype != SD_BF16) return SD_ERR_DTYPE;
+    if (B <= 0 || C <= 0 || HW <= 0) return SD_ERR_SHAPE;
+    if (group < 1 || !(tau > 0.f)) return SD_ERR_VALUE;
+    if (group > C) group = C;  // one ragged row per sample either way
+    const long long numel = (long long)B * C * HW;
+    const long long row_len = (long long)group * HW;
+    if (row_len >= (1ll << 31) || numel >= (1ll << 40)) return SD_ERR_SHAPE;
+    const sd::RowsWorkspace wl = sd::rows_workspace_layout(B, C, HW, group);
+    if (workspace_bytes < wl.bytes) return SD_ERR_WORKSPACE;
+    DeviceInfo& dev = device_info();
+    if (dev.cc_major != 10) return SD_ERR_DEVICE;
+
+    const int es = elem_size(dtype);
+    const int VE = 16 / es;
+    sd::RowsParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.S = S;
+    p.T = T;
+    p.dS = dS;
+    char* ws = static_cast<char*>(workspace);
+    p.row_kl = row_kl ? row_kl : reinterpret_cast<float*>(ws + wl.off_rowkl);
+    p.loss = loss;
+    p.mse_loss = mse_weight != 0.f ? mse_loss : nullptr;
+    p.perm = chan_perm;
+    p.B = B;
+    p.C = C;
+    p.HW = HW;
+    p.g = group;
+    p.G = (C + group - 1) / group;
+    p.G_full = C / group;
+    p.g_last = C % group;
+    p.R = B * p.G;
+    p.c2 = (float)(1.4426950408889634 / (double)tau);
+    p.inv_tau = (float)(1.0 / (double)tau);
+    p.coef = (float)((double)grad_scale * (double)alpha / ((double)p.R * (double)tau));
+    p.loss_scale = (float)((double)alpha / (double)p.R);
+    p.mse_gcoef = (float)((double)grad_scale * 2.0 * (double)mse_weight / (double)numel);
+    p.mse_scale = (float)((double)mse_weight / (double)numel);
+    p.KC = (HW + sd::kGenericChunk - 1) / sd::kGenericChunk;
+    p.ctrl = reinterpret_cast<unsigned*>(ws + wl.off_ctrl);
+    p.cta_part = reinterpret_cast<float*>(ws + wl.off_cta);
+    p.row_cnt = reinterpret_cast<unsigned*>(ws + wl.off_rowcnt);
+    p.unit_part = reinterpret_cast<float*>(ws + wl.off_unit);
+
+    // TMA path: rows must start on 16-byte boundaries
+    const int cap = sd::kl_rows_tma_chunk_capacity();
+    p.nch_full = p.G_full > 0 ? (int)((row_len + cap - 1) / cap) : 1;
+    long long ce = p.G_full > 0 ? (row_len + p.nch_full - 1) / p.nch_full : (long long)p.g_last * HW;
+    ce = (ce + VE - 1) / VE * VE;
+    if (ce > cap) ce = cap;
+    p.chunk_elems = (int)ce;
+    p.nch_last = p.g_last ? (int)(((long long)p.g_last * HW + ce - 1) / ce) : 0;
+    p.units_per_sample = p.G_full * p.nch_full + p.nch_last;
+    p.total_units = (long long)B * p.units_per_sample;
+    const int max_nch = p.nch_full > p.nch_last ? p.nch_full : p.nch_last;
+    int grid = (int)(p.total_units < dev.sms ? p.total_units : dev.sms);
+    if (grid > sd::kMaxGrid) grid = sd::kMaxGrid;
+    const bool layout_ok = ((long long)HW * es) % 16 == 0 && aligned16(S) && aligned16(T) && aligned16(dS);
+    const bool tma_ok = layout_ok && max_nch <= grid;
+    const long long gen_units = (long long)B * C * p.KC;
+    if (gen_units >= (1ll << 31)) return SD_ERR_SHAPE;
+
+    bool use_tma;
+    if (algo == SD_ALGO_TMA) {
+        if (!tma_ok) return SD_ERR_UNSUPPORTED;
+        use_tma = true;
+    } else if (algo == SD_ALGO_GENERIC) {
+        use_tma = false;
+    } else if (algo == SD_ALGO_AUTO) {
+        use_tma = tma_ok;
+    } else {
+        return SD_ERR_VALUE;
+    }
+
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    if (use_tma) {
+        e = sd::launch_kl_rows_tma(p, dtype == SD_BF16, grid, /*cooperative=*/max_nch > 1, st);
+        g_launches += 1;
+        t_last_kernel = max_nch > 1 ? "kl_rows_tma_kernel(split-row)" : "kl_rows_tma_kernel";
+    } else {
+        e = sd::launch_kl_rows_generic(p, dtype == SD_BF16, st);
+        g_launches += 3;
+        t_last_kernel = "kl_rows_generic";
+    }
+    return e == cudaSuccess ? SD_OK : (int)e;
+}
+
+// ============================================================================ pixels
+size_t sd_kl_pixels_workspace_bytes(int B, int C, int HW) {
+    if (B <= 0 || C <= 0 || HW <= 0) return 0;
+    return sd::pix_workspace_layout(B, C, HW).bytes;
+}
+
+int sd_kl_pixels_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl, float* loss, int B, int C, int HW,
+                         int dtype, float tau, float alpha, float grad_scale, float at_weight, float* at_loss,
+                         void* workspace, size_t workspace_bytes, int algo, void* stream) {
+    if (!S || !T || !dS || !loss || !workspace) return SD_ERR_NULL;
+    if (at_weight != 0.f && !at_loss) return SD_ERR_NULL;
+    if (dtype != SD_F32 && dtype != SD_BF16) return SD_ERR_DTYPE;
+    if (B <= 0 || C <= 0 || HW <= 0) return SD_ERR_SHAPE;
+    if (!(tau > 0.f)) return SD_ERR_VALUE;
+    const long long R = (long long)B * HW;
+    if (R >= (1ll << 31) || (long long)B * C * HW >= (1ll << 40)) return SD_ERR_SHAPE;
+    const sd::PixWorkspace wl = sd::pix_workspace_layout(B, C, HW);
+    if (workspace_bytes < wl.bytes) return SD_ERR_WORKSPACE;
+    DeviceInfo& dev = device_info();
+    if (dev.cc_major != 10) return SD_ERR_DEVICE;
+
+    const int es = elem_size(dtype);
+    const bool bf16 = dtype == SD_BF16;
+    sd::PixParams p;
+    std::memset(&p, 0, sizeof(p));
+    char* ws = static_cast<char*>(workspace);
+    p.S = S;
+    p.T = T;
+    p.dS = dS;
+    p.row_kl = row_kl ? row_kl : reinterpret_cast<float*>(ws + wl.off_rowkl);
+    p.loss = loss;
+    p.at_loss = at_weight != 0.f ? at_loss : nullptr;
+    p.B = B;
+    p.C = C;
+    p.HW = HW;
+    p.c2 = (float)(1.4426950408889634 / (double)tau);
+    p.inv_tau = (float)(1.0 / (double)tau);
+    p.coef = (float)((double)grad_scale * (double)alpha / ((double)R * (double)tau));
+    p.loss_scale = (float)((double)alpha / (double)R);
+    p.at_gcoef = (float)((double)grad_scale * 2.0 * (double)at_weight / ((double)C * (double)R));
+    p.at_scale = (float)((double)at_weight / (double)R);
+    p.inv_C = (float)(1.0 / (double)C);
+    p.ctrl = reinterpret_cast<unsigned*>(ws + wl.off_ctrl);
+    p.cta_part = reinterpret_cast<float*>(ws + wl.off_cta);
+    p.nparts = (int)wl.nparts;
+
+    const int tile_px = sd::kl_pixels_tile_pixels(bf16);
+    p.tiles_per_sample = (HW + tile_px - 1) / tile_px;
+    p.total_tiles = (long long)B * p.tiles_per_sample;
+    p.stage_bytes = (unsigned)C * 256u;
+    // ring depth: as many stages as fit next to the reduction scratch (at most 4)
+    int nstages = 0;
+    for (int n = 4; n >= 1; --n) {
+        if (sd::pix_tma_smem_bytes(C, bf16 ? 2 : 1, n) <= 227u * 1024u) {
+            nstages = n;
+            break;
+        }
+    }
+    p.nstages = nstages;
+    const bool layout_ok = ((long long)HW * es) % 16 == 0 && aligned16(S) && aligned16(T) && aligned16(dS);
+    const bool tma_ok = layout_ok && nstages >= 1 && C <= sd::kl_pixels_tma_max_channels(bf16) && C <= 256 &&
+                        tensor_map_encoder() != nullptr;
+
+    bool use_tma;
+    if (algo == SD_ALGO_TMA) {
+        if (!tma_ok) return SD_ERR_UNSUPPORTED;
+        use_tma = true;
+    } else if (algo == SD_ALGO_GENERIC) {
+        use_tma = false;
+    } else if (algo == SD_ALGO_AUTO) {
+        use_tma = tma_ok;
+    } else {
+        return SD_ERR_VALUE;
+    }
+
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    if (use_tma) {
+        alignas(64) CUtensorMap mS, mT;
+        if (!encode_pixel_map(&mS, S, B, C, HW, dtype, tile_px) || !encode_pixel_map(&mT, T, B, C, HW, dtype, tile_px))
+            return (int)cudaErrorInvalidValue;
+        int grid = (int)(p.total_tiles < dev.sms ? p.total_tiles : dev.sms);
+        e = sd::launch_kl_pixels_tma(&mS, &mT, p, bf16, grid, sd::pix_tma_smem_bytes(C, bf16 ? 2 : 1, nstages), st);
+        g_launches += 1;
+        t_last_kernel = "kl_pixels_tma_kernel";
+    } else {
+        e = sd::launch_kl_pixels_generic(p, bf16, st);
+        g_launches += 2;
+        t_last_kernel = "kl_pixels_generic";
+    }
+    return e == cudaSuccess ? SD_OK : (int)e;
+}
+
+// ============================================================================ MSE
+size_t sd_mse_workspace_bytes(int64_t numel) {
+    (void)numel;
+    return sizeof(float) * sd::kMseMaxGrid;
+}
+
+int sd_mse_fwd_bwd(const void* S, const void* T, void* dS, float* loss, int64_t numel, int dtype, float weight,
+                   float grad_scale, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!S || !T || !dS || !loss || !workspace) return SD_ERR_NULL;
+    if (dtype != SD_F32 && dtype != SD_BF16) return SD_ERR_DTYPE;
+    if (numel <= 0 || numel >= (1ll << 40)) return SD_ERR_SHAPE;
+    if (workspace_bytes < sd_mse_workspace_bytes(numel)) return SD_ERR_WORKSPACE;
+    DeviceInfo& dev = device_info();
+    if (dev.cc_major != 10) return SD_ERR_DEVICE;
+    const int VE = 16 / elem_size(dtype);
+    long long want = (numel / VE + 255) / 256;
+    if (want < 1) want = 1;
+    int grid = dev.sms * 8;
+    if (grid > sd::kMseMaxGrid) grid = sd::kMseMaxGrid;
+    if (want < grid) grid = (int)want;
+    const float gcoef = (float)((double)grad_scale * 2.0 * (double)weight / (double)numel);
+    const float scale = (float)((double)weight / (double)numel);
+    cudaError_t e = sd::launch_mse(S, T, dS, loss, static_cast<float*>(workspace), numel, dtype == SD_BF16, gcoef,
+                                   scale, grid, static_cast<cudaStream_t>(stream));
+    g_launches += 2;
+    t_last_kernel = "mse_kernel";
+    return e == cudaSuccess ? SD_OK : (int)e;
+}
+
+int sd_scale_grad(void* dS, int64_t numel, int dtype, const float* grad_output, void* stream) {
+    if (!dS || !grad_output) return SD_ERR_NULL;
+    if (dtype != SD_F32 && dtype != SD_BF16) return SD_ERR_DTYPE;
+    if (numel <= 0) return SD_ERR_SHAPE;
+    DeviceInfo& dev = device_info();
+    if (dev.cc_major != 10) return SD_ERR_DEVICE;
+    const int VE = 16 / elem_size(dtype);
+    long long want = (numel / VE + 255) / 256;
+    if (want < 1) want = 1;
+    int grid = dev.sms * 8;
+    if (want < grid) grid = (int)want;
+    cudaError_t e = sd::launch_scale_grad(dS, numel, dtype == SD_BF16, grad_output, grid,
+                                          static_cast<cudaStream_t>(stream));
+    g_launches += 1;
+    t_last_kernel = "scale_grad_kernel";
+    return e == cudaSuccess ? SD_OK : (int)e;
+}
+
+}  // extern "C"

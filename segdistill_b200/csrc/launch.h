@@ -1,0 +1,28 @@
+// Host-side launchers implemented next to their kernels; called from cabi.cu only.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "params.h"
+
+namespace sd {
+
+// kl_rows.cu
+cudaError_t launch_kl_rows_tma(const RowsParams& p, bool bf16, int grid, bool cooperative, cudaStream_t stream);
+cudaError_t launch_kl_rows_generic(const RowsParams& p, bool bf16, cudaStream_t stream);
+int kl_rows_tma_chunk_capacity();
+
+// kl_pixels.cu   (mapS/mapT point at CUtensorMap objects)
+cudaError_t launch_kl_pixels_tma(const void* mapS, const void* mapT, const PixParams& p, bool bf16, int grid,
+                                 size_t smem, cudaStream_t stream);
+cudaError_t launch_kl_pixels_generic(const PixParams& p, bool bf16, cudaStream_t stream);
+size_t pix_tma_smem_bytes(int C, int pxt, int nstages);
+int kl_pixels_tma_max_channels(bool bf16);
+int kl_pixels_tile_pixels(bool bf16);
+
+// mse.cu
+cudaError_t launch_mse(const void* S, const void* T, void* dS, float* loss, float* partials, long long n, bool bf16,
+                       float gcoef, float scale, int grid, cudaStream_t stream);
+cudaError_t launch_scale_grad(void* dS, long long n, bool bf16, const float* g, int grid, cudaStream_t stream);
+
+}  // namespace sd

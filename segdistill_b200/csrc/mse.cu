@@ -1,0 +1,136 @@
+// Feature MSE, forward + backward fused, and the backward grad_output scaling helper.
+//
+// sd_mse_fwd_bwd replaces nn.MSELoss / weight*mean((s-t)**2) (mmseg/models/distillation/
+// losses.py:178,190,:202,235,:829) and its backward: one streaming pass, 12 B/elem fp32.
+#include "common.cuh"
+#include "params.h"
+
+namespace sd {
+
+constexpr int kMseThreads = 256;
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kMseThreads) mse_kernel(const T* __restrict__ S, const T* __restrict__ Tt,
+                                                          T* __restrict__ dS, float* __restrict__ partials,
+                                                          long long n, float gcoef) {
+    using E = Elem<T>;
+    using vec_t = typename E::vec_t;
+    constexpr int VE = E::kVec;
+    __shared__ float sh[kMseThreads / 32];
+    float sq = 0.f;
+    const long long stride = (long long)gridDim.x * kMseThreads;
+    const long long gid = (long long)blockIdx.x * kMseThreads + threadIdx.x;
+    long long done = 0;
+    if (VEC) {
+        const long long nvec = n / VE;
+        const vec_t* vs = reinterpret_cast<const vec_t*>(S);
+        const vec_t* vt = reinterpret_cast<const vec_t*>(Tt);
+        vec_t* vo = reinterpret_cast<vec_t*>(dS);
+        for (long long i = gid; i < nvec; i += stride) {
+            float a[VE], b[VE], o[VE];
+            E::unpack(__ldcs(vs + i), a);
+            E::unpack(__ldcs(vt + i), b);
+#pragma unroll
+            for (int k = 0; k < VE; ++k) {
+                const float d = a[k] - b[k];
+                sq = fmaf(d, d, sq);
+                o[k] = gcoef * d;
+            }
+            vo[i] = E::pack(o);
+        }
+        done = nvec * VE;
+    }
+    for (long long i = done + gid; i < n; i += stride) {
+        const float d = E::load(S + i) - E::load(Tt + i);
+        sq = fmaf(d, d, sq);
+        E::store(dS + i, gcoef * d);
+    }
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < kMseThreads / 32; ++w) a += sh[w];
+        partials[blockIdx.x] = a;
+    }
+}
+
+__global__ void __launch_bounds__(1024) mse_finalize(const float* __restrict__ partials, int nparts, float scale,
+                                                     float* __restrict__ loss) {
+    __shared__ double sh[32];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += 1024) a += (double)partials[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 32; ++w) t += sh[w];
+        *loss = (float)((double)scale * t);
+    }
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) scale_grad_kernel(T* __restrict__ x, long long n, const float* __restrict__ g) {
+    using E = Elem<T>;
+    using vec_t = typename E::vec_t;
+    constexpr int VE = E::kVec;
+    const float gv = *g;
+    if (gv == 1.0f) return;  // the usual case: loss enters the total as a plain sum
+    const long long stride = (long long)gridDim.x * 256;
+    const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+    long long done = 0;
+    if (VEC) {
+        const long long nvec = n / VE;
+        vec_t* vx = reinterpret_cast<vec_t*>(x);
+        for (long long i = gid; i < nvec; i += stride) {
+            float a[VE];
+            E::unpack(vx[i], a);
+#pragma unroll
+            for (int k = 0; k < VE; ++k) a[k] *= gv;
+            vx[i] = E::pack(a);
+        }
+        done = nvec * VE;
+    }
+    for (long long i = done + gid; i < n; i += stride) E::store(x + i, E::load(x + i) * gv);
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+cudaError_t launch_mse(const void* S, const void* T, void* dS, float* loss, float* partials, long long n, bool bf16,
+                       float gcoef, float scale, int grid, cudaStream_t stream) {
+    const bool vec = aligned16(S) && aligned16(T) && aligned16(dS);
+    if (bf16) {
+        auto s = static_cast<const __nv_bfloat16*>(S);
+        auto t = static_cast<const __nv_bfloat16*>(T);
+        auto o = static_cast<__nv_bfloat16*>(dS);
+        if (vec) mse_kernel<__nv_bfloat16, true><<<grid, kMseThreads, 0, stream>>>(s, t, o, partials, n, gcoef);
+        else mse_kernel<__nv_bfloat16, false><<<grid, kMseThreads, 0, stream>>>(s, t, o, partials, n, gcoef);
+    } else {
+        auto s = static_cast<const float*>(S);
+        auto t = static_cast<const float*>(T);
+        auto o = static_cast<float*>(dS);
+        if (vec) mse_kernel<float, true><<<grid, kMseThreads, 0, stream>>>(s, t, o, partials, n, gcoef);
+        else mse_kernel<float, false><<<grid, kMseThreads, 0, stream>>>(s, t, o, partials, n, gcoef);
+    }
+    mse_finalize<<<1, 1024, 0, stream>>>(partials, grid, scale, loss);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scale_grad(void* dS, long long n, bool bf16, const float* g, int grid, cudaStream_t stream) {
+    const bool vec = aligned16(dS);
+    if (bf16) {
+        auto x = static_cast<__nv_bfloat16*>(dS);
+        if (vec) scale_grad_kernel<__nv_bfloat16, true><<<grid, 256, 0, stream>>>(x, n, g);
+        else scale_grad_kernel<__nv_bfloat16, false><<<grid, 256, 0, stream>>>(x, n, g);
+    } else {
+        auto x = static_cast<float*>(dS);
+        if (vec) scale_grad_kernel<float, true><<<grid, 256, 0, stream>>>(x, n, g);
+        else scale_grad_kernel<float, false><<<grid, 256, 0, stream>>>(x, n, g);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace sd

@@ -1,0 +1,193 @@
+"""Drop-in loss modules: same names, constructor arguments and 4-argument call as the
+reference's ``mmseg/models/distillation/losses.py`` (``KLDLoss`` :9-113, ``PDLoss`` :115,
+``CDLoss`` :130, ``CGDLoss`` :145, ``CGDLossWS`` :160, ``ATLoss`` :175), computing through the
+sm_100a kernels.  ``criterion(x_student, x_teacher, gt_semantic_seg, step)`` -> 0-dim loss
+whose backward delivers the gradient to ``x_student`` only (reference call site:
+``mmseg/models/distillation/opts.py:103``).  The 2-argument form is accepted too
+(``gt=None`` => no resize, ``step=0``).
+
+Host-side behaviour kept from the reference: the alpha warm-up / early-decay state machine
+(:61-92), the channel shuffle drawn from ``torch.randperm`` on the CPU global generator
+(:39) every ``interval`` steps, the bilinear resize to the label size (:25-33).  What changed:
+the shuffle and the ragged-group pad cost no copies (the kernel gathers / skips), the resize is
+skipped when sizes already match (it is an exact identity there), and when ``alpha == 0`` no
+kernel runs at all.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as SF
+
+__all__ = ['KLDLoss', 'PDLoss', 'CDLoss', 'CGDLoss', 'CGDLossWS', 'ATLoss',
+           'FeatureMSELoss', 'CDMSELoss', 'CGDCorrLoss']
+
+
+def _ramp(kind, alpha0, frac):
+    if kind == 'linear':
+        return alpha0 * frac
+    if kind == 'exp':
+        return alpha0 ** frac
+    if kind == 'jump':
+        return 0
+    return None
+
+
+class KLDLoss(nn.Module):
+    algo = 'auto'          # 'auto' | 'tma' | 'generic' (tests force one)
+
+    def __init__(self, alpha=1, tau=1, resize_config=None, shuffle_config=None, transform_config=None,
+                 warmup_config=None, earlydecay_config=None):
+        super().__init__()
+        self.alpha_0 = alpha
+        self.alpha = alpha
+        self.tau = tau
+        self.resize_config = resize_config
+        self.shuffle_config = shuffle_config
+        self.transform_config = transform_config
+        self.warmup_config = warmup_config
+        self.earlydecay_config = earlydecay_config
+        self.last_perm = None
+
+    # -- host-side schedules (reference :61-92); a branch that does not fire keeps the old alpha
+    def _update_alpha(self, n_iter):
+        wc, dc = self.warmup_config, self.earlydecay_config
+        if wc:
+            span = wc['warmup_iters']
+            if n_iter == span:
+                self.alpha = self.alpha_0
+            elif n_iter < span:
+                v = _ramp(wc['mode'], self.alpha_0, n_iter / span)
+                if v is not None:
+                    self.alpha = v
+        if dc:
+            begin, stop = dc['earlydecay_start'], dc['earlydecay_end']
+            if n_iter >= stop:
+                self.alpha = 0
+            elif begin < n_iter < stop:
+                frac = (stop - n_iter) / (stop - begin)
+                v = _ramp(dc['mode'], self.alpha_0, frac)
+                if v is not None:
+                    self.alpha = 0.001 * v if dc['mode'] == 'exp' else v
+
+    def _resized(self, x, gt):
+        if gt is None or tuple(gt.shape[2:]) == tuple(x.shape[2:]):
+            return x                   # bilinear resize to the same size is an exact identity
+        return F.interpolate(x, size=tuple(gt.shape[2:]), mode=self.resize_config['mode'],
+                             align_corners=self.resize_config['align_corners'])
+
+    def forward(self, x_student, x_teacher, gt=None, n_iter=0):
+        self._update_alpha(n_iter)
+        if self.resize_config:
+            x_student, x_teacher = self._resized(x_student, gt), self._resized(x_teacher, gt)
+        perm = None
+        if self.shuffle_config and n_iter % self.shuffle_config['interval'] == 0:
+            perm = torch.randperm(x_student.shape[1])      # same draw as the reference (:39)
+        self.last_perm = perm
+        if self.alpha == 0:
+            return SF.zero_loss(x_student).to(x_student.dtype)
+
+        tc = self.transform_config
+        kind = tc['loss_type'] if tc else None
+        if kind == 'pixel':
+            # softmax over all channels of a pixel: a channel permutation changes nothing
+            loss = SF.kl_pixels_loss(x_student, x_teacher, tau=self.tau, alpha=self.alpha, algo=self.algo)
+        elif kind == 'channel':
+            loss = SF.kl_rows_loss(x_student, x_teacher, group=tc['group_size'], tau=self.tau,
+                                   alpha=self.alpha, perm=perm, algo=self.algo)
+        else:
+            # no transform: softmax over the last dim of the 4-D maps; rows = (b, c, h)
+            lead = x_student.numel() // x_student.shape[-1]
+            loss = SF.kl_rows_loss(x_student, x_teacher, group=1, tau=self.tau, alpha=self.alpha,
+                                   algo=self.algo, bchw=(1, lead, x_student.shape[-1]))
+        return loss.to(x_student.dtype)
+
+
+def _bilinear():
+    return {'mode': 'bilinear', 'align_corners': False}
+
+
+class PDLoss(KLDLoss):
+    """Per-pixel logit KL (reference :115-128)."""
+
+    def __init__(self):
+        super().__init__(alpha=1, tau=1, resize_config=_bilinear(), transform_config={'loss_type': 'pixel'})
+
+
+class CDLoss(KLDLoss):
+    """Channel-wise spatial-softmax KL, a.k.a. CWD (reference :130-143)."""
+
+    def __init__(self):
+        super().__init__(alpha=1, tau=1, resize_config=_bilinear(),
+                         transform_config={'loss_type': 'channel', 'group_size': 1})
+
+
+class CGDLoss(KLDLoss):
+    """Channel Group Distillation: the same KL over groups of ``group_size`` channels (reference :145-158)."""
+
+    def __init__(self, group_size=10, alpha=3, tau=2):
+        super().__init__(alpha=alpha, tau=tau, resize_config=_bilinear(), shuffle_config={'interval': 1000},
+                         transform_config={'loss_type': 'channel', 'group_size': group_size})
+
+
+class CGDLossWS(KLDLoss):
+    """CGD with warm-up and early decay of the weight (reference :160-173)."""
+
+    def __init__(self):
+        super().__init__(alpha=3, tau=2, resize_config=_bilinear(), shuffle_config={'interval': 1000},
+                         transform_config={'loss_type': 'channel', 'group_size': 10},
+                         warmup_config={'mode': 'linear', 'warmup_iters': 2000},
+                         earlydecay_config={'mode': 'linear', 'earlydecay_start': 110000,
+                                            'earlydecay_end': 120000})
+
+
+class ATLoss(nn.Module):
+    """MSE of the channel-mean maps + per-pixel KL, one fused kernel (reference :175-197)."""
+    algo = 'auto'
+
+    def __init__(self):
+        super().__init__()
+
+    def forward(self, x_student, x_teacher, gt=None, step=0):
+        loss = SF.kl_pixels_loss(x_student, x_teacher, tau=1.0, alpha=1.0, at_weight=1.0, algo=self.algo)
+        return loss.to(x_student.dtype)
+
+
+class FeatureMSELoss(nn.Module):
+    """``weight * mean((s - t)^2)`` - the feature-MSE term (reference :178,190 / commented class :812-830)."""
+
+    def __init__(self, weight=1.0):
+        super().__init__()
+        self.weight = weight
+
+    def forward(self, x_student, x_teacher, gt=None, step=0):
+        return SF.mse_loss(x_student, x_teacher, self.weight).to(x_student.dtype)
+
+
+class CDMSELoss(nn.Module):
+    """CWD (tau, alpha) + feature MSE on the same pair in ONE pass over the maps (BASELINE config 4)."""
+    algo = 'auto'
+
+    def __init__(self, alpha=1, tau=1, mse_weight=1.0, group_size=1):
+        super().__init__()
+        self.alpha, self.tau, self.mse_weight, self.group_size = alpha, tau, mse_weight, group_size
+        self.last_parts = None
+
+    def forward(self, x_student, x_teacher, gt=None, step=0):
+        total, kl, mse = SF.kl_rows_mse_loss(x_student, x_teacher, group=self.group_size, tau=self.tau,
+                                             alpha=self.alpha, mse_weight=self.mse_weight, algo=self.algo)
+        self.last_parts = (kl, mse)
+        return total.to(x_student.dtype)
+
+
+class CGDCorrLoss(nn.Module):
+    """Per-group Gram-matrix (correlation) loss - an extension, NOT in the reference."""
+
+    def __init__(self, group_size=10, alpha=1.0):
+        super().__init__()
+        self.group_size, self.alpha = group_size, alpha
+
+    def forward(self, x_student, x_teacher, gt=None, step=0):
+        return SF.cgd_corr_loss(x_student, x_teacher, self.group_size, self.alpha).to(x_student.dtype)

@@ -1,0 +1,77 @@
+"""Dispatcher mirror of the reference's ``mmseg/models/distillation/opts.py``.
+
+``Extractor`` (:13-71) records hooked layer outputs; ``DistillationLoss`` (:74-112) builds one
+criterion per ``distillation`` entry from ``loss_name`` + ``loss_config`` and names each result
+``loss_{student_layer}<->{teacher_layer}_{loss_info}`` (:105-110).  The reference resolves
+``loss_name`` with ``eval`` in a namespace star-imported from its losses module; here the same
+bare names resolve through ``LOSS_CLASSES`` (register extra classes there).
+"""
+from __future__ import annotations
+
+from functools import partial
+
+import torch.nn as nn
+
+from . import losses as _losses
+
+LOSS_CLASSES = {name: getattr(_losses, name) for name in _losses.__all__}
+
+
+def build_criterion(loss_name, loss_config):
+    if isinstance(loss_config, tuple):          # reference unwraps tuple-wrapped configs (:81-82)
+        loss_config = loss_config[0]
+    try:
+        cls = LOSS_CLASSES[loss_name]
+    except KeyError:
+        raise NameError(f"name '{loss_name}' is not defined (known losses: {sorted(LOSS_CLASSES)})")
+    return cls(**loss_config)
+
+
+class Extractor(nn.Module):
+    """Forward hooks on the named student / teacher layers; outputs are kept only in training mode."""
+
+    def __init__(self, student, teacher, distillation):
+        super().__init__()
+        self.teacher_features = {}
+        self.student_features = {}
+        want_s, want_t = [], []
+        for entry in distillation:
+            for names, bucket in ((entry['student_layer'], want_s), (entry['teacher_layer'], want_t)):
+                bucket.extend(names if isinstance(names, list) else [names])
+        for role, model, wanted in (('teacher', teacher, want_t), ('student', student, want_s)):
+            for name, module in model.named_modules():
+                if name in wanted:
+                    module.register_forward_hook(partial(self._record, name=name, role=role))
+
+    def _record(self, module, inputs, output, name, role):
+        if self.training:
+            (self.student_features if role == 'student' else self.teacher_features)[name] = output
+
+
+class DistillationLoss(nn.Module):
+    def __init__(self, distillation):
+        super().__init__()
+        self.distillation = distillation
+        crits = []
+        for entry in distillation:
+            entry['criterion'] = build_criterion(entry['loss_name'], entry['loss_config'])
+            crits.append(entry['criterion'])
+        self.criteria = nn.ModuleList(crits)
+
+    def forward(self, student_features, teacher_features, gt_semantic_seg, step, student=None, teacher=None):
+        out = {}
+        for entry in self.distillation:
+            s_name, t_name = entry['student_layer'], entry['teacher_layer']
+            crit = entry['criterion']
+            if isinstance(s_name, list):
+                # attention/value pair form of the reference (:92-99); no shipped loss uses it
+                loss = crit(student_features[s_name[0]], student_features[s_name[1]],
+                            teacher_features[t_name[0]], teacher_features[t_name[1]],
+                            student, teacher, gt_semantic_seg, step)
+                out[f"loss_{s_name[0]}<->{t_name}_{entry['loss_name']}"] = loss
+                continue
+            loss = crit(student_features[s_name], teacher_features[t_name], gt_semantic_seg, step)
+            cfg = entry['loss_config'][0] if isinstance(entry['loss_config'], tuple) else entry['loss_config']
+            info = cfg.get('transform_config', 'other') if isinstance(cfg, dict) else 'other'
+            out[f'loss_{s_name}<->{t_name}_{info}'] = loss
+        return out

@@ -1,0 +1,411 @@
+"""Parity of the CUDA path against the oracle (B200 only; `pytest -m gpu`).
+
+Tolerances (BASELINE.json north_star): fp32 loss rel. err <= 1e-5, gradients <= 1e-4 of
+max|grad| (we hold 2e-5); bf16 inputs are compared with the oracle run on the fp32 upcast of
+the same bf16 values: loss rel <= 2e-5 (fp32 accumulation), gradient <= 1 bf16 ulp (2^-8 rel)
+of max|grad| (output rounding only).
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import segdistill_b200 as sd
+from segdistill_b200 import _cabi
+from segdistill_b200 import functional as SF
+from helpers import golden_cases, load_golden, rel_err, seeded_pair
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_RTOL = 2e-5        # of max|grad|; north_star allows 1e-4
+BF16_GRAD_RTOL = 2.0 ** -8
+
+
+def dev():
+    return torch.device('cuda', 0)
+
+
+def _module_from_fixture(rec):
+    cls, kw = rec['cls'], dict(rec['kwargs'])
+    return getattr(sd, cls)(**kw)
+
+
+def _run(crit, s_cpu, t_cpu, gt_hw=None, n_iter=1, algo='auto', seed=None):
+    crit.algo = algo
+    s = s_cpu.to(dev()).requires_grad_(True)
+    t = t_cpu.to(dev())
+    gt = None if gt_hw is None else torch.zeros(s.shape[0], 1, *gt_hw, dtype=torch.long, device=dev())
+    if seed is not None:
+        torch.manual_seed(seed)
+    loss = crit(s, t, gt, n_iter)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert _cabi.workspace_error_flag() == 0
+    return loss.detach().float().cpu().item(), s.grad.detach().float().cpu()
+
+
+def _assert_close(loss, grad, ref_loss, ref_grad, loss_rtol=LOSS_RTOL, grad_rtol=GRAD_RTOL):
+    assert rel_err(loss, ref_loss) <= loss_rtol, (loss, ref_loss)
+    ref_grad = torch.as_tensor(ref_grad, dtype=torch.float32)
+    scale = ref_grad.abs().max().item()
+    err = (grad - ref_grad).abs().max().item()
+    assert err <= grad_rtol * scale, (err, scale)
+
+
+# ------------------------------------------------------------------ golden vectors of the reference
+@pytest.mark.parametrize('algo', ['auto', 'generic'])
+@pytest.mark.parametrize('name', golden_cases('kld_'))
+def test_golden_vectors(name, algo):
+    rec = load_golden(name)
+    crit = _module_from_fixture(rec)
+    loss, grad = _run(crit, torch.from_numpy(rec['S']), torch.from_numpy(rec['T']),
+                      [int(v) for v in rec['gt_hw']], int(rec['n_iter']), algo, seed=int(rec['manual_seed']))
+    if 'near' in name:
+        # S ~ T: KL ~ 5e-5; the fp32 reference itself is only ~6e-4 accurate here
+        f64_loss, f64_grad, _ = oracle.kld_closed_form_f64(rec['S'], rec['T'], 'channel', 1, 1.0, 1.0)
+        assert rel_err(loss, f64_loss) <= 5e-3
+        assert (grad.double().numpy() - f64_grad).__abs__().max() <= 1e-4 * np.abs(f64_grad).max() + 1e-9
+        return
+    _assert_close(loss, grad, float(rec['loss']), rec['grad'])
+    assert float(crit.alpha) == pytest.approx(float(rec['alpha_after']), rel=1e-12)
+
+
+def test_golden_atloss():
+    z = load_golden('atloss_2x6x5x8')
+    for algo in ('auto', 'generic'):
+        loss, grad = _run(sd.ATLoss(), torch.from_numpy(z['S']), torch.from_numpy(z['T']), algo=algo)
+        _assert_close(loss, grad, float(z['loss']), z['grad'])
+
+
+def test_cfg1_smoke_values():
+    z = load_golden('smoke_cfg1')
+    torch.manual_seed(0)
+    s = torch.randn(2, 150, 64, 64)
+    t = torch.randn(2, 150, 64, 64)
+    for cls in ('CDLoss', 'PDLoss', 'CGDLoss', 'ATLoss'):
+        loss, grad = _run(getattr(sd, cls)(), s, t, (64, 64), 1)
+        assert rel_err(loss, z[cls + '_loss']) <= LOSS_RTOL
+        np.testing.assert_allclose(grad[1, 77, 13, 5:13].numpy(), z[cls + '_grad_probe'], rtol=2e-4, atol=1e-12)
+        assert rel_err(grad.double().abs().sum().item(), z[cls + '_grad_abs_sum']) <= 1e-5
+
+
+# ------------------------------------------------------------------ seeded inputs vs the oracle
+def _oracle_run(preset, kw, s, t, gt_hw, n_iter, perm=None):
+    x = s.clone().float().requires_grad_(True)
+    gt = torch.zeros(s.shape[0], 1, *gt_hw, dtype=torch.long)
+    crit = oracle.make_preset(preset, **kw) if preset != 'KLDLoss' else oracle.OracleKLD(**kw)
+    loss = crit(x, t.float(), gt, n_iter, perm=perm)
+    loss.backward()
+    return loss.item(), x.grad
+
+
+CFG1 = (2, 150, 64, 64)
+
+
+@pytest.mark.parametrize('algo', ['tma', 'generic'])
+@pytest.mark.parametrize('g', [1, 3, 10, 30, 50, 150])
+def test_cfg1_group_size_sweep(g, algo):
+    """local_configs/Group_Size/cgd{1,3,10,30,50,150}.py on the cfg1 logits; g >= 10 splits rows over CTAs."""
+    s, t = seeded_pair(CFG1, seed=g)
+    kw = dict(group_size=g, alpha=3, tau=2)
+    ref = _oracle_run('CGDLoss', kw, s, t, CFG1[2:], 1)
+    got = _run(sd.CGDLoss(**kw), s, t, CFG1[2:], 1, algo)
+    _assert_close(*got, *ref)
+
+
+@pytest.mark.parametrize('alpha,tau', [(1, 1), (1, 4), (2, 3), (3, 1), (3, 4)])
+def test_weight_temperature_sweep(alpha, tau):
+    """local_configs/Weight_Temperature/w=*_t=*.py"""
+    s, t = seeded_pair((2, 150, 32, 32), seed=alpha * 10 + tau, scale=3.0)
+    kw = dict(alpha=alpha, tau=tau)
+    ref = _oracle_run('CGDLoss', kw, s, t, (32, 32), 1)
+    got = _run(sd.CGDLoss(**kw), s, t, (32, 32), 1)
+    _assert_close(*got, *ref)
+
+
+@pytest.mark.parametrize('algo', ['tma', 'generic'])
+@pytest.mark.parametrize('shape', [(4, 32, 128, 128), (4, 64, 64, 64), (4, 160, 32, 32), (4, 256, 16, 16)])
+def test_cfg2_stage_features_cgd_with_ragged_groups(shape, algo):
+    """MiT-B0 stage widths 32/64/160/256 at strides 4/8/16/32 (B cut to 4 for the CPU oracle); 32,64,256 % 10 != 0."""
+    s, t = seeded_pair(shape, seed=shape[1])
+    ref = _oracle_run('CGDLoss', {}, s, t, shape[2:], 1)
+    got = _run(sd.CGDLoss(), s, t, shape[2:], 1, algo)
+    _assert_close(*got, *ref)
+
+
+@pytest.mark.parametrize('algo', ['tma', 'generic'])
+@pytest.mark.parametrize('cls', ['CDLoss', 'PDLoss'])
+def test_cfg3_quarter_batch_bf16(cls, algo):
+    s, t = seeded_pair((4, 150, 128, 128), seed=3, dtype=torch.bfloat16)
+    ref = _oracle_run(cls, {}, s, t, (128, 128), 1)        # oracle on the fp32 upcast of the same bf16 values
+    got = _run(getattr(sd, cls)(), s, t, (128, 128), 1, algo)
+    _assert_close(*got, *ref, loss_rtol=2e-5, grad_rtol=BF16_GRAD_RTOL)
+
+
+@pytest.mark.parametrize('algo', ['tma', 'generic'])
+@pytest.mark.parametrize('cls', ['CDLoss', 'PDLoss'])
+def test_cfg3_quarter_batch_fp32(cls, algo):
+    s, t = seeded_pair((4, 150, 128, 128), seed=4)
+    ref = _oracle_run(cls, {}, s, t, (128, 128), 1)
+    got = _run(getattr(sd, cls)(), s, t, (128, 128), 1, algo)
+    _assert_close(*got, *ref)
+
+
+@pytest.mark.parametrize('tau,alpha', [(1, 1), (4, 3)])
+def test_cfg4_feature_mse_plus_cwd(tau, alpha):
+    """PSPNet 512-channel 1/8-res maps: separate MSE and CWD kernels, and the fused single pass."""
+    shape = (2, 512, 64, 64)
+    s, t = seeded_pair(shape, seed=11)
+    x = s.clone().requires_grad_(True)
+    ref_kl = oracle.OracleKLD(alpha=alpha, tau=tau, transform_config={'loss_type': 'channel', 'group_size': 1})(
+        x, t, None, 1)
+    ref_mse = oracle.mse_loss_torch(x, t, 0.7)
+    (ref_kl + ref_mse).backward()
+    ref_total, ref_grad = (ref_kl + ref_mse).item(), x.grad
+    # fused
+    crit = sd.CDMSELoss(alpha=alpha, tau=tau, mse_weight=0.7)
+    for algo in ('tma', 'generic'):
+        loss, grad = _run(crit, s, t, algo=algo)
+        _assert_close(loss, grad, ref_total, ref_grad)
+        assert rel_err(crit.last_parts[0].item(), ref_kl.item()) <= LOSS_RTOL
+        assert rel_err(crit.last_parts[1].item(), ref_mse.item()) <= LOSS_RTOL
+    # separate modules, gradients accumulate through autograd
+    sg = s.to(dev()).requires_grad_(True)
+    tg = t.to(dev())
+    total = sd.KLDLoss(alpha=alpha, tau=tau, transform_config={'loss_type': 'channel', 'group_size': 1})(sg, tg) \
+        + sd.FeatureMSELoss(0.7)(sg, tg)
+    total.backward()
+    _assert_close(total.item(), sg.grad.cpu(), ref_total, ref_grad)
+
+
+@pytest.mark.parametrize('algo', ['tma', 'generic'])
+def test_channel_shuffle_matches_reference_gather(algo):
+    s, t = seeded_pair((2, 150, 64, 64), seed=21)
+    torch.manual_seed(99)
+    perm = torch.randperm(150)
+    ref = _oracle_run('CGDLoss', {}, s, t, (64, 64), 3000, perm=perm)
+    crit = sd.CGDLoss()
+    got = _run(crit, s, t, (64, 64), 3000, algo, seed=99)
+    assert torch.equal(crit.last_perm, perm)
+    _assert_close(*got, *ref)
+
+
+@pytest.mark.parametrize('shape,g', [((2, 7, 5, 7), 3), ((1, 3, 9, 9), 1), ((3, 10, 33, 31), 4), ((1, 1, 1, 1), 1),
+                                     ((2, 5, 2, 2), 10), ((1, 21, 17, 4), 21)])
+def test_unaligned_and_tiny_shapes_fall_back_to_the_generic_kernel(shape, g):
+    s, t = seeded_pair(shape, seed=5)
+    kw = dict(group_size=g, alpha=1.5, tau=0.5)
+    ref = _oracle_run('CGDLoss', kw, s, t, shape[2:], 1)
+    got = _run(sd.CGDLoss(**kw), s, t, shape[2:], 1)
+    _assert_close(*got, *ref)
+    refp = _oracle_run('PDLoss', {}, s, t, shape[2:], 1)
+    gotp = _run(sd.PDLoss(), s, t, shape[2:], 1)
+    _assert_close(*gotp, *refp)
+
+
+@pytest.mark.parametrize('C', [2, 19, 24, 25, 64, 150, 171, 256, 300])
+def test_pixel_kernel_channel_counts(C):
+    """Register tiling of the pixel kernel switches at C = 24 / 64 / 152 / 256; C > 256 is generic."""
+    s, t = seeded_pair((2, C, 24, 24), seed=C, scale=2.0)
+    ref = _oracle_run('PDLoss', {}, s, t, (24, 24), 1)
+    got = _run(sd.PDLoss(), s, t, (24, 24), 1)
+    _assert_close(*got, *ref)
+    sb, tb = s.bfloat16(), t.bfloat16()
+    refb = _oracle_run('PDLoss', {}, sb, tb, (24, 24), 1)
+    gotb = _run(sd.PDLoss(), sb, tb, (24, 24), 1)
+    _assert_close(*gotb, *refb, loss_rtol=2e-5, grad_rtol=BF16_GRAD_RTOL)
+
+
+def test_resize_to_label_size_is_honoured():
+    s, t = seeded_pair((2, 12, 16, 16), seed=8)
+    for cls in ('CDLoss', 'PDLoss', 'CGDLoss'):
+        ref = _oracle_run(cls, {}, s, t, (64, 64), 1)
+        got = _run(getattr(sd, cls)(), s, t, (64, 64), 1)
+        _assert_close(*got, *ref)
+
+
+def test_plain_kldloss_softmax_over_last_dim():
+    s, t = seeded_pair((2, 5, 12, 64), seed=9)
+    ref = _oracle_run('KLDLoss', dict(alpha=2, tau=3), s, t, (12, 64), 1)
+    got = _run(sd.KLDLoss(alpha=2, tau=3), s, t, (12, 64), 1)
+    _assert_close(*got, *ref)
+
+
+# ------------------------------------------------------------------ per-row parity against the f64 closed form
+@pytest.mark.parametrize('algo', ['tma', 'generic'])
+def test_per_row_kl_against_closed_form(algo):
+    s, t = seeded_pair((2, 60, 64, 64), seed=31, scale=2.0)
+    for g, mode in ((1, 'channel'), (10, 'channel'), (0, 'pixel')):
+        f64_loss, f64_grad, f64_rows = oracle.kld_closed_form_f64(s.numpy(), t.numpy(), mode, max(g, 1), 2.0, 3.0)
+        if mode == 'channel':
+            loss, ds, rows, _ = _cabi.kl_rows(s.to(dev()), t.to(dev()), group=g, tau=2.0, alpha=3.0,
+                                              algo=_cabi.ALGOS[algo], want_row_kl=True)
+        else:
+            loss, ds, rows, _ = _cabi.kl_pixels(s.to(dev()), t.to(dev()), tau=2.0, alpha=3.0,
+                                                algo=_cabi.ALGOS[algo], want_row_kl=True)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(rows.cpu().numpy(), f64_rows, rtol=2e-5, atol=1e-7)
+        assert rel_err(loss.item(), f64_loss) <= 2e-6
+        assert np.abs(ds.cpu().numpy() - f64_grad).max() <= 2e-6 * np.abs(f64_grad).max()
+
+
+# ------------------------------------------------------------------ autograd contract
+def test_grad_output_scaling_and_nonleaf_student():
+    s, t = seeded_pair((2, 20, 32, 32), seed=41)
+    base = s.to(dev()).requires_grad_(True)
+    tg = t.to(dev()).requires_grad_(True)
+    stu = base * 1.0 + 0.0                      # non-leaf, like a conv output
+    loss = sd.CDLoss()(stu, tg, None, 1)
+    (loss * 512.0).backward()                   # Fp16OptimizerHook(loss_scale=512.)
+    ref_loss, ref_grad = _oracle_run('CDLoss', {}, s, t, (32, 32), 1)
+    _assert_close(loss.item(), base.grad.cpu() / 512.0, ref_loss, ref_grad)
+    assert tg.grad is None                      # the teacher never receives a gradient
+
+
+def test_gradient_buffer_is_adopted_without_copy_and_fp16_inputs_work():
+    s, t = seeded_pair((1, 8, 16, 16), seed=42)
+    x = s.to(dev()).requires_grad_(True)
+    sd.CDLoss()(x, t.to(dev())).backward()
+    assert x.grad.is_contiguous() and x.grad.shape == x.shape
+    xh = s.half().to(dev()).requires_grad_(True)
+    loss = sd.CDLoss()(xh, t.half().to(dev()))
+    loss.backward()
+    assert xh.grad.dtype == torch.float16 and loss.dtype == torch.float16
+    ref = _oracle_run('CDLoss', {}, s.half().float(), t.half().float(), (16, 16), 1)
+    assert rel_err(loss.float().item(), ref[0]) <= 2e-3
+
+
+def test_dispatcher_end_to_end():
+    cfg = [{'student_layer': 'head', 'teacher_layer': 'head', 'loss_name': 'CGDLoss',
+            'loss_config': {'alpha': 2, 'tau': 3}},
+           {'student_layer': 'head', 'teacher_layer': 'head', 'loss_name': 'PDLoss', 'loss_config': {}}]
+    d = sd.DistillationLoss(cfg)
+    s, t = seeded_pair((2, 150, 32, 32), seed=43)
+    x = s.to(dev()).requires_grad_(True)
+    gt = torch.zeros(2, 1, 32, 32, dtype=torch.long, device=dev())
+    out = d({'head': x}, {'head': t.to(dev())}, gt, 1, None, None)
+    from segdistill_b200 import dist as sdist
+    total, logs = sdist.parse_losses(out)
+    total.backward()
+    r1 = _oracle_run('CGDLoss', dict(alpha=2, tau=3), s, t, (32, 32), 1)
+    r2 = _oracle_run('PDLoss', {}, s, t, (32, 32), 1)
+    _assert_close(total.item(), x.grad.cpu(), r1[0] + r2[0], r1[1] + r2[1])
+    assert logs['loss'] == pytest.approx(r1[0] + r2[0], rel=1e-5)
+
+
+def test_c_abi_error_codes_on_device():
+    lib = _cabi.load()
+    assert lib.sd_device_check() == 0
+    s = torch.randn(1, 4, 8, 8, device=dev())
+    out = torch.zeros(2, device=dev())
+    ws = torch.zeros(64, dtype=torch.uint8, device=dev())
+    rc = lib.sd_kl_rows_fwd_bwd(s.data_ptr(), s.data_ptr(), s.data_ptr(), None, out.data_ptr(), None, 1, 4, 64, 1, 0,
+                                1.0, 1.0, 1.0, 0.0, None, ws.data_ptr(), ws.numel(), 0, None)
+    assert rc == -5
+    big = torch.zeros(1 << 20, dtype=torch.uint8, device=dev())
+    odd = torch.randn(1, 4, 7, 5, device=dev())
+    rc = lib.sd_kl_rows_fwd_bwd(odd.data_ptr(), odd.data_ptr(), odd.data_ptr(), None, out.data_ptr(), None, 1, 4, 35,
+                                1, 0, 1.0, 1.0, 1.0, 0.0, None, big.data_ptr(), big.numel(), _cabi.ALGO_TMA, None)
+    assert rc == -6                              # forced TMA on an unaligned layout
+    with pytest.raises(_cabi.SegDistillError):
+        sd.CDLoss()(torch.randn(1, 2, 4, 4, device=dev()), torch.randn(1, 3, 4, 4, device=dev()))
+    with pytest.raises(_cabi.SegDistillError):
+        sd.CDLoss()(torch.randn(1, 2, 4, 4), torch.randn(1, 2, 4, 4))     # CPU tensors: no fallback
+
+
+# ------------------------------------------------------------------ full BASELINE sizes: size-independent properties
+FULL = (16, 150, 128, 128)
+
+
+@pytest.fixture(scope='module')
+def full_pair():
+    g = torch.Generator(device='cuda').manual_seed(0)
+    s = torch.randn(FULL, device=dev(), generator=g)
+    t = torch.randn(FULL, device=dev(), generator=g)
+    return s, t
+
+
+@pytest.mark.parametrize('kind', ['cd', 'cgd10', 'pd'])
+def test_full_size_properties(full_pair, kind):
+    s, t = full_pair
+
+    def run(a, b, alpha=1.0, tau=2.0, algo='auto'):
+        if kind == 'pd':
+            loss, ds, rows, _ = _cabi.kl_pixels(a, b, tau=tau, alpha=alpha, algo=_cabi.ALGOS[algo], want_row_kl=True)
+        else:
+            loss, ds, rows, _ = _cabi.kl_rows(a, b, group=1 if kind == 'cd' else 10, tau=tau, alpha=alpha,
+                                              algo=_cabi.ALGOS[algo], want_row_kl=True)
+        return loss, ds, rows
+
+    l1, d1, r1 = run(s, t)
+    l1b, d1b, r1b = run(s, t)
+    torch.cuda.synchronize()
+    assert _cabi.workspace_error_flag() == 0
+    # determinism: bit-identical reruns
+    assert torch.equal(l1, l1b) and torch.equal(d1, d1b) and torch.equal(r1, r1b)
+    # KL >= 0 per row, loss = alpha/R * sum rows
+    assert r1.min().item() >= -1e-6
+    assert rel_err(l1.item(), r1.double().mean().item()) <= 1e-6
+    # every softmax row of (q - p) sums to zero: checksum of the gradient, relative to coef = alpha/(R*tau)
+    if kind == 'pd':
+        chk = d1.double().sum(dim=1)
+    else:
+        g = 1 if kind == 'cd' else 10
+        chk = d1.double().reshape(FULL[0], FULL[1] // g, -1).sum(-1)
+    coef = 1.0 / (r1.numel() * 2.0)
+    assert chk.abs().max().item() <= 5e-6 * coef
+    # linearity in alpha
+    l3, d3, _ = run(s, t, alpha=3.0)
+    assert rel_err(l3.item(), 3.0 * l1.item()) <= 1e-6
+    assert (d3 - 3.0 * d1).abs().max().item() <= 1e-6 * d3.abs().max().item()
+    # identical maps: zero loss, zero gradient
+    l0, d0, _ = run(s, s.clone())
+    assert abs(l0.item()) <= 1e-6 and d0.abs().max().item() <= 1e-6 * d1.abs().max().item()
+    # batch shards: mean of the two halves' losses == full loss; gradients are the halves' / 2
+    la, da, _ = run(s[:8], t[:8])
+    lb, db, _ = run(s[8:], t[8:])
+    assert rel_err(0.5 * (la.item() + lb.item()), l1.item()) <= 1e-6
+    assert (torch.cat([da, db]) * 0.5 - d1).abs().max().item() <= 1e-6 * d1.abs().max().item()
+    # the two kernels agree
+    lg, dg, rg = run(s, t, algo='generic')
+    assert rel_err(lg.item(), l1.item()) <= 2e-6
+    assert (dg - d1).abs().max().item() <= 2e-6 * d1.abs().max().item()
+    # a sample of rows against the f64 closed form
+    sub_s, sub_t = s[3:4, 40:50].cpu().numpy(), t[3:4, 40:50].cpu().numpy()
+    if kind == 'pd':
+        return
+    g = 1 if kind == 'cd' else 10
+    _, _, rows64 = oracle.kld_closed_form_f64(sub_s, sub_t, 'channel', g, 2.0, 1.0)
+    G = FULL[1] // g
+    got = r1.reshape(FULL[0], G)[3, 40 // g:50 // g].cpu().numpy()
+    np.testing.assert_allclose(got, rows64, rtol=2e-5)
+
+
+def test_full_size_bf16_roundtrip_properties():
+    g = torch.Generator(device='cuda').manual_seed(1)
+    s = torch.randn(FULL, device=dev(), generator=g).bfloat16()
+    t = torch.randn(FULL, device=dev(), generator=g).bfloat16()
+    for fn in (lambda a, b: _cabi.kl_rows(a, b, group=1), lambda a, b: _cabi.kl_pixels(a, b)):
+        l16, d16, _, _ = fn(s, t)
+        l32, d32, _, _ = fn(s.float(), t.float())
+        torch.cuda.synchronize()
+        assert d16.dtype == torch.bfloat16
+        assert rel_err(l16.item(), l32.item()) <= 2e-6          # same values, same fp32 arithmetic
+        assert (d16.float() - d32).abs().max().item() <= BF16_GRAD_RTOL * d32.abs().max().item()
+
+
+def test_mse_full_size_and_scale_grad():
+    g = torch.Generator(device='cuda').manual_seed(2)
+    s = torch.randn(16, 512, 64, 64, device=dev(), generator=g)
+    t = torch.randn(16, 512, 64, 64, device=dev(), generator=g)
+    loss, ds = _cabi.mse(s, t, weight=0.5)
+    ref = 0.5 * ((s.double() - t.double()) ** 2).mean()
+    assert rel_err(loss.item(), ref.item()) <= 1e-6
+    ref_g = (s - t) * (2 * 0.5 / s.numel())
+    assert (ds - ref_g).abs().max().item() <= 1e-6 * ref_g.abs().max().item()
+    keep = ds.clone()
+    _cabi.scale_grad_(ds, torch.ones((), device=dev()))
+    assert torch.equal(ds, keep)
+    _cabi.scale_grad_(ds, torch.full((), 512.0, device=dev()))
+    assert torch.equal(ds, keep * 512.0)

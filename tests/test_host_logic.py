@@ -1,0 +1,145 @@
+"""Host-side mirror of the reference interface (CPU): schedules, RNG use, dispatcher naming."""
+import numpy as np
+import pytest
+import torch
+
+import segdistill_b200 as sd
+from segdistill_b200 import dist as sdist
+from helpers import load_golden
+
+
+def test_constructor_signatures_match_reference():
+    import inspect
+    sig = inspect.signature(sd.KLDLoss.__init__)
+    assert list(sig.parameters)[1:] == ['alpha', 'tau', 'resize_config', 'shuffle_config', 'transform_config',
+                                        'warmup_config', 'earlydecay_config']
+    assert [p.default for p in list(sig.parameters.values())[1:]] == [1, 1, None, None, None, None, None]
+    sig = inspect.signature(sd.CGDLoss.__init__)
+    assert [(k, v.default) for k, v in list(sig.parameters.items())[1:]] == [('group_size', 10), ('alpha', 3),
+                                                                              ('tau', 2)]
+    for cls in (sd.PDLoss, sd.CDLoss, sd.CGDLossWS, sd.ATLoss):
+        assert len(inspect.signature(cls.__init__).parameters) == 1
+    m = sd.CGDLossWS()
+    assert (m.alpha_0, m.tau) == (3, 2)
+    assert m.shuffle_config == {'interval': 1000}
+    assert m.transform_config == {'loss_type': 'channel', 'group_size': 10}
+    assert m.warmup_config == {'mode': 'linear', 'warmup_iters': 2000}
+    assert m.earlydecay_config == {'mode': 'linear', 'earlydecay_start': 110000, 'earlydecay_end': 120000}
+    assert sd.PDLoss().transform_config == {'loss_type': 'pixel'}
+    assert sd.CDLoss().resize_config == {'mode': 'bilinear', 'align_corners': False}
+
+
+def test_alpha_state_machine_matches_reference_fixture():
+    z = load_golden('schedules')
+    m = sd.CGDLossWS()
+    got = []
+    for n in z['ws_steps']:
+        m._update_alpha(int(n))
+        got.append(float(m.alpha))
+    np.testing.assert_allclose(got, z['ws_alpha'], rtol=1e-12, atol=0)
+    for mode in ('linear', 'exp', 'jump'):
+        m = sd.KLDLoss(alpha=2.0, tau=1, warmup_config={'mode': mode, 'warmup_iters': 10},
+                       earlydecay_config={'mode': mode, 'earlydecay_start': 20, 'earlydecay_end': 30})
+        got = []
+        for n in z[f'{mode}_steps']:
+            m._update_alpha(int(n))
+            got.append(float(m.alpha))
+        np.testing.assert_allclose(got, z[f'{mode}_alpha'], rtol=1e-12, atol=0)
+
+
+def test_zero_alpha_short_circuit_runs_without_a_kernel():
+    m = sd.CGDLossWS()                       # warm-up: alpha(0) = 0
+    s = torch.randn(1, 20, 4, 4, requires_grad=True)
+    loss = m(s, torch.randn(1, 20, 4, 4), torch.zeros(1, 1, 4, 4, dtype=torch.long), 0)
+    assert loss.item() == 0.0 and loss.requires_grad
+    loss.backward()
+    assert s.grad is None or float(s.grad.abs().sum()) == 0.0
+    m2 = sd.CGDLossWS()
+    loss = m2(s, s.detach(), None, 125000)   # after early decay
+    assert loss.item() == 0.0
+
+
+def test_shuffle_draws_the_same_permutation_as_the_reference():
+    rec = load_golden('kld_cgd_shuffle_n1000')
+    m = sd.CGDLossWS()                       # alpha == 0 at n_iter 0 -> no kernel, but the draw happens
+    m.warmup_config = None
+    m.alpha = m.alpha_0 = 0
+    torch.manual_seed(int(rec['manual_seed']))
+    s = torch.from_numpy(rec['S'])
+    m(s, torch.from_numpy(rec['T']), None, 1000)
+    assert m.last_perm is not None
+    np.testing.assert_array_equal(m.last_perm.numpy(), rec['perm'])
+    m(s, torch.from_numpy(rec['T']), None, 1001)
+    assert m.last_perm is None               # only when n_iter % interval == 0
+
+
+def test_dispatcher_builds_and_names_like_the_reference():
+    cfg = [
+        {'student_layer': 'decode_head.linear_pred', 'teacher_layer': 'decode_head.linear_pred',
+         'loss_name': 'CGDLossWS', 'loss_config': {}},
+        {'student_layer': 'a', 'teacher_layer': 'b', 'loss_name': 'KLDLoss',
+         'loss_config': ({'alpha': 0, 'tau': 2, 'transform_config': {'loss_type': 'channel', 'group_size': 2}},)},
+    ]
+    d = sd.DistillationLoss(cfg)
+    assert isinstance(cfg[0]['criterion'], sd.CGDLossWS)
+    x = torch.randn(1, 4, 2, 2)
+    feats = {'decode_head.linear_pred': x, 'a': x}
+    featt = {'decode_head.linear_pred': x, 'b': x}
+    out = d(feats, featt, None, 0, None, None)       # both alphas are 0 -> no kernel needed on CPU
+    assert list(out) == ['loss_decode_head.linear_pred<->decode_head.linear_pred_other',
+                         "loss_a<->b_{'loss_type': 'channel', 'group_size': 2}"]
+    with pytest.raises(NameError):
+        sd.build_criterion('NoSuchLoss', {})
+    with pytest.raises(TypeError):
+        sd.build_criterion('CDLoss', {'alpha': 1})     # CDLoss() takes no kwargs, as in the reference
+
+
+def test_extractor_records_only_in_training_mode():
+    import torch.nn as nn
+    stu = nn.Sequential(nn.Conv2d(3, 4, 1), nn.Conv2d(4, 5, 1))
+    tea = nn.Sequential(nn.Conv2d(3, 4, 1), nn.Conv2d(4, 5, 1))
+    ex = sd.Extractor(stu, tea, [{'student_layer': '1', 'teacher_layer': '1'}])
+    x = torch.randn(1, 3, 4, 4)
+    ex.train()
+    stu(x), tea(x)
+    assert ex.student_features['1'].shape == (1, 5, 4, 4) and '1' in ex.teacher_features
+    ex.student_features.clear()
+    ex.eval()
+    stu(x)
+    assert ex.student_features == {}
+
+
+def test_shard_bounds_cover_the_batch():
+    for batch, world in ((128, 8), (16, 2), (7, 4), (3, 8)):
+        pieces = [sdist.shard_bounds(batch, r, world) for r in range(world)]
+        assert pieces[0][0] == 0 and pieces[-1][1] == batch
+        assert all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+
+
+def test_parse_losses_single_process():
+    losses = {'loss_seg': torch.tensor(1.5), 'acc': torch.tensor(80.0), 'loss_kd': [torch.tensor(0.25), torch.tensor(0.5)]}
+    total, logs = sdist.parse_losses(losses)
+    assert total.item() == pytest.approx(2.25)
+    assert logs == {'loss_seg': 1.5, 'acc': 80.0, 'loss_kd': 0.75, 'loss': 2.25}
+
+
+def test_autograd_adopts_the_gradient_buffer_without_copy():
+    """The pattern functional._finish_backward relies on: dropping ctx's reference lets autograd keep dS."""
+    holder = {}
+
+    class Fn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x):
+            ctx.ds = torch.full_like(x, 2.0)
+            holder['ptr'] = ctx.ds.data_ptr()
+            return x.sum() * 0 + 1.0
+
+        @staticmethod
+        def backward(ctx, g):
+            ds = ctx.ds
+            ctx.ds = None
+            return ds
+
+    x = torch.randn(64, requires_grad=True)
+    Fn.apply(x).backward()
+    assert x.grad.data_ptr() == holder['ptr']
