@@ -29,8 +29,10 @@
  *   - feature maps are contiguous NCHW: element (b,c,p) at ((b*C + c)*HW + p).
  *   - return value: 0 = ok, negative = SD_ERR_* argument error, positive = cudaError_t.
  *     No C++ exception crosses the boundary.  sd_strerror() names any of them.
- *   - `workspace` must be zero-filled once when it is allocated (the kernels keep their
- *     counters self-resetting); one workspace must not be shared by concurrent streams.
+ *   - `workspace` must be zero-filled once when it is allocated.  Its first bytes are a counter
+ *     arena common to every entry point (the kernels leave it zeroed again), so ONE workspace
+ *     of the largest size requested may serve any sequence of calls and shapes on a stream;
+ *     it must not be shared by concurrent streams.
  *   - fp32 accumulation regardless of `dtype`; dS has the dtype of S.
  *   - deterministic: no floating-point atomics; reductions run in a fixed order for a
  *     given shape and device.

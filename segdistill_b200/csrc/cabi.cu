@@ -300,7 +300,7 @@ int sd_kl_pixels_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl, 
 // ============================================================================ MSE
 size_t sd_mse_workspace_bytes(int64_t numel) {
     (void)numel;
-    return sizeof(float) * sd::kMseMaxGrid;
+    return sd::kArenaBytes + sizeof(float) * sd::kMseMaxGrid;
 }
 
 int sd_mse_fwd_bwd(const void* S, const void* T, void* dS, float* loss, int64_t numel, int dtype, float weight,
@@ -319,7 +319,8 @@ int sd_mse_fwd_bwd(const void* S, const void* T, void* dS, float* loss, int64_t 
     if (want < grid) grid = (int)want;
     const float gcoef = (float)((double)grad_scale * 2.0 * (double)weight / (double)numel);
     const float scale = (float)((double)weight / (double)numel);
-    cudaError_t e = sd::launch_mse(S, T, dS, loss, static_cast<float*>(workspace), numel, dtype == SD_BF16, gcoef,
+    cudaError_t e = sd::launch_mse(S, T, dS, loss,
+                                   reinterpret_cast<float*>(static_cast<char*>(workspace) + sd::kArenaBytes), numel, dtype == SD_BF16, gcoef,
                                    scale, grid, static_cast<cudaStream_t>(stream));
     g_launches += 2;
     t_last_kernel = "mse_kernel";

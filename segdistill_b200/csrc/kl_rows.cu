@@ -248,14 +248,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1) kl_rows_tma_kernel(const Rows
         // ---- rows split over several CTAs: exchange (max, sum) partials through global memory
         float Ms = ms, Mt = mt, fs = 1.f, ft = 1.f;
         if (x.nch > 1) {
+            unsigned* rcnt = &p.row_cnt[x.row & (kRowCntRing - 1)];
             if (tid == 0) {
                 float* slot = p.unit_part + (size_t)u * kPartWords;
                 __stcg(reinterpret_cast<float4*>(slot), make_float4(ms, Zs, mt, Zt));
                 __stcg(slot + 4, A);
                 __threadfence();
-                atomicAdd(&p.row_cnt[x.row], 1u);
+                atomicAdd(rcnt, 1u);
                 unsigned spins = 0;
-                while (ld_acquire_gpu(&p.row_cnt[x.row]) < (unsigned)x.nch) {
+                while (ld_acquire_gpu(rcnt) < (unsigned)x.nch) {
                     if (++spins > kSpinLimit) {
                         atomicExch(&p.ctrl[1], 1u);  // never expected: reported by the host wrapper
                         break;
@@ -316,8 +317,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) kl_rows_tma_kernel(const Rows
             fs = fast_exp2((ms - Ms) * c2);
             ft = fast_exp2((mt - Mt) * c2);
             if (tid == 0) {
-                const unsigned old = atomicAdd(&p.row_cnt[x.row], 1u);
-                if (old == 2u * (unsigned)x.nch - 1u) atomicExch(&p.row_cnt[x.row], 0u);  // last one out resets
+                const unsigned old = atomicAdd(rcnt, 1u);
+                if (old == 2u * (unsigned)x.nch - 1u) atomicExch(rcnt, 0u);  // last one out resets
             }
         }
 

@@ -6,7 +6,14 @@
 
 namespace sd {
 
+// Every workspace, whatever the op or shape, starts with the same COUNTER ARENA: integer words that
+// must be zero between launches (each kernel leaves them zero again).  Nothing else is ever stored
+// there, so one workspace can serve any sequence of ops and shapes on a stream; the regions behind
+// the arena hold floats that are always written before they are read within a launch.
 constexpr int kCtrlWords = 64;     // [0] completion ticket, [1] error flag (spin time-out)
+constexpr int kRowCntRing = 4096;  // split-row arrival counters, indexed by row % ring (rows in flight
+                                   // at once are bounded by the persistent grid size, <= kMaxGrid)
+constexpr size_t kArenaBytes = sizeof(unsigned) * (kCtrlWords + kRowCntRing);
 constexpr int kMaxGrid = 1024;     // upper bound on persistent-grid size (per-CTA partial slots)
 constexpr int kGenericChunk = 4096;  // elements of one channel plane per generic work unit
 constexpr int kPartWords = 8;      // floats per published unit partial
@@ -42,12 +49,12 @@ struct RowsParams {
     // workspace
     unsigned* ctrl;
     float* cta_part;      // [2][kMaxGrid]
-    unsigned* row_cnt;    // [R]
+    unsigned* row_cnt;    // [kRowCntRing]
     float* unit_part;     // [units][kPartWords]
 };
 
 struct RowsWorkspace {
-    size_t off_ctrl, off_cta, off_rowcnt, off_rowkl, off_unit, bytes;
+    size_t off_ctrl, off_rowcnt, off_cta, off_rowkl, off_unit, bytes;
 };
 inline RowsWorkspace rows_workspace_layout(long long B, long long C, long long HW, long long g) {
     RowsWorkspace w;
@@ -57,8 +64,8 @@ inline RowsWorkspace rows_workspace_layout(long long B, long long C, long long H
     const long long units = B * C * KC;  // >= number of TMA units as well
     size_t o = 0;
     w.off_ctrl = o;   o += sizeof(unsigned) * kCtrlWords;
+    w.off_rowcnt = o; o += sizeof(unsigned) * kRowCntRing;   // == kArenaBytes
     w.off_cta = o;    o += sizeof(float) * 2 * kMaxGrid;
-    w.off_rowcnt = o; o += sizeof(unsigned) * (size_t)R;
     w.off_rowkl = o;  o += sizeof(float) * (size_t)R;
     o = (o + 31) & ~(size_t)31;
     w.off_unit = o;   o += sizeof(float) * kPartWords * (size_t)units;
@@ -100,7 +107,7 @@ inline PixWorkspace pix_workspace_layout(long long B, long long C, long long HW)
     if (nparts < kMaxGrid) nparts = kMaxGrid;
     w.nparts = nparts;
     size_t o = 0;
-    w.off_ctrl = o;  o += sizeof(unsigned) * kCtrlWords;
+    w.off_ctrl = o;  o = kArenaBytes;
     w.off_cta = o;   o += sizeof(float) * 2 * (size_t)nparts;
     w.off_rowkl = o; o += sizeof(float) * (size_t)R;
     w.bytes = (o + 255) & ~(size_t)255;

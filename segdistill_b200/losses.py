@@ -10,8 +10,9 @@ Host-side behaviour kept from the reference: the alpha warm-up / early-decay sta
 (:61-92), the channel shuffle drawn from ``torch.randperm`` on the CPU global generator
 (:39) every ``interval`` steps, the bilinear resize to the label size (:25-33).  What changed:
 the shuffle and the ragged-group pad cost no copies (the kernel gathers / skips), the resize is
-skipped when sizes already match (it is an exact identity there), and when ``alpha == 0`` no
-kernel runs at all.
+skipped when sizes already match (it is an exact identity there), when ``alpha == 0`` no
+kernel runs at all, and the returned scalar is always fp32 (the kernels accumulate in fp32;
+the reference returns the feature dtype, i.e. a bf16/fp16-rounded loss under mixed precision).
 """
 from __future__ import annotations
 
@@ -87,7 +88,7 @@ class KLDLoss(nn.Module):
             perm = torch.randperm(x_student.shape[1])      # same draw as the reference (:39)
         self.last_perm = perm
         if self.alpha == 0:
-            return SF.zero_loss(x_student).to(x_student.dtype)
+            return SF.zero_loss(x_student)
 
         tc = self.transform_config
         kind = tc['loss_type'] if tc else None
@@ -102,7 +103,7 @@ class KLDLoss(nn.Module):
             lead = x_student.numel() // x_student.shape[-1]
             loss = SF.kl_rows_loss(x_student, x_teacher, group=1, tau=self.tau, alpha=self.alpha,
                                    algo=self.algo, bchw=(1, lead, x_student.shape[-1]))
-        return loss.to(x_student.dtype)
+        return loss
 
 
 def _bilinear():
@@ -152,7 +153,7 @@ class ATLoss(nn.Module):
 
     def forward(self, x_student, x_teacher, gt=None, step=0):
         loss = SF.kl_pixels_loss(x_student, x_teacher, tau=1.0, alpha=1.0, at_weight=1.0, algo=self.algo)
-        return loss.to(x_student.dtype)
+        return loss
 
 
 class FeatureMSELoss(nn.Module):
@@ -163,7 +164,7 @@ class FeatureMSELoss(nn.Module):
         self.weight = weight
 
     def forward(self, x_student, x_teacher, gt=None, step=0):
-        return SF.mse_loss(x_student, x_teacher, self.weight).to(x_student.dtype)
+        return SF.mse_loss(x_student, x_teacher, self.weight)
 
 
 class CDMSELoss(nn.Module):
@@ -179,7 +180,7 @@ class CDMSELoss(nn.Module):
         total, kl, mse = SF.kl_rows_mse_loss(x_student, x_teacher, group=self.group_size, tau=self.tau,
                                              alpha=self.alpha, mse_weight=self.mse_weight, algo=self.algo)
         self.last_parts = (kl, mse)
-        return total.to(x_student.dtype)
+        return total
 
 
 class CGDCorrLoss(nn.Module):
@@ -190,4 +191,4 @@ class CGDCorrLoss(nn.Module):
         self.group_size, self.alpha = group_size, alpha
 
     def forward(self, x_student, x_teacher, gt=None, step=0):
-        return SF.cgd_corr_loss(x_student, x_teacher, self.group_size, self.alpha).to(x_student.dtype)
+        return SF.cgd_corr_loss(x_student, x_teacher, self.group_size, self.alpha)

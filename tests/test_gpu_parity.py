@@ -271,7 +271,7 @@ def test_gradient_buffer_is_adopted_without_copy_and_fp16_inputs_work():
     xh = s.half().to(dev()).requires_grad_(True)
     loss = sd.CDLoss()(xh, t.half().to(dev()))
     loss.backward()
-    assert xh.grad.dtype == torch.float16 and loss.dtype == torch.float16
+    assert xh.grad.dtype == torch.float16 and loss.dtype == torch.float32   # the scalar stays fp32
     ref = _oracle_run('CDLoss', {}, s.half().float(), t.half().float(), (16, 16), 1)
     assert rel_err(loss.float().item(), ref[0]) <= 2e-3
 
@@ -279,12 +279,15 @@ def test_gradient_buffer_is_adopted_without_copy_and_fp16_inputs_work():
 def test_dispatcher_end_to_end():
     cfg = [{'student_layer': 'head', 'teacher_layer': 'head', 'loss_name': 'CGDLoss',
             'loss_config': {'alpha': 2, 'tau': 3}},
-           {'student_layer': 'head', 'teacher_layer': 'head', 'loss_name': 'PDLoss', 'loss_config': {}}]
+           {'student_layer': 'aux', 'teacher_layer': 'aux', 'loss_name': 'PDLoss', 'loss_config': {}}]
     d = sd.DistillationLoss(cfg)
     s, t = seeded_pair((2, 150, 32, 32), seed=43)
     x = s.to(dev()).requires_grad_(True)
     gt = torch.zeros(2, 1, 32, 32, dtype=torch.long, device=dev())
-    out = d({'head': x}, {'head': t.to(dev())}, gt, 1, None, None)
+    tg = t.to(dev())
+    # distinct layer names: two entries on the same pair without transform_config share ONE key
+    # ('loss_head<->head_other') in the reference too (opts.py:105-110) and the second overwrites the first
+    out = d({'head': x, 'aux': x}, {'head': tg, 'aux': tg}, gt, 1, None, None)
     from segdistill_b200 import dist as sdist
     total, logs = sdist.parse_losses(out)
     total.backward()
