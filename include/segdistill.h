@@ -15,6 +15,7 @@
  *                         with at_weight != 0 also ATLoss :175-197 (channel-mean MSE :190
  *                         + per-pixel KL :192-195)
  *   sd_mse_fwd_bwd        losses.py:178,190 / :202,235 (nn.MSELoss), :812-830 (feature MSE)
+ *   sd_kl_rows_multi_fwd_bwd  the same for two `distillation` entries on one pair (opts.py:100-103)
  *   sd_scale_grad         the autograd multiply by grad_output that torch would run in
  *                         backward (loss enters the total as a plain sum,
  *                         mmseg/models/segmentors/SD_structure.py:121-122; 512 under fp16
@@ -105,6 +106,25 @@ SD_API int sd_kl_rows_fwd_bwd(const void* S, const void* T, void* dS,
                        void* workspace, size_t workspace_bytes,
                        int algo, void* stream);
 
+/*
+ * Up to two softmax-KL losses over the SAME (S, T) pair in one pass (dispatcher-level batching of
+ * mmseg/models/distillation/opts.py:100-103 when two `distillation` entries hook the same tensors,
+ * e.g. CD + CGD on the logits): S and T are read once and the SUM of the gradients is written once.
+ *   groups/taus/alphas: host arrays [n_losses]; every row of the loss with the larger group must be
+ *   a union of whole rows of the other (groups[1] % groups[0] == 0, or groups[1] >= C).
+ *   losses[k]: device float[1]; row_kls: NULL or host array of device float[R_k] (entries may be NULL).
+ *   dS = grad_scale * sum_k g_k * alpha_k/(R_k*tau_k) * (q_k - p_k), with g_k = *grad_outputs[k]
+ *   (device scalars) or 1 when grad_outputs (or the entry) is NULL.
+ *   run_if: NULL, or a device word: the launch is a no-op when it reads 0 (conditional backward
+ *   re-run after sd_scale_grad2 found non-uniform upstream gradients).
+ * TMA path only: SD_ERR_UNSUPPORTED when the layout cannot take it (call the single-loss entry per loss).
+ */
+SD_API int sd_kl_rows_multi_fwd_bwd(const void* S, const void* T, void* dS, int n_losses, const int* groups,
+                             const float* taus, const float* alphas, float* const* losses,
+                             float* const* row_kls, const float* const* grad_outputs,
+                             const unsigned* run_if, int B, int C, int HW, int dtype, float grad_scale,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ pixels (PD / AT) */
 SD_API size_t sd_kl_pixels_workspace_bytes(int B, int C, int HW);
 
@@ -133,6 +153,11 @@ SD_API int sd_mse_fwd_bwd(const void* S, const void* T, void* dS, float* loss,
 /* ------------------------------------------------------------------ backward helper */
 /* dS *= *grad_output (a device scalar); exits without touching dS when it equals 1. */
 SD_API int sd_scale_grad(void* dS, int64_t numel, int dtype, const float* grad_output, void* stream);
+
+/* Two upstream gradients for one fused two-loss dS: if *grad_output0 == *grad_output1, dS *= that value
+ * and *nonuniform_flag = 0; else dS is left alone and *nonuniform_flag = 1 (see run_if above). */
+SD_API int sd_scale_grad2(void* dS, int64_t numel, int dtype, const float* grad_output0, const float* grad_output1,
+                   unsigned* nonuniform_flag, void* stream);
 
 /* ------------------------------------------------------------------ CGD correlation (extension) */
 SD_API size_t sd_cgd_corr_workspace_bytes(int B, int C, int HW, int group);

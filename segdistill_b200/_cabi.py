@@ -23,7 +23,7 @@ ALGOS = {'auto': ALGO_AUTO, 'generic': ALGO_GENERIC, 'tma': ALGO_TMA}
 # every symbol include/segdistill.h declares (tests check the library exports all of them)
 EXPORTS = (
     'sd_abi_version', 'sd_strerror', 'sd_device_check',
-    'sd_kl_rows_workspace_bytes', 'sd_kl_rows_fwd_bwd',
+    'sd_kl_rows_workspace_bytes', 'sd_kl_rows_fwd_bwd', 'sd_kl_rows_multi_fwd_bwd', 'sd_scale_grad2',
     'sd_kl_pixels_workspace_bytes', 'sd_kl_pixels_fwd_bwd',
     'sd_mse_workspace_bytes', 'sd_mse_fwd_bwd', 'sd_scale_grad',
     'sd_cgd_corr_workspace_bytes', 'sd_cgd_corr_fwd_bwd',
@@ -36,6 +36,10 @@ _lock = threading.Lock()
 
 class SegDistillError(RuntimeError):
     pass
+
+
+class SegDistillUnsupported(SegDistillError):
+    """SD_ERR_UNSUPPORTED: the requested kernel cannot run this layout (the caller picks another entry point)."""
 
 
 def load():
@@ -62,6 +66,11 @@ def load():
         lib.sd_kl_rows_fwd_bwd.restype = i32
         lib.sd_kl_rows_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
                                            f32, f32, f32, f32, vp, vp, sz, i32, vp]
+        lib.sd_kl_rows_multi_fwd_bwd.restype = i32
+        lib.sd_kl_rows_multi_fwd_bwd.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp,
+                                                 i32, i32, i32, i32, f32, vp, sz, vp]
+        lib.sd_scale_grad2.restype = i32
+        lib.sd_scale_grad2.argtypes = [vp, i64, i32, vp, vp, vp, vp]
         lib.sd_kl_pixels_workspace_bytes.restype = sz
         lib.sd_kl_pixels_workspace_bytes.argtypes = [i32, i32, i32]
         lib.sd_kl_pixels_fwd_bwd.restype = i32
@@ -86,6 +95,8 @@ def load():
 
 
 def _check(rc: int):
+    if rc == -6:
+        raise SegDistillUnsupported(f'{load().sd_strerror(rc).decode()} (rc={rc})')
     if rc != 0:
         raise SegDistillError(f'{load().sd_strerror(rc).decode()} (rc={rc})')
 
@@ -185,6 +196,62 @@ def kl_rows(x_student, x_teacher, group=1, tau=1.0, alpha=1.0, perm: Optional[to
             ws.data_ptr(), ws.numel(), int(algo), _stream_ptr(dev))
         _check(rc)
     return out[0], ds, row_kl, (out[1] if mse_weight != 0 else None)
+
+
+def kl_rows_multi(x_student, x_teacher, groups, taus, alphas, grad_outputs=None, run_if=None, ds=None):
+    """Two row-wise softmax-KL losses over the same pair in one pass. Returns (losses[n], dS).
+
+    ``grad_outputs``/``run_if``/``ds`` serve the conditional backward re-run (see functional._KLRowsMulti).
+    """
+    lib = load()
+    s, t, code = _prep_pair(x_student, x_teacher)
+    n = len(groups)
+    B, C = s.shape[0], s.shape[1]
+    HW = s[0, 0].numel()
+    dev = s.device
+    c = ctypes
+    with torch.cuda.device(dev):
+        if ds is None:
+            ds = torch.empty_like(s)
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+        g_arr = (c.c_int * n)(*[int(g) for g in groups])
+        t_arr = (c.c_float * n)(*[float(v) for v in taus])
+        a_arr = (c.c_float * n)(*[float(v) for v in alphas])
+        l_arr = (c.c_void_p * n)(*[out[k:].data_ptr() for k in range(n)])
+        go_arr = None
+        if grad_outputs is not None:
+            go_arr = (c.c_void_p * n)(*[g.data_ptr() for g in grad_outputs])
+        ws = _workspace(dev, lib.sd_kl_rows_workspace_bytes(B, C, HW, min(int(g) for g in groups)))
+        rc = lib.sd_kl_rows_multi_fwd_bwd(
+            s.data_ptr(), t.data_ptr(), ds.data_ptr(), n, g_arr, t_arr, a_arr, l_arr, None, go_arr,
+            run_if.data_ptr() if run_if is not None else None,
+            B, C, HW, code, 1.0, ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        _check(rc)
+    return out, ds
+
+
+def multi_supported(shape, groups, elem_size):
+    """Host-side mirror of the C ABI's fusability test (nesting + 16-byte rows); the co-residency
+    limit is checked by the library, which answers SD_ERR_UNSUPPORTED."""
+    C = shape[1]
+    HW = 1
+    for d in shape[2:]:
+        HW *= d
+    g = sorted(min(int(v), C) for v in groups)
+    if len(g) != 2 or (HW * elem_size) % 16:
+        return False
+    return g[1] == C or g[1] % g[0] == 0
+
+
+def scale_grad2_(ds: torch.Tensor, go0: torch.Tensor, go1: torch.Tensor) -> torch.Tensor:
+    """dS *= go when go0 == go1; returns the device flag (1 = non-uniform, dS untouched)."""
+    lib = load()
+    flag = torch.empty(1, dtype=torch.int32, device=ds.device)
+    with torch.cuda.device(ds.device):
+        rc = lib.sd_scale_grad2(ds.data_ptr(), ds.numel(), _dtype_code(ds), go0.data_ptr(), go1.data_ptr(),
+                                flag.data_ptr(), _stream_ptr(ds.device))
+        _check(rc)
+    return flag
 
 
 def kl_pixels(x_student, x_teacher, tau=1.0, alpha=1.0, grad_scale=1.0, at_weight=0.0,

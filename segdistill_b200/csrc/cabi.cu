@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstring>
+#include <utility>
 
 #include "../../include/segdistill.h"
 #include "launch.h"
@@ -110,58 +111,109 @@ size_t sd_kl_rows_workspace_bytes(int B, int C, int HW, int group) {
     return sd::rows_workspace_layout(B, C, HW, group).bytes;
 }
 
-int sd_kl_rows_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl, float* loss, const int32_t* chan_perm,
-                       int B, int C, int HW, int group, int dtype, float tau, float alpha, float grad_scale,
-                       float mse_weight, float* mse_loss, void* workspace, size_t workspace_bytes, int algo,
-                       void* stream) {
-    if (!S || !T || !dS || !loss || !workspace) return SD_ERR_NULL;
-    if (mse_weight != 0.f && !mse_loss) return SD_ERR_NULL;
-    if (dtype != SD_F32 && dtype != SD_BF16) return SD_ERR_DTYPE;
-    if (B <= 0 || C <= 0 || HW <= 0) return SD_ERR_SHAPE;
-    if (group < 1 || !(tau > 0.f)) return SD_ERR_VALUE;
-    if (group > C) group = C;  // one ragged row per sample either way
+namespace {
+
+struct RowsCall {
+    const void* S;
+    const void* T;
+    void* dS;
+    const int32_t* perm;
+    int B, C, HW, dtype;
+    int nl;
+    int group[sd::kMaxLosses];
+    float tau[sd::kMaxLosses], alpha[sd::kMaxLosses];
+    float* loss[sd::kMaxLosses];
+    float* row_kl[sd::kMaxLosses];
+    const float* grad_out[sd::kMaxLosses];
+    const unsigned* run_if;
+    float grad_scale;
+    float mse_weight;
+    float* mse_loss;
+    void* workspace;
+    size_t workspace_bytes;
+    int algo;
+    void* stream;
+};
+
+int rows_dispatch(RowsCall c) {
+    if (!c.S || !c.T || !c.dS || !c.workspace) return SD_ERR_NULL;
+    if (c.nl < 1 || c.nl > sd::kMaxLosses) return SD_ERR_VALUE;
+    for (int k = 0; k < c.nl; ++k) {
+        if (!c.loss[k]) return SD_ERR_NULL;
+        if (c.group[k] < 1 || !(c.tau[k] > 0.f)) return SD_ERR_VALUE;
+        if (c.group[k] > c.C) c.group[k] = c.C;  // one ragged row per sample either way
+    }
+    if (c.mse_weight != 0.f && !c.mse_loss) return SD_ERR_NULL;
+    if (c.dtype != SD_F32 && c.dtype != SD_BF16) return SD_ERR_DTYPE;
+    if (c.B <= 0 || c.C <= 0 || c.HW <= 0) return SD_ERR_SHAPE;
+    if (c.nl == 2) {
+        if (c.perm || c.mse_weight != 0.f) return SD_ERR_UNSUPPORTED;
+        if (c.group[1] < c.group[0]) {  // l[0] must have the smaller rows
+            std::swap(c.group[0], c.group[1]);
+            std::swap(c.tau[0], c.tau[1]);
+            std::swap(c.alpha[0], c.alpha[1]);
+            std::swap(c.loss[0], c.loss[1]);
+            std::swap(c.row_kl[0], c.row_kl[1]);
+            std::swap(c.grad_out[0], c.grad_out[1]);
+        }
+        // every row of l[1] must be a union of whole rows of l[0]
+        if (c.group[1] != c.C && c.group[1] % c.group[0] != 0) return SD_ERR_UNSUPPORTED;
+    }
+    const int B = c.B, C = c.C, HW = c.HW, g0 = c.group[0];
     const long long numel = (long long)B * C * HW;
-    const long long row_len = (long long)group * HW;
-    if (row_len >= (1ll << 31) || numel >= (1ll << 40)) return SD_ERR_SHAPE;
-    const sd::RowsWorkspace wl = sd::rows_workspace_layout(B, C, HW, group);
-    if (workspace_bytes < wl.bytes) return SD_ERR_WORKSPACE;
+    const long long row_len = (long long)g0 * HW;
+    if ((long long)c.group[c.nl - 1] * HW >= (1ll << 31) || numel >= (1ll << 40)) return SD_ERR_SHAPE;
+    const sd::RowsWorkspace wl = sd::rows_workspace_layout(B, C, HW, g0);
+    if (c.workspace_bytes < wl.bytes) return SD_ERR_WORKSPACE;
     DeviceInfo& dev = device_info();
     if (dev.cc_major != 10) return SD_ERR_DEVICE;
 
-    const int es = elem_size(dtype);
+    const int es = elem_size(c.dtype);
     const int VE = 16 / es;
     sd::RowsParams p;
     std::memset(&p, 0, sizeof(p));
-    p.S = S;
-    p.T = T;
-    p.dS = dS;
-    char* ws = static_cast<char*>(workspace);
-    p.row_kl = row_kl ? row_kl : reinterpret_cast<float*>(ws + wl.off_rowkl);
-    p.loss = loss;
-    p.mse_loss = mse_weight != 0.f ? mse_loss : nullptr;
-    p.perm = chan_perm;
+    p.S = c.S;
+    p.T = c.T;
+    p.dS = c.dS;
+    p.perm = c.perm;
     p.B = B;
     p.C = C;
     p.HW = HW;
-    p.g = group;
-    p.G = (C + group - 1) / group;
-    p.G_full = C / group;
-    p.g_last = C % group;
-    p.R = B * p.G;
-    p.c2 = (float)(1.4426950408889634 / (double)tau);
-    p.inv_tau = (float)(1.0 / (double)tau);
-    p.coef = (float)((double)grad_scale * (double)alpha / ((double)p.R * (double)tau));
-    p.loss_scale = (float)((double)alpha / (double)p.R);
-    p.mse_gcoef = (float)((double)grad_scale * 2.0 * (double)mse_weight / (double)numel);
-    p.mse_scale = (float)((double)mse_weight / (double)numel);
+    p.nl = c.nl;
+    char* ws = static_cast<char*>(c.workspace);
+    const int G0 = (C + g0 - 1) / g0;
+    for (int k = 0; k < c.nl; ++k) {
+        sd::RowLoss& l = p.l[k];
+        l.g = c.group[k];
+        l.m = k == 0 ? 1 : (c.group[k] == C ? G0 : c.group[k] / g0);
+        l.G = (C + l.g - 1) / l.g;
+        l.R = B * l.G;
+        l.c2 = (float)(1.4426950408889634 / (double)c.tau[k]);
+        l.inv_tau = (float)(1.0 / (double)c.tau[k]);
+        l.coef = (float)((double)c.grad_scale * (double)c.alpha[k] / ((double)l.R * (double)c.tau[k]));
+        l.loss_scale = (float)((double)c.alpha[k] / (double)l.R);
+        l.loss = c.loss[k];
+        l.row_kl = c.row_kl[k];
+        p.grad_out[k] = c.grad_out[k];
+    }
+    p.run_if = c.run_if;
+    p.mse_loss = c.mse_weight != 0.f ? c.mse_loss : nullptr;
+    p.mse_gcoef = (float)((double)c.grad_scale * 2.0 * (double)c.mse_weight / (double)numel);
+    p.mse_scale = (float)((double)c.mse_weight / (double)numel);
+    p.G_full = C / g0;
+    p.g_last = C % g0;
     p.KC = (HW + sd::kGenericChunk - 1) / sd::kGenericChunk;
     p.ctrl = reinterpret_cast<unsigned*>(ws + wl.off_ctrl);
     p.cta_part = reinterpret_cast<float*>(ws + wl.off_cta);
-    p.row_cnt = reinterpret_cast<unsigned*>(ws + wl.off_rowcnt);
+    p.pkt = reinterpret_cast<unsigned long long*>(ws + wl.off_unit);
     p.unit_part = reinterpret_cast<float*>(ws + wl.off_unit);
+    static std::atomic<unsigned> g_epoch{0};
+    unsigned epoch = ++g_epoch;
+    if (epoch == 0) epoch = ++g_epoch;
+    p.epoch = epoch;
 
     // TMA path: rows must start on 16-byte boundaries
-    const int cap = sd::kl_rows_tma_chunk_capacity();
+    const int cap = sd::kl_rows_tma_chunk_capacity(c.nl);
     p.nch_full = p.G_full > 0 ? (int)((row_len + cap - 1) / cap) : 1;
     long long ce = p.G_full > 0 ? (row_len + p.nch_full - 1) / p.nch_full : (long long)p.g_last * HW;
     ce = (ce + VE - 1) / VE * VE;
@@ -170,38 +222,94 @@ int sd_kl_rows_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl, fl
     p.nch_last = p.g_last ? (int)(((long long)p.g_last * HW + ce - 1) / ce) : 0;
     p.units_per_sample = p.G_full * p.nch_full + p.nch_last;
     p.total_units = (long long)B * p.units_per_sample;
-    const int max_nch = p.nch_full > p.nch_last ? p.nch_full : p.nch_last;
+    // the longest row of any fused loss, in units: all of them must be co-resident
+    long long max_row_units = p.nch_full > p.nch_last ? p.nch_full : p.nch_last;
+    for (int k = 1; k < c.nl; ++k) {
+        const long long m = p.l[k].m;
+        long long n = m * p.nch_full;
+        if (m > p.G_full) n = (long long)p.G_full * p.nch_full + p.nch_last;
+        if (n > max_row_units) max_row_units = n;
+    }
     int grid = (int)(p.total_units < dev.sms ? p.total_units : dev.sms);
     if (grid > sd::kMaxGrid) grid = sd::kMaxGrid;
-    const bool layout_ok = ((long long)HW * es) % 16 == 0 && aligned16(S) && aligned16(T) && aligned16(dS);
-    const bool tma_ok = layout_ok && max_nch <= grid;
+    const bool layout_ok = ((long long)HW * es) % 16 == 0 && aligned16(c.S) && aligned16(c.T) && aligned16(c.dS);
+    const bool tma_ok = layout_ok && max_row_units <= grid;
     const long long gen_units = (long long)B * C * p.KC;
     if (gen_units >= (1ll << 31)) return SD_ERR_SHAPE;
 
     bool use_tma;
-    if (algo == SD_ALGO_TMA) {
+    if (c.algo == SD_ALGO_TMA) {
         if (!tma_ok) return SD_ERR_UNSUPPORTED;
         use_tma = true;
-    } else if (algo == SD_ALGO_GENERIC) {
+    } else if (c.algo == SD_ALGO_GENERIC) {
         use_tma = false;
-    } else if (algo == SD_ALGO_AUTO) {
+    } else if (c.algo == SD_ALGO_AUTO) {
         use_tma = tma_ok;
     } else {
         return SD_ERR_VALUE;
     }
+    if (!use_tma && (c.nl > 1 || c.run_if || c.grad_out[0])) return SD_ERR_UNSUPPORTED;
 
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStream_t st = static_cast<cudaStream_t>(c.stream);
     cudaError_t e;
     if (use_tma) {
-        e = sd::launch_kl_rows_tma(p, dtype == SD_BF16, grid, /*cooperative=*/max_nch > 1, st);
+        const bool split = max_row_units > 1;
+        e = sd::launch_kl_rows_tma(p, c.dtype == SD_BF16, grid, /*cooperative=*/split, st);
         g_launches += 1;
-        t_last_kernel = max_nch > 1 ? "kl_rows_tma_kernel(split-row)" : "kl_rows_tma_kernel";
+        t_last_kernel = c.nl == 2 ? "kl_rows_tma_kernel(2 losses)"
+                                  : (split ? "kl_rows_tma_kernel(split-row)" : "kl_rows_tma_kernel");
     } else {
-        e = sd::launch_kl_rows_generic(p, dtype == SD_BF16, st);
+        if (!p.l[0].row_kl) p.l[0].row_kl = reinterpret_cast<float*>(ws + wl.off_rowkl);
+        e = sd::launch_kl_rows_generic(p, c.dtype == SD_BF16, st);
         g_launches += 3;
         t_last_kernel = "kl_rows_generic";
     }
     return e == cudaSuccess ? SD_OK : (int)e;
+}
+
+}  // namespace
+
+int sd_kl_rows_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl, float* loss, const int32_t* chan_perm,
+                       int B, int C, int HW, int group, int dtype, float tau, float alpha, float grad_scale,
+                       float mse_weight, float* mse_loss, void* workspace, size_t workspace_bytes, int algo,
+                       void* stream) {
+    RowsCall c;
+    std::memset(&c, 0, sizeof(c));
+    c.S = S; c.T = T; c.dS = dS; c.perm = chan_perm;
+    c.B = B; c.C = C; c.HW = HW; c.dtype = dtype;
+    c.nl = 1;
+    c.group[0] = group; c.tau[0] = tau; c.alpha[0] = alpha;
+    c.loss[0] = loss; c.row_kl[0] = row_kl;
+    c.grad_scale = grad_scale;
+    c.mse_weight = mse_weight; c.mse_loss = mse_loss;
+    c.workspace = workspace; c.workspace_bytes = workspace_bytes;
+    c.algo = algo; c.stream = stream;
+    return rows_dispatch(c);
+}
+
+int sd_kl_rows_multi_fwd_bwd(const void* S, const void* T, void* dS, int n_losses, const int* groups,
+                             const float* taus, const float* alphas, float* const* losses, float* const* row_kls,
+                             const float* const* grad_outputs, const unsigned* run_if,
+                             int B, int C, int HW, int dtype, float grad_scale,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+    if (!groups || !taus || !alphas || !losses) return SD_ERR_NULL;
+    if (n_losses < 1 || n_losses > sd::kMaxLosses) return SD_ERR_VALUE;
+    RowsCall c;
+    std::memset(&c, 0, sizeof(c));
+    c.S = S; c.T = T; c.dS = dS;
+    c.B = B; c.C = C; c.HW = HW; c.dtype = dtype;
+    c.nl = n_losses;
+    for (int k = 0; k < n_losses; ++k) {
+        c.group[k] = groups[k]; c.tau[k] = taus[k]; c.alpha[k] = alphas[k];
+        c.loss[k] = losses[k];
+        c.row_kl[k] = row_kls ? row_kls[k] : nullptr;
+        c.grad_out[k] = grad_outputs ? grad_outputs[k] : nullptr;
+    }
+    c.run_if = run_if;
+    c.grad_scale = grad_scale;
+    c.workspace = workspace; c.workspace_bytes = workspace_bytes;
+    c.algo = SD_ALGO_TMA; c.stream = stream;
+    return rows_dispatch(c);
 }
 
 // ============================================================================ pixels
@@ -342,6 +450,25 @@ int sd_scale_grad(void* dS, int64_t numel, int dtype, const float* grad_output, 
                                           static_cast<cudaStream_t>(stream));
     g_launches += 1;
     t_last_kernel = "scale_grad_kernel";
+    return e == cudaSuccess ? SD_OK : (int)e;
+}
+
+int sd_scale_grad2(void* dS, int64_t numel, int dtype, const float* grad_output0, const float* grad_output1,
+                   unsigned* nonuniform_flag, void* stream) {
+    if (!dS || !grad_output0 || !grad_output1 || !nonuniform_flag) return SD_ERR_NULL;
+    if (dtype != SD_F32 && dtype != SD_BF16) return SD_ERR_DTYPE;
+    if (numel <= 0) return SD_ERR_SHAPE;
+    DeviceInfo& dev = device_info();
+    if (dev.cc_major != 10) return SD_ERR_DEVICE;
+    const int VE = 16 / elem_size(dtype);
+    long long want = (numel / VE + 255) / 256;
+    if (want < 1) want = 1;
+    int grid = dev.sms * 8;
+    if (want < grid) grid = (int)want;
+    cudaError_t e = sd::launch_scale_grad2(dS, numel, dtype == SD_BF16, grad_output0, grad_output1, nonuniform_flag,
+                                           grid, static_cast<cudaStream_t>(stream));
+    g_launches += 1;
+    t_last_kernel = "scale_grad2_kernel";
     return e == cudaSuccess ? SD_OK : (int)e;
 }
 

@@ -1,18 +1,25 @@
-// Row-wise softmax-KL, forward + backward fused (CD / CGD / plain KLDLoss).
+// Row-wise softmax-KL, forward + backward fused (CD / CGD / plain KLDLoss), one or two losses
+// over the same (student, teacher) pair per pass.
 //
 // Replaces the ATen chain of mmseg/models/distillation/losses.py:35-42 (channel gather),
 // :50-58 (group reshape, -1e9 pad) and :108-112 (div, log_softmax, softmax, kl_div, mul)
 // plus its autograd backward.  Row = `g` consecutive (gathered) channels x HW.
 //
-//   kl_rows_tma_kernel      persistent: row chunks stream into a shared-memory ring with 1-D TMA
-//                           bulk copies (cp.async.bulk + mbarrier complete_tx) issued by one
-//                           elected thread as soon as a slot has been drained; the 16 warps pull
-//                           a chunk (<= 16384 elements) into REGISTERS, reduce max / sum-exp,
-//                           and write dS straight from registers.  HBM traffic is the
-//                           algorithmic 12 B/elem (fp32) / 6 B/elem (bf16): S and T are read
-//                           once, dS written once.  Rows longer than one chunk are split over
-//                           several CTAs which exchange (max, sum) partials through global
-//                           memory flags (all CTAs co-resident: cooperative launch).
+//   kl_rows_tma_kernel      persistent, one CTA per SM.  Row chunks stream into a 7-stage
+//                           shared-memory ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier
+//                           complete_tx) issued by one elected thread as soon as a slot has been
+//                           drained; the 16 warps pull a chunk into REGISTERS (32 elements of S and
+//                           of T per thread), exponentiate against a thread-local maximum (no block
+//                           barrier before the exponentials), combine (max, sum) partials with
+//                           warp shuffles and ONE CTA barrier, and write dS straight from
+//                           registers.  HBM traffic is the algorithmic 12 B/elem (fp32) /
+//                           6 B/elem (bf16): S and T are read once, dS written once.
+//                           NL = 2 fuses two losses with nested rows (e.g. CD + CGD on the same
+//                           logits): still one read of S and T and one write of the summed
+//                           gradient.  Rows longer than one chunk are split over several CTAs which
+//                           exchange partials through epoch-tagged 8-byte packets in global memory
+//                           (no atomics, no counters to reset; all CTAs co-resident: cooperative
+//                           launch).
 //   kl_rows_generic_*       any alignment / any row length: three plain passes.
 #include "common.cuh"
 #include "params.h"
@@ -20,22 +27,25 @@
 namespace sd {
 
 // ------------------------------------------------------------------ configuration
-constexpr int kCons = 512;                        // threads per CTA (16 warps x 128 registers)
-constexpr int kConsWarps = kCons / 32;
-constexpr int kRowsThreads = kCons;
-constexpr int kEPT = 32;                          // elements per consumer thread and tensor
-constexpr int kChunkCap = kCons * kEPT;           // 16384 elements per chunk
+constexpr int kThreads = 512;                     // 16 warps x 128 registers
+constexpr int kWarps = kThreads / 32;
+constexpr int kDataRegs = 32;                     // register-resident elements per thread and tensor (NL = 1)
 constexpr int kSlotVecRows = 2;                   // 16-byte vectors per thread and ring slot
-constexpr int kSlotVecs = kSlotVecRows * kCons;   // 1024 vectors
+constexpr int kSlotVecs = kSlotVecRows * kThreads;  // 1024 vectors
 constexpr int kSlotBytes = kSlotVecs * 16;        // 16 KB per tensor
 constexpr int kStageBytes = 2 * kSlotBytes;       // S + T
 constexpr int kStages = 7;                        // 224 KB ring
-constexpr unsigned kSpinLimit = 1u << 24;
-constexpr size_t kRowsSmemBytes = (size_t)kStages * kStageBytes + 2 * kStages * sizeof(uint64_t) +  // (2nd barrier array: spare)
-                                  kConsWarps * (sizeof(float2) + sizeof(float4)) + 8 * sizeof(float);
+constexpr unsigned kSpinLimit = 1u << 22;
+constexpr int kRedFloats = 8;                     // per-warp record: Ms, Mt, {Zs, Zt, A} x NL, (SQ)
+constexpr size_t kRowsSmemBytes = (size_t)kStages * kStageBytes + (kStages + 1) * sizeof(uint64_t) +
+                                  2 * kWarps * kRedFloats * sizeof(float) + kMaxLosses * 8 * sizeof(float);
+constexpr float kPadValue = -1.0e30f;             // stands in for elements a partial chunk does not have
+constexpr float kMaxFloor = -1.0e29f;             // floor of a thread's local maximum: a thread that holds only
+                                                  // padding then exponentiates to exact zeros (not to exp2 of
+                                                  // the rounding error of kPadValue * c2)
 
 struct Unit {
-    int b, grp, ck, nch, row;
+    int b, grp, ck, nch;
     int e0;   // first logical row element of this chunk
     int len;  // elements in this chunk
 };
@@ -50,7 +60,7 @@ __device__ __forceinline__ Unit decode_unit(const RowsParams& p, long long u) {
         x.grp = r / p.nch_full;
         x.ck = r - x.grp * p.nch_full;
         x.nch = p.nch_full;
-        g_real = p.g;
+        g_real = p.l[0].g;
     } else {
         x.grp = p.G_full;
         x.ck = r - full_units;
@@ -60,35 +70,84 @@ __device__ __forceinline__ Unit decode_unit(const RowsParams& p, long long u) {
     const int L = g_real * p.HW;
     x.e0 = x.ck * p.chunk_elems;
     x.len = min(p.chunk_elems, L - x.e0);
-    x.row = x.b * p.G + x.grp;
     return x;
 }
 
-// global element offset of logical row element e (gathered channel order)
-__device__ __forceinline__ size_t row_elem_offset(const RowsParams& p, const Unit& x, int e) {
-    if (p.perm == nullptr) return ((size_t)x.b * p.C + (size_t)x.grp * p.g) * p.HW + e;
+// first unit (within the sample) of l[0] row j; j == number of rows gives the end
+__device__ __forceinline__ int unit_start(const RowsParams& p, int j) {
+    return j <= p.G_full ? j * p.nch_full : p.units_per_sample;
+}
+
+// global element offset of logical row element e of a gathered row
+__device__ __forceinline__ size_t perm_elem_offset(const RowsParams& p, const Unit& x, int e) {
     const int j = e / p.HW;
     const int pos = e - j * p.HW;
-    const int ch = p.perm[x.grp * p.g + j];
+    const int ch = p.perm[x.grp * p.l[0].g + j];
     return ((size_t)x.b * p.C + ch) * p.HW + pos;
 }
 
-template <typename T, bool MSE>
-__global__ void __launch_bounds__(kRowsThreads, 1) kl_rows_tma_kernel(const RowsParams p) {
+// softmax statistics of a piece of a row: raw-value maxima (ms, mt) and sums relative to them
+struct RowStat {
+    float ms, zs, mt, zt, a;
+};
+__device__ __forceinline__ RowStat rowstat_empty() { return RowStat{-INFINITY, 0.f, -INFINITY, 0.f, 0.f}; }
+__device__ __forceinline__ RowStat rowstat_merge(const RowStat& x, const RowStat& y, float c2) {
+    RowStat r;
+    r.ms = fmaxf(x.ms, y.ms);
+    r.mt = fmaxf(x.mt, y.mt);
+    const float fxs = x.zs > 0.f ? fast_exp2((x.ms - r.ms) * c2) : 0.f;
+    const float fys = y.zs > 0.f ? fast_exp2((y.ms - r.ms) * c2) : 0.f;
+    const float fxt = x.zt > 0.f ? fast_exp2((x.mt - r.mt) * c2) : 0.f;
+    const float fyt = y.zt > 0.f ? fast_exp2((y.mt - r.mt) * c2) : 0.f;
+    r.zs = __fadd_rn(__fmul_rn(x.zs, fxs), __fmul_rn(y.zs, fys));
+    r.zt = __fadd_rn(__fmul_rn(x.zt, fxt), __fmul_rn(y.zt, fyt));
+    r.a = __fadd_rn(__fmul_rn(x.a, fxt), __fmul_rn(y.a, fyt));
+    return r;
+}
+
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ float sum16(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float max16(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <typename T, int NL, bool MSE>
+__global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsParams p) {
     using E = Elem<T>;
     using vec_t = typename E::vec_t;
     constexpr int VE = E::kVec;
-    constexpr int NV = kEPT / VE;  // vector rows per thread
+    constexpr int EPT = kDataRegs / NL;  // elements per thread and tensor
+    constexpr int NV = EPT / VE;         // 16-byte vectors per thread and tensor
+    constexpr int NJ = (NV + kSlotVecRows - 1) / kSlotVecRows;  // ring slots of a whole chunk
+    static_assert(NV >= 1 && EPT % VE == 0, "layout");
+    static_assert(!(MSE && NL > 1), "the fused MSE term is a single-loss feature");
 
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
-    float2* red_max = reinterpret_cast<float2*>(full + 2 * kStages);
-    float4* red_sum = reinterpret_cast<float4*>(red_max + kConsWarps);
-    float* bcast = reinterpret_cast<float*>(red_sum + kConsWarps);
+    float* red = reinterpret_cast<float*>(full + kStages + 1);      // [2][kWarps][kRedFloats]
+    float* bcast = red + 2 * kWarps * kRedFloats;                   // [kMaxLosses][8]
 
-    const int lane = threadIdx.x & 31;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
 
-    if (threadIdx.x == 0) {
+    if (p.run_if != nullptr && *p.run_if == 0u) return;  // cancelled backward re-run (uniform over the grid)
+
+    if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
         fence_barrier_init();
     }
@@ -100,19 +159,19 @@ __global__ void __launch_bounds__(kRowsThreads, 1) kl_rows_tma_kernel(const Rows
     long long prod_u = blockIdx.x;
     int prod_v0 = 0, prod_stage = 0, free_slots = kStages;
     uint64_t pol = 0;
-    if (threadIdx.x == 0) pol = l2_policy_evict_first();
+    if (tid == 0) pol = l2_policy_evict_first();
     auto issue_loads = [&]() {
         while (free_slots > 0 && prod_u < p.total_units) {
             const Unit x = decode_unit(p, prod_u);
             const int nvec = x.len / VE;
-            const int nv = min(kSlotVecs, nvec - prod_v0);
+            const int nv = min(kSlotVecRows * kThreads, nvec - prod_v0);
             const uint32_t bytes = (uint32_t)nv * 16u;
             mbar_arrive_expect_tx(&full[prod_stage], 2u * bytes);
             unsigned char* dst_s = smem + (size_t)prod_stage * kStageBytes;
             unsigned char* dst_t = dst_s + kSlotBytes;
             const int e = x.e0 + prod_v0 * VE;
             if (p.perm == nullptr) {
-                const size_t off = row_elem_offset(p, x, e) * sizeof(T);
+                const size_t off = (((size_t)x.b * p.C + (size_t)x.grp * p.l[0].g) * p.HW + e) * sizeof(T);
                 tma_bulk_g2s(dst_s, static_cast<const char*>(p.S) + off, bytes, &full[prod_stage], pol);
                 tma_bulk_g2s(dst_t, static_cast<const char*>(p.T) + off, bytes, &full[prod_stage], pol);
             } else {
@@ -124,7 +183,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) kl_rows_tma_kernel(const Rows
                     const int j = cur / p.HW;
                     const int pos = cur - j * p.HW;
                     const int n = min(remaining, p.HW - pos);
-                    const size_t off = row_elem_offset(p, x, cur) * sizeof(T);
+                    const size_t off = perm_elem_offset(p, x, cur) * sizeof(T);
                     const uint32_t nb = (uint32_t)n * (uint32_t)sizeof(T);
                     tma_bulk_g2s(dst_s + doff, static_cast<const char*>(p.S) + off, nb, &full[prod_stage], pol);
                     tma_bulk_g2s(dst_t + doff, static_cast<const char*>(p.T) + off, nb, &full[prod_stage], pol);
@@ -142,42 +201,52 @@ __global__ void __launch_bounds__(kRowsThreads, 1) kl_rows_tma_kernel(const Rows
             --free_slots;
         }
     };
-    if (threadIdx.x == 0) issue_loads();
+    if (tid == 0) issue_loads();
 
     // ================================ 16 warps, chunk lives in registers ================================
-    const int tid = threadIdx.x;
-    const int cwarp = tid >> 5;
-    const float c2 = p.c2;
-    float s[kEPT], t[kEPT];
-    float cta_kl = 0.f, cta_sq = 0.f;  // accumulated by tid 0 in unit order (deterministic)
+    float c2[NL], coef[NL];
+#pragma unroll
+    for (int k = 0; k < NL; ++k) {
+        c2[k] = p.l[k].c2;
+        coef[k] = p.l[k].coef;
+        if (p.grad_out[k] != nullptr) coef[k] *= *p.grad_out[k];
+    }
+    // s/t: raw values, then the exponentials of loss NL-1; xs/xt: exponentials of loss 0 when NL == 2
+    float s[EPT], t[EPT];
+    float xs[NL > 1 ? EPT : 1], xt[NL > 1 ? EPT : 1];
+    float cta_kl[NL], cta_sq = 0.f;  // accumulated by thread 0 in unit order (deterministic)
+#pragma unroll
+    for (int k = 0; k < NL; ++k) cta_kl[k] = 0.f;
     int stage = 0;
     uint32_t phase = 0;
+    int par = 0;
 
     for (long long u = blockIdx.x; u < p.total_units; u += gridDim.x) {
         const Unit x = decode_unit(p, u);
         const int nvec = x.len / VE;
+        const bool whole = nvec == NV * kThreads;  // every thread holds NV vectors
 
-        // ---- ring -> registers, running max of the raw values
+        // ---- ring -> registers
         const int nslots = (nvec + kSlotVecs - 1) / kSlotVecs;
-        float mxs = -INFINITY, mxt = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < NV / kSlotVecRows; ++j) {
-            if (j * kSlotVecs < nvec) {
+        for (int j = 0; j < NJ; ++j) {
+            if (whole || j * kSlotVecs < nvec) {
                 mbar_wait(&full[stage], phase);
                 const vec_t* bs = reinterpret_cast<const vec_t*>(smem + (size_t)stage * kStageBytes);
                 const vec_t* bt = reinterpret_cast<const vec_t*>(smem + (size_t)stage * kStageBytes + kSlotBytes);
 #pragma unroll
                 for (int r = 0; r < kSlotVecRows; ++r) {
                     const int v = j * kSlotVecRows + r;
-                    if (v * kCons + tid < nvec) {
-                        const vec_t a = bs[r * kCons + tid];
-                        const vec_t b = bt[r * kCons + tid];
-                        E::unpack(a, &s[v * VE]);
-                        E::unpack(b, &t[v * VE]);
+                    if (v < NV) {
+                        if (whole || v * kThreads + tid < nvec) {
+                            E::unpack(bs[r * kThreads + tid], &s[v * VE]);
+                            E::unpack(bt[r * kThreads + tid], &t[v * VE]);
+                        } else {
 #pragma unroll
-                        for (int k = 0; k < VE; ++k) {
-                            mxs = fmaxf(mxs, s[v * VE + k]);
-                            mxt = fmaxf(mxt, t[v * VE + k]);
+                            for (int q = 0; q < VE; ++q) {
+                                s[v * VE + q] = kPadValue;
+                                t[v * VE + q] = kPadValue;
+                            }
                         }
                     }
                 }
@@ -185,204 +254,305 @@ __global__ void __launch_bounds__(kRowsThreads, 1) kl_rows_tma_kernel(const Rows
                     stage = 0;
                     phase ^= 1u;
                 }
+            } else {
+#pragma unroll
+                for (int r = 0; r < kSlotVecRows; ++r) {
+                    const int v = j * kSlotVecRows + r;
+                    if (v < NV) {
+#pragma unroll
+                        for (int q = 0; q < VE; ++q) {
+                            s[v * VE + q] = kPadValue;
+                            t[v * VE + q] = kPadValue;
+                        }
+                    }
+                }
             }
         }
 
-        // ---- chunk max over the CTA
-        mxs = warp_max(mxs);
-        mxt = warp_max(mxt);
-        if (lane == 0) red_max[cwarp] = make_float2(mxs, mxt);
+        // ---- thread-local maxima of the raw values: no barrier before the exponentials
+        float ms = fmaxf(s[0], kMaxFloor), mt = fmaxf(t[0], kMaxFloor);
+#pragma unroll
+        for (int i = 1; i < EPT; ++i) {
+            ms = fmaxf(ms, s[i]);
+            mt = fmaxf(mt, t[i]);
+        }
+
+        // ---- exponentials (kept in registers), thread-partial sums relative to (ms, mt)
+        float zs[NL], zt[NL], a[NL], sq = 0.f;
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+            zs[k] = 0.f;
+            zt[k] = 0.f;
+            a[k] = 0.f;
+        }
+        {
+            float ms2[NL], mt2[NL];
+#pragma unroll
+            for (int k = 0; k < NL; ++k) {
+                ms2[k] = ms * c2[k];
+                mt2[k] = mt * c2[k];
+            }
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                const float d = t[i] - s[i];
+                if (MSE) sq = fmaf(d, d, sq);
+                if (NL > 1) {
+                    const float es0 = fast_exp2(fmaf(s[i], c2[0], -ms2[0]));
+                    const float et0 = fast_exp2(fmaf(t[i], c2[0], -mt2[0]));
+                    zs[0] += es0;
+                    zt[0] += et0;
+                    a[0] = fmaf(et0, d, a[0]);
+                    xs[i] = es0;
+                    xt[i] = et0;
+                }
+                const float es = fast_exp2(fmaf(s[i], c2[NL - 1], -ms2[NL - 1]));
+                const float et = fast_exp2(fmaf(t[i], c2[NL - 1], -mt2[NL - 1]));
+                zs[NL - 1] += es;
+                zt[NL - 1] += et;
+                a[NL - 1] = fmaf(et, d, a[NL - 1]);
+                if (!MSE) {
+                    s[i] = es;
+                    t[i] = et;
+                }
+            }
+        }
+
+        // ---- warp: raw maxima are common to all losses, sums are rescaled to them
+        const float msw = warp_max(ms), mtw = warp_max(mt);
+        float rec[kRedFloats];
+#pragma unroll
+        for (int i = 0; i < kRedFloats; ++i) rec[i] = 0.f;
+        rec[0] = msw;
+        rec[1] = mtw;
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+            const float fs = fast_exp2((ms - msw) * c2[k]);
+            const float ft = fast_exp2((mt - mtw) * c2[k]);
+            rec[2 + 3 * k] = warp_sum(zs[k] * fs);
+            rec[3 + 3 * k] = warp_sum(zt[k] * ft);
+            rec[4 + 3 * k] = warp_sum(a[k] * ft);
+        }
+        if (MSE) rec[5] = warp_sum(sq);
+        float* my_red = red + (par * kWarps + warp) * kRedFloats;
+        if (lane == 0) {
+            reinterpret_cast<float4*>(my_red)[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+            reinterpret_cast<float4*>(my_red)[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+        }
         __syncthreads();
         if (tid == 0) {  // every thread holds its elements in registers: this unit's slots are free
             free_slots += nslots;
             issue_loads();
         }
-        float ms = -INFINITY, mt = -INFINITY;
-#pragma unroll
-        for (int w = 0; w < kConsWarps; ++w) {
-            const float2 r = red_max[w];
-            ms = fmaxf(ms, r.x);
-            mt = fmaxf(mt, r.y);
-        }
-        const float ms2 = ms * c2, mt2 = mt * c2;
 
-        // ---- exponentials (kept in registers), partial sums
-        float zs = 0.f, zt = 0.f, a = 0.f, sq = 0.f;
+        // ---- CTA: every warp merges the 16 warp records (lanes l and l+16 mirror each other)
+        float Ms, Mt, Zs[NL], Zt[NL], A[NL], SQ = 0.f;
+        {
+            const float* q = red + (par * kWarps + (lane & 15)) * kRedFloats;
+            const float4 r0 = reinterpret_cast<const float4*>(q)[0];
+            const float4 r1 = reinterpret_cast<const float4*>(q)[1];
+            const float rr[kRedFloats] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            Ms = max16(rr[0]);
+            Mt = max16(rr[1]);
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            if (v * kCons + tid < nvec) {
+            for (int k = 0; k < NL; ++k) {
+                const float fs = fast_exp2((rr[0] - Ms) * c2[k]);
+                const float ft = fast_exp2((rr[1] - Mt) * c2[k]);
+                Zs[k] = sum16(rr[2 + 3 * k] * fs);
+                Zt[k] = sum16(rr[3 + 3 * k] * ft);
+                A[k] = sum16(rr[4 + 3 * k] * ft);
+            }
+            if (MSE) SQ = sum16(rr[5]);
+        }
+        par ^= 1;
+
+        // ---- rows split over several CTAs: exchange partials through epoch-tagged packets
+        int rown[NL];          // units in this unit's row of loss k
+        long long rowu[NL];    // first unit of that row
+        int rowi[NL];          // row index (for row_kl)
+        rown[0] = x.nch;
+        rowu[0] = u - x.ck;
+        rowi[0] = x.b * p.l[0].G + x.grp;
 #pragma unroll
-                for (int k = 0; k < VE; ++k) {
-                    const int i = v * VE + k;
-                    const float d = t[i] - s[i];
-                    const float es = fast_exp2(fmaf(s[i], c2, -ms2));
-                    const float et = fast_exp2(fmaf(t[i], c2, -mt2));
-                    zs += es;
-                    zt += et;
-                    a = fmaf(et, d, a);
-                    if (MSE) {
-                        sq = fmaf(d, d, sq);
-                    } else {
-                        s[i] = es;
-                        t[i] = et;
+        for (int k = 1; k < NL; ++k) {
+            const int m = p.l[k].m;
+            const int rk = x.grp / m;
+            const int j0 = rk * m;
+            const int j1 = min(j0 + m, p.l[0].G);
+            const int us = unit_start(p, j0);
+            rown[k] = unit_start(p, j1) - us;
+            rowu[k] = (long long)x.b * p.units_per_sample + us;
+            rowi[k] = x.b * p.l[k].G + rk;
+        }
+        bool split = false;
+#pragma unroll
+        for (int k = 0; k < NL; ++k) split = split || rown[k] > 1;
+
+        float Msr[NL], Mtr[NL];
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+            Msr[k] = Ms;
+            Mtr[k] = Mt;
+        }
+        if (split) {
+            if (warp == 0) {
+                // publish this unit's partials: one 8-byte {value, epoch} word per lane
+                {
+                    float val = 0.f;
+#pragma unroll
+                    for (int k = 0; k < NL; ++k) {
+                        if (lane == 6 * k + 0) val = Ms;
+                        if (lane == 6 * k + 1) val = Zs[k];
+                        if (lane == 6 * k + 2) val = Mt;
+                        if (lane == 6 * k + 3) val = Zt[k];
+                        if (lane == 6 * k + 4) val = A[k];
+                    }
+                    if (lane < 6 * NL)
+                        st_relaxed_u64(p.pkt + (size_t)u * kPktWords + lane,
+                                       ((unsigned long long)p.epoch << 32) | __float_as_uint(val));
+                }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < NL; ++k) {
+                    if (rown[k] > 1) {
+                        RowStat acc = rowstat_empty();
+                        for (int j = lane; j < rown[k]; j += 32) {
+                            const unsigned long long* q = p.pkt + (size_t)(rowu[k] + j) * kPktWords + 6 * k;
+                            unsigned long long w[5];
+                            unsigned spins = 0;
+                            for (;;) {
+                                bool ok = true;
+#pragma unroll
+                                for (int i = 0; i < 5; ++i) {
+                                    w[i] = ld_relaxed_u64(q + i);
+                                    ok = ok && (unsigned)(w[i] >> 32) == p.epoch;
+                                }
+                                if (ok) break;
+                                if (++spins > kSpinLimit) {
+                                    atomicExch(&p.ctrl[1], 1u);  // never expected: reported by the host wrapper
+                                    break;
+                                }
+                                __nanosleep(40);
+                            }
+                            RowStat r;
+                            r.ms = __uint_as_float((unsigned)w[0]);
+                            r.zs = __uint_as_float((unsigned)w[1]);
+                            r.mt = __uint_as_float((unsigned)w[2]);
+                            r.zt = __uint_as_float((unsigned)w[3]);
+                            r.a = __uint_as_float((unsigned)w[4]);
+                            acc = rowstat_merge(acc, r, c2[k]);
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            RowStat other;
+                            other.ms = __shfl_xor_sync(0xffffffffu, acc.ms, o);
+                            other.zs = __shfl_xor_sync(0xffffffffu, acc.zs, o);
+                            other.mt = __shfl_xor_sync(0xffffffffu, acc.mt, o);
+                            other.zt = __shfl_xor_sync(0xffffffffu, acc.zt, o);
+                            other.a = __shfl_xor_sync(0xffffffffu, acc.a, o);
+                            acc = rowstat_merge(acc, other, c2[k]);
+                        }
+                        if (lane == 0) {
+                            bcast[8 * k + 0] = acc.ms;
+                            bcast[8 * k + 1] = acc.zs;
+                            bcast[8 * k + 2] = acc.mt;
+                            bcast[8 * k + 3] = acc.zt;
+                            bcast[8 * k + 4] = acc.a;
+                        }
                     }
                 }
             }
-        }
-        zs = warp_sum(zs);
-        zt = warp_sum(zt);
-        a = warp_sum(a);
-        if (MSE) sq = warp_sum(sq);
-        if (lane == 0) red_sum[cwarp] = make_float4(zs, zt, a, sq);
-        __syncthreads();
-        float Zs = 0.f, Zt = 0.f, A = 0.f, SQ = 0.f;
-#pragma unroll
-        for (int w = 0; w < kConsWarps; ++w) {
-            const float4 r = red_sum[w];
-            Zs += r.x;
-            Zt += r.y;
-            A += r.z;
-            SQ += r.w;
-        }
-
-        // ---- rows split over several CTAs: exchange (max, sum) partials through global memory
-        float Ms = ms, Mt = mt, fs = 1.f, ft = 1.f;
-        if (x.nch > 1) {
-            unsigned* rcnt = &p.row_cnt[x.row & (kRowCntRing - 1)];
-            if (tid == 0) {
-                float* slot = p.unit_part + (size_t)u * kPartWords;
-                __stcg(reinterpret_cast<float4*>(slot), make_float4(ms, Zs, mt, Zt));
-                __stcg(slot + 4, A);
-                __threadfence();
-                atomicAdd(rcnt, 1u);
-                unsigned spins = 0;
-                while (ld_acquire_gpu(rcnt) < (unsigned)x.nch) {
-                    if (++spins > kSpinLimit) {
-                        atomicExch(&p.ctrl[1], 1u);  // never expected: reported by the host wrapper
-                        break;
-                    }
-                    __nanosleep(32);
-                }
-            }
             __syncthreads();
-            if (cwarp == 0) {
-                const long long u0 = u - x.ck;
-                Stat ss = {-INFINITY, 0.f}, st = {-INFINITY, 0.f};
-                float aa = 0.f;
-                for (int k = lane; k < x.nch; k += 32) {
-                    const float* q = p.unit_part + (size_t)(u0 + k) * kPartWords;
-                    const float4 v = __ldcg(reinterpret_cast<const float4*>(q));
-                    const float ak = __ldcg(q + 4);
-                    ss = stat_merge(ss, Stat{v.x, v.y}, c2);
-                    const float nm = fmaxf(st.m, v.z);
-                    const float fo = (st.z > 0.f) ? fast_exp2((st.m - nm) * c2) : 0.f;
-                    const float fn = fast_exp2((v.z - nm) * c2);
-                    st.z = st.z * fo + v.w * fn;
-                    aa = aa * fo + ak * fn;
-                    st.m = nm;
-                }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    Stat os, ot;
-                    os.m = __shfl_xor_sync(0xffffffffu, ss.m, o);
-                    os.z = __shfl_xor_sync(0xffffffffu, ss.z, o);
-                    ot.m = __shfl_xor_sync(0xffffffffu, st.m, o);
-                    ot.z = __shfl_xor_sync(0xffffffffu, st.z, o);
-                    const float oa = __shfl_xor_sync(0xffffffffu, aa, o);
-                    ss = stat_merge(ss, os, c2);
-                    const float nm = fmaxf(st.m, ot.m);
-                    const float f1 = (st.z > 0.f) ? fast_exp2((st.m - nm) * c2) : 0.f;
-                    const float f2 = (ot.z > 0.f) ? fast_exp2((ot.m - nm) * c2) : 0.f;
-                    // symmetric form: both partners compute bit-identical results
-                    const float z1 = st.z * f1, z2 = ot.z * f2;
-                    const float a1 = aa * f1, a2 = oa * f2;
-                    st.z = (lane & o) ? (z2 + z1) : (z1 + z2);
-                    aa = (lane & o) ? (a2 + a1) : (a1 + a2);
-                    st.m = nm;
+            for (int k = 0; k < NL; ++k) {
+                if (rown[k] > 1) {
+                    Msr[k] = bcast[8 * k + 0];
+                    Zs[k] = bcast[8 * k + 1];
+                    Mtr[k] = bcast[8 * k + 2];
+                    Zt[k] = bcast[8 * k + 3];
+                    A[k] = bcast[8 * k + 4];
                 }
-                if (lane == 0) {
-                    bcast[0] = ss.m;
-                    bcast[1] = ss.z;
-                    bcast[2] = st.m;
-                    bcast[3] = st.z;
-                    bcast[4] = aa;
-                }
-            }
-            __syncthreads();
-            Ms = bcast[0];
-            Zs = bcast[1];
-            Mt = bcast[2];
-            Zt = bcast[3];
-            A = bcast[4];
-            fs = fast_exp2((ms - Ms) * c2);
-            ft = fast_exp2((mt - Mt) * c2);
-            if (tid == 0) {
-                const unsigned old = atomicAdd(rcnt, 1u);
-                if (old == 2u * (unsigned)x.nch - 1u) atomicExch(rcnt, 0u);  // last one out resets
             }
         }
 
         if (tid == 0) {
-            if (x.ck == 0) {
-                // KL(p||q) = sum p (t - s)/tau - lse_t + lse_s
-                const float kl = p.inv_tau * A / Zt - ((Mt - Ms) * p.inv_tau + (logf(Zt) - logf(Zs)));
-                if (p.row_kl) p.row_kl[x.row] = kl;
-                cta_kl += kl;
+#pragma unroll
+            for (int k = 0; k < NL; ++k) {
+                if (u == rowu[k]) {
+                    // KL(p||q) = sum p (t - s)/tau - lse_t + lse_s
+                    const float kl = p.l[k].inv_tau * A[k] / Zt[k] -
+                                     ((Mtr[k] - Msr[k]) * p.l[k].inv_tau + (logf(Zt[k]) - logf(Zs[k])));
+                    if (p.l[k].row_kl) p.l[k].row_kl[rowi[k]] = kl;
+                    cta_kl[k] += kl;
+                }
             }
             if (MSE) cta_sq += SQ;
         }
 
         // ---- gradient straight from registers
-        const float ks = p.coef * fs / Zs;
-        const float kt = p.coef * ft / Zt;
+        float ks[NL], kt[NL];
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+            ks[k] = coef[k] * fast_exp2((ms - Msr[k]) * c2[k]) / Zs[k];
+            kt[k] = coef[k] * fast_exp2((mt - Mtr[k]) * c2[k]) / Zt[k];
+        }
         T* out = static_cast<T*>(p.dS);
+        const size_t base = ((size_t)x.b * p.C + (size_t)x.grp * p.l[0].g) * p.HW + x.e0;
+        const float ms2 = ms * c2[0], mt2 = mt * c2[0];
+        const bool gathered = p.perm != nullptr;
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
-            const int vi = v * kCons + tid;
-            if (vi < nvec) {
+            const int vi = v * kThreads + tid;
+            if (whole || vi < nvec) {
                 float o[VE];
 #pragma unroll
-                for (int k = 0; k < VE; ++k) {
-                    const int i = v * VE + k;
+                for (int q = 0; q < VE; ++q) {
+                    const int i = v * VE + q;
                     if (MSE) {
-                        const float es = fast_exp2(fmaf(s[i], c2, -ms2));
-                        const float et = fast_exp2(fmaf(t[i], c2, -mt2));
-                        o[k] = fmaf(es, ks, -et * kt) + p.mse_gcoef * (s[i] - t[i]);
+                        const float es = fast_exp2(fmaf(s[i], c2[0], -ms2));
+                        const float et = fast_exp2(fmaf(t[i], c2[0], -mt2));
+                        o[q] = fmaf(es, ks[0], -et * kt[0]) + p.mse_gcoef * (s[i] - t[i]);
+                    } else if (NL > 1) {
+                        o[q] = fmaf(xs[i], ks[0], -xt[i] * kt[0]) + fmaf(s[i], ks[NL - 1], -t[i] * kt[NL - 1]);
                     } else {
-                        o[k] = fmaf(s[i], ks, -t[i] * kt);
+                        o[q] = fmaf(s[i], ks[0], -t[i] * kt[0]);
                     }
                 }
-                const size_t off = row_elem_offset(p, x, x.e0 + vi * VE);
+                const size_t off = gathered ? perm_elem_offset(p, x, x.e0 + vi * VE) : base + (size_t)vi * VE;
                 *reinterpret_cast<vec_t*>(out + off) = E::pack(o);
             }
         }
     }
 
     // ================================ loss: per-CTA partials, last CTA sums them in a fixed order ================================
-    if (cwarp == 0) {
+    if (warp == 0) {
         unsigned ticket = 0;
         if (lane == 0) {
-            __stcg(&p.cta_part[blockIdx.x], cta_kl);
-            __stcg(&p.cta_part[kMaxGrid + blockIdx.x], cta_sq);
+#pragma unroll
+            for (int k = 0; k < NL; ++k) __stcg(&p.cta_part[k * kMaxGrid + blockIdx.x], cta_kl[k]);
+            __stcg(&p.cta_part[kMaxLosses * kMaxGrid + blockIdx.x], cta_sq);
             __threadfence();
             ticket = atomicAdd(&p.ctrl[0], 1u);
         }
         ticket = __shfl_sync(0xffffffffu, ticket, 0);
         if (ticket == gridDim.x - 1) {
             __threadfence();
-            double kl = 0.0, sq = 0.0;
+            double acc[NL + 1];
+#pragma unroll
+            for (int k = 0; k <= NL; ++k) acc[k] = 0.0;
             for (int i = lane; i < (int)gridDim.x; i += 32) {
-                kl += (double)__ldcg(&p.cta_part[i]);
-                sq += (double)__ldcg(&p.cta_part[kMaxGrid + i]);
+#pragma unroll
+                for (int k = 0; k < NL; ++k) acc[k] += (double)__ldcg(&p.cta_part[k * kMaxGrid + i]);
+                acc[NL] += (double)__ldcg(&p.cta_part[kMaxLosses * kMaxGrid + i]);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                kl += __shfl_down_sync(0xffffffffu, kl, o);
-                sq += __shfl_down_sync(0xffffffffu, sq, o);
+#pragma unroll
+                for (int k = 0; k <= NL; ++k) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
             }
             if (lane == 0) {
-                *p.loss = (float)((double)p.loss_scale * kl);
-                if (MSE && p.mse_loss) *p.mse_loss = (float)((double)p.mse_scale * sq);
+#pragma unroll
+                for (int k = 0; k < NL; ++k) *p.l[k].loss = (float)((double)p.l[k].loss_scale * acc[k]);
+                if (MSE && p.mse_loss) *p.mse_loss = (float)((double)p.mse_scale * acc[NL]);
                 atomicExch(&p.ctrl[0], 0u);
             }
         }
@@ -390,7 +560,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) kl_rows_tma_kernel(const Rows
 }
 
 // ====================================================================================================
-// generic path: unit = (sample, logical channel, plane chunk); no alignment requirement
+// generic path (single loss): unit = (sample, logical channel, plane chunk); no alignment requirement
 // ====================================================================================================
 constexpr int kGenThreads = 256;
 
@@ -454,6 +624,7 @@ __global__ void __launch_bounds__(kGenThreads) kl_rows_generic_stats(const RowsP
     __shared__ float scratch[4 * 8];
     const long long u = blockIdx.x;
     const GenUnit x = decode_gen(p, u);
+    const float c2 = p.l[0].c2;
     const T* s = static_cast<const T*>(p.S) + x.off;
     const T* t = static_cast<const T*>(p.T) + x.off;
     float ms = -INFINITY, mt = -INFINITY;
@@ -462,13 +633,13 @@ __global__ void __launch_bounds__(kGenThreads) kl_rows_generic_stats(const RowsP
         mt = fmaxf(mt, E::load(t + i));
     }
     block_max2(ms, mt, scratch);
-    const float ms2 = ms * p.c2, mt2 = mt * p.c2;
+    const float ms2 = ms * c2, mt2 = mt * c2;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};  // zs, zt, a, sq
     for (int i = threadIdx.x; i < x.n; i += kGenThreads) {
         const float a = E::load(s + i), b = E::load(t + i);
         const float d = b - a;
-        const float et = fast_exp2(fmaf(b, p.c2, -mt2));
-        acc[0] += fast_exp2(fmaf(a, p.c2, -ms2));
+        const float et = fast_exp2(fmaf(b, c2, -mt2));
+        acc[0] += fast_exp2(fmaf(a, c2, -ms2));
         acc[1] += et;
         acc[2] = fmaf(et, d, acc[2]);
         acc[3] = fmaf(d, d, acc[3]);
@@ -491,66 +662,53 @@ __global__ void __launch_bounds__(kGenThreads) kl_rows_generic_grad(const RowsPa
     __shared__ float row_stat[8];
     const long long u = blockIdx.x;
     const GenUnit x = decode_gen(p, u);
-    const int grp = x.cl / p.g;
-    const int c0 = grp * p.g;
-    const int g_real = min(p.g, p.C - c0);
+    const float c2 = p.l[0].c2;
+    const int g = p.l[0].g;
+    const int grp = x.cl / g;
+    const int c0 = grp * g;
+    const int g_real = min(g, p.C - c0);
     const long long u0 = ((long long)x.b * p.C + c0) * p.KC;
     const int nparts = g_real * p.KC;
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
-        Stat ss = {-INFINITY, 0.f}, st = {-INFINITY, 0.f};
-        float aa = 0.f;
+        RowStat acc = rowstat_empty();
         for (int k = lane; k < nparts; k += 32) {
             const float* q = p.unit_part + (size_t)(u0 + k) * kPartWords;
-            ss = stat_merge(ss, Stat{q[0], q[1]}, p.c2);
-            const float nm = fmaxf(st.m, q[2]);
-            const float fo = (st.z > 0.f) ? fast_exp2((st.m - nm) * p.c2) : 0.f;
-            const float fn = fast_exp2((q[2] - nm) * p.c2);
-            st.z = st.z * fo + q[3] * fn;
-            aa = aa * fo + q[4] * fn;
-            st.m = nm;
+            acc = rowstat_merge(acc, RowStat{q[0], q[1], q[2], q[3], q[4]}, c2);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            Stat os, ot;
-            os.m = __shfl_xor_sync(0xffffffffu, ss.m, o);
-            os.z = __shfl_xor_sync(0xffffffffu, ss.z, o);
-            ot.m = __shfl_xor_sync(0xffffffffu, st.m, o);
-            ot.z = __shfl_xor_sync(0xffffffffu, st.z, o);
-            const float oa = __shfl_xor_sync(0xffffffffu, aa, o);
-            ss = stat_merge(ss, os, p.c2);
-            const float nm = fmaxf(st.m, ot.m);
-            const float f1 = (st.z > 0.f) ? fast_exp2((st.m - nm) * p.c2) : 0.f;
-            const float f2 = (ot.z > 0.f) ? fast_exp2((ot.m - nm) * p.c2) : 0.f;
-            const float z1 = st.z * f1, z2 = ot.z * f2;
-            const float a1 = aa * f1, a2 = oa * f2;
-            st.z = (lane & o) ? (z2 + z1) : (z1 + z2);
-            aa = (lane & o) ? (a2 + a1) : (a1 + a2);
-            st.m = nm;
+            RowStat other;
+            other.ms = __shfl_xor_sync(0xffffffffu, acc.ms, o);
+            other.zs = __shfl_xor_sync(0xffffffffu, acc.zs, o);
+            other.mt = __shfl_xor_sync(0xffffffffu, acc.mt, o);
+            other.zt = __shfl_xor_sync(0xffffffffu, acc.zt, o);
+            other.a = __shfl_xor_sync(0xffffffffu, acc.a, o);
+            acc = rowstat_merge(acc, other, c2);
         }
         if (lane == 0) {
-            row_stat[0] = ss.m;
-            row_stat[1] = ss.z;
-            row_stat[2] = st.m;
-            row_stat[3] = st.z;
-            row_stat[4] = aa;
+            row_stat[0] = acc.ms;
+            row_stat[1] = acc.zs;
+            row_stat[2] = acc.mt;
+            row_stat[3] = acc.zt;
+            row_stat[4] = acc.a;
         }
     }
     __syncthreads();
     const float Ms = row_stat[0], Zs = row_stat[1], Mt = row_stat[2], Zt = row_stat[3], A = row_stat[4];
     if (threadIdx.x == 0 && u == u0) {
-        const float kl = p.inv_tau * A / Zt - ((Mt - Ms) * p.inv_tau + (logf(Zt) - logf(Zs)));
-        p.row_kl[x.b * p.G + grp] = kl;
+        const float kl = p.l[0].inv_tau * A / Zt - ((Mt - Ms) * p.l[0].inv_tau + (logf(Zt) - logf(Zs)));
+        p.l[0].row_kl[x.b * p.l[0].G + grp] = kl;
     }
-    const float ms2 = Ms * p.c2, mt2 = Mt * p.c2;
-    const float ks = p.coef / Zs, kt = p.coef / Zt;
+    const float ms2 = Ms * c2, mt2 = Mt * c2;
+    const float ks = p.l[0].coef / Zs, kt = p.l[0].coef / Zt;
     const T* s = static_cast<const T*>(p.S) + x.off;
     const T* t = static_cast<const T*>(p.T) + x.off;
     T* o = static_cast<T*>(p.dS) + x.off;
     for (int i = threadIdx.x; i < x.n; i += kGenThreads) {
         const float a = E::load(s + i), b = E::load(t + i);
-        const float es = fast_exp2(fmaf(a, p.c2, -ms2));
-        const float et = fast_exp2(fmaf(b, p.c2, -mt2));
+        const float es = fast_exp2(fmaf(a, c2, -ms2));
+        const float et = fast_exp2(fmaf(b, c2, -mt2));
         E::store(o + i, fmaf(es, ks, -et * kt) + p.mse_gcoef * (a - b));
     }
 }
@@ -559,7 +717,7 @@ __global__ void __launch_bounds__(kGenThreads) kl_rows_generic_grad(const RowsPa
 __global__ void __launch_bounds__(1024) kl_rows_generic_finalize(const RowsParams p, long long n_units) {
     __shared__ double sh[2][32];
     double kl = 0.0, sq = 0.0;
-    for (int i = threadIdx.x; i < p.R; i += 1024) kl += (double)p.row_kl[i];
+    for (int i = threadIdx.x; i < p.l[0].R; i += 1024) kl += (double)p.l[0].row_kl[i];
     if (p.mse_loss)
         for (long long i = threadIdx.x; i < n_units; i += 1024) sq += (double)p.unit_part[(size_t)i * kPartWords + 5];
 #pragma unroll
@@ -578,7 +736,7 @@ __global__ void __launch_bounds__(1024) kl_rows_generic_finalize(const RowsParam
             a += sh[0][w];
             b += sh[1][w];
         }
-        *p.loss = (float)((double)p.loss_scale * a);
+        *p.l[0].loss = (float)((double)p.l[0].loss_scale * a);
         if (p.mse_loss) *p.mse_loss = (float)((double)p.mse_scale * b);
     }
 }
@@ -586,9 +744,9 @@ __global__ void __launch_bounds__(1024) kl_rows_generic_finalize(const RowsParam
 // ====================================================================================================
 // host launchers
 // ====================================================================================================
-template <typename T, bool MSE>
+template <typename T, int NL, bool MSE>
 static cudaError_t launch_tma_t(const RowsParams& p, int grid, bool cooperative, cudaStream_t stream) {
-    auto kern = kl_rows_tma_kernel<T, MSE>;
+    auto kern = kl_rows_tma_kernel<T, NL, MSE>;
     static bool configured = false;  // per instantiation
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmemBytes);
@@ -597,7 +755,7 @@ static cudaError_t launch_tma_t(const RowsParams& p, int grid, bool cooperative,
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(kRowsThreads);
+    cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = kRowsSmemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -610,15 +768,19 @@ static cudaError_t launch_tma_t(const RowsParams& p, int grid, bool cooperative,
 
 cudaError_t launch_kl_rows_tma(const RowsParams& p, bool bf16, int grid, bool cooperative, cudaStream_t stream) {
     const bool mse = p.mse_gcoef != 0.f || p.mse_loss != nullptr;
-    if (bf16) {
-        return mse ? launch_tma_t<__nv_bfloat16, true>(p, grid, cooperative, stream)
-                   : launch_tma_t<__nv_bfloat16, false>(p, grid, cooperative, stream);
+    if (p.nl == 2) {
+        return bf16 ? launch_tma_t<__nv_bfloat16, 2, false>(p, grid, cooperative, stream)
+                    : launch_tma_t<float, 2, false>(p, grid, cooperative, stream);
     }
-    return mse ? launch_tma_t<float, true>(p, grid, cooperative, stream)
-               : launch_tma_t<float, false>(p, grid, cooperative, stream);
+    if (bf16) {
+        return mse ? launch_tma_t<__nv_bfloat16, 1, true>(p, grid, cooperative, stream)
+                   : launch_tma_t<__nv_bfloat16, 1, false>(p, grid, cooperative, stream);
+    }
+    return mse ? launch_tma_t<float, 1, true>(p, grid, cooperative, stream)
+               : launch_tma_t<float, 1, false>(p, grid, cooperative, stream);
 }
 
-int kl_rows_tma_chunk_capacity() { return kChunkCap; }
+int kl_rows_tma_chunk_capacity(int nl) { return kThreads * (kDataRegs / nl); }
 
 cudaError_t launch_kl_rows_generic(const RowsParams& p, bool bf16, cudaStream_t stream) {
     const long long units = (long long)p.B * p.C * p.KC;

@@ -10,7 +10,7 @@ namespace sd {
 // kl_rows.cu
 cudaError_t launch_kl_rows_tma(const RowsParams& p, bool bf16, int grid, bool cooperative, cudaStream_t stream);
 cudaError_t launch_kl_rows_generic(const RowsParams& p, bool bf16, cudaStream_t stream);
-int kl_rows_tma_chunk_capacity();
+int kl_rows_tma_chunk_capacity(int n_losses);
 
 // kl_pixels.cu   (mapS/mapT point at CUtensorMap objects)
 cudaError_t launch_kl_pixels_tma(const void* mapS, const void* mapT, const PixParams& p, bool bf16, int grid,
@@ -24,5 +24,7 @@ int kl_pixels_tile_pixels(bool bf16);
 cudaError_t launch_mse(const void* S, const void* T, void* dS, float* loss, float* partials, long long n, bool bf16,
                        float gcoef, float scale, int grid, cudaStream_t stream);
 cudaError_t launch_scale_grad(void* dS, long long n, bool bf16, const float* g, int grid, cudaStream_t stream);
+cudaError_t launch_scale_grad2(void* dS, long long n, bool bf16, const float* g0, const float* g1, unsigned* flag,
+                               int grid, cudaStream_t stream);
 
 }  // namespace sd

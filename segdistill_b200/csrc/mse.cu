@@ -97,6 +97,38 @@ __global__ void __launch_bounds__(256) scale_grad_kernel(T* __restrict__ x, long
     for (long long i = done + gid; i < n; i += stride) E::store(x + i, E::load(x + i) * gv);
 }
 
+// Backward of a fused two-loss launch: dS was computed for d(total)/d(loss_k) == 1.  When the two
+// upstream gradients are equal (the loss terms enter the total as a plain sum, possibly times one
+// loss scale) dS is scaled in place and *flag = 0; otherwise *flag = 1 and the caller's conditional
+// re-run of the fused kernel (run_if = flag) rebuilds dS with the individual factors.
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) scale_grad2_kernel(T* __restrict__ x, long long n, const float* __restrict__ g0,
+                                                          const float* __restrict__ g1, unsigned* __restrict__ flag) {
+    using E = Elem<T>;
+    using vec_t = typename E::vec_t;
+    constexpr int VE = E::kVec;
+    const float a = *g0, b = *g1;
+    const bool uniform = a == b;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *flag = uniform ? 0u : 1u;
+    if (!uniform || a == 1.0f) return;
+    const long long stride = (long long)gridDim.x * 256;
+    const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+    long long done = 0;
+    if (VEC) {
+        const long long nvec = n / VE;
+        vec_t* vx = reinterpret_cast<vec_t*>(x);
+        for (long long i = gid; i < nvec; i += stride) {
+            float v[VE];
+            E::unpack(vx[i], v);
+#pragma unroll
+            for (int k = 0; k < VE; ++k) v[k] *= a;
+            vx[i] = E::pack(v);
+        }
+        done = nvec * VE;
+    }
+    for (long long i = done + gid; i < n; i += stride) E::store(x + i, E::load(x + i) * a);
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 cudaError_t launch_mse(const void* S, const void* T, void* dS, float* loss, float* partials, long long n, bool bf16,
@@ -129,6 +161,21 @@ cudaError_t launch_scale_grad(void* dS, long long n, bool bf16, const float* g, 
         auto x = static_cast<float*>(dS);
         if (vec) scale_grad_kernel<float, true><<<grid, 256, 0, stream>>>(x, n, g);
         else scale_grad_kernel<float, false><<<grid, 256, 0, stream>>>(x, n, g);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scale_grad2(void* dS, long long n, bool bf16, const float* g0, const float* g1, unsigned* flag,
+                               int grid, cudaStream_t stream) {
+    const bool vec = aligned16(dS);
+    if (bf16) {
+        auto x = static_cast<__nv_bfloat16*>(dS);
+        if (vec) scale_grad2_kernel<__nv_bfloat16, true><<<grid, 256, 0, stream>>>(x, n, g0, g1, flag);
+        else scale_grad2_kernel<__nv_bfloat16, false><<<grid, 256, 0, stream>>>(x, n, g0, g1, flag);
+    } else {
+        auto x = static_cast<float*>(dS);
+        if (vec) scale_grad2_kernel<float, true><<<grid, 256, 0, stream>>>(x, n, g0, g1, flag);
+        else scale_grad2_kernel<float, false><<<grid, 256, 0, stream>>>(x, n, g0, g1, flag);
     }
     return cudaGetLastError();
 }

@@ -9,66 +9,95 @@ namespace sd {
 // Every workspace, whatever the op or shape, starts with the same COUNTER ARENA: integer words that
 // must be zero between launches (each kernel leaves them zero again).  Nothing else is ever stored
 // there, so one workspace can serve any sequence of ops and shapes on a stream; the regions behind
-// the arena hold floats that are always written before they are read within a launch.
-constexpr int kCtrlWords = 64;     // [0] completion ticket, [1] error flag (spin time-out)
-constexpr int kRowCntRing = 4096;  // split-row arrival counters, indexed by row % ring (rows in flight
-                                   // at once are bounded by the persistent grid size, <= kMaxGrid)
-constexpr size_t kArenaBytes = sizeof(unsigned) * (kCtrlWords + kRowCntRing);
-constexpr int kMaxGrid = 1024;     // upper bound on persistent-grid size (per-CTA partial slots)
+// the arena hold data that is always written before it is read within a launch, or that is
+// validated by a per-launch epoch tag (the unit packets of the split-row exchange).
+constexpr int kCtrlWords = 64;  // [0] completion ticket, [1] error flag (spin time-out)
+constexpr size_t kArenaBytes = sizeof(unsigned) * kCtrlWords;
+
+constexpr int kMaxGrid = 1024;       // upper bound on persistent-grid size (per-CTA partial slots)
 constexpr int kGenericChunk = 4096;  // elements of one channel plane per generic work unit
-constexpr int kPartWords = 8;      // floats per published unit partial
+constexpr int kPartWords = 8;        // floats per published unit partial (generic kernels)
+constexpr int kMaxLosses = 2;        // softmax-KL losses fused over one (S, T) pair in one pass
+constexpr int kPktWords = 16;        // 8-byte {value, epoch} words per unit packet (6 per loss, padded)
+constexpr int kChunkCapMin = 8192;   // smallest chunk capacity any TMA kernel instantiation uses
+
+// one softmax-KL loss over rows of `g` consecutive (gathered) channels x HW
+struct RowLoss {
+    int g;             // channels per row
+    int m;             // rows of l[0] per row of this loss (1 for l[0] itself)
+    int G;             // rows per sample = ceil(C/g)
+    int R;             // B*G
+    float c2;          // log2(e)/tau
+    float inv_tau;
+    float coef;        // grad_scale*alpha/(R*tau)
+    float loss_scale;  // alpha/R
+    float* loss;       // [1]
+    float* row_kl;     // [R] or null
+};
 
 // ---------------------------------------------------------------- rows (CD / CGD)
 struct RowsParams {
     const void* S;
     const void* T;
     void* dS;
-    float* row_kl;        // [R] (user buffer or workspace)
-    float* loss;          // [1]
+    const int32_t* perm;  // [C] or null (single-loss launches only)
+    int B, C, HW;
+    int nl;               // fused losses (1..kMaxLosses); l[0] has the smallest rows and every row of
+                          // l[k] is a union of whole rows of l[0]  (l[k].g % l[0].g == 0)
+    RowLoss l[kMaxLosses];
     float* mse_loss;      // [1] or null
-    const int32_t* perm;  // [C] or null
-    int B, C, HW, g;
-    int G;                // groups (rows) per sample = ceil(C/g)
-    int G_full;           // complete groups per sample = C/g
-    int g_last;           // channels in the ragged last group (0 = none)
-    int R;                // B*G
-    float c2;             // log2(e)/tau
-    float inv_tau;
-    float coef;           // grad_scale*alpha/(R*tau)
-    float loss_scale;     // alpha/R
     float mse_gcoef;      // grad_scale*2*w/numel   (0 = MSE off)
     float mse_scale;      // w/numel
-    // TMA kernel work decomposition: a unit is one chunk of one row
+    // TMA kernel work decomposition: a unit is one chunk of one row of l[0]
+    int G_full;           // complete l[0] rows per sample = C/g0
+    int g_last;           // channels in the ragged last l[0] row (0 = none)
     int chunk_elems;      // logical row elements per chunk (multiple of the vector width)
-    int nch_full;         // chunks per complete row
-    int nch_last;         // chunks per ragged row
+    int nch_full;         // chunks per complete l[0] row
+    int nch_last;         // chunks per ragged l[0] row
     int units_per_sample;
     long long total_units;
+    unsigned epoch;       // tag of this launch's unit packets (never 0)
+    // backward re-runs: device scalars d(total)/d(loss_k) folded into the gradient (null = 1), and a
+    // device flag that cancels the launch when it reads 0
+    const float* grad_out[kMaxLosses];
+    const unsigned* run_if;
     // generic kernel decomposition: unit = (b, logical channel, plane chunk)
     int KC;               // chunks per channel plane
     // workspace
     unsigned* ctrl;
-    float* cta_part;      // [2][kMaxGrid]
-    unsigned* row_cnt;    // [kRowCntRing]
-    float* unit_part;     // [units][kPartWords]
+    float* cta_part;            // [kMaxLosses + 1][kMaxGrid]
+    unsigned long long* pkt;    // [TMA units][kPktWords]
+    float* unit_part;           // [generic units][kPartWords]
 };
 
+inline long long tma_units_upper(long long B, long long C, long long HW, long long g) {
+    if (g > C) g = C;
+    const long long full = C / g, rest = C % g;
+    const long long per_sample = full * ((g * HW + kChunkCapMin - 1) / kChunkCapMin) +
+                                 (rest ? (rest * HW + kChunkCapMin - 1) / kChunkCapMin : 0);
+    return B * per_sample;
+}
+
 struct RowsWorkspace {
-    size_t off_ctrl, off_rowcnt, off_cta, off_rowkl, off_unit, bytes;
+    size_t off_ctrl, off_cta, off_rowkl, off_unit, bytes;
 };
+// g = the smallest group size of the fused losses
 inline RowsWorkspace rows_workspace_layout(long long B, long long C, long long HW, long long g) {
     RowsWorkspace w;
+    if (g > C) g = C;
     const long long G = (C + g - 1) / g;
     const long long R = B * G;
     const long long KC = (HW + kGenericChunk - 1) / kGenericChunk;
-    const long long units = B * C * KC;  // >= number of TMA units as well
+    const long long gen_units = B * C * KC;
     size_t o = 0;
-    w.off_ctrl = o;   o += sizeof(unsigned) * kCtrlWords;
-    w.off_rowcnt = o; o += sizeof(unsigned) * kRowCntRing;   // == kArenaBytes
-    w.off_cta = o;    o += sizeof(float) * 2 * kMaxGrid;
-    w.off_rowkl = o;  o += sizeof(float) * (size_t)R;
-    o = (o + 31) & ~(size_t)31;
-    w.off_unit = o;   o += sizeof(float) * kPartWords * (size_t)units;
+    w.off_ctrl = o;   o += kArenaBytes;
+    w.off_cta = o;    o += sizeof(float) * (kMaxLosses + 1) * kMaxGrid;
+    w.off_rowkl = o;  o += sizeof(float) * (size_t)R * kMaxLosses;
+    o = (o + 127) & ~(size_t)127;
+    w.off_unit = o;
+    const size_t gen_bytes = sizeof(float) * kPartWords * (size_t)gen_units;
+    const size_t tma_bytes = sizeof(unsigned long long) * kPktWords * (size_t)tma_units_upper(B, C, HW, g);
+    o += gen_bytes > tma_bytes ? gen_bytes : tma_bytes;
     w.bytes = (o + 255) & ~(size_t)255;
     return w;
 }

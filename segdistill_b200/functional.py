@@ -46,6 +46,45 @@ class _KLRows(torch.autograd.Function):
         return (_finish_backward(ctx, grad_output),) + (None,) * 8
 
 
+class _KLRowsMulti(torch.autograd.Function):
+    """Two channel-mode KL losses on one pair, one kernel: returns both scalars; dS is their summed gradient.
+
+    dS is built in forward for upstream gradients of 1.  Backward: if both upstream gradients are equal
+    (the usual plain sum, possibly times a loss scale) dS is scaled in place on the device; if they differ,
+    a flag set by that same kernel lets a second launch of the fused kernel rebuild dS with the individual
+    factors - no host synchronisation either way.
+    """
+
+    @staticmethod
+    def forward(ctx, x_student, x_teacher, g0, tau0, alpha0, g1, tau1, alpha1):
+        losses, ds = _cabi.kl_rows_multi(x_student, x_teacher, (g0, g1), (tau0, tau1), (alpha0, alpha1))
+        need_grad = x_student.requires_grad
+        ctx.ds = ds if need_grad else None
+        ctx.cfg = ((g0, g1), (tau0, tau1), (alpha0, alpha1))
+        ctx.in_dtype, ctx.in_shape = x_student.dtype, x_student.shape
+        if need_grad:
+            ctx.save_for_backward(x_student, x_teacher)
+        return losses[0], losses[1]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, go0, go1):
+        ds = ctx.ds
+        ctx.ds = None
+        if ds is None:
+            return (None,) * 8
+        dev = ds.device
+        go0 = go0.detach().to(device=dev, dtype=torch.float32).reshape(1)
+        go1 = go1.detach().to(device=dev, dtype=torch.float32).reshape(1)
+        flag = _cabi.scale_grad2_(ds, go0, go1)
+        x_student, x_teacher = ctx.saved_tensors
+        groups, taus, alphas = ctx.cfg
+        _cabi.kl_rows_multi(x_student, x_teacher, groups, taus, alphas, grad_outputs=(go0, go1), run_if=flag, ds=ds)
+        if ds.dtype != ctx.in_dtype:
+            ds = ds.to(ctx.in_dtype)
+        return (ds.view(ctx.in_shape),) + (None,) * 7
+
+
 class _KLPixels(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_student, x_teacher, tau, alpha, at_weight, algo):
@@ -113,6 +152,12 @@ def kl_rows_mse_loss(x_student, x_teacher, group=1, tau=1.0, alpha=1.0, mse_weig
     """Fused CWD + feature MSE on the same pair: returns (total, kl_part, mse_part); only total carries grad."""
     return _KLRows.apply(x_student, x_teacher, int(group), float(tau), float(alpha), perm, float(mse_weight),
                          _cabi.ALGOS[algo], None)
+
+
+def kl_rows_pair_loss(x_student, x_teacher, group0, tau0, alpha0, group1, tau1, alpha1):
+    """Two channel-mode KL losses over the same pair in one pass; returns (loss0, loss1)."""
+    return _KLRowsMulti.apply(x_student, x_teacher, int(group0), float(tau0), float(alpha0),
+                              int(group1), float(tau1), float(alpha1))
 
 
 def kl_pixels_loss(x_student, x_teacher, tau=1.0, alpha=1.0, at_weight=0.0, algo='auto'):

@@ -79,31 +79,80 @@ class KLDLoss(nn.Module):
         return F.interpolate(x, size=tuple(gt.shape[2:]), mode=self.resize_config['mode'],
                              align_corners=self.resize_config['align_corners'])
 
-    def forward(self, x_student, x_teacher, gt=None, n_iter=0):
+    # -- the host-side half of a call: schedules, resize, shuffle draw (same order as the reference :96-106)
+    def plan(self, x_student, x_teacher, gt=None, n_iter=0, resized=None):
+        """Everything ``forward`` decides on the host, without launching: a dict the dispatcher can
+        inspect to batch two entries that hook the same tensors into one kernel.  ``resized`` is an
+        optional cache {(id(tensor), size): resized tensor} shared between the entries of one step."""
         self._update_alpha(n_iter)
         if self.resize_config:
-            x_student, x_teacher = self._resized(x_student, gt), self._resized(x_teacher, gt)
+            x_student = self._resized_cached(x_student, gt, resized)
+            x_teacher = self._resized_cached(x_teacher, gt, resized)
         perm = None
         if self.shuffle_config and n_iter % self.shuffle_config['interval'] == 0:
             perm = torch.randperm(x_student.shape[1])      # same draw as the reference (:39)
         self.last_perm = perm
-        if self.alpha == 0:
-            return SF.zero_loss(x_student)
-
         tc = self.transform_config
-        kind = tc['loss_type'] if tc else None
+        return {'student': x_student, 'teacher': x_teacher, 'perm': perm, 'alpha': self.alpha, 'tau': self.tau,
+                'kind': tc['loss_type'] if tc else None, 'group': tc.get('group_size') if tc else None,
+                'algo': self.algo}
+
+    def _resized_cached(self, x, gt, cache):
+        if cache is None or gt is None:
+            return self._resized(x, gt)
+        key = (id(x), tuple(gt.shape[2:]), self.resize_config['mode'], self.resize_config['align_corners'])
+        if key not in cache:
+            cache[key] = self._resized(x, gt)
+        return cache[key]
+
+    @staticmethod
+    def run(plan):
+        x_student, x_teacher = plan['student'], plan['teacher']
+        if plan['alpha'] == 0:
+            return SF.zero_loss(x_student)
+        kind = plan['kind']
         if kind == 'pixel':
             # softmax over all channels of a pixel: a channel permutation changes nothing
-            loss = SF.kl_pixels_loss(x_student, x_teacher, tau=self.tau, alpha=self.alpha, algo=self.algo)
-        elif kind == 'channel':
-            loss = SF.kl_rows_loss(x_student, x_teacher, group=tc['group_size'], tau=self.tau,
-                                   alpha=self.alpha, perm=perm, algo=self.algo)
-        else:
-            # no transform: softmax over the last dim of the 4-D maps; rows = (b, c, h)
-            lead = x_student.numel() // x_student.shape[-1]
-            loss = SF.kl_rows_loss(x_student, x_teacher, group=1, tau=self.tau, alpha=self.alpha,
-                                   algo=self.algo, bchw=(1, lead, x_student.shape[-1]))
-        return loss
+            return SF.kl_pixels_loss(x_student, x_teacher, tau=plan['tau'], alpha=plan['alpha'], algo=plan['algo'])
+        if kind == 'channel':
+            return SF.kl_rows_loss(x_student, x_teacher, group=plan['group'], tau=plan['tau'],
+                                   alpha=plan['alpha'], perm=plan['perm'], algo=plan['algo'])
+        # no transform: softmax over the last dim of the 4-D maps; rows = (b, c, h)
+        lead = x_student.numel() // x_student.shape[-1]
+        return SF.kl_rows_loss(x_student, x_teacher, group=1, tau=plan['tau'], alpha=plan['alpha'],
+                               algo=plan['algo'], bchw=(1, lead, x_student.shape[-1]))
+
+    @staticmethod
+    def can_fuse(pa, pb):
+        """Two planned calls that one two-loss launch can serve: channel mode on the very same (resized)
+        tensors, no shuffle this step, non-zero weights, nested rows, default kernel selection."""
+        if pa['kind'] != 'channel' or pb['kind'] != 'channel':
+            return False
+        if pa['student'] is not pb['student'] or pa['teacher'] is not pb['teacher']:
+            return False
+        if pa['perm'] is not None or pb['perm'] is not None or pa['alpha'] == 0 or pb['alpha'] == 0:
+            return False
+        if pa['algo'] != 'auto' or pb['algo'] != 'auto':
+            return False
+        x = pa['student']
+        if x.dim() != 4 or x.dtype not in (torch.float32, torch.bfloat16) or not x.is_cuda:
+            return False
+        from . import _cabi
+        return _cabi.multi_supported(x.shape, (pa['group'], pb['group']), x.element_size())
+
+    @staticmethod
+    def run_pair(pa, pb):
+        """(loss_a, loss_b) of two fusable plans from ONE pass over the maps; falls back to two launches
+        when the library declines the layout (rows too long to keep every chunk co-resident)."""
+        from . import _cabi
+        try:
+            return SF.kl_rows_pair_loss(pa['student'], pa['teacher'], pa['group'], pa['tau'], pa['alpha'],
+                                        pb['group'], pb['tau'], pb['alpha'])
+        except _cabi.SegDistillUnsupported:
+            return KLDLoss.run(pa), KLDLoss.run(pb)
+
+    def forward(self, x_student, x_teacher, gt=None, n_iter=0):
+        return self.run(self.plan(x_student, x_teacher, gt, n_iter))
 
 
 def _bilinear():

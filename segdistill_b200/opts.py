@@ -49,6 +49,8 @@ class Extractor(nn.Module):
 
 
 class DistillationLoss(nn.Module):
+    batch_pairs = True      # serve two KLD entries on the same tensors with one launch when possible
+
     def __init__(self, distillation):
         super().__init__()
         self.distillation = distillation
@@ -59,8 +61,29 @@ class DistillationLoss(nn.Module):
         self.criteria = nn.ModuleList(crits)
 
     def forward(self, student_features, teacher_features, gt_semantic_seg, step, student=None, teacher=None):
+        """Same results and key names as the reference loop (:87-112).  One difference in HOW: the host-side
+        half of every KLD criterion (schedules, resize, shuffle draw) runs first, in entry order, so that two
+        entries hooking the very same tensors (e.g. CD + CGD on the logits) can be served by one two-loss
+        kernel launch - one read of the maps, one write of the summed gradient."""
         out = {}
-        for entry in self.distillation:
+        plans, resized = {}, {}
+        for i, entry in enumerate(self.distillation):
+            crit = entry['criterion']
+            if isinstance(entry['student_layer'], list) or not isinstance(crit, _losses.KLDLoss):
+                continue
+            plans[i] = crit.plan(student_features[entry['student_layer']], teacher_features[entry['teacher_layer']],
+                                 gt_semantic_seg, step, resized)
+        results, pending = {}, list(plans)
+        while pending:
+            i = pending.pop(0)
+            mate = next((j for j in pending if _losses.KLDLoss.can_fuse(plans[i], plans[j])), None) \
+                if self.batch_pairs else None
+            if mate is None:
+                results[i] = _losses.KLDLoss.run(plans[i])
+            else:
+                pending.remove(mate)
+                results[i], results[mate] = _losses.KLDLoss.run_pair(plans[i], plans[mate])
+        for i, entry in enumerate(self.distillation):
             s_name, t_name = entry['student_layer'], entry['teacher_layer']
             crit = entry['criterion']
             if isinstance(s_name, list):
@@ -70,7 +93,10 @@ class DistillationLoss(nn.Module):
                             student, teacher, gt_semantic_seg, step)
                 out[f"loss_{s_name[0]}<->{t_name}_{entry['loss_name']}"] = loss
                 continue
-            loss = crit(student_features[s_name], teacher_features[t_name], gt_semantic_seg, step)
+            if i in results:
+                loss = results[i]
+            else:
+                loss = crit(student_features[s_name], teacher_features[t_name], gt_semantic_seg, step)
             cfg = entry['loss_config'][0] if isinstance(entry['loss_config'], tuple) else entry['loss_config']
             info = cfg.get('transform_config', 'other') if isinstance(cfg, dict) else 'other'
             out[f'loss_{s_name}<->{t_name}_{info}'] = loss

@@ -297,6 +297,89 @@ def test_dispatcher_end_to_end():
     assert logs['loss'] == pytest.approx(r1[0] + r2[0], rel=1e-5)
 
 
+# ------------------------------------------------------------------ two losses on one pair, one launch
+PAIR_CASES = [
+    ((2, 150, 64, 64), dict(group_size=1, alpha=1, tau=1), dict(group_size=10, alpha=3, tau=2)),     # CD + CGD (cfg5)
+    ((4, 64, 64, 64), dict(group_size=10, alpha=3, tau=2), dict(group_size=1, alpha=1, tau=1)),      # ragged CGD rows
+    ((2, 32, 32, 32), dict(group_size=5, alpha=2, tau=3), dict(group_size=10, alpha=1, tau=0.5)),    # both ragged
+    ((2, 32, 48, 48), dict(group_size=3, alpha=1, tau=1), dict(group_size=150, alpha=2, tau=4)),     # g >= C: whole sample
+    ((1, 20, 128, 128), dict(group_size=1, alpha=1, tau=1), dict(group_size=10, alpha=3, tau=2)),    # every row split
+]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('case', range(len(PAIR_CASES)))
+def test_two_losses_one_launch(case, dtype):
+    shape, ka, kb = PAIR_CASES[case]
+    s, t = seeded_pair(shape, seed=100 + case, scale=1.5, dtype=dtype)
+    ra = _oracle_run('CGDLoss', ka, s, t, shape[2:], 1)
+    rb = _oracle_run('CGDLoss', kb, s, t, shape[2:], 1)
+    ca, cb = sd.CGDLoss(**ka), sd.CGDLoss(**kb)
+    x = s.to(dev()).requires_grad_(True)
+    tg = t.to(dev())
+    pa, pb = ca.plan(x, tg, None, 1), cb.plan(x, tg, None, 1)
+    assert sd.KLDLoss.can_fuse(pa, pb)
+    la, lb = sd.KLDLoss.run_pair(pa, pb)
+    assert _cabi.last_kernel() == 'kl_rows_tma_kernel(2 losses)'
+    (la + lb).backward()
+    torch.cuda.synchronize()
+    assert _cabi.workspace_error_flag() == 0
+    lt = 2e-5 if dtype == torch.bfloat16 else LOSS_RTOL
+    gt_ = BF16_GRAD_RTOL if dtype == torch.bfloat16 else GRAD_RTOL
+    assert rel_err(la.item(), ra[0]) <= lt and rel_err(lb.item(), rb[0]) <= lt
+    _assert_close(la.item() + lb.item(), x.grad.float().cpu(), ra[0] + rb[0], ra[1] + rb[1], loss_rtol=lt, grad_rtol=gt_)
+
+
+@pytest.mark.parametrize('w', [(512.0, 512.0), (2.0, 5.0), (1.0, 0.0)])
+def test_two_losses_upstream_gradients(w):
+    """Equal upstream gradients scale dS in place; different ones trigger the conditional re-run."""
+    shape, ka, kb = PAIR_CASES[0]
+    s, t = seeded_pair(shape, seed=77)
+    ra = _oracle_run('CGDLoss', ka, s, t, shape[2:], 1)
+    rb = _oracle_run('CGDLoss', kb, s, t, shape[2:], 1)
+    x = s.to(dev()).requires_grad_(True)
+    tg = t.to(dev())
+    la, lb = sd.KLDLoss.run_pair(sd.CGDLoss(**ka).plan(x, tg, None, 1), sd.CGDLoss(**kb).plan(x, tg, None, 1))
+    (w[0] * la + w[1] * lb).backward()
+    torch.cuda.synchronize()
+    ref_grad = w[0] * ra[1] + w[1] * rb[1]
+    assert (x.grad.cpu() - ref_grad).abs().max().item() <= GRAD_RTOL * ref_grad.abs().max().item()
+
+
+def test_dispatcher_batches_entries_on_the_same_tensors():
+    """decode_head and decode_head.linear_pred return the same tensor object: CD on one, CGD on the other."""
+    cfg = [{'student_layer': 'decode_head.linear_pred', 'teacher_layer': 'decode_head.linear_pred',
+            'loss_name': 'CGDLoss', 'loss_config': {'group_size': 10, 'alpha': 3, 'tau': 2}},
+           {'student_layer': 'decode_head', 'teacher_layer': 'decode_head', 'loss_name': 'CDLoss', 'loss_config': {}}]
+    d = sd.DistillationLoss(cfg)
+    s, t = seeded_pair((2, 150, 64, 64), seed=44)
+    x = s.to(dev()).requires_grad_(True)
+    tg = t.to(dev())
+    gt = torch.zeros(2, 1, 64, 64, dtype=torch.long, device=dev())
+    before = _cabi.launch_count()
+    out = d({'decode_head.linear_pred': x, 'decode_head': x}, {'decode_head.linear_pred': tg, 'decode_head': tg},
+            gt, 1, None, None)
+    assert _cabi.launch_count() - before == 1 and _cabi.last_kernel() == 'kl_rows_tma_kernel(2 losses)'
+    assert list(out) == ['loss_decode_head.linear_pred<->decode_head.linear_pred_other',
+                         'loss_decode_head<->decode_head_other']
+    sum(out.values()).backward()
+    r1 = _oracle_run('CGDLoss', {}, s, t, (64, 64), 1)
+    r2 = _oracle_run('CDLoss', {}, s, t, (64, 64), 1)
+    vals = [v.item() for v in out.values()]
+    assert rel_err(vals[0], r1[0]) <= LOSS_RTOL and rel_err(vals[1], r2[0]) <= LOSS_RTOL
+    _assert_close(sum(vals), x.grad.cpu(), r1[0] + r2[0], r1[1] + r2[1])
+    # shuffle step of CGD (n_iter % 1000 == 0): not fusable, two launches, same numbers as the reference
+    torch.manual_seed(5)
+    perm = torch.randperm(150)
+    x2 = s.to(dev()).requires_grad_(True)
+    torch.manual_seed(5)
+    out2 = d({'decode_head.linear_pred': x2, 'decode_head': x2}, {'decode_head.linear_pred': tg, 'decode_head': tg},
+             gt, 2000, None, None)
+    sum(out2.values()).backward()
+    r1s = _oracle_run('CGDLoss', {}, s, t, (64, 64), 2000, perm=perm)
+    _assert_close(sum(v.item() for v in out2.values()), x2.grad.cpu(), r1s[0] + r2[0], r1s[1] + r2[1])
+
+
 def test_c_abi_error_codes_on_device():
     lib = _cabi.load()
     assert lib.sd_device_check() == 0
