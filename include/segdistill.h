@@ -60,11 +60,14 @@ extern "C" {
 #define SD_F32  0
 #define SD_BF16 1
 
-/* algo: AUTO picks the TMA-staged register-resident kernel when the layout allows it
- * (16-byte aligned rows) and the plain multi-pass kernel otherwise. */
+/* algo: AUTO picks a TMA-staged kernel when the layout allows it (16-byte aligned rows): the
+ * register-resident single pass for rows of up to 16384 elements, the streaming two-phase kernel for
+ * longer rows and for two fused losses; the plain multi-pass kernel otherwise.  TMA = AUTO without
+ * the fallback; STREAM forces the two-phase kernel (rows only). */
 #define SD_ALGO_AUTO    0
 #define SD_ALGO_GENERIC 1
 #define SD_ALGO_TMA     2
+#define SD_ALGO_STREAM  3
 
 /* argument errors */
 #define SD_OK               0

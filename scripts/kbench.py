@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Kernel-level timings through the C ABI (no autograd, no modules): CUDA events over back-to-back launches.
+
+    python scripts/kbench.py [--iters 50] [--only cd_f32,fused_f32]
+Prints one line per case: microseconds per launch, achieved GB/s on the algorithmic bytes
+(read S + read T + write dS) and the fraction of the measured HBM peak.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from segdistill_b200 import _cabi  # noqa: E402
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+    except Exception:
+        return 6650.0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--iters', type=int, default=50)
+    ap.add_argument('--only', default='')
+    a = ap.parse_args()
+    dev = torch.device('cuda', 0)
+    pk = peak()
+
+    def pair(shape, dtype):
+        g = torch.Generator(device=dev).manual_seed(0)
+        return (torch.randn(shape, device=dev, generator=g).to(dtype),
+                torch.randn(shape, device=dev, generator=g).to(dtype))
+
+    L = (16, 150, 128, 128)
+    cases = {
+        'cd_f32': (L, torch.float32, lambda s, t: _cabi.kl_rows(s, t, group=1)),
+        'cd_bf16': (L, torch.bfloat16, lambda s, t: _cabi.kl_rows(s, t, group=1)),
+        'cgd10_f32': (L, torch.float32, lambda s, t: _cabi.kl_rows(s, t, group=10, tau=2.0, alpha=3.0)),
+        'cgd10_bf16': (L, torch.bfloat16, lambda s, t: _cabi.kl_rows(s, t, group=10, tau=2.0, alpha=3.0)),
+        'fused_f32': (L, torch.float32, lambda s, t: _cabi.kl_rows_multi(s, t, (10, 1), (2.0, 1.0), (3.0, 1.0))),
+        'fused_bf16': (L, torch.bfloat16, lambda s, t: _cabi.kl_rows_multi(s, t, (10, 1), (2.0, 1.0), (3.0, 1.0))),
+        'pd_f32': (L, torch.float32, lambda s, t: _cabi.kl_pixels(s, t)),
+        'pd_bf16': (L, torch.bfloat16, lambda s, t: _cabi.kl_pixels(s, t)),
+        'cd_512ch_f32': ((16, 512, 64, 64), torch.float32, lambda s, t: _cabi.kl_rows(s, t, group=1, tau=4.0)),
+        'cd+mse_512ch_f32': ((16, 512, 64, 64), torch.float32,
+                             lambda s, t: _cabi.kl_rows(s, t, group=1, tau=4.0, mse_weight=1.0)),
+        'mse_512ch_f32': ((16, 512, 64, 64), torch.float32, lambda s, t: _cabi.mse(s, t)),
+        'cd_cfg1_f32': ((2, 150, 64, 64), torch.float32, lambda s, t: _cabi.kl_rows(s, t, group=1)),
+        'cgd150_f32': ((16, 150, 64, 64), torch.float32, lambda s, t: _cabi.kl_rows(s, t, group=150, tau=2.0)),
+    }
+    only = [x for x in a.only.split(',') if x]
+    for name, (shape, dtype, fn) in cases.items():
+        if only and name not in only:
+            continue
+        s, t = pair(shape, dtype)
+        for _ in range(5):
+            fn(s, t)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.iters):
+            fn(s, t)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / a.iters * 1e3
+        nbytes = 3 * s.numel() * s.element_size()
+        gbs = nbytes / us / 1e3
+        print(f'{name:20s} {us:9.1f} us  {gbs:8.1f} GB/s  {gbs / pk:6.3f} of measured peak   [{_cabi.last_kernel()}]',
+              flush=True)
+        assert _cabi.workspace_error_flag() == 0
+        del s, t
+
+
+if __name__ == '__main__':
+    main()

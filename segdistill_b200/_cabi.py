@@ -17,8 +17,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, 'libsegdistill_sm100.so')
 
 SD_F32, SD_BF16 = 0, 1
-ALGO_AUTO, ALGO_GENERIC, ALGO_TMA = 0, 1, 2
-ALGOS = {'auto': ALGO_AUTO, 'generic': ALGO_GENERIC, 'tma': ALGO_TMA}
+ALGO_AUTO, ALGO_GENERIC, ALGO_TMA, ALGO_STREAM = 0, 1, 2, 3
+ALGOS = {'auto': ALGO_AUTO, 'generic': ALGO_GENERIC, 'tma': ALGO_TMA, 'stream': ALGO_STREAM}
 
 # every symbol include/segdistill.h declares (tests check the library exports all of them)
 EXPORTS = (

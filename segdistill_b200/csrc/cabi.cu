@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <utility>
 
@@ -113,6 +114,18 @@ size_t sd_kl_rows_workspace_bytes(int B, int C, int HW, int group) {
 
 namespace {
 
+// phase-2 lag of the streaming kernel, in units (SEGDISTILL_STREAM_DELAY overrides; tuning knob)
+int stream_delay() {
+    static int d = 0;
+    if (d == 0) {
+        const char* e = std::getenv("SEGDISTILL_STREAM_DELAY");
+        d = e ? std::atoi(e) : 2;
+        if (d < 1) d = 1;
+        if (d > 64) d = 64;
+    }
+    return d;
+}
+
 struct RowsCall {
     const void* S;
     const void* T;
@@ -212,8 +225,31 @@ int rows_dispatch(RowsCall c) {
     if (epoch == 0) epoch = ++g_epoch;
     p.epoch = epoch;
 
-    // TMA path: rows must start on 16-byte boundaries
-    const int cap = sd::kl_rows_tma_chunk_capacity(c.nl);
+    // TMA paths: rows must start on 16-byte boundaries.  Rows of one loss that fit one CTA's registers
+    // (16384 elements) take the register-resident single pass, everything else the streaming kernel.
+    const bool layout_ok = ((long long)HW * es) % 16 == 0 && aligned16(c.S) && aligned16(c.T) && aligned16(c.dS);
+    const long long longest0 = p.G_full > 0 ? row_len : (long long)p.g_last * HW;
+    const bool fits_regs = c.nl == 1 && longest0 <= sd::kl_rows_tma_chunk_capacity(1);
+    const long long gen_units = (long long)B * C * p.KC;
+    if (gen_units >= (1ll << 31)) return SD_ERR_SHAPE;
+
+    enum { kGeneric, kRegs, kStream } path;
+    switch (c.algo) {
+        case SD_ALGO_AUTO: path = !layout_ok ? kGeneric : (fits_regs ? kRegs : kStream); break;
+        case SD_ALGO_TMA:
+            if (!layout_ok) return SD_ERR_UNSUPPORTED;
+            path = fits_regs ? kRegs : kStream;
+            break;
+        case SD_ALGO_STREAM:
+            if (!layout_ok) return SD_ERR_UNSUPPORTED;
+            path = kStream;
+            break;
+        case SD_ALGO_GENERIC: path = kGeneric; break;
+        default: return SD_ERR_VALUE;
+    }
+    if (path == kGeneric && (c.nl > 1 || c.run_if || c.grad_out[0])) return SD_ERR_UNSUPPORTED;
+
+    const int cap = path == kStream ? sd::kl_rows_stream_chunk_capacity() : sd::kl_rows_tma_chunk_capacity(1);
     p.nch_full = p.G_full > 0 ? (int)((row_len + cap - 1) / cap) : 1;
     long long ce = p.G_full > 0 ? (row_len + p.nch_full - 1) / p.nch_full : (long long)p.g_last * HW;
     ce = (ce + VE - 1) / VE * VE;
@@ -222,7 +258,7 @@ int rows_dispatch(RowsCall c) {
     p.nch_last = p.g_last ? (int)(((long long)p.g_last * HW + ce - 1) / ce) : 0;
     p.units_per_sample = p.G_full * p.nch_full + p.nch_last;
     p.total_units = (long long)B * p.units_per_sample;
-    // the longest row of any fused loss, in units: all of them must be co-resident
+    // the longest row of any fused loss, in units
     long long max_row_units = p.nch_full > p.nch_last ? p.nch_full : p.nch_last;
     for (int k = 1; k < c.nl; ++k) {
         const long long m = p.l[k].m;
@@ -230,34 +266,21 @@ int rows_dispatch(RowsCall c) {
         if (m > p.G_full) n = (long long)p.G_full * p.nch_full + p.nch_last;
         if (n > max_row_units) max_row_units = n;
     }
-    int grid = (int)(p.total_units < dev.sms ? p.total_units : dev.sms);
-    if (grid > sd::kMaxGrid) grid = sd::kMaxGrid;
-    const bool layout_ok = ((long long)HW * es) % 16 == 0 && aligned16(c.S) && aligned16(c.T) && aligned16(c.dS);
-    const bool tma_ok = layout_ok && max_row_units <= grid;
-    const long long gen_units = (long long)B * C * p.KC;
-    if (gen_units >= (1ll << 31)) return SD_ERR_SHAPE;
-
-    bool use_tma;
-    if (c.algo == SD_ALGO_TMA) {
-        if (!tma_ok) return SD_ERR_UNSUPPORTED;
-        use_tma = true;
-    } else if (c.algo == SD_ALGO_GENERIC) {
-        use_tma = false;
-    } else if (c.algo == SD_ALGO_AUTO) {
-        use_tma = tma_ok;
-    } else {
-        return SD_ERR_VALUE;
-    }
-    if (!use_tma && (c.nl > 1 || c.run_if || c.grad_out[0])) return SD_ERR_UNSUPPORTED;
+    if (max_row_units >= (1ll << 30)) return SD_ERR_SHAPE;
+    p.max_row_units = (int)max_row_units;
+    p.delay = stream_delay();
 
     cudaStream_t st = static_cast<cudaStream_t>(c.stream);
     cudaError_t e;
-    if (use_tma) {
-        const bool split = max_row_units > 1;
-        e = sd::launch_kl_rows_tma(p, c.dtype == SD_BF16, grid, /*cooperative=*/split, st);
+    if (path == kRegs) {
+        int grid = (int)(p.total_units < dev.sms ? p.total_units : dev.sms);
+        e = sd::launch_kl_rows_tma(p, c.dtype == SD_BF16, grid, /*cooperative=*/false, st);
         g_launches += 1;
-        t_last_kernel = c.nl == 2 ? "kl_rows_tma_kernel(2 losses)"
-                                  : (split ? "kl_rows_tma_kernel(split-row)" : "kl_rows_tma_kernel");
+        t_last_kernel = "kl_rows_tma_kernel";
+    } else if (path == kStream) {
+        e = sd::launch_kl_rows_stream(p, c.dtype == SD_BF16, dev.sms, st);
+        g_launches += 1;
+        t_last_kernel = c.nl == 2 ? "kl_rows_stream_kernel(2 losses)" : "kl_rows_stream_kernel";
     } else {
         if (!p.l[0].row_kl) p.l[0].row_kl = reinterpret_cast<float*>(ws + wl.off_rowkl);
         e = sd::launch_kl_rows_generic(p, c.dtype == SD_BF16, st);

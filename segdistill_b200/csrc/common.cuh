@@ -79,6 +79,13 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     return pol;
 }
 
+// data that will be read again soon (phase 2 of the streaming kernel): keep it in L2
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
 // ---------------------------------------------------------------- named barrier (subset of the CTA)
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -21,8 +21,7 @@
 //                           (no atomics, no counters to reset; all CTAs co-resident: cooperative
 //                           launch).
 //   kl_rows_generic_*       any alignment / any row length: three plain passes.
-#include "common.cuh"
-#include "params.h"
+#include "rows_common.cuh"
 
 namespace sd {
 
@@ -35,96 +34,8 @@ constexpr int kSlotVecs = kSlotVecRows * kThreads;  // 1024 vectors
 constexpr int kSlotBytes = kSlotVecs * 16;        // 16 KB per tensor
 constexpr int kStageBytes = 2 * kSlotBytes;       // S + T
 constexpr int kStages = 7;                        // 224 KB ring
-constexpr unsigned kSpinLimit = 1u << 22;
-constexpr int kRedFloats = 8;                     // per-warp record: Ms, Mt, {Zs, Zt, A} x NL, (SQ)
 constexpr size_t kRowsSmemBytes = (size_t)kStages * kStageBytes + (kStages + 1) * sizeof(uint64_t) +
                                   2 * kWarps * kRedFloats * sizeof(float) + kMaxLosses * 8 * sizeof(float);
-constexpr float kPadValue = -1.0e30f;             // stands in for elements a partial chunk does not have
-constexpr float kMaxFloor = -1.0e29f;             // floor of a thread's local maximum: a thread that holds only
-                                                  // padding then exponentiates to exact zeros (not to exp2 of
-                                                  // the rounding error of kPadValue * c2)
-
-struct Unit {
-    int b, grp, ck, nch;
-    int e0;   // first logical row element of this chunk
-    int len;  // elements in this chunk
-};
-
-__device__ __forceinline__ Unit decode_unit(const RowsParams& p, long long u) {
-    Unit x;
-    x.b = (int)(u / p.units_per_sample);
-    const int r = (int)(u - (long long)x.b * p.units_per_sample);
-    const int full_units = p.G_full * p.nch_full;
-    int g_real;
-    if (r < full_units) {
-        x.grp = r / p.nch_full;
-        x.ck = r - x.grp * p.nch_full;
-        x.nch = p.nch_full;
-        g_real = p.l[0].g;
-    } else {
-        x.grp = p.G_full;
-        x.ck = r - full_units;
-        x.nch = p.nch_last;
-        g_real = p.g_last;
-    }
-    const int L = g_real * p.HW;
-    x.e0 = x.ck * p.chunk_elems;
-    x.len = min(p.chunk_elems, L - x.e0);
-    return x;
-}
-
-// first unit (within the sample) of l[0] row j; j == number of rows gives the end
-__device__ __forceinline__ int unit_start(const RowsParams& p, int j) {
-    return j <= p.G_full ? j * p.nch_full : p.units_per_sample;
-}
-
-// global element offset of logical row element e of a gathered row
-__device__ __forceinline__ size_t perm_elem_offset(const RowsParams& p, const Unit& x, int e) {
-    const int j = e / p.HW;
-    const int pos = e - j * p.HW;
-    const int ch = p.perm[x.grp * p.l[0].g + j];
-    return ((size_t)x.b * p.C + ch) * p.HW + pos;
-}
-
-// softmax statistics of a piece of a row: raw-value maxima (ms, mt) and sums relative to them
-struct RowStat {
-    float ms, zs, mt, zt, a;
-};
-__device__ __forceinline__ RowStat rowstat_empty() { return RowStat{-INFINITY, 0.f, -INFINITY, 0.f, 0.f}; }
-__device__ __forceinline__ RowStat rowstat_merge(const RowStat& x, const RowStat& y, float c2) {
-    RowStat r;
-    r.ms = fmaxf(x.ms, y.ms);
-    r.mt = fmaxf(x.mt, y.mt);
-    const float fxs = x.zs > 0.f ? fast_exp2((x.ms - r.ms) * c2) : 0.f;
-    const float fys = y.zs > 0.f ? fast_exp2((y.ms - r.ms) * c2) : 0.f;
-    const float fxt = x.zt > 0.f ? fast_exp2((x.mt - r.mt) * c2) : 0.f;
-    const float fyt = y.zt > 0.f ? fast_exp2((y.mt - r.mt) * c2) : 0.f;
-    r.zs = __fadd_rn(__fmul_rn(x.zs, fxs), __fmul_rn(y.zs, fys));
-    r.zt = __fadd_rn(__fmul_rn(x.zt, fxt), __fmul_rn(y.zt, fyt));
-    r.a = __fadd_rn(__fmul_rn(x.a, fxt), __fmul_rn(y.a, fyt));
-    return r;
-}
-
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ float sum16(float v) {
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ float max16(float v) {
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
 template <typename T, int NL, bool MSE>
 __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsParams p) {
     using E = Elem<T>;
@@ -156,13 +67,14 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
     // ================================ TMA issue (thread 0 only) ================================
     // Slots are refilled in ring order.  `free_slots` counts slots every thread has drained: a
     // unit's slots are released by the CTA barrier that follows its ring->register copy.
-    long long prod_u = blockIdx.x;
+    UnitCursor prod;
+    prod.init(p, blockIdx.x);
     int prod_v0 = 0, prod_stage = 0, free_slots = kStages;
     uint64_t pol = 0;
     if (tid == 0) pol = l2_policy_evict_first();
     auto issue_loads = [&]() {
-        while (free_slots > 0 && prod_u < p.total_units) {
-            const Unit x = decode_unit(p, prod_u);
+        while (free_slots > 0 && prod.u < p.total_units) {
+            const Unit x = decode_unit(p, prod.b, prod.r);
             const int nvec = x.len / VE;
             const int nv = min(kSlotVecRows * kThreads, nvec - prod_v0);
             const uint32_t bytes = (uint32_t)nv * 16u;
@@ -195,7 +107,7 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
             prod_v0 += kSlotVecs;
             if (prod_v0 >= nvec) {
                 prod_v0 = 0;
-                prod_u += gridDim.x;
+                prod.advance(p, (int)gridDim.x);
             }
             if (++prod_stage == kStages) prod_stage = 0;
             --free_slots;
@@ -221,16 +133,18 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
     uint32_t phase = 0;
     int par = 0;
 
-    for (long long u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-        const Unit x = decode_unit(p, u);
+    UnitCursor cur;
+    for (cur.init(p, blockIdx.x); cur.u < p.total_units; cur.advance(p, (int)gridDim.x)) {
+        const long long u = cur.u;
+        const Unit x = decode_unit(p, cur.b, cur.r);
         const int nvec = x.len / VE;
         const bool whole = nvec == NV * kThreads;  // every thread holds NV vectors
 
         // ---- ring -> registers
         const int nslots = (nvec + kSlotVecs - 1) / kSlotVecs;
+        if (whole) {
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            if (whole || j * kSlotVecs < nvec) {
+            for (int j = 0; j < NJ; ++j) {
                 mbar_wait(&full[stage], phase);
                 const vec_t* bs = reinterpret_cast<const vec_t*>(smem + (size_t)stage * kStageBytes);
                 const vec_t* bt = reinterpret_cast<const vec_t*>(smem + (size_t)stage * kStageBytes + kSlotBytes);
@@ -238,35 +152,49 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
                 for (int r = 0; r < kSlotVecRows; ++r) {
                     const int v = j * kSlotVecRows + r;
                     if (v < NV) {
-                        if (whole || v * kThreads + tid < nvec) {
-                            E::unpack(bs[r * kThreads + tid], &s[v * VE]);
-                            E::unpack(bt[r * kThreads + tid], &t[v * VE]);
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < VE; ++q) {
-                                s[v * VE + q] = kPadValue;
-                                t[v * VE + q] = kPadValue;
-                            }
-                        }
+                        E::unpack(bs[r * kThreads + tid], &s[v * VE]);
+                        E::unpack(bt[r * kThreads + tid], &t[v * VE]);
                     }
                 }
                 if (++stage == kStages) {
                     stage = 0;
                     phase ^= 1u;
                 }
-            } else {
+            }
+        } else {
 #pragma unroll
-                for (int r = 0; r < kSlotVecRows; ++r) {
-                    const int v = j * kSlotVecRows + r;
-                    if (v < NV) {
+            for (int i = 0; i < EPT; ++i) {
+                s[i] = kPadValue;
+                t[i] = kPadValue;
+            }
 #pragma unroll
-                        for (int q = 0; q < VE; ++q) {
-                            s[v * VE + q] = kPadValue;
-                            t[v * VE + q] = kPadValue;
+            for (int j = 0; j < NJ; ++j) {
+                if (j * kSlotVecs < nvec) {
+                    mbar_wait(&full[stage], phase);
+                    const vec_t* bs = reinterpret_cast<const vec_t*>(smem + (size_t)stage * kStageBytes);
+                    const vec_t* bt = reinterpret_cast<const vec_t*>(smem + (size_t)stage * kStageBytes + kSlotBytes);
+#pragma unroll
+                    for (int r = 0; r < kSlotVecRows; ++r) {
+                        const int v = j * kSlotVecRows + r;
+                        if (v < NV && v * kThreads + tid < nvec) {
+                            E::unpack(bs[r * kThreads + tid], &s[v * VE]);
+                            E::unpack(bt[r * kThreads + tid], &t[v * VE]);
                         }
+                    }
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
                     }
                 }
             }
+        }
+
+        // every thread holds its elements in registers: hand the unit's slots back to the TMA thread now,
+        // so the next loads fly during the exponentials
+        __syncthreads();
+        if (tid == 0) {
+            free_slots += nslots;
+            issue_loads();
         }
 
         // ---- thread-local maxima of the raw values: no barrier before the exponentials
@@ -339,10 +267,6 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
             reinterpret_cast<float4*>(my_red)[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
         }
         __syncthreads();
-        if (tid == 0) {  // every thread holds its elements in registers: this unit's slots are free
-            free_slots += nslots;
-            issue_loads();
-        }
 
         // ---- CTA: every warp merges the 16 warp records (lanes l and l+16 mirror each other)
         float Ms, Mt, Zs[NL], Zt[NL], A[NL], SQ = 0.f;
@@ -495,30 +419,51 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
             ks[k] = coef[k] * fast_exp2((ms - Msr[k]) * c2[k]) / Zs[k];
             kt[k] = coef[k] * fast_exp2((mt - Mtr[k]) * c2[k]) / Zt[k];
         }
-        T* out = static_cast<T*>(p.dS);
-        const size_t base = ((size_t)x.b * p.C + (size_t)x.grp * p.l[0].g) * p.HW + x.e0;
         const float ms2 = ms * c2[0], mt2 = mt * c2[0];
-        const bool gathered = p.perm != nullptr;
+        auto grad_vec = [&](int v, float* o) {
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            const int vi = v * kThreads + tid;
-            if (whole || vi < nvec) {
-                float o[VE];
+            for (int q = 0; q < VE; ++q) {
+                const int i = v * VE + q;
+                if (MSE) {
+                    const float es = fast_exp2(fmaf(s[i], c2[0], -ms2));
+                    const float et = fast_exp2(fmaf(t[i], c2[0], -mt2));
+                    o[q] = fmaf(es, ks[0], -et * kt[0]) + p.mse_gcoef * (s[i] - t[i]);
+                } else if (NL > 1) {
+                    o[q] = fmaf(xs[i], ks[0], -xt[i] * kt[0]) + fmaf(s[i], ks[NL - 1], -t[i] * kt[NL - 1]);
+                } else {
+                    o[q] = fmaf(s[i], ks[0], -t[i] * kt[0]);
+                }
+            }
+        };
+        T* out = static_cast<T*>(p.dS);
+        if (p.perm == nullptr) {
+            vec_t* dst = reinterpret_cast<vec_t*>(out + ((size_t)x.b * p.C + (size_t)x.grp * p.l[0].g) * p.HW + x.e0) + tid;
+            if (whole) {
 #pragma unroll
-                for (int q = 0; q < VE; ++q) {
-                    const int i = v * VE + q;
-                    if (MSE) {
-                        const float es = fast_exp2(fmaf(s[i], c2[0], -ms2));
-                        const float et = fast_exp2(fmaf(t[i], c2[0], -mt2));
-                        o[q] = fmaf(es, ks[0], -et * kt[0]) + p.mse_gcoef * (s[i] - t[i]);
-                    } else if (NL > 1) {
-                        o[q] = fmaf(xs[i], ks[0], -xt[i] * kt[0]) + fmaf(s[i], ks[NL - 1], -t[i] * kt[NL - 1]);
-                    } else {
-                        o[q] = fmaf(s[i], ks[0], -t[i] * kt[0]);
+                for (int v = 0; v < NV; ++v) {
+                    float o[VE];
+                    grad_vec(v, o);
+                    dst[v * kThreads] = E::pack(o);
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    if (v * kThreads + tid < nvec) {
+                        float o[VE];
+                        grad_vec(v, o);
+                        dst[v * kThreads] = E::pack(o);
                     }
                 }
-                const size_t off = gathered ? perm_elem_offset(p, x, x.e0 + vi * VE) : base + (size_t)vi * VE;
-                *reinterpret_cast<vec_t*>(out + off) = E::pack(o);
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const int vi = v * kThreads + tid;
+                if (vi < nvec) {
+                    float o[VE];
+                    grad_vec(v, o);
+                    *reinterpret_cast<vec_t*>(out + perm_elem_offset(p, x, x.e0 + vi * VE)) = E::pack(o);
+                }
             }
         }
     }

@@ -11,6 +11,9 @@ namespace sd {
 cudaError_t launch_kl_rows_tma(const RowsParams& p, bool bf16, int grid, bool cooperative, cudaStream_t stream);
 cudaError_t launch_kl_rows_generic(const RowsParams& p, bool bf16, cudaStream_t stream);
 int kl_rows_tma_chunk_capacity(int n_losses);
+// kl_rows_stream.cu
+cudaError_t launch_kl_rows_stream(const RowsParams& p, bool bf16, int sms, cudaStream_t stream);
+int kl_rows_stream_chunk_capacity();
 
 // kl_pixels.cu   (mapS/mapT point at CUtensorMap objects)
 cudaError_t launch_kl_pixels_tma(const void* mapS, const void* mapT, const PixParams& p, bool bf16, int grid,

@@ -19,7 +19,7 @@ constexpr int kGenericChunk = 4096;  // elements of one channel plane per generi
 constexpr int kPartWords = 8;        // floats per published unit partial (generic kernels)
 constexpr int kMaxLosses = 2;        // softmax-KL losses fused over one (S, T) pair in one pass
 constexpr int kPktWords = 16;        // 8-byte {value, epoch} words per unit packet (6 per loss, padded)
-constexpr int kChunkCapMin = 8192;   // smallest chunk capacity any TMA kernel instantiation uses
+constexpr int kChunkCapMin = 7680;   // smallest chunk capacity of the TMA kernels (streaming kernel: 480 x 16)
 
 // one softmax-KL loss over rows of `g` consecutive (gathered) channels x HW
 struct RowLoss {
@@ -57,6 +57,8 @@ struct RowsParams {
     int units_per_sample;
     long long total_units;
     unsigned epoch;       // tag of this launch's unit packets (never 0)
+    int max_row_units;    // units of the longest row of any fused loss
+    int delay;            // streaming kernel: phase 2 trails phase 1 by this many units
     // backward re-runs: device scalars d(total)/d(loss_k) folded into the gradient (null = 1), and a
     // device flag that cancels the launch when it reads 0
     const float* grad_out[kMaxLosses];

@@ -103,10 +103,11 @@ def _oracle_run(preset, kw, s, t, gt_hw, n_iter, perm=None):
 CFG1 = (2, 150, 64, 64)
 
 
-@pytest.mark.parametrize('algo', ['tma', 'generic'])
+@pytest.mark.parametrize('algo', ['tma', 'stream', 'generic'])
 @pytest.mark.parametrize('g', [1, 3, 10, 30, 50, 150])
 def test_cfg1_group_size_sweep(g, algo):
-    """local_configs/Group_Size/cgd{1,3,10,30,50,150}.py on the cfg1 logits; g >= 10 splits rows over CTAs."""
+    """local_configs/Group_Size/cgd{1,3,10,30,50,150}.py on the cfg1 logits; g >= 10 splits rows over CTAs
+    (streaming two-phase kernel); 'stream' forces that kernel for the short rows too."""
     s, t = seeded_pair(CFG1, seed=g)
     kw = dict(group_size=g, alpha=3, tau=2)
     ref = _oracle_run('CGDLoss', kw, s, t, CFG1[2:], 1)
@@ -124,7 +125,7 @@ def test_weight_temperature_sweep(alpha, tau):
     _assert_close(*got, *ref)
 
 
-@pytest.mark.parametrize('algo', ['tma', 'generic'])
+@pytest.mark.parametrize('algo', ['tma', 'stream', 'generic'])
 @pytest.mark.parametrize('shape', [(4, 32, 128, 128), (4, 64, 64, 64), (4, 160, 32, 32), (4, 256, 16, 16)])
 def test_cfg2_stage_features_cgd_with_ragged_groups(shape, algo):
     """MiT-B0 stage widths 32/64/160/256 at strides 4/8/16/32 (B cut to 4 for the CPU oracle); 32,64,256 % 10 != 0."""
@@ -165,7 +166,7 @@ def test_cfg4_feature_mse_plus_cwd(tau, alpha):
     ref_total, ref_grad = (ref_kl + ref_mse).item(), x.grad
     # fused
     crit = sd.CDMSELoss(alpha=alpha, tau=tau, mse_weight=0.7)
-    for algo in ('tma', 'generic'):
+    for algo in ('tma', 'stream', 'generic'):
         loss, grad = _run(crit, s, t, algo=algo)
         _assert_close(loss, grad, ref_total, ref_grad)
         assert rel_err(crit.last_parts[0].item(), ref_kl.item()) <= LOSS_RTOL
@@ -179,7 +180,7 @@ def test_cfg4_feature_mse_plus_cwd(tau, alpha):
     _assert_close(total.item(), sg.grad.cpu(), ref_total, ref_grad)
 
 
-@pytest.mark.parametrize('algo', ['tma', 'generic'])
+@pytest.mark.parametrize('algo', ['tma', 'stream', 'generic'])
 def test_channel_shuffle_matches_reference_gather(algo):
     s, t = seeded_pair((2, 150, 64, 64), seed=21)
     torch.manual_seed(99)
@@ -233,10 +234,12 @@ def test_plain_kldloss_softmax_over_last_dim():
 
 
 # ------------------------------------------------------------------ per-row parity against the f64 closed form
-@pytest.mark.parametrize('algo', ['tma', 'generic'])
+@pytest.mark.parametrize('algo', ['tma', 'stream', 'generic'])
 def test_per_row_kl_against_closed_form(algo):
     s, t = seeded_pair((2, 60, 64, 64), seed=31, scale=2.0)
     for g, mode in ((1, 'channel'), (10, 'channel'), (0, 'pixel')):
+        if mode == 'pixel' and algo == 'stream':
+            continue
         f64_loss, f64_grad, f64_rows = oracle.kld_closed_form_f64(s.numpy(), t.numpy(), mode, max(g, 1), 2.0, 3.0)
         if mode == 'channel':
             loss, ds, rows, _ = _cabi.kl_rows(s.to(dev()), t.to(dev()), group=g, tau=2.0, alpha=3.0,
@@ -320,7 +323,7 @@ def test_two_losses_one_launch(case, dtype):
     pa, pb = ca.plan(x, tg, None, 1), cb.plan(x, tg, None, 1)
     assert sd.KLDLoss.can_fuse(pa, pb)
     la, lb = sd.KLDLoss.run_pair(pa, pb)
-    assert _cabi.last_kernel() == 'kl_rows_tma_kernel(2 losses)'
+    assert _cabi.last_kernel() == 'kl_rows_stream_kernel(2 losses)'
     (la + lb).backward()
     torch.cuda.synchronize()
     assert _cabi.workspace_error_flag() == 0
@@ -359,7 +362,7 @@ def test_dispatcher_batches_entries_on_the_same_tensors():
     before = _cabi.launch_count()
     out = d({'decode_head.linear_pred': x, 'decode_head': x}, {'decode_head.linear_pred': tg, 'decode_head': tg},
             gt, 1, None, None)
-    assert _cabi.launch_count() - before == 1 and _cabi.last_kernel() == 'kl_rows_tma_kernel(2 losses)'
+    assert _cabi.launch_count() - before == 1 and _cabi.last_kernel() == 'kl_rows_stream_kernel(2 losses)'
     assert list(out) == ['loss_decode_head.linear_pred<->decode_head.linear_pred_other',
                          'loss_decode_head<->decode_head_other']
     sum(out.values()).backward()
