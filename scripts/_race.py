@@ -1,0 +1,28 @@
+import sys, torch
+sys.path.insert(0, '/root/repo')
+from segdistill_b200 import _cabi
+dev = torch.device('cuda', 0)
+g = torch.Generator(device=dev).manual_seed(0)
+FULL = (16, 150, 128, 128)
+s = torch.randn(FULL, device=dev, generator=g); t = torch.randn(FULL, device=dev, generator=g)
+def run(a, b, group, **kw):
+    return _cabi.kl_rows(a, b, group=group, tau=2.0, want_row_kl=True, **kw)
+for trial in range(8):
+    # interleave with other kernels / shapes like the test-suite does
+    run(s, t, 1); run(s[:8], t[:8], 10); run(s, t, 1, algo=_cabi.ALGO_GENERIC)
+    l1, d1, r1, _ = run(s, t, 10)
+    l2, d2, r2, _ = run(s, t, 10)
+    torch.cuda.synchronize()
+    diff = (d1 != d2)
+    nd = int(diff.sum())
+    print('trial', trial, 'loss eq', bool(l1 == l2), 'rows neq', int((r1 != r2).sum()), 'ds neq', nd, flush=True)
+    if nd:
+        idx = diff.flatten().nonzero().flatten()
+        print('  first', idx[:3].tolist(), 'last', idx[-3:].tolist(), 'span', int(idx[-1] - idx[0]) + 1)
+        rows = (idx // (10 * 16384)).unique()
+        print('  rows affected', rows.tolist()[:10], 'count', len(rows))
+        per_unit = ((idx % (10*16384)) // 7124).unique()
+        print('  chunks in row', per_unit.tolist()[:24])
+        print('  max rel diff', ((d1.flatten()[idx]-d2.flatten()[idx]).abs().max()/d1.abs().max()).item())
+        lanes = (idx % 4).unique().tolist()
+        print('  elem%4', lanes, ' vec idx within chunk %448 sample', (((idx % (10*16384)) % 7124)//4 % 448)[:10].tolist())

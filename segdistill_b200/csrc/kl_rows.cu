@@ -189,20 +189,20 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
             }
         }
 
-        // every thread holds its elements in registers: hand the unit's slots back to the TMA thread now,
-        // so the next loads fly during the exponentials
-        __syncthreads();
-        if (tid == 0) {
-            free_slots += nslots;
-            issue_loads();
-        }
-
         // ---- thread-local maxima of the raw values: no barrier before the exponentials
         float ms = fmaxf(s[0], kMaxFloor), mt = fmaxf(t[0], kMaxFloor);
 #pragma unroll
         for (int i = 1; i < EPT; ++i) {
             ms = fmaxf(ms, s[i]);
             mt = fmaxf(mt, t[i]);
+        }
+
+        // every thread holds its elements in registers (the maxima consumed every shared-memory read):
+        // hand the unit's slots back to the TMA thread now, so the next loads fly during the exponentials
+        __syncthreads();
+        if (tid == 0) {
+            free_slots += nslots;
+            issue_loads();
         }
 
         // ---- exponentials (kept in registers), thread-partial sums relative to (ms, mt)

@@ -5,7 +5,7 @@
 // A row of CGD with g = 10 on 128x128 logits is 163 840 elements (1.3 MB for S and T): no SM can hold
 // it, so its softmax statistics need every chunk before any gradient can be written.  Instead of
 // stalling a CTA until the other chunks' partials arrive, each persistent CTA runs its units
-// (7680-element chunks, u = blockIdx.x + j*gridDim.x) through two phases that are `delay` units apart:
+// (7168-element chunks, u = blockIdx.x + j*gridDim.x) through two phases that are `delay` units apart:
 //
 //   phase 1 (unit j)          chunk -> shared (TMA) -> thread-local max, exponentials, per-warp partial
 //                             (max, sum, sum p*(t-s)) per loss.  Nothing is kept.
@@ -14,27 +14,28 @@
 //                             written from the stream.
 //
 // Warp roles (no CTA-wide barrier anywhere):
-//   15 consumer warps   do the arithmetic; they wait only on mbarriers (a ring slot is full, the row
+//   14 consumer warps   do the arithmetic; they wait only on mbarriers (a ring slot is full, the row
 //                       statistics of the phase-2 unit are there) and never on each other.
-//   1 control warp      one lane issues the 1-D TMA bulk copies as ring slots drain; the whole warp
-//                       merges the consumers' partials and publishes the unit's packet (epoch-tagged
+//   1 TMA warp          one lane issues the 1-D TMA bulk copies of the tasks, in consumption order, as
+//                       ring slots drain.
+//   1 control warp      merges the consumers' partials and publishes the unit's packet (epoch-tagged
 //                       8-byte words in global memory: no atomics, no counters to reset), and - ahead
 //                       of the consumers - gathers the packets of the phase-2 unit's row-mates from the
 //                       other CTAs and broadcasts the row statistics through shared memory.
 //
 // HBM traffic stays the algorithmic read S + read T + write dS; the price is a second pass of
 // exponentials (4 ex2 per element and loss instead of 2).  Two CTAs per SM (<= 64 registers, a 3-stage
-// 90 KB ring each).  NL = 2 serves two losses with nested rows (CD + CGD on the same logits).
+// 84 KB ring each).  NL = 2 serves two losses with nested rows (CD + CGD on the same logits).
 #include "rows_common.cuh"
 
 namespace sd {
 
 constexpr int kSThreads = 512;
-constexpr int kSCons = 480;                        // consumer threads (15 warps); warp 15 is the control warp
+constexpr int kSCons = 448;                        // consumer threads (14 warps); warp 14 issues TMA, warp 15 is the control warp
 constexpr int kSConsWarps = kSCons / 32;
 constexpr int kSEPT = 16;                          // elements per consumer thread and tensor of one unit
 constexpr int kSSlotVecRows = 2;
-constexpr int kSSlotVecs = kSSlotVecRows * kSCons; // 960 vectors = 15 KB per tensor
+constexpr int kSSlotVecs = kSSlotVecRows * kSCons; // 896 vectors = 14 KB per tensor
 constexpr int kSSlotBytes = kSSlotVecs * 16;
 constexpr int kSStageBytes = 2 * kSSlotBytes;      // S + T
 constexpr int kSStages = 3;
@@ -90,16 +91,14 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
 
     if (warp == kSConsWarps) {
         // =====================================================================================
-        // control warp
+        // TMA warp: one lane streams the chunks of the tasks, in consumption order, into ring slots as
+        // they drain
         // =====================================================================================
+        if (lane != 0) return;
         int pstage = 0;
         uint32_t pphase = 0;
-        uint64_t pol_keep = 0, pol_stream = 0;
-        if (lane == 0) {
-            pol_keep = l2_policy_evict_last();
-            pol_stream = l2_policy_evict_first();
-        }
-        // lane 0: all TMA copies of one task (a unit's chunk), waiting for each ring slot to drain
+        const uint64_t pol_keep = l2_policy_evict_last();
+        const uint64_t pol_stream = l2_policy_evict_first();
         auto load_unit = [&](const Unit& x, uint64_t pol) {
             const int nvec = x.len / VE;
             for (int v0 = 0; v0 < nvec; v0 += kSSlotVecs) {
@@ -137,7 +136,26 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
                 }
             }
         };
+        UnitCursor c1, c2;
+        c1.init(p, blockIdx.x);
+        c2.init(p, blockIdx.x);
+        for (int step = 0; step < n_steps; ++step) {
+            if (step < n_units) {
+                load_unit(decode_unit(p, c1.b, c1.r), pol_keep);
+                c1.advance(p, grid);
+            }
+            if (step >= D) {
+                load_unit(decode_unit(p, c2.b, c2.r), pol_stream);
+                c2.advance(p, grid);
+            }
+        }
+        return;
+    }
 
+    if (warp == kSConsWarps + 1) {
+        // =====================================================================================
+        // control warp: unit packets out, row statistics in
+        // =====================================================================================
         float cta_kl[NL], cta_sq = 0.f;  // lane 0, in unit order (deterministic)
 #pragma unroll
         for (int k = 0; k < NL; ++k) cta_kl[k] = 0.f;
@@ -148,10 +166,6 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
             const bool has1 = step < n_units, has2 = step >= D;
             const int par1 = step & 1, par2 = (step - D) & 1;
             const uint32_t ph1 = (uint32_t)(step >> 1) & 1u, ph2 = (uint32_t)((step - D) >> 1) & 1u;
-            if (has1) {
-                const Unit x1 = decode_unit(p, c1.b, c1.r);
-                if (lane == 0) load_unit(x1, pol_keep);
-            }
             if (has2) {
                 // ---- row statistics of the phase-2 unit from the packets of its row-mates (all CTAs)
                 const long long u = c2.u;
@@ -230,10 +244,7 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
                     }
                 }
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&stat_ready[par2]);
-                    load_unit(x2, pol_stream);
-                }
+                if (lane == 0) mbar_arrive(&stat_ready[par2]);
                 c2.advance(p, grid);
             }
             if (has1) {
@@ -385,7 +396,6 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
                             vt[r] = bt[r * kSCons + tid];
                         }
                     }
-                    release_slot();
 #pragma unroll
                     for (int r = 0; r < kSSlotVecRows; ++r) {
                         if (whole || (j * kSSlotVecRows + r) * kSCons + tid < nvec) {
@@ -407,6 +417,9 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
                             }
                         }
                     }
+                    // only now: the arrival must not overtake the shared-memory reads above (an mbarrier
+                    // arrive is not ordered behind LDS that are still in flight; the arithmetic is)
+                    release_slot();
                 }
             }
             // warp record: raw maxima are common to all losses, sums are rescaled to them
@@ -471,7 +484,6 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
                             vt[r] = bt[r * kSCons + tid];
                         }
                     }
-                    release_slot();
 #pragma unroll
                     for (int r = 0; r < kSSlotVecRows; ++r) {
                         const int v = j * kSSlotVecRows + r;
@@ -496,6 +508,7 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
                             else *reinterpret_cast<vec_t*>(out + perm_elem_offset(p, x, x.e0 + vi * VE)) = E::pack(o);
                         }
                     }
+                    release_slot();  // after the arithmetic that consumed the shared-memory reads (see phase 1)
                 }
             }
             c2.advance(p, grid);

@@ -19,7 +19,7 @@ constexpr int kGenericChunk = 4096;  // elements of one channel plane per generi
 constexpr int kPartWords = 8;        // floats per published unit partial (generic kernels)
 constexpr int kMaxLosses = 2;        // softmax-KL losses fused over one (S, T) pair in one pass
 constexpr int kPktWords = 16;        // 8-byte {value, epoch} words per unit packet (6 per loss, padded)
-constexpr int kChunkCapMin = 7680;   // smallest chunk capacity of the TMA kernels (streaming kernel: 480 x 16)
+constexpr int kChunkCapMin = 7168;   // smallest chunk capacity of the TMA kernels (streaming kernel: 448 x 16)
 
 // one softmax-KL loss over rows of `g` consecutive (gathered) channels x HW
 struct RowLoss {
