@@ -6,7 +6,9 @@ if the library is missing, or the device is not sm_100, the calls raise.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
+import math
 import os
 import threading
 from typing import Optional
@@ -132,13 +134,28 @@ def _prep_pair(x_student: torch.Tensor, x_teacher: torch.Tensor):
     return s, t, _dtype_code(s)
 
 
+_NULL_CTX = contextlib.nullcontext()
+
+
+def _on(device: torch.device):
+    """Device guard that costs nothing when `device` already is the current device (the usual case)."""
+    if device.index is None or torch.cuda.current_device() == device.index:
+        return _NULL_CTX
+    return torch.cuda.device(device)
+
+
+def _dev_index(device: torch.device) -> int:
+    return torch.cuda.current_device() if device.index is None else device.index
+
+
 # ---------------------------------------------------------------- workspaces
 _workspaces = {}
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
     """Zero-initialised scratch, one per (device, stream); grown on demand, never shared across streams."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    idx = _dev_index(device)
+    key = (idx, _raw_stream(idx))
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
@@ -149,15 +166,31 @@ def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
 def workspace_error_flag(device=None) -> int:
     """Spin time-out flag of the split-row kernel (0 = never fired); synchronises. Tests only."""
     device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    idx = _dev_index(device)
+    key = (idx, _raw_stream(idx))
     ws = _workspaces.get(key)
     if ws is None:
         return 0
     return int(ws[:8].view(torch.int32)[1].item())
 
 
+def _raw_stream(index: int) -> int:
+    return torch._C._cuda_getCurrentRawStream(index)
+
+
 def _stream_ptr(device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    return _raw_stream(_dev_index(device))
+
+
+_ws_bytes_cache = {}
+
+
+def _rows_ws_bytes(lib, B, C, HW, group):
+    key = (B, C, HW, group)
+    n = _ws_bytes_cache.get(key)
+    if n is None:
+        n = _ws_bytes_cache[key] = lib.sd_kl_rows_workspace_bytes(B, C, HW, group)
+    return n
 
 
 # ---------------------------------------------------------------- entry points
@@ -171,11 +204,11 @@ def kl_rows(x_student, x_teacher, group=1, tau=1.0, alpha=1.0, perm: Optional[to
     s, t, code = _prep_pair(x_student, x_teacher)
     if bchw is None:
         B, C = s.shape[0], s.shape[1]
-        HW = s[0, 0].numel()
+        HW = math.prod(s.shape[2:])
     else:
         B, C, HW = bchw
     dev = s.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         ds = torch.empty_like(s)
         out = torch.empty(2, dtype=torch.float32, device=dev)
         G = (C + min(group, C) - 1) // min(group, C)
@@ -185,8 +218,7 @@ def kl_rows(x_student, x_teacher, group=1, tau=1.0, alpha=1.0, perm: Optional[to
             perm_dev = perm.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
             if perm_dev.numel() != C:
                 raise SegDistillError('chan_perm must have C entries')
-        nbytes = lib.sd_kl_rows_workspace_bytes(B, C, HW, group)
-        ws = _workspace(dev, nbytes)
+        ws = _workspace(dev, _rows_ws_bytes(lib, B, C, HW, group))
         rc = lib.sd_kl_rows_fwd_bwd(
             s.data_ptr(), t.data_ptr(), ds.data_ptr(),
             row_kl.data_ptr() if row_kl is not None else None, out.data_ptr(),
@@ -198,6 +230,9 @@ def kl_rows(x_student, x_teacher, group=1, tau=1.0, alpha=1.0, perm: Optional[to
     return out[0], ds, row_kl, (out[1] if mse_weight != 0 else None)
 
 
+_multi_arrays = {}
+
+
 def kl_rows_multi(x_student, x_teacher, groups, taus, alphas, grad_outputs=None, run_if=None, ds=None):
     """Two row-wise softmax-KL losses over the same pair in one pass. Returns (losses[n], dS).
 
@@ -207,21 +242,26 @@ def kl_rows_multi(x_student, x_teacher, groups, taus, alphas, grad_outputs=None,
     s, t, code = _prep_pair(x_student, x_teacher)
     n = len(groups)
     B, C = s.shape[0], s.shape[1]
-    HW = s[0, 0].numel()
+    HW = math.prod(s.shape[2:])
     dev = s.device
     c = ctypes
-    with torch.cuda.device(dev):
+    with _on(dev):
         if ds is None:
             ds = torch.empty_like(s)
         out = torch.empty(n, dtype=torch.float32, device=dev)
-        g_arr = (c.c_int * n)(*[int(g) for g in groups])
-        t_arr = (c.c_float * n)(*[float(v) for v in taus])
-        a_arr = (c.c_float * n)(*[float(v) for v in alphas])
-        l_arr = (c.c_void_p * n)(*[out[k:].data_ptr() for k in range(n)])
+        key = (tuple(groups), tuple(taus), tuple(alphas))
+        arrs = _multi_arrays.get(key)
+        if arrs is None:
+            arrs = _multi_arrays[key] = ((c.c_int * n)(*[int(g) for g in groups]),
+                                         (c.c_float * n)(*[float(v) for v in taus]),
+                                         (c.c_float * n)(*[float(v) for v in alphas]))
+        g_arr, t_arr, a_arr = arrs
+        base = out.data_ptr()
+        l_arr = (c.c_void_p * n)(*[base + 4 * k for k in range(n)])
         go_arr = None
         if grad_outputs is not None:
             go_arr = (c.c_void_p * n)(*[g.data_ptr() for g in grad_outputs])
-        ws = _workspace(dev, lib.sd_kl_rows_workspace_bytes(B, C, HW, min(int(g) for g in groups)))
+        ws = _workspace(dev, _rows_ws_bytes(lib, B, C, HW, min(int(g) for g in groups)))
         rc = lib.sd_kl_rows_multi_fwd_bwd(
             s.data_ptr(), t.data_ptr(), ds.data_ptr(), n, g_arr, t_arr, a_arr, l_arr, None, go_arr,
             run_if.data_ptr() if run_if is not None else None,
@@ -247,7 +287,7 @@ def scale_grad2_(ds: torch.Tensor, go0: torch.Tensor, go1: torch.Tensor) -> torc
     """dS *= go when go0 == go1; returns the device flag (1 = non-uniform, dS untouched)."""
     lib = load()
     flag = torch.empty(1, dtype=torch.int32, device=ds.device)
-    with torch.cuda.device(ds.device):
+    with _on(ds.device):
         rc = lib.sd_scale_grad2(ds.data_ptr(), ds.numel(), _dtype_code(ds), go0.data_ptr(), go1.data_ptr(),
                                 flag.data_ptr(), _stream_ptr(ds.device))
         _check(rc)
@@ -260,9 +300,9 @@ def kl_pixels(x_student, x_teacher, tau=1.0, alpha=1.0, grad_scale=1.0, at_weigh
     lib = load()
     s, t, code = _prep_pair(x_student, x_teacher)
     B, C = s.shape[0], s.shape[1]
-    HW = s[0, 0].numel()
+    HW = math.prod(s.shape[2:])
     dev = s.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         ds = torch.empty_like(s)
         out = torch.empty(2, dtype=torch.float32, device=dev)
         row_kl = torch.empty(B * HW, dtype=torch.float32, device=dev) if want_row_kl else None
@@ -283,7 +323,7 @@ def mse(x_student, x_teacher, weight=1.0, grad_scale=1.0):
     lib = load()
     s, t, code = _prep_pair(x_student, x_teacher)
     dev = s.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         ds = torch.empty_like(s)
         out = torch.empty(1, dtype=torch.float32, device=dev)
         ws = _workspace(dev, lib.sd_mse_workspace_bytes(s.numel()))
@@ -298,9 +338,9 @@ def cgd_corr(x_student, x_teacher, group=10, alpha=1.0, grad_scale=1.0):
     lib = load()
     s, t, code = _prep_pair(x_student, x_teacher)
     B, C = s.shape[0], s.shape[1]
-    HW = s[0, 0].numel()
+    HW = math.prod(s.shape[2:])
     dev = s.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         ds = torch.empty_like(s)
         out = torch.empty(1, dtype=torch.float32, device=dev)
         ws = _workspace(dev, lib.sd_cgd_corr_workspace_bytes(B, C, HW, group))
@@ -314,8 +354,10 @@ def cgd_corr(x_student, x_teacher, group=10, alpha=1.0, grad_scale=1.0):
 def scale_grad_(ds: torch.Tensor, grad_output: torch.Tensor):
     """In place ``ds *= grad_output`` on the device; a no-op launch when grad_output == 1."""
     lib = load()
-    g = grad_output.detach().to(device=ds.device, dtype=torch.float32).reshape(1)
-    with torch.cuda.device(ds.device):
+    g = grad_output
+    if g.device != ds.device or g.dtype != torch.float32 or g.numel() != 1 or g.requires_grad:
+        g = grad_output.detach().to(device=ds.device, dtype=torch.float32).reshape(1)
+    with _on(ds.device):
         rc = lib.sd_scale_grad(ds.data_ptr(), ds.numel(), _dtype_code(ds), g.data_ptr(), _stream_ptr(ds.device))
         _check(rc)
     return ds

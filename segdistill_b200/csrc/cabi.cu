@@ -220,16 +220,12 @@ int rows_dispatch(RowsCall c) {
     p.cta_part = reinterpret_cast<float*>(ws + wl.off_cta);
     p.pkt = reinterpret_cast<unsigned long long*>(ws + wl.off_unit);
     p.unit_part = reinterpret_cast<float*>(ws + wl.off_unit);
-    static std::atomic<unsigned> g_epoch{0};
-    unsigned epoch = ++g_epoch;
-    if (epoch == 0) epoch = ++g_epoch;
-    p.epoch = epoch;
 
     // TMA paths: rows must start on 16-byte boundaries.  Rows of one loss that fit one CTA's registers
     // (16384 elements) take the register-resident single pass, everything else the streaming kernel.
     const bool layout_ok = ((long long)HW * es) % 16 == 0 && aligned16(c.S) && aligned16(c.T) && aligned16(c.dS);
     const long long longest0 = p.G_full > 0 ? row_len : (long long)p.g_last * HW;
-    const bool fits_regs = c.nl == 1 && longest0 <= sd::kl_rows_tma_chunk_capacity(1);
+    const bool fits_regs = c.nl == 1 && longest0 <= sd::kl_rows_tma_chunk_capacity();
     const long long gen_units = (long long)B * C * p.KC;
     if (gen_units >= (1ll << 31)) return SD_ERR_SHAPE;
 
@@ -249,7 +245,7 @@ int rows_dispatch(RowsCall c) {
     }
     if (path == kGeneric && (c.nl > 1 || c.run_if || c.grad_out[0])) return SD_ERR_UNSUPPORTED;
 
-    const int cap = path == kStream ? sd::kl_rows_stream_chunk_capacity() : sd::kl_rows_tma_chunk_capacity(1);
+    const int cap = path == kStream ? sd::kl_rows_stream_chunk_capacity() : sd::kl_rows_tma_chunk_capacity();
     p.nch_full = p.G_full > 0 ? (int)((row_len + cap - 1) / cap) : 1;
     long long ce = p.G_full > 0 ? (row_len + p.nch_full - 1) / p.nch_full : (long long)p.g_last * HW;
     ce = (ce + VE - 1) / VE * VE;
@@ -274,7 +270,7 @@ int rows_dispatch(RowsCall c) {
     cudaError_t e;
     if (path == kRegs) {
         int grid = (int)(p.total_units < dev.sms ? p.total_units : dev.sms);
-        e = sd::launch_kl_rows_tma(p, c.dtype == SD_BF16, grid, /*cooperative=*/false, st);
+        e = sd::launch_kl_rows_tma(p, c.dtype == SD_BF16, grid, st);
         g_launches += 1;
         t_last_kernel = "kl_rows_tma_kernel";
     } else if (path == kStream) {

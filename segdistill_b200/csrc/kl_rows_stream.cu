@@ -83,6 +83,9 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
     }
     __syncthreads();
 
+    // tag of this launch's unit packets: the workspace's launch counter (bumped by the last CTA to finish,
+    // i.e. after every CTA has read it) + 1, so a packet left by any earlier launch never validates
+    const unsigned epoch = __ldcg(&p.ctrl[2]) + 1u;
     const int grid = (int)gridDim.x;
     const int n_units = blockIdx.x < p.total_units ? (int)((p.total_units - blockIdx.x + grid - 1) / grid) : 0;
     const int D = p.delay;
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
 #pragma unroll
                             for (int i = 0; i < 5; ++i) {
                                 w[i] = ld_relaxed_u64(q + i);
-                                ok = ok && (unsigned)(w[i] >> 32) == p.epoch;
+                                ok = ok && (unsigned)(w[i] >> 32) == epoch;
                             }
                             if (ok) break;
                             if (++spins > kSpinLimit) {
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
                 if (MSE) cta_sq += warp_sum(rr[5]);
                 if (lane < 6 * NL)
                     st_relaxed_u64(p.pkt + (size_t)c1.u * kPktWords + lane,
-                                   ((unsigned long long)p.epoch << 32) | __float_as_uint(val));
+                                   ((unsigned long long)epoch << 32) | __float_as_uint(val));
                 c1.advance(p, grid);
             }
         }
@@ -312,6 +315,7 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
 #pragma unroll
                 for (int k = 0; k < NL; ++k) *p.l[k].loss = (float)((double)p.l[k].loss_scale * acc[k]);
                 if (MSE && p.mse_loss) *p.mse_loss = (float)((double)p.mse_scale * acc[NL]);
+                atomicAdd(&p.ctrl[2], 1u);
                 atomicExch(&p.ctrl[0], 0u);
             }
         }

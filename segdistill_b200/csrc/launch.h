@@ -8,9 +8,9 @@
 namespace sd {
 
 // kl_rows.cu
-cudaError_t launch_kl_rows_tma(const RowsParams& p, bool bf16, int grid, bool cooperative, cudaStream_t stream);
+cudaError_t launch_kl_rows_tma(const RowsParams& p, bool bf16, int grid, cudaStream_t stream);
 cudaError_t launch_kl_rows_generic(const RowsParams& p, bool bf16, cudaStream_t stream);
-int kl_rows_tma_chunk_capacity(int n_losses);
+int kl_rows_tma_chunk_capacity();
 // kl_rows_stream.cu
 cudaError_t launch_kl_rows_stream(const RowsParams& p, bool bf16, int sms, cudaStream_t stream);
 int kl_rows_stream_chunk_capacity();

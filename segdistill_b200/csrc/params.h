@@ -11,7 +11,8 @@ namespace sd {
 // there, so one workspace can serve any sequence of ops and shapes on a stream; the regions behind
 // the arena hold data that is always written before it is read within a launch, or that is
 // validated by a per-launch epoch tag (the unit packets of the split-row exchange).
-constexpr int kCtrlWords = 64;  // [0] completion ticket, [1] error flag (spin time-out)
+constexpr int kCtrlWords = 64;  // [0] completion ticket, [1] error flag (spin time-out), [2] launch epoch of the
+                                // streaming kernel (tag of its unit packets; counts launches, never reset)
 constexpr size_t kArenaBytes = sizeof(unsigned) * kCtrlWords;
 
 constexpr int kMaxGrid = 1024;       // upper bound on persistent-grid size (per-CTA partial slots)
@@ -56,7 +57,6 @@ struct RowsParams {
     int nch_last;         // chunks per ragged l[0] row
     int units_per_sample;
     long long total_units;
-    unsigned epoch;       // tag of this launch's unit packets (never 0)
     int max_row_units;    // units of the longest row of any fused loss
     int delay;            // streaming kernel: phase 2 trails phase 1 by this many units
     // backward re-runs: device scalars d(total)/d(loss_k) folded into the gradient (null = 1), and a

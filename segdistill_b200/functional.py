@@ -74,12 +74,17 @@ class _KLRowsMulti(torch.autograd.Function):
         if ds is None:
             return (None,) * 8
         dev = ds.device
-        go0 = go0.detach().to(device=dev, dtype=torch.float32).reshape(1)
-        go1 = go1.detach().to(device=dev, dtype=torch.float32).reshape(1)
-        flag = _cabi.scale_grad2_(ds, go0, go1)
-        x_student, x_teacher = ctx.saved_tensors
-        groups, taus, alphas = ctx.cfg
-        _cabi.kl_rows_multi(x_student, x_teacher, groups, taus, alphas, grad_outputs=(go0, go1), run_if=flag, ds=ds)
+        if go0 is go1 or (go0.data_ptr() == go1.data_ptr() and go0.device == go1.device):
+            # the two terms entered one sum: a single upstream gradient, one in-place scaling launch
+            _cabi.scale_grad_(ds, go0)
+        else:
+            go0 = go0.detach().to(device=dev, dtype=torch.float32).reshape(1)
+            go1 = go1.detach().to(device=dev, dtype=torch.float32).reshape(1)
+            flag = _cabi.scale_grad2_(ds, go0, go1)
+            x_student, x_teacher = ctx.saved_tensors
+            groups, taus, alphas = ctx.cfg
+            _cabi.kl_rows_multi(x_student, x_teacher, groups, taus, alphas, grad_outputs=(go0, go1), run_if=flag,
+                                ds=ds)
         if ds.dtype != ctx.in_dtype:
             ds = ds.to(ctx.in_dtype)
         return (ds.view(ctx.in_shape),) + (None,) * 7
