@@ -61,13 +61,16 @@ extern "C" {
 #define SD_BF16 1
 
 /* algo: AUTO picks a TMA-staged kernel when the layout allows it (16-byte aligned rows): the
- * register-resident single pass for rows of up to 16384 elements, the streaming two-phase kernel for
- * longer rows and for two fused losses; the plain multi-pass kernel otherwise.  TMA = AUTO without
- * the fallback; STREAM forces the two-phase kernel (rows only). */
+ * register-resident single pass for rows of up to 16384 elements; for longer rows and for two fused
+ * losses the cluster-resident single pass (rows that fit the shared memory of 8 CTAs), else the
+ * streaming two-phase kernel; the plain multi-pass kernel otherwise.  TMA = AUTO without the generic
+ * fallback; STREAM / CLUSTER force that kernel (rows only; CLUSTER answers SD_ERR_UNSUPPORTED when
+ * the rows do not fit). */
 #define SD_ALGO_AUTO    0
 #define SD_ALGO_GENERIC 1
 #define SD_ALGO_TMA     2
 #define SD_ALGO_STREAM  3
+#define SD_ALGO_CLUSTER 4
 
 /* argument errors */
 #define SD_OK               0
@@ -120,13 +123,15 @@ SD_API int sd_kl_rows_fwd_bwd(const void* S, const void* T, void* dS,
  *   (device scalars) or 1 when grad_outputs (or the entry) is NULL.
  *   run_if: NULL, or a device word: the launch is a no-op when it reads 0 (conditional backward
  *   re-run after sd_scale_grad2 found non-uniform upstream gradients).
- * TMA path only: SD_ERR_UNSUPPORTED when the layout cannot take it (call the single-loss entry per loss).
+ * algo: SD_ALGO_AUTO (cluster-resident kernel when the rows fit, else the streaming kernel), or
+ * SD_ALGO_CLUSTER / SD_ALGO_STREAM to force one.  TMA paths only: SD_ERR_UNSUPPORTED when the layout
+ * cannot take it (call the single-loss entry per loss).
  */
 SD_API int sd_kl_rows_multi_fwd_bwd(const void* S, const void* T, void* dS, int n_losses, const int* groups,
                              const float* taus, const float* alphas, float* const* losses,
                              float* const* row_kls, const float* const* grad_outputs,
                              const unsigned* run_if, int B, int C, int HW, int dtype, float grad_scale,
-                             void* workspace, size_t workspace_bytes, void* stream);
+                             void* workspace, size_t workspace_bytes, int algo, void* stream);
 
 /* ------------------------------------------------------------------ pixels (PD / AT) */
 SD_API size_t sd_kl_pixels_workspace_bytes(int B, int C, int HW);

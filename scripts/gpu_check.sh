@@ -21,8 +21,16 @@ for st in $STAGES; do
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 60 --csv --log-file gpurun_out/launches.csv \
          python bench.py --steps 4 --warmup 2 --no-cpu-baseline --no-e2e > gpurun_out/launches_run.log 2>&1; echo "launches rc=$?" | tee -a gpurun_out/summary.txt; tail -12 gpurun_out/launches.csv;;
     ncu)
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:kl_rows_tma -s 4 -c 2 -o gpurun_out/prof_rows -f \
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:kl_rows -s 3 -c 2 -o gpurun_out/prof_bench -f \
          python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e > gpurun_out/ncu_run.log 2>&1; echo "ncu rc=$?" | tee -a gpurun_out/summary.txt; tail -5 gpurun_out/ncu_run.log;;
+    ncu_k)
+      # one capture per kernel family through the C ABI (scripts/kbench.py): CD (register kernel), CGD (stream), PD (pixels)
+      for c in cd_f32 cgd10_f32 pd_f32 cd_bf16; do
+        timeout 600 ncu --set full --clock-control none --import-source on -k regex:'kl_rows|kl_pixels' -s 6 -c 1 -o gpurun_out/prof_$c -f \
+           python scripts/kbench.py --iters 3 --only $c > gpurun_out/ncu_$c.log 2>&1; echo "ncu_k $c rc=$?" | tee -a gpurun_out/summary.txt
+      done;;
+    kbench)
+      timeout 600 python scripts/kbench.py --iters 50 > gpurun_out/kbench.log 2>&1; echo "kbench rc=$?" | tee -a gpurun_out/summary.txt; cat gpurun_out/kbench.log;;
   esac
 done
 cat gpurun_out/summary.txt

@@ -12,7 +12,8 @@ top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 txt = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 lines = txt.splitlines()
 start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
-rows = list(csv.DictReader(io.StringIO('\n'.join(lines[start:]))))
+end = next((i for i in range(start + 1, len(lines)) if lines[i].startswith('"Address"') or not lines[i].strip()), len(lines))
+rows = list(csv.DictReader(io.StringIO('\n'.join(lines[start:end]))))  # first kernel of the report only
 tot_samples = sum(int(r['# Samples'] or 0) for r in rows)
 tot_inst = sum(int(r['Instructions Executed'] or 0) for r in rows)
 print(f'{len(rows)} SASS lines, {tot_samples} samples, {tot_inst} warp-instructions')

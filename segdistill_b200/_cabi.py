@@ -19,8 +19,9 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, 'libsegdistill_sm100.so')
 
 SD_F32, SD_BF16 = 0, 1
-ALGO_AUTO, ALGO_GENERIC, ALGO_TMA, ALGO_STREAM = 0, 1, 2, 3
-ALGOS = {'auto': ALGO_AUTO, 'generic': ALGO_GENERIC, 'tma': ALGO_TMA, 'stream': ALGO_STREAM}
+ALGO_AUTO, ALGO_GENERIC, ALGO_TMA, ALGO_STREAM, ALGO_CLUSTER = 0, 1, 2, 3, 4
+ALGOS = {'auto': ALGO_AUTO, 'generic': ALGO_GENERIC, 'tma': ALGO_TMA, 'stream': ALGO_STREAM,
+         'cluster': ALGO_CLUSTER}
 
 # every symbol include/segdistill.h declares (tests check the library exports all of them)
 EXPORTS = (
@@ -70,7 +71,7 @@ def load():
                                            f32, f32, f32, f32, vp, vp, sz, i32, vp]
         lib.sd_kl_rows_multi_fwd_bwd.restype = i32
         lib.sd_kl_rows_multi_fwd_bwd.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp,
-                                                 i32, i32, i32, i32, f32, vp, sz, vp]
+                                                 i32, i32, i32, i32, f32, vp, sz, i32, vp]
         lib.sd_scale_grad2.restype = i32
         lib.sd_scale_grad2.argtypes = [vp, i64, i32, vp, vp, vp, vp]
         lib.sd_kl_pixels_workspace_bytes.restype = sz
@@ -233,7 +234,8 @@ def kl_rows(x_student, x_teacher, group=1, tau=1.0, alpha=1.0, perm: Optional[to
 _multi_arrays = {}
 
 
-def kl_rows_multi(x_student, x_teacher, groups, taus, alphas, grad_outputs=None, run_if=None, ds=None):
+def kl_rows_multi(x_student, x_teacher, groups, taus, alphas, grad_outputs=None, run_if=None, ds=None,
+                  algo=ALGO_AUTO):
     """Two row-wise softmax-KL losses over the same pair in one pass. Returns (losses[n], dS).
 
     ``grad_outputs``/``run_if``/``ds`` serve the conditional backward re-run (see functional._KLRowsMulti).
@@ -265,7 +267,7 @@ def kl_rows_multi(x_student, x_teacher, groups, taus, alphas, grad_outputs=None,
         rc = lib.sd_kl_rows_multi_fwd_bwd(
             s.data_ptr(), t.data_ptr(), ds.data_ptr(), n, g_arr, t_arr, a_arr, l_arr, None, go_arr,
             run_if.data_ptr() if run_if is not None else None,
-            B, C, HW, code, 1.0, ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+            B, C, HW, code, 1.0, ws.data_ptr(), ws.numel(), int(algo), _stream_ptr(dev))
         _check(rc)
     return out, ds
 

@@ -229,16 +229,50 @@ int rows_dispatch(RowsCall c) {
     const long long gen_units = (long long)B * C * p.KC;
     if (gen_units >= (1ll << 31)) return SD_ERR_SHAPE;
 
-    enum { kGeneric, kRegs, kStream } path;
+    // cluster-resident single pass: the longest row of the larger-group loss, cut into nc slices, must fit
+    // nc CTAs' shared memory, and a slice may intersect only a few rows of the smaller-group loss
+    sd::ClusterGeom cg;
+    std::memset(&cg, 0, sizeof(cg));
+    bool cluster_ok = false;
+    if (layout_ok && !c.perm && c.mse_weight == 0.f) {
+        const int g_big = c.group[c.nl - 1];
+        const long long hwv = (long long)HW / VE;
+        const long long lv = (long long)g_big * hwv;
+        const long long rv0 = (long long)g0 * hwv;
+        const long long slice_cap = (long long)sd::kClusterMaxChunks * sd::kClusterChunkVecs;
+        for (int nc = 1; nc <= sd::kClusterMaxSize && !cluster_ok; nc *= 2) {
+            long long slv = (lv + nc - 1) / nc;
+            slv = (slv + sd::kClusterChunkVecs - 1) / sd::kClusterChunkVecs * sd::kClusterChunkVecs;
+            if (slv > slice_cap) continue;
+            if (rv0 < 512) break;
+            if (slv / rv0 + 2 > sd::kClusterMaxPieces) continue;  // more, shorter slices
+            cg.nc = nc;
+            cg.g_big = g_big;
+            cg.G_big = (C + g_big - 1) / g_big;
+            cg.hwv = (int)hwv;
+            cg.slv = (int)slv;
+            cg.rv0 = (int)rv0;
+            cg.total_sr = B * cg.G_big;
+            cluster_ok = sd::launch_kl_rows_cluster(p, cg, c.dtype == SD_BF16, dev.sms, nullptr, true) == cudaSuccess;
+        }
+    }
+
+    enum { kGeneric, kRegs, kStream, kCluster } path;
     switch (c.algo) {
-        case SD_ALGO_AUTO: path = !layout_ok ? kGeneric : (fits_regs ? kRegs : kStream); break;
+        case SD_ALGO_AUTO:
+            path = !layout_ok ? kGeneric : (fits_regs ? kRegs : (cluster_ok ? kCluster : kStream));
+            break;
         case SD_ALGO_TMA:
             if (!layout_ok) return SD_ERR_UNSUPPORTED;
-            path = fits_regs ? kRegs : kStream;
+            path = fits_regs ? kRegs : (cluster_ok ? kCluster : kStream);
             break;
         case SD_ALGO_STREAM:
             if (!layout_ok) return SD_ERR_UNSUPPORTED;
             path = kStream;
+            break;
+        case SD_ALGO_CLUSTER:
+            if (!cluster_ok) return SD_ERR_UNSUPPORTED;
+            path = kCluster;
             break;
         case SD_ALGO_GENERIC: path = kGeneric; break;
         default: return SD_ERR_VALUE;
@@ -273,6 +307,10 @@ int rows_dispatch(RowsCall c) {
         e = sd::launch_kl_rows_tma(p, c.dtype == SD_BF16, grid, st);
         g_launches += 1;
         t_last_kernel = "kl_rows_tma_kernel";
+    } else if (path == kCluster) {
+        e = sd::launch_kl_rows_cluster(p, cg, c.dtype == SD_BF16, dev.sms, st, false);
+        g_launches += 1;
+        t_last_kernel = c.nl == 2 ? "kl_rows_cluster_kernel(2 losses)" : "kl_rows_cluster_kernel";
     } else if (path == kStream) {
         e = sd::launch_kl_rows_stream(p, c.dtype == SD_BF16, dev.sms, st);
         g_launches += 1;
@@ -310,7 +348,7 @@ int sd_kl_rows_multi_fwd_bwd(const void* S, const void* T, void* dS, int n_losse
                              const float* taus, const float* alphas, float* const* losses, float* const* row_kls,
                              const float* const* grad_outputs, const unsigned* run_if,
                              int B, int C, int HW, int dtype, float grad_scale,
-                             void* workspace, size_t workspace_bytes, void* stream) {
+                             void* workspace, size_t workspace_bytes, int algo, void* stream) {
     if (!groups || !taus || !alphas || !losses) return SD_ERR_NULL;
     if (n_losses < 1 || n_losses > sd::kMaxLosses) return SD_ERR_VALUE;
     RowsCall c;
@@ -327,7 +365,8 @@ int sd_kl_rows_multi_fwd_bwd(const void* S, const void* T, void* dS, int n_losse
     c.run_if = run_if;
     c.grad_scale = grad_scale;
     c.workspace = workspace; c.workspace_bytes = workspace_bytes;
-    c.algo = SD_ALGO_TMA; c.stream = stream;
+    if (algo == SD_ALGO_GENERIC) return SD_ERR_UNSUPPORTED;
+    c.algo = algo == SD_ALGO_AUTO ? SD_ALGO_TMA : algo; c.stream = stream;
     return rows_dispatch(c);
 }
 

@@ -15,6 +15,10 @@ int kl_rows_tma_chunk_capacity();
 cudaError_t launch_kl_rows_stream(const RowsParams& p, bool bf16, int sms, cudaStream_t stream);
 int kl_rows_stream_chunk_capacity();
 
+// kl_rows_cluster.cu   (probe_only: just answer whether a cluster of g.nc CTAs can be resident)
+cudaError_t launch_kl_rows_cluster(const RowsParams& p, const ClusterGeom& g, bool bf16, int sms, cudaStream_t stream,
+                                   bool probe_only);
+
 // kl_pixels.cu   (mapS/mapT point at CUtensorMap objects)
 cudaError_t launch_kl_pixels_tma(const void* mapS, const void* mapT, const PixParams& p, bool bf16, int grid,
                                  size_t smem, cudaStream_t stream);

@@ -46,6 +46,9 @@ class _KLRows(torch.autograd.Function):
         return (_finish_backward(ctx, grad_output),) + (None,) * 8
 
 
+PAIR_ALGO = 'auto'      # kernel of the fused two-loss launch: 'auto' | 'cluster' | 'stream' (tests force one)
+
+
 class _KLRowsMulti(torch.autograd.Function):
     """Two channel-mode KL losses on one pair, one kernel: returns both scalars; dS is their summed gradient.
 
@@ -57,10 +60,12 @@ class _KLRowsMulti(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_student, x_teacher, g0, tau0, alpha0, g1, tau1, alpha1):
-        losses, ds = _cabi.kl_rows_multi(x_student, x_teacher, (g0, g1), (tau0, tau1), (alpha0, alpha1))
+        algo = _cabi.ALGOS[PAIR_ALGO]
+        losses, ds = _cabi.kl_rows_multi(x_student, x_teacher, (g0, g1), (tau0, tau1), (alpha0, alpha1), algo=algo)
         need_grad = x_student.requires_grad
         ctx.ds = ds if need_grad else None
         ctx.cfg = ((g0, g1), (tau0, tau1), (alpha0, alpha1))
+        ctx.algo = algo
         ctx.in_dtype, ctx.in_shape = x_student.dtype, x_student.shape
         if need_grad:
             ctx.save_for_backward(x_student, x_teacher)
@@ -84,7 +89,7 @@ class _KLRowsMulti(torch.autograd.Function):
             x_student, x_teacher = ctx.saved_tensors
             groups, taus, alphas = ctx.cfg
             _cabi.kl_rows_multi(x_student, x_teacher, groups, taus, alphas, grad_outputs=(go0, go1), run_if=flag,
-                                ds=ds)
+                                ds=ds, algo=ctx.algo)
         if ds.dtype != ctx.in_dtype:
             ds = ds.to(ctx.in_dtype)
         return (ds.view(ctx.in_shape),) + (None,) * 7

@@ -103,6 +103,23 @@ def _oracle_run(preset, kw, s, t, gt_hw, n_iter, perm=None):
 CFG1 = (2, 150, 64, 64)
 
 
+@pytest.mark.parametrize('g,shape', [(3, CFG1), (10, CFG1), (30, CFG1), (10, (1, 25, 128, 128)), (3, (2, 7, 96, 96)),
+                                     (5, (3, 12, 72, 72))])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_cluster_resident_rows(g, shape, dtype):
+    """Rows kept resident in the shared memory of a thread-block cluster (1, 2, 4 or 8 CTAs per row),
+    complete and ragged (25 % 10, 7 % 3 != 0) groups, slices that end inside a chunk (96x96, 72x72)."""
+    s, t = seeded_pair(shape, seed=g, dtype=dtype)
+    kw = dict(group_size=g, alpha=3, tau=2)
+    ref = _oracle_run('CGDLoss', kw, s, t, shape[2:], 1)
+    got = _run(sd.CGDLoss(**kw), s, t, shape[2:], 1, 'cluster')
+    assert _cabi.last_kernel() in ('kl_rows_cluster_kernel', 'scale_grad_kernel')
+    if dtype == torch.bfloat16:
+        _assert_close(*got, *ref, loss_rtol=2e-5, grad_rtol=BF16_GRAD_RTOL)
+    else:
+        _assert_close(*got, *ref)
+
+
 @pytest.mark.parametrize('algo', ['tma', 'stream', 'generic'])
 @pytest.mark.parametrize('g', [1, 3, 10, 30, 50, 150])
 def test_cfg1_group_size_sweep(g, algo):
@@ -310,9 +327,17 @@ PAIR_CASES = [
 ]
 
 
+@pytest.fixture
+def pair_algo(request):
+    SF.PAIR_ALGO = request.param
+    yield request.param
+    SF.PAIR_ALGO = 'auto'
+
+
+@pytest.mark.parametrize('pair_algo', ['cluster', 'stream'], indirect=True)
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('case', range(len(PAIR_CASES)))
-def test_two_losses_one_launch(case, dtype):
+def test_two_losses_one_launch(case, dtype, pair_algo):
     shape, ka, kb = PAIR_CASES[case]
     s, t = seeded_pair(shape, seed=100 + case, scale=1.5, dtype=dtype)
     ra = _oracle_run('CGDLoss', ka, s, t, shape[2:], 1)
@@ -323,7 +348,7 @@ def test_two_losses_one_launch(case, dtype):
     pa, pb = ca.plan(x, tg, None, 1), cb.plan(x, tg, None, 1)
     assert sd.KLDLoss.can_fuse(pa, pb)
     la, lb = sd.KLDLoss.run_pair(pa, pb)
-    assert _cabi.last_kernel() == 'kl_rows_stream_kernel(2 losses)'
+    assert _cabi.last_kernel() == f'kl_rows_{pair_algo}_kernel(2 losses)'
     (la + lb).backward()
     torch.cuda.synchronize()
     assert _cabi.workspace_error_flag() == 0
@@ -333,8 +358,9 @@ def test_two_losses_one_launch(case, dtype):
     _assert_close(la.item() + lb.item(), x.grad.float().cpu(), ra[0] + rb[0], ra[1] + rb[1], loss_rtol=lt, grad_rtol=gt_)
 
 
+@pytest.mark.parametrize('pair_algo', ['cluster', 'stream'], indirect=True)
 @pytest.mark.parametrize('w', [(512.0, 512.0), (2.0, 5.0), (1.0, 0.0)])
-def test_two_losses_upstream_gradients(w):
+def test_two_losses_upstream_gradients(w, pair_algo):
     """Equal upstream gradients scale dS in place; different ones trigger the conditional re-run."""
     shape, ka, kb = PAIR_CASES[0]
     s, t = seeded_pair(shape, seed=77)
@@ -362,7 +388,7 @@ def test_dispatcher_batches_entries_on_the_same_tensors():
     before = _cabi.launch_count()
     out = d({'decode_head.linear_pred': x, 'decode_head': x}, {'decode_head.linear_pred': tg, 'decode_head': tg},
             gt, 1, None, None)
-    assert _cabi.launch_count() - before == 1 and _cabi.last_kernel() == 'kl_rows_stream_kernel(2 losses)'
+    assert _cabi.launch_count() - before == 1 and _cabi.last_kernel() == 'kl_rows_cluster_kernel(2 losses)'
     assert list(out) == ['loss_decode_head.linear_pred<->decode_head.linear_pred_other',
                          'loss_decode_head<->decode_head_other']
     sum(out.values()).backward()
