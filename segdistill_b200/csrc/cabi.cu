@@ -234,9 +234,9 @@ int rows_dispatch(RowsCall c) {
     sd::ClusterGeom cg;
     std::memset(&cg, 0, sizeof(cg));
     bool cluster_ok = false;
-    if (layout_ok && !c.perm && c.mse_weight == 0.f) {
+    if (layout_ok && HW % 4 == 0 && !c.perm && c.mse_weight == 0.f) {
         const int g_big = c.group[c.nl - 1];
-        const long long hwv = (long long)HW / VE;
+        const long long hwv = (long long)HW / 4;   // the cluster kernel works on 4-element vectors
         const long long lv = (long long)g_big * hwv;
         const long long rv0 = (long long)g0 * hwv;
         const long long slice_cap = (long long)sd::kClusterMaxChunks * sd::kClusterChunkVecs;
@@ -260,11 +260,12 @@ int rows_dispatch(RowsCall c) {
     enum { kGeneric, kRegs, kStream, kCluster } path;
     switch (c.algo) {
         case SD_ALGO_AUTO:
-            path = !layout_ok ? kGeneric : (fits_regs ? kRegs : (cluster_ok ? kCluster : kStream));
+            path = !layout_ok ? kGeneric : (fits_regs ? kRegs : (cluster_ok && c.nl == 2 ? kCluster : kStream));
             break;
         case SD_ALGO_TMA:
             if (!layout_ok) return SD_ERR_UNSUPPORTED;
-            path = fits_regs ? kRegs : (cluster_ok ? kCluster : kStream);
+            // (measured on B200: the cluster-resident kernel wins for two fused losses, the streaming kernel for one)
+            path = fits_regs ? kRegs : (cluster_ok && c.nl == 2 ? kCluster : kStream);
             break;
         case SD_ALGO_STREAM:
             if (!layout_ok) return SD_ERR_UNSUPPORTED;

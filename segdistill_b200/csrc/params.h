@@ -106,15 +106,15 @@ inline RowsWorkspace rows_workspace_layout(long long B, long long C, long long H
 
 // ---------------------------------------------------------------- rows, cluster-resident kernel
 constexpr int kClusterMaxSize = 8;     // portable cluster size
-constexpr int kClusterMaxChunks = 8;   // 32 KB chunks (S + T) of a CTA's slice (TMEM holds 8 per thread)
-constexpr int kClusterChunkVecs = 1024;  // 16-byte vectors per chunk and tensor
+constexpr int kClusterMaxChunks = 6;   // 4096-element chunks of a CTA's slice (TMEM: 20 columns per chunk and thread)
+constexpr int kClusterChunkVecs = 1024;  // 4-element vectors per chunk and tensor
 constexpr int kClusterMaxPieces = 8;   // rows of l[0] that may intersect one slice
 // a "super-row" is a row of the loss with the larger group; the cluster keeps it resident, slice by slice
 struct ClusterGeom {
     int nc;        // CTAs per cluster
     int g_big;     // channels per super-row
     int G_big;     // super-rows per sample
-    int hwv;       // 16-byte vectors per channel plane
+    int hwv;       // 4-element vectors per channel plane
     int slv;       // vectors per slice (multiple of kClusterChunkVecs)
     int rv0;       // vectors per complete row of l[0]
     int total_sr;  // B * G_big
