@@ -71,6 +71,23 @@ bool encode_pixel_map(CUtensorMap* m, const void* base, int B, int C, int HW, in
     return r == CUDA_SUCCESS;
 }
 
+// (B*C, HW) view of an NCHW map; box = (128 bytes of HW, rows channels), 128-byte swizzle for the tensor cores
+bool encode_rows_map(CUtensorMap* m, const void* base, int B, int C, int HW, int dtype, int box_cols, int box_rows,
+                     bool atom32 = false) {
+    auto enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t es = (cuuint64_t)elem_size(dtype);
+    cuuint64_t gdim[2] = {(cuuint64_t)HW, (cuuint64_t)B * (cuuint64_t)C};
+    cuuint64_t gstr[1] = {(cuuint64_t)HW * es};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = enc(m, dtype == SD_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                           const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 }  // namespace
 
 extern "C" {
@@ -528,6 +545,50 @@ int sd_scale_grad2(void* dS, int64_t numel, int dtype, const float* grad_output0
                                            grid, static_cast<cudaStream_t>(stream));
     g_launches += 1;
     t_last_kernel = "scale_grad2_kernel";
+    return e == cudaSuccess ? SD_OK : (int)e;
+}
+
+}  // extern "C"
+
+// ============================================================================ CGD correlation (extension)
+extern "C" {
+
+size_t sd_cgd_corr_workspace_bytes(int B, int C, int HW, int group) {
+    if (B <= 0 || C <= 0 || HW <= 0 || group <= 0) return 0;
+    return sd::cgd_corr_workspace_bytes(B, C, HW, group);
+}
+
+int sd_cgd_corr_fwd_bwd(const void* S, const void* T, void* dS, float* loss, int B, int C, int HW, int group, int dtype,
+                        float alpha, float grad_scale, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!S || !T || !dS || !loss || !workspace) return SD_ERR_NULL;
+    if (dtype != SD_F32 && dtype != SD_BF16) return SD_ERR_DTYPE;
+    if (B <= 0 || C <= 0 || HW <= 0) return SD_ERR_SHAPE;
+    if (group < 1) return SD_ERR_VALUE;
+    if ((long long)B * C >= (1ll << 31) || (long long)B * C * HW >= (1ll << 40)) return SD_ERR_SHAPE;
+    if (workspace_bytes < sd::cgd_corr_workspace_bytes(B, C, HW, group)) return SD_ERR_WORKSPACE;
+    DeviceInfo& dev = device_info();
+    if (dev.cc_major != 10) return SD_ERR_DEVICE;
+    const int es = elem_size(dtype);
+    // TMA rows and 16-element epilogue vectors
+    if (((long long)HW * es) % 16 != 0 || HW % 16 != 0 || !aligned16(S) || !aligned16(T) || !aligned16(dS))
+        return SD_ERR_UNSUPPORTED;
+    int rows0 = 0, rows1 = 0, kbox = 0;
+    if (!sd::cgd_corr_geometry(B, C, HW, group, dtype, &rows0, &rows1, &kbox)) return SD_ERR_UNSUPPORTED;  // group > 256
+    // maps 0-3: S, T tiles for the Gram (K-major, 128-byte swizzle); maps 4-5: the S tiles again for the gradient
+    // GEMM, where they are read MN-major - 32-bit operands then need the 32-byte-atom flavour of the swizzle
+    alignas(64) CUtensorMap maps[6];
+    const bool atom32 = dtype == SD_F32;
+    if (!encode_rows_map(&maps[0], S, B, C, HW, dtype, kbox, rows0) ||
+        !encode_rows_map(&maps[1], T, B, C, HW, dtype, kbox, rows0) ||
+        !encode_rows_map(&maps[2], S, B, C, HW, dtype, kbox, rows1 > 0 ? rows1 : rows0) ||
+        !encode_rows_map(&maps[3], T, B, C, HW, dtype, kbox, rows1 > 0 ? rows1 : rows0) ||
+        !encode_rows_map(&maps[4], S, B, C, HW, dtype, kbox, rows0, atom32) ||
+        !encode_rows_map(&maps[5], S, B, C, HW, dtype, kbox, rows1 > 0 ? rows1 : rows0, atom32))
+        return (int)cudaErrorInvalidValue;
+    cudaError_t e = sd::launch_cgd_corr(dS, loss, B, C, HW, group, dtype, alpha, grad_scale, workspace, maps,
+                                        static_cast<cudaStream_t>(stream));
+    g_launches += 3;
+    t_last_kernel = "cgd_corr (gram, mask, grad: tcgen05)";
     return e == cudaSuccess ? SD_OK : (int)e;
 }
 

@@ -27,6 +27,12 @@ size_t pix_tma_smem_bytes(int C, int pxt, int nstages);
 int kl_pixels_tma_max_channels(bool bf16);
 int kl_pixels_tile_pixels(bool bf16);
 
+// corr_gemm.cu   (maps: CUtensorMap[4] built by cabi.cu with the box rows cgd_corr_geometry reports)
+size_t cgd_corr_workspace_bytes(int B, int C, int HW, int group);
+bool cgd_corr_geometry(int B, int C, int HW, int group, int dtype, int* rows0, int* rows1, int* kbox);
+cudaError_t launch_cgd_corr(void* dS, float* loss, int B, int C, int HW, int group, int dtype, float alpha, float grad_scale,
+                            void* workspace, const void* maps, cudaStream_t stream);
+
 // mse.cu
 cudaError_t launch_mse(const void* S, const void* T, void* dS, float* loss, float* partials, long long n, bool bf16,
                        float gcoef, float scale, int grid, cudaStream_t stream);

@@ -524,3 +524,26 @@ def test_mse_full_size_and_scale_grad():
     assert torch.equal(ds, keep)
     _cabi.scale_grad_(ds, torch.full((), 512.0, device=dev()))
     assert torch.equal(ds, keep * 512.0)
+
+
+# ------------------------------------------------------------------ CGD correlation extension (tcgen05)
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('shape,g', [((2, 20, 32, 32), 10), ((2, 150, 64, 64), 10), ((1, 150, 32, 32), 150),
+                                     ((2, 32, 16, 16), 3), ((1, 64, 48, 48), 30), ((3, 150, 16, 16), 50)])
+def test_cgd_corr_extension(shape, g, dtype):
+    """Per-group Gram-matrix loss on the tensor cores (not in the reference; oracle = corr_loss_torch).
+    fp32 inputs run as tf32 (10-bit mantissa): loss and gradient within 3e-3; bf16 inputs are exact in the
+    multiplier, fp32 accumulation: loss 1e-4, gradient 1 bf16 ulp of max|grad| (output rounding + bf16 A operand)."""
+    s, t = seeded_pair(shape, seed=g, dtype=dtype)
+    x = s.float().clone().requires_grad_(True)
+    ref = oracle.corr_loss_torch(x, t.float(), g, 2.0)
+    ref.backward()
+    y = s.to(dev()).requires_grad_(True)
+    got = sd.CGDCorrLoss(group_size=g, alpha=2.0)(y, t.to(dev()))
+    got.backward()
+    torch.cuda.synchronize()
+    lt, gtol = (3e-3, 3e-3) if dtype == torch.float32 else (1e-4, 2.0 ** -7)
+    assert rel_err(got.item(), ref.item()) <= lt, (got.item(), ref.item())
+    scale = x.grad.abs().max().item()
+    err = (y.grad.float().cpu() - x.grad).abs().max().item()
+    assert err <= gtol * scale, (err, scale)
