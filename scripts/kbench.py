@@ -48,6 +48,11 @@ def main():
         'cgd10_f32_stream': (L, torch.float32, lambda s, t: _cabi.kl_rows(s, t, group=10, tau=2.0, alpha=3.0, algo=3)),
         'fused_f32_stream': (L, torch.float32,
                              lambda s, t: _cabi.kl_rows_multi(s, t, (10, 1), (2.0, 1.0), (3.0, 1.0), algo=3)),
+        'corr10_f32': (L, torch.float32, lambda s, t: _cabi.cgd_corr(s, t, group=10)),
+        'corr10_bf16': (L, torch.bfloat16, lambda s, t: _cabi.cgd_corr(s, t, group=10)),
+        'corr150_bf16': (L, torch.bfloat16, lambda s, t: _cabi.cgd_corr(s, t, group=150)),
+        'corr256_512ch_bf16': ((16, 512, 64, 64), torch.bfloat16, lambda s, t: _cabi.cgd_corr(s, t, group=256)),
+        'corr256_512ch_f32': ((16, 512, 64, 64), torch.float32, lambda s, t: _cabi.cgd_corr(s, t, group=256)),
         'pd_f32': (L, torch.float32, lambda s, t: _cabi.kl_pixels(s, t)),
         'pd_bf16': (L, torch.bfloat16, lambda s, t: _cabi.kl_pixels(s, t)),
         'cd_512ch_f32': ((16, 512, 64, 64), torch.float32, lambda s, t: _cabi.kl_rows(s, t, group=1, tau=4.0)),

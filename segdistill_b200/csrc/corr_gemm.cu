@@ -158,7 +158,7 @@ corr_gram_kernel(const __grid_constant__ CUtensorMap mapS0, const __grid_constan
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
-    if (warp == 0) tc_alloc(tmem_slot, kGTmemCols);
+    if (warp == 0) tc_alloc(tmem_slot, (uint32_t)(p.MT * 256));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -246,36 +246,41 @@ corr_gram_kernel(const __grid_constant__ CUtensorMap mapS0, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tc_dealloc(tmem, kGTmemCols);
+    if (warp == 0) tc_dealloc(tmem, (uint32_t)(p.MT * 256));
 }
 
 // ====================================================================================================
 // K2: sum the splits, keep the block-diagonal, loss, A operand of K3
 // ====================================================================================================
+constexpr int kMaskPerCta = 2048;   // Gram entries per CTA of K2
+
 template <bool BF16>
 __global__ void __launch_bounds__(256) corr_mask_kernel(const CorrParams p) {
     __shared__ double red[8];
-    const int blk = blockIdx.x;
+    const int M = p.MT * 128;
+    const int chunks = (M * p.CBp + kMaskPerCta - 1) / kMaskPerCta;
+    const int blk = blockIdx.x / chunks, chunk = blockIdx.x - blk * chunks;
     const int bi = blk % p.blocks_per_sample;
     const int c_real = min(p.CB, p.C - bi * p.CB);                 // real channels of this block
-    const int M = p.MT * 128;
     const float* part = p.partial + (size_t)blk * p.ksplit * (size_t)M * p.CBp;
     unsigned char* dm = p.dmask + (size_t)blk * p.dmask_bytes;
     constexpr int ES = BF16 ? 2 : 4;
     constexpr int CH = 16 / ES;                                    // elements per 16-byte chunk
+    const size_t tile_bytes = (size_t)(p.CBp / CH) * 2048;         // A operand of one 128-row tile
     double acc = 0.0;
-    for (int idx = threadIdx.x; idx < M * p.CBp; idx += 256) {
+    const int end = min(M * p.CBp, (chunk + 1) * kMaskPerCta);
+    for (int idx = chunk * kMaskPerCta + threadIdx.x; idx < end; idx += 256) {
         const int i = idx / p.CBp, j = idx - i * p.CBp;
         float e = 0.f;
-        for (int s = 0; s < p.ksplit; ++s) e += part[(size_t)s * M * p.CBp + idx];
+        for (int s = 0; s < p.ksplit; ++s) e += __ldcs(&part[(size_t)s * M * p.CBp + idx]);   // fixed order
         const bool keep = i < c_real && j < c_real && i / p.g == j / p.g;
         const float d = keep ? e * p.inv_hw : 0.f;
         acc += (double)d * (double)d;
         // canonical K-major layout without swizzle: 8-row x 16-byte core matrices; row groups 128 bytes apart
-        // (SBO), 16-byte K chunks M/8*128 bytes apart (LBO)
+        // (SBO), 16-byte K chunks 2048 bytes apart (LBO); one such operand per 128-row tile
         const int m = i >> 7, r = i & 127;
-        const size_t off = (size_t)m * (size_t)(p.CBp / CH) * 2048 + (size_t)(j / CH) * 2048 + (size_t)(r >> 3) * 128 +
-                           (size_t)(r & 7) * 16 + (size_t)(j % CH) * ES;
+        const size_t off = (size_t)m * tile_bytes + (size_t)(j / CH) * 2048 + (size_t)(r >> 3) * 128 + (size_t)(r & 7) * 16 +
+                           (size_t)(j % CH) * ES;
         const float a = p.dcoef * d;
         if (BF16) *reinterpret_cast<__nv_bfloat16*>(dm + off) = __float2bfloat16_rn(a);
         else *reinterpret_cast<float*>(dm + off) = a;
@@ -284,18 +289,26 @@ __global__ void __launch_bounds__(256) corr_mask_kernel(const CorrParams p) {
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double a = 0.0;
-        for (int w = 0; w < 8; ++w) a += red[w];
-        __stcg(&p.blk_loss[blk], (float)a);
-        __threadfence();
-        const unsigned ticket = atomicAdd(&p.ctrl[0], 1u);
+    if (threadIdx.x < 32) {
+        unsigned ticket = 0;
+        if (threadIdx.x == 0) {
+            double a = 0.0;
+            for (int w = 0; w < 8; ++w) a += red[w];
+            __stcg(&p.blk_loss[blockIdx.x], (float)a);
+            __threadfence();
+            ticket = atomicAdd(&p.ctrl[0], 1u);
+        }
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
         if (ticket == gridDim.x - 1) {
             __threadfence();
             double t = 0.0;
-            for (int i = 0; i < (int)gridDim.x; ++i) t += (double)__ldcg(&p.blk_loss[i]);   // fixed order
-            *p.loss = (float)((double)p.loss_scale * t);
-            atomicExch(&p.ctrl[0], 0u);
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) t += (double)__ldcg(&p.blk_loss[i]);   // fixed order
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+            if (threadIdx.x == 0) {
+                *p.loss = (float)((double)p.loss_scale * t);
+                atomicExch(&p.ctrl[0], 0u);
+            }
         }
     }
 }
@@ -313,8 +326,9 @@ corr_grad_kernel(const __grid_constant__ CUtensorMap mapS0, const __grid_constan
     constexpr int KSTEP = BF16 ? 16 : 8;                            // channels per MMA
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    // [A = D of the block][stages: p.gboxes x MT tiles of X_S][barriers]
-    const int a_bytes = (p.dmask_bytes + 1023) & ~1023;
+    // [A = the CTA's 128 rows of D][stages: gboxes x MT tiles of X_S][barriers]
+    const int a_tile_bytes = (p.CBp * ES / 16) * 2048;
+    const int a_bytes = (a_tile_bytes + 1023) & ~1023;
     const int stage_bytes = p.gboxes * p.MT * kGTileBytes;
     unsigned char* stages = smem + a_bytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(stages + (size_t)p.nstages * stage_bytes);
@@ -324,13 +338,18 @@ corr_grad_kernel(const __grid_constant__ CUtensorMap mapS0, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int blk = blockIdx.x / p.nsplit, split = blockIdx.x - blk * p.nsplit;
+    // CTA = (block, 128-row tile of the output, HW range)
+    const int per_blk = p.MT * p.nsplit;
+    const int blk = blockIdx.x / per_blk;
+    const int mt = (blockIdx.x - blk * per_blk) / p.nsplit, split = blockIdx.x - blk * per_blk - mt * p.nsplit;
     const int b = blk / p.blocks_per_sample, bi = blk - b * p.blocks_per_sample;
     const int row0 = b * p.C + bi * p.CB;
     const int c_real = min(p.CB, p.C - bi * p.CB);
     const int BN = p.gboxes * p.kbox;                              // HW positions per tile
     const int nt_total = (p.HW + BN - 1) / BN;
     const int t_lo = (int)((long long)nt_total * split / p.nsplit), t_hi = (int)((long long)nt_total * (split + 1) / p.nsplit);
+    const int ncols = BN < 32 ? 32 : BN;                           // TMEM columns of one accumulator buffer
+    const uint32_t tmem_cols = 2 * ncols < 32 ? 32 : 2 * ncols;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.nstages; ++s) {
@@ -343,20 +362,18 @@ corr_grad_kernel(const __grid_constant__ CUtensorMap mapS0, const __grid_constan
         }
         fence_barrier_init();
     }
-    if (warp == 0) tc_alloc(tmem_slot, kGTmemCols);
-    // A operand: the block's masked, scaled Gram difference (already in the canonical layout)
+    if (warp == 0) tc_alloc(tmem_slot, tmem_cols);
+    // A operand: rows [128 mt, 128 mt + 128) of the block's masked, scaled Gram difference (canonical layout)
     {
-        const uint4* src = reinterpret_cast<const uint4*>(p.dmask + (size_t)blk * p.dmask_bytes);
+        const uint4* src = reinterpret_cast<const uint4*>(p.dmask + (size_t)blk * p.dmask_bytes + (size_t)mt * a_tile_bytes);
         uint4* dst = reinterpret_cast<uint4*>(smem);
-        for (int i = threadIdx.x; i < p.dmask_bytes / 16; i += kGThreads) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < a_tile_bytes / 16; i += kGThreads) dst[i] = __ldg(src + i);
     }
     fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    // accumulator buffers: buf x MT tiles x BN columns
-    const int ncols = (BN + 31) & ~31;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -369,7 +386,7 @@ corr_grad_kernel(const __grid_constant__ CUtensorMap mapS0, const __grid_constan
                 mbar_arrive_expect_tx(&full[s], bytes);
                 unsigned char* st = stages + (size_t)s * stage_bytes;
                 for (int x = 0; x < p.gboxes; ++x) {
-                    // box x of tile m at (x*MT + m) * 16 KB: the MN (HW) chunks of one 128-row tile are MT*16 KB apart
+                    // box x of row tile kt at (x*MT + kt) * 16 KB: the HW chunks of one 128-row tile are MT*16 KB apart
                     tma_tile2d_g2s(st + (size_t)(x * p.MT) * kGTileBytes, &mapS0, t * BN + x * p.kbox, row0, &full[s]);
                     if (p.MT == 2)
                         tma_tile2d_g2s(st + (size_t)(x * p.MT + 1) * kGTileBytes, &mapS1, t * BN + x * p.kbox, row0 + 128,
@@ -385,8 +402,6 @@ corr_grad_kernel(const __grid_constant__ CUtensorMap mapS0, const __grid_constan
         if (lane == 0) {
             const uint32_t idesc = instr_desc(BF16, 128, BN, false, false, true);      // A K-major, B MN-major
             const uint32_t a_base = smem_u32(smem);
-            const uint32_t a_lbo = 2048, a_sbo = 128;
-            const int a_tile_bytes = (p.CBp * ES / 16) * 2048;                            // one 128-row tile of A
             int s = 0;
             uint32_t ph = 0;
             for (int t = t_lo; t < t_hi; ++t) {
@@ -396,18 +411,16 @@ corr_grad_kernel(const __grid_constant__ CUtensorMap mapS0, const __grid_constan
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint32_t sb = smem_u32(stages + (size_t)s * stage_bytes);
-                for (int m = 0; m < p.MT; ++m) {
-                    for (int k = 0; k < p.CBp; k += KSTEP) {
-                        // A: rows of tile m, K chunk k (KSTEP*ES = 32 bytes = 2 core matrices along K)
-                        const uint64_t ad = smem_desc(a_base + (uint32_t)(m * a_tile_bytes + (k * ES / 16) * 2048), a_lbo, a_sbo, 0);
-                        // B: channels k.. of the X_S tile: 8-row groups 1024 bytes apart (SBO), the HW chunks
-                        // MT*16 KB apart (LBO); channel k lives in row tile k/128
-                        const int kt = k >> 7, kr = k & 127;
-                        // (tf32 operands read MN-major use the 32-byte-atom swizzle: 4-row groups, layout type 1)
-                        const uint64_t bd = smem_desc(sb + (uint32_t)(kt * kGTileBytes + kr * 128),
-                                                      (uint32_t)(p.MT * kGTileBytes), BF16 ? 1024 : 512, BF16 ? 2 : 1);
-                        tc_mma<BF16>(tmem + (uint32_t)((buf * p.MT + m) * ncols), ad, bd, idesc, k > 0 ? 1u : 0u);
-                    }
+                for (int k = 0; k < p.CBp; k += KSTEP) {
+                    // A: K chunk k (KSTEP*ES = 32 bytes = 2 core matrices along K, 2048 bytes apart; row groups 128)
+                    const uint64_t ad = smem_desc(a_base + (uint32_t)((k * ES / 16) * 2048), 2048, 128, 0);
+                    // B: channels k.. of the X_S tile, read MN-major (HW contiguous): row groups along K (SBO), the
+                    // 128-byte HW chunks MT*16 KB apart (LBO); channel k lives in row tile k/128.  tf32 operands read
+                    // MN-major use the 32-byte-atom swizzle (4-row groups, layout type 1)
+                    const int kt = k >> 7, kr = k & 127;
+                    const uint64_t bd = smem_desc(sb + (uint32_t)(kt * kGTileBytes + kr * 128), (uint32_t)(p.MT * kGTileBytes),
+                                                  BF16 ? 1024 : 512, BF16 ? 2 : 1);
+                    tc_mma<BF16>(tmem + (uint32_t)(buf * ncols), ad, bd, idesc, k > 0 ? 1u : 0u);
                 }
                 tc_commit(&empty[s]);
                 tc_commit(&acc_full[buf]);
@@ -420,45 +433,43 @@ corr_grad_kernel(const __grid_constant__ CUtensorMap mapS0, const __grid_constan
     } else {
         const int q = warp & 3;
         T* out = static_cast<T*>(p.dS);
+        const int ch = mt * 128 + q * 32 + lane;                     // channel of the block = TMEM lane
         for (int t = t_lo; t < t_hi; ++t) {
             const int buf = (t - t_lo) & 1;
             const uint32_t aph = (uint32_t)((t - t_lo) >> 1) & 1u;
             mbar_wait(&acc_full[buf], aph);
             tc_fence_after();
-            for (int m = 0; m < p.MT; ++m) {
-                const int ch = m * 128 + q * 32 + lane;                  // channel of the block = TMEM lane
-                T* orow = out + (size_t)(row0 + ch) * p.HW + (size_t)t * BN;
-                for (int c0 = 0; c0 < BN; c0 += 16) {
-                    uint32_t v[16];
-                    tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.MT + m) * ncols + c0), v);
-                    tc_wait_ld(v);
-                    if (ch < c_real) {
-                        const int pos = t * BN + c0;
-                        if (pos + 16 <= p.HW) {
-                            if (BF16) {
-                                uint4 w0, w1;
-                                w0.x = Elem<__nv_bfloat16>::pack2(__uint_as_float(v[0]), __uint_as_float(v[1]));
-                                w0.y = Elem<__nv_bfloat16>::pack2(__uint_as_float(v[2]), __uint_as_float(v[3]));
-                                w0.z = Elem<__nv_bfloat16>::pack2(__uint_as_float(v[4]), __uint_as_float(v[5]));
-                                w0.w = Elem<__nv_bfloat16>::pack2(__uint_as_float(v[6]), __uint_as_float(v[7]));
-                                w1.x = Elem<__nv_bfloat16>::pack2(__uint_as_float(v[8]), __uint_as_float(v[9]));
-                                w1.y = Elem<__nv_bfloat16>::pack2(__uint_as_float(v[10]), __uint_as_float(v[11]));
-                                w1.z = Elem<__nv_bfloat16>::pack2(__uint_as_float(v[12]), __uint_as_float(v[13]));
-                                w1.w = Elem<__nv_bfloat16>::pack2(__uint_as_float(v[14]), __uint_as_float(v[15]));
-                                uint4* o = reinterpret_cast<uint4*>(orow + c0);
-                                o[0] = w0;
-                                o[1] = w1;
-                            } else {
-                                float4* o = reinterpret_cast<float4*>(orow + c0);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i)
-                                    o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                                       __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-                            }
+            T* orow = out + (size_t)(row0 + ch) * p.HW + (size_t)t * BN;
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t v[16];
+                tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ncols + c0), v);
+                tc_wait_ld(v);
+                if (ch < c_real) {
+                    const int pos = t * BN + c0;
+                    if (pos + 16 <= p.HW) {
+                        if (BF16) {
+                            uint4 w0, w1;
+                            w0.x = Elem<__nv_bfloat16>::pack2(__uint_as_float(v[0]), __uint_as_float(v[1]));
+                            w0.y = Elem<__nv_bfloat16>::pack2(__uint_as_float(v[2]), __uint_as_float(v[3]));
+                            w0.z = Elem<__nv_bfloat16>::pack2(__uint_as_float(v[4]), __uint_as_float(v[5]));
+                            w0.w = Elem<__nv_bfloat16>::pack2(__uint_as_float(v[6]), __uint_as_float(v[7]));
+                            w1.x = Elem<__nv_bfloat16>::pack2(__uint_as_float(v[8]), __uint_as_float(v[9]));
+                            w1.y = Elem<__nv_bfloat16>::pack2(__uint_as_float(v[10]), __uint_as_float(v[11]));
+                            w1.z = Elem<__nv_bfloat16>::pack2(__uint_as_float(v[12]), __uint_as_float(v[13]));
+                            w1.w = Elem<__nv_bfloat16>::pack2(__uint_as_float(v[14]), __uint_as_float(v[15]));
+                            uint4* o = reinterpret_cast<uint4*>(orow + c0);
+                            o[0] = w0;
+                            o[1] = w1;
                         } else {
-                            for (int i = 0; i < 16; ++i)
-                                if (pos + i < p.HW) Elem<T>::store(orow + c0 + i, __uint_as_float(v[i]));
+                            float4* o = reinterpret_cast<float4*>(orow + c0);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                   __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
                         }
+                    } else {
+                        for (int i = 0; i < 16; ++i)
+                            if (pos + i < p.HW) Elem<T>::store(orow + c0 + i, __uint_as_float(v[i]));
                     }
                 }
             }
@@ -469,7 +480,7 @@ corr_grad_kernel(const __grid_constant__ CUtensorMap mapS0, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tc_dealloc(tmem, kGTmemCols);
+    if (warp == 0) tc_dealloc(tmem, tmem_cols);
 }
 
 // ====================================================================================================
@@ -506,19 +517,22 @@ static CorrPlan corr_plan(int B, int C, int HW, int group, int dtype) {
     p.rows0 = p.CBp < 128 ? p.CBp : 128;
     p.rows1 = p.MT == 2 ? p.CBp - 128 : 0;
     const int nk = (HW + p.kbox - 1) / p.kbox;
-    int want = (2 * kPlanSMs + p.nblocks - 1) / p.nblocks;    // about two waves of CTAs
-    p.ksplit = want < 1 ? 1 : (want > nk ? nk : want);
+    // K1: about one wave of CTAs (every split costs a partial Gram in the workspace), at least 4 K steps each
+    int want = (kPlanSMs + p.nblocks - 1) / p.nblocks;
+    p.ksplit = want < 1 ? 1 : (want > nk / 4 ? (nk / 4 > 0 ? nk / 4 : 1) : want);
     if (p.ksplit > 16) p.ksplit = 16;
     p.dmask_bytes = p.MT * (p.CBp * es / 16) * 2048;
     // K3: the A operand and at least two stages of X_S tiles must fit 200 KB
     p.gboxes = kGradBoxes;
-    while (p.gboxes > 1 && ((p.dmask_bytes + 1023) & ~1023) + 2 * p.gboxes * p.MT * kGTileBytes > 200 * 1024) --p.gboxes;
+    const int a_tile = ((p.CBp * es / 16) * 2048 + 1023) & ~1023;
+    while (p.gboxes > 1 && a_tile + 2 * p.gboxes * p.MT * kGTileBytes > 200 * 1024) --p.gboxes;
     const int nt = (HW + p.gboxes * p.kbox - 1) / (p.gboxes * p.kbox);
-    p.nsplit = want < 1 ? 1 : (want > nt ? nt : want);
+    int want3 = (2 * kPlanSMs + p.nblocks * p.MT - 1) / (p.nblocks * p.MT);   // about two waves
+    p.nsplit = want3 < 1 ? 1 : (want3 > nt ? nt : want3);
     if (p.nsplit > 64) p.nsplit = 64;
     size_t o = kArenaBytes;
     pl.off_ctrl = 0;
-    pl.off_blk = o;       o += sizeof(float) * (size_t)p.nblocks;
+    pl.off_blk = o;       o += sizeof(float) * (size_t)p.nblocks * (size_t)((p.MT * 128 * p.CBp + kMaskPerCta - 1) / kMaskPerCta);
     o = (o + 255) & ~(size_t)255;
     pl.off_partial = o;   o += sizeof(float) * (size_t)p.nblocks * p.ksplit * (size_t)(p.MT * 128) * p.CBp;
     o = (o + 255) & ~(size_t)255;
@@ -546,16 +560,16 @@ static cudaError_t corr_launch_t(CorrPlan& pl, const CUtensorMap* maps, cudaStre
     CorrParams& p = pl.p;
     // K1: as many 2*MT*16 KB stages as fit
     const int st1 = 2 * p.MT * kGTileBytes;
-    int ns1 = (int)((200 * 1024) / st1);
-    if (ns1 > 8) ns1 = 8;
+    int ns1 = p.MT == 1 ? 3 : (int)((200 * 1024) / st1);   // one 128-row tile: 98 KB and 256 TMEM columns, two CTAs per SM
     const size_t smem1 = (size_t)ns1 * st1 + 2048;
     auto k1 = corr_gram_kernel<BF16>;
     cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
     if (e != cudaSuccess) return e;
     p.nstages = ns1;
     k1<<<p.nblocks * p.ksplit, kGThreads, smem1, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
-    corr_mask_kernel<BF16><<<p.nblocks, 256, 0, stream>>>(p);
-    const int a_bytes = (p.dmask_bytes + 1023) & ~1023;
+    const int chunks = (p.MT * 128 * p.CBp + kMaskPerCta - 1) / kMaskPerCta;
+    corr_mask_kernel<BF16><<<p.nblocks * chunks, 256, 0, stream>>>(p);
+    const int a_bytes = (((p.CBp * (BF16 ? 2 : 4)) / 16) * 2048 + 1023) & ~1023;
     const int st3 = p.gboxes * p.MT * kGTileBytes;
     int ns3 = (int)((200 * 1024 - a_bytes) / st3);
     if (ns3 > 4) ns3 = 4;
@@ -565,7 +579,7 @@ static cudaError_t corr_launch_t(CorrPlan& pl, const CUtensorMap* maps, cudaStre
     e = cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
     if (e != cudaSuccess) return e;
     p.nstages = ns3;
-    k3<<<p.nblocks * p.nsplit, kGThreads, smem3, stream>>>(maps[4], maps[5], p);
+    k3<<<p.nblocks * p.MT * p.nsplit, kGThreads, smem3, stream>>>(maps[4], maps[5], p);
     return cudaGetLastError();
 }
 
