@@ -252,7 +252,7 @@ corr_gram_kernel(const __grid_constant__ CUtensorMap mapS0, const __grid_constan
 // ====================================================================================================
 // K2: sum the splits, keep the block-diagonal, loss, A operand of K3
 // ====================================================================================================
-constexpr int kMaskPerCta = 2048;   // Gram entries per CTA of K2
+constexpr int kMaskPerCta = 512;    // Gram entries per CTA of K2
 
 template <bool BF16>
 __global__ void __launch_bounds__(256) corr_mask_kernel(const CorrParams p) {
@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(256) corr_mask_kernel(const CorrParams p) {
     for (int idx = chunk * kMaskPerCta + threadIdx.x; idx < end; idx += 256) {
         const int i = idx / p.CBp, j = idx - i * p.CBp;
         float e = 0.f;
+#pragma unroll 4
         for (int s = 0; s < p.ksplit; ++s) e += __ldcs(&part[(size_t)s * M * p.CBp + idx]);   // fixed order
         const bool keep = i < c_real && j < c_real && i / p.g == j / p.g;
         const float d = keep ? e * p.inv_hw : 0.f;
