@@ -61,7 +61,8 @@ extern "C" {
 #define SD_BF16 1
 
 /* algo: AUTO picks a TMA-staged kernel when the layout allows it (16-byte aligned rows): the
- * register-resident single pass for rows of up to 16384 elements; for longer rows and for two fused
+ * register-resident single pass for rows of up to 16384 elements (several whole rows per CTA pass when they
+ * are short powers of two); for longer rows and for two fused
  * losses the cluster-resident single pass (rows that fit the shared memory of 8 CTAs), else the
  * streaming two-phase kernel; the plain multi-pass kernel otherwise.  TMA = AUTO without the generic
  * fallback; STREAM / CLUSTER force that kernel (rows only; CLUSTER answers SD_ERR_UNSUPPORTED when
@@ -71,6 +72,7 @@ extern "C" {
 #define SD_ALGO_TMA     2
 #define SD_ALGO_STREAM  3
 #define SD_ALGO_CLUSTER 4
+#define SD_ALGO_ROWS1   5   /* one row per CTA pass even where several short rows could be packed (tests) */
 
 /* argument errors */
 #define SD_OK               0

@@ -274,15 +274,32 @@ int rows_dispatch(RowsCall c) {
         }
     }
 
-    enum { kGeneric, kRegs, kStream, kCluster } path;
+    // packed short rows: whole rows of 32 * TPR elements (TPR a power of two), contiguous in memory
+    bool pack_ok = false;
+    if (layout_ok && fits_regs && !c.perm && C % g0 == 0 && row_len % 32 == 0) {
+        const long long tpr = row_len / 32;
+        const long long nvec_row = row_len / VE;
+        if (tpr >= 8 && tpr <= 256 && (tpr & (tpr - 1)) == 0 && nvec_row <= 1024) {
+            pack_ok = true;
+            p.pack_tpr = (int)tpr;
+            p.pack_rows = 512 / (int)tpr;
+            p.pack_units = ((long long)B * (C / g0) + p.pack_rows - 1) / p.pack_rows;
+        }
+    }
+
+    enum { kGeneric, kRegs, kStream, kCluster, kPack } path;
     switch (c.algo) {
         case SD_ALGO_AUTO:
-            path = !layout_ok ? kGeneric : (fits_regs ? kRegs : (cluster_ok && c.nl == 2 ? kCluster : kStream));
+            path = !layout_ok ? kGeneric : (pack_ok ? kPack : fits_regs ? kRegs : (cluster_ok && c.nl == 2 ? kCluster : kStream));
             break;
         case SD_ALGO_TMA:
             if (!layout_ok) return SD_ERR_UNSUPPORTED;
             // (measured on B200: the cluster-resident kernel wins for two fused losses, the streaming kernel for one)
-            path = fits_regs ? kRegs : (cluster_ok && c.nl == 2 ? kCluster : kStream);
+            path = pack_ok ? kPack : fits_regs ? kRegs : (cluster_ok && c.nl == 2 ? kCluster : kStream);
+            break;
+        case SD_ALGO_ROWS1:
+            if (!layout_ok || !fits_regs) return SD_ERR_UNSUPPORTED;
+            path = kRegs;
             break;
         case SD_ALGO_STREAM:
             if (!layout_ok) return SD_ERR_UNSUPPORTED;
@@ -320,7 +337,12 @@ int rows_dispatch(RowsCall c) {
 
     cudaStream_t st = static_cast<cudaStream_t>(c.stream);
     cudaError_t e;
-    if (path == kRegs) {
+    if (path == kPack) {
+        int grid = (int)(p.pack_units < dev.sms ? p.pack_units : dev.sms);
+        e = sd::launch_kl_rows_pack(p, c.dtype == SD_BF16, grid, st);
+        g_launches += 1;
+        t_last_kernel = "kl_rows_pack_kernel";
+    } else if (path == kRegs) {
         int grid = (int)(p.total_units < dev.sms ? p.total_units : dev.sms);
         e = sd::launch_kl_rows_tma(p, c.dtype == SD_BF16, grid, st);
         g_launches += 1;

@@ -334,6 +334,272 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
 }
 
 // ====================================================================================================
+// packed short rows: several WHOLE rows per CTA pass
+// ====================================================================================================
+// Rows of 256 ... 8192 elements (16x16 ... 64x64 maps, CD on 512-channel features) would leave most of a 512-thread
+// CTA idle or pay two CTA barriers per tiny row.  Here a unit is 512/TPR consecutive rows (they are contiguous in
+// memory: no shuffle, C % g == 0), TPR threads x 32 elements each; every thread still keeps its elements in
+// registers, reductions stay inside the row's team (sub-warp shuffles for TPR < 32; for TPR > 32 one exchange
+// through shared memory), the ring / TMA machinery is the one of kl_rows_tma_kernel.
+template <typename T, bool MSE>
+__global__ void __launch_bounds__(kThreads, 1) kl_rows_pack_kernel(const RowsParams p) {
+    using E = Elem<T>;
+    using vec_t = typename E::vec_t;
+    constexpr int VE = E::kVec;
+    constexpr int EPT = kDataRegs;
+    constexpr int NV = EPT / VE;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
+    float* red = reinterpret_cast<float*>(full + kStages + 1);      // [2][kWarps][kRedFloats]
+    ProducerState& ps = *reinterpret_cast<ProducerState*>(red + 2 * kWarps * kRedFloats);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int TPR = p.pack_tpr;
+    const int RPU = p.pack_rows;
+    const int nvec_row = TPR * NV;                       // 16-byte vectors per row
+    const int R = p.l[0].R;
+    const int seg = TPR < 32 ? TPR : 32;                 // lanes of a row inside one warp
+    const int tw = TPR >> 5;                             // warps per row (0: several rows per warp)
+    const int q = tid / TPR, lt = tid - q * TPR;         // my row within the unit, my position in its team
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        fence_barrier_init();
+        ps.cur.u = blockIdx.x;
+        ps.stage = 0;
+        ps.free_slots = kStages;
+        ps.pol = l2_policy_evict_first();
+    }
+    __syncthreads();
+
+    auto unit_vecs = [&](long long u) {                  // vectors of unit u (the last one may hold fewer rows)
+        const long long r0 = u * RPU;
+        const int nrows = (int)(R - r0 < RPU ? R - r0 : RPU);
+        return nrows * nvec_row;
+    };
+    // TMA issue (thread 0): whole units only, as many as there are free slots for
+    auto issue_loads = [&](int newly_free) {
+        int free_slots = ps.free_slots + newly_free, pstage = ps.stage;
+        while (ps.cur.u < p.pack_units) {
+            const int nvec = unit_vecs(ps.cur.u);
+            const int nslots = (nvec + kSlotVecs - 1) / kSlotVecs;
+            if (nslots > free_slots) break;
+            const size_t base = (size_t)ps.cur.u * RPU * nvec_row * 16;     // bytes
+            for (int sl = 0; sl < nslots; ++sl) {
+                const int nv = min(kSlotVecs, nvec - sl * kSlotVecs);
+                const uint32_t bytes = (uint32_t)nv * 16u;
+                mbar_arrive_expect_tx(&full[pstage], 2u * bytes);
+                unsigned char* dst_s = smem + (size_t)pstage * kStageBytes;
+                const size_t off = base + (size_t)sl * kSlotBytes;
+                tma_bulk_g2s(dst_s, static_cast<const char*>(p.S) + off, bytes, &full[pstage], ps.pol);
+                tma_bulk_g2s(dst_s + kSlotBytes, static_cast<const char*>(p.T) + off, bytes, &full[pstage], ps.pol);
+                if (++pstage == kStages) pstage = 0;
+            }
+            free_slots -= nslots;
+            ps.cur.u += gridDim.x;
+        }
+        ps.free_slots = free_slots;
+        ps.stage = pstage;
+    };
+    if (tid == 0) issue_loads(0);
+
+    const float c2 = p.l[0].c2;
+    float s[EPT], t[EPT];
+    float my_kl = 0.f, my_sq = 0.f;
+    int stage = 0;
+    uint32_t phase = 0;
+    int par = 0;
+
+    for (long long u = blockIdx.x; u < p.pack_units; u += gridDim.x) {
+        const int nvec = unit_vecs(u);
+        const int nslots = (nvec + kSlotVecs - 1) / kSlotVecs;
+        const int nrows = nvec / nvec_row;
+        const bool active = q < nrows;
+        const int cv0 = q * nvec_row + lt;               // my first vector of the unit; the others follow at stride TPR
+        if (active) {
+            // a row never straddles slots (nvec_row <= 1024 divides the slot): one barrier per thread
+            const int sl = cv0 / kSlotVecs;
+            int st = stage + sl;
+            uint32_t ph = phase;
+            if (st >= kStages) {
+                st -= kStages;
+                ph ^= 1u;
+            }
+            mbar_wait(&full[st], ph);
+            const vec_t* bs = reinterpret_cast<const vec_t*>(smem + (size_t)st * kStageBytes) + (cv0 - sl * kSlotVecs);
+            const vec_t* bt = reinterpret_cast<const vec_t*>(smem + (size_t)st * kStageBytes + kSlotBytes) + (cv0 - sl * kSlotVecs);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                E::unpack(bs[j * TPR], &s[j * VE]);
+                E::unpack(bt[j * TPR], &t[j * VE]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                s[i] = kPadValue;
+                t[i] = kPadValue;
+            }
+        }
+        stage += nslots;
+        if (stage >= kStages) {
+            stage -= kStages;
+            phase ^= 1u;
+        }
+
+        float ms = fmaxf(s[0], kMaxFloor), mt = fmaxf(t[0], kMaxFloor);
+#pragma unroll
+        for (int i = 1; i < EPT; ++i) {
+            ms = fmaxf(ms, s[i]);
+            mt = fmaxf(mt, t[i]);
+        }
+        // the maxima consumed every shared-memory read: hand the unit's slots back
+        __syncthreads();
+        if (tid == 0) issue_loads(nslots);
+
+        float zs = 0.f, zt = 0.f, a = 0.f;
+        const float ms2 = ms * c2, mt2 = mt * c2;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const float d = t[i] - s[i];
+            if (MSE) my_sq = fmaf(d, d, my_sq);
+            const float es = fast_exp2(fmaf(s[i], c2, -ms2));
+            const float et = fast_exp2(fmaf(t[i], c2, -mt2));
+            zs += es;
+            zt += et;
+            a = fmaf(et, d, a);
+            if (!MSE) {
+                s[i] = es;
+                t[i] = et;
+            }
+        }
+        // ---- the row's lanes of this warp
+        float Ms = ms, Mt = mt;
+        for (int o = seg >> 1; o > 0; o >>= 1) {
+            Ms = fmaxf(Ms, __shfl_xor_sync(0xffffffffu, Ms, o));
+            Mt = fmaxf(Mt, __shfl_xor_sync(0xffffffffu, Mt, o));
+        }
+        float Zs = zs * fast_exp2((ms - Ms) * c2), Zt, A;
+        {
+            const float ft = fast_exp2((mt - Mt) * c2);
+            Zt = zt * ft;
+            A = a * ft;
+        }
+        for (int o = seg >> 1; o > 0; o >>= 1) {
+            Zs += __shfl_xor_sync(0xffffffffu, Zs, o);
+            Zt += __shfl_xor_sync(0xffffffffu, Zt, o);
+            A += __shfl_xor_sync(0xffffffffu, A, o);
+        }
+        // ---- the row's warps (rows wider than a warp): one exchange through shared memory
+        if (tw > 1) {
+            if (lane == 0) {
+                float* my_red = red + (par * kWarps + warp) * kRedFloats;
+                reinterpret_cast<float4*>(my_red)[0] = make_float4(Ms, Mt, Zs, Zt);
+                my_red[4] = A;
+            }
+            __syncthreads();
+            const float* rq = red + (par * kWarps + (warp / tw) * tw + (lane & (tw - 1))) * kRedFloats;
+            const float4 r0 = reinterpret_cast<const float4*>(rq)[0];
+            const float r1 = rq[4];
+            float M2s = r0.x, M2t = r0.y;
+            for (int o = tw >> 1; o > 0; o >>= 1) {
+                M2s = fmaxf(M2s, __shfl_xor_sync(0xffffffffu, M2s, o));
+                M2t = fmaxf(M2t, __shfl_xor_sync(0xffffffffu, M2t, o));
+            }
+            const float fs = fast_exp2((r0.x - M2s) * c2), ft = fast_exp2((r0.y - M2t) * c2);
+            float z2s = r0.z * fs, z2t = r0.w * ft, a2 = r1 * ft;
+            for (int o = tw >> 1; o > 0; o >>= 1) {
+                z2s += __shfl_xor_sync(0xffffffffu, z2s, o);
+                z2t += __shfl_xor_sync(0xffffffffu, z2t, o);
+                a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+            }
+            Ms = M2s;
+            Mt = M2t;
+            Zs = z2s;
+            Zt = z2t;
+            A = a2;
+            par ^= 1;
+        }
+        if (active && lt == 0) {
+            // KL(p||q) = sum p (t - s)/tau - lse_t + lse_s
+            const float kl = p.l[0].inv_tau * A / Zt - ((Mt - Ms) * p.l[0].inv_tau + (logf(Zt) - logf(Zs)));
+            if (p.l[0].row_kl) p.l[0].row_kl[u * RPU + q] = kl;
+            my_kl += kl;
+        }
+        // ---- gradient straight from registers
+        if (active) {
+            float coef = p.l[0].coef;
+            if (p.grad_out[0] != nullptr) coef *= __ldg(p.grad_out[0]);
+            const float ks = coef * fast_exp2((ms - Ms) * c2) / Zs;
+            const float kt = coef * fast_exp2((mt - Mt) * c2) / Zt;
+            vec_t* dst = reinterpret_cast<vec_t*>(static_cast<T*>(p.dS)) + (size_t)u * RPU * nvec_row + cv0;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                float o[VE];
+#pragma unroll
+                for (int k = 0; k < VE; ++k) {
+                    const int i = j * VE + k;
+                    if (MSE) {
+                        const float es = fast_exp2(fmaf(s[i], c2, -ms2));
+                        const float et = fast_exp2(fmaf(t[i], c2, -mt2));
+                        o[k] = fmaf(es, ks, -et * kt) + p.mse_gcoef * (s[i] - t[i]);
+                    } else {
+                        o[k] = fmaf(s[i], ks, -t[i] * kt);
+                    }
+                }
+                dst[j * TPR] = E::pack(o);
+            }
+        }
+    }
+
+    // ================================ loss: thread partials -> CTA partial (fixed order) -> last CTA sums
+    __syncthreads();
+    {
+        const float wk = warp_sum(my_kl), wq = MSE ? warp_sum(my_sq) : 0.f;
+        if (lane == 0) {
+            red[warp] = wk;
+            red[kWarps + warp] = wq;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        unsigned ticket = 0;
+        if (lane == 0) {
+            float ck = 0.f, cq = 0.f;
+            for (int w = 0; w < kWarps; ++w) {
+                ck += red[w];
+                cq += red[kWarps + w];
+            }
+            __stcg(&p.cta_part[blockIdx.x], ck);
+            __stcg(&p.cta_part[kMaxLosses * kMaxGrid + blockIdx.x], cq);
+            __threadfence();
+            ticket = atomicAdd(&p.ctrl[0], 1u);
+        }
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            double kl = 0.0, sq = 0.0;
+            for (int i = lane; i < (int)gridDim.x; i += 32) {
+                kl += (double)__ldcg(&p.cta_part[i]);
+                sq += (double)__ldcg(&p.cta_part[kMaxLosses * kMaxGrid + i]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                kl += __shfl_down_sync(0xffffffffu, kl, o);
+                sq += __shfl_down_sync(0xffffffffu, sq, o);
+            }
+            if (lane == 0) {
+                *p.l[0].loss = (float)((double)p.l[0].loss_scale * kl);
+                if (MSE && p.mse_loss) *p.mse_loss = (float)((double)p.mse_scale * sq);
+                atomicExch(&p.ctrl[0], 0u);
+            }
+        }
+    }
+}
+
+// ====================================================================================================
 // generic path (single loss): unit = (sample, logical channel, plane chunk); no alignment requirement
 // ====================================================================================================
 constexpr int kGenThreads = 256;
@@ -541,6 +807,27 @@ cudaError_t launch_kl_rows_tma(const RowsParams& p, bool bf16, int grid, cudaStr
 }
 
 int kl_rows_tma_chunk_capacity() { return kThreads * kDataRegs; }
+
+template <typename T, bool MSE>
+static cudaError_t launch_pack_t(const RowsParams& p, int grid, cudaStream_t stream) {
+    auto kern = kl_rows_pack_kernel<T, MSE>;
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmemBytes);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<grid, kThreads, kRowsSmemBytes, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kl_rows_pack(const RowsParams& p, bool bf16, int grid, cudaStream_t stream) {
+    const bool mse = p.mse_gcoef != 0.f || p.mse_loss != nullptr;
+    if (bf16) {
+        return mse ? launch_pack_t<__nv_bfloat16, true>(p, grid, stream) : launch_pack_t<__nv_bfloat16, false>(p, grid, stream);
+    }
+    return mse ? launch_pack_t<float, true>(p, grid, stream) : launch_pack_t<float, false>(p, grid, stream);
+}
 
 cudaError_t launch_kl_rows_generic(const RowsParams& p, bool bf16, cudaStream_t stream) {
     const long long units = (long long)p.B * p.C * p.KC;

@@ -11,6 +11,7 @@ namespace sd {
 cudaError_t launch_kl_rows_tma(const RowsParams& p, bool bf16, int grid, cudaStream_t stream);
 cudaError_t launch_kl_rows_generic(const RowsParams& p, bool bf16, cudaStream_t stream);
 int kl_rows_tma_chunk_capacity();
+cudaError_t launch_kl_rows_pack(const RowsParams& p, bool bf16, int grid, cudaStream_t stream);
 // kl_rows_stream.cu
 cudaError_t launch_kl_rows_stream(const RowsParams& p, bool bf16, int sms, cudaStream_t stream);
 int kl_rows_stream_chunk_capacity();

@@ -59,6 +59,10 @@ struct RowsParams {
     long long total_units;
     int max_row_units;    // units of the longest row of any fused loss
     int delay;            // streaming kernel: phase 2 trails phase 1 by this many units
+    // packed short rows (kl_rows_pack_kernel): a unit is pack_rows whole rows, pack_tpr threads each
+    int pack_tpr;         // threads per row (8..256, power of two); row length = 32 * pack_tpr
+    int pack_rows;        // rows per unit = 512 / pack_tpr
+    long long pack_units; // ceil(R / pack_rows)
     // backward re-runs: device scalars d(total)/d(loss_k) folded into the gradient (null = 1), and a
     // device flag that cancels the launch when it reads 0
     const float* grad_out[kMaxLosses];

@@ -547,3 +547,41 @@ def test_cgd_corr_extension(shape, g, dtype):
     scale = x.grad.abs().max().item()
     err = (y.grad.float().cpu() - x.grad).abs().max().item()
     assert err <= gtol * scale, (err, scale)
+
+
+# ------------------------------------------------------------------ several short rows per CTA pass
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('shape,g', [((2, 150, 64, 64), 1), ((4, 160, 32, 32), 1), ((4, 256, 16, 16), 1), ((3, 64, 16, 32), 1),
+                                     ((2, 6, 32, 64), 1), ((5, 7, 64, 64), 1), ((2, 12, 16, 16), 4), ((2, 12, 64, 128), 1)])
+def test_packed_short_rows(shape, g, dtype):
+    """Rows of 256..8192 elements (power of two): 512/TPR whole rows per unit, TPR = 8..256 threads per row;
+    a last unit with fewer rows (5*7 = 35 rows of 4096); the same rows one per CTA pass ('rows1') as cross-check."""
+    s, t = seeded_pair(shape, seed=shape[1], scale=2.0, dtype=dtype)
+    kw = dict(group_size=g, alpha=2, tau=3)
+    ref = _oracle_run('CGDLoss', kw, s, t, shape[2:], 1)
+    tol = dict(loss_rtol=2e-5, grad_rtol=BF16_GRAD_RTOL) if dtype == torch.bfloat16 else {}
+    got = _run(sd.CGDLoss(**kw), s, t, shape[2:], 1, 'auto')
+    L = g * shape[2] * shape[3]
+    packed = L * s.element_size() // 16 <= 1024
+    _assert_close(*got, *ref, **tol)
+    loss, ds, row_kl, _ = _cabi.kl_rows(s.to(dev()), t.to(dev()), group=g, tau=3.0, alpha=2.0, want_row_kl=True)
+    assert _cabi.last_kernel() == ('kl_rows_pack_kernel' if packed else 'kl_rows_tma_kernel')
+    loss1, ds1, row_kl1, _ = _cabi.kl_rows(s.to(dev()), t.to(dev()), group=g, tau=3.0, alpha=2.0, want_row_kl=True,
+                                           algo=_cabi.ALGO_ROWS1)
+    assert _cabi.last_kernel() == 'kl_rows_tma_kernel'
+    torch.cuda.synchronize()
+    assert rel_err(loss.item(), loss1.item()) <= 2e-6
+    assert (row_kl - row_kl1).abs().max().item() <= 2e-5 * row_kl1.abs().max().item()
+    assert (ds.float() - ds1.float()).abs().max().item() <= (2.0 ** -7 if dtype == torch.bfloat16 else 1e-5) * ds1.float().abs().max().item()
+
+
+def test_packed_short_rows_with_fused_mse():
+    shape = (2, 512, 64, 64)
+    s, t = seeded_pair(shape, seed=5)
+    crit = sd.CDMSELoss(alpha=2, tau=4, mse_weight=0.5)
+    got = _run(crit, s, t)
+    r1 = _oracle_run('CGDLoss', dict(group_size=1, alpha=2, tau=4), s, t, shape[2:], 1)
+    x = s.clone().requires_grad_(True)
+    m = oracle.mse_loss_torch(x, t, 0.5)
+    m.backward()
+    _assert_close(got[0], got[1], r1[0] + m.item(), r1[1] + x.grad)
