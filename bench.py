@@ -396,6 +396,7 @@ def extra_configs(dev):
     out = {}
 
     def timeit(fn, n=20):
+        """(eager ms, CUDA-graph replay ms) per call of fn (forward + backward through the module API)."""
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
@@ -405,7 +406,29 @@ def extra_configs(dev):
             fn()
         b.record()
         torch.cuda.synchronize()
-        return a.elapsed_time(b) / n
+        eager = a.elapsed_time(b) / n
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(n):
+                g.replay()
+            b.record()
+            torch.cuda.synchronize()
+            return eager, a.elapsed_time(b) / n
+        except Exception:
+            torch.cuda.synchronize()
+            return eager, eager
 
     def fwd_bwd(crit, s, t):
         def f():
@@ -427,9 +450,9 @@ def extra_configs(dev):
             ('cfg4_cd+mse_fused_16x512x64x64_f32', sd.CDMSELoss(alpha=1, tau=4), (16, 512, 64, 64), torch.float32),
             ('cfg4_mse_16x512x64x64_f32', sd.FeatureMSELoss(), (16, 512, 64, 64), torch.float32)):
         s, t = pair(shape, dtype)
-        ms = timeit(fwd_bwd(crit, s, t))
+        eager, ms = timeit(fwd_bwd(crit, s, t))
         nbytes = 3 * s.numel() * s.element_size()
-        out[name] = {'ms': ms, 'mpixel_s': shape[0] * shape[2] * shape[3] / ms / 1e3,
+        out[name] = {'ms': ms, 'ms_eager': eager, 'mpixel_s': shape[0] * shape[2] * shape[3] / ms / 1e3,
                      'gbs': nbytes / ms / 1e6, 'frac_of_measured_peak': nbytes / ms / 1e6 / peak}
     stages = [(16, 32, 128, 128), (16, 64, 64, 64), (16, 160, 32, 32), (16, 256, 16, 16)]
     pairs = [pair(sh, torch.float32) for sh in stages]
@@ -439,9 +462,21 @@ def extra_configs(dev):
         for s, t in pairs:
             s.grad = None
             crit(s, t, None, 1).backward()
-    ms = timeit(cfg2)
+    eager, ms = timeit(cfg2)
     nbytes = sum(3 * s.numel() * 4 for s, _ in pairs)
-    out['cfg2_cgd_4stages_b16_f32'] = {'ms': ms, 'gbs': nbytes / ms / 1e6, 'frac_of_measured_peak': nbytes / ms / 1e6 / peak}
+    out['cfg2_cgd_4stages_b16_f32'] = {'ms': ms, 'ms_eager': eager, 'mpixel_s': sum(s.shape[0] * s.shape[2] * s.shape[3] for s, _ in pairs) / ms / 1e3,
+                                       'gbs': nbytes / ms / 1e6, 'frac_of_measured_peak': nbytes / ms / 1e6 / peak}
+    # the correlation extension (tensor cores): algorithmic traffic 16 B/element fp32 (S, T read; S read again; dS written)
+    for name, g, shape, dtype in (('corr_g10_16x150x128x128_bf16', 10, (16, 150, 128, 128), torch.bfloat16),
+                                  ('corr_g10_16x150x128x128_f32', 10, (16, 150, 128, 128), torch.float32),
+                                  ('corr_g256_16x512x64x64_bf16', 256, (16, 512, 64, 64), torch.bfloat16)):
+        s, t = pair(shape, dtype)
+        eager, ms = timeit(fwd_bwd(sd.CGDCorrLoss(group_size=g), s, t))
+        nbytes = 4 * s.numel() * s.element_size()
+        gpb = -(-shape[1] // g)
+        flops = 6.0 * shape[0] * gpb * g * g * shape[2] * shape[3]        # useful: 2 Grams + the gradient GEMM
+        out[name] = {'ms': ms, 'ms_eager': eager, 'gbs': nbytes / ms / 1e6, 'frac_of_measured_peak': nbytes / ms / 1e6 / peak,
+                     'useful_tflops': flops / ms / 1e9}
     return out
 
 
