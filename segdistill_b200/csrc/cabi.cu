@@ -251,7 +251,8 @@ int rows_dispatch(RowsCall c) {
     sd::ClusterGeom cg;
     std::memset(&cg, 0, sizeof(cg));
     bool cluster_ok = false;
-    if (layout_ok && HW % 4 == 0 && !c.perm && c.mse_weight == 0.f) {
+    // (HW % 128 == 0: a warp's 32 consecutive vectors never straddle two rows of l[0] or the end of a slice)
+    if (layout_ok && HW % 128 == 0 && !c.perm && c.mse_weight == 0.f) {
         const int g_big = c.group[c.nl - 1];
         const long long hwv = (long long)HW / 4;   // the cluster kernel works on 4-element vectors
         const long long lv = (long long)g_big * hwv;

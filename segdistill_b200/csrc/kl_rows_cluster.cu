@@ -5,51 +5,67 @@
 // Same mathematics as kl_rows.cu (mmseg/models/distillation/losses.py:50-58,:108-112 + backward).
 // A CGD row (g = 10 channels of 128x128 logits) is 1.3 MB of S and T: no SM holds it, a cluster of 8
 // does.  The cluster owns one "super-row" (a row of the loss with the larger group) at a time; CTA c
-// owns slice c of it:
+// owns slice c of it.  Three kinds of warps, coupled by mbarriers only (no CTA-wide barrier in the loop):
 //
-//   phase 1   the slice streams through a 6 x 32 KB shared-memory ring (1-D TMA bulk copies, mbarrier
-//             full/empty pairs, a dedicated TMA warp).  Each of the 16 consumer warps pulls its vectors of
-//             a chunk into registers ONCE, parks the raw bits in TMEM (tcgen05.st, 16 columns per chunk and
-//             thread - the 256 KB of tensor memory hold a 32768-element fp32 slice of S and T), hands the
-//             ring slot back at once - the next super-row keeps streaming in during everything below - and
-//             updates ONLINE softmax statistics (running thread-local maximum, sums rescaled when it
-//             moves) per PIECE, the part of one row of the smaller-group loss inside this slice.
-//             Warp shuffles -> 16 warp records per piece -> one summary per piece.
-//   exchange  every CTA PUSHES its piece summaries into the shared memory of all CTAs of the cluster
-//             (st.async through DSMEM, completing bytes on the receiver's mbarrier): no cluster barrier, no
-//             release fence behind the gradient stores; one warp per row merges what arrived.
-//   phase 2   the slice comes back from TMEM (tcgen05.ld), the gradient is written once.
+//   TMA warp     streams the CTA's slices, chunk by chunk (4096 elements of S and of T), through a 6 x 32 KB
+//                shared-memory ring (1-D bulk copies, full/empty mbarriers) - up to a super-row ahead.
+//   8 PARK warps (phase 1) pull a chunk into registers once (16 elements of S and of T per thread), hand the ring
+//                slot back, update softmax statistics of the PIECE (part of one row of the smaller-group loss
+//                inside this slice) against a WARP-UNIFORM running maximum (redux.sync.max.f32), and park the
+//                exponentials in tensor memory (tcgen05.st; 32 columns per thread and chunk, 8 chunk slots per
+//                warp: all 512 columns; the references of a chunk go to shared memory, once per warp).  A piece
+//                that ends -> one warp record (transposed butterfly: 9 shuffles for 6 sums).
+//   8 GRADIENT   (phase 2) warp 8 + i reads what park warp i parked (same TMEM lane quarter, same columns):
+//     warps      tcgen05.ld brings a chunk back; one multiply-add per element and loss, no ex2 per element;
+//                written once; the TMEM slot goes back to the park warp (one mbarrier per pair and slot).
+//   stats warp   8 warp records -> one summary per piece; PUSHES the summaries into the shared memory of every
+//                CTA of the cluster (st.async through DSMEM, completing bytes on the receiver's mbarrier - no
+//                cluster barrier); merges what arrived into the row statistics the gradient warps wait for.
+//
+// Park and gradient run CONCURRENTLY on different warps of the same SM sub-partitions: the park side is bound by
+// the MUFU/FMA pipes and shared-memory reads, the gradient side by the tensor-memory read path (64 B/clk) and
+// the global stores.  The park warps run up to 8 chunks ahead of the gradient warps (a slice is 5 chunks at
+// 16x150x128x128): the statistics of super-row i travel through the cluster while super-row i + 1 is parked.
 //
 // HBM traffic is the algorithmic read S + read T + write dS.  With two losses whose temperatures are
 // tau and 2*tau (CD tau = 1 next to CGD tau = 2, the reference's defaults) exp(x/tau) = exp(x/2tau)^2:
-// 2 ex2 per element and phase instead of 4.
+// 2 ex2 per element for both losses.
+//
+// Geometry contract (cabi.cu): HW % 128 == 0, so every 32-vector row of a warp lies inside one piece of one
+// slice; slices are whole chunks.
 #include "rows_common.cuh"
 
 namespace sd {
 
-constexpr int kCCons = 512;
-constexpr int kCConsWarps = kCCons / 32;
-constexpr int kCThreads = kCCons + 32;
-constexpr int kCChunkRows = 2;                         // 4-element vectors per consumer thread, chunk and tensor
-constexpr int kCChunkVecs = kCChunkRows * kCCons;      // 1024 vectors = 4096 elements per tensor
+constexpr int kCPark = 256;                            // park threads (warps 0..7); gradient threads: warps 8..15
+constexpr int kCParkWarps = kCPark / 32;
+constexpr int kCTmaWarp = 2 * kCParkWarps;             // warp 16
+constexpr int kCStatWarp = 2 * kCParkWarps + 1;        // warp 17
+constexpr int kCThreads = 2 * kCPark + 64;
+constexpr int kCChunkRows = 4;                         // 4-element vectors per park thread, chunk and tensor
+constexpr int kCChunkVecs = kCChunkRows * kCPark;      // 1024 vectors = 4096 elements per tensor
 constexpr int kCChunkBytes = kCChunkVecs * 16;         // fp32; bf16 chunks fill half a slot
 constexpr int kCRing = 6;                              // ring slots of 32 KB (S chunk + T chunk)
-constexpr int kCMaxChunks = kClusterMaxChunks;         // chunks per slice: 6 x 20 TMEM columns per thread
-constexpr int kCRowCols = 10;                          // TMEM columns of one parked vector-row: 4 + 4 values, 2 references
+constexpr int kCSlots = 8;                             // TMEM chunk slots per park warp
+constexpr int kCSlotCols = 32;                         // ... of 32 columns: 4 vector-rows x (4 of S + 4 of T)
 constexpr int kCMaxPieces = kClusterMaxPieces;
 constexpr int kCRecFloats = 8;                         // ms, mt, {zs, zt, a} x 2
 constexpr int kCTmemCols = 512;
-static_assert(kCMaxChunks * kCChunkRows * kCRowCols * (kCConsWarps / 4) <= kCTmemCols, "TMEM columns");
+static_assert(kCSlots * kCSlotCols * (kCParkWarps / 4) == kCTmemCols, "TMEM columns");
+static_assert(kClusterMaxChunks <= kCSlots, "a slice must fit the TMEM slots");
 static_assert(kCChunkVecs == kClusterChunkVecs, "chunk size");
 
 struct ClusterSmem {
     unsigned char ring[kCRing][2][kCChunkBytes];
     uint64_t full[kCRing], empty[kCRing];
-    float rec[2][kCMaxPieces][kCConsWarps][kCRecFloats];  // warp records of the pieces, by iteration parity
+    uint64_t xch[2];                                      // bytes of the pushed summaries complete here
+    uint64_t recbar[2];                                   // 8 park warps: "my records of this row are written"
+    uint64_t finbar[2];                                   // stats warp: "the row statistics are written"
+    uint64_t tfree[kCParkWarps][kCSlots];                 // gradient warp -> its park warp: "this TMEM slot is read"
+    float rec[2][kCMaxPieces][kCParkWarps][kCRecFloats];  // warp records of the pieces, by row parity
     float summ[2][kClusterMaxSize][kCMaxPieces][kCRecFloats];  // summaries of every CTA of the cluster (pushed)
-    uint64_t xch[2];                                      // ... their bytes complete on these
-    float fin[kCMaxPieces + 1][4];                        // row statistics for phase 2: {Ms, Mt, coef/Zs, coef/Zt}
-    float klpart[kCConsWarps][2];
+    float fin[2][kCMaxPieces + 1][4];                     // row statistics for phase 2: {Ms, Mt, coef/Zs, coef/Zt}
+    float refs[kCParkWarps][kCSlots][2 * kCChunkRows];    // references of a parked chunk: {ms, mt} of its vector-rows
     uint32_t tmem_base;
 };
 constexpr size_t kClusterSmemBytes = sizeof(ClusterSmem);
@@ -93,36 +109,36 @@ __device__ __forceinline__ void tmem_fence_before_sync() {
 __device__ __forceinline__ void tmem_fence_after_sync() {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// warp-collective: thread i of the warp owns TMEM lane (lane quarter of the warp) + i, 8 consecutive columns
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4& a, const uint4& b) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
-                 "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+// one parked chunk of a thread: 32 consecutive TMEM columns of its lane.
+// warp-collective: thread i of the warp owns TMEM lane (lane quarter of the warp) + i
+struct Parked {
+    uint32_t w[kCSlotCols];
+};
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const Parked& x) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                 ::"r"(taddr), "r"(x.w[0]), "r"(x.w[1]), "r"(x.w[2]), "r"(x.w[3]), "r"(x.w[4]), "r"(x.w[5]), "r"(x.w[6]), "r"(x.w[7]), "r"(x.w[8]), "r"(x.w[9]), "r"(x.w[10]), "r"(x.w[11]), "r"(x.w[12]), "r"(x.w[13]), "r"(x.w[14]), "r"(x.w[15]), "r"(x.w[16]), "r"(x.w[17]), "r"(x.w[18]), "r"(x.w[19]), "r"(x.w[20]), "r"(x.w[21]), "r"(x.w[22]), "r"(x.w[23]), "r"(x.w[24]), "r"(x.w[25]), "r"(x.w[26]), "r"(x.w[27]), "r"(x.w[28]), "r"(x.w[29]), "r"(x.w[30]), "r"(x.w[31])
                  : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint4& a, uint4& b) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, Parked& x) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(x.w[0]), "=r"(x.w[1]), "=r"(x.w[2]), "=r"(x.w[3]), "=r"(x.w[4]), "=r"(x.w[5]), "=r"(x.w[6]), "=r"(x.w[7]), "=r"(x.w[8]), "=r"(x.w[9]), "=r"(x.w[10]), "=r"(x.w[11]), "=r"(x.w[12]), "=r"(x.w[13]), "=r"(x.w[14]), "=r"(x.w[15]), "=r"(x.w[16]), "=r"(x.w[17]), "=r"(x.w[18]), "=r"(x.w[19]), "=r"(x.w[20]), "=r"(x.w[21]), "=r"(x.w[22]), "=r"(x.w[23]), "=r"(x.w[24]), "=r"(x.w[25]), "=r"(x.w[26]), "=r"(x.w[27]), "=r"(x.w[28]), "=r"(x.w[29]), "=r"(x.w[30]), "=r"(x.w[31])
                  : "r"(taddr)
                  : "memory");
 }
-__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
-}
-__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t& a, uint32_t& b) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
-}
 // the loaded registers are operands of the wait: nothing may read (or copy) them before it
-__device__ __forceinline__ void tmem_wait_ld(uint4& a, uint4& b, uint32_t& c, uint32_t& d) {
+__device__ __forceinline__ void tmem_wait_ld(Parked& x) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(a.x), "+r"(a.y), "+r"(a.z), "+r"(a.w), "+r"(b.x), "+r"(b.y), "+r"(b.z), "+r"(b.w), "+r"(c), "+r"(d)
+                 : "+r"(x.w[0]), "+r"(x.w[1]), "+r"(x.w[2]), "+r"(x.w[3]), "+r"(x.w[4]), "+r"(x.w[5]), "+r"(x.w[6]), "+r"(x.w[7]), "+r"(x.w[8]), "+r"(x.w[9]), "+r"(x.w[10]), "+r"(x.w[11]), "+r"(x.w[12]), "+r"(x.w[13]), "+r"(x.w[14]), "+r"(x.w[15]), "+r"(x.w[16]), "+r"(x.w[17]), "+r"(x.w[18]), "+r"(x.w[19]), "+r"(x.w[20]), "+r"(x.w[21]), "+r"(x.w[22]), "+r"(x.w[23]), "+r"(x.w[24]), "+r"(x.w[25]), "+r"(x.w[26]), "+r"(x.w[27]), "+r"(x.w[28]), "+r"(x.w[29]), "+r"(x.w[30]), "+r"(x.w[31])
                  :
                  : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <typename V>
-__device__ __forceinline__ uint4 as_bits(const V& v) {
-    return *reinterpret_cast<const uint4*>(&v);
+// maximum over the warp, identical bits in every lane (also orders the lanes: everybody contributed)
+__device__ __forceinline__ float warp_max_uniform(float v) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
 }
 
 // ---------------------------------------------------------------- statistics of a part of a row
@@ -169,12 +185,13 @@ __device__ __forceinline__ void exps(float x, const float (&ref2)[NL], const flo
 }
 // reduce over `width` lanes (xor butterfly; every lane ends with the same bits): maxima first, then the
 // sums rescaled to them - one exponential stage instead of one per butterfly step
-template <int NL, int R>
-__device__ __forceinline__ PStat<NL> pstat_reduce(const PStat<NL>& x, const float (&c2)[NL], int width) {
+template <int NL, int R, int WIDTH>
+__device__ __forceinline__ PStat<NL> pstat_reduce(const PStat<NL>& x, const float (&c2)[NL]) {
     PStat<NL> r;
     r.ms = x.ms;
     r.mt = x.mt;
-    for (int o = width >> 1; o > 0; o >>= 1) {
+#pragma unroll
+    for (int o = WIDTH >> 1; o > 0; o >>= 1) {
         r.ms = fmaxf(r.ms, __shfl_xor_sync(0xffffffffu, r.ms, o));
         r.mt = fmaxf(r.mt, __shfl_xor_sync(0xffffffffu, r.mt, o));
     }
@@ -187,7 +204,8 @@ __device__ __forceinline__ PStat<NL> pstat_reduce(const PStat<NL>& x, const floa
         r.zt[k] = x.zt[k] * ft[k];
         r.a[k] = x.a[k] * ft[k];
     }
-    for (int o = width >> 1; o > 0; o >>= 1) {
+#pragma unroll
+    for (int o = WIDTH >> 1; o > 0; o >>= 1) {
 #pragma unroll
         for (int k = 0; k < NL; ++k) {
             r.zs[k] += __shfl_xor_sync(0xffffffffu, r.zs[k], o);
@@ -217,17 +235,6 @@ __device__ __forceinline__ PStat<NL> pstat_merge(const PStat<NL>& x, const PStat
     return r;
 }
 template <int NL>
-__device__ __forceinline__ void pstat_store(float* rec, const PStat<NL>& x) {
-    float v[kCRecFloats] = {x.ms, x.mt, x.zs[0], x.zt[0], x.a[0], 0.f, 0.f, 0.f};
-    if (NL == 2) {
-        v[5] = x.zs[NL - 1];
-        v[6] = x.zt[NL - 1];
-        v[7] = x.a[NL - 1];
-    }
-    reinterpret_cast<float4*>(rec)[0] = make_float4(v[0], v[1], v[2], v[3]);
-    reinterpret_cast<float4*>(rec)[1] = make_float4(v[4], v[5], v[6], v[7]);
-}
-template <int NL>
 __device__ __forceinline__ PStat<NL> pstat_from(const float4& r0, const float4& r1) {
     PStat<NL> x;
     x.ms = r0.x;
@@ -242,25 +249,83 @@ __device__ __forceinline__ PStat<NL> pstat_from(const float4& r0, const float4& 
     }
     return x;
 }
+// sums of 8 values over the 32 lanes in 9 shuffles (halve the values a lane carries at every step, then two
+// plain steps); lane L returns the total of v[L >> 2].  Fixed order: deterministic.
+__device__ __forceinline__ float warp_sum8_transposed(const float (&v)[8], int lane) {
+    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+    float w[4], u[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float keep = b4 ? v[j + 4] : v[j], send = b4 ? v[j] : v[j + 4];
+        w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float keep = b3 ? w[j + 2] : w[j], send = b3 ? w[j] : w[j + 2];
+        u[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const float keep = b2 ? u[1] : u[0], send = b2 ? u[0] : u[1];
+    float t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    return t;
+}
 __device__ __forceinline__ float kl_of_row(float inv_tau, float ms, float mt, float zs, float zt, float a) {
     // KL(p||q) = sum p (t - s)/tau - lse_t + lse_s
     return inv_tau * a / zt - ((mt - ms) * inv_tau + (logf(zt) - logf(zs)));
 }
 
-// geometry of one super-row, identical on every thread of the cluster
-struct SuperRow {
-    int b, grp;        // sample, index of the larger-group row inside it
-    int lv;            // 4-element vectors of the super-row
-    size_t base;       // element offset of its first element
+// ---------------------------------------------------------------- geometry
+// position of a super-row; walks sr += n_clusters without a division per row
+struct RowCursor {
+    int b, grp;
+    __device__ __forceinline__ void init(const ClusterGeom& g, int sr) {
+        b = sr / g.G_big;
+        grp = sr - b * g.G_big;
+    }
+    __device__ __forceinline__ void advance(const ClusterGeom& g, int step) {
+        grp += step;
+        while (grp >= g.G_big) {
+            grp -= g.G_big;
+            ++b;
+        }
+    }
+    // 4-element vectors of this super-row (the last group of a sample may be ragged)
+    __device__ __forceinline__ int lv(const RowsParams& p, const ClusterGeom& g) const {
+        return min(g.g_big, p.C - grp * g.g_big) * g.hwv;
+    }
+    __device__ __forceinline__ size_t base(const RowsParams& p, const ClusterGeom& g) const {
+        return ((size_t)b * p.C + (size_t)grp * g.g_big) * p.HW;
+    }
 };
-__device__ __forceinline__ SuperRow super_row(const RowsParams& p, const ClusterGeom& g, int sr) {
-    SuperRow x;
-    x.b = sr / g.G_big;
-    x.grp = sr - x.b * g.G_big;
-    const int ch = min(g.g_big, p.C - x.grp * g.g_big);
-    x.lv = ch * g.hwv;
-    x.base = ((size_t)x.b * p.C + (size_t)x.grp * g.g_big) * p.HW;
-    return x;
+// my slice of a super-row of lv vectors
+struct SliceGeo {
+    int v0, v1, nvs;       // the slice, in vectors of the super-row; its length
+    int r_first;           // first row of l[0] (within the super-row) that intersects it
+    int n_pieces;          // rows of l[0] that intersect it
+    int nchunks;
+    uint32_t xch_bytes;    // summaries all CTAs of the cluster push for this super-row (32 bytes a piece)
+};
+__device__ __forceinline__ int pieces_of(const ClusterGeom& g, int lv, int c) {
+    const int cv0 = min(lv, c * g.slv), cv1 = min(lv, cv0 + g.slv);
+    return cv1 > cv0 ? (cv1 - 1) / g.rv0 - cv0 / g.rv0 + 1 : 0;
+}
+__device__ __forceinline__ SliceGeo slice_geo(const ClusterGeom& g, int lv, int rank) {
+    SliceGeo s;
+    s.v0 = min(lv, rank * g.slv);
+    s.v1 = min(lv, s.v0 + g.slv);
+    s.nvs = s.v1 - s.v0;
+    s.r_first = s.v0 / g.rv0;
+    s.n_pieces = s.nvs > 0 ? (s.v1 - 1) / g.rv0 - s.r_first + 1 : 0;
+    s.nchunks = (s.nvs + kCChunkVecs - 1) / kCChunkVecs;
+    int total = 0;
+    for (int c = 0; c < g.nc; ++c) total += pieces_of(g, lv, c);
+    s.xch_bytes = (uint32_t)total * 32u;
+    return s;
+}
+// end of piece pc, in vectors of the slice
+__device__ __forceinline__ int piece_end(const ClusterGeom& g, const SliceGeo& s, int pc) {
+    return min(s.v1, (s.r_first + pc + 1) * g.rv0) - s.v0;
 }
 
 // a thread's unit of work is a 4-element vector whatever the dtype (16 bytes of fp32, 8 bytes of bf16): the
@@ -291,9 +356,17 @@ struct Vec4<__nv_bfloat16> {
 };
 
 // R: 0 = independent exponentials per loss, 2 = l[1].tau == 2 * l[0].tau.
-// With one loss, or with R == 2, phase 1 parks the EXPONENTIALS (relative to the thread's running maximum at
-// that moment, parked next to them): phase 2 is then a multiply-add per element, no ex2.  Otherwise the raw
+// With one loss, or with R == 2, phase 1 parks the EXPONENTIALS (relative to the warp's running maximum at
+// that moment, kept in shared memory): phase 2 is then a multiply-add per element, no ex2.  Otherwise the raw
 // values are parked and phase 2 recomputes.
+#ifdef SD_CLUSTER_TIMING
+#define SD_TICK(var) const long long var = clock64()
+#define SD_TACC(slot, a, b) tacc[slot] += (b) - (a)
+#else
+#define SD_TICK(var)
+#define SD_TACC(slot, a, b)
+#endif
+
 template <typename T, int NL, int R>
 __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const RowsParams p, const ClusterGeom g) {
     using V = Vec4<T>;
@@ -311,7 +384,6 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
     const int warp = tid >> 5;
     const uint32_t rank = cluster_ctarank();
     const int NC = g.nc;
-    const int slv = g.slv;
     const int cluster_id = blockIdx.x / NC;
     const int n_clusters = gridDim.x / NC;
 
@@ -320,13 +392,18 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
     if (tid == 0) {
         for (int c = 0; c < kCRing; ++c) {
             mbar_init(&sm.full[c], 1);
-            mbar_init(&sm.empty[c], kCConsWarps);
+            mbar_init(&sm.empty[c], kCParkWarps);
         }
-        mbar_init(&sm.xch[0], 1);
-        mbar_init(&sm.xch[1], 1);
+        for (int q = 0; q < 2; ++q) {
+            mbar_init(&sm.xch[q], 1);
+            mbar_init(&sm.recbar[q], kCParkWarps);
+            mbar_init(&sm.finbar[q], 1);
+        }
+        for (int w = 0; w < kCParkWarps; ++w)
+            for (int q = 0; q < kCSlots; ++q) mbar_init(&sm.tfree[w][q], 1);
         fence_barrier_init();
     }
-    if (warp == kCConsWarps) tmem_alloc(&sm.tmem_base, kCTmemCols);
+    if (warp == kCTmaWarp) tmem_alloc(&sm.tmem_base, kCTmemCols);
     tmem_fence_before_sync();
     __syncthreads();
     tmem_fence_after_sync();
@@ -336,26 +413,32 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
     cluster_wait_acquire();
 
     const int n_iter = cluster_id < g.total_sr ? (g.total_sr - cluster_id + n_clusters - 1) / n_clusters : 0;
+    // every complete super-row is cut the same way; only a ragged last group needs its own geometry
+    const int lv_full = g.g_big * g.hwv;
+    const SliceGeo geo_full = slice_geo(g, lv_full, (int)rank);
+    auto geo_of = [&](int lv) { return lv == lv_full ? geo_full : slice_geo(g, lv, (int)rank); };
 
-    if (warp == kCConsWarps) {
+    if (warp == kCTmaWarp) {
         // =====================================================================================
-        // TMA warp: lane 0 streams this CTA's slices, chunk by chunk, into the ring as slots drain - up to
-        // a whole super-row ahead of the consumers
+        // TMA warp: lane 0 streams this CTA's slices, chunk by chunk, into the ring as slots drain
         // =====================================================================================
-        const uint64_t pol = l2_policy_evict_first();
-        int slot = 0;
-        uint32_t phase = 0;
         if (lane == 0) {
+            const uint64_t pol = l2_policy_evict_first();
+            int slot = 0;
+            uint32_t phase = 0;
+            RowCursor rc;
+            rc.init(g, cluster_id);
             for (int it = 0; it < n_iter; ++it) {
-                const SuperRow x = super_row(p, g, cluster_id + it * n_clusters);
-                const int v0 = min(x.lv, (int)rank * slv);
-                const int v1 = min(x.lv, v0 + slv);
+                const int lv = rc.lv(p, g);
+                const size_t base = rc.base(p, g);
+                const int v0 = min(lv, (int)rank * g.slv);
+                const int v1 = min(lv, v0 + g.slv);
                 for (int c = 0; c * kCChunkVecs < v1 - v0; ++c) {
                     mbar_wait(&sm.empty[slot], phase ^ 1u);
                     const int nv = min(kCChunkVecs, v1 - v0 - c * kCChunkVecs);
                     const uint32_t bytes = (uint32_t)nv * (uint32_t)sizeof(vec_t);
                     mbar_arrive_expect_tx(&sm.full[slot], 2u * bytes);
-                    const size_t off = (x.base + (size_t)(v0 + c * kCChunkVecs) * VE) * sizeof(T);
+                    const size_t off = (base + (size_t)(v0 + c * kCChunkVecs) * VE) * sizeof(T);
                     tma_bulk_g2s(sm.ring[slot][0], static_cast<const char*>(p.S) + off, bytes, &sm.full[slot], pol);
                     tma_bulk_g2s(sm.ring[slot][1], static_cast<const char*>(p.T) + off, bytes, &sm.full[slot], pol);
                     if (++slot == kCRing) {
@@ -363,6 +446,7 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
                         phase ^= 1u;
                     }
                 }
+                rc.advance(g, n_clusters);
             }
         }
         __syncwarp();
@@ -372,305 +456,437 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
         return;
     }
 
-    // =========================================================================================
-    // consumer warps
-    // =========================================================================================
     float c2[NL];
 #pragma unroll
     for (int k = 0; k < NL; ++k) c2[k] = p.l[k].c2;
     const int rv0 = g.rv0;             // vectors of a complete row of l[0]
-    // my TMEM window: lane quarter of the warp, 128 columns per warp of that quarter; a vector-row of a
-    // chunk takes kCRowCols columns: 4 + 4 parked values of S and T, and the two references
-    const uint32_t tmem_mine = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 128);
-    int slot = 0;
-    uint32_t phase = 0;
-    float kl_acc[NL];                  // lane 0 of the warps that finish rows
+
+    if (warp == kCStatWarp) {
+        // =====================================================================================
+        // stats warp: records -> summaries -> (cluster) -> row statistics, one super-row after the other
+        // =====================================================================================
+        float kl_acc[NL];
 #pragma unroll
-    for (int k = 0; k < NL; ++k) kl_acc[k] = 0.f;
-
-    for (int it = 0; it < n_iter; ++it) {
-        const int sr = cluster_id + it * n_clusters;
-        const SuperRow x = super_row(p, g, sr);
-        const int par = it & 1;
-        const int v0 = min(x.lv, (int)rank * slv);     // my slice, in vectors of the super-row
-        const int v1 = min(x.lv, v0 + slv);
-        const int nvs = v1 - v0;
-        const int r_first = v0 / rv0;                  // first row of l[0] (within the super-row) in my slice
-        const int n_pieces = nvs > 0 ? (v1 - 1) / rv0 - r_first + 1 : 0;
-        if (tid == kCCons - 1) {
-            // this iteration's summaries: 32 bytes per piece of every CTA of the cluster will land in summ[par]
-            int total = 0;
-            for (int c = 0; c < NC; ++c) {
-                const int cv0 = min(x.lv, c * slv), cv1 = min(x.lv, cv0 + slv);
-                total += cv1 > cv0 ? (cv1 - 1) / rv0 - cv0 / rv0 + 1 : 0;
+        for (int k = 0; k < NL; ++k) kl_acc[k] = 0.f;
+        RowCursor rc;
+        rc.init(g, cluster_id);
+        // Which summaries this lane merges depends on the geometry only: planned once for the complete
+        // super-rows (integer divisions stay out of the per-row chain), again for a ragged one.
+        constexpr int kSrRecs = (kClusterMaxSize * kCMaxPieces + 31) / 32;   // summaries of a super-row per lane
+        constexpr int kPrPasses = (kCMaxPieces + 3) / 4;                     // rows of l[0]: four per pass, 8 lanes each
+        struct StatPlan {
+            int sr_off[kSrRecs];     // float offset (in summ[par]) of the summaries this lane folds into the super-row, or -1
+            int pr_off[kPrPasses];   // ... of the summary (CTA ca + j, its piece of my row) this lane contributes, or -1
+            int pr_row[kPrPasses];   // row of l[0] within the super-row (-1: no such piece)
+            int pr_ca[kPrPasses];    // first CTA that holds a piece of it (the one that accounts for its KL term)
+        };
+        auto make_plan = [&](int lv, const SliceGeo& s) {
+            StatPlan pl;
+#pragma unroll
+            for (int q = 0; q < kSrRecs; ++q) {
+                const int i = lane + 32 * q;
+                const int c = i / kCMaxPieces, pc = i - c * kCMaxPieces;
+                pl.sr_off[q] = (c < NC && pc < pieces_of(g, lv, c)) ? (c * kCMaxPieces + pc) * kCRecFloats : -1;
             }
-            mbar_arrive_expect_tx(&sm.xch[par], (uint32_t)total * 32u);
+#pragma unroll
+            for (int q = 0; q < kPrPasses; ++q) {
+                const int pc = 4 * q + (lane >> 3), j = lane & 7;
+                pl.pr_off[q] = -1;
+                pl.pr_row[q] = -1;
+                pl.pr_ca[q] = 0;
+                if (pc < s.n_pieces) {
+                    const int row = s.r_first + pc;                           // row of l[0] within the super-row
+                    const int rv_lo = row * rv0, rv_hi = min(lv, rv_lo + rv0);
+                    const int ca = rv_lo / g.slv, cb = (rv_hi - 1) / g.slv;   // its pieces live in CTAs ca..cb, one each
+                    pl.pr_row[q] = row;
+                    pl.pr_ca[q] = ca;
+                    if (j <= cb - ca) {
+                        const int c = ca + j;
+                        const int cpc = row - min(lv, c * g.slv) / rv0;
+                        pl.pr_off[q] = (c * kCMaxPieces + cpc) * kCRecFloats;
+                    }
+                }
+            }
+            return pl;
+        };
+        const StatPlan plan_full = make_plan(lv_full, geo_full);
+        // where lane w (< NC) of a group of 8 pushes: summ[0][rank][0] and xch[0] of CTA w
+        const uint32_t push_to = (uint32_t)(lane & 7) < (uint32_t)NC ? (uint32_t)(lane & 7) : rank;
+        const uint32_t push_dst = map_to_cta(sm.summ[0][rank][0], push_to);
+        const uint32_t push_bar = map_to_cta(&sm.xch[0], push_to);
+        float coef[NL];
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+            coef[k] = p.l[k].coef;
+            if (p.grad_out[k] != nullptr) coef[k] *= __ldg(p.grad_out[k]);
         }
+        auto load_stat = [&](const float* base, int off) {
+            PStat<NL> x = pstat_empty<NL>();
+            if (off >= 0) {
+                const float4* q = reinterpret_cast<const float4*>(base + off);
+                x = pstat_from<NL>(q[0], q[1]);
+            }
+            return x;
+        };
+#ifdef SD_CLUSTER_TIMING
+        long long tacc[4] = {0, 0, 0, 0};
+#endif
+        for (int it = 0; it < n_iter; ++it) {
+            const int par = it & 1;
+            const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+            SD_TICK(t0);
+            const int lv = rc.lv(p, g);
+            const bool full = lv == lv_full;
+            const SliceGeo s = full ? geo_full : slice_geo(g, lv, (int)rank);
+            const StatPlan pl = full ? plan_full : make_plan(lv, s);
+            // this row's summaries: 32 bytes per piece of every CTA of the cluster will land in summ[par]
+            if (lane == 0) mbar_arrive_expect_tx(&sm.xch[par], s.xch_bytes);
+            mbar_wait(&sm.recbar[par], ph);
+            SD_TICK(t1);
+            // ---- 8 warp records -> one summary per piece, four pieces per pass (8 lanes each);
+            //      lane c of the group pushes the summary into CTA c (this CTA included)
+            for (int pc0 = 0; pc0 < s.n_pieces; pc0 += 4) {
+                const int pc = pc0 + (lane >> 3), w = lane & 7;
+                PStat<NL> st = load_stat(sm.rec[par][0][0], pc < s.n_pieces ? (pc * kCParkWarps + w) * kCRecFloats : -1);
+                st = pstat_reduce<NL, R, 8>(st, c2);
+                if (pc < s.n_pieces && w < NC) {
+                    const uint32_t off = (uint32_t)(((par * kClusterMaxSize) * kCMaxPieces + pc) * kCRecFloats * 4);
+                    const uint32_t dst = push_dst + off, bar = push_bar + (uint32_t)par * 8u;
+                    st_async_f4(dst, make_float4(st.ms, st.mt, st.zs[0], st.zt[0]), bar);
+                    st_async_f4(dst + 16, make_float4(st.a[0], st.zs[NL - 1], st.zt[NL - 1], st.a[NL - 1]), bar);
+                }
+            }
+            SD_TICK(t2);
+            mbar_wait(&sm.xch[par], ph);
+            SD_TICK(t3);
+            // ---- merge what arrived: the super-row (two losses: every summary of every CTA) and the rows of
+            //      l[0] my pieces belong to (four per pass, 8 lanes each: a row lives in <= 8 CTAs).  Straight-line
+            //      code: the two butterflies interleave.
+            const float* sbase = sm.summ[par][0][0];
+            PStat<NL> sr = pstat_empty<NL>();
+            if (NL == 2) {
+                sr = load_stat(sbase, pl.sr_off[0]);
+#pragma unroll
+                for (int q = 1; q < kSrRecs; ++q)
+                    if (__any_sync(0xffffffffu, pl.sr_off[q] >= 0)) sr = pstat_merge<NL, R>(sr, load_stat(sbase, pl.sr_off[q]), c2);
+            }
+            PStat<NL> pr[kPrPasses];
+            pr[0] = load_stat(sbase, pl.pr_off[0]);
+            if (NL == 2) sr = pstat_reduce<NL, R, 32>(sr, c2);
+            pr[0] = pstat_reduce<NL, R, 8>(pr[0], c2);
+            if (NL == 2 && lane == 0)
+                *reinterpret_cast<float4*>(sm.fin[par][kCMaxPieces]) =
+                    make_float4(sr.ms, sr.mt, __fdividef(coef[K], sr.zs[K]), __fdividef(coef[K], sr.zt[K]));
+            if ((lane & 7) == 0 && pl.pr_row[0] >= 0)
+                *reinterpret_cast<float4*>(sm.fin[par][lane >> 3]) =
+                    make_float4(pr[0].ms, pr[0].mt, __fdividef(coef[0], pr[0].zs[0]), __fdividef(coef[0], pr[0].zt[0]));
+#pragma unroll
+            for (int q = 1; q < kPrPasses; ++q) {
+                pr[q] = pstat_empty<NL>();
+                if (s.n_pieces > 4 * q) {
+                    pr[q] = pstat_reduce<NL, R, 8>(load_stat(sbase, pl.pr_off[q]), c2);
+                    if ((lane & 7) == 0 && pl.pr_row[q] >= 0)
+                        *reinterpret_cast<float4*>(sm.fin[par][4 * q + (lane >> 3)]) =
+                            make_float4(pr[q].ms, pr[q].mt, __fdividef(coef[0], pr[q].zs[0]), __fdividef(coef[0], pr[q].zt[0]));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.finbar[par]);
+            SD_TICK(t4);
+            // ---- off the critical path: the KL terms of the rows this CTA accounts for
+            if (NL == 2 && lane == 0 && rank == 0) {
+                const float kl = kl_of_row(p.l[K].inv_tau, sr.ms, sr.mt, sr.zs[K], sr.zt[K], sr.a[K]);
+                if (p.l[K].row_kl) p.l[K].row_kl[rc.b * p.l[K].G + rc.grp] = kl;
+                kl_acc[K] += kl;
+            }
+#pragma unroll
+            for (int q = 0; q < kPrPasses; ++q) {
+                if ((lane & 7) == 0 && pl.pr_row[q] >= 0 && (int)rank == pl.pr_ca[q]) {
+                    const float kl = kl_of_row(p.l[0].inv_tau, pr[q].ms, pr[q].mt, pr[q].zs[0], pr[q].zt[0], pr[q].a[0]);
+                    const int rowi = NL == 2 ? rc.b * p.l[0].G + rc.grp * p.l[NL - 1].m + pl.pr_row[q] : rc.b * p.l[0].G + rc.grp;
+                    if (p.l[0].row_kl) p.l[0].row_kl[rowi] = kl;
+                    kl_acc[0] += kl;
+                }
+            }
+            SD_TACC(0, t0, t1);
+            SD_TACC(1, t1, t2);
+            SD_TACC(2, t2, t3);
+            SD_TACC(3, t3, t4);
+            rc.advance(g, n_clusters);
+        }
+#ifdef SD_CLUSTER_TIMING
+        if (lane == 0)
+            for (int q = 0; q < 4; ++q) p.pkt[blockIdx.x * 16 + q] = (unsigned long long)tacc[q];
+#endif
+        // ---- loss: lanes 0, 8, 16, 24 hold the row terms of this CTA, summed in a fixed order
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+            const float a8 = __shfl_sync(0xffffffffu, kl_acc[k], 8), a16 = __shfl_sync(0xffffffffu, kl_acc[k], 16),
+                        a24 = __shfl_sync(0xffffffffu, kl_acc[k], 24);
+            kl_acc[k] = (kl_acc[k] + a8) + (a16 + a24);
+        }
+        // every consumer is through with TMEM (the TMA warp frees it); nobody pushes at this CTA any more: its
+        // last exchange completed above
+        bar_sync(3, kCThreads);
+        unsigned ticket = 0;
+        if (lane == 0) {
+            __stcg(&p.cta_part[blockIdx.x], kl_acc[0]);
+            if (NL == 2) __stcg(&p.cta_part[kMaxGrid + blockIdx.x], kl_acc[NL - 1]);
+            __threadfence();
+            ticket = atomicAdd(&p.ctrl[0], 1u);
+        }
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket == gridDim.x - 1) {
+            // the last CTA sums the partials in a fixed order
+            __threadfence();
+            double acc[NL];
+#pragma unroll
+            for (int k = 0; k < NL; ++k) acc[k] = 0.0;
+            for (int i = lane; i < (int)gridDim.x; i += 32) {
+#pragma unroll
+                for (int k = 0; k < NL; ++k) acc[k] += (double)__ldcg(&p.cta_part[k * kMaxGrid + i]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int k = 0; k < NL; ++k) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < NL; ++k) *p.l[k].loss = (float)((double)p.l[k].loss_scale * acc[k]);
+                atomicExch(&p.ctrl[0], 0u);
+            }
+        }
+        return;
+    }
 
-        // ------------------------------------------------ phase 1: piece statistics, park the slice
-        // chunk-major: a chunk is pulled from the ring once; the piece it belongs to (rarely: the two or three
-        // pieces it straddles) gets its running statistics updated; every vector-row is parked with the
-        // reference of ITS piece
-        {
-            const int nchunks = (nvs + kCChunkVecs - 1) / kCChunkVecs;
-            int pc = 0;                                                  // current piece
-            int pv1 = min(v1, (r_first + 1) * rv0) - v0;                // ... ends here (vectors of my slice)
-            PStat<NL> st = pstat_empty<NL>();
-            for (int c = 0; c < nchunks; ++c) {
+    // =========================================================================================
+    // park warps 0..7 and gradient warps 8..15: warp 8 + i retrieves what warp i parked
+    // =========================================================================================
+    const int pw = warp & (kCParkWarps - 1);
+    const int ptid = tid & (kCPark - 1);
+    // the pair's TMEM window: lane quarter of both warps, 256 columns, 8 chunk slots of 32
+    const uint32_t tmem_mine = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((pw >> 2) * 256);
+    const int wv = pw * 32;            // the pair's vector-rows of a chunk start here, + 256 r (r < 4)
+
+    if (warp < kCParkWarps) {
+        // ------------------------------------------------ phase 1: statistics, park the slice
+        RowCursor rcA;
+        rcA.init(g, cluster_id);
+        SliceGeo gA = geo_full;
+        int itA = 0, cA = 0;               // super-row, chunk
+        int pcA = 0, pv1A = 0;             // current piece and its end
+        PStat<NL> st = pstat_empty<NL>();  // its statistics so far: maxima identical in every lane, sums per lane
+        uint32_t qA = 0;                   // chunks parked so far -> TMEM slot
+        int slot = 0;
+        uint32_t phase = 0;
+#ifdef SD_CLUSTER_TIMING
+        long long tacc[4] = {0, 0, 0, 0};
+        const long long tstart = clock64();
+#endif
+
+        // a piece ends: the warp's record (maxima + 3 sums per loss)
+        auto close_piece = [&]() {
+            float v[8] = {st.zs[0], st.zt[0], st.a[0], 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (NL == 2) {
+                v[3] = st.zs[NL - 1];
+                v[4] = st.zt[NL - 1];
+                v[5] = st.a[NL - 1];
+            }
+            const float tot = warp_sum8_transposed(v, lane);
+            float* rec = sm.rec[itA & 1][pcA][pw];
+            if ((lane & 3) == 0 && lane < 4 * 3 * NL) rec[2 + (lane >> 2)] = tot;
+            if (lane == 1) rec[0] = st.ms;
+            if (lane == 2) rec[1] = st.mt;
+            st = pstat_empty<NL>();
+            ++pcA;
+            pv1A = piece_end(g, gA, pcA);
+        };
+        // the running maxima move to (at least) wms, wmt: rescale the sums (rarely needed after the first chunks)
+        auto raise_refs = [&](float wms, float wmt) {
+            const float nms = fmaxf(st.ms, wms), nmt = fmaxf(st.mt, wmt);
+            if (nms != st.ms || nmt != st.mt) {      // warp-uniform
+                float rs[NL], rt[NL];
+                exps<NL, R>(st.ms, nms, c2, rs);
+                exps<NL, R>(st.mt, nmt, c2, rt);
+#pragma unroll
+                for (int k = 0; k < NL; ++k) {
+                    st.zs[k] *= rs[k];
+                    st.zt[k] *= rt[k];
+                    st.a[k] *= rt[k];
+                }
+                st.ms = nms;
+                st.mt = nmt;
+            }
+        };
+        // N elements into the statistics of the current piece; what gets parked replaces them in fs / ft
+        auto accumulate = [&](float* fs, float* ft, int n) {
+            float refs2[NL], reft2[NL];
+#pragma unroll
+            for (int k = 0; k < NL; ++k) {
+                refs2[k] = st.ms * c2[k];
+                reft2[k] = st.mt * c2[k];
+            }
+#pragma unroll
+            for (int i = 0; i < NE; ++i) {
+                if (i < n) {
+                    const float d = ft[i] - fs[i];
+                    float es[NL], et[NL];
+                    exps<NL, R>(fs[i], refs2, c2, es);
+                    exps<NL, R>(ft[i], reft2, c2, et);
+#pragma unroll
+                    for (int k = 0; k < NL; ++k) {
+                        st.zs[k] += es[k];
+                        st.zt[k] += et[k];
+                        st.a[k] = fmaf(et[k], d, st.a[k]);
+                    }
+                    if (kParkExp) {
+                        fs[i] = es[K];
+                        ft[i] = et[K];
+                    }
+                }
+            }
+        };
+
+        for (; itA < n_iter; ++itA, rcA.advance(g, n_clusters)) {
+            gA = geo_of(rcA.lv(p, g));
+            pcA = 0;
+            pv1A = piece_end(g, gA, 0);
+            st = pstat_empty<NL>();
+            SD_TICK(t0);
+            for (cA = 0; cA < gA.nchunks; ++cA, ++qA) {
+                // ---- one chunk: ring -> registers -> statistics -> TMEM
+                const uint32_t ts = qA & (uint32_t)(kCSlots - 1);
+                if (qA >= (uint32_t)kCSlots) {
+                    // the slot's previous chunk has been retrieved by my gradient warp
+                    SD_TICK(w0);
+                    mbar_wait(&sm.tfree[pw][ts], ((qA >> 3) - 1u) & 1u);
+                    SD_TICK(w1);
+                    SD_TACC(1, w0, w1);
+                    tmem_fence_after_sync();
+                }
+                SD_TICK(w2);
                 mbar_wait(&sm.full[slot], phase);
+                SD_TICK(w3);
+                SD_TACC(2, w2, w3);
                 const vec_t* bs = reinterpret_cast<const vec_t*>(sm.ring[slot][0]);
                 const vec_t* bt = reinterpret_cast<const vec_t*>(sm.ring[slot][1]);
                 float fs[NE], ft[NE];
 #pragma unroll
                 for (int r = 0; r < kCChunkRows; ++r) {
-                    V::unpack(bs[r * kCCons + tid], &fs[r * VE]);
-                    V::unpack(bt[r * kCCons + tid], &ft[r * VE]);
+                    V::unpack(bs[r * kCPark + ptid], &fs[r * VE]);
+                    V::unpack(bt[r * kCPark + ptid], &ft[r * VE]);
                 }
-                const int cbeg = c * kCChunkVecs, cend = cbeg + kCChunkVecs;
-                float ps[NE], pt[NE], pref[kCChunkRows][2];            // what gets parked
-                if (cend <= pv1) {
-                    // ---- the whole chunk lies in the current piece: no masks
-                    float nms = st.ms, nmt = st.mt;
-#pragma unroll
-                    for (int i = 0; i < NE; ++i) {
-                        nms = fmaxf(nms, fs[i]);
-                        nmt = fmaxf(nmt, ft[i]);
-                    }
-                    // the maxima consumed every shared-memory read: the slot may go back to the TMA warp (an
-                    // mbarrier arrival is not ordered behind LDS that are still in flight)
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.empty[slot]);
-                    float refs2[NL], reft2[NL], rs[NL], rt[NL];
-#pragma unroll
-                    for (int k = 0; k < NL; ++k) {
-                        refs2[k] = nms * c2[k];
-                        reft2[k] = nmt * c2[k];
-                    }
-                    // exact differences for the rescale: both references may still be the -1e29 floor
-                    exps<NL, R>(st.ms, nms, c2, rs);
-                    exps<NL, R>(st.mt, nmt, c2, rt);
-#pragma unroll
-                    for (int k = 0; k < NL; ++k) {
-                        st.zs[k] *= rs[k];
-                        st.zt[k] *= rt[k];
-                        st.a[k] *= rt[k];
-                    }
-                    st.ms = nms;
-                    st.mt = nmt;
-#pragma unroll
-                    for (int i = 0; i < NE; ++i) {
-                        const float d = ft[i] - fs[i];
-                        float es[NL], et[NL];
-                        exps<NL, R>(fs[i], refs2, c2, es);
-                        exps<NL, R>(ft[i], reft2, c2, et);
-#pragma unroll
-                        for (int k = 0; k < NL; ++k) {
-                            st.zs[k] += es[k];
-                            st.zt[k] += et[k];
-                            st.a[k] = fmaf(et[k], d, st.a[k]);
-                        }
-                        ps[i] = kParkExp ? es[K] : fs[i];
-                        pt[i] = kParkExp ? et[K] : ft[i];
-                    }
-#pragma unroll
-                    for (int r = 0; r < kCChunkRows; ++r) {
-                        pref[r][0] = nms;
-                        pref[r][1] = nmt;
-                    }
-                } else {
-                    // ---- the chunk runs past the end of the piece (or of the slice): piece by piece, masked
-                    float raw_s[NE], raw_t[NE];
-#pragma unroll
-                    for (int i = 0; i < NE; ++i) {
-                        raw_s[i] = fs[i];
-                        raw_t[i] = ft[i];
-                        ps[i] = pt[i] = 0.f;
-                    }
-#pragma unroll
-                    for (int r = 0; r < kCChunkRows; ++r) pref[r][0] = pref[r][1] = 0.f;
-                    for (;;) {
-                        // the part of piece pc inside this chunk: [lo, hi)
-                        const int lo = max(cbeg, max(v0, (r_first + pc) * rv0) - v0), hi = min(min(cend, nvs), pv1);
-                        bool mine[kCChunkRows];
-#pragma unroll
-                        for (int r = 0; r < kCChunkRows; ++r) {
-                            const int v = cbeg + r * kCCons + tid;
-                            mine[r] = v >= lo && v < hi;
-#pragma unroll
-                            for (int q = 0; q < VE; ++q) {
-                                fs[r * VE + q] = mine[r] ? raw_s[r * VE + q] : kPadValue;
-                                ft[r * VE + q] = mine[r] ? raw_t[r * VE + q] : kPadValue;
-                            }
-                        }
-                        float nms = st.ms, nmt = st.mt;
-#pragma unroll
-                        for (int i = 0; i < NE; ++i) {
-                            nms = fmaxf(nms, fs[i]);
-                            nmt = fmaxf(nmt, ft[i]);
-                        }
-                        float refs2[NL], reft2[NL], rs[NL], rt[NL];
-#pragma unroll
-                        for (int k = 0; k < NL; ++k) {
-                            refs2[k] = nms * c2[k];
-                            reft2[k] = nmt * c2[k];
-                        }
-                        exps<NL, R>(st.ms, nms, c2, rs);
-                        exps<NL, R>(st.mt, nmt, c2, rt);
-#pragma unroll
-                        for (int k = 0; k < NL; ++k) {
-                            st.zs[k] *= rs[k];
-                            st.zt[k] *= rt[k];
-                            st.a[k] *= rt[k];
-                        }
-                        st.ms = nms;
-                        st.mt = nmt;
-#pragma unroll
-                        for (int i = 0; i < NE; ++i) {
-                            const float d = ft[i] - fs[i];
-                            float es[NL], et[NL];
-                            exps<NL, R>(fs[i], refs2, c2, es);
-                            exps<NL, R>(ft[i], reft2, c2, et);
-#pragma unroll
-                            for (int k = 0; k < NL; ++k) {
-                                st.zs[k] += es[k];
-                                st.zt[k] += et[k];
-                                st.a[k] = fmaf(et[k], d, st.a[k]);
-                            }
-                            if (mine[i / VE]) {
-                                ps[i] = kParkExp ? es[K] : raw_s[i];
-                                pt[i] = kParkExp ? et[K] : raw_t[i];
-                            }
-                        }
-#pragma unroll
-                        for (int r = 0; r < kCChunkRows; ++r) {
-                            if (mine[r]) {
-                                pref[r][0] = nms;
-                                pref[r][1] = nmt;
-                            }
-                        }
-                        if (pv1 > min(cend, nvs)) break;            // the piece continues in the next chunk
-                        // the piece ends in this chunk: its warp record; on to the next piece, if any
-                        st = pstat_reduce<NL, R>(st, c2, 32);
-                        if (lane == 0) pstat_store<NL>(sm.rec[par][pc][warp], st);
-                        st = pstat_empty<NL>();
-                        ++pc;
-                        if (pc >= n_pieces) break;
-                        pv1 = min(v1, (r_first + pc + 1) * rv0) - v0;
-                        if (max(v0, (r_first + pc) * rv0) - v0 >= min(cend, nvs)) break;   // it starts in the next chunk
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.empty[slot]);   // (the arithmetic above consumed the reads)
-                }
-                // ---- park: registers -> TMEM
+                float mxs[kCChunkRows], mxt[kCChunkRows];
 #pragma unroll
                 for (int r = 0; r < kCChunkRows; ++r) {
-                    const uint32_t ta = tmem_mine + (uint32_t)((c * kCChunkRows + r) * kCRowCols);
-                    tmem_st8(ta,
-                             make_uint4(__float_as_uint(ps[r * VE]), __float_as_uint(ps[r * VE + 1]),
-                                        __float_as_uint(ps[r * VE + 2]), __float_as_uint(ps[r * VE + 3])),
-                             make_uint4(__float_as_uint(pt[r * VE]), __float_as_uint(pt[r * VE + 1]),
-                                        __float_as_uint(pt[r * VE + 2]), __float_as_uint(pt[r * VE + 3])));
-                    if (kParkExp) tmem_st2(ta + 8, __float_as_uint(pref[r][0]), __float_as_uint(pref[r][1]));
+                    mxs[r] = fmaxf(fmaxf(fs[r * VE], fs[r * VE + 1]), fmaxf(fs[r * VE + 2], fs[r * VE + 3]));
+                    mxt[r] = fmaxf(fmaxf(ft[r * VE], ft[r * VE + 1]), fmaxf(ft[r * VE + 2], ft[r * VE + 3]));
+                }
+                const int vA = cA * kCChunkVecs + wv;      // my first vector-row, in vectors of the slice; + 256 r
+                float rf[2 * kCChunkRows];
+                while (pcA < gA.n_pieces && vA >= pv1A) close_piece();
+                if (vA + (kCChunkRows - 1) * kCPark < pv1A) {
+                    // ---- all my vector-rows lie in the current piece (the common case)
+                    const float wms = warp_max_uniform(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])));
+                    const float wmt = warp_max_uniform(fmaxf(fmaxf(mxt[0], mxt[1]), fmaxf(mxt[2], mxt[3])));
+                    // every lane's shared-memory reads went into the maxima: the slot may go back to the TMA warp
+                    if (lane == 0) mbar_arrive(&sm.empty[slot]);
+                    raise_refs(wms, wmt);
+                    accumulate(fs, ft, NE);
+#pragma unroll
+                    for (int r = 0; r < kCChunkRows; ++r) {
+                        rf[2 * r] = st.ms;
+                        rf[2 * r + 1] = st.mt;
+                    }
+                } else {
+                    // ---- a piece (or the slice) ends in this chunk: vector-row by vector-row
+#pragma unroll
+                    for (int r = 0; r < kCChunkRows; ++r) {
+                        const int v = vA + r * kCPark;
+                        while (pcA < gA.n_pieces && v >= pv1A) close_piece();
+                        rf[2 * r] = rf[2 * r + 1] = 0.f;
+                        if (v < gA.nvs) {
+                            const float wms = warp_max_uniform(mxs[r]);
+                            const float wmt = warp_max_uniform(mxt[r]);
+                            raise_refs(wms, wmt);
+                            accumulate(&fs[r * VE], &ft[r * VE], VE);
+                            rf[2 * r] = st.ms;
+                            rf[2 * r + 1] = st.mt;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.empty[slot]);   // (the maxima above consumed the reads)
+                }
+                // ---- park: registers -> TMEM; the references once per warp
+                Parked pk;
+#pragma unroll
+                for (int r = 0; r < kCChunkRows; ++r) {
+#pragma unroll
+                    for (int q = 0; q < VE; ++q) {
+                        pk.w[r * 8 + q] = __float_as_uint(fs[r * VE + q]);
+                        pk.w[r * 8 + 4 + q] = __float_as_uint(ft[r * VE + q]);
+                    }
+                }
+                tmem_st32(tmem_mine + ts * kCSlotCols, pk);
+                if (kParkExp && lane == 0) {
+                    float4* d = reinterpret_cast<float4*>(sm.refs[pw][ts]);
+                    d[0] = make_float4(rf[0], rf[1], rf[2], rf[3]);
+                    d[1] = make_float4(rf[4], rf[5], rf[6], rf[7]);
                 }
                 if (++slot == kCRing) {
                     slot = 0;
                     phase ^= 1u;
                 }
-                // a piece that ends exactly with this chunk (the common case) closes here
-                if (pc < n_pieces && cend == pv1) {
-                    st = pstat_reduce<NL, R>(st, c2, 32);
-                    if (lane == 0) pstat_store<NL>(sm.rec[par][pc][warp], st);
-                    st = pstat_empty<NL>();
-                    ++pc;
-                    pv1 = min(v1, (r_first + pc + 1) * rv0) - v0;
-                }
             }
+            // the slice is parked (or empty): the records of the pieces still open; what I stored in TMEM is
+            // complete and ordered before the arrival the gradient warps will (transitively) wait on
+            while (pcA < gA.n_pieces) close_piece();
+            tmem_wait_st();
+            tmem_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.recbar[itA & 1]);
+            SD_TICK(t1);
+            SD_TACC(0, t0, t1);
         }
-
-        // ------------------------------------------------ 16 warp records -> one summary per piece
-        bar_sync(1, kCCons);
-        if (warp < n_pieces) {
-            const float4* q = reinterpret_cast<const float4*>(sm.rec[par][warp][lane & 15]);
-            const PStat<NL> st = pstat_reduce<NL, R>(pstat_from<NL>(q[0], q[1]), c2, 16);
-            // ---- exchange: lane c pushes the summary into CTA c (this CTA included)
-            if (lane < NC) {
-                const uint32_t dst = map_to_cta(sm.summ[par][rank][warp], (uint32_t)lane);
-                const uint32_t bar = map_to_cta(&sm.xch[par], (uint32_t)lane);
-                st_async_f4(dst, make_float4(st.ms, st.mt, st.zs[0], st.zt[0]), bar);
-                st_async_f4(dst + 16, make_float4(st.a[0], st.zs[NL - 1], st.zt[NL - 1], st.a[NL - 1]), bar);
-            }
+#ifdef SD_CLUSTER_TIMING
+        if (tid == 0) {
+            for (int q = 0; q < 3; ++q) p.pkt[blockIdx.x * 16 + 4 + q] = (unsigned long long)tacc[q];
+            p.pkt[blockIdx.x * 16 + 7] = (unsigned long long)(clock64() - tstart);
         }
-
-        // one warp per row: warp 0 the super-row (two losses), warp 1 + pc the row of l[0] of piece pc
-        if (NL == 2 && warp == 0) {
-            mbar_wait(&sm.xch[par], (uint32_t)(it >> 1) & 1u);
-            PStat<NL> acc = pstat_empty<NL>();
-            for (int i = lane; i < NC * kCMaxPieces; i += 32) {
-                const int c = i / kCMaxPieces, pc = i - c * kCMaxPieces;
-                const int cv0 = min(x.lv, c * slv), cv1 = min(x.lv, cv0 + slv);
-                const int np = cv1 > cv0 ? (cv1 - 1) / rv0 - cv0 / rv0 + 1 : 0;
-                if (pc < np) {
-                    const float4* q = reinterpret_cast<const float4*>(sm.summ[par][c][pc]);
-                    acc = pstat_merge<NL, R>(acc, pstat_from<NL>(q[0], q[1]), c2);
-                }
-            }
-            acc = pstat_reduce<NL, R>(acc, c2, 32);
-            if (lane == 0) {
-                float coef = p.l[K].coef;
-                if (p.grad_out[K] != nullptr) coef *= __ldg(p.grad_out[K]);
-                *reinterpret_cast<float4*>(sm.fin[kCMaxPieces]) =
-                    make_float4(acc.ms, acc.mt, coef / acc.zs[K], coef / acc.zt[K]);
-                if (rank == 0) {
-                    const float kl = kl_of_row(p.l[K].inv_tau, acc.ms, acc.mt, acc.zs[K], acc.zt[K], acc.a[K]);
-                    if (p.l[K].row_kl) p.l[K].row_kl[x.b * p.l[K].G + x.grp] = kl;
-                    kl_acc[K] += kl;
-                }
-            }
-        } else if (warp >= 1 && warp <= n_pieces) {
-            const int pc = warp - 1;
-            const int row = r_first + pc;                       // row of l[0] within the super-row
-            const int rv_lo = row * rv0, rv_hi = min(x.lv, rv_lo + rv0);
-            const int ca = rv_lo / slv, cb = (rv_hi - 1) / slv;   // its pieces live in CTAs ca..cb, one each
-            mbar_wait(&sm.xch[par], (uint32_t)(it >> 1) & 1u);
-            PStat<NL> acc = pstat_empty<NL>();
-            if (lane <= cb - ca) {
-                const int c = ca + lane;
-                const int cpc = row - min(x.lv, c * slv) / rv0;
-                const float4* q = reinterpret_cast<const float4*>(sm.summ[par][c][cpc]);
-                acc = pstat_from<NL>(q[0], q[1]);
-            }
-            acc = pstat_reduce<NL, R>(acc, c2, 32);
-            if (lane == 0) {
-                float coef = p.l[0].coef;
-                if (p.grad_out[0] != nullptr) coef *= __ldg(p.grad_out[0]);
-                *reinterpret_cast<float4*>(sm.fin[pc]) = make_float4(acc.ms, acc.mt, coef / acc.zs[0], coef / acc.zt[0]);
-                if ((int)rank == ca) {
-                    const float kl = kl_of_row(p.l[0].inv_tau, acc.ms, acc.mt, acc.zs[0], acc.zt[0], acc.a[0]);
-                    const int rowi = NL == 2 ? x.b * p.l[0].G + x.grp * p.l[NL - 1].m + row : x.b * p.l[0].G + x.grp;
-                    if (p.l[0].row_kl) p.l[0].row_kl[rowi] = kl;
-                    kl_acc[0] += kl;
-                }
-            }
-        }
-        // the thread that armed the exchange always sees it complete: a CTA whose slice is empty (ragged last
-        // super-row) must neither re-arm the barrier early nor exit while peers still push at it
-        if (tid == kCCons - 1) mbar_wait(&sm.xch[par], (uint32_t)(it >> 1) & 1u);
-        bar_sync(2, kCCons);
-
+#endif
+    } else {
         // ------------------------------------------------ phase 2: gradient from the parked slice
-        tmem_wait_st();
-        {
-            T* out = static_cast<T*>(p.dS) + x.base + (size_t)v0 * VE;
-            const int nchunks = (nvs + kCChunkVecs - 1) / kCChunkVecs;
-            const float4 fb = *reinterpret_cast<const float4*>(sm.fin[kCMaxPieces]);   // {Ms, Mt, coef/Zs, coef/Zt} of the super-row
-            // one vector-row: parked values + references -> gradient, given the statistics `fa` of its l[0] row
-            auto grad_row = [&](const uint4& bs, const uint4& bt, float ref_s, float ref_t, const float4& fa, int v) {
-                const float fs[VE] = {__uint_as_float(bs.x), __uint_as_float(bs.y), __uint_as_float(bs.z), __uint_as_float(bs.w)};
-                const float ft[VE] = {__uint_as_float(bt.x), __uint_as_float(bt.y), __uint_as_float(bt.z), __uint_as_float(bt.w)};
-                float o[VE];
+        RowCursor rcB;
+        rcB.init(g, cluster_id);
+        uint32_t qB = 0;                   // chunks retrieved so far -> TMEM slot
+#ifdef SD_CLUSTER_TIMING
+        long long tacc[4] = {0, 0, 0, 0};
+#endif
+        for (int itB = 0; itB < n_iter; ++itB, rcB.advance(g, n_clusters)) {
+            const int par = itB & 1;
+            const SliceGeo gB = geo_of(rcB.lv(p, g));
+            if (gB.nchunks == 0) continue;
+            SD_TICK(t0);
+            mbar_wait(&sm.finbar[par], (uint32_t)(itB >> 1) & 1u);
+            tmem_fence_after_sync();
+            SD_TICK(t1);
+            T* out = static_cast<T*>(p.dS) + rcB.base(p, g) + (size_t)gB.v0 * VE;
+            const float4 fb = *reinterpret_cast<const float4*>(sm.fin[par][kCMaxPieces]);   // {Ms, Mt, coef/Zs, coef/Zt} of the super-row
+            int pc = 0;
+            int pv1 = piece_end(g, gB, 0);
+            float4 fa = *reinterpret_cast<const float4*>(sm.fin[par][0]);
+            // one vector-row: parked values (+ the references they were taken against) -> gradient, given the
+            // statistics `fa` of its l[0] row
+            auto grad = [&](const uint32_t* w, float ref_s, float ref_t, int v) {
+                float fs[VE], ft[VE], o[VE];
+#pragma unroll
+                for (int q = 0; q < VE; ++q) {
+                    fs[q] = __uint_as_float(w[q]);
+                    ft[q] = __uint_as_float(w[4 + q]);
+                }
                 if (kParkExp) {
-                    // parked: e = exp2((x - ref) c2[K]) against the thread's reference of that moment;
-                    // softmax_k = e^(c2[k]/c2[K]) * exp2((ref - M_k) c2[k]) / Z_k, and ref <= M_k
+                    // parked: e = exp2((x - ref) c2[K]); softmax_k = e^(c2[k]/c2[K]) * exp2((ref - M_k) c2[k]) / Z_k, ref <= M_k
                     const float gsK = (NL == 2 ? fb.z : fa.z) * fast_exp2((ref_s - (NL == 2 ? fb.x : fa.x)) * c2[K]);
                     const float gtK = (NL == 2 ? fb.w : fa.w) * fast_exp2((ref_t - (NL == 2 ? fb.y : fa.y)) * c2[K]);
                     if (NL == 2) {
@@ -695,104 +911,87 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
                         o[q] = fmaf(es0, fa.z, es1 * fb.z) - fmaf(et0, fa.w, et1 * fb.w);
                     }
                 }
-                V::store(out + (size_t)v * VE, o);
+                V::store(out + (size_t)(v + lane) * VE, o);
             };
-            // parked rows in flight from TMEM, one chunk ahead of the arithmetic
-            uint4 ls[kCChunkRows], lt[kCChunkRows];
-            uint32_t lr[kCChunkRows][2];
-            auto fetch = [&](int c) {
+            auto grad_chunk = [&](int c, const Parked& pk, uint32_t ts) {
+                const int vA = c * kCChunkVecs + wv;
+                float rf[2 * kCChunkRows];
 #pragma unroll
-                for (int r = 0; r < kCChunkRows; ++r) {
-                    const uint32_t ta = tmem_mine + (uint32_t)((c * kCChunkRows + r) * kCRowCols);
-                    tmem_ld8(ta, ls[r], lt[r]);
-                    if (kParkExp) tmem_ld2(ta + 8, lr[r][0], lr[r][1]);
+                for (int q = 0; q < 2 * kCChunkRows; ++q) rf[q] = 0.f;
+                if (kParkExp) {
+                    const float4* d = reinterpret_cast<const float4*>(sm.refs[pw][ts]);
+                    const float4 d0 = d[0], d1 = d[1];
+                    rf[0] = d0.x; rf[1] = d0.y; rf[2] = d0.z; rf[3] = d0.w;
+                    rf[4] = d1.x; rf[5] = d1.y; rf[6] = d1.z; rf[7] = d1.w;
                 }
-            };
-            int pc = 0;
-            int pv1 = min(v1, (r_first + 1) * rv0) - v0;
-            float4 fa = *reinterpret_cast<const float4*>(sm.fin[0]);
-            if (nchunks > 0) fetch(0);
-            for (int c = 0; c < nchunks; ++c) {
-                static_assert(kCChunkRows == 2, "the waits below name the registers of two rows");
-                tmem_wait_ld(ls[0], lt[0], lr[0][0], lr[0][1]);
-                tmem_wait_ld(ls[1], lt[1], lr[1][0], lr[1][1]);
-                uint4 bs[kCChunkRows], bt[kCChunkRows];
-                float ref[kCChunkRows][2];
+                // the parked values are in registers, the references too: the slot may be parked into again
+                __syncwarp();
+                tmem_fence_before_sync();
+                if (lane == 0) mbar_arrive(&sm.tfree[pw][ts]);
+                auto next_piece = [&]() {
+                    ++pc;
+                    pv1 = piece_end(g, gB, pc);
+                    if (pc < gB.n_pieces) fa = *reinterpret_cast<const float4*>(sm.fin[par][pc]);
+                };
+                while (pc < gB.n_pieces && vA >= pv1) next_piece();
+                if (vA + (kCChunkRows - 1) * kCPark < pv1) {
+                    if (kParkExp && NL == 2) {
+                        // all vector-rows in one piece, parked against the same references: the four factors once
+                        const float gsK = fb.z * fast_exp2((rf[0] - fb.x) * c2[K]);
+                        const float gtK = fb.w * fast_exp2((rf[1] - fb.y) * c2[K]);
+                        const float gs0 = fa.z * fast_exp2((rf[0] - fa.x) * c2[0]);
+                        const float gt0 = fa.w * fast_exp2((rf[1] - fa.y) * c2[0]);
 #pragma unroll
-                for (int r = 0; r < kCChunkRows; ++r) {
-                    bs[r] = ls[r];
-                    bt[r] = lt[r];
-                    ref[r][0] = __uint_as_float(lr[r][0]);
-                    ref[r][1] = __uint_as_float(lr[r][1]);
-                }
-                if (c + 1 < nchunks) fetch(c + 1);     // the next chunk comes in underneath the arithmetic of this one
-                const int cbeg = c * kCChunkVecs, cend = cbeg + kCChunkVecs;
-                if (cend <= pv1) {
+                        for (int r = 0; r < kCChunkRows; ++r) {
+                            float o[VE];
 #pragma unroll
-                    for (int r = 0; r < kCChunkRows; ++r) grad_row(bs[r], bt[r], ref[r][0], ref[r][1], fa, cbeg + r * kCCons + tid);
+                            for (int q = 0; q < VE; ++q) {
+                                const float es = __uint_as_float(pk.w[r * 8 + q]), et = __uint_as_float(pk.w[r * 8 + 4 + q]);
+                                o[q] = es * fmaf(es, gs0, gsK) - et * fmaf(et, gt0, gtK);
+                            }
+                            V::store(out + (size_t)(vA + r * kCPark + lane) * VE, o);
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < kCChunkRows; ++r) grad(&pk.w[r * 8], rf[2 * r], rf[2 * r + 1], vA + r * kCPark);
+                    }
                 } else {
-                    // the chunk straddles pieces or the end of the slice: look the row's piece up
 #pragma unroll
                     for (int r = 0; r < kCChunkRows; ++r) {
-                        const int v = cbeg + r * kCCons + tid;
-                        if (v < nvs) {
-                            const int q = (v0 + v) / rv0 - r_first;
-                            grad_row(bs[r], bt[r], ref[r][0], ref[r][1], *reinterpret_cast<const float4*>(sm.fin[q]), v);
-                        }
+                        const int v = vA + r * kCPark;
+                        while (pc < gB.n_pieces && v >= pv1) next_piece();
+                        if (v < gB.nvs) grad(&pk.w[r * 8], rf[2 * r], rf[2 * r + 1], v);
                     }
                 }
-                while (pc < n_pieces && pv1 <= min(cend, nvs)) {    // pieces that ended with this chunk
-                    ++pc;
-                    pv1 = min(v1, (r_first + pc + 1) * rv0) - v0;
-                    if (pc < n_pieces) fa = *reinterpret_cast<const float4*>(sm.fin[pc]);
+            };
+            // parked chunks in flight from TMEM, one ahead of the arithmetic, in two register sets
+            Parked pa, pb;
+            const int n = gB.nchunks;
+            tmem_ld32(tmem_mine + (qB & (uint32_t)(kCSlots - 1)) * kCSlotCols, pa);
+            for (int c = 0; c < n; c += 2) {
+                const uint32_t t0_ = (qB + (uint32_t)c) & (uint32_t)(kCSlots - 1), t1_ = (t0_ + 1) & (uint32_t)(kCSlots - 1),
+                               t2_ = (t0_ + 2) & (uint32_t)(kCSlots - 1);
+                tmem_wait_ld(pa);
+                if (c + 1 < n) tmem_ld32(tmem_mine + t1_ * kCSlotCols, pb);
+                grad_chunk(c, pa, t0_);
+                if (c + 1 < n) {
+                    tmem_wait_ld(pb);
+                    if (c + 2 < n) tmem_ld32(tmem_mine + t2_ * kCSlotCols, pa);
+                    grad_chunk(c + 1, pb, t1_);
                 }
             }
+            qB += (uint32_t)n;
+            SD_TICK(t2);
+            SD_TACC(0, t0, t1);
+            SD_TACC(1, t1, t2);
         }
+#ifdef SD_CLUSTER_TIMING
+        if (tid == kCPark)
+            for (int q = 0; q < 2; ++q) p.pkt[blockIdx.x * 16 + 8 + q] = (unsigned long long)tacc[q];
+#endif
     }
-
-    // ================================ loss: warp partials -> CTA partial -> the last CTA sums in a fixed order
-    if (lane == 0) {
-        sm.klpart[warp][0] = kl_acc[0];
-        sm.klpart[warp][1] = NL == 2 ? kl_acc[NL - 1] : 0.f;
-    }
-    // every consumer is through with TMEM (the TMA warp frees it); nobody pushes at this CTA any more: its
-    // last exchange completed before its last gradient pass
+    // every consumer is through with TMEM (the TMA warp frees it)
     bar_sync(3, kCThreads);
-    if (warp == 0) {
-        unsigned ticket = 0;
-        if (lane == 0) {
-            float s0 = 0.f, s1 = 0.f;
-            for (int w = 0; w < kCConsWarps; ++w) {
-                s0 += sm.klpart[w][0];
-                s1 += sm.klpart[w][1];
-            }
-            __stcg(&p.cta_part[blockIdx.x], s0);
-            if (NL == 2) __stcg(&p.cta_part[kMaxGrid + blockIdx.x], s1);
-            __threadfence();
-            ticket = atomicAdd(&p.ctrl[0], 1u);
-        }
-        ticket = __shfl_sync(0xffffffffu, ticket, 0);
-        if (ticket == gridDim.x - 1) {
-            __threadfence();
-            double acc[NL];
-#pragma unroll
-            for (int k = 0; k < NL; ++k) acc[k] = 0.0;
-            for (int i = lane; i < (int)gridDim.x; i += 32) {
-#pragma unroll
-                for (int k = 0; k < NL; ++k) acc[k] += (double)__ldcg(&p.cta_part[k * kMaxGrid + i]);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                for (int k = 0; k < NL; ++k) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
-            }
-            if (lane == 0) {
-#pragma unroll
-                for (int k = 0; k < NL; ++k) *p.l[k].loss = (float)((double)p.l[k].loss_scale * acc[k]);
-                atomicExch(&p.ctrl[0], 0u);
-            }
-        }
-    }
 }
 
 // ====================================================================================================

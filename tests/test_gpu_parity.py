@@ -104,11 +104,11 @@ CFG1 = (2, 150, 64, 64)
 
 
 @pytest.mark.parametrize('g,shape', [(3, CFG1), (10, CFG1), (30, CFG1), (10, (1, 25, 128, 128)), (3, (2, 7, 96, 96)),
-                                     (5, (3, 12, 72, 72))])
+                                     (5, (3, 12, 80, 80))])
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_cluster_resident_rows(g, shape, dtype):
     """Rows kept resident in the shared memory of a thread-block cluster (1, 2, 4 or 8 CTAs per row),
-    complete and ragged (25 % 10, 7 % 3 != 0) groups, slices that end inside a chunk (96x96, 72x72)."""
+    complete and ragged (25 % 10, 7 % 3 != 0) groups, slices that end inside a chunk (96x96, 80x80)."""
     s, t = seeded_pair(shape, seed=g, dtype=dtype)
     kw = dict(group_size=g, alpha=3, tau=2)
     ref = _oracle_run('CGDLoss', kw, s, t, shape[2:], 1)
