@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 from segdistill_b200 import _cabi  # noqa: E402
 
 dev = torch.device('cuda', 0)
-shape = (16, 150, 128, 128)
+shape = (int(os.environ.get('SD_B', '16')), 150, 128, 128)
 dtype = torch.bfloat16 if 'bf16' in sys.argv else torch.float32
 g = torch.Generator(device=dev).manual_seed(0)
 s = torch.randn(shape, device=dev, generator=g).to(dtype)
@@ -28,9 +28,9 @@ ws = next(iter(_cabi._workspaces.values()))
 R = shape[0] * shape[1]
 off = 256 + 4 * 3 * 1024 + 4 * R * 2
 off = (off + 127) // 128 * 128
-n_cta = 120
+n_cta = min(120, shape[0] * 15 * 8)
 v = ws[off:off + n_cta * 16 * 8].view(torch.int64).view(n_cta, 16).cpu()
-names = ['st:wait_rec', 'st:summ', 'st:wait_xch', 'st:merge', 'pk:rows', 'pk:wait_tmem', 'pk:wait_ring', 'pk:total', 'gr:wait_fin', 'gr:grad']
+names = ['st:wait_rec', 'st:summ', 'st:wait_xch', 'st:merge', 'pk:rows', 'pk:wait_tmem', 'pk:wait_ring', 'pk:total', 'gr:wait_fin', 'gr:grad', 'pk:lds+max', 'pk:redux', 'pk:math', 'pk:chunk_after_lds', 'T:fin_last', 'T:grad_done']
 for i, nme in enumerate(names):
     col = v[:, i].float()
-    print(f'{nme:12s} mean {col.mean():10.0f}  min {col.min():10.0f}  max {col.max():10.0f} cycles  (per row: {col.mean() / 16:8.0f})')
+    print(f'{nme:12s} mean {col.mean():10.0f}  min {col.min():10.0f}  max {col.max():10.0f} cycles  (per row: {col.mean() / max(1, shape[0] * 15 // 15):8.0f})')

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <utility>
 
@@ -271,6 +272,11 @@ int rows_dispatch(RowsCall c) {
             cg.slv = (int)slv;
             cg.rv0 = (int)rv0;
             cg.total_sr = B * cg.G_big;
+            cg.pieces_full = 0;
+            for (int cta = 0; cta < nc; ++cta) {
+                const long long cv0 = std::min<long long>(lv, cta * slv), cv1 = std::min<long long>(lv, cv0 + slv);
+                if (cv1 > cv0) cg.pieces_full += (int)((cv1 - 1) / rv0 - cv0 / rv0 + 1);
+            }
             cluster_ok = sd::launch_kl_rows_cluster(p, cg, c.dtype == SD_BF16, dev.sms, nullptr, true) == cudaSuccess;
         }
     }
@@ -291,12 +297,12 @@ int rows_dispatch(RowsCall c) {
     enum { kGeneric, kRegs, kStream, kCluster, kPack } path;
     switch (c.algo) {
         case SD_ALGO_AUTO:
-            path = !layout_ok ? kGeneric : (pack_ok ? kPack : fits_regs ? kRegs : (cluster_ok && c.nl == 2 ? kCluster : kStream));
+            path = !layout_ok ? kGeneric : (pack_ok ? kPack : fits_regs ? kRegs : (cluster_ok ? kCluster : kStream));
             break;
         case SD_ALGO_TMA:
             if (!layout_ok) return SD_ERR_UNSUPPORTED;
-            // (measured on B200: the cluster-resident kernel wins for two fused losses, the streaming kernel for one)
-            path = pack_ok ? kPack : fits_regs ? kRegs : (cluster_ok && c.nl == 2 ? kCluster : kStream);
+            // (measured on B200: the cluster-resident kernel beats the streaming kernel for one loss and for two)
+            path = pack_ok ? kPack : fits_regs ? kRegs : (cluster_ok ? kCluster : kStream);
             break;
         case SD_ALGO_ROWS1:
             if (!layout_ok || !fits_regs) return SD_ERR_UNSUPPORTED;

@@ -50,6 +50,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// the same for waits that may last microseconds: with a suspend-time hint the failed try becomes a sleep that the
+// phase completion ends (SASS: NANOSLEEP.SYNCS) instead of a poll every few dozen cycles - polling warps share the
+// MIO queue with the MUFU / shared-memory instructions of the warps that do the work
+template <uint32_t kHintNs>
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(kHintNs)
+            : "memory");
+    } while (ok == 0);
+}
 
 // ---------------------------------------------------------------- TMA: 1-D bulk copy global -> shared
 // bytes % 16 == 0, both addresses 16-byte aligned; completion is signalled on `bar` (complete_tx).

@@ -34,6 +34,10 @@
 // Geometry contract (cabi.cu): HW % 128 == 0, so every 32-vector row of a warp lies inside one piece of one
 // slice; slices are whole chunks.
 #include "rows_common.cuh"
+#ifndef SD_WAIT_NS
+#define SD_WAIT_NS 20000
+#endif
+#define mbar_wait mbar_wait_sleep<SD_WAIT_NS>
 
 namespace sd {
 
@@ -310,7 +314,8 @@ __device__ __forceinline__ int pieces_of(const ClusterGeom& g, int lv, int c) {
     const int cv0 = min(lv, c * g.slv), cv1 = min(lv, cv0 + g.slv);
     return cv1 > cv0 ? (cv1 - 1) / g.rv0 - cv0 / g.rv0 + 1 : 0;
 }
-__device__ __forceinline__ SliceGeo slice_geo(const ClusterGeom& g, int lv, int rank) {
+// total_pieces: pieces of all slices of this super-row when the host knows them (complete super-rows), else -1
+__device__ __forceinline__ SliceGeo slice_geo(const ClusterGeom& g, int lv, int rank, int total_pieces = -1) {
     SliceGeo s;
     s.v0 = min(lv, rank * g.slv);
     s.v1 = min(lv, s.v0 + g.slv);
@@ -318,8 +323,11 @@ __device__ __forceinline__ SliceGeo slice_geo(const ClusterGeom& g, int lv, int 
     s.r_first = s.v0 / g.rv0;
     s.n_pieces = s.nvs > 0 ? (s.v1 - 1) / g.rv0 - s.r_first + 1 : 0;
     s.nchunks = (s.nvs + kCChunkVecs - 1) / kCChunkVecs;
-    int total = 0;
-    for (int c = 0; c < g.nc; ++c) total += pieces_of(g, lv, c);
+    int total = total_pieces;
+    if (total < 0) {
+        total = 0;
+        for (int c = 0; c < g.nc; ++c) total += pieces_of(g, lv, c);
+    }
     s.xch_bytes = (uint32_t)total * 32u;
     return s;
 }
@@ -388,6 +396,12 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
     const int n_clusters = gridDim.x / NC;
 
     if (p.run_if != nullptr && *p.run_if == 0u) return;  // cancelled backward re-run (uniform over the grid)
+#ifdef SD_CLUSTER_TIMING
+    const long long tk0 = clock64();
+#define SD_STAMP(i) p.pkt[blockIdx.x * 16 + (i)] = (unsigned long long)(clock64() - tk0)
+#else
+#define SD_STAMP(i)
+#endif
 
     if (tid == 0) {
         for (int c = 0; c < kCRing; ++c) {
@@ -412,10 +426,13 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
     cluster_arrive_release();
     cluster_wait_acquire();
 
+#ifdef SD_CLUSTER_TIMING
+    if (tid == 0) SD_STAMP(10);      // prologue done (barriers, TMEM, cluster sync)
+#endif
     const int n_iter = cluster_id < g.total_sr ? (g.total_sr - cluster_id + n_clusters - 1) / n_clusters : 0;
     // every complete super-row is cut the same way; only a ragged last group needs its own geometry
     const int lv_full = g.g_big * g.hwv;
-    const SliceGeo geo_full = slice_geo(g, lv_full, (int)rank);
+    const SliceGeo geo_full = slice_geo(g, lv_full, (int)rank, g.pieces_full);
     auto geo_of = [&](int lv) { return lv == lv_full ? geo_full : slice_geo(g, lv, (int)rank); };
 
     if (warp == kCTmaWarp) {
@@ -769,6 +786,9 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
                 mbar_wait(&sm.full[slot], phase);
                 SD_TICK(w3);
                 SD_TACC(2, w2, w3);
+#ifdef SD_CLUSTER_TIMING
+                if (tid == 0 && qA == 0) SD_STAMP(11);   // first chunk arrived
+#endif
                 const vec_t* bs = reinterpret_cast<const vec_t*>(sm.ring[slot][0]);
                 const vec_t* bt = reinterpret_cast<const vec_t*>(sm.ring[slot][1]);
                 float fs[NE], ft[NE];
@@ -848,6 +868,9 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
             if (lane == 0) mbar_arrive(&sm.recbar[itA & 1]);
             SD_TICK(t1);
             SD_TACC(0, t0, t1);
+#ifdef SD_CLUSTER_TIMING
+            if (tid == 0 && itA == 0) SD_STAMP(12);      // first row parked
+#endif
         }
 #ifdef SD_CLUSTER_TIMING
         if (tid == 0) {
@@ -871,6 +894,10 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
             mbar_wait(&sm.finbar[par], (uint32_t)(itB >> 1) & 1u);
             tmem_fence_after_sync();
             SD_TICK(t1);
+#ifdef SD_CLUSTER_TIMING
+            if (tid == kCPark && itB == 0) SD_STAMP(13);     // first row statistics arrived
+            if (tid == kCPark && itB == n_iter - 1) SD_STAMP(14);   // last row statistics arrived
+#endif
             T* out = static_cast<T*>(p.dS) + rcB.base(p, g) + (size_t)gB.v0 * VE;
             const float4 fb = *reinterpret_cast<const float4*>(sm.fin[par][kCMaxPieces]);   // {Ms, Mt, coef/Zs, coef/Zt} of the super-row
             int pc = 0;
@@ -990,6 +1017,9 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
             for (int q = 0; q < 2; ++q) p.pkt[blockIdx.x * 16 + 8 + q] = (unsigned long long)tacc[q];
 #endif
     }
+#ifdef SD_CLUSTER_TIMING
+    if (tid == kCPark) SD_STAMP(15);                         // last gradient written
+#endif
     // every consumer is through with TMEM (the TMA warp frees it)
     bar_sync(3, kCThreads);
 }

@@ -122,6 +122,7 @@ struct ClusterGeom {
     int slv;       // vectors per slice (multiple of kClusterChunkVecs)
     int rv0;       // vectors per complete row of l[0]
     int total_sr;  // B * G_big
+    int pieces_full;  // pieces (rows of l[0] x slices they intersect) of one complete super-row
 };
 
 // ---------------------------------------------------------------- pixels (PD / AT)
