@@ -239,7 +239,9 @@ def run_ours(args, rank, local_rank, world):
             torch.cuda.current_stream().wait_stream(side)
             sync_all()
             g_ = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_):
+            # capture on the stream the warm-up ran on: its zero-filled workspace exists already (a fresh
+            # capture stream would put the one-time workspace allocation + fill into every replay)
+            with torch.cuda.graph(g_, stream=side):
                 static_losses = step()
             graph, graph_note = g_, 'CUDA graph replay of the captured module-API step'
             for _ in range(3):
