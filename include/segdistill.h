@@ -14,6 +14,8 @@
  *   sd_kl_pixels_fwd_bwd  losses.py:47-49 (permute to NHWC rows) + :108-112 - PDLoss :115-128;
  *                         with at_weight != 0 also ATLoss :175-197 (channel-mean MSE :190
  *                         + per-pixel KL :192-195)
+ *   sd_kl_rows_up_fwd_bwd the same behind KLDLoss.resize (losses.py:25-33,101-102; ops/wrappers.py:8-29):
+ *                         bilinear up-sampling fused into the loss and its backward
  *   sd_mse_fwd_bwd        losses.py:178,190 / :202,235 (nn.MSELoss), :812-830 (feature MSE)
  *   sd_kl_rows_multi_fwd_bwd  the same for two `distillation` entries on one pair (opts.py:100-103)
  *   sd_scale_grad         the autograd multiply by grad_output that torch would run in
@@ -152,6 +154,22 @@ SD_API int sd_kl_pixels_fwd_bwd(const void* S, const void* T, void* dS,
                          float at_weight, float* at_loss,
                          void* workspace, size_t workspace_bytes,
                          int algo, void* stream);
+
+/* ------------------------------------------------------------------ rows on up-sampled maps */
+SD_API size_t sd_kl_rows_up_workspace_bytes(int B, int C, int Hl, int Wl, int group);
+/*
+ * The channel-mode loss of sd_kl_rows_fwd_bwd on maps that the reference first resizes to the label
+ * size (KLDLoss.resize, mmseg/models/distillation/losses.py:25-33,101-102: F.interpolate(mode='bilinear',
+ * align_corners=False) through mmseg/ops/wrappers.py:8-29) - without materialising the resized maps:
+ * S, T and dS are the LOW-resolution [B, C, Hl, Wl] maps, rows are `group` channels x (scale*Hl) x (scale*Wl)
+ * up-sampled values, dS is the gradient with respect to the low-resolution S (the backward of the
+ * interpolation included).  scale in {2, 4, 8}; anything else: SD_ERR_UNSUPPORTED (resize on the host, then
+ * sd_kl_rows_fwd_bwd).  row_kl: [B*ceil(C/group)] or null; chan_perm as in sd_kl_rows_fwd_bwd.
+ */
+SD_API int sd_kl_rows_up_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl, float* loss,
+                          const int32_t* chan_perm, int B, int C, int Hl, int Wl, int scale, int group, int dtype,
+                          float tau, float alpha, float grad_scale,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ feature MSE */
 SD_API size_t sd_mse_workspace_bytes(int64_t numel);

@@ -28,6 +28,7 @@ EXPORTS = (
     'sd_abi_version', 'sd_strerror', 'sd_device_check',
     'sd_kl_rows_workspace_bytes', 'sd_kl_rows_fwd_bwd', 'sd_kl_rows_multi_fwd_bwd', 'sd_scale_grad2',
     'sd_kl_pixels_workspace_bytes', 'sd_kl_pixels_fwd_bwd',
+    'sd_kl_rows_up_workspace_bytes', 'sd_kl_rows_up_fwd_bwd',
     'sd_mse_workspace_bytes', 'sd_mse_fwd_bwd', 'sd_scale_grad',
     'sd_cgd_corr_workspace_bytes', 'sd_cgd_corr_fwd_bwd',
     'sd_launch_count', 'sd_last_kernel',
@@ -79,6 +80,11 @@ def load():
         lib.sd_kl_pixels_fwd_bwd.restype = i32
         lib.sd_kl_pixels_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32,
                                              f32, f32, f32, f32, vp, vp, sz, i32, vp]
+        lib.sd_kl_rows_up_workspace_bytes.restype = sz
+        lib.sd_kl_rows_up_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
+        lib.sd_kl_rows_up_fwd_bwd.restype = i32
+        lib.sd_kl_rows_up_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32,
+                                              f32, f32, f32, vp, sz, vp]
         lib.sd_mse_workspace_bytes.restype = sz
         lib.sd_mse_workspace_bytes.argtypes = [i64]
         lib.sd_mse_fwd_bwd.restype = i32
@@ -318,6 +324,42 @@ def kl_pixels(x_student, x_teacher, tau=1.0, alpha=1.0, grad_scale=1.0, at_weigh
             ws.data_ptr(), ws.numel(), int(algo), _stream_ptr(dev))
         _check(rc)
     return out[0], ds, row_kl, (out[1] if at_weight != 0 else None)
+
+
+UP_SCALES = (2, 4, 8)
+
+
+def up_supported(hl: int, wl: int) -> bool:
+    """Whether a low-resolution plane of this width fits the strip buffers of kl_rows_up (csrc/params.h:up_strip_rows)."""
+    return (100 * 1024 // 4 // int(wl) - 8) // 11 >= 1 and hl >= 1
+
+
+def kl_rows_up(x_student, x_teacher, scale, group=1, tau=1.0, alpha=1.0, perm: Optional[torch.Tensor] = None,
+               grad_scale=1.0, want_row_kl=False):
+    """Channel-mode softmax-KL on the maps up-sampled ``scale`` x (bilinear, align_corners=False) without
+    materialising them.  x_*: low-resolution [B, C, Hl, Wl].  Returns (loss, dS at low resolution, row_kl)."""
+    lib = load()
+    s, t, code = _prep_pair(x_student, x_teacher)
+    if s.dim() != 4:
+        raise ValueError('kl_rows_up expects 4-D NCHW maps')
+    B, C, Hl, Wl = s.shape
+    dev = s.device
+    with _on(dev):
+        ds = torch.empty_like(s)
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        G = -(-C // min(int(group), C))
+        row_kl = torch.empty(B * G, dtype=torch.float32, device=dev) if want_row_kl else None
+        p = None
+        if perm is not None:
+            p = perm.to(device=dev, dtype=torch.int32).contiguous()
+        ws = _workspace(dev, lib.sd_kl_rows_up_workspace_bytes(B, C, Hl, Wl, int(group)))
+        rc = lib.sd_kl_rows_up_fwd_bwd(s.data_ptr(), t.data_ptr(), ds.data_ptr(),
+                                       row_kl.data_ptr() if row_kl is not None else None, out.data_ptr(),
+                                       p.data_ptr() if p is not None else None, B, C, Hl, Wl, int(scale), int(group),
+                                       code, float(tau), float(alpha), float(grad_scale), ws.data_ptr(), ws.numel(),
+                                       _stream_ptr(dev))
+        _check(rc)
+    return out[0], ds, row_kl
 
 
 def mse(x_student, x_teacher, weight=1.0, grad_scale=1.0):

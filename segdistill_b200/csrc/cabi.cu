@@ -510,6 +510,54 @@ int sd_kl_pixels_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl, 
     return e == cudaSuccess ? SD_OK : (int)e;
 }
 
+// ============================================================================ rows on up-sampled maps
+size_t sd_kl_rows_up_workspace_bytes(int B, int C, int Hl, int Wl, int group) {
+    if (B <= 0 || C <= 0 || Hl <= 0 || Wl <= 0 || group <= 0) return 0;
+    return sd::up_workspace_layout(B, C, Hl, Wl, group).bytes;
+}
+
+int sd_kl_rows_up_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl, float* loss, const int32_t* chan_perm,
+                          int B, int C, int Hl, int Wl, int scale, int group, int dtype, float tau, float alpha,
+                          float grad_scale, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!S || !T || !dS || !loss || !workspace) return SD_ERR_NULL;
+    if (dtype != SD_F32 && dtype != SD_BF16) return SD_ERR_DTYPE;
+    if (B <= 0 || C <= 0 || Hl <= 0 || Wl <= 0) return SD_ERR_SHAPE;
+    if (group < 1 || !(tau > 0.f)) return SD_ERR_VALUE;
+    if (scale != 2 && scale != 4 && scale != 8) return SD_ERR_UNSUPPORTED;
+    if (group > C) group = C;
+    const long long numel = (long long)B * C * Hl * Wl;
+    if (numel >= (1ll << 40) || (long long)group * Hl * Wl * scale * scale >= (1ll << 40)) return SD_ERR_SHAPE;
+    const int SR = sd::up_strip_rows(Hl, Wl);
+    if (SR < 1) return SD_ERR_UNSUPPORTED;
+    const sd::UpWorkspace wl = sd::up_workspace_layout(B, C, Hl, Wl, group);
+    if (workspace_bytes < wl.bytes) return SD_ERR_WORKSPACE;
+    DeviceInfo& dev = device_info();
+    if (dev.cc_major != 10) return SD_ERR_DEVICE;
+    sd::UpParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.S = S; p.T = T; p.dS = dS; p.perm = chan_perm;
+    p.B = B; p.C = C; p.Hl = Hl; p.Wl = Wl; p.scale = scale;
+    p.g = group;
+    p.G = (C + group - 1) / group;
+    p.R = B * p.G;
+    p.SR = SR;
+    p.NS = (Hl + SR - 1) / SR;
+    p.units = (long long)B * C * p.NS;
+    p.c2 = (float)(1.4426950408889634 / (double)tau);
+    p.inv_tau = (float)(1.0 / (double)tau);
+    p.coef = (float)((double)grad_scale * (double)alpha / ((double)p.R * (double)tau));
+    p.loss_scale = (float)((double)alpha / (double)p.R);
+    p.loss = loss;
+    char* ws = static_cast<char*>(workspace);
+    p.row_kl = row_kl ? row_kl : reinterpret_cast<float*>(ws + wl.off_rowkl);
+    p.part = reinterpret_cast<float*>(ws + wl.off_part);
+    p.ctrl = reinterpret_cast<unsigned*>(ws + wl.off_ctrl);
+    cudaError_t e = sd::launch_kl_rows_up(p, dtype == SD_BF16, dev.sms, static_cast<cudaStream_t>(stream));
+    g_launches += 2;
+    t_last_kernel = "kl_rows_up_kernel";
+    return e == cudaSuccess ? SD_OK : (int)e;
+}
+
 // ============================================================================ MSE
 size_t sd_mse_workspace_bytes(int64_t numel) {
     (void)numel;

@@ -1,0 +1,407 @@
+// Channel-mode softmax-KL (CD / CGD) on maps that the reference first RESIZES to the label size:
+// KLDLoss.resize (mmseg/models/distillation/losses.py:25-33, F.interpolate(..., mode='bilinear',
+// align_corners=False), ops/wrappers.py:8-29) followed by the transform + KL chain (:50-58, :108-112) and autograd's
+// backward through both.  Every shipped preset resizes logits at 1/4 or 1/8 resolution to 512x512 (SURVEY.md 8 a8 /
+// f1): the reference then streams 16-64x the data through ~20 kernels and keeps several full-resolution temporaries.
+//
+// Here the up-sampled maps never exist.  For an integer scale s (2, 4, 8) the s x s block of up-sampled values
+// that belongs to one low-resolution cell depends on the 3 x 3 cells around it with CONSTANT weights
+// ((k + 1/2)/s -+ 1/2), so a thread regenerates the block in registers from shared memory:
+//
+//   kernel 1 (statistics)  unit = (sample, channel, strip of low-res rows): load the strip (+ one halo row each
+//                          side) of S and T, reference = maximum of the strip (an up-sampled value is a convex
+//                          combination of cells, so never larger), sums of exp2 over the up-sampled block of
+//                          every cell -> one partial record per unit.
+//   kernel 2 (gradient)    merges the records of its row (g channels x strips) into the row statistics,
+//                          regenerates the block, g = coef (q - p), and applies the TRANSPOSED stencil: a cell's
+//                          block contributes a 3 x 3 matrix W_y^T g W_x to the cells around it; every thread
+//                          stores its nine contributions to nine shared-memory planes (no atomics), then every
+//                          output cell sums its nine planes in a fixed order.  A strip also computes the cell rows
+//                          just outside it, so no gradient crosses CTAs.  HBM traffic: the low-resolution maps
+//                          twice (L2-resident the second time) + dS once.
+//
+// Deterministic (no floating-point atomics); fp32 arithmetic; dS has the dtype and the (low) resolution of S.
+#include "common.cuh"
+#include "params.h"
+
+namespace sd {
+
+constexpr int kUpThreads = 256;
+constexpr float kUpFloor = -1.0e29f;
+
+template <typename T>
+__device__ __forceinline__ float up_load(const T* p);
+template <>
+__device__ __forceinline__ float up_load<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float up_load<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T>
+__device__ __forceinline__ void up_store(T* p, float v);
+template <>
+__device__ __forceinline__ void up_store<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void up_store<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// weights of up-sampled index s*i + k on the cells (i-1, i, i+1): PyTorch's source index (k + 1/2)/s - 1/2 + i
+template <int S>
+struct UpW {
+    // tap pair of phase k: (i-1, i) for k < S/2, (i, i+1) otherwise; w1 = weight of the second tap
+    static __device__ __forceinline__ constexpr int first(int k) { return k < S / 2 ? -1 : 0; }
+    static __device__ __forceinline__ constexpr float w1(int k) {
+        return k < S / 2 ? (k + 0.5f) / S + 0.5f : (k + 0.5f) / S - 0.5f;
+    }
+};
+
+// unit -> plane and strip
+struct UpUnit {
+    int b, lc, grp, j;  // sample, logical channel, row of the loss within the sample, channel within the row
+    int ch;             // physical channel (through the permutation)
+    int i0, i1;         // low-res rows [i0, i1) of the strip
+};
+__device__ __forceinline__ UpUnit up_unit(const UpParams& p, long long u) {
+    UpUnit x;
+    const int plane = (int)(u / p.NS);
+    const int strip = (int)(u - (long long)plane * p.NS);
+    x.b = plane / p.C;
+    x.lc = plane - x.b * p.C;
+    x.grp = x.lc / p.g;
+    x.j = x.lc - x.grp * p.g;
+    x.ch = p.perm ? p.perm[x.lc] : x.lc;
+    x.i0 = strip * p.SR;
+    x.i1 = min(p.Hl, x.i0 + p.SR);
+    return x;
+}
+
+// strip rows [i0 - 1, i1 + 1) (clamped to the plane) of S and T -> shared memory; returns the maxima of what was loaded
+template <typename T>
+__device__ __forceinline__ void up_load_strip(const UpParams& p, const UpUnit& x, int halo, float* sS, float* sT, int& r0,
+                                              int& nr, float& ms, float& mt) {
+    r0 = max(0, x.i0 - halo);
+    const int r1 = min(p.Hl, x.i1 + halo);
+    nr = r1 - r0;
+    const size_t base = ((size_t)x.b * p.C + x.ch) * (size_t)p.Hl * p.Wl + (size_t)r0 * p.Wl;
+    const T* gs = static_cast<const T*>(p.S) + base;
+    const T* gt = static_cast<const T*>(p.T) + base;
+    ms = kUpFloor;
+    mt = kUpFloor;
+    for (int e = threadIdx.x; e < nr * p.Wl; e += kUpThreads) {
+        const float a = up_load<T>(gs + e), b = up_load<T>(gt + e);
+        sS[e] = a;
+        sT[e] = b;
+        ms = fmaxf(ms, a);
+        mt = fmaxf(mt, b);
+    }
+}
+
+// the 3 x 3 neighbourhood of cell (i, j) with clamped indices, from the strip in shared memory
+__device__ __forceinline__ void up_nbhd(const float* sm, int Wl, int Hl, int r0, int i, int j, float (&a)[3][3]) {
+    const int im = max(i - 1, 0) - r0, ic = i - r0, ip = min(i + 1, Hl - 1) - r0;
+    const int jm = max(j - 1, 0), jp = min(j + 1, Wl - 1);
+    a[0][0] = sm[im * Wl + jm]; a[0][1] = sm[im * Wl + j]; a[0][2] = sm[im * Wl + jp];
+    a[1][0] = sm[ic * Wl + jm]; a[1][1] = sm[ic * Wl + j]; a[1][2] = sm[ic * Wl + jp];
+    a[2][0] = sm[ip * Wl + jm]; a[2][1] = sm[ip * Wl + j]; a[2][2] = sm[ip * Wl + jp];
+}
+// horizontal pass: h[d][kx] = value of neighbourhood row d at up-sampled column s*j + kx (same operation order
+// as ATen's upsample_bilinear2d: w0*x0 + w1*x1)
+template <int S>
+__device__ __forceinline__ void up_hrows(const float (&a)[3][3], float (&h)[3][S]) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int kx = 0; kx < S; ++kx) {
+            const int f = UpW<S>::first(kx) + 1;
+            const float w1 = UpW<S>::w1(kx);
+            h[d][kx] = (1.f - w1) * a[d][f] + w1 * a[d][f + 1];
+        }
+    }
+}
+template <int S>
+__device__ __forceinline__ float up_value(const float (&h)[3][S], int ky, int kx) {
+    const int f = UpW<S>::first(ky) + 1;
+    const float w1 = UpW<S>::w1(ky);
+    return (1.f - w1) * h[f][kx] + w1 * h[f + 1][kx];
+}
+
+__device__ __forceinline__ float block_max(float v, float* red) {
+    v = warp_max(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float r = red[0];
+#pragma unroll
+    for (int w = 1; w < kUpThreads / 32; ++w) r = fmaxf(r, red[w]);
+    return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float r = red[0];
+#pragma unroll
+    for (int w = 1; w < kUpThreads / 32; ++w) r += red[w];
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------ kernel 1
+template <typename T, int S>
+__global__ void __launch_bounds__(kUpThreads) kl_rows_up_stats_kernel(const UpParams p) {
+    extern __shared__ __align__(16) float up_smem[];
+    float* sS = up_smem;
+    float* sT = sS + (p.SR + 2) * p.Wl;
+    __shared__ float red[kUpThreads / 32];
+    for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const UpUnit x = up_unit(p, u);
+        int r0, nr;
+        float ms, mt;
+        __syncthreads();   // the previous unit's readers are done with the strip
+        up_load_strip<T>(p, x, 1, sS, sT, r0, nr, ms, mt);
+        ms = block_max(ms, red);
+        mt = block_max(mt, red);
+        const float rs2 = ms * p.c2, rt2 = mt * p.c2;
+        float zs = 0.f, zt = 0.f, acc = 0.f;
+        const int ncell = (x.i1 - x.i0) * p.Wl;
+        for (int c = threadIdx.x; c < ncell; c += kUpThreads) {
+            const int i = x.i0 + c / p.Wl, j = c % p.Wl;
+            float a[3][3], hs[3][S], ht[3][S];
+            up_nbhd(sS, p.Wl, p.Hl, r0, i, j, a);
+            up_hrows<S>(a, hs);
+            up_nbhd(sT, p.Wl, p.Hl, r0, i, j, a);
+            up_hrows<S>(a, ht);
+#pragma unroll
+            for (int ky = 0; ky < S; ++ky) {
+#pragma unroll
+                for (int kx = 0; kx < S; ++kx) {
+                    const float vs = up_value<S>(hs, ky, kx), vt = up_value<S>(ht, ky, kx);
+                    const float es = fast_exp2(fmaf(vs, p.c2, -rs2)), et = fast_exp2(fmaf(vt, p.c2, -rt2));
+                    zs += es;
+                    zt += et;
+                    acc = fmaf(et, vt - vs, acc);
+                }
+            }
+        }
+        zs = block_sum(zs, red);
+        zt = block_sum(zt, red);
+        acc = block_sum(acc, red);
+        if (threadIdx.x == 0) {
+            float4* rec = reinterpret_cast<float4*>(p.part + u * 8);
+            rec[0] = make_float4(ms, mt, zs, zt);
+            rec[1] = make_float4(acc, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ kernel 2
+template <typename T, int S>
+__global__ void __launch_bounds__(kUpThreads) kl_rows_up_grad_kernel(const UpParams p) {
+    extern __shared__ __align__(16) float up_smem[];
+    float* sS = up_smem;
+    float* sT = sS + (p.SR + 4) * p.Wl;
+    float* planes = sT + (p.SR + 4) * p.Wl;          // [9][SR][Wl]
+    __shared__ float rowstat[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int plane_sz = p.SR * p.Wl;
+    for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const UpUnit x = up_unit(p, u);
+        __syncthreads();   // the previous unit is done with the shared memory
+        // ---- the statistics of my row: merge the records of its channels x strips (warp 0, fixed order)
+        if (warp == 0) {
+            const int g_real = min(p.g, p.C - x.grp * p.g);
+            const long long first = ((long long)x.b * p.C + (long long)x.grp * p.g) * p.NS;
+            const int nrec = g_real * p.NS;
+            float ms = kUpFloor, mt = kUpFloor;
+            for (int r = lane; r < nrec; r += 32) {
+                const float4 q = *reinterpret_cast<const float4*>(p.part + (first + r) * 8);
+                ms = fmaxf(ms, q.x);
+                mt = fmaxf(mt, q.y);
+            }
+            ms = warp_max(ms);
+            mt = warp_max(mt);
+            float zs = 0.f, zt = 0.f, acc = 0.f;
+            for (int r = lane; r < nrec; r += 32) {
+                const float4 q0 = *reinterpret_cast<const float4*>(p.part + (first + r) * 8);
+                const float a = p.part[(first + r) * 8 + 4];
+                const float fs = fast_exp2((q0.x - ms) * p.c2), ft = fast_exp2((q0.y - mt) * p.c2);
+                zs = fmaf(q0.z, fs, zs);
+                zt = fmaf(q0.w, ft, zt);
+                acc = fmaf(a, ft, acc);
+            }
+            zs = warp_sum(zs);
+            zt = warp_sum(zt);
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                rowstat[0] = ms;
+                rowstat[1] = mt;
+                rowstat[2] = p.coef / zs;
+                rowstat[3] = p.coef / zt;
+                if (x.j == 0 && x.i0 == 0) {
+                    // KL(p||q) = sum p (t - s)/tau - lse_t + lse_s, once per row
+                    const float kl = p.inv_tau * acc / zt - ((mt - ms) * p.inv_tau + (logf(zt) - logf(zs)));
+                    p.row_kl[x.b * p.G + x.grp] = kl;
+                }
+            }
+        }
+        int r0, nr;
+        float dum0, dum1;
+        up_load_strip<T>(p, x, 2, sS, sT, r0, nr, dum0, dum1);
+        __syncthreads();
+        const float rs2 = rowstat[0] * p.c2, rt2 = rowstat[1] * p.c2, gsc = rowstat[2], gtc = rowstat[3];
+        // ---- cells of the strip and of the cell rows just outside it: block gradient -> nine contributions
+        const int ca = max(0, x.i0 - 1), cb = min(p.Hl, x.i1 + 1);
+        const int ncell = (cb - ca) * p.Wl;
+        for (int c = threadIdx.x; c < ncell; c += kUpThreads) {
+            const int i = ca + c / p.Wl, j = c % p.Wl;
+            float a[3][3], hs[3][S], ht[3][S];
+            up_nbhd(sS, p.Wl, p.Hl, r0, i, j, a);
+            up_hrows<S>(a, hs);
+            up_nbhd(sT, p.Wl, p.Hl, r0, i, j, a);
+            up_hrows<S>(a, ht);
+            float m[3][3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int e = 0; e < 3; ++e) m[d][e] = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < S; ++ky) {
+                float tr[3] = {0.f, 0.f, 0.f};      // this block row folded onto the three low-res columns
+#pragma unroll
+                for (int kx = 0; kx < S; ++kx) {
+                    const float vs = up_value<S>(hs, ky, kx), vt = up_value<S>(ht, ky, kx);
+                    const float es = fast_exp2(fmaf(vs, p.c2, -rs2)), et = fast_exp2(fmaf(vt, p.c2, -rt2));
+                    const float gv = es * gsc - et * gtc;
+                    const int f = UpW<S>::first(kx) + 1;
+                    const float w1 = UpW<S>::w1(kx);
+                    tr[f] = fmaf(1.f - w1, gv, tr[f]);
+                    tr[f + 1] = fmaf(w1, gv, tr[f + 1]);
+                }
+                const int f = UpW<S>::first(ky) + 1;
+                const float w1 = UpW<S>::w1(ky);
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                    m[f][e] = fmaf(1.f - w1, tr[e], m[f][e]);
+                    m[f + 1][e] = fmaf(w1, tr[e], m[f + 1][e]);
+                }
+            }
+            // taps clamped at the border of the plane fall onto the cell itself
+            if (i == 0) {
+#pragma unroll
+                for (int e = 0; e < 3; ++e) { m[1][e] += m[0][e]; m[0][e] = 0.f; }
+            }
+            if (i == p.Hl - 1) {
+#pragma unroll
+                for (int e = 0; e < 3; ++e) { m[1][e] += m[2][e]; m[2][e] = 0.f; }
+            }
+            if (j == 0) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) { m[d][1] += m[d][0]; m[d][0] = 0.f; }
+            }
+            if (j == p.Wl - 1) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) { m[d][1] += m[d][2]; m[d][2] = 0.f; }
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const int ti = i + d - 1;
+                if (ti < x.i0 || ti >= x.i1) continue;
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                    const int tj = j + e - 1;
+                    if (tj < 0 || tj >= p.Wl) continue;
+                    planes[(d * 3 + e) * plane_sz + (ti - x.i0) * p.Wl + tj] = m[d][e];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- every output cell: its nine contributions in a fixed order
+        T* out = static_cast<T*>(p.dS) + ((size_t)x.b * p.C + x.ch) * (size_t)p.Hl * p.Wl + (size_t)x.i0 * p.Wl;
+        const int nout = (x.i1 - x.i0) * p.Wl;
+        for (int c = threadIdx.x; c < nout; c += kUpThreads) {
+            const int ti = x.i0 + c / p.Wl, tj = c % p.Wl;
+            float v = 0.f;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const int si = ti - (d - 1);           // the cell this contribution comes from
+                if (si < 0 || si >= p.Hl) continue;
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                    const int sj = tj - (e - 1);
+                    if (sj < 0 || sj >= p.Wl) continue;
+                    v += planes[(d * 3 + e) * plane_sz + c];
+                }
+            }
+            up_store<T>(out + c, v);
+        }
+    }
+    // ---- loss: the last CTA sums the row terms in a fixed order
+    __shared__ unsigned ticket_s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        ticket_s = atomicAdd(&p.ctrl[0], 1u);
+    }
+    __syncthreads();
+    if (ticket_s == gridDim.x - 1) {
+        __threadfence();
+        double acc = 0.0;
+        for (int r = threadIdx.x; r < p.R; r += kUpThreads) acc += (double)__ldcg(&p.row_kl[r]);
+        // block reduction in double, fixed order
+        __shared__ double dred[kUpThreads / 32];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) dred[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < kUpThreads / 32; ++w) t += dred[w];
+            *p.loss = (float)((double)p.loss_scale * t);
+            atomicExch(&p.ctrl[0], 0u);
+        }
+    }
+}
+
+// ====================================================================================================
+size_t up_smem_bytes(int SR, int Wl) { return sizeof(float) * ((size_t)2 * (SR + 4) * Wl + (size_t)9 * SR * Wl); }
+
+template <typename T, int S>
+static cudaError_t launch_up_t(const UpParams& p, int sms, cudaStream_t stream) {
+    const size_t smem1 = sizeof(float) * (size_t)2 * (p.SR + 2) * p.Wl;
+    const size_t smem2 = up_smem_bytes(p.SR, p.Wl);
+    auto k1 = kl_rows_up_stats_kernel<T, S>;
+    auto k2 = kl_rows_up_grad_kernel<T, S>;
+    static bool configured = false;
+    static int occ1 = 1, occ2 = 1;
+    static size_t cfg1 = 0, cfg2 = 0;
+    if (!configured || smem1 > cfg1 || smem2 > cfg2) {
+        cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e != cudaSuccess) return e;
+        cfg1 = smem1;
+        cfg2 = smem2;
+        configured = true;
+    }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k1, kUpThreads, smem1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k2, kUpThreads, smem2);
+    if (occ1 < 1 || occ2 < 1) return cudaErrorLaunchOutOfResources;
+    long long g1 = (long long)sms * occ1, g2 = (long long)sms * occ2;
+    if (g1 > p.units) g1 = p.units;
+    if (g2 > p.units) g2 = p.units;
+    k1<<<(unsigned)g1, kUpThreads, smem1, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k2<<<(unsigned)g2, kUpThreads, smem2, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kl_rows_up(const UpParams& p, bool bf16, int sms, cudaStream_t stream) {
+    switch (p.scale) {
+        case 2: return bf16 ? launch_up_t<__nv_bfloat16, 2>(p, sms, stream) : launch_up_t<float, 2>(p, sms, stream);
+        case 4: return bf16 ? launch_up_t<__nv_bfloat16, 4>(p, sms, stream) : launch_up_t<float, 4>(p, sms, stream);
+        case 8: return bf16 ? launch_up_t<__nv_bfloat16, 8>(p, sms, stream) : launch_up_t<float, 8>(p, sms, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace sd

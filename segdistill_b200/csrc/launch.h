@@ -20,6 +20,9 @@ int kl_rows_stream_chunk_capacity();
 cudaError_t launch_kl_rows_cluster(const RowsParams& p, const ClusterGeom& g, bool bf16, int sms, cudaStream_t stream,
                                    bool probe_only);
 
+// kl_rows_up.cu
+cudaError_t launch_kl_rows_up(const UpParams& p, bool bf16, int sms, cudaStream_t stream);
+
 // kl_pixels.cu   (mapS/mapT point at CUtensorMap objects)
 cudaError_t launch_kl_pixels_tma(const void* mapS, const void* mapT, const PixParams& p, bool bf16, int grid,
                                  size_t smem, cudaStream_t stream);

@@ -125,6 +125,48 @@ struct ClusterGeom {
     int pieces_full;  // pieces (rows of l[0] x slices they intersect) of one complete super-row
 };
 
+// ---------------------------------------------------------------- rows on bilinearly up-sampled maps (kl_rows_up.cu)
+struct UpParams {
+    const void* S;
+    const void* T;
+    void* dS;                // low resolution, like S
+    const int32_t* perm;     // [C] or null
+    int B, C, Hl, Wl;        // low-resolution maps
+    int scale;               // 2, 4 or 8: the maps are up-sampled to (scale*Hl) x (scale*Wl), bilinear, align_corners=False
+    int g, G, R;             // channels per row, rows per sample, B*G
+    int SR, NS;              // low-res rows per strip, strips per plane
+    long long units;         // B*C*NS
+    float c2, inv_tau, coef, loss_scale;
+    float* loss;
+    float* row_kl;           // [R]
+    float* part;             // [units][8] partial records of kernel 1
+    unsigned* ctrl;
+};
+struct UpWorkspace {
+    size_t off_ctrl, off_rowkl, off_part, bytes;
+};
+inline int up_strip_rows(int Hl, int Wl) {
+    long long sr = (100 * 1024 / 4 / (long long)Wl - 8) / 11;
+    if (sr > 16) sr = 16;
+    if (sr > Hl) sr = Hl;
+    return (int)sr;            // < 1: the plane is too wide for this kernel
+}
+inline UpWorkspace up_workspace_layout(long long B, long long C, long long Hl, long long Wl, long long g) {
+    UpWorkspace w;
+    if (g > C) g = C;
+    const long long G = (C + g - 1) / g;
+    int sr = up_strip_rows((int)Hl, (int)Wl);
+    if (sr < 1) sr = 1;
+    const long long NS = (Hl + sr - 1) / sr;
+    size_t o = 0;
+    w.off_ctrl = o;   o += kArenaBytes;
+    w.off_rowkl = o;  o += sizeof(float) * (size_t)(B * G);
+    o = (o + 127) & ~(size_t)127;
+    w.off_part = o;   o += sizeof(float) * 8 * (size_t)(B * C * NS);
+    w.bytes = (o + 255) & ~(size_t)255;
+    return w;
+}
+
 // ---------------------------------------------------------------- pixels (PD / AT)
 struct PixParams {
     const void* S;

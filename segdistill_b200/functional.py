@@ -46,6 +46,22 @@ class _KLRows(torch.autograd.Function):
         return (_finish_backward(ctx, grad_output),) + (None,) * 8
 
 
+class _KLRowsUp(torch.autograd.Function):
+    """Channel-mode KL behind the reference's bilinear resize (losses.py:25-33,101-102), the resize fused in."""
+
+    @staticmethod
+    def forward(ctx, x_student, x_teacher, scale, group, tau, alpha, perm):
+        loss, ds, _ = _cabi.kl_rows_up(x_student, x_teacher, scale, group=group, tau=tau, alpha=alpha, perm=perm)
+        ctx.ds = ds if x_student.requires_grad else None
+        ctx.in_dtype, ctx.in_shape = x_student.dtype, x_student.shape
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        return (_finish_backward(ctx, grad_output),) + (None,) * 6
+
+
 PAIR_ALGO = 'auto'      # kernel of the fused two-loss launch: 'auto' | 'cluster' | 'stream' (tests force one)
 
 
@@ -156,6 +172,12 @@ def kl_rows_loss(x_student, x_teacher, group=1, tau=1.0, alpha=1.0, perm=None, a
     """alpha/R * sum_rows KL(softmax(T_row/tau) || softmax(S_row/tau)); rows = ``group`` channels x HW."""
     return _KLRows.apply(x_student, x_teacher, int(group), float(tau), float(alpha), perm, 0.0,
                          _cabi.ALGOS[algo], bchw)
+
+
+def kl_rows_up_loss(x_student, x_teacher, scale, group=1, tau=1.0, alpha=1.0, perm=None):
+    """The same on maps up-sampled ``scale`` x (bilinear, align_corners=False) inside the kernel; the gradient
+    arrives at the low-resolution ``x_student``."""
+    return _KLRowsUp.apply(x_student, x_teacher, int(scale), int(group), float(tau), float(alpha), perm)
 
 
 def kl_rows_mse_loss(x_student, x_teacher, group=1, tau=1.0, alpha=1.0, mse_weight=1.0, perm=None, algo='auto'):

@@ -10,7 +10,9 @@ Host-side behaviour kept from the reference: the alpha warm-up / early-decay sta
 (:61-92), the channel shuffle drawn from ``torch.randperm`` on the CPU global generator
 (:39) every ``interval`` steps, the bilinear resize to the label size (:25-33).  What changed:
 the shuffle and the ragged-group pad cost no copies (the kernel gathers / skips), the resize is
-skipped when sizes already match (it is an exact identity there), when ``alpha == 0`` no
+skipped when sizes already match (it is an exact identity there) and, for channel-mode losses behind a
+2x / 4x / 8x bilinear resize (every shipped preset), done inside the kernel without materialising the
+resized maps (``fuse_resize``), when ``alpha == 0`` no
 kernel runs at all, and the returned scalar is always fp32 (the kernels accumulate in fp32;
 the reference returns the feature dtype, i.e. a bf16/fp16-rounded loss under mixed precision).
 """
@@ -38,6 +40,7 @@ def _ramp(kind, alpha0, frac):
 
 class KLDLoss(nn.Module):
     algo = 'auto'          # 'auto' | 'tma' | 'generic' (tests force one)
+    fuse_resize = True     # channel mode behind a 2x / 4x / 8x bilinear resize: up-sample inside the kernel
 
     def __init__(self, alpha=1, tau=1, resize_config=None, shuffle_config=None, transform_config=None,
                  warmup_config=None, earlydecay_config=None):
@@ -85,7 +88,8 @@ class KLDLoss(nn.Module):
         inspect to batch two entries that hook the same tensors into one kernel.  ``resized`` is an
         optional cache {(id(tensor), size): resized tensor} shared between the entries of one step."""
         self._update_alpha(n_iter)
-        if self.resize_config:
+        upscale = self._fusable_upscale(x_student, x_teacher, gt)
+        if self.resize_config and not upscale:
             x_student = self._resized_cached(x_student, gt, resized)
             x_teacher = self._resized_cached(x_teacher, gt, resized)
         perm = None
@@ -95,7 +99,26 @@ class KLDLoss(nn.Module):
         tc = self.transform_config
         return {'student': x_student, 'teacher': x_teacher, 'perm': perm, 'alpha': self.alpha, 'tau': self.tau,
                 'kind': tc['loss_type'] if tc else None, 'group': tc.get('group_size') if tc else None,
-                'algo': self.algo}
+                'algo': self.algo, 'upscale': upscale}
+
+    def _fusable_upscale(self, x_student, x_teacher, gt):
+        """Integer factor of the resize when the kernel can do it on the fly (reference :25-33 with the presets'
+        bilinear / align_corners=False, channel mode, maps on the GPU), else 0 (resize on the host as before)."""
+        from . import _cabi
+        rc, tc = self.resize_config, self.transform_config
+        if not (self.fuse_resize and rc and tc and gt is not None and self.algo == 'auto'):
+            return 0
+        if tc['loss_type'] != 'channel' or rc.get('mode') != 'bilinear' or rc.get('align_corners'):
+            return 0
+        x = x_student
+        if x.dim() != 4 or not x.is_cuda or x.shape != x_teacher.shape or x.dtype != x_teacher.dtype:
+            return 0
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            return 0
+        (h, w), (hg, wg) = x.shape[2:], gt.shape[2:]
+        if hg % h or wg % w or hg // h != wg // w or hg // h not in _cabi.UP_SCALES:
+            return 0
+        return hg // h if _cabi.up_supported(h, w) else 0
 
     def _resized_cached(self, x, gt, cache):
         if cache is None or gt is None:
@@ -111,6 +134,9 @@ class KLDLoss(nn.Module):
         if plan['alpha'] == 0:
             return SF.zero_loss(x_student)
         kind = plan['kind']
+        if plan.get('upscale'):
+            return SF.kl_rows_up_loss(x_student, x_teacher, plan['upscale'], group=plan['group'], tau=plan['tau'],
+                                      alpha=plan['alpha'], perm=plan['perm'])
         if kind == 'pixel':
             # softmax over all channels of a pixel: a channel permutation changes nothing
             return SF.kl_pixels_loss(x_student, x_teacher, tau=plan['tau'], alpha=plan['alpha'], algo=plan['algo'])
@@ -126,7 +152,7 @@ class KLDLoss(nn.Module):
     def can_fuse(pa, pb):
         """Two planned calls that one two-loss launch can serve: channel mode on the very same (resized)
         tensors, no shuffle this step, non-zero weights, nested rows, default kernel selection."""
-        if pa['kind'] != 'channel' or pb['kind'] != 'channel':
+        if pa['kind'] != 'channel' or pb['kind'] != 'channel' or pa.get('upscale') or pb.get('upscale'):
             return False
         if pa['student'] is not pb['student'] or pa['teacher'] is not pb['teacher']:
             return False

@@ -585,3 +585,83 @@ def test_packed_short_rows_with_fused_mse():
     m = oracle.mse_loss_torch(x, t, 0.5)
     m.backward()
     _assert_close(got[0], got[1], r1[0] + m.item(), r1[1] + x.grad)
+
+
+# ------------------------------------------------------------------ bilinear resize fused into the channel-mode kernels
+UP_CASES = [
+    # shape (low resolution), scale, module kwargs, n_iter
+    ((2, 19, 16, 16), 2, dict(group_size=1, alpha=1, tau=1), 1),
+    ((2, 12, 32, 32), 4, dict(group_size=5, alpha=2, tau=3), 1),            # ragged last group (12 % 5)
+    ((1, 10, 24, 40), 8, dict(group_size=10, alpha=3, tau=2), 1),           # non-square, one row per sample
+    ((2, 30, 40, 24), 4, dict(group_size=10, alpha=3, tau=2), 1000),        # shuffle step: channel gather
+    ((1, 4, 50, 7), 2, dict(group_size=3, alpha=1, tau=0.5), 1),            # strips of 16 rows: 50 = 3*16 + 2
+    ((3, 6, 1, 1), 4, dict(group_size=2, alpha=1, tau=1), 1),               # a single cell: every tap clamped
+]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('case', range(len(UP_CASES)))
+def test_fused_bilinear_resize_matches_reference_resize(case, dtype):
+    """KLDLoss.resize (losses.py:25-33) + channel transform + KL, the up-sampled maps never materialised."""
+    shape, scale, kw, n_iter = UP_CASES[case]
+    s, t = seeded_pair(shape, seed=300 + case, scale=2.0, dtype=dtype)
+    gt_hw = (shape[2] * scale, shape[3] * scale)
+    torch.manual_seed(11)
+    perm = torch.randperm(shape[1]) if n_iter % 1000 == 0 else None
+    ref = _oracle_run('CGDLoss', kw, s, t, gt_hw, n_iter, perm=perm)
+    crit = sd.CGDLoss(**kw)
+    x = s.to(dev()).requires_grad_(True)
+    gt = torch.zeros(shape[0], 1, *gt_hw, dtype=torch.long, device=dev())
+    torch.manual_seed(11)
+    before = _cabi.launch_count()
+    loss = crit(x, t.to(dev()), gt, n_iter)
+    assert _cabi.last_kernel() == 'kl_rows_up_kernel' and _cabi.launch_count() - before == 2
+    loss.backward()
+    torch.cuda.synchronize()
+    assert x.grad.shape == x.shape and x.grad.dtype == dtype
+    got = (loss.item(), x.grad.float().cpu())
+    if dtype == torch.bfloat16:
+        _assert_close(*got, *ref, loss_rtol=2e-5, grad_rtol=BF16_GRAD_RTOL)
+    else:
+        _assert_close(*got, *ref)
+    if dtype == torch.bfloat16:
+        return    # (F.interpolate would round the up-sampled maps to bf16: not the same numbers)
+    # the host-side resize + the ordinary kernels give the same numbers
+    crit2 = sd.CGDLoss(**kw)
+    crit2.fuse_resize = False
+    y = s.to(dev()).requires_grad_(True)
+    torch.manual_seed(11)
+    loss2 = crit2(y, t.to(dev()), gt, n_iter)
+    assert _cabi.last_kernel() != 'kl_rows_up_kernel'
+    loss2.backward()
+    _assert_close(loss2.item(), y.grad.float().cpu(), *ref)
+
+
+def test_fused_resize_only_where_it_applies():
+    """Non-integer or unsupported factors, pixel mode and the plain KLDLoss keep the host-side resize."""
+    s, t = seeded_pair((2, 6, 8, 8), seed=5)
+    for crit, gt_hw in ((sd.CDLoss(), (24, 24)), (sd.CDLoss(), (12, 8)), (sd.PDLoss(), (32, 32)), (sd.CDLoss(), (4, 4))):
+        name = type(crit).__name__
+        ref = _oracle_run(name, {}, s, t, gt_hw, 1)
+        got = _run(crit, s, t, gt_hw, 1)
+        _assert_close(*got, *ref)
+    x = s.to(dev()).requires_grad_(True)
+    gt = torch.zeros(2, 1, 24, 24, dtype=torch.long, device=dev())
+    sd.CDLoss()(x, t.to(dev()), gt, 1)
+    assert _cabi.last_kernel() != 'kl_rows_up_kernel'
+
+
+def test_fused_resize_training_shape_cgd_and_cd():
+    """The shipped presets: logits 2x150x128x128 (1/4 resolution) resized to 512x512 (samples_per_gpu=2)."""
+    shape = (2, 150, 128, 128)
+    s, t = seeded_pair(shape, seed=9, scale=3.0)
+    for cls, kw in (('CGDLoss', {}), ('CDLoss', {})):
+        ref = _oracle_run(cls, kw, s, t, (512, 512), 1)
+        got = _run(getattr(sd, cls)(**kw), s, t, (512, 512), 1)
+        _assert_close(*got, *ref)
+    # size-independent property: the gradient of every row sums to zero through the (partition-of-unity) stencil
+    x = s.to(dev()).requires_grad_(True)
+    gt = torch.zeros(2, 1, 512, 512, dtype=torch.long, device=dev())
+    sd.CDLoss()(x, t.to(dev()), gt, 1).backward()
+    rows = x.grad.double().sum(dim=(2, 3)).abs().max().item()
+    assert rows <= 1e-6 * x.grad.double().abs().sum(dim=(2, 3)).max().item()
