@@ -468,6 +468,27 @@ def extra_configs(dev):
     nbytes = sum(3 * s.numel() * 4 for s, _ in pairs)
     out['cfg2_cgd_4stages_b16_f32'] = {'ms': ms, 'ms_eager': eager, 'mpixel_s': sum(s.shape[0] * s.shape[2] * s.shape[3] for s, _ in pairs) / ms / 1e3,
                                        'gbs': nbytes / ms / 1e6, 'frac_of_measured_peak': nbytes / ms / 1e6 / peak}
+    # the reference's real training path: logits at 1/4 resolution resized to the 512x512 labels;
+    # fused = bilinear up-sampling inside the loss kernels, host = F.interpolate first (what the reference does)
+    for name, cls, shape in (('f1_cgd_resize4_2x150x128x128_f32', sd.CGDLoss, (2, 150, 128, 128)),
+                             ('f1_cd_resize4_16x150x128x128_f32', sd.CDLoss, (16, 150, 128, 128))):
+        s, t = pair(shape, torch.float32)
+        gt = torch.zeros(shape[0], 1, 4 * shape[2], 4 * shape[3], dtype=torch.long, device=dev)
+        rec = {}
+        for tag, fuse in (('fused', True), ('host_resize', False)):
+            crit = cls()
+            crit.fuse_resize = fuse
+
+            def f(crit=crit):
+                s.grad = None
+                crit(s, t, gt, 1).backward()
+            eager, ms = timeit(f, n=10)
+            rec[tag + '_ms'] = ms
+        hi = shape[0] * shape[1] * 16 * shape[2] * shape[3]
+        rec['mpixel_s'] = shape[0] * 16 * shape[2] * shape[3] / rec['fused_ms'] / 1e3
+        rec['upsampled_gelem_s'] = hi / rec['fused_ms'] / 1e6
+        rec['speedup_vs_host_resize'] = rec['host_resize_ms'] / rec['fused_ms']
+        out[name] = rec
     # the correlation extension (tensor cores): algorithmic traffic 16 B/element fp32 (S, T read; S read again; dS written)
     for name, g, shape, dtype in (('corr_g10_16x150x128x128_bf16', 10, (16, 150, 128, 128), torch.bfloat16),
                                   ('corr_g10_16x150x128x128_f32', 10, (16, 150, 128, 128), torch.float32),

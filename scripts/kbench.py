@@ -55,6 +55,10 @@ def main():
         'corr150_bf16': (L, torch.bfloat16, lambda s, t: _cabi.cgd_corr(s, t, group=150)),
         'corr256_512ch_bf16': ((16, 512, 64, 64), torch.bfloat16, lambda s, t: _cabi.cgd_corr(s, t, group=256)),
         'corr256_512ch_f32': ((16, 512, 64, 64), torch.float32, lambda s, t: _cabi.cgd_corr(s, t, group=256)),
+        'up4_cgd10_2x150x128_f32': ((2, 150, 128, 128), torch.float32, lambda s, t: _cabi.kl_rows_up(s, t, 4, group=10, tau=2.0, alpha=3.0)),
+        'up4_cgd10_16x150x128_f32': (L, torch.float32, lambda s, t: _cabi.kl_rows_up(s, t, 4, group=10, tau=2.0, alpha=3.0)),
+        'up8_cd_16x150x64_f32': ((16, 150, 64, 64), torch.float32, lambda s, t: _cabi.kl_rows_up(s, t, 8, group=1)),
+        'up4_cgd10_16x150x128_bf16': (L, torch.bfloat16, lambda s, t: _cabi.kl_rows_up(s, t, 4, group=10, tau=2.0, alpha=3.0)),
         'pd_f32': (L, torch.float32, lambda s, t: _cabi.kl_pixels(s, t)),
         'pd_bf16': (L, torch.bfloat16, lambda s, t: _cabi.kl_pixels(s, t)),
         'cd_512ch_f32': ((16, 512, 64, 64), torch.float32, lambda s, t: _cabi.kl_rows(s, t, group=1, tau=4.0)),

@@ -544,6 +544,8 @@ int sd_kl_rows_up_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl,
     p.NS = (Hl + SR - 1) / SR;
     p.units = (long long)B * C * p.NS;
     p.c2 = (float)(1.4426950408889634 / (double)tau);
+    p.inv_c2 = (float)((double)tau / 1.4426950408889634);
+    p.inv_Wl = 1.0f / (float)Wl;
     p.inv_tau = (float)(1.0 / (double)tau);
     p.coef = (float)((double)grad_scale * (double)alpha / ((double)p.R * (double)tau));
     p.loss_scale = (float)((double)alpha / (double)p.R);

@@ -72,10 +72,12 @@ __device__ __forceinline__ UpUnit up_unit(const UpParams& p, long long u) {
     return x;
 }
 
-// strip rows [i0 - 1, i1 + 1) (clamped to the plane) of S and T -> shared memory; returns the maxima of what was loaded
-template <typename T>
+// strip rows [i0 - halo, i1 + halo) (clamped to the plane) of S and T -> shared memory; returns the maxima of what
+// was loaded.  SCALED: stored as (x - ref) * c2, the exponent the kernels need (interpolation is affine-invariant:
+// the weights of a pixel sum to one).
+template <typename T, bool SCALED>
 __device__ __forceinline__ void up_load_strip(const UpParams& p, const UpUnit& x, int halo, float* sS, float* sT, int& r0,
-                                              int& nr, float& ms, float& mt) {
+                                              int& nr, float& ms, float& mt, float ref_s = 0.f, float ref_t = 0.f) {
     r0 = max(0, x.i0 - halo);
     const int r1 = min(p.Hl, x.i1 + halo);
     nr = r1 - r0;
@@ -86,11 +88,16 @@ __device__ __forceinline__ void up_load_strip(const UpParams& p, const UpUnit& x
     mt = kUpFloor;
     for (int e = threadIdx.x; e < nr * p.Wl; e += kUpThreads) {
         const float a = up_load<T>(gs + e), b = up_load<T>(gt + e);
-        sS[e] = a;
-        sT[e] = b;
+        sS[e] = SCALED ? (a - ref_s) * p.c2 : a;
+        sT[e] = SCALED ? (b - ref_t) * p.c2 : b;
         ms = fmaxf(ms, a);
         mt = fmaxf(mt, b);
     }
+}
+// cell index -> (row, column) without an integer division (c < 2^20)
+__device__ __forceinline__ void up_cell(int c, int Wl, float inv_Wl, int& r, int& j) {
+    r = (int)(((float)c + 0.5f) * inv_Wl);
+    j = c - r * Wl;
 }
 
 // the 3 x 3 neighbourhood of cell (i, j) with clamped indices, from the strip in shared memory
@@ -101,25 +108,32 @@ __device__ __forceinline__ void up_nbhd(const float* sm, int Wl, int Hl, int r0,
     a[1][0] = sm[ic * Wl + jm]; a[1][1] = sm[ic * Wl + j]; a[1][2] = sm[ic * Wl + jp];
     a[2][0] = sm[ip * Wl + jm]; a[2][1] = sm[ip * Wl + j]; a[2][2] = sm[ip * Wl + jp];
 }
-// horizontal pass: h[d][kx] = value of neighbourhood row d at up-sampled column s*j + kx (same operation order
-// as ATen's upsample_bilinear2d: w0*x0 + w1*x1)
+// horizontal pass: h[d][kx] = value of neighbourhood row d at up-sampled column s*j + kx, as x0 + w1 (x1 - x0)
 template <int S>
 __device__ __forceinline__ void up_hrows(const float (&a)[3][3], float (&h)[3][S]) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
+        const float dx[2] = {a[d][1] - a[d][0], a[d][2] - a[d][1]};
 #pragma unroll
         for (int kx = 0; kx < S; ++kx) {
             const int f = UpW<S>::first(kx) + 1;
-            const float w1 = UpW<S>::w1(kx);
-            h[d][kx] = (1.f - w1) * a[d][f] + w1 * a[d][f + 1];
+            h[d][kx] = fmaf(UpW<S>::w1(kx), dx[f], a[d][f]);
         }
     }
 }
+// vertical differences of the three interpolated rows: v(ky, kx) = h[f][kx] + w1 dv[f][kx]
 template <int S>
-__device__ __forceinline__ float up_value(const float (&h)[3][S], int ky, int kx) {
+__device__ __forceinline__ void up_vdiff(const float (&h)[3][S], float (&dv)[2][S]) {
+#pragma unroll
+    for (int kx = 0; kx < S; ++kx) {
+        dv[0][kx] = h[1][kx] - h[0][kx];
+        dv[1][kx] = h[2][kx] - h[1][kx];
+    }
+}
+template <int S>
+__device__ __forceinline__ float up_value(const float (&h)[3][S], const float (&dv)[2][S], int ky, int kx) {
     const int f = UpW<S>::first(ky) + 1;
-    const float w1 = UpW<S>::w1(ky);
-    return (1.f - w1) * h[f][kx] + w1 * h[f + 1][kx];
+    return fmaf(UpW<S>::w1(ky), dv[f][kx], h[f][kx]);
 }
 
 __device__ __forceinline__ float block_max(float v, float* red) {
@@ -157,25 +171,34 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_stats_kernel(const UpPa
         int r0, nr;
         float ms, mt;
         __syncthreads();   // the previous unit's readers are done with the strip
-        up_load_strip<T>(p, x, 1, sS, sT, r0, nr, ms, mt);
+        up_load_strip<T, false>(p, x, 1, sS, sT, r0, nr, ms, mt);
         ms = block_max(ms, red);
         mt = block_max(mt, red);
-        const float rs2 = ms * p.c2, rt2 = mt * p.c2;
+        // second sweep over the (small) strip: raw values -> exponents relative to the strip maxima
+        for (int e = threadIdx.x; e < nr * p.Wl; e += kUpThreads) {
+            sS[e] = (sS[e] - ms) * p.c2;
+            sT[e] = (sT[e] - mt) * p.c2;
+        }
+        __syncthreads();
         float zs = 0.f, zt = 0.f, acc = 0.f;
         const int ncell = (x.i1 - x.i0) * p.Wl;
         for (int c = threadIdx.x; c < ncell; c += kUpThreads) {
-            const int i = x.i0 + c / p.Wl, j = c % p.Wl;
-            float a[3][3], hs[3][S], ht[3][S];
+            int i, j;
+            up_cell(c, p.Wl, p.inv_Wl, i, j);
+            i += x.i0;
+            float a[3][3], hs[3][S], ht[3][S], ds_[2][S], dt_[2][S];
             up_nbhd(sS, p.Wl, p.Hl, r0, i, j, a);
             up_hrows<S>(a, hs);
             up_nbhd(sT, p.Wl, p.Hl, r0, i, j, a);
             up_hrows<S>(a, ht);
+            up_vdiff<S>(hs, ds_);
+            up_vdiff<S>(ht, dt_);
 #pragma unroll
             for (int ky = 0; ky < S; ++ky) {
 #pragma unroll
                 for (int kx = 0; kx < S; ++kx) {
-                    const float vs = up_value<S>(hs, ky, kx), vt = up_value<S>(ht, ky, kx);
-                    const float es = fast_exp2(fmaf(vs, p.c2, -rs2)), et = fast_exp2(fmaf(vt, p.c2, -rt2));
+                    const float vs = up_value<S>(hs, ds_, ky, kx), vt = up_value<S>(ht, dt_, ky, kx);
+                    const float es = fast_exp2(vs), et = fast_exp2(vt);
                     zs += es;
                     zt += et;
                     acc = fmaf(et, vt - vs, acc);
@@ -185,6 +208,8 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_stats_kernel(const UpPa
         zs = block_sum(zs, red);
         zt = block_sum(zt, red);
         acc = block_sum(acc, red);
+        // acc = sum et ((t - mt) - (s - ms)) c2  ->  sum et (t - s)
+        acc = acc * p.inv_c2 + (mt - ms) * zt;
         if (threadIdx.x == 0) {
             float4* rec = reinterpret_cast<float4*>(p.part + u * 8);
             rec[0] = make_float4(ms, mt, zs, zt);
@@ -199,10 +224,11 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_grad_kernel(const UpPar
     extern __shared__ __align__(16) float up_smem[];
     float* sS = up_smem;
     float* sT = sS + (p.SR + 4) * p.Wl;
-    float* planes = sT + (p.SR + 4) * p.Wl;          // [9][SR][Wl]
+    float* planes = sT + (p.SR + 4) * p.Wl;          // [9][SR][Wl + 2]: column tj lives at tj + 1, so tj = -1 and Wl land in the pad
     __shared__ float rowstat[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int plane_sz = p.SR * p.Wl;
+    const int pstride = p.Wl + 2;
+    const int plane_sz = p.SR * pstride;
     for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
         const UpUnit x = up_unit(p, u);
         __syncthreads();   // the previous unit is done with the shared memory
@@ -243,21 +269,26 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_grad_kernel(const UpPar
                 }
             }
         }
+        __syncthreads();
+        const float gsc = rowstat[2], gtc = rowstat[3];
         int r0, nr;
         float dum0, dum1;
-        up_load_strip<T>(p, x, 2, sS, sT, r0, nr, dum0, dum1);
+        up_load_strip<T, true>(p, x, 2, sS, sT, r0, nr, dum0, dum1, rowstat[0], rowstat[1]);
         __syncthreads();
-        const float rs2 = rowstat[0] * p.c2, rt2 = rowstat[1] * p.c2, gsc = rowstat[2], gtc = rowstat[3];
         // ---- cells of the strip and of the cell rows just outside it: block gradient -> nine contributions
         const int ca = max(0, x.i0 - 1), cb = min(p.Hl, x.i1 + 1);
         const int ncell = (cb - ca) * p.Wl;
         for (int c = threadIdx.x; c < ncell; c += kUpThreads) {
-            const int i = ca + c / p.Wl, j = c % p.Wl;
-            float a[3][3], hs[3][S], ht[3][S];
+            int i, j;
+            up_cell(c, p.Wl, p.inv_Wl, i, j);
+            i += ca;
+            float a[3][3], hs[3][S], ht[3][S], ds_[2][S], dt_[2][S];
             up_nbhd(sS, p.Wl, p.Hl, r0, i, j, a);
             up_hrows<S>(a, hs);
             up_nbhd(sT, p.Wl, p.Hl, r0, i, j, a);
             up_hrows<S>(a, ht);
+            up_vdiff<S>(hs, ds_);
+            up_vdiff<S>(ht, dt_);
             float m[3][3];
 #pragma unroll
             for (int d = 0; d < 3; ++d)
@@ -268,8 +299,7 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_grad_kernel(const UpPar
                 float tr[3] = {0.f, 0.f, 0.f};      // this block row folded onto the three low-res columns
 #pragma unroll
                 for (int kx = 0; kx < S; ++kx) {
-                    const float vs = up_value<S>(hs, ky, kx), vt = up_value<S>(ht, ky, kx);
-                    const float es = fast_exp2(fmaf(vs, p.c2, -rs2)), et = fast_exp2(fmaf(vt, p.c2, -rt2));
+                    const float es = fast_exp2(up_value<S>(hs, ds_, ky, kx)), et = fast_exp2(up_value<S>(ht, dt_, ky, kx));
                     const float gv = es * gsc - et * gtc;
                     const int f = UpW<S>::first(kx) + 1;
                     const float w1 = UpW<S>::w1(kx);
@@ -301,15 +331,14 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_grad_kernel(const UpPar
 #pragma unroll
                 for (int d = 0; d < 3; ++d) { m[d][1] += m[d][2]; m[d][2] = 0.f; }
             }
+            // (contributions that left the plane were folded above and are zero; the pad columns swallow them)
+            float* pl = planes + (i - 1 - x.i0) * pstride + j;           // target (i - 1, j - 1) at column j - 1 + 1
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 const int ti = i + d - 1;
-                if (ti < x.i0 || ti >= x.i1) continue;
+                if (ti >= x.i0 && ti < x.i1) {                             // (uniform over a warp when Wl % 32 == 0)
 #pragma unroll
-                for (int e = 0; e < 3; ++e) {
-                    const int tj = j + e - 1;
-                    if (tj < 0 || tj >= p.Wl) continue;
-                    planes[(d * 3 + e) * plane_sz + (ti - x.i0) * p.Wl + tj] = m[d][e];
+                    for (int e = 0; e < 3; ++e) pl[(d * 3 + e) * plane_sz + d * pstride + e] = m[d][e];
                 }
             }
         }
@@ -318,17 +347,21 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_grad_kernel(const UpPar
         T* out = static_cast<T*>(p.dS) + ((size_t)x.b * p.C + x.ch) * (size_t)p.Hl * p.Wl + (size_t)x.i0 * p.Wl;
         const int nout = (x.i1 - x.i0) * p.Wl;
         for (int c = threadIdx.x; c < nout; c += kUpThreads) {
-            const int ti = x.i0 + c / p.Wl, tj = c % p.Wl;
+            int ti, tj;
+            up_cell(c, p.Wl, p.inv_Wl, ti, tj);
+            ti += x.i0;
+            // plane (d, e) holds what cell (ti - d + 1, tj - e + 1) sent here; where that cell does not exist
+            // (outside the map) nothing was stored
+            const float* pl = planes + (ti - x.i0) * pstride + tj + 1;
+            const bool okd[3] = {ti + 1 < p.Hl, true, ti >= 1};
+            const bool oke[3] = {tj + 1 < p.Wl, true, tj >= 1};
             float v = 0.f;
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-                const int si = ti - (d - 1);           // the cell this contribution comes from
-                if (si < 0 || si >= p.Hl) continue;
 #pragma unroll
                 for (int e = 0; e < 3; ++e) {
-                    const int sj = tj - (e - 1);
-                    if (sj < 0 || sj >= p.Wl) continue;
-                    v += planes[(d * 3 + e) * plane_sz + c];
+                    const float q = pl[(d * 3 + e) * plane_sz];
+                    v += (okd[d] && oke[e]) ? q : 0.f;
                 }
             }
             up_store<T>(out + c, v);
@@ -362,7 +395,7 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_grad_kernel(const UpPar
 }
 
 // ====================================================================================================
-size_t up_smem_bytes(int SR, int Wl) { return sizeof(float) * ((size_t)2 * (SR + 4) * Wl + (size_t)9 * SR * Wl); }
+size_t up_smem_bytes(int SR, int Wl) { return sizeof(float) * ((size_t)2 * (SR + 4) * Wl + (size_t)9 * SR * (Wl + 2)); }
 
 template <typename T, int S>
 static cudaError_t launch_up_t(const UpParams& p, int sms, cudaStream_t stream) {

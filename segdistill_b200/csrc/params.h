@@ -136,7 +136,8 @@ struct UpParams {
     int g, G, R;             // channels per row, rows per sample, B*G
     int SR, NS;              // low-res rows per strip, strips per plane
     long long units;         // B*C*NS
-    float c2, inv_tau, coef, loss_scale;
+    float c2, inv_c2, inv_tau, coef, loss_scale;
+    float inv_Wl;
     float* loss;
     float* row_kl;           // [R]
     float* part;             // [units][8] partial records of kernel 1
