@@ -170,6 +170,22 @@ def run_reference_arm(args, rank):
 
 
 # ------------------------------------------------------------------ GPU arm
+def _note(rank, msg):
+    """progress marker on stderr (a multi-GPU run that stalls shows where)"""
+    if os.environ.get('SD_BENCH_VERBOSE', '') or int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        print(f'[bench rank {rank} +{time.perf_counter() - _T0:6.1f}s] {msg}', file=sys.stderr, flush=True)
+
+
+_T0 = time.perf_counter()
+
+
+def _arm_watchdog(seconds):
+    """A rank that stalls (a peer died, a collective never completes) must not hold the box: dump the Python stacks
+    and exit non-zero after `seconds`."""
+    import faulthandler
+    faulthandler.dump_traceback_later(seconds, exit=True)
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -177,10 +193,13 @@ def run_ours(args, rank, local_rank, world):
     from segdistill_b200 import _cabi
     from segdistill_b200 import dist as sdist
 
+    _arm_watchdog(int(os.environ.get('SD_BENCH_WATCHDOG_S', '420')))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        _note(rank, 'init_process_group(nccl)')
         dist.init_process_group('nccl', device_id=dev)
+        _note(rank, 'process group up')
     assert _cabi.load().sd_device_check() == 0, 'not an sm_100 device'
 
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -199,7 +218,7 @@ def run_ours(args, rank, local_rank, world):
         return {'decode_head.linear_pred': x, 'decode_head': x}
     fS, fT = feats(S), feats(T)
 
-    def step(record=None):
+    def compute(record=None):
         S.grad = None
         if record:
             record[0].record()
@@ -211,20 +230,42 @@ def run_ours(args, rank, local_rank, world):
         (l1 + l2).backward()
         if record:
             record[2].record()
-        if world > 1:                      # the path's only collective: packed loss scalars, async
+        if world > 1:
             packed[0], packed[1] = l1.detach(), l2.detach()
-            dist.all_reduce(packed)
         return l1, l2
 
+    pending = []
+
+    def reduce_scalars():
+        """The path's only collective: the packed loss scalars of this step, all-reduced asynchronously on a copy so
+        that the next step's kernels do not queue behind it; at most 4 in flight."""
+        if world > 1:
+            buf = packed.clone()
+            pending.append((dist.all_reduce(buf, async_op=True), buf))
+            if len(pending) > 4:
+                pending.pop(0)[0].wait()
+
+    def drain_scalars():
+        while pending:
+            pending.pop(0)[0].wait()
+
+    def step(record=None):
+        r = compute(record)
+        reduce_scalars()
+        return r
+
     def sync_all():
+        drain_scalars()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
 
+    _note(rank, 'warm-up')
     for _ in range(args.warmup):
         step()
     sync_all()
+    _note(rank, 'warm-up done')
 
     # The step (dispatcher forward + autograd backward [+ the scalar all-reduce]) is a fixed launch sequence:
     # capture it once into a CUDA graph and replay it.  Eager per-step numbers are measured beside it.
@@ -242,11 +283,13 @@ def run_ours(args, rank, local_rank, world):
             # capture on the stream the warm-up ran on: its zero-filled workspace exists already (a fresh
             # capture stream would put the one-time workspace allocation + fill into every replay)
             with torch.cuda.graph(g_, stream=side):
-                static_losses = step()
+                static_losses = compute()        # (the scalar all-reduce is launched after each replay, not captured)
             graph, graph_note = g_, 'CUDA graph replay of the captured module-API step'
             for _ in range(3):
                 graph.replay()
+                reduce_scalars()
             sync_all()
+            _note(rank, 'graph captured')
         except Exception as exc:          # capture is an optimisation, never a requirement
             graph, graph_note = None, f'eager launches (graph capture failed: {type(exc).__name__})'
             torch.cuda.synchronize()
@@ -254,6 +297,7 @@ def run_ours(args, rank, local_rank, world):
     if rank == 0:
         sampler.start()
 
+    _note(rank, 'timed region')
     # ---- timed region: exactly K steps, device time
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -263,6 +307,7 @@ def run_ours(args, rank, local_rank, world):
     t_begin.record()
     for i in range(args.steps):
         l1, l2 = step(evs[i])
+    drain_scalars()
     t_end.record()
     sync_all()
     launches = _cabi.launch_count() - launches0
@@ -273,6 +318,8 @@ def run_ours(args, rank, local_rank, world):
         t_begin.record()
         for i in range(args.steps):
             graph.replay()
+            reduce_scalars()
+        drain_scalars()                      # the timed region ends when the last collective has completed
         t_end.record()
         sync_all()
         l1, l2 = static_losses
@@ -302,6 +349,7 @@ def run_ours(args, rank, local_rank, world):
     ms_per_step = elapsed_ms / args.steps
     value = world * B_PER_GPU * H * W / (ms_per_step * 1e-3) / 1e6
 
+    _note(rank, f'timed region done: {elapsed_ms / args.steps:.4f} ms per step')
     # ---- e2e: pinned host buffers -> H2D -> modules -> D2H of the loss scalars, every step
     e2e = None
     if not args.no_e2e:
@@ -387,6 +435,7 @@ def run_ours(args, rank, local_rank, world):
         if extra:
             line['extra'] = extra
         print(json.dumps(line), flush=True)
+    _note(rank, 'done')
     if world > 1:
         dist.destroy_process_group()
 
