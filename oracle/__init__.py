@@ -15,5 +15,5 @@ where ``/root/reference`` is mounted, against the live reference classes).
 """
 from .kld_oracle import (  # noqa: F401
     kld_loss_torch, kld_closed_form_f64, mse_loss_torch, at_loss_torch,
-    alpha_schedule, OracleKLD, ORACLE_PRESETS, make_preset, corr_loss_torch,
+    alpha_schedule, OracleKLD, ORACLE_PRESETS, make_preset, corr_loss_torch, ifvd_loss_torch,
 )

@@ -4,7 +4,7 @@ Only the hot path lives here: the CUDA kernels + C ABI (``csrc/``, ``include/seg
 the ctypes binding (``_cabi``), the autograd bridges (``functional``) and the host-side mirror of
 the reference's loss-module / dispatcher interface (``losses``, ``opts``, ``dist``).
 """
-from .losses import (ATLoss, CDLoss, CDMSELoss, CGDCorrLoss, CGDLoss, CGDLossWS, FeatureMSELoss,  # noqa: F401
+from .losses import (ATLoss, CDLoss, CDMSELoss, CGDCorrLoss, CGDLoss, CGDLossWS, FeatureMSELoss, IFVDLoss,  # noqa: F401
                      KLDLoss, PDLoss)
 from .opts import DistillationLoss, Extractor, LOSS_CLASSES, build_criterion  # noqa: F401
 

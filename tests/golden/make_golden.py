@@ -187,8 +187,29 @@ def at_cases(ref):
     return out
 
 
+def ifvd_cases(ref):
+    """IFVDLoss (losses.py:199-238): labels at twice the feature resolution (nearest-resized inside), with
+    ignore pixels (255) and a class that never occurs."""
+    out = {}
+    g = torch.Generator().manual_seed(88)
+    s = torch.randn(2, 5, 6, 8, generator=g).requires_grad_(True)
+    t = torch.randn(2, 5, 6, 8, generator=g)
+    target = torch.randint(0, 4, (2, 1, 12, 16), generator=g)
+    target[0, 0, :3, :5] = 255
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        loss = ref.IFVDLoss()(s, t, target, 0)
+    loss.backward()
+    out.update(S=s.detach().numpy(), T=t.numpy(), target=target.numpy(), loss=np.array(loss.item(), dtype=np.float64),
+               grad=s.grad.numpy())
+    return out
+
+
 def main():
     ref = load_reference_losses()
+    if sys.argv[1:] == ['ifvd']:               # add this fixture without rewriting the others
+        np.savez_compressed(os.path.join(HERE, 'ifvd_2x5x6x8.npz'), **ifvd_cases(ref))
+        return
     for i, case in enumerate(CASES):
         rec = run_case(ref, case, seed=100 + i)
         np.savez_compressed(os.path.join(HERE, f'kld_{case[0]}.npz'), **rec)
@@ -196,6 +217,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'schedules.npz'), **schedule_table(ref))
     np.savez_compressed(os.path.join(HERE, 'smoke_cfg1.npz'), **smoke_values(ref))
     np.savez_compressed(os.path.join(HERE, 'atloss_2x6x5x8.npz'), **at_cases(ref))
+    np.savez_compressed(os.path.join(HERE, 'ifvd_2x5x6x8.npz'), **ifvd_cases(ref))
     print('torch', torch.__version__, 'reference', REF)
 
 

@@ -665,3 +665,24 @@ def test_fused_resize_training_shape_cgd_and_cd():
     sd.CDLoss()(x, t.to(dev()), gt, 1).backward()
     rows = x.grad.double().sum(dim=(2, 3)).abs().max().item()
     assert rows <= 1e-6 * x.grad.double().abs().sum(dim=(2, 3)).max().item()
+
+
+# ------------------------------------------------------------------ IFVDLoss (reference losses.py:199-238)
+def test_ifvd_golden_and_seeded():
+    z = load_golden('ifvd_2x5x6x8')
+    x = torch.from_numpy(z['S']).to(dev()).requires_grad_(True)
+    loss = sd.IFVDLoss()(x, torch.from_numpy(z['T']).to(dev()), torch.from_numpy(z['target']).to(dev()), 0)
+    loss.backward()
+    _assert_close(loss.item(), x.grad.cpu(), float(z['loss']), z['grad'])
+    # logits-like case: 19 classes, labels at twice the resolution with ignore pixels
+    s, t = seeded_pair((2, 19, 32, 32), seed=61, scale=2.0)
+    g = torch.Generator().manual_seed(62)
+    target = torch.randint(0, 19, (2, 1, 64, 64), generator=g)
+    target[:, :, :9, 20:40] = 255
+    xr = s.clone().requires_grad_(True)
+    ref = oracle.ifvd_loss_torch(xr, t, target)
+    ref.backward()
+    x = s.to(dev()).requires_grad_(True)
+    loss = sd.IFVDLoss()(x, t.to(dev()), target.to(dev()), 0)
+    loss.backward()
+    _assert_close(loss.item(), x.grad.cpu(), ref.item(), xr.grad)

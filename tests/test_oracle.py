@@ -139,3 +139,12 @@ def test_mse_and_corr_oracles_differentiable():
     t = torch.randn(2, 7, 4, 4, generator=g, dtype=torch.float64)
     assert torch.autograd.gradcheck(lambda x: oracle.mse_loss_torch(x, t, 0.7), (s,))
     assert torch.autograd.gradcheck(lambda x: oracle.corr_loss_torch(x, t, 3, 1.5), (s,))
+
+
+def test_ifvd_matches_reference():
+    z = load_golden('ifvd_2x5x6x8')
+    s = torch.from_numpy(z['S']).requires_grad_(True)
+    loss = oracle.ifvd_loss_torch(s, torch.from_numpy(z['T']), torch.from_numpy(z['target']))
+    loss.backward()
+    assert rel_err(loss.item(), z['loss']) <= 1e-6
+    np.testing.assert_allclose(s.grad.numpy(), z['grad'], rtol=1e-5, atol=1e-9)
