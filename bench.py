@@ -520,6 +520,7 @@ def extra_configs(dev):
     # the reference's real training path: logits at 1/4 resolution resized to the 512x512 labels;
     # fused = bilinear up-sampling inside the loss kernels, host = F.interpolate first (what the reference does)
     for name, cls, shape in (('f1_cgd_resize4_2x150x128x128_f32', sd.CGDLoss, (2, 150, 128, 128)),
+                             ('f1_pd_resize4_2x150x128x128_f32', sd.PDLoss, (2, 150, 128, 128)),
                              ('f1_cd_resize4_16x150x128x128_f32', sd.CDLoss, (16, 150, 128, 128))):
         s, t = pair(shape, torch.float32)
         gt = torch.zeros(shape[0], 1, 4 * shape[2], 4 * shape[3], dtype=torch.long, device=dev)

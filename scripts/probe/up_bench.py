@@ -20,7 +20,7 @@ for shape, hw in (((2, 150, 128, 128), (512, 512)), ((2, 150, 64, 64), (512, 512
     s = torch.randn(shape, device=dev, generator=g).requires_grad_(True)
     t = torch.randn(shape, device=dev, generator=g)
     gt = torch.zeros(shape[0], 1, *hw, dtype=torch.long, device=dev)
-    for cls in (sd.CGDLoss, sd.CDLoss):
+    for cls in (sd.CGDLoss, sd.CDLoss, sd.PDLoss):
         res = {}
         for fuse in (True, False):
             crit = cls(); crit.fuse_resize = fuse

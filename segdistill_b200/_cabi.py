@@ -28,7 +28,7 @@ EXPORTS = (
     'sd_abi_version', 'sd_strerror', 'sd_device_check',
     'sd_kl_rows_workspace_bytes', 'sd_kl_rows_fwd_bwd', 'sd_kl_rows_multi_fwd_bwd', 'sd_scale_grad2',
     'sd_kl_pixels_workspace_bytes', 'sd_kl_pixels_fwd_bwd',
-    'sd_kl_rows_up_workspace_bytes', 'sd_kl_rows_up_fwd_bwd',
+    'sd_kl_rows_up_workspace_bytes', 'sd_kl_rows_up_fwd_bwd', 'sd_kl_pixels_up_workspace_bytes', 'sd_kl_pixels_up_fwd_bwd',
     'sd_mse_workspace_bytes', 'sd_mse_fwd_bwd', 'sd_scale_grad',
     'sd_cgd_corr_workspace_bytes', 'sd_cgd_corr_fwd_bwd',
     'sd_launch_count', 'sd_last_kernel',
@@ -85,6 +85,10 @@ def load():
         lib.sd_kl_rows_up_fwd_bwd.restype = i32
         lib.sd_kl_rows_up_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32,
                                               f32, f32, f32, vp, sz, vp]
+        lib.sd_kl_pixels_up_workspace_bytes.restype = sz
+        lib.sd_kl_pixels_up_workspace_bytes.argtypes = [i32, i32, i32, i32]
+        lib.sd_kl_pixels_up_fwd_bwd.restype = i32
+        lib.sd_kl_pixels_up_fwd_bwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, f32, vp, sz, vp]
         lib.sd_mse_workspace_bytes.restype = sz
         lib.sd_mse_workspace_bytes.argtypes = [i64]
         lib.sd_mse_fwd_bwd.restype = i32
@@ -360,6 +364,29 @@ def kl_rows_up(x_student, x_teacher, scale, group=1, tau=1.0, alpha=1.0, perm: O
                                        _stream_ptr(dev))
         _check(rc)
     return out[0], ds, row_kl
+
+
+UP_PIXEL_SCALES = (2, 4)
+
+
+def kl_pixels_up(x_student, x_teacher, scale, tau=1.0, alpha=1.0, grad_scale=1.0):
+    """Per-pixel softmax-KL over channels on the maps up-sampled ``scale`` x (bilinear, align_corners=False)
+    without materialising them.  Returns (loss, dS at low resolution)."""
+    lib = load()
+    s, t, code = _prep_pair(x_student, x_teacher)
+    if s.dim() != 4:
+        raise ValueError('kl_pixels_up expects 4-D NCHW maps')
+    B, C, Hl, Wl = s.shape
+    dev = s.device
+    with _on(dev):
+        ds = torch.empty_like(s)
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        ws = _workspace(dev, lib.sd_kl_pixels_up_workspace_bytes(B, C, Hl, Wl))
+        rc = lib.sd_kl_pixels_up_fwd_bwd(s.data_ptr(), t.data_ptr(), ds.data_ptr(), out.data_ptr(), B, C, Hl, Wl,
+                                         int(scale), code, float(tau), float(alpha), float(grad_scale),
+                                         ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        _check(rc)
+    return out[0], ds
 
 
 def mse(x_student, x_teacher, weight=1.0, grad_scale=1.0):

@@ -560,6 +560,44 @@ int sd_kl_rows_up_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl,
     return e == cudaSuccess ? SD_OK : (int)e;
 }
 
+size_t sd_kl_pixels_up_workspace_bytes(int B, int C, int Hl, int Wl) {
+    (void)B; (void)C; (void)Hl; (void)Wl;
+    return sd::kArenaBytes + sizeof(float) * sd::kMaxGrid;
+}
+
+int sd_kl_pixels_up_fwd_bwd(const void* S, const void* T, void* dS, float* loss, int B, int C, int Hl, int Wl, int scale,
+                            int dtype, float tau, float alpha, float grad_scale, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+    if (!S || !T || !dS || !loss || !workspace) return SD_ERR_NULL;
+    if (dtype != SD_F32 && dtype != SD_BF16) return SD_ERR_DTYPE;
+    if (B <= 0 || C <= 0 || Hl <= 0 || Wl <= 0) return SD_ERR_SHAPE;
+    if (!(tau > 0.f)) return SD_ERR_VALUE;
+    if (scale != 2 && scale != 4) return SD_ERR_UNSUPPORTED;
+    if ((long long)B * C * Hl * Wl >= (1ll << 40)) return SD_ERR_SHAPE;
+    if (workspace_bytes < sd_kl_pixels_up_workspace_bytes(B, C, Hl, Wl)) return SD_ERR_WORKSPACE;
+    DeviceInfo& dev = device_info();
+    if (dev.cc_major != 10) return SD_ERR_DEVICE;
+    sd::UpParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.S = S; p.T = T; p.dS = dS;
+    p.B = B; p.C = C; p.Hl = Hl; p.Wl = Wl; p.scale = scale;
+    const double R = (double)B * Hl * Wl * scale * scale;        // rows = up-sampled pixels
+    p.c2 = (float)(1.4426950408889634 / (double)tau);
+    p.inv_c2 = (float)((double)tau / 1.4426950408889634);
+    p.inv_Wl = 1.0f / (float)Wl;
+    p.inv_tau = (float)(1.0 / (double)tau);
+    p.coef = (float)((double)grad_scale * (double)alpha / (R * (double)tau));
+    p.loss_scale = (float)((double)alpha / R);
+    p.loss = loss;
+    char* ws = static_cast<char*>(workspace);
+    p.ctrl = reinterpret_cast<unsigned*>(ws);
+    p.part = reinterpret_cast<float*>(ws + sd::kArenaBytes);
+    cudaError_t e = sd::launch_kl_pixels_up(p, dtype == SD_BF16, dev.sms, static_cast<cudaStream_t>(stream));
+    g_launches += 1;
+    t_last_kernel = "kl_pixels_up_kernel";
+    return e == cudaSuccess ? SD_OK : (int)e;
+}
+
 // ============================================================================ MSE
 size_t sd_mse_workspace_bytes(int64_t numel) {
     (void)numel;

@@ -159,6 +159,19 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return r;
 }
 
+template <int NT>
+__device__ __forceinline__ float block_sum_n(float v, float* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float r = red[0];
+#pragma unroll
+    for (int w = 1; w < NT / 32; ++w) r += red[w];
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------ kernel 1
 template <typename T, int S>
 __global__ void __launch_bounds__(kUpThreads) kl_rows_up_stats_kernel(const UpParams p) {
@@ -391,6 +404,285 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_grad_kernel(const UpPar
             *p.loss = (float)((double)p.loss_scale * t);
             atomicExch(&p.ctrl[0], 0u);
         }
+    }
+}
+
+// ====================================================================================================
+// Pixel mode (PDLoss behind the resize, losses.py:25-33 + :47-49 + :108-112): softmax over the C channels of every
+// UP-SAMPLED pixel.  One thread per low-resolution cell keeps the statistics of the s x s pixels of its block in
+// registers while it walks the channels twice - once for the sums (running per-cell reference, sums rescaled when
+// it moves), once for the gradient - and the transposed stencil runs per channel through nine shared-memory planes
+// (double buffered: one CTA barrier per channel).  A CTA computes a 16 x 16 tile of cells and owns the 14 x 14
+// inside (gradients never cross CTAs).  Channels stream through shared memory in chunks of 4.
+constexpr int kPxTile = 16;                    // computed cells per tile side = threads per side
+constexpr int kPxOwn = kPxTile - 2;            // owned (output) cells per tile side
+constexpr int kPxLoad = kPxTile + 2;           // loaded cells per tile side (3 x 3 neighbourhoods)
+constexpr int kPxCh = 4;                       // channels per shared-memory stage (static shared memory stays under 48 KB)
+constexpr int kPxThreads = kPxTile * kPxTile;
+constexpr int kPxPlane = kPxTile * (kPxTile + 2);   // a contribution plane of the tile, padded columns
+
+struct PxSmem {
+    float st[2][2][kPxCh][kPxLoad * kPxLoad];  // [stage][S|T][channel][cell]
+    float planes[2][9][kPxPlane];
+    float red[kPxThreads / 32];
+};
+
+template <typename T, int S>
+__global__ void __launch_bounds__(kPxThreads) kl_pixels_up_kernel(const UpParams p) {
+    __shared__ PxSmem sm;
+    const int tid = threadIdx.x;
+    const int ty = tid / kPxTile, tx = tid % kPxTile;
+    const int tiles_x = (p.Wl + kPxOwn - 1) / kPxOwn, tiles_y = (p.Hl + kPxOwn - 1) / kPxOwn;
+    const long long n_tiles = (long long)p.B * tiles_y * tiles_x;
+    const size_t plane_elems = (size_t)p.Hl * p.Wl;
+    float kl_acc = 0.f;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int b = (int)(tile / (tiles_y * tiles_x));
+        const int trem = (int)(tile - (long long)b * tiles_y * tiles_x);
+        const int i0 = (trem / tiles_x) * kPxOwn - 1, j0 = (trem % tiles_x) * kPxOwn - 1;   // first computed cell
+        const int i = i0 + ty, j = j0 + tx;                                                 // my cell
+        const bool in_map = i >= 0 && i < p.Hl && j >= 0 && j < p.Wl;
+        const bool owned = in_map && ty >= 1 && ty <= kPxOwn && tx >= 1 && tx <= kPxOwn;
+        const T* gS = static_cast<const T*>(p.S) + (size_t)b * p.C * plane_elems;
+        const T* gT = static_cast<const T*>(p.T) + (size_t)b * p.C * plane_elems;
+        // chunk of channels [c0, c0 + kPxCh) -> stage: loaded cell (ly, lx) = map cell clamp(i0 - 1 + ly, j0 - 1 + lx)
+        auto load_chunk = [&](int c0, int stage) {
+            const int nch = min(kPxCh, p.C - c0);
+            for (int e = tid; e < nch * kPxLoad * kPxLoad; e += kPxThreads) {
+                const int ch = e / (kPxLoad * kPxLoad), cell = e - ch * (kPxLoad * kPxLoad);
+                const int ly = cell / kPxLoad, lx = cell - ly * kPxLoad;
+                const int yi = min(max(i0 - 1 + ly, 0), p.Hl - 1), xj = min(max(j0 - 1 + lx, 0), p.Wl - 1);
+                const size_t off = (size_t)(c0 + ch) * plane_elems + (size_t)yi * p.Wl + xj;
+                sm.st[stage][0][ch][cell] = up_load<T>(gS + off);
+                sm.st[stage][1][ch][cell] = up_load<T>(gT + off);
+            }
+        };
+        // neighbourhood of my cell in the stage (clamping happened at load time; the border cells of the MAP must
+        // see their own row/column instead of the clamped neighbour only when the neighbour is outside the map -
+        // which the clamped load already delivers)
+        auto nbhd = [&](const float* cellp, float (&a)[3][3]) {
+            const float* q = cellp + ty * kPxLoad + tx;          // loaded cell (ty, tx) = my cell (-1, -1)
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int e = 0; e < 3; ++e) a[d][e] = q[d * kPxLoad + e];
+        };
+        const int n_chunks = (p.C + kPxCh - 1) / kPxCh;
+
+        // ---------------- pass 1: per-pixel sums over the channels (reference = running maximum of the cell)
+        float zs[S * S], zt[S * S], ak[S * S];
+#pragma unroll
+        for (int q = 0; q < S * S; ++q) zs[q] = zt[q] = ak[q] = 0.f;
+        float ref_s = kUpFloor, ref_t = kUpFloor;
+        __syncthreads();
+        load_chunk(0, 0);
+        for (int ck = 0; ck < n_chunks; ++ck) {
+            __syncthreads();
+            if (ck + 1 < n_chunks) load_chunk((ck + 1) * kPxCh, (ck + 1) & 1);
+            const int nch = min(kPxCh, p.C - ck * kPxCh);
+            if (in_map) {
+                for (int ch = 0; ch < nch; ++ch) {
+                    float a[3][3], hs[3][S], ht[3][S], ds_[2][S], dt_[2][S];
+                    nbhd(sm.st[ck & 1][0][ch], a);
+                    float ms = a[0][0];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+#pragma unroll
+                        for (int e = 0; e < 3; ++e) ms = fmaxf(ms, a[d][e]);
+                    up_hrows<S>(a, hs);
+                    nbhd(sm.st[ck & 1][1][ch], a);
+                    float mt = a[0][0];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+#pragma unroll
+                        for (int e = 0; e < 3; ++e) mt = fmaxf(mt, a[d][e]);
+                    up_hrows<S>(a, ht);
+                    if (ms > ref_s) {
+                        const float f = fast_exp2((ref_s - ms) * p.c2);
+#pragma unroll
+                        for (int q = 0; q < S * S; ++q) zs[q] *= f;
+                        ref_s = ms;
+                    }
+                    if (mt > ref_t) {
+                        const float f = fast_exp2((ref_t - mt) * p.c2);
+#pragma unroll
+                        for (int q = 0; q < S * S; ++q) {
+                            zt[q] *= f;
+                            ak[q] *= f;
+                        }
+                        ref_t = mt;
+                    }
+                    up_vdiff<S>(hs, ds_);
+                    up_vdiff<S>(ht, dt_);
+                    const float rs2 = ref_s * p.c2, rt2 = ref_t * p.c2;
+#pragma unroll
+                    for (int ky = 0; ky < S; ++ky) {
+#pragma unroll
+                        for (int kx = 0; kx < S; ++kx) {
+                            const float vs = up_value<S>(hs, ds_, ky, kx), vt = up_value<S>(ht, dt_, ky, kx);
+                            const float es = fast_exp2(fmaf(vs, p.c2, -rs2)), et = fast_exp2(fmaf(vt, p.c2, -rt2));
+                            zs[ky * S + kx] += es;
+                            zt[ky * S + kx] += et;
+                            ak[ky * S + kx] = fmaf(et, vt - vs, ak[ky * S + kx]);
+                        }
+                    }
+                }
+            }
+        }
+        // KL of my pixels (owned cells only), then the sums become the gradient factors coef / Z
+        if (owned) {
+#pragma unroll
+            for (int q = 0; q < S * S; ++q)
+                kl_acc += p.inv_tau * ak[q] / zt[q] - ((ref_t - ref_s) * p.inv_tau + (logf(zt[q]) - logf(zs[q])));
+        }
+        if (in_map) {
+#pragma unroll
+            for (int q = 0; q < S * S; ++q) {
+                zs[q] = __fdividef(p.coef, zs[q]);
+                zt[q] = __fdividef(p.coef, zt[q]);
+            }
+        }
+        const float rs2 = ref_s * p.c2, rt2 = ref_t * p.c2;
+
+        // ---------------- pass 2: per channel, block gradient -> nine contributions -> owned cells
+        T* gD = static_cast<T*>(p.dS) + (size_t)b * p.C * plane_elems;
+        __syncthreads();
+        load_chunk(0, 0);
+        int cglob = 0;
+        for (int ck = 0; ck < n_chunks; ++ck) {
+            __syncthreads();
+            if (ck + 1 < n_chunks) load_chunk((ck + 1) * kPxCh, (ck + 1) & 1);
+            const int nch = min(kPxCh, p.C - ck * kPxCh);
+            for (int ch = 0; ch < nch; ++ch, ++cglob) {
+                float* pl = sm.planes[cglob & 1][0];
+                if (in_map) {
+                    float a[3][3], hs[3][S], ht[3][S], ds_[2][S], dt_[2][S];
+                    nbhd(sm.st[ck & 1][0][ch], a);
+                    up_hrows<S>(a, hs);
+                    nbhd(sm.st[ck & 1][1][ch], a);
+                    up_hrows<S>(a, ht);
+                    up_vdiff<S>(hs, ds_);
+                    up_vdiff<S>(ht, dt_);
+                    float m[3][3];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+#pragma unroll
+                        for (int e = 0; e < 3; ++e) m[d][e] = 0.f;
+#pragma unroll
+                    for (int ky = 0; ky < S; ++ky) {
+                        float tr[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int kx = 0; kx < S; ++kx) {
+                            const float es = fast_exp2(fmaf(up_value<S>(hs, ds_, ky, kx), p.c2, -rs2));
+                            const float et = fast_exp2(fmaf(up_value<S>(ht, dt_, ky, kx), p.c2, -rt2));
+                            const float gv = es * zs[ky * S + kx] - et * zt[ky * S + kx];
+                            const int f = UpW<S>::first(kx) + 1;
+                            const float w1 = UpW<S>::w1(kx);
+                            tr[f] = fmaf(1.f - w1, gv, tr[f]);
+                            tr[f + 1] = fmaf(w1, gv, tr[f + 1]);
+                        }
+                        const int f = UpW<S>::first(ky) + 1;
+                        const float w1 = UpW<S>::w1(ky);
+#pragma unroll
+                        for (int e = 0; e < 3; ++e) {
+                            m[f][e] = fmaf(1.f - w1, tr[e], m[f][e]);
+                            m[f + 1][e] = fmaf(w1, tr[e], m[f + 1][e]);
+                        }
+                    }
+                    // taps clamped at the border of the map fall onto the cell itself
+                    if (i == 0) {
+#pragma unroll
+                        for (int e = 0; e < 3; ++e) { m[1][e] += m[0][e]; m[0][e] = 0.f; }
+                    }
+                    if (i == p.Hl - 1) {
+#pragma unroll
+                        for (int e = 0; e < 3; ++e) { m[1][e] += m[2][e]; m[2][e] = 0.f; }
+                    }
+                    if (j == 0) {
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) { m[d][1] += m[d][0]; m[d][0] = 0.f; }
+                    }
+                    if (j == p.Wl - 1) {
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) { m[d][1] += m[d][2]; m[d][2] = 0.f; }
+                    }
+                    // contribution (d, e) goes to tile cell (ty + d - 1, tx + e - 1): plane (d, e), row ty + d - 1,
+                    // padded column tx + e
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const int ry = ty + d - 1;
+                        if (ry >= 0 && ry < kPxTile) {
+#pragma unroll
+                            for (int e = 0; e < 3; ++e) pl[(d * 3 + e) * kPxPlane + ry * (kPxTile + 2) + tx + e] = m[d][e];
+                        }
+                    }
+                }
+                __syncthreads();
+                if (owned) {
+                    // plane (d, e) at my position holds what cell (i - d + 1, j - e + 1) sent here
+                    const float* q = pl + ty * (kPxTile + 2) + tx + 1;
+                    const bool okd[3] = {i + 1 < p.Hl, true, i >= 1};
+                    const bool oke[3] = {j + 1 < p.Wl, true, j >= 1};
+                    float v = 0.f;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+#pragma unroll
+                        for (int e = 0; e < 3; ++e) {
+                            const float x = q[(d * 3 + e) * kPxPlane];
+                            v += (okd[d] && oke[e]) ? x : 0.f;
+                        }
+                    up_store<T>(gD + (size_t)(ck * kPxCh + ch) * plane_elems + (size_t)i * p.Wl + j, v);
+                }
+            }
+        }
+    }
+    // ---- loss: CTA partial, the last CTA sums the partials in a fixed order
+    kl_acc = block_sum_n<kPxThreads>(kl_acc, sm.red);
+    __shared__ unsigned ticket_s;
+    if (tid == 0) {
+        __stcg(&p.part[blockIdx.x], kl_acc);
+        __threadfence();
+        ticket_s = atomicAdd(&p.ctrl[0], 1u);
+    }
+    __syncthreads();
+    if (ticket_s == gridDim.x - 1) {
+        __threadfence();
+        double acc = 0.0;
+        for (int r = tid; r < (int)gridDim.x; r += kPxThreads) acc += (double)__ldcg(&p.part[r]);
+        __shared__ double dred[kPxThreads / 32];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if ((tid & 31) == 0) dred[tid >> 5] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < kPxThreads / 32; ++w) t += dred[w];
+            *p.loss = (float)((double)p.loss_scale * t);
+            atomicExch(&p.ctrl[0], 0u);
+        }
+    }
+}
+
+template <typename T, int S>
+static cudaError_t launch_px_up_t(const UpParams& p, int sms, cudaStream_t stream, int* grid_out) {
+    auto k = kl_pixels_up_kernel<T, S>;
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kPxThreads, 0);
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    const long long tiles = (long long)p.B * ((p.Hl + kPxOwn - 1) / kPxOwn) * ((p.Wl + kPxOwn - 1) / kPxOwn);
+    long long grid = (long long)sms * occ;
+    if (grid > tiles) grid = tiles;
+    if (grid > kMaxGrid) grid = kMaxGrid;
+    if (grid_out) *grid_out = (int)grid;
+    k<<<(unsigned)grid, kPxThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kl_pixels_up(const UpParams& p, bool bf16, int sms, cudaStream_t stream) {
+    switch (p.scale) {
+        case 2: return bf16 ? launch_px_up_t<__nv_bfloat16, 2>(p, sms, stream, nullptr) : launch_px_up_t<float, 2>(p, sms, stream, nullptr);
+        case 4: return bf16 ? launch_px_up_t<__nv_bfloat16, 4>(p, sms, stream, nullptr) : launch_px_up_t<float, 4>(p, sms, stream, nullptr);
+        default: return cudaErrorInvalidValue;
     }
 }
 

@@ -22,6 +22,7 @@ cudaError_t launch_kl_rows_cluster(const RowsParams& p, const ClusterGeom& g, bo
 
 // kl_rows_up.cu
 cudaError_t launch_kl_rows_up(const UpParams& p, bool bf16, int sms, cudaStream_t stream);
+cudaError_t launch_kl_pixels_up(const UpParams& p, bool bf16, int sms, cudaStream_t stream);   // p.part: [kMaxGrid] CTA partials
 
 // kl_pixels.cu   (mapS/mapT point at CUtensorMap objects)
 cudaError_t launch_kl_pixels_tma(const void* mapS, const void* mapT, const PixParams& p, bool bf16, int grid,

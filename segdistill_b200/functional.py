@@ -62,6 +62,22 @@ class _KLRowsUp(torch.autograd.Function):
         return (_finish_backward(ctx, grad_output),) + (None,) * 6
 
 
+class _KLPixelsUp(torch.autograd.Function):
+    """Pixel-mode KL behind the reference's bilinear resize, the resize fused in."""
+
+    @staticmethod
+    def forward(ctx, x_student, x_teacher, scale, tau, alpha):
+        loss, ds = _cabi.kl_pixels_up(x_student, x_teacher, scale, tau=tau, alpha=alpha)
+        ctx.ds = ds if x_student.requires_grad else None
+        ctx.in_dtype, ctx.in_shape = x_student.dtype, x_student.shape
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        return (_finish_backward(ctx, grad_output),) + (None,) * 4
+
+
 PAIR_ALGO = 'auto'      # kernel of the fused two-loss launch: 'auto' | 'cluster' | 'stream' (tests force one)
 
 
@@ -178,6 +194,11 @@ def kl_rows_up_loss(x_student, x_teacher, scale, group=1, tau=1.0, alpha=1.0, pe
     """The same on maps up-sampled ``scale`` x (bilinear, align_corners=False) inside the kernel; the gradient
     arrives at the low-resolution ``x_student``."""
     return _KLRowsUp.apply(x_student, x_teacher, int(scale), int(group), float(tau), float(alpha), perm)
+
+
+def kl_pixels_up_loss(x_student, x_teacher, scale, tau=1.0, alpha=1.0):
+    """Per-pixel KL over channels on maps up-sampled ``scale`` x inside the kernel; gradient at low resolution."""
+    return _KLPixelsUp.apply(x_student, x_teacher, int(scale), float(tau), float(alpha))
 
 
 def kl_rows_mse_loss(x_student, x_teacher, group=1, tau=1.0, alpha=1.0, mse_weight=1.0, perm=None, algo='auto'):

@@ -40,7 +40,7 @@ def _ramp(kind, alpha0, frac):
 
 class KLDLoss(nn.Module):
     algo = 'auto'          # 'auto' | 'tma' | 'generic' (tests force one)
-    fuse_resize = True     # channel mode behind a 2x / 4x / 8x bilinear resize: up-sample inside the kernel
+    fuse_resize = True     # behind a 2x / 4x (/ 8x, channel mode) bilinear resize: up-sample inside the kernel
 
     def __init__(self, alpha=1, tau=1, resize_config=None, shuffle_config=None, transform_config=None,
                  warmup_config=None, earlydecay_config=None):
@@ -108,7 +108,7 @@ class KLDLoss(nn.Module):
         rc, tc = self.resize_config, self.transform_config
         if not (self.fuse_resize and rc and tc and gt is not None and self.algo == 'auto'):
             return 0
-        if tc['loss_type'] != 'channel' or rc.get('mode') != 'bilinear' or rc.get('align_corners'):
+        if tc['loss_type'] not in ('channel', 'pixel') or rc.get('mode') != 'bilinear' or rc.get('align_corners'):
             return 0
         x = x_student
         if x.dim() != 4 or not x.is_cuda or x.shape != x_teacher.shape or x.dtype != x_teacher.dtype:
@@ -116,7 +116,8 @@ class KLDLoss(nn.Module):
         if x.dtype not in (torch.float32, torch.bfloat16):
             return 0
         (h, w), (hg, wg) = x.shape[2:], gt.shape[2:]
-        if hg % h or wg % w or hg // h != wg // w or hg // h not in _cabi.UP_SCALES:
+        scales = _cabi.UP_SCALES if tc['loss_type'] == 'channel' else _cabi.UP_PIXEL_SCALES
+        if hg % h or wg % w or hg // h != wg // w or hg // h not in scales:
             return 0
         return hg // h if _cabi.up_supported(h, w) else 0
 
@@ -134,6 +135,8 @@ class KLDLoss(nn.Module):
         if plan['alpha'] == 0:
             return SF.zero_loss(x_student)
         kind = plan['kind']
+        if plan.get('upscale') and kind == 'pixel':
+            return SF.kl_pixels_up_loss(x_student, x_teacher, plan['upscale'], tau=plan['tau'], alpha=plan['alpha'])
         if plan.get('upscale'):
             return SF.kl_rows_up_loss(x_student, x_teacher, plan['upscale'], group=plan['group'], tau=plan['tau'],
                                       alpha=plan['alpha'], perm=plan['perm'])

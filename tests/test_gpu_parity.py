@@ -637,10 +637,35 @@ def test_fused_bilinear_resize_matches_reference_resize(case, dtype):
     _assert_close(loss2.item(), y.grad.float().cpu(), *ref)
 
 
+PX_UP_CASES = [((2, 19, 16, 16), 2), ((2, 150, 32, 32), 4), ((1, 7, 20, 33), 4), ((3, 5, 1, 1), 2), ((1, 21, 14, 15), 2),
+               ((2, 6, 29, 15), 4)]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('case', range(len(PX_UP_CASES)))
+def test_fused_bilinear_resize_pixel_mode(case, dtype):
+    """PDLoss behind its resize (losses.py:25-33 + :47-49): softmax over channels of every up-sampled pixel."""
+    shape, scale = PX_UP_CASES[case]
+    s, t = seeded_pair(shape, seed=400 + case, scale=2.0, dtype=dtype)
+    gt_hw = (shape[2] * scale, shape[3] * scale)
+    ref = _oracle_run('PDLoss', {}, s, t, gt_hw, 1)
+    x = s.to(dev()).requires_grad_(True)
+    gt = torch.zeros(shape[0], 1, *gt_hw, dtype=torch.long, device=dev())
+    loss = sd.PDLoss()(x, t.to(dev()), gt, 1)
+    assert _cabi.last_kernel() == 'kl_pixels_up_kernel'
+    loss.backward()
+    torch.cuda.synchronize()
+    got = (loss.item(), x.grad.float().cpu())
+    if dtype == torch.bfloat16:
+        _assert_close(*got, *ref, loss_rtol=2e-5, grad_rtol=BF16_GRAD_RTOL)
+    else:
+        _assert_close(*got, *ref)
+
+
 def test_fused_resize_only_where_it_applies():
     """Non-integer or unsupported factors, pixel mode and the plain KLDLoss keep the host-side resize."""
     s, t = seeded_pair((2, 6, 8, 8), seed=5)
-    for crit, gt_hw in ((sd.CDLoss(), (24, 24)), (sd.CDLoss(), (12, 8)), (sd.PDLoss(), (32, 32)), (sd.CDLoss(), (4, 4))):
+    for crit, gt_hw in ((sd.CDLoss(), (24, 24)), (sd.CDLoss(), (12, 8)), (sd.PDLoss(), (64, 64)), (sd.CDLoss(), (4, 4))):
         name = type(crit).__name__
         ref = _oracle_run(name, {}, s, t, gt_hw, 1)
         got = _run(crit, s, t, gt_hw, 1)
@@ -655,7 +680,7 @@ def test_fused_resize_training_shape_cgd_and_cd():
     """The shipped presets: logits 2x150x128x128 (1/4 resolution) resized to 512x512 (samples_per_gpu=2)."""
     shape = (2, 150, 128, 128)
     s, t = seeded_pair(shape, seed=9, scale=3.0)
-    for cls, kw in (('CGDLoss', {}), ('CDLoss', {})):
+    for cls, kw in (('CGDLoss', {}), ('CDLoss', {}), ('PDLoss', {})):
         ref = _oracle_run(cls, kw, s, t, (512, 512), 1)
         got = _run(getattr(sd, cls)(**kw), s, t, (512, 512), 1)
         _assert_close(*got, *ref)
