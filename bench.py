@@ -72,9 +72,11 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, window=None):
+        """window = (t0, t1) in perf_counter seconds: only samples that arrived inside it count (the GPU was under
+        the benchmark's load then)."""
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
@@ -85,7 +87,9 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons, power = [], None, set(), []
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.lines:
+        for stamp, ln in self.lines:
+            if window is not None and not (window[0] <= stamp <= window[1]):
+                continue
             f = [x.strip() for x in ln.split(',')]
             if len(f) < 9:
                 continue
@@ -261,6 +265,12 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # clocks / throttle reasons are sampled from here to the end of the timed region (nvidia-smi needs ~0.2 s to come up:
+    # started right before a 3 ms timed loop it would sample nothing and contend for the driver inside it)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.5)
     _note(rank, 'warm-up')
     for _ in range(args.warmup):
         step()
@@ -293,11 +303,8 @@ def run_ours(args, rank, local_rank, world):
         except Exception as exc:          # capture is an optimisation, never a requirement
             graph, graph_note = None, f'eager launches (graph capture failed: {type(exc).__name__})'
             torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-
     _note(rank, 'timed region')
+    t_load0 = time.perf_counter()
     # ---- timed region: exactly K steps, device time
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -325,7 +332,17 @@ def run_ours(args, rank, local_rank, world):
         l1, l2 = static_losses
         launches = per_step_launches * args.steps
     elapsed_ms = t_begin.elapsed_time(t_end)
-    clocks = sampler.stop() if rank == 0 else None
+    # the timed region lasts a few milliseconds, nvidia-smi samples every 100 ms: keep the SAME load running (untimed)
+    # for ~0.6 s so that the clock / throttle samples are taken under it
+    t_hold = time.perf_counter() + 0.6
+    while time.perf_counter() < t_hold:
+        for _ in range(50):
+            if graph is not None:
+                graph.replay()
+            else:
+                compute()
+        torch.cuda.synchronize()
+    clocks = sampler.stop(window=(t_load0, time.perf_counter())) if rank == 0 else None
     if world > 1:
         tt = torch.tensor([elapsed_ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
