@@ -47,7 +47,9 @@ size_t pix_tma_smem_bytes(int C, int pxt, int nstages) {
            + 128;                                                  // barriers
 }
 
-template <typename T, int CPT, bool AT>
+// EXACT: C > 8 * (CPT - 1), i.e. only the last of a thread's CPT channel slots can be missing - the channel guards
+// of the other slots fold away at compile time (C = 150 with CPT = 19; the guards were a quarter of the instructions)
+template <typename T, int CPT, bool AT, bool EXACT>
 __global__ void __launch_bounds__(kPixThreads, 1)
 kl_pixels_tma_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUtensorMap mapT,
                      const PixParams p) {
@@ -113,7 +115,7 @@ kl_pixels_tma_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_cons
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
             const int c = cg + kPixCG * k;
-            if (c < p.C) {
+            if ((EXACT && k < CPT - 1) || c < p.C) {
                 PixTraits<T>::unpack(ws[c * kPixCols + col], &s[k * PXT]);
                 PixTraits<T>::unpack(wt[c * kPixCols + col], &t[k * PXT]);
             }
@@ -134,7 +136,7 @@ kl_pixels_tma_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_cons
         }
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
-            if (cg + kPixCG * k < p.C) {
+            if ((EXACT && k < CPT - 1) || cg + kPixCG * k < p.C) {
 #pragma unroll
                 for (int q = 0; q < PXT; ++q) {
                     mxs[q] = fmaxf(mxs[q], s[k * PXT + q]);
@@ -181,7 +183,7 @@ kl_pixels_tma_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_cons
         }
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
-            if (cg + kPixCG * k < p.C) {
+            if ((EXACT && k < CPT - 1) || cg + kPixCG * k < p.C) {
 #pragma unroll
                 for (int q = 0; q < PXT; ++q) {
                     const int i = k * PXT + q;
@@ -229,7 +231,7 @@ kl_pixels_tma_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_cons
 #pragma unroll
             for (int k = 0; k < CPT; ++k) {
                 const int c = cg + kPixCG * k;
-                if (c < p.C) {
+                if ((EXACT && k < CPT - 1) || c < p.C) {
                     float o[PXT];
 #pragma unroll
                     for (int q = 0; q < PXT; ++q) o[q] = fmaf(s[k * PXT + q], ks[q], -t[k * PXT + q] * kt[q]) + ga[q];
@@ -381,10 +383,19 @@ __global__ void __launch_bounds__(1024) kl_pixels_generic_finalize(const PixPara
 template <typename T, int CPT, bool AT>
 static cudaError_t launch_pix_tma_t(const CUtensorMap& mS, const CUtensorMap& mT, const PixParams& p, int grid,
                                     size_t smem, cudaStream_t stream) {
-    auto kern = kl_pixels_tma_kernel<T, CPT, AT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, kPixThreads, smem, stream>>>(mS, mT, p);
+    const bool exact = p.C > kPixCG * (CPT - 1);
+    cudaError_t e;
+    if (exact) {
+        auto kern = kl_pixels_tma_kernel<T, CPT, AT, true>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, kPixThreads, smem, stream>>>(mS, mT, p);
+    } else {
+        auto kern = kl_pixels_tma_kernel<T, CPT, AT, false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, kPixThreads, smem, stream>>>(mS, mT, p);
+    }
     return cudaGetLastError();
 }
 
