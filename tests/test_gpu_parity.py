@@ -711,3 +711,38 @@ def test_ifvd_golden_and_seeded():
     loss = sd.IFVDLoss()(x, t.to(dev()), target.to(dev()), 0)
     loss.backward()
     _assert_close(loss.item(), x.grad.cpu(), ref.item(), xr.grad)
+
+
+def test_dispatcher_with_resized_labels_runs_the_fused_resize_per_entry():
+    """Two entries on the same logits with labels at 4x the resolution (the shipped presets' situation): each
+    entry up-samples inside its own kernels (no two-loss launch, no materialised resize), numbers as the reference."""
+    cfg = [{'student_layer': 'decode_head.linear_pred', 'teacher_layer': 'decode_head.linear_pred',
+            'loss_name': 'CGDLoss', 'loss_config': {'group_size': 10, 'alpha': 3, 'tau': 2}},
+           {'student_layer': 'decode_head', 'teacher_layer': 'decode_head', 'loss_name': 'PDLoss', 'loss_config': {}}]
+    d = sd.DistillationLoss(cfg)
+    s, t = seeded_pair((2, 20, 24, 24), seed=45)
+    x = s.to(dev()).requires_grad_(True)
+    tg = t.to(dev())
+    gt = torch.zeros(2, 1, 96, 96, dtype=torch.long, device=dev())
+    before = _cabi.launch_count()
+    out = d({'decode_head.linear_pred': x, 'decode_head': x}, {'decode_head.linear_pred': tg, 'decode_head': tg},
+            gt, 1, None, None)
+    assert _cabi.launch_count() - before == 3          # statistics + gradient kernels of CGD, one kernel of PD
+    sum(out.values()).backward()
+    r1 = _oracle_run('CGDLoss', {}, s, t, (96, 96), 1)
+    r2 = _oracle_run('PDLoss', {}, s, t, (96, 96), 1)
+    vals = [v.item() for v in out.values()]
+    assert rel_err(vals[0], r1[0]) <= LOSS_RTOL and rel_err(vals[1], r2[0]) <= LOSS_RTOL
+    _assert_close(sum(vals), x.grad.cpu(), r1[0] + r2[0], r1[1] + r2[1])
+
+
+def test_fused_resize_without_grad_and_with_upstream_scale():
+    s, t = seeded_pair((2, 10, 16, 16), seed=46)
+    gt = torch.zeros(2, 1, 64, 64, dtype=torch.long, device=dev())
+    with torch.no_grad():
+        l0 = sd.CDLoss()(s.to(dev()), t.to(dev()), gt, 1)
+    ref = _oracle_run('CDLoss', {}, s, t, (64, 64), 1)
+    assert rel_err(l0.item(), ref[0]) <= LOSS_RTOL
+    x = s.to(dev()).requires_grad_(True)
+    (512.0 * sd.CDLoss()(x, t.to(dev()), gt, 1)).backward()       # fp16-style loss scaling upstream
+    assert (x.grad.cpu() - 512.0 * ref[1]).abs().max().item() <= GRAD_RTOL * 512.0 * ref[1].abs().max().item()
