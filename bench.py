@@ -413,13 +413,14 @@ def run_ours(args, rank, local_rank, world):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample_b = 4
-        times, _ = cpu_oracle_step_time(sample_b, steps=2, warmup=1, threads=cores)
+        sample_b = 8
+        times, _ = cpu_oracle_step_time(sample_b, steps=8, warmup=2, threads=cores)
         best = min(times)
         cpu = {'value': sample_b * H * W / best / 1e6, 'unit': UNIT, 'cores': torch.get_num_threads(),
                'kind': 'port',
                'sample': f'CGD+CD fwd+bwd on {sample_b} of the {B_PER_GPU} samples ({sample_b}x{C}x{H}x{W} fp32), '
-                         f'best of 2 after 1 warm-up, oracle port of losses.py on torch CPU'}
+                         f'best of 8 after 2 warm-ups ({sum(times):.1f} s of CPU work), oracle port of losses.py on '
+                         f'torch CPU, every host thread'}
 
     if rank == 0:
         peak, peak_src = measured_peak()
