@@ -174,9 +174,9 @@ SD_API int sd_kl_rows_up_fwd_bwd(const void* S, const void* T, void* dS, float* 
 /*
  * The pixel-mode loss of sd_kl_pixels_fwd_bwd (PDLoss, losses.py:115-128) behind the same resize: softmax over
  * the C channels of every UP-SAMPLED pixel, rows R = B*(scale*Hl)*(scale*Wl); S, T, dS at low resolution.
- * scale in {2, 4}; anything else: SD_ERR_UNSUPPORTED.
+ * scale in {2, 4, 8}; anything else: SD_ERR_UNSUPPORTED.
  */
-SD_API size_t sd_kl_pixels_up_workspace_bytes(int B, int C, int Hl, int Wl);
+SD_API size_t sd_kl_pixels_up_workspace_bytes(int B, int C, int Hl, int Wl, int scale);
 SD_API int sd_kl_pixels_up_fwd_bwd(const void* S, const void* T, void* dS, float* loss,
                             int B, int C, int Hl, int Wl, int scale, int dtype,
                             float tau, float alpha, float grad_scale,

@@ -86,7 +86,7 @@ def load():
         lib.sd_kl_rows_up_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32,
                                               f32, f32, f32, vp, sz, vp]
         lib.sd_kl_pixels_up_workspace_bytes.restype = sz
-        lib.sd_kl_pixels_up_workspace_bytes.argtypes = [i32, i32, i32, i32]
+        lib.sd_kl_pixels_up_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
         lib.sd_kl_pixels_up_fwd_bwd.restype = i32
         lib.sd_kl_pixels_up_fwd_bwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, f32, vp, sz, vp]
         lib.sd_mse_workspace_bytes.restype = sz
@@ -366,7 +366,7 @@ def kl_rows_up(x_student, x_teacher, scale, group=1, tau=1.0, alpha=1.0, perm: O
     return out[0], ds, row_kl
 
 
-UP_PIXEL_SCALES = (2, 4)
+UP_PIXEL_SCALES = (2, 4, 8)
 
 
 def kl_pixels_up(x_student, x_teacher, scale, tau=1.0, alpha=1.0, grad_scale=1.0):
@@ -381,7 +381,7 @@ def kl_pixels_up(x_student, x_teacher, scale, tau=1.0, alpha=1.0, grad_scale=1.0
     with _on(dev):
         ds = torch.empty_like(s)
         out = torch.empty(1, dtype=torch.float32, device=dev)
-        ws = _workspace(dev, lib.sd_kl_pixels_up_workspace_bytes(B, C, Hl, Wl))
+        ws = _workspace(dev, lib.sd_kl_pixels_up_workspace_bytes(B, C, Hl, Wl, int(scale)))
         rc = lib.sd_kl_pixels_up_fwd_bwd(s.data_ptr(), t.data_ptr(), ds.data_ptr(), out.data_ptr(), B, C, Hl, Wl,
                                          int(scale), code, float(tau), float(alpha), float(grad_scale),
                                          ws.data_ptr(), ws.numel(), _stream_ptr(dev))

@@ -560,9 +560,11 @@ int sd_kl_rows_up_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl,
     return e == cudaSuccess ? SD_OK : (int)e;
 }
 
-size_t sd_kl_pixels_up_workspace_bytes(int B, int C, int Hl, int Wl) {
-    (void)B; (void)C; (void)Hl; (void)Wl;
-    return sd::kArenaBytes + sizeof(float) * sd::kMaxGrid;
+size_t sd_kl_pixels_up_workspace_bytes(int B, int C, int Hl, int Wl, int scale) {
+    size_t n = sd::kArenaBytes + sizeof(float) * sd::kMaxGrid;
+    if (scale == 8 && B > 0 && C > 0 && Hl > 0 && Wl > 0)       // the four window planes of the gradient, fp32
+        n += sizeof(float) * 4 * (size_t)B * C * Hl * Wl;
+    return (n + 255) & ~(size_t)255;
 }
 
 int sd_kl_pixels_up_fwd_bwd(const void* S, const void* T, void* dS, float* loss, int B, int C, int Hl, int Wl, int scale,
@@ -572,9 +574,9 @@ int sd_kl_pixels_up_fwd_bwd(const void* S, const void* T, void* dS, float* loss,
     if (dtype != SD_F32 && dtype != SD_BF16) return SD_ERR_DTYPE;
     if (B <= 0 || C <= 0 || Hl <= 0 || Wl <= 0) return SD_ERR_SHAPE;
     if (!(tau > 0.f)) return SD_ERR_VALUE;
-    if (scale != 2 && scale != 4) return SD_ERR_UNSUPPORTED;
+    if (scale != 2 && scale != 4 && scale != 8) return SD_ERR_UNSUPPORTED;
     if ((long long)B * C * Hl * Wl >= (1ll << 40)) return SD_ERR_SHAPE;
-    if (workspace_bytes < sd_kl_pixels_up_workspace_bytes(B, C, Hl, Wl)) return SD_ERR_WORKSPACE;
+    if (workspace_bytes < sd_kl_pixels_up_workspace_bytes(B, C, Hl, Wl, scale)) return SD_ERR_WORKSPACE;
     DeviceInfo& dev = device_info();
     if (dev.cc_major != 10) return SD_ERR_DEVICE;
     sd::UpParams p;
@@ -592,8 +594,9 @@ int sd_kl_pixels_up_fwd_bwd(const void* S, const void* T, void* dS, float* loss,
     char* ws = static_cast<char*>(workspace);
     p.ctrl = reinterpret_cast<unsigned*>(ws);
     p.part = reinterpret_cast<float*>(ws + sd::kArenaBytes);
+    p.wpart = reinterpret_cast<float*>(ws + sd::kArenaBytes + sizeof(float) * sd::kMaxGrid);
     cudaError_t e = sd::launch_kl_pixels_up(p, dtype == SD_BF16, dev.sms, static_cast<cudaStream_t>(stream));
-    g_launches += 1;
+    g_launches += scale == 8 ? 2 : 1;
     t_last_kernel = "kl_pixels_up_kernel";
     return e == cudaSuccess ? SD_OK : (int)e;
 }

@@ -136,6 +136,26 @@ __device__ __forceinline__ float up_value(const float (&h)[3][S], const float (&
     return fmaf(UpW<S>::w1(ky), dv[f][kx], h[f][kx]);
 }
 
+// the same for a window of SB x SB values of the block (columns kx0 .., rows ky0 ..): pixel mode at s = 8 walks the
+// block in four 4 x 4 windows so that the per-pixel statistics fit the registers
+template <int S, int SB>
+__device__ __forceinline__ void up_hrows_win(const float (&a)[3][3], int kx0, float (&h)[3][SB]) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float dx[2] = {a[d][1] - a[d][0], a[d][2] - a[d][1]};
+#pragma unroll
+        for (int kx = 0; kx < SB; ++kx) {
+            const int f = UpW<S>::first(kx0 + kx) + 1;
+            h[d][kx] = fmaf(UpW<S>::w1(kx0 + kx), dx[f], a[d][f]);
+        }
+    }
+}
+template <int S, int SB>
+__device__ __forceinline__ float up_value_win(const float (&h)[3][SB], const float (&dv)[2][SB], int ky, int kx) {
+    const int f = UpW<S>::first(ky) + 1;     // ky: row within the whole block
+    return fmaf(UpW<S>::w1(ky), dv[f][kx], h[f][kx]);
+}
+
 __device__ __forceinline__ float block_max(float v, float* red) {
     v = warp_max(v);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -429,6 +449,8 @@ struct PxSmem {
 
 template <typename T, int S>
 __global__ void __launch_bounds__(kPxThreads) kl_pixels_up_kernel(const UpParams p) {
+    constexpr int SB = S > 4 ? 4 : S;              // window side
+    constexpr int NWIN = (S / SB) * (S / SB);
     __shared__ PxSmem sm;
     const int tid = threadIdx.x;
     const int ty = tid / kPxTile, tx = tid % kPxTile;
@@ -436,7 +458,11 @@ __global__ void __launch_bounds__(kPxThreads) kl_pixels_up_kernel(const UpParams
     const long long n_tiles = (long long)p.B * tiles_y * tiles_x;
     const size_t plane_elems = (size_t)p.Hl * p.Wl;
     float kl_acc = 0.f;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // with several windows per block (s = 8) a unit is (tile, window): four times the parallelism, and the windows'
+    // gradients go to separate fp32 planes of the workspace that up_sum_windows_kernel adds in a fixed order
+    for (long long unit = blockIdx.x; unit < n_tiles * NWIN; unit += gridDim.x) {
+        const long long tile = unit / NWIN;
+        const int my_win = (int)(unit - tile * NWIN);
         const int b = (int)(tile / (tiles_y * tiles_x));
         const int trem = (int)(tile - (long long)b * tiles_y * tiles_x);
         const int i0 = (trem / tiles_x) * kPxOwn - 1, j0 = (trem % tiles_x) * kPxOwn - 1;   // first computed cell
@@ -469,169 +495,179 @@ __global__ void __launch_bounds__(kPxThreads) kl_pixels_up_kernel(const UpParams
         };
         const int n_chunks = (p.C + kPxCh - 1) / kPxCh;
 
-        // ---------------- pass 1: per-pixel sums over the channels (reference = running maximum of the cell)
-        float zs[S * S], zt[S * S], ak[S * S];
-#pragma unroll
-        for (int q = 0; q < S * S; ++q) zs[q] = zt[q] = ak[q] = 0.f;
-        float ref_s = kUpFloor, ref_t = kUpFloor;
-        __syncthreads();
-        load_chunk(0, 0);
-        for (int ck = 0; ck < n_chunks; ++ck) {
-            __syncthreads();
-            if (ck + 1 < n_chunks) load_chunk((ck + 1) * kPxCh, (ck + 1) & 1);
-            const int nch = min(kPxCh, p.C - ck * kPxCh);
-            if (in_map) {
-                for (int ch = 0; ch < nch; ++ch) {
-                    float a[3][3], hs[3][S], ht[3][S], ds_[2][S], dt_[2][S];
-                    nbhd(sm.st[ck & 1][0][ch], a);
-                    float ms = a[0][0];
-#pragma unroll
-                    for (int d = 0; d < 3; ++d)
-#pragma unroll
-                        for (int e = 0; e < 3; ++e) ms = fmaxf(ms, a[d][e]);
-                    up_hrows<S>(a, hs);
-                    nbhd(sm.st[ck & 1][1][ch], a);
-                    float mt = a[0][0];
-#pragma unroll
-                    for (int d = 0; d < 3; ++d)
-#pragma unroll
-                        for (int e = 0; e < 3; ++e) mt = fmaxf(mt, a[d][e]);
-                    up_hrows<S>(a, ht);
-                    if (ms > ref_s) {
-                        const float f = fast_exp2((ref_s - ms) * p.c2);
-#pragma unroll
-                        for (int q = 0; q < S * S; ++q) zs[q] *= f;
-                        ref_s = ms;
-                    }
-                    if (mt > ref_t) {
-                        const float f = fast_exp2((ref_t - mt) * p.c2);
-#pragma unroll
-                        for (int q = 0; q < S * S; ++q) {
-                            zt[q] *= f;
-                            ak[q] *= f;
-                        }
-                        ref_t = mt;
-                    }
-                    up_vdiff<S>(hs, ds_);
-                    up_vdiff<S>(ht, dt_);
-                    const float rs2 = ref_s * p.c2, rt2 = ref_t * p.c2;
-#pragma unroll
-                    for (int ky = 0; ky < S; ++ky) {
-#pragma unroll
-                        for (int kx = 0; kx < S; ++kx) {
-                            const float vs = up_value<S>(hs, ds_, ky, kx), vt = up_value<S>(ht, dt_, ky, kx);
-                            const float es = fast_exp2(fmaf(vs, p.c2, -rs2)), et = fast_exp2(fmaf(vt, p.c2, -rt2));
-                            zs[ky * S + kx] += es;
-                            zt[ky * S + kx] += et;
-                            ak[ky * S + kx] = fmaf(et, vt - vs, ak[ky * S + kx]);
-                        }
-                    }
-                }
-            }
-        }
-        // KL of my pixels (owned cells only), then the sums become the gradient factors coef / Z
-        if (owned) {
-#pragma unroll
-            for (int q = 0; q < S * S; ++q)
-                kl_acc += p.inv_tau * ak[q] / zt[q] - ((ref_t - ref_s) * p.inv_tau + (logf(zt[q]) - logf(zs[q])));
-        }
-        if (in_map) {
-#pragma unroll
-            for (int q = 0; q < S * S; ++q) {
-                zs[q] = __fdividef(p.coef, zs[q]);
-                zt[q] = __fdividef(p.coef, zt[q]);
-            }
-        }
-        const float rs2 = ref_s * p.c2, rt2 = ref_t * p.c2;
-
-        // ---------------- pass 2: per channel, block gradient -> nine contributions -> owned cells
         T* gD = static_cast<T*>(p.dS) + (size_t)b * p.C * plane_elems;
-        __syncthreads();
-        load_chunk(0, 0);
-        int cglob = 0;
-        for (int ck = 0; ck < n_chunks; ++ck) {
+        // the s x s block of a cell is walked in windows of SB x SB pixels (one window for s <= 4, four for s = 8):
+        // per window two sweeps over the channels
+#pragma unroll
+        for (int win = 0; win < NWIN; ++win) {
+            if (NWIN > 1 && win != my_win) continue;          // (uniform over the CTA)
+            const int ky0 = (win / (S / SB)) * SB, kx0 = (win % (S / SB)) * SB;
+            // ---------------- pass 1: per-pixel sums over the channels (reference = running maximum of the cell)
+            float zs[SB * SB], zt[SB * SB], ak[SB * SB];
+#pragma unroll
+            for (int q = 0; q < SB * SB; ++q) zs[q] = zt[q] = ak[q] = 0.f;
+            float ref_s = kUpFloor, ref_t = kUpFloor;
             __syncthreads();
-            if (ck + 1 < n_chunks) load_chunk((ck + 1) * kPxCh, (ck + 1) & 1);
-            const int nch = min(kPxCh, p.C - ck * kPxCh);
-            for (int ch = 0; ch < nch; ++ch, ++cglob) {
-                float* pl = sm.planes[cglob & 1][0];
+            load_chunk(0, 0);
+            for (int ck = 0; ck < n_chunks; ++ck) {
+                __syncthreads();
+                if (ck + 1 < n_chunks) load_chunk((ck + 1) * kPxCh, (ck + 1) & 1);
+                const int nch = min(kPxCh, p.C - ck * kPxCh);
                 if (in_map) {
-                    float a[3][3], hs[3][S], ht[3][S], ds_[2][S], dt_[2][S];
-                    nbhd(sm.st[ck & 1][0][ch], a);
-                    up_hrows<S>(a, hs);
-                    nbhd(sm.st[ck & 1][1][ch], a);
-                    up_hrows<S>(a, ht);
-                    up_vdiff<S>(hs, ds_);
-                    up_vdiff<S>(ht, dt_);
-                    float m[3][3];
+                    for (int ch = 0; ch < nch; ++ch) {
+                        float a[3][3], hs[3][SB], ht[3][SB], ds_[2][SB], dt_[2][SB];
+                        nbhd(sm.st[ck & 1][0][ch], a);
+                        float ms = a[0][0];
 #pragma unroll
-                    for (int d = 0; d < 3; ++d)
+                        for (int d = 0; d < 3; ++d)
 #pragma unroll
-                        for (int e = 0; e < 3; ++e) m[d][e] = 0.f;
+                            for (int e = 0; e < 3; ++e) ms = fmaxf(ms, a[d][e]);
+                        up_hrows_win<S, SB>(a, kx0, hs);
+                        nbhd(sm.st[ck & 1][1][ch], a);
+                        float mt = a[0][0];
 #pragma unroll
-                    for (int ky = 0; ky < S; ++ky) {
-                        float tr[3] = {0.f, 0.f, 0.f};
+                        for (int d = 0; d < 3; ++d)
 #pragma unroll
-                        for (int kx = 0; kx < S; ++kx) {
-                            const float es = fast_exp2(fmaf(up_value<S>(hs, ds_, ky, kx), p.c2, -rs2));
-                            const float et = fast_exp2(fmaf(up_value<S>(ht, dt_, ky, kx), p.c2, -rt2));
-                            const float gv = es * zs[ky * S + kx] - et * zt[ky * S + kx];
-                            const int f = UpW<S>::first(kx) + 1;
-                            const float w1 = UpW<S>::w1(kx);
-                            tr[f] = fmaf(1.f - w1, gv, tr[f]);
-                            tr[f + 1] = fmaf(w1, gv, tr[f + 1]);
+                            for (int e = 0; e < 3; ++e) mt = fmaxf(mt, a[d][e]);
+                        up_hrows_win<S, SB>(a, kx0, ht);
+                        if (ms > ref_s) {
+                            const float f = fast_exp2((ref_s - ms) * p.c2);
+#pragma unroll
+                            for (int q = 0; q < SB * SB; ++q) zs[q] *= f;
+                            ref_s = ms;
                         }
-                        const int f = UpW<S>::first(ky) + 1;
-                        const float w1 = UpW<S>::w1(ky);
+                        if (mt > ref_t) {
+                            const float f = fast_exp2((ref_t - mt) * p.c2);
 #pragma unroll
-                        for (int e = 0; e < 3; ++e) {
-                            m[f][e] = fmaf(1.f - w1, tr[e], m[f][e]);
-                            m[f + 1][e] = fmaf(w1, tr[e], m[f + 1][e]);
+                            for (int q = 0; q < SB * SB; ++q) {
+                                zt[q] *= f;
+                                ak[q] *= f;
+                            }
+                            ref_t = mt;
                         }
-                    }
-                    // taps clamped at the border of the map fall onto the cell itself
-                    if (i == 0) {
+                        up_vdiff<SB>(hs, ds_);
+                        up_vdiff<SB>(ht, dt_);
+                        const float rs2 = ref_s * p.c2, rt2 = ref_t * p.c2;
 #pragma unroll
-                        for (int e = 0; e < 3; ++e) { m[1][e] += m[0][e]; m[0][e] = 0.f; }
-                    }
-                    if (i == p.Hl - 1) {
+                        for (int ky = 0; ky < SB; ++ky) {
 #pragma unroll
-                        for (int e = 0; e < 3; ++e) { m[1][e] += m[2][e]; m[2][e] = 0.f; }
-                    }
-                    if (j == 0) {
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) { m[d][1] += m[d][0]; m[d][0] = 0.f; }
-                    }
-                    if (j == p.Wl - 1) {
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) { m[d][1] += m[d][2]; m[d][2] = 0.f; }
-                    }
-                    // contribution (d, e) goes to tile cell (ty + d - 1, tx + e - 1): plane (d, e), row ty + d - 1,
-                    // padded column tx + e
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        const int ry = ty + d - 1;
-                        if (ry >= 0 && ry < kPxTile) {
-#pragma unroll
-                            for (int e = 0; e < 3; ++e) pl[(d * 3 + e) * kPxPlane + ry * (kPxTile + 2) + tx + e] = m[d][e];
+                            for (int kx = 0; kx < SB; ++kx) {
+                                const float vs = up_value_win<S, SB>(hs, ds_, ky0 + ky, kx);
+                                const float vt = up_value_win<S, SB>(ht, dt_, ky0 + ky, kx);
+                                const float es = fast_exp2(fmaf(vs, p.c2, -rs2)), et = fast_exp2(fmaf(vt, p.c2, -rt2));
+                                zs[ky * SB + kx] += es;
+                                zt[ky * SB + kx] += et;
+                                ak[ky * SB + kx] = fmaf(et, vt - vs, ak[ky * SB + kx]);
+                            }
                         }
                     }
                 }
+            }
+            // KL of my pixels (owned cells only), then the sums become the gradient factors coef / Z
+            if (owned) {
+#pragma unroll
+                for (int q = 0; q < SB * SB; ++q)
+                    kl_acc += p.inv_tau * ak[q] / zt[q] - ((ref_t - ref_s) * p.inv_tau + (logf(zt[q]) - logf(zs[q])));
+            }
+            if (in_map) {
+#pragma unroll
+                for (int q = 0; q < SB * SB; ++q) {
+                    zs[q] = __fdividef(p.coef, zs[q]);
+                    zt[q] = __fdividef(p.coef, zt[q]);
+                }
+            }
+            const float rs2 = ref_s * p.c2, rt2 = ref_t * p.c2;
+
+            // ---------------- pass 2: per channel, window gradient -> nine contributions -> owned cells
+            __syncthreads();
+            load_chunk(0, 0);
+            int cglob = 0;
+            for (int ck = 0; ck < n_chunks; ++ck) {
                 __syncthreads();
-                if (owned) {
-                    // plane (d, e) at my position holds what cell (i - d + 1, j - e + 1) sent here
-                    const float* q = pl + ty * (kPxTile + 2) + tx + 1;
-                    const bool okd[3] = {i + 1 < p.Hl, true, i >= 1};
-                    const bool oke[3] = {j + 1 < p.Wl, true, j >= 1};
-                    float v = 0.f;
+                if (ck + 1 < n_chunks) load_chunk((ck + 1) * kPxCh, (ck + 1) & 1);
+                const int nch = min(kPxCh, p.C - ck * kPxCh);
+                for (int ch = 0; ch < nch; ++ch, ++cglob) {
+                    float* pl = sm.planes[cglob & 1][0];
+                    if (in_map) {
+                        float a[3][3], hs[3][SB], ht[3][SB], ds_[2][SB], dt_[2][SB];
+                        nbhd(sm.st[ck & 1][0][ch], a);
+                        up_hrows_win<S, SB>(a, kx0, hs);
+                        nbhd(sm.st[ck & 1][1][ch], a);
+                        up_hrows_win<S, SB>(a, kx0, ht);
+                        up_vdiff<SB>(hs, ds_);
+                        up_vdiff<SB>(ht, dt_);
+                        float m[3][3];
 #pragma unroll
-                    for (int d = 0; d < 3; ++d)
+                        for (int d = 0; d < 3; ++d)
 #pragma unroll
-                        for (int e = 0; e < 3; ++e) {
-                            const float x = q[(d * 3 + e) * kPxPlane];
-                            v += (okd[d] && oke[e]) ? x : 0.f;
+                            for (int e = 0; e < 3; ++e) m[d][e] = 0.f;
+#pragma unroll
+                        for (int ky = 0; ky < SB; ++ky) {
+                            float tr[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                            for (int kx = 0; kx < SB; ++kx) {
+                                const float es = fast_exp2(fmaf(up_value_win<S, SB>(hs, ds_, ky0 + ky, kx), p.c2, -rs2));
+                                const float et = fast_exp2(fmaf(up_value_win<S, SB>(ht, dt_, ky0 + ky, kx), p.c2, -rt2));
+                                const float gv = es * zs[ky * SB + kx] - et * zt[ky * SB + kx];
+                                const int f = UpW<S>::first(kx0 + kx) + 1;
+                                const float w1 = UpW<S>::w1(kx0 + kx);
+                                tr[f] = fmaf(1.f - w1, gv, tr[f]);
+                                tr[f + 1] = fmaf(w1, gv, tr[f + 1]);
+                            }
+                            const int f = UpW<S>::first(ky0 + ky) + 1;
+                            const float w1 = UpW<S>::w1(ky0 + ky);
+#pragma unroll
+                            for (int e = 0; e < 3; ++e) {
+                                m[f][e] = fmaf(1.f - w1, tr[e], m[f][e]);
+                                m[f + 1][e] = fmaf(w1, tr[e], m[f + 1][e]);
+                            }
                         }
-                    up_store<T>(gD + (size_t)(ck * kPxCh + ch) * plane_elems + (size_t)i * p.Wl + j, v);
+                        // taps clamped at the border of the map fall onto the cell itself
+                        if (i == 0) {
+#pragma unroll
+                            for (int e = 0; e < 3; ++e) { m[1][e] += m[0][e]; m[0][e] = 0.f; }
+                        }
+                        if (i == p.Hl - 1) {
+#pragma unroll
+                            for (int e = 0; e < 3; ++e) { m[1][e] += m[2][e]; m[2][e] = 0.f; }
+                        }
+                        if (j == 0) {
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) { m[d][1] += m[d][0]; m[d][0] = 0.f; }
+                        }
+                        if (j == p.Wl - 1) {
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) { m[d][1] += m[d][2]; m[d][2] = 0.f; }
+                        }
+                        // contribution (d, e) goes to tile cell (ty + d - 1, tx + e - 1): plane (d, e), row ty + d - 1,
+                        // padded column tx + e
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            const int ry = ty + d - 1;
+                            if (ry >= 0 && ry < kPxTile) {
+#pragma unroll
+                                for (int e = 0; e < 3; ++e) pl[(d * 3 + e) * kPxPlane + ry * (kPxTile + 2) + tx + e] = m[d][e];
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    if (owned) {
+                        // plane (d, e) at my position holds what cell (i - d + 1, j - e + 1) sent here
+                        const float* q = pl + ty * (kPxTile + 2) + tx + 1;
+                        const bool okd[3] = {i + 1 < p.Hl, true, i >= 1};
+                        const bool oke[3] = {j + 1 < p.Wl, true, j >= 1};
+                        float v = 0.f;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d)
+#pragma unroll
+                            for (int e = 0; e < 3; ++e) {
+                                const float x = q[(d * 3 + e) * kPxPlane];
+                                v += (okd[d] && oke[e]) ? x : 0.f;
+                            }
+                        const size_t off = (size_t)(ck * kPxCh + ch) * plane_elems + (size_t)i * p.Wl + j;
+                        if (NWIN > 1) p.wpart[((size_t)win * p.B + b) * p.C * plane_elems + off] = v;
+                        else up_store<T>(gD + off, v);
+                    }
                 }
             }
         }
@@ -663,18 +699,37 @@ __global__ void __launch_bounds__(kPxThreads) kl_pixels_up_kernel(const UpParams
     }
 }
 
+// dS = sum of the window planes (s = 8), fixed order
+template <typename T>
+__global__ void __launch_bounds__(256) up_sum_windows_kernel(const float* __restrict__ wpart, T* __restrict__ dS,
+                                                             long long n, int nwin) {
+    const long long stride = (long long)gridDim.x * 256;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+        float v = 0.f;
+        for (int w = 0; w < nwin; ++w) v += wpart[(size_t)w * n + i];
+        up_store<T>(dS + i, v);
+    }
+}
+
 template <typename T, int S>
 static cudaError_t launch_px_up_t(const UpParams& p, int sms, cudaStream_t stream, int* grid_out) {
     auto k = kl_pixels_up_kernel<T, S>;
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kPxThreads, 0);
     if (occ < 1) return cudaErrorLaunchOutOfResources;
-    const long long tiles = (long long)p.B * ((p.Hl + kPxOwn - 1) / kPxOwn) * ((p.Wl + kPxOwn - 1) / kPxOwn);
+    constexpr int nwin = S > 4 ? (S / 4) * (S / 4) : 1;
+    const long long units = (long long)p.B * ((p.Hl + kPxOwn - 1) / kPxOwn) * ((p.Wl + kPxOwn - 1) / kPxOwn) * nwin;
     long long grid = (long long)sms * occ;
-    if (grid > tiles) grid = tiles;
+    if (grid > units) grid = units;
     if (grid > kMaxGrid) grid = kMaxGrid;
     if (grid_out) *grid_out = (int)grid;
     k<<<(unsigned)grid, kPxThreads, 0, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || nwin == 1) return e;
+    const long long n = (long long)p.B * p.C * p.Hl * p.Wl;
+    long long g2 = (n + 255) / 256;
+    if (g2 > (long long)sms * 8) g2 = (long long)sms * 8;
+    up_sum_windows_kernel<T><<<(unsigned)g2, 256, 0, stream>>>(p.wpart, static_cast<T*>(p.dS), n, nwin);
     return cudaGetLastError();
 }
 
@@ -682,6 +737,7 @@ cudaError_t launch_kl_pixels_up(const UpParams& p, bool bf16, int sms, cudaStrea
     switch (p.scale) {
         case 2: return bf16 ? launch_px_up_t<__nv_bfloat16, 2>(p, sms, stream, nullptr) : launch_px_up_t<float, 2>(p, sms, stream, nullptr);
         case 4: return bf16 ? launch_px_up_t<__nv_bfloat16, 4>(p, sms, stream, nullptr) : launch_px_up_t<float, 4>(p, sms, stream, nullptr);
+        case 8: return bf16 ? launch_px_up_t<__nv_bfloat16, 8>(p, sms, stream, nullptr) : launch_px_up_t<float, 8>(p, sms, stream, nullptr);
         default: return cudaErrorInvalidValue;
     }
 }

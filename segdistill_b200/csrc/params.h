@@ -141,6 +141,7 @@ struct UpParams {
     float* loss;
     float* row_kl;           // [R]
     float* part;             // [units][8] partial records of kernel 1
+    float* wpart;            // pixel mode, scale 8: [4][B*C*Hl*Wl] gradients of the four windows of a block
     unsigned* ctrl;
 };
 struct UpWorkspace {

@@ -40,7 +40,7 @@ def _ramp(kind, alpha0, frac):
 
 class KLDLoss(nn.Module):
     algo = 'auto'          # 'auto' | 'tma' | 'generic' (tests force one)
-    fuse_resize = True     # behind a 2x / 4x (/ 8x, channel mode) bilinear resize: up-sample inside the kernel
+    fuse_resize = True     # behind a 2x / 4x / 8x bilinear resize: up-sample inside the kernel
 
     def __init__(self, alpha=1, tau=1, resize_config=None, shuffle_config=None, transform_config=None,
                  warmup_config=None, earlydecay_config=None):

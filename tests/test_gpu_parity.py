@@ -638,7 +638,7 @@ def test_fused_bilinear_resize_matches_reference_resize(case, dtype):
 
 
 PX_UP_CASES = [((2, 19, 16, 16), 2), ((2, 150, 32, 32), 4), ((1, 7, 20, 33), 4), ((3, 5, 1, 1), 2), ((1, 21, 14, 15), 2),
-               ((2, 6, 29, 15), 4)]
+               ((2, 6, 29, 15), 4), ((2, 19, 17, 9), 8), ((1, 150, 16, 16), 8)]
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
