@@ -9,8 +9,8 @@
 // ((k + 1/2)/s -+ 1/2), so a thread regenerates the block in registers from shared memory:
 //
 //   kernel 1 (statistics)  unit = (sample, channel, strip of low-res rows): load the strip (+ one halo row each
-//                          side) of S and T, reference = maximum of the strip (an up-sampled value is a convex
-//                          combination of cells, so never larger), sums of exp2 over the up-sampled block of
+//                          side) of S and T, reference = the exact maximum of the unit's up-sampled values (found
+//                          at the samples next to the cell centres), sums of exp2 over the up-sampled block of
 //                          every cell -> one partial record per unit.
 //   kernel 2 (gradient)    merges the records of its row (g channels x strips) into the row statistics,
 //                          regenerates the block, g = coef (q - p), and applies the TRANSPOSED stencil: a cell's
@@ -205,42 +205,100 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_stats_kernel(const UpPa
         float ms, mt;
         __syncthreads();   // the previous unit's readers are done with the strip
         up_load_strip<T, false>(p, x, 1, sS, sT, r0, nr, ms, mt);
+        // reference of the exponentials: the maximum of the strip - an up-sampled value is a convex combination of
+        // cells, so never larger.  (If it is so much smaller everywhere that the sums underflow - an isolated spike
+        // between cells - the unit is redone below against the exact maximum.)
         ms = block_max(ms, red);
         mt = block_max(mt, red);
-        // second sweep over the (small) strip: raw values -> exponents relative to the strip maxima
-        for (int e = threadIdx.x; e < nr * p.Wl; e += kUpThreads) {
-            sS[e] = (sS[e] - ms) * p.c2;
-            sT[e] = (sT[e] - mt) * p.c2;
-        }
-        __syncthreads();
-        float zs = 0.f, zt = 0.f, acc = 0.f;
-        const int ncell = (x.i1 - x.i0) * p.Wl;
-        for (int c = threadIdx.x; c < ncell; c += kUpThreads) {
-            int i, j;
-            up_cell(c, p.Wl, p.inv_Wl, i, j);
-            i += x.i0;
-            float a[3][3], hs[3][S], ht[3][S], ds_[2][S], dt_[2][S];
-            up_nbhd(sS, p.Wl, p.Hl, r0, i, j, a);
-            up_hrows<S>(a, hs);
-            up_nbhd(sT, p.Wl, p.Hl, r0, i, j, a);
-            up_hrows<S>(a, ht);
-            up_vdiff<S>(hs, ds_);
-            up_vdiff<S>(ht, dt_);
+        float zs, zt, acc;
+        for (int attempt = 0;; ++attempt) {
+            // sweep over the (small) strip: values -> exponents relative to the references (the redo reloads the raw
+            // values: exponents thousands below the old reference have lost their low bits)
+            if (attempt > 0) {
+                float d0, d1;
+                up_load_strip<T, false>(p, x, 1, sS, sT, r0, nr, d0, d1);
+                __syncthreads();
+            }
+            for (int e = threadIdx.x; e < nr * p.Wl; e += kUpThreads) {
+                sS[e] = (sS[e] - ms) * p.c2;
+                sT[e] = (sT[e] - mt) * p.c2;
+            }
+            __syncthreads();
+            zs = 0.f;
+            zt = 0.f;
+            acc = 0.f;
+            const int ncell = (x.i1 - x.i0) * p.Wl;
+            for (int c = threadIdx.x; c < ncell; c += kUpThreads) {
+                int i, j;
+                up_cell(c, p.Wl, p.inv_Wl, i, j);
+                i += x.i0;
+                float a[3][3], hs[3][S], ht[3][S], ds_[2][S], dt_[2][S];
+                up_nbhd(sS, p.Wl, p.Hl, r0, i, j, a);
+                up_hrows<S>(a, hs);
+                up_nbhd(sT, p.Wl, p.Hl, r0, i, j, a);
+                up_hrows<S>(a, ht);
+                up_vdiff<S>(hs, ds_);
+                up_vdiff<S>(ht, dt_);
 #pragma unroll
-            for (int ky = 0; ky < S; ++ky) {
+                for (int ky = 0; ky < S; ++ky) {
 #pragma unroll
-                for (int kx = 0; kx < S; ++kx) {
-                    const float vs = up_value<S>(hs, ds_, ky, kx), vt = up_value<S>(ht, dt_, ky, kx);
-                    const float es = fast_exp2(vs), et = fast_exp2(vt);
-                    zs += es;
-                    zt += et;
-                    acc = fmaf(et, vt - vs, acc);
+                    for (int kx = 0; kx < S; ++kx) {
+                        const float vs = up_value<S>(hs, ds_, ky, kx), vt = up_value<S>(ht, dt_, ky, kx);
+                        const float es = fast_exp2(vs), et = fast_exp2(vt);
+                        zs += es;
+                        zt += et;
+                        acc = fmaf(et, vt - vs, acc);
+                    }
                 }
             }
+            zs = block_sum(zs, red);
+            zt = block_sum(zt, red);
+            acc = block_sum(acc, red);
+            if (attempt > 0 || (zs >= 1e-20f && zt >= 1e-20f)) break;      // (uniform over the CTA)
+            // ---- rare: EXACT maximum of the up-sampled values of my cells.  Between four cell centres the interpolant
+            // is bilinear, and a bilinear patch takes its extremes at the corners of any axis-aligned rectangle of
+            // samples: only the samples next to the cell centres can be the maximum - plus, on the first and last row
+            // of the strip, the outermost sample rows (the rectangle is cut there).  (Values in shared memory are
+            // exponents relative to the old references: maxima and shifts are taken in that domain.)
+            float es_max = -3.0e38f, et_max = -3.0e38f;
+            constexpr int KC0 = S / 2 - 1, KC1 = S / 2;
+            for (int c = threadIdx.x; c < ncell; c += kUpThreads) {
+                int i, j;
+                up_cell(c, p.Wl, p.inv_Wl, i, j);
+                i += x.i0;
+                float as[3][3], at[3][3];
+                up_nbhd(sS, p.Wl, p.Hl, r0, i, j, as);
+                up_nbhd(sT, p.Wl, p.Hl, r0, i, j, at);
+                auto sample = [](const float (&a)[3][3], int ky, int kx) {
+                    const int fy = UpW<S>::first(ky) + 1, fx = UpW<S>::first(kx) + 1;
+                    const float wy = UpW<S>::w1(ky), wx = UpW<S>::w1(kx);
+                    const float top = fmaf(wx, a[fy][fx + 1] - a[fy][fx], a[fy][fx]);
+                    const float bot = fmaf(wx, a[fy + 1][fx + 1] - a[fy + 1][fx], a[fy + 1][fx]);
+                    return fmaf(wy, bot - top, top);
+                };
+#pragma unroll
+                for (int kx = KC0; kx <= KC1; ++kx) {
+#pragma unroll
+                    for (int ky = KC0; ky <= KC1; ++ky) {
+                        es_max = fmaxf(es_max, sample(as, ky, kx));
+                        et_max = fmaxf(et_max, sample(at, ky, kx));
+                    }
+                    if (i == x.i0) {
+                        es_max = fmaxf(es_max, sample(as, 0, kx));
+                        et_max = fmaxf(et_max, sample(at, 0, kx));
+                    }
+                    if (i == x.i1 - 1) {
+                        es_max = fmaxf(es_max, sample(as, S - 1, kx));
+                        et_max = fmaxf(et_max, sample(at, S - 1, kx));
+                    }
+                }
+            }
+            es_max = block_max(es_max, red);
+            et_max = block_max(et_max, red);
+            ms += es_max * p.inv_c2;          // the new references, back in the value domain (any value close to the
+            mt += et_max * p.inv_c2;          // true maximum serves: what matters is that it is used consistently)
+            __syncthreads();
         }
-        zs = block_sum(zs, red);
-        zt = block_sum(zt, red);
-        acc = block_sum(acc, red);
         // acc = sum et ((t - mt) - (s - ms)) c2  ->  sum et (t - s)
         acc = acc * p.inv_c2 + (mt - ms) * zt;
         if (threadIdx.x == 0) {
@@ -270,14 +328,26 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_grad_kernel(const UpPar
             const int g_real = min(p.g, p.C - x.grp * p.g);
             const long long first = ((long long)x.b * p.C + (long long)x.grp * p.g) * p.NS;
             const int nrec = g_real * p.NS;
-            float ms = kUpFloor, mt = kUpFloor;
+            // row reference = the largest log-sum-exp of its units: the merged sums then lie in [1, number of units]
+            // whatever reference a unit used, and no up-sampled value exceeds it.  Taken relative to the largest unit
+            // reference so that nothing is rounded at the magnitude of the values themselves.
+            float bs = kUpFloor, bt = kUpFloor;
             for (int r = lane; r < nrec; r += 32) {
                 const float4 q = *reinterpret_cast<const float4*>(p.part + (first + r) * 8);
-                ms = fmaxf(ms, q.x);
-                mt = fmaxf(mt, q.y);
+                bs = fmaxf(bs, q.x);
+                bt = fmaxf(bt, q.y);
             }
-            ms = warp_max(ms);
-            mt = warp_max(mt);
+            bs = warp_max(bs);
+            bt = warp_max(bt);
+            float ls = -3.0e38f, lt = -3.0e38f;
+            for (int r = lane; r < nrec; r += 32) {
+                const float4 q = *reinterpret_cast<const float4*>(p.part + (first + r) * 8);
+                ls = fmaxf(ls, fmaf(q.x - bs, p.c2, log2f(q.z)));
+                lt = fmaxf(lt, fmaf(q.y - bt, p.c2, log2f(q.w)));
+            }
+            ls = warp_max(ls);
+            lt = warp_max(lt);
+            const float ms = bs + ls * p.inv_c2, mt = bt + lt * p.inv_c2;     // used consistently from here on
             float zs = 0.f, zt = 0.f, acc = 0.f;
             for (int r = lane; r < nrec; r += 32) {
                 const float4 q0 = *reinterpret_cast<const float4*>(p.part + (first + r) * 8);
@@ -285,6 +355,7 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_grad_kernel(const UpPar
                 const float fs = fast_exp2((q0.x - ms) * p.c2), ft = fast_exp2((q0.y - mt) * p.c2);
                 zs = fmaf(q0.z, fs, zs);
                 zt = fmaf(q0.w, ft, zt);
+                // a is sum et (t - s) against the unit's reference; (t - s) needs no shift, et scales like zt
                 acc = fmaf(a, ft, acc);
             }
             zs = warp_sum(zs);

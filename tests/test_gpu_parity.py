@@ -746,3 +746,36 @@ def test_fused_resize_without_grad_and_with_upstream_scale():
     x = s.to(dev()).requires_grad_(True)
     (512.0 * sd.CDLoss()(x, t.to(dev()), gt, 1)).backward()       # fp16-style loss scaling upstream
     assert (x.grad.cpu() - 512.0 * ref[1]).abs().max().item() <= GRAD_RTOL * 512.0 * ref[1].abs().max().item()
+
+
+def test_fused_resize_isolated_spikes_stay_finite():
+    """A spike between cells: every up-sampled value is far below the low-resolution maximum, so the reference
+    of the exponentials must be the maximum of the UP-SAMPLED values (found exactly at the samples next to the
+    cell centres) or the sums underflow."""
+    s, t = seeded_pair((1, 4, 16, 16), seed=47)
+    s[0, 1, 5, 7] += 3000.0
+    t[0, 1, 9, 2] += 2500.0
+    s[0, 3, 0, 0] += 4000.0          # a corner cell: clamped taps
+    t[0, 2, 15, 8] -= 5000.0
+    for scale in (2, 4, 8):
+        hw = (16 * scale, 16 * scale)
+        ref = _oracle_run('CGDLoss', dict(group_size=2, alpha=1, tau=1), s, t, hw, 1)
+        got = _run(sd.CGDLoss(group_size=2, alpha=1, tau=1), s, t, hw, 1)
+        assert _cabi.last_kernel() in ('kl_rows_up_kernel', 'scale_grad_kernel')
+        assert np.isfinite(got[0]) and torch.isfinite(got[1]).all()
+        _assert_close(*got, *ref, loss_rtol=2e-5, grad_rtol=1e-4)
+
+
+def test_fused_resize_pixel_mode_large_logit_steps():
+    """Pixel mode keeps one reference per low-resolution cell (the maximum over channels of its 3x3 neighbourhood): steps
+    of up to ~87*tau between neighbouring cells stay inside the fp32 exponent range (documented limit)."""
+    s, t = seeded_pair((1, 6, 12, 12), seed=48)
+    s[0, 1, 5, 7] += 60.0
+    t[0, 2, 9, 2] += 50.0
+    s[0, 3, 0, 0] -= 70.0
+    for scale in (2, 4, 8):
+        hw = (12 * scale, 12 * scale)
+        ref = _oracle_run('PDLoss', {}, s, t, hw, 1)
+        got = _run(sd.PDLoss(), s, t, hw, 1)
+        assert np.isfinite(got[0]) and torch.isfinite(got[1]).all()
+        _assert_close(*got, *ref, loss_rtol=2e-5, grad_rtol=1e-4)
