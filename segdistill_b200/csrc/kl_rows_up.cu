@@ -1,4 +1,5 @@
-// Channel-mode softmax-KL (CD / CGD) on maps that the reference first RESIZES to the label size:
+// Softmax-KL losses on maps that the reference first RESIZES to the label size - channel mode (CD / CGD: this
+// comment) and pixel mode (PD: kl_pixels_up_kernel further down):
 // KLDLoss.resize (mmseg/models/distillation/losses.py:25-33, F.interpolate(..., mode='bilinear',
 // align_corners=False), ops/wrappers.py:8-29) followed by the transform + KL chain (:50-58, :108-112) and autograd's
 // backward through both.  Every shipped preset resizes logits at 1/4 or 1/8 resolution to 512x512 (SURVEY.md 8 a8 /
@@ -9,10 +10,10 @@
 // ((k + 1/2)/s -+ 1/2), so a thread regenerates the block in registers from shared memory:
 //
 //   kernel 1 (statistics)  unit = (sample, channel, strip of low-res rows): load the strip (+ one halo row each
-//                          side) of S and T, reference = the exact maximum of the unit's up-sampled values (found
-//                          at the samples next to the cell centres), sums of exp2 over the up-sampled block of
-//                          every cell -> one partial record per unit.
-//   kernel 2 (gradient)    merges the records of its row (g channels x strips) into the row statistics,
+//                          side) of S and T, reference = the strip maximum (a unit whose sums underflow against
+//                          it is redone against the exact maximum of its up-sampled values), sums of exp2 over
+//                          the up-sampled block of every cell -> one partial record per unit.
+//   kernel 2 (gradient)    merges the records of its row (g channels x strips) by log-sum-exp into the row statistics,
 //                          regenerates the block, g = coef (q - p), and applies the TRANSPOSED stencil: a cell's
 //                          block contributes a 3 x 3 matrix W_y^T g W_x to the cells around it; every thread
 //                          stores its nine contributions to nine shared-memory planes (no atomics), then every
