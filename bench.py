@@ -217,6 +217,7 @@ def run_ours(args, rank, local_rank, world):
     dl.batch_pairs = not args.unfused
     numel = S.numel()
     packed = torch.zeros(3, device=dev)
+    slots = [torch.zeros(3, device=dev) for _ in range(2)]      # N>1: what the collectives read (two steps in flight)
 
     def feats(x):
         return {'decode_head.linear_pred': x, 'decode_head': x}
@@ -240,13 +241,14 @@ def run_ours(args, rank, local_rank, world):
 
     pending = []
 
-    def reduce_scalars():
-        """The path's only collective: the packed loss scalars of this step, all-reduced asynchronously on a copy so
-        that the next step's kernels do not queue behind it; at most 4 in flight."""
+    def reduce_scalars(slot=None):
+        """The path's only collective: the packed loss scalars of this step, all-reduced asynchronously so that the
+        next step's kernels do not queue behind it.  slot: the static buffer a captured step copied them to (replays
+        alternate between two graphs / slots); None: an eager step, a fresh copy is made."""
         if world > 1:
-            buf = packed.clone()
+            buf = packed.clone() if slot is None else slots[slot]
             pending.append((dist.all_reduce(buf, async_op=True), buf))
-            if len(pending) > 4:
+            if len(pending) > 1:                       # before a slot is written again its collective has completed
                 pending.pop(0)[0].wait()
 
     def drain_scalars():
@@ -289,15 +291,22 @@ def run_ours(args, rank, local_rank, world):
                     step()
             torch.cuda.current_stream().wait_stream(side)
             sync_all()
-            g_ = torch.cuda.CUDAGraph()
             # capture on the stream the warm-up ran on: its zero-filled workspace exists already (a fresh
-            # capture stream would put the one-time workspace allocation + fill into every replay)
-            with torch.cuda.graph(g_, stream=side):
-                static_losses = compute()        # (the scalar all-reduce is launched after each replay, not captured)
-            graph, graph_note = g_, 'CUDA graph replay of the captured module-API step'
-            for _ in range(3):
-                graph.replay()
-                reduce_scalars()
+            # capture stream would put the one-time workspace allocation + fill into every replay).  The scalar
+            # all-reduce is launched after each replay, not captured; with N > 1 two graphs alternate, each ending
+            # with a copy of the packed scalars into its own slot for the collective to read.
+            graphs = []
+            for k in range(2 if world > 1 else 1):
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_, stream=side):
+                    static_losses = compute()
+                    if world > 1:
+                        slots[k].copy_(packed)
+                graphs.append(g_)
+            graph, graph_note = graphs, 'CUDA graph replay of the captured module-API step'
+            for i in range(4):
+                graph[i % len(graph)].replay()
+                reduce_scalars(i % len(graph))
             sync_all()
             _note(rank, 'graph captured')
         except Exception as exc:          # capture is an optimisation, never a requirement
@@ -324,8 +333,8 @@ def run_ours(args, rank, local_rank, world):
         per_step_launches = launches // args.steps
         t_begin.record()
         for i in range(args.steps):
-            graph.replay()
-            reduce_scalars()
+            graph[i % len(graph)].replay()
+            reduce_scalars(i % len(graph))
         drain_scalars()                      # the timed region ends when the last collective has completed
         t_end.record()
         sync_all()
@@ -338,7 +347,7 @@ def run_ours(args, rank, local_rank, world):
     while time.perf_counter() < t_hold:
         for _ in range(50):
             if graph is not None:
-                graph.replay()
+                graph[0].replay()
             else:
                 compute()
         torch.cuda.synchronize()
