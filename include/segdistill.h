@@ -17,6 +17,8 @@
  *   sd_kl_rows_up_fwd_bwd the same behind KLDLoss.resize (losses.py:25-33,101-102; ops/wrappers.py:8-29):
  *                         bilinear up-sampling fused into the loss and its backward
  *   sd_mse_fwd_bwd        losses.py:178,190 / :202,235 (nn.MSELoss), :812-830 (feature MSE)
+ *   sd_ifvd_sim_fwd_bwd   losses.py:218-235 - IFVDLoss: per-class centres (the loop over C classes :226-230),
+ *                         nn.CosineSimilarity to the centre of the pixel's class, 10*nn.MSELoss
  *   sd_kl_rows_multi_fwd_bwd  the same for two `distillation` entries on one pair (opts.py:100-103)
  *   sd_scale_grad         the autograd multiply by grad_output that torch would run in
  *                         backward (loss enters the total as a plain sum,
@@ -188,6 +190,20 @@ SD_API size_t sd_mse_workspace_bytes(int64_t numel);
 SD_API int sd_mse_fwd_bwd(const void* S, const void* T, void* dS, float* loss,
                    int64_t numel, int dtype, float weight, float grad_scale,
                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ IFVDLoss similarity term */
+/*
+ * mmseg/models/distillation/losses.py:218-235 (IFVDLoss without its per-pixel KL, which is sd_kl_pixels_fwd_bwd):
+ *   centre_X[:, k] = sum_{p: cls[p] == k} X[:, p] / (n_k + 1e-6)   per sample, X in {S, T}
+ *   sim_X(p) = cosine_similarity(X[:, p], centre_X[:, cls[p]])      (ATen semantics, eps = 1e-8)
+ *   *loss = weight * mean_{b,p} (sim_S - sim_T)^2;  dS = grad_scale * d loss / d S, including the path through the
+ *   class centres.  cls: int32 (B, HW), class index in [0, C) or C for pixels without a class (they keep their own
+ *   feature as centre: sim = 1, zero gradient).  Deterministic (no float atomics).
+ */
+SD_API size_t sd_ifvd_sim_workspace_bytes(int B, int C, int HW);
+SD_API int sd_ifvd_sim_fwd_bwd(const void* S, const void* T, const int32_t* cls, void* dS, float* loss,
+                        int B, int C, int HW, int dtype, float weight, float grad_scale,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ backward helper */
 /* dS *= *grad_output (a device scalar); exits without touching dS when it equals 1. */

@@ -70,6 +70,35 @@ def main():
         'cd_cfg1_f32': ((2, 150, 64, 64), torch.float32, lambda s, t: _cabi.kl_rows(s, t, group=1)),
         'cgd150_f32': ((16, 150, 64, 64), torch.float32, lambda s, t: _cabi.kl_rows(s, t, group=150, tau=2.0)),
     }
+    def blocky(shape, block=8):
+        b, c, h, w = shape
+        g = torch.Generator(device=dev).manual_seed(1)
+        coarse = torch.randint(0, c, (b, 1, h // block, w // block), device=dev, generator=g)
+        return coarse.repeat_interleave(block, 2).repeat_interleave(block, 3).reshape(b, h * w).to(torch.int32)
+
+    def torch_ifvd_sim(s, t, cls):
+        """the similarity term as ATen ops under autograd (scatter-add centres) - what ifvd.cu replaced"""
+        import torch.nn.functional as F
+        b, c = s.shape[:2]
+        k = cls.long()
+        x = s.reshape(b, c, -1).detach().requires_grad_(True)
+
+        def sim(f):
+            gi = k.unsqueeze(1).expand_as(f)
+            sums = f.new_zeros(b, c, c + 1).scatter_add_(2, gi, f)
+            cnt = f.new_zeros(b, c + 1).scatter_add_(1, k, torch.ones_like(k, dtype=f.dtype))
+            return F.cosine_similarity(f, torch.gather(sums / (cnt.unsqueeze(1) + 1e-6), 2, gi), dim=1)
+
+        (10 * F.mse_loss(sim(x), sim(t.reshape(b, c, -1)))).backward()
+
+    S2 = (2, 150, 128, 128)
+    cls2, cls16 = blocky(S2), blocky(L)
+    cases.update({
+        'ifvd_sim_2x150x128_f32': (S2, torch.float32, lambda s, t: _cabi.ifvd_sim(s, t, cls2)),
+        'ifvd_sim_2x150x128_aten': (S2, torch.float32, lambda s, t: torch_ifvd_sim(s, t, cls2)),
+        'ifvd_sim_16x150x128_f32': (L, torch.float32, lambda s, t: _cabi.ifvd_sim(s, t, cls16)),
+        'ifvd_sim_16x150x128_aten': (L, torch.float32, lambda s, t: torch_ifvd_sim(s, t, cls16)),
+    })
     only = [x for x in a.only.split(',') if x]
     for name, (shape, dtype, fn) in cases.items():
         if only and name not in only:

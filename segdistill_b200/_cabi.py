@@ -29,7 +29,7 @@ EXPORTS = (
     'sd_kl_rows_workspace_bytes', 'sd_kl_rows_fwd_bwd', 'sd_kl_rows_multi_fwd_bwd', 'sd_scale_grad2',
     'sd_kl_pixels_workspace_bytes', 'sd_kl_pixels_fwd_bwd',
     'sd_kl_rows_up_workspace_bytes', 'sd_kl_rows_up_fwd_bwd', 'sd_kl_pixels_up_workspace_bytes', 'sd_kl_pixels_up_fwd_bwd',
-    'sd_mse_workspace_bytes', 'sd_mse_fwd_bwd', 'sd_scale_grad',
+    'sd_mse_workspace_bytes', 'sd_mse_fwd_bwd', 'sd_ifvd_sim_workspace_bytes', 'sd_ifvd_sim_fwd_bwd', 'sd_scale_grad',
     'sd_cgd_corr_workspace_bytes', 'sd_cgd_corr_fwd_bwd',
     'sd_launch_count', 'sd_last_kernel',
 )
@@ -93,6 +93,10 @@ def load():
         lib.sd_mse_workspace_bytes.argtypes = [i64]
         lib.sd_mse_fwd_bwd.restype = i32
         lib.sd_mse_fwd_bwd.argtypes = [vp, vp, vp, vp, i64, i32, f32, f32, vp, sz, vp]
+        lib.sd_ifvd_sim_workspace_bytes.restype = sz
+        lib.sd_ifvd_sim_workspace_bytes.argtypes = [i32, i32, i32]
+        lib.sd_ifvd_sim_fwd_bwd.restype = i32
+        lib.sd_ifvd_sim_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, sz, vp]
         lib.sd_scale_grad.restype = i32
         lib.sd_scale_grad.argtypes = [vp, i64, i32, vp, vp]
         lib.sd_cgd_corr_workspace_bytes.restype = sz
@@ -400,6 +404,28 @@ def mse(x_student, x_teacher, weight=1.0, grad_scale=1.0):
         ws = _workspace(dev, lib.sd_mse_workspace_bytes(s.numel()))
         rc = lib.sd_mse_fwd_bwd(s.data_ptr(), t.data_ptr(), ds.data_ptr(), out.data_ptr(), s.numel(), code,
                                 float(weight), float(grad_scale), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        _check(rc)
+    return out[0], ds
+
+
+def ifvd_sim(x_student, x_teacher, cls, weight=10.0, grad_scale=1.0):
+    """IFVDLoss similarity term: ``weight * mean((cos(s, centre_s) - cos(t, centre_t))^2)``; ``cls`` is the (B, H*W)
+    class index of every pixel, ``C`` meaning "no class". Returns (loss, dS)."""
+    lib = load()
+    s, t, code = _prep_pair(x_student, x_teacher)
+    B, C = s.shape[0], s.shape[1]
+    HW = math.prod(s.shape[2:])
+    dev = s.device
+    if cls.device != dev or cls.numel() != B * HW:
+        raise SegDistillError(f'class map must hold B*H*W = {B * HW} entries on {dev}')
+    with _on(dev):
+        k = cls.reshape(B, HW).to(torch.int32).contiguous()
+        ds = torch.empty_like(s)
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        ws = _workspace(dev, lib.sd_ifvd_sim_workspace_bytes(B, C, HW))
+        rc = lib.sd_ifvd_sim_fwd_bwd(s.data_ptr(), t.data_ptr(), k.data_ptr(), ds.data_ptr(), out.data_ptr(), B, C, HW,
+                                     code, float(weight), float(grad_scale), ws.data_ptr(), ws.numel(),
+                                     _stream_ptr(dev))
         _check(rc)
     return out[0], ds
 

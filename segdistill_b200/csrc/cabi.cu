@@ -601,6 +601,40 @@ int sd_kl_pixels_up_fwd_bwd(const void* S, const void* T, void* dS, float* loss,
     return e == cudaSuccess ? SD_OK : (int)e;
 }
 
+// ============================================================================ IFVD similarity term
+size_t sd_ifvd_sim_workspace_bytes(int B, int C, int HW) {
+    if (B <= 0 || C <= 0 || HW <= 0) return 0;
+    return sd::ifvd_workspace_layout(B, C, HW, sd::ifvd_pix_threads()).bytes;
+}
+
+int sd_ifvd_sim_fwd_bwd(const void* S, const void* T, const int32_t* cls, void* dS, float* loss, int B, int C, int HW,
+                        int dtype, float weight, float grad_scale, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+    if (!S || !T || !cls || !dS || !loss || !workspace) return SD_ERR_NULL;
+    if (dtype != SD_F32 && dtype != SD_BF16) return SD_ERR_DTYPE;
+    if (B <= 0 || C <= 0 || HW <= 0 || B > 65535 || C > 4096 || (long long)B * C * HW >= (1ll << 40)) return SD_ERR_SHAPE;
+    const sd::IfvdWorkspace w = sd::ifvd_workspace_layout(B, C, HW, sd::ifvd_pix_threads());
+    if (workspace_bytes < w.bytes) return SD_ERR_WORKSPACE;
+    DeviceInfo& dev = device_info();
+    if (dev.cc_major != 10) return SD_ERR_DEVICE;
+    char* ws = static_cast<char*>(workspace);
+    sd::IfvdParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.S = S; p.T = T; p.cls = cls; p.dS = dS; p.loss = loss;
+    p.sums = reinterpret_cast<float*>(ws + w.off_sums);
+    p.wsum = reinterpret_cast<float*>(ws + w.off_wsum);
+    p.pix = reinterpret_cast<float*>(ws + w.off_pix);
+    p.part = reinterpret_cast<float*>(ws + w.off_part);
+    p.B = B; p.C = C; p.HW = HW;
+    const double npix = (double)B * (double)HW;
+    p.gcoef = (float)((double)grad_scale * 2.0 * (double)weight / npix);
+    cudaError_t e = sd::launch_ifvd_sim(p, dtype == SD_BF16, (float)((double)weight / npix),
+                                        static_cast<cudaStream_t>(stream));
+    g_launches += 5;
+    t_last_kernel = "ifvd_sim (class sums, sim, weighted class sums, grad)";
+    return e == cudaSuccess ? SD_OK : (int)e;
+}
+
 // ============================================================================ MSE
 size_t sd_mse_workspace_bytes(int64_t numel) {
     (void)numel;

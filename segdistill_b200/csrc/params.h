@@ -213,4 +213,35 @@ inline PixWorkspace pix_workspace_layout(long long B, long long C, long long HW)
 // ---------------------------------------------------------------- MSE
 constexpr int kMseMaxGrid = 148 * 8;
 
+// ---------------------------------------------------------------- IFVD similarity term (ifvd.cu)
+struct IfvdParams {
+    const void* S;      // (B, C, HW)
+    const void* T;
+    const int* cls;     // (B, HW) class of each pixel in [0, C), or C for "no class"
+    void* dS;
+    float* loss;
+    float* sums;        // [2][B][C+1][C+1] class sums of S, of T; row C = class counts
+    float* wsum;        // [B][C+1][C+1]    gradient reaching the class sums of S; row C = V_k
+    float* pix;         // [4][B][HW]       per-pixel backward coefficients
+    float* part;        // one loss partial per CTA of the per-pixel kernel
+    int B, C, HW;
+    float gcoef;        // grad_scale * 2 * weight / (B*HW)
+};
+struct IfvdWorkspace {
+    size_t off_sums, off_wsum, off_pix, off_part, bytes;
+    long long nparts;
+};
+inline IfvdWorkspace ifvd_workspace_layout(long long B, long long C, long long HW, long long pix_threads) {
+    IfvdWorkspace w;
+    const size_t K1 = (size_t)C + 1;
+    size_t o = kArenaBytes;
+    w.off_sums = o;  o += sizeof(float) * 2 * (size_t)B * K1 * K1;
+    w.off_wsum = o;  o += sizeof(float) * (size_t)B * K1 * K1;
+    w.off_pix = o;   o += sizeof(float) * 4 * (size_t)B * (size_t)HW;
+    w.nparts = B * ((HW + pix_threads - 1) / pix_threads);
+    w.off_part = o;  o += sizeof(float) * (size_t)w.nparts;
+    w.bytes = (o + 255) & ~(size_t)255;
+    return w;
+}
+
 }  // namespace sd

@@ -158,6 +158,22 @@ class _MSE(torch.autograd.Function):
         return _finish_backward(ctx, grad_output), None, None
 
 
+class _IFVDSim(torch.autograd.Function):
+    """IFVDLoss's similarity term (losses.py:218-235): class centres, cosine similarity, MSE and their backward."""
+
+    @staticmethod
+    def forward(ctx, x_student, x_teacher, cls, weight):
+        loss, ds = _cabi.ifvd_sim(x_student, x_teacher, cls, weight=weight)
+        ctx.ds = ds if x_student.requires_grad else None
+        ctx.in_dtype, ctx.in_shape = x_student.dtype, x_student.shape
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        return _finish_backward(ctx, grad_output), None, None, None
+
+
 class _CGDCorr(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_student, x_teacher, group, alpha):
@@ -220,6 +236,11 @@ def kl_pixels_loss(x_student, x_teacher, tau=1.0, alpha=1.0, at_weight=0.0, algo
 
 def mse_loss(x_student, x_teacher, weight=1.0):
     return _MSE.apply(x_student, x_teacher, float(weight))
+
+
+def ifvd_sim_loss(x_student, x_teacher, cls, weight=10.0):
+    """weight * mean over pixels of (cos(s, centre_s) - cos(t, centre_t))^2, centres per sample and class."""
+    return _IFVDSim.apply(x_student, x_teacher, cls, float(weight))
 
 
 def cgd_corr_loss(x_student, x_teacher, group=10, alpha=1.0):

@@ -238,9 +238,10 @@ class IFVDLoss(nn.Module):
     """Intra-class feature variation distillation (reference :199-238): per-pixel KL + 10 * MSE between the
     student's and the teacher's maps of cosine similarity of every pixel to the centre of its class.
 
-    The KL term runs in the fused pixel kernel.  The class centres - a Python loop over all C classes in the
-    reference, ~10 full-size ATen ops per class - are ONE segmented reduction here (scatter-add of the features
-    by label, gather back), under autograd, so the gradient through the centres matches the reference's.
+    The KL term runs in the fused pixel kernel.  The similarity term - in the reference a Python loop over all C
+    classes (~10 full-size ATen ops per class and tensor), two cosine similarities, an MSE and the autograd
+    backward of all of it - is one C-ABI call (csrc/ifvd.cu: deterministic segmented reductions for the class
+    centres, one sweep per pixel, the gradient including the path through the centres).
     Pixels whose label matches no class (ignore index 255) keep their own feature as centre, as in the reference.
     """
     algo = 'auto'
@@ -249,15 +250,14 @@ class IFVDLoss(nn.Module):
         super().__init__()
 
     @staticmethod
-    def _similarity(feat, idx, valid):
-        b, c, hw = feat.shape
-        n_bins = c + 1                                            # bin c collects the pixels without a class
-        gidx = idx.unsqueeze(1).expand(b, c, hw)
-        sums = feat.new_zeros(b, c, n_bins).scatter_add_(2, gidx, feat)
-        cnt = feat.new_zeros(b, n_bins).scatter_add_(1, idx, torch.ones_like(idx, dtype=feat.dtype))
-        centre = sums / (cnt.unsqueeze(1) + 1e-6)                 # :226-230
-        cf = torch.where(valid.unsqueeze(1), torch.gather(centre, 2, gidx), feat)
-        return F.cosine_similarity(feat, cf, dim=1)               # :231-233
+    def _class_map(target, c, h, w):
+        """(B, h*w) int32 class of every pixel: the label nearest-resized to the feature size (:218-219) where it
+        equals one of the class indices 0..C-1 the reference loops over (:222-224), else C ("no class")."""
+        b = target.shape[0]
+        lab = F.interpolate(target.float(), size=(h, w), mode='nearest').reshape(b, h * w)
+        k = lab.long()
+        valid = (k.to(lab.dtype) == lab) & (k >= 0) & (k < c)
+        return torch.where(valid, k, torch.full_like(k, c)).to(torch.int32)
 
     def forward(self, preds_S, preds_T, target, step=0):
         feat_s, feat_t = preds_S, preds_T
@@ -266,13 +266,8 @@ class IFVDLoss(nn.Module):
         feat_t = feat_t.detach()
         loss_pd = SF.kl_pixels_loss(feat_s, feat_t, tau=1.0, alpha=1.0, algo=self.algo)                    # :213-215
         b, c, h, w = feat_s.shape
-        lab = F.interpolate(target.float(), size=(h, w), mode='nearest').reshape(b, h * w)                 # :218-219
-        k = lab.long()
-        valid = (k.to(lab.dtype) == lab) & (k >= 0) & (k < c)                                              # :223-224
-        idx = torch.where(valid, k, torch.full_like(k, c))
-        sim_s = self._similarity(feat_s.reshape(b, c, h * w).float(), idx, valid)
-        sim_t = self._similarity(feat_t.reshape(b, c, h * w).float(), idx, valid)
-        return 10 * F.mse_loss(sim_s, sim_t) + loss_pd                                                    # :235-237
+        cls = self._class_map(target, c, h, w)
+        return SF.ifvd_sim_loss(feat_s, feat_t, cls, 10.0) + loss_pd                                      # :226-237
 
 
 class FeatureMSELoss(nn.Module):

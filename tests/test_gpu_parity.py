@@ -713,6 +713,87 @@ def test_ifvd_golden_and_seeded():
     _assert_close(loss.item(), x.grad.cpu(), ref.item(), xr.grad)
 
 
+def _ifvd_sim_ref64(s, t, cls, weight=10.0):
+    """float64 restatement of losses.py:218-235 with the class centres as one index_add (CPU, autograd)."""
+    import torch.nn.functional as F
+    b, c = s.shape[:2]
+    x = s.double().reshape(b, c, -1).detach().requires_grad_(True)
+    y = t.double().reshape(b, c, -1)
+    k = cls.long()
+    valid = k < c
+
+    def sim(f):
+        sums = f.new_zeros(b, c, c + 1).scatter_add(2, k.unsqueeze(1).expand_as(f), f)
+        cnt = f.new_zeros(b, c + 1).scatter_add(1, k, torch.ones_like(k, dtype=f.dtype))
+        centre = sums / (cnt.unsqueeze(1) + 1e-6)
+        cf = torch.where(valid.unsqueeze(1), torch.gather(centre, 2, k.unsqueeze(1).expand_as(f)), f)
+        return F.cosine_similarity(f, cf, dim=1)
+
+    loss = weight * F.mse_loss(sim(x), sim(y))
+    loss.backward()
+    return loss.item(), x.grad.reshape(s.shape)
+
+
+def _blocky_labels(b, h, w, n_classes, seed, block=8):
+    g = torch.Generator().manual_seed(seed)
+    coarse = torch.randint(0, n_classes, (b, 1, (h + block - 1) // block, (w + block - 1) // block), generator=g)
+    return coarse.repeat_interleave(block, 2).repeat_interleave(block, 3)[:, :, :h, :w].contiguous()
+
+
+@pytest.mark.parametrize('shape,labels', [((2, 150, 64, 64), 'blocky'), ((2, 19, 33, 47), 'random'),
+                                          ((1, 150, 128, 128), 'blocky'), ((3, 5, 7, 9), 'random')])
+def test_ifvd_similarity_term_cabi_vs_float64(shape, labels):
+    """sd_ifvd_sim_fwd_bwd against the float64 restatement: spatially coherent label maps (whole warps in one class),
+    random labels (every lane its own class), pixels without a class, classes without a pixel, odd sizes."""
+    b, c, h, w = shape
+    s, t = seeded_pair(shape, seed=71, scale=2.0)
+    if labels == 'blocky':
+        target = _blocky_labels(b, h, w, c, seed=72)
+        target[:, :, : h // 5, w // 3: w // 2] = 255
+    else:
+        target = torch.randint(0, c + 2, (b, 1, h, w), generator=torch.Generator().manual_seed(72))
+    cls = sd.IFVDLoss._class_map(target, c, h, w)
+    ref_loss, ref_grad = _ifvd_sim_ref64(s, t, cls)
+    loss, ds = _cabi.ifvd_sim(s.to(dev()), t.to(dev()), cls.to(dev()), weight=10.0)
+    assert 'ifvd' in _cabi.last_kernel()
+    _assert_close(loss.item(), ds.cpu(), ref_loss, ref_grad)
+    assert float(ds.cpu().reshape(b, c, -1)[(cls == c).unsqueeze(1).expand(b, c, h * w)].abs().sum()) == 0.0
+    # deterministic: no float atomics anywhere
+    loss2, ds2 = _cabi.ifvd_sim(s.to(dev()), t.to(dev()), cls.to(dev()), weight=10.0)
+    assert loss2.item() == loss.item() and torch.equal(ds, ds2)
+
+
+def test_ifvd_similarity_term_bf16_and_upstream_scale():
+    shape = (2, 150, 32, 32)
+    s, t = seeded_pair(shape, seed=73, scale=2.0, dtype=torch.bfloat16)
+    target = _blocky_labels(2, 32, 32, 150, seed=74, block=4)
+    cls = sd.IFVDLoss._class_map(target, 150, 32, 32)
+    ref_loss, ref_grad = _ifvd_sim_ref64(s.float(), t.float(), cls)
+    x = s.to(dev()).requires_grad_(True)
+    from segdistill_b200 import functional as SF
+    loss = SF.ifvd_sim_loss(x, t.to(dev()), cls.to(dev()), 10.0)
+    (loss * 4.0).backward()
+    assert x.grad.dtype == torch.bfloat16
+    _assert_close(loss.item(), x.grad.float().cpu() / 4.0, ref_loss, ref_grad, loss_rtol=2e-5,
+                  grad_rtol=BF16_GRAD_RTOL)
+
+
+def test_ifvd_module_on_the_training_shape():
+    """IFVDLoss on logits 2x150x128x128 with labels at 512x512 (the exp_tab5 *_IFVD situation) vs the oracle loop."""
+    s, t = seeded_pair((2, 150, 128, 128), seed=75, scale=2.0)
+    target = _blocky_labels(2, 512, 512, 150, seed=76, block=32)
+    target[:, :, 100:140, :200] = 255
+    xr = s.clone().requires_grad_(True)
+    ref = oracle.ifvd_loss_torch(xr, t, target)
+    ref.backward()
+    x = s.to(dev()).requires_grad_(True)
+    before = _cabi.launch_count()
+    loss = sd.IFVDLoss()(x, t.to(dev()), target.to(dev()), 0)
+    assert _cabi.launch_count() - before == 6          # one pixel-KL kernel + five of the similarity term
+    loss.backward()
+    _assert_close(loss.item(), x.grad.cpu(), ref.item(), xr.grad)
+
+
 def test_dispatcher_with_resized_labels_runs_the_fused_resize_per_entry():
     """Two entries on the same logits with labels at 4x the resolution (the shipped presets' situation): each
     entry up-samples inside its own kernels (no two-loss launch, no materialised resize), numbers as the reference."""
