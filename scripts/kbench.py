@@ -92,11 +92,13 @@ def main():
         (10 * F.mse_loss(sim(x), sim(t.reshape(b, c, -1)))).backward()
 
     S2 = (2, 150, 128, 128)
-    cls2, cls16 = blocky(S2), blocky(L)
+    cls2, cls16, cls16c = blocky(S2), blocky(L), blocky(L, 32)   # label blocks of 8x8 / 32x32 pixels
     cases.update({
         'ifvd_sim_2x150x128_f32': (S2, torch.float32, lambda s, t: _cabi.ifvd_sim(s, t, cls2)),
         'ifvd_sim_2x150x128_aten': (S2, torch.float32, lambda s, t: torch_ifvd_sim(s, t, cls2)),
         'ifvd_sim_16x150x128_f32': (L, torch.float32, lambda s, t: _cabi.ifvd_sim(s, t, cls16)),
+        'ifvd_sim_16x150x128_f32_coarse': (L, torch.float32, lambda s, t: _cabi.ifvd_sim(s, t, cls16c)),
+        'ifvd_sim_16x150x128_bf16': (L, torch.bfloat16, lambda s, t: _cabi.ifvd_sim(s, t, cls16)),
         'ifvd_sim_16x150x128_aten': (L, torch.float32, lambda s, t: torch_ifvd_sim(s, t, cls16)),
     })
     only = [x for x in a.only.split(',') if x]

@@ -612,7 +612,8 @@ int sd_ifvd_sim_fwd_bwd(const void* S, const void* T, const int32_t* cls, void* 
                         void* stream) {
     if (!S || !T || !cls || !dS || !loss || !workspace) return SD_ERR_NULL;
     if (dtype != SD_F32 && dtype != SD_BF16) return SD_ERR_DTYPE;
-    if (B <= 0 || C <= 0 || HW <= 0 || B > 65535 || C > 4096 || (long long)B * C * HW >= (1ll << 40)) return SD_ERR_SHAPE;
+    if (B <= 0 || C <= 0 || HW <= 0 || B > 32767 || (long long)B * C * HW >= (1ll << 40)) return SD_ERR_SHAPE;
+    if (C > sd::ifvd_max_channels()) return SD_ERR_UNSUPPORTED;
     const sd::IfvdWorkspace w = sd::ifvd_workspace_layout(B, C, HW, sd::ifvd_pix_threads());
     if (workspace_bytes < w.bytes) return SD_ERR_WORKSPACE;
     DeviceInfo& dev = device_info();
@@ -625,12 +626,15 @@ int sd_ifvd_sim_fwd_bwd(const void* S, const void* T, const int32_t* cls, void* 
     p.wsum = reinterpret_cast<float*>(ws + w.off_wsum);
     p.pix = reinterpret_cast<float*>(ws + w.off_pix);
     p.part = reinterpret_cast<float*>(ws + w.off_part);
+    p.spart = reinterpret_cast<float*>(ws + w.off_spart);
     p.B = B; p.C = C; p.HW = HW;
+    p.splits = w.splits;
+    p.vec = HW % 4 == 0 && aligned16(S) && aligned16(T) && aligned16(workspace);
     const double npix = (double)B * (double)HW;
     p.gcoef = (float)((double)grad_scale * 2.0 * (double)weight / npix);
     cudaError_t e = sd::launch_ifvd_sim(p, dtype == SD_BF16, (float)((double)weight / npix),
                                         static_cast<cudaStream_t>(stream));
-    g_launches += 5;
+    g_launches += w.splits > 1 ? 7 : 5;
     t_last_kernel = "ifvd_sim (class sums, sim, weighted class sums, grad)";
     return e == cudaSuccess ? SD_OK : (int)e;
 }

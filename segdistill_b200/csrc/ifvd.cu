@@ -32,105 +32,206 @@
 namespace sd {
 
 constexpr int kIfvdWarps = 8;          // planes per CTA of the class-sum kernels
-constexpr int kIfvdPixThreads = 128;   // pixels per CTA of the per-pixel kernels
+constexpr int kIfvdPixThreads = 32;    // pixels per CTA of the per-pixel kernels
+constexpr int kIfvdSlices = 8;         // channel slices per pixel of the per-pixel kernels
 constexpr float kCosEps = 1e-8f;       // ATen cosine_similarity eps (the reference uses the default)
 constexpr float kCentreEps = 1e-6f;    // losses.py:229-230
 
 // ------------------------------------------------------------------------------------------------
 // class sums: out[(tensor, b), c, k] = sum over the pixels p of class k of value(c, p)
-//   plain:    value = X[b, c, p]              (virtual channel c == C: 1 -> class counts), X = S (z = 0) or T (z = 1)
+//   plain:    value = X[b, c, p]              (virtual channel c == C: 1 -> class counts), X = S (z even) or T (z odd)
 //   weighted: value = a0[p] * S[b, c, p]      (virtual channel c == C: a1[p])
+//
+// lane = channel.  A warp owns 32 channels and a run of pixels; it stages [32 channels x 32 pixels] through a padded
+// shared-memory tile (coalesced along the pixels on the way in, one channel per lane on the way out) and then walks the
+// 32 pixels one by one: the class of a pixel is the same for every lane, so the control flow is warp-uniform, the bin
+// `bins[k][lane]` is private to the lane, and a run of pixels of one class is summed in a register before it touches
+// the bin.  No match/shuffle reductions, no atomics; every (channel, class) sum has a fixed order: pixels in order
+// inside a warp, warps in order inside a CTA, CTAs (`splits` pixel ranges) in order in ifvd_combine_kernel.
 // ------------------------------------------------------------------------------------------------
-template <typename T, bool WEIGHTED>
-__global__ void __launch_bounds__(kIfvdWarps * 32) ifvd_class_sums_kernel(const IfvdParams p) {
-    extern __shared__ float bins[];  // [kIfvdWarps][K1]
+constexpr int kTilePitch = 33;
+
+__device__ __forceinline__ void load4(const float* p, float* f) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+__device__ __forceinline__ void load4(const __nv_bfloat16* p, float* f) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    Elem<__nv_bfloat16>::unpack2(v.x, f[0], f[1]);
+    Elem<__nv_bfloat16>::unpack2(v.y, f[2], f[3]);
+}
+
+// VEC (HW % 4 == 0): a lane fetches 4 consecutive pixels of a channel per load, a warp-load covers 4 channel rows
+template <typename T, bool WEIGHTED, bool VEC>
+__global__ void __launch_bounds__(kIfvdWarps * 32, 1) ifvd_class_sums_kernel(const IfvdParams p) {
+    extern __shared__ float smem_f[];  // bins [kIfvdWarps][K1][32], tiles [kIfvdWarps][32][33]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.y;
-    const int c = blockIdx.x * kIfvdWarps + warp;
     const int C = p.C, HW = p.HW, K1 = C + 1;
-    if (c > C) return;  // warp-uniform; no CTA barrier below
+    const int split = blockIdx.x, c0 = blockIdx.y * 32;
+    const int b = WEIGHTED ? blockIdx.z : blockIdx.z >> 1;
+    const bool second = !WEIGHTED && (blockIdx.z & 1);
 
-    float* my = bins + warp * K1;
-    for (int k = lane; k < K1; k += 32) my[k] = 0.f;
-    __syncwarp();
+    float* bins = smem_f + (size_t)warp * K1 * 32;
+    float* tile = smem_f + (size_t)kIfvdWarps * K1 * 32 + (size_t)warp * 32 * kTilePitch;
+    for (int i = lane; i < K1 * 32; i += 32) bins[i] = 0.f;
 
-    const bool second = !WEIGHTED && blockIdx.z == 1;
-    const T* feat = static_cast<const T*>(second ? p.T : p.S) + ((size_t)b * C + (c < C ? c : 0)) * HW;
+    // this warp's run of 32-pixel steps
+    const int steps = (HW + 31) / 32;
+    const int per_cta = (steps + p.splits - 1) / p.splits;
+    const int per_warp = (per_cta + kIfvdWarps - 1) / kIfvdWarps;
+    const int s0 = split * per_cta + warp * per_warp;
+    const int s1 = min(min(s0 + per_warp, (split + 1) * per_cta), steps);
+
+    const T* feat = static_cast<const T*>(second ? p.T : p.S) + ((size_t)b * C + c0) * HW;
     const int* cls = p.cls + (size_t)b * HW;
     const float* a0 = p.pix + (size_t)b * HW;
     const float* a1 = a0 + (size_t)p.B * HW;
-    const bool real = c < C;
 
-    constexpr int U = 4;
-    for (int i0 = 0; i0 < HW; i0 += 32 * U) {
-        int k[U];
-        float v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int px = i0 + u * 32 + lane;
-            k[u] = C;      // lanes past the end of the plane: the "no class" bin, value 0
-            v[u] = 0.f;
-            if (px < HW) {
-                k[u] = __ldg(cls + px);
-                if (WEIGHTED) v[u] = real ? __ldg(a0 + px) * Elem<T>::load(feat + px) : __ldg(a1 + px);
-                else v[u] = real ? Elem<T>::load(feat + px) : 1.f;
+    int cur = C;       // class of the run being summed in `acc` (C: the bin nobody reads)
+    float acc = 0.f;
+    // one step = 32 pixels x 32 channels; the next step's global loads fly while this one is walked
+    float v[32], w[4] = {1.f, 1.f, 1.f, 1.f};
+    int kreg = C;
+    const int sr = lane >> 3, px4 = 4 * (lane & 7);  // VEC: sub-row and first pixel of this lane's loads
+    auto load_step = [&](int st) {
+        const int px = st * 32 + lane;
+        kreg = px < HW ? __ldg(cls + px) : C;
+        if (VEC) {
+            const int q0 = st * 32 + px4;
+            const bool in = q0 < HW;
+            if (WEIGHTED) {
+                if (in) load4(a0 + q0, w);
+                else w[0] = w[1] = w[2] = w[3] = 0.f;
             }
-        }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const unsigned m = __match_any_sync(0xffffffffu, k[u]);
-            float acc;
-            if (m == 0xffffffffu) {  // the whole warp sits in one class (the usual case on label maps)
-                acc = v[u];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            } else {                 // lanes of a class summed in lane order
-                acc = 0.f;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float o = __shfl_sync(0xffffffffu, v[u], j);
-                    if ((m >> j) & 1u) acc += o;
+            for (int q = 0; q < 8; ++q) {
+                const int r = 4 * q + sr, c = c0 + r;
+                float* d = &v[4 * q];
+                d[0] = d[1] = d[2] = d[3] = 0.f;
+                if (in) {
+                    if (c < C) load4(feat + (size_t)r * HW + q0, d);
+                    else if (c == C) {
+                        if (WEIGHTED) load4(a1 + q0, d);
+                        else d[0] = d[1] = d[2] = d[3] = 1.f;
+                    }
                 }
             }
-            if (lane == __ffs(m) - 1) my[k[u]] += acc;
-            __syncwarp();
+        } else {
+            const bool in = px < HW;
+            if (WEIGHTED) w[0] = in ? __ldg(a0 + px) : 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const int c = c0 + r;
+                v[r] = 0.f;
+                if (in) {
+                    if (c < C) v[r] = Elem<T>::load(feat + (size_t)r * HW + px);
+                    else if (c == C) v[r] = WEIGHTED ? __ldg(a1 + px) : 1.f;
+                }
+            }
         }
+    };
+    if (s0 < s1) load_step(s0);
+    __syncwarp();
+    for (int st = s0; st < s1; ++st) {
+        if (VEC) {  // bank = (row + pixel) % 32 = (4q + sr + px4 + e) % 32: distinct over the warp
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int r = 4 * q + sr;
+                const bool scale = WEIGHTED && c0 + r < C;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) tile[r * kTilePitch + px4 + e] = scale ? w[e] * v[4 * q + e] : v[4 * q + e];
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) tile[r * kTilePitch + lane] = (WEIGHTED && c0 + r < C) ? w[0] * v[r] : v[r];
+        }
+        const int kcur = kreg;
+        __syncwarp();
+        if (st + 1 < s1) load_step(st + 1);
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = tile[lane * kTilePitch + j];
+        // bit j: pixel j starts a new run (its class differs from its predecessor's)
+        const int kprev = __shfl_up_sync(0xffffffffu, kcur, 1);
+        const unsigned chg = __ballot_sync(0xffffffffu, lane == 0 ? kcur != cur : kcur != kprev);
+        if (chg == 0u) {  // the whole step continues the current run (the usual case on label maps)
+            float t[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t[q] = (x[4 * q] + x[4 * q + 1]) + (x[4 * q + 2] + x[4 * q + 3]);
+            acc += ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if ((chg >> j) & 1u) {  // warp-uniform
+                    bins[cur * 32 + lane] += acc;
+                    acc = 0.f;
+                    cur = __shfl_sync(0xffffffffu, kcur, j);
+                }
+                acc += x[j];
+            }
+        }
+        __syncwarp();
     }
+    bins[cur * 32 + lane] += acc;
+    __syncthreads();
 
-    float* out = (WEIGHTED ? p.wsum : p.sums + (second ? (size_t)p.B * K1 * K1 : 0)) + ((size_t)b * K1 + c) * K1;
-    for (int k = lane; k < K1; k += 32) out[k] = my[k];
+    // warps summed in order; out[(tensor, b)][k][c]: one contiguous row of channels per class
+    float* out = (p.splits > 1 ? p.spart + (size_t)split * (WEIGHTED ? 1 : 2) * p.B * K1 * K1 : (WEIGHTED ? p.wsum : p.sums)) +
+                 ((size_t)(second ? p.B : 0) + b) * K1 * K1;
+    const float* all = smem_f;
+    for (int i = threadIdx.x; i < 32 * K1; i += kIfvdWarps * 32) {
+        const int k = i >> 5, ch = i & 31;
+        if (c0 + ch > C) continue;
+        float a = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < kIfvdWarps; ++wv) a += all[((size_t)wv * K1 + k) * 32 + ch];
+        out[(size_t)k * K1 + c0 + ch] = a;
+    }
+}
+
+// pixel ranges summed in order (only launched when splits > 1)
+__global__ void __launch_bounds__(256) ifvd_combine_kernel(const float* spart, float* out, long long n, int splits) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    float a = 0.f;
+    for (int s = 0; s < splits; ++s) a += spart[(size_t)s * n + i];
+    out[i] = a;
 }
 
 // ------------------------------------------------------------------------------------------------
 // per pixel: sim_S, sim_T, loss partial, backward coefficients
 //   pix[0] = g/|f|   pix[1] = g*sim_S   pix[2] = g*sim_S/|f|^2 (0 when |f| is clamped)   pix[3] = max(|centre|, eps)
+// CTA = 32 pixels (threadIdx.x, coalesced) x kIfvdSlices channel slices (threadIdx.y): the sweep over the channels is
+// split so that the two-sample batches the reference trains on still fill the GPU; slices are merged in order.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kIfvdPixThreads) ifvd_sim_kernel(const IfvdParams p) {
-    __shared__ float red[kIfvdPixThreads / 32];
+__global__ void __launch_bounds__(kIfvdPixThreads* kIfvdSlices) ifvd_sim_kernel(const IfvdParams p) {
+    __shared__ float red[kIfvdSlices][6][kIfvdPixThreads];
     const int b = blockIdx.y;
-    const int px = blockIdx.x * kIfvdPixThreads + threadIdx.x;
+    const int lane = threadIdx.x, slice = threadIdx.y;
+    const int px = blockIdx.x * kIfvdPixThreads + lane;
     const int C = p.C, HW = p.HW, K1 = C + 1;
-    float d2 = 0.f;
-    if (px < HW) {
-        const int k = __ldg(p.cls + (size_t)b * HW + px);
+    const int cps = (C + kIfvdSlices - 1) / kIfvdSlices;
+    const int cbeg = slice * cps, cend = min(C, cbeg + cps);
+    const bool in = px < HW;
+    const int k = in ? __ldg(p.cls + (size_t)b * HW + px) : C;
+    float dots = 0.f, fs2 = 0.f, cs2 = 0.f, dott = 0.f, ft2 = 0.f, ct2 = 0.f;
+    if (in) {
         const T* s = static_cast<const T*>(p.S) + (size_t)b * C * HW + px;
         const T* t = static_cast<const T*>(p.T) + (size_t)b * C * HW + px;
-        float dots = 0.f, fs2 = 0.f, cs2 = 0.f, dott = 0.f, ft2 = 0.f, ct2 = 0.f, inv_n = 1.f;
         if (k < C) {
-            const float* zs = p.sums + (size_t)b * K1 * K1 + k;
+            const float* zs = p.sums + ((size_t)b * K1 + k) * K1;   // the class's row: C channel sums, then the count
             const float* zt = zs + (size_t)p.B * K1 * K1;
-#pragma unroll 5
-            for (int c = 0; c < C; ++c) {
+#pragma unroll 4
+            for (int c = cbeg; c < cend; ++c) {
                 const float fs = Elem<T>::load(s + (size_t)c * HW), ft = Elem<T>::load(t + (size_t)c * HW);
-                const float cs = __ldg(zs + (size_t)c * K1), ct = __ldg(zt + (size_t)c * K1);
+                const float cs = __ldg(zs + c), ct = __ldg(zt + c);
                 dots = fmaf(fs, cs, dots); fs2 = fmaf(fs, fs, fs2); cs2 = fmaf(cs, cs, cs2);
                 dott = fmaf(ft, ct, dott); ft2 = fmaf(ft, ft, ft2); ct2 = fmaf(ct, ct, ct2);
             }
-            inv_n = 1.f / (__ldg(zs + (size_t)C * K1) + kCentreEps);
         } else {  // no class: the pixel is its own centre
-#pragma unroll 5
-            for (int c = 0; c < C; ++c) {
+#pragma unroll 4
+            for (int c = cbeg; c < cend; ++c) {
                 const float fs = Elem<T>::load(s + (size_t)c * HW), ft = Elem<T>::load(t + (size_t)c * HW);
                 fs2 = fmaf(fs, fs, fs2);
                 ft2 = fmaf(ft, ft, ft2);
@@ -138,6 +239,20 @@ __global__ void __launch_bounds__(kIfvdPixThreads) ifvd_sim_kernel(const IfvdPar
             dots = cs2 = fs2;
             dott = ct2 = ft2;
         }
+    }
+    red[slice][0][lane] = dots; red[slice][1][lane] = fs2; red[slice][2][lane] = cs2;
+    red[slice][3][lane] = dott; red[slice][4][lane] = ft2; red[slice][5][lane] = ct2;
+    __syncthreads();
+    if (slice != 0) return;
+    float d2 = 0.f;
+    if (in) {
+        dots = fs2 = cs2 = dott = ft2 = ct2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < kIfvdSlices; ++q) {
+            dots += red[q][0][lane]; fs2 += red[q][1][lane]; cs2 += red[q][2][lane];
+            dott += red[q][3][lane]; ft2 += red[q][4][lane]; ct2 += red[q][5][lane];
+        }
+        const float inv_n = k < C ? 1.f / (__ldg(p.sums + ((size_t)b * K1 + k) * K1 + C) + kCentreEps) : 1.f;
         const float nfs_raw = sqrtf(fs2), nft = fmaxf(sqrtf(ft2), kCosEps);
         const float nfs = fmaxf(nfs_raw, kCosEps);
         const float ncs = fmaxf(sqrtf(cs2) * inv_n, kCosEps), nct = fmaxf(sqrtf(ct2) * inv_n, kCosEps);
@@ -154,44 +269,39 @@ __global__ void __launch_bounds__(kIfvdPixThreads) ifvd_sim_kernel(const IfvdPar
         p.pix[3 * n + o] = ncs;
     }
     d2 = warp_sum(d2);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d2;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float a = 0.f;
-#pragma unroll
-        for (int w = 0; w < kIfvdPixThreads / 32; ++w) a += red[w];
-        p.part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = a;
-    }
+    if (lane == 0) p.part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = d2;
 }
 
 // ------------------------------------------------------------------------------------------------
-// gradient
+// gradient (same CTA shape; every slice writes its own channels)
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kIfvdPixThreads) ifvd_grad_kernel(const IfvdParams p) {
+__global__ void __launch_bounds__(kIfvdPixThreads* kIfvdSlices) ifvd_grad_kernel(const IfvdParams p) {
     const int b = blockIdx.y;
     const int px = blockIdx.x * kIfvdPixThreads + threadIdx.x;
     const int C = p.C, HW = p.HW, K1 = C + 1;
+    const int cps = (C + kIfvdSlices - 1) / kIfvdSlices;
+    const int cbeg = threadIdx.y * cps, cend = min(C, cbeg + cps);
     if (px >= HW) return;
     const int k = __ldg(p.cls + (size_t)b * HW + px);
     const T* s = static_cast<const T*>(p.S) + (size_t)b * C * HW + px;
     T* out = static_cast<T*>(p.dS) + (size_t)b * C * HW + px;
     if (k >= C) {
-        for (int c = 0; c < C; ++c) Elem<T>::store(out + (size_t)c * HW, 0.f);
+        for (int c = cbeg; c < cend; ++c) Elem<T>::store(out + (size_t)c * HW, 0.f);
         return;
     }
     const size_t o = (size_t)b * HW + px, n = (size_t)p.B * HW;
     const float a0 = p.pix[o], a2 = p.pix[2 * n + o], nc = p.pix[3 * n + o];
-    const float* zs = p.sums + (size_t)b * K1 * K1 + k;
-    const float* us = p.wsum + (size_t)b * K1 * K1 + k;
-    const float inv_n = 1.f / (__ldg(zs + (size_t)C * K1) + kCentreEps);
+    const float* zs = p.sums + ((size_t)b * K1 + k) * K1;
+    const float* us = p.wsum + ((size_t)b * K1 + k) * K1;
+    const float inv_n = 1.f / (__ldg(zs + C) + kCentreEps);
     const float cp = inv_n / nc;                                    // d centre^ / d sum
-    const float dp = nc > kCosEps ? __ldg(us + (size_t)C * K1) * cp * cp : 0.f;
+    const float dp = nc > kCosEps ? __ldg(us + C) * cp * cp : 0.f;
     const float ks = a0 * cp - dp;
-#pragma unroll 5
-    for (int c = 0; c < C; ++c) {
+#pragma unroll 4
+    for (int c = cbeg; c < cend; ++c) {
         const float f = Elem<T>::load(s + (size_t)c * HW);
-        const float z = __ldg(zs + (size_t)c * K1), u = __ldg(us + (size_t)c * K1);
+        const float z = __ldg(zs + c), u = __ldg(us + c);
         Elem<T>::store(out + (size_t)c * HW, fmaf(ks, z, fmaf(cp, u, -a2 * f)));
     }
 }
@@ -214,16 +324,31 @@ __global__ void __launch_bounds__(256) ifvd_finalize_kernel(const float* part, i
 template <typename T>
 static cudaError_t launch_ifvd_t(const IfvdParams& p, float loss_scale, cudaStream_t stream) {
     const int K1 = p.C + 1;
-    const size_t bins = (size_t)kIfvdWarps * K1 * sizeof(float);
-    const dim3 gsum((K1 + kIfvdWarps - 1) / kIfvdWarps, p.B, 2), gwsum(gsum.x, p.B, 1);
+    const size_t smem = (size_t)kIfvdWarps * (K1 * 32 + 32 * kTilePitch) * sizeof(float);
+    const bool vec = p.vec != 0;
+    auto sums = vec ? ifvd_class_sums_kernel<T, false, true> : ifvd_class_sums_kernel<T, false, false>;
+    auto wsums = vec ? ifvd_class_sums_kernel<T, true, true> : ifvd_class_sums_kernel<T, true, false>;
+    cudaError_t e = cudaFuncSetAttribute(sums, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wsums, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    const int groups = (K1 + 31) / 32;
+    const dim3 gsum(p.splits, groups, 2 * p.B), gwsum(p.splits, groups, p.B);
     const dim3 gpix((p.HW + kIfvdPixThreads - 1) / kIfvdPixThreads, p.B, 1);
-    ifvd_class_sums_kernel<T, false><<<gsum, kIfvdWarps * 32, bins, stream>>>(p);
-    ifvd_sim_kernel<T><<<gpix, kIfvdPixThreads, 0, stream>>>(p);
-    ifvd_class_sums_kernel<T, true><<<gwsum, kIfvdWarps * 32, bins, stream>>>(p);
-    ifvd_grad_kernel<T><<<gpix, kIfvdPixThreads, 0, stream>>>(p);
+    const long long plane = (long long)p.B * K1 * K1;
+    sums<<<gsum, kIfvdWarps * 32, smem, stream>>>(p);
+    if (p.splits > 1)
+        ifvd_combine_kernel<<<(unsigned)((2 * plane + 255) / 256), 256, 0, stream>>>(p.spart, p.sums, 2 * plane, p.splits);
+    ifvd_sim_kernel<T><<<gpix, dim3(kIfvdPixThreads, kIfvdSlices), 0, stream>>>(p);
+    wsums<<<gwsum, kIfvdWarps * 32, smem, stream>>>(p);
+    if (p.splits > 1)
+        ifvd_combine_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, stream>>>(p.spart, p.wsum, plane, p.splits);
+    ifvd_grad_kernel<T><<<gpix, dim3(kIfvdPixThreads, kIfvdSlices), 0, stream>>>(p);
     ifvd_finalize_kernel<<<1, 256, 0, stream>>>(p.part, (int)(gpix.x * gpix.y), loss_scale, p.loss);
     return cudaGetLastError();
 }
+
+// class-sum bins (C+1 classes x 32 channels per warp) must fit the CTA's shared memory
+int ifvd_max_channels() { return (int)((227 * 1024 / sizeof(float) / kIfvdWarps - 32 * kTilePitch) / 32) - 1; }
 
 int ifvd_pix_threads() { return kIfvdPixThreads; }
 

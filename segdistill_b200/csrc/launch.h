@@ -48,5 +48,6 @@ cudaError_t launch_scale_grad2(void* dS, long long n, bool bf16, const float* g0
 // ifvd.cu
 cudaError_t launch_ifvd_sim(const IfvdParams& p, bool bf16, float loss_scale, cudaStream_t stream);
 int ifvd_pix_threads();
+int ifvd_max_channels();
 
 }  // namespace sd

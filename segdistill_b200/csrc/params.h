@@ -220,26 +220,45 @@ struct IfvdParams {
     const int* cls;     // (B, HW) class of each pixel in [0, C), or C for "no class"
     void* dS;
     float* loss;
-    float* sums;        // [2][B][C+1][C+1] class sums of S, of T; row C = class counts
-    float* wsum;        // [B][C+1][C+1]    gradient reaching the class sums of S; row C = V_k
+    float* sums;        // [2][B][C+1 classes][C+1] class sums of S, of T: a row of C channel sums + the class count
+    float* wsum;        // [B][C+1 classes][C+1]    gradient reaching the class sums of S: C channels + V_k
     float* pix;         // [4][B][HW]       per-pixel backward coefficients
     float* part;        // one loss partial per CTA of the per-pixel kernel
+    float* spart;       // [splits][2][B][C+1][C+1] class sums per pixel range (splits > 1)
     int B, C, HW;
+    int splits;         // pixel ranges (CTAs) per (sample, 32 channels) of the class-sum kernels
+    int vec;            // HW % 4 == 0 and S, T 16-byte aligned: 4-pixel loads
     float gcoef;        // grad_scale * 2 * weight / (B*HW)
 };
 struct IfvdWorkspace {
-    size_t off_sums, off_wsum, off_pix, off_part, bytes;
+    size_t off_sums, off_wsum, off_pix, off_part, off_spart, bytes;
     long long nparts;
+    int splits;
 };
+// the class-sum CTAs own a whole SM (their bins fill its shared memory): at least four waves of a 148-SM part so that
+// the last, partial wave costs little, but no less than 8 warps x 2 steps of 32 pixels per CTA; a function of the
+// shape only, so that sd_ifvd_sim_workspace_bytes and the launch agree
+inline int ifvd_splits(long long B, long long C, long long HW) {
+    const long long groups = (C + 1 + 31) / 32;
+    const long long ctas = 2 * B * groups;
+    long long s = (592 + ctas - 1) / ctas;
+    const long long most = (HW + 511) / 512;
+    if (s > most) s = most;
+    if (s > 32) s = 32;
+    return s < 1 ? 1 : (int)s;
+}
 inline IfvdWorkspace ifvd_workspace_layout(long long B, long long C, long long HW, long long pix_threads) {
     IfvdWorkspace w;
     const size_t K1 = (size_t)C + 1;
     size_t o = kArenaBytes;
-    w.off_sums = o;  o += sizeof(float) * 2 * (size_t)B * K1 * K1;
-    w.off_wsum = o;  o += sizeof(float) * (size_t)B * K1 * K1;
-    w.off_pix = o;   o += sizeof(float) * 4 * (size_t)B * (size_t)HW;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    w.off_sums = o;  o = up(o + sizeof(float) * 2 * (size_t)B * K1 * K1);
+    w.off_wsum = o;  o = up(o + sizeof(float) * (size_t)B * K1 * K1);
+    w.off_pix = o;   o = up(o + sizeof(float) * 4 * (size_t)B * (size_t)HW);   // 16-byte aligned: read as float4
     w.nparts = B * ((HW + pix_threads - 1) / pix_threads);
     w.off_part = o;  o += sizeof(float) * (size_t)w.nparts;
+    w.splits = ifvd_splits(B, C, HW);
+    w.off_spart = o; o += w.splits > 1 ? sizeof(float) * 2 * (size_t)w.splits * (size_t)B * K1 * K1 : 0;
     w.bytes = (o + 255) & ~(size_t)255;
     return w;
 }
