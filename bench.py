@@ -566,6 +566,17 @@ def extra_configs(dev):
         rec['upsampled_gelem_s'] = hi / rec['fused_ms'] / 1e6
         rec['speedup_vs_host_resize'] = rec['host_resize_ms'] / rec['fused_ms']
         out[name] = rec
+    # IFVDLoss on the training shape: logits 2x150x128x128, labels 512x512 in 32-pixel blocks with an ignore band
+    s, t = pair((2, 150, 128, 128), torch.float32)
+    lab = torch.randint(0, 150, (2, 1, 16, 16), device=dev).repeat_interleave(32, 2).repeat_interleave(32, 3)
+    lab[:, :, 100:140, :200] = 255
+    ifvd = sd.IFVDLoss()
+
+    def f_ifvd():
+        s.grad = None
+        ifvd(s, t, lab, 1).backward()
+    eager, ms = timeit(f_ifvd)
+    out['f2_ifvd_2x150x128x128_f32'] = {'ms': ms, 'ms_eager': eager, 'mpixel_s': 2 * 128 * 128 / ms / 1e3}
     # the correlation extension (tensor cores): algorithmic traffic 16 B/element fp32 (S, T read; S read again; dS written)
     for name, g, shape, dtype in (('corr_g10_16x150x128x128_bf16', 10, (16, 150, 128, 128), torch.bfloat16),
                                   ('corr_g10_16x150x128x128_f32', 10, (16, 150, 128, 128), torch.float32),

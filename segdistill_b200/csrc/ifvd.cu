@@ -9,17 +9,20 @@
 //   pixels without a class (label outside [0, C), e.g. ignore index 255) keep their own feature as centre
 //   (sim = 1 for S and for T): no loss, no gradient.
 //
-// Four launches + a finalize, all on tensors that stay in the 126 MB L2 at the sizes the reference trains on:
-//   1. ifvd_class_sums_kernel<false>   class sums of S and T and the class counts - a segmented reduction, one warp per
-//                                      (sample, channel) plane, warp-private shared-memory bins; lanes holding the same
-//                                      class are found with match.any and summed in lane order by the lowest of
-//                                      them, so there are no float atomics and the result is deterministic.
-//                                      (Cosine similarity is scale-invariant: the sums are used, the division by
-//                                      n_k + 1e-6 appears only in the eps clamp and in the gradient.)
-//   2. ifvd_sim_kernel                 one thread per pixel: both similarities in one sweep over the channels,
-//                                      (sim_S - sim_T)^2 partials, per-pixel backward coefficients.
-//   3. ifvd_class_sums_kernel<true>    the gradient reaching each centre: U_k = sum_{p in k} g_p * S[:, p]/|S[:, p]|,
-//                                      V_k = sum_{p in k} g_p * sim_S(p)   (same segmented reduction, weighted).
+// Launches (all on tensors that stay in the 126 MB L2 at the sizes the reference trains on):
+//   1. ifvd_class_sums_kernel<plain>   class sums of S and T and the class counts - a segmented reduction with
+//                                      lane = channel: a warp walks its pixels one by one, the class of a pixel is
+//                                      warp-uniform, a run of pixels of one class is summed in a register and then
+//                                      added to the lane's private shared-memory bin.  No atomics, no shuffle
+//                                      reductions, fixed summation order -> deterministic.  (Cosine similarity is
+//                                      scale-invariant: the sums are used, the division by n_k + 1e-6 appears only in
+//                                      the eps clamp and in the gradient.)
+//      ifvd_combine_kernel             when the pixels of a sample are spread over several CTAs: their partial
+//                                      sums added in CTA order.
+//   2. ifvd_sim_kernel                 per pixel: both similarities in one sweep over the channels (8 channel slices
+//                                      per pixel), (sim_S - sim_T)^2 partials, per-pixel backward coefficients.
+//   3. ifvd_class_sums_kernel<weighted> (+ combine)  the gradient reaching each centre:
+//                                      U_k = sum_{p in k} g_p * S[:, p]/|S[:, p]|,  V_k = sum_{p in k} g_p * sim_S(p).
 //   4. ifvd_grad_kernel                dS[:, p] = g_p*(c^/|f| - sim*f/|f|^2) + (U_k/|c| - V_k*c/|c|^2)/(n_k + 1e-6)
 //   5. ifvd_finalize_kernel            loss partials summed in a fixed order (fp64).
 //
