@@ -6,6 +6,7 @@ the reference's loss-module / dispatcher interface (``losses``, ``opts``, ``dist
 """
 from .losses import (ATLoss, CDLoss, CDMSELoss, CGDCorrLoss, CGDLoss, CGDLossWS, FeatureMSELoss, IFVDLoss,  # noqa: F401
                      KLDLoss, PDLoss)
-from .opts import DistillationLoss, Extractor, LOSS_CLASSES, build_criterion  # noqa: F401
+from .opts import (DistillationLoss, DistillationLossMT, Extractor, ExtractorMT, LOSS_CLASSES,  # noqa: F401
+                   build_criterion)
 
 __version__ = '0.1.0'

@@ -109,6 +109,36 @@ def test_extractor_records_only_in_training_mode():
     assert ex.student_features == {}
 
 
+def test_multi_teacher_dispatcher_pairs_entry_i_with_teacher_i():
+    """opts.py:127-210: teacher i's hooked layer is recorded as name+str(i); entry i is computed against it and
+    named loss_{student}<->{teacher}{i}_{i}; a mismatching number of teacher maps goes to `loss_random`."""
+    import torch.nn as nn
+    stu = nn.Sequential(nn.Conv2d(3, 4, 1), nn.Conv2d(4, 5, 1))
+    teachers = [nn.Sequential(nn.Conv2d(3, 4, 1), nn.Conv2d(4, 5, 1)) for _ in range(2)]
+    cfg = [{'student_layer': '1', 'teacher_layer': '1', 'loss_name': 'KLDLoss', 'loss_config': {'alpha': 0}}
+           for _ in range(2)]
+    ex = sd.ExtractorMT(stu, teachers, cfg)
+    ex.train()
+    x = torch.randn(1, 3, 4, 4)
+    stu(x)
+    for t in teachers:
+        t(x)
+    assert sorted(ex.teacher_features) == ['10', '11'] and list(ex.student_features) == ['1']
+    d = sd.DistillationLossMT(cfg)
+    out = d(ex.student_features, ex.teacher_features, None, 0)          # alpha 0 -> no kernel needed on CPU
+    assert list(out) == ['loss_1<->10_0', 'loss_1<->11_1']
+    seen = {}
+
+    class Spy(nn.Module):
+        def forward(self, s, t, gt, step):
+            seen['teacher'] = t
+            return s.sum() * 0
+
+    cfg[0]['criterion'] = Spy()
+    out = d(ex.student_features, {'10': ex.teacher_features['10']}, None, 0)
+    assert list(out) == ['loss_random'] and isinstance(seen['teacher'], list) and len(seen['teacher']) == 1
+
+
 def test_shard_bounds_cover_the_batch():
     for batch, world in ((128, 8), (16, 2), (7, 4), (3, 8)):
         pieces = [sdist.shard_bounds(batch, r, world) for r in range(world)]
