@@ -235,13 +235,13 @@ struct IfvdWorkspace {
     long long nparts;
     int splits;
 };
-// the class-sum CTAs own a whole SM (their bins fill its shared memory): at least four waves of a 148-SM part so that
-// the last, partial wave costs little, but no less than 8 warps x 2 steps of 32 pixels per CTA; a function of the
-// shape only, so that sd_ifvd_sim_workspace_bytes and the launch agree
+// the class-sum CTAs own a whole SM (their bins fill its shared memory): as many pixel ranges as keep the plain launch
+// (S and T) within four waves of a 148-SM part, but no less than 8 warps x 2 steps of 32 pixels per CTA; a function
+// of the shape only, so that sd_ifvd_sim_workspace_bytes and the launch agree
 inline int ifvd_splits(long long B, long long C, long long HW) {
     const long long groups = (C + 1 + 31) / 32;
     const long long ctas = 2 * B * groups;
-    long long s = (592 + ctas - 1) / ctas;
+    long long s = 592 / ctas;
     const long long most = (HW + 511) / 512;
     if (s > most) s = most;
     if (s > 32) s = 32;
