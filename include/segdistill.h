@@ -199,11 +199,19 @@ SD_API int sd_mse_fwd_bwd(const void* S, const void* T, void* dS, float* loss,
  *   *loss = weight * mean_{b,p} (sim_S - sim_T)^2;  dS = grad_scale * d loss / d S, including the path through the
  *   class centres.  cls: int32 (B, HW), class index in [0, C) or C for pixels without a class (they keep their own
  *   feature as centre: sim = 1, zero gradient).  Deterministic (no float atomics).
+ *   accumulate != 0: dS += the gradient (dS already holds the gradient of the per-pixel KL term of the same loss,
+ *   written by sd_kl_pixels_fwd_bwd with the same grad_scale).
  */
 SD_API size_t sd_ifvd_sim_workspace_bytes(int B, int C, int HW);
 SD_API int sd_ifvd_sim_fwd_bwd(const void* S, const void* T, const int32_t* cls, void* dS, float* loss,
-                        int B, int C, int HW, int dtype, float weight, float grad_scale,
+                        int B, int C, int HW, int dtype, float weight, float grad_scale, int accumulate,
                         void* workspace, size_t workspace_bytes, void* stream);
+/*
+ * losses.py:218-224: cls[b, y, x] = the label at the nearest-resized position (nn.Upsample(size=(h, w),
+ * mode='nearest') of target (B, 1, Ht, Wt), int64) if it is one of the class indices 0..C-1, else C.
+ */
+SD_API int sd_ifvd_class_map(const int64_t* target, int32_t* cls, int B, int Ht, int Wt, int h, int w, int C,
+                      void* stream);
 
 /* ------------------------------------------------------------------ backward helper */
 /* dS *= *grad_output (a device scalar); exits without touching dS when it equals 1. */

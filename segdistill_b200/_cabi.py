@@ -29,7 +29,7 @@ EXPORTS = (
     'sd_kl_rows_workspace_bytes', 'sd_kl_rows_fwd_bwd', 'sd_kl_rows_multi_fwd_bwd', 'sd_scale_grad2',
     'sd_kl_pixels_workspace_bytes', 'sd_kl_pixels_fwd_bwd',
     'sd_kl_rows_up_workspace_bytes', 'sd_kl_rows_up_fwd_bwd', 'sd_kl_pixels_up_workspace_bytes', 'sd_kl_pixels_up_fwd_bwd',
-    'sd_mse_workspace_bytes', 'sd_mse_fwd_bwd', 'sd_ifvd_sim_workspace_bytes', 'sd_ifvd_sim_fwd_bwd', 'sd_scale_grad',
+    'sd_mse_workspace_bytes', 'sd_mse_fwd_bwd', 'sd_ifvd_sim_workspace_bytes', 'sd_ifvd_sim_fwd_bwd', 'sd_ifvd_class_map', 'sd_scale_grad',
     'sd_cgd_corr_workspace_bytes', 'sd_cgd_corr_fwd_bwd',
     'sd_launch_count', 'sd_last_kernel',
 )
@@ -96,7 +96,9 @@ def load():
         lib.sd_ifvd_sim_workspace_bytes.restype = sz
         lib.sd_ifvd_sim_workspace_bytes.argtypes = [i32, i32, i32]
         lib.sd_ifvd_sim_fwd_bwd.restype = i32
-        lib.sd_ifvd_sim_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, sz, vp]
+        lib.sd_ifvd_sim_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, i32, vp, sz, vp]
+        lib.sd_ifvd_class_map.restype = i32
+        lib.sd_ifvd_class_map.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
         lib.sd_scale_grad.restype = i32
         lib.sd_scale_grad.argtypes = [vp, i64, i32, vp, vp]
         lib.sd_cgd_corr_workspace_bytes.restype = sz
@@ -408,9 +410,10 @@ def mse(x_student, x_teacher, weight=1.0, grad_scale=1.0):
     return out[0], ds
 
 
-def ifvd_sim(x_student, x_teacher, cls, weight=10.0, grad_scale=1.0):
+def ifvd_sim(x_student, x_teacher, cls, weight=10.0, grad_scale=1.0, ds=None):
     """IFVDLoss similarity term: ``weight * mean((cos(s, centre_s) - cos(t, centre_t))^2)``; ``cls`` is the (B, H*W)
-    class index of every pixel, ``C`` meaning "no class". Returns (loss, dS)."""
+    class index of every pixel, ``C`` meaning "no class". Returns (loss, dS); with ``ds`` given (the gradient of
+    another loss on the same student map, same dtype and shape) the gradient is added to it in place."""
     lib = load()
     s, t, code = _prep_pair(x_student, x_teacher)
     B, C = s.shape[0], s.shape[1]
@@ -418,16 +421,36 @@ def ifvd_sim(x_student, x_teacher, cls, weight=10.0, grad_scale=1.0):
     dev = s.device
     if cls.device != dev or cls.numel() != B * HW:
         raise SegDistillError(f'class map must hold B*H*W = {B * HW} entries on {dev}')
+    if ds is not None and (ds.shape != s.shape or ds.dtype != s.dtype or not ds.is_contiguous()):
+        raise SegDistillError('ds must be a contiguous tensor of the (converted) student map\'s shape and dtype')
     with _on(dev):
         k = cls.reshape(B, HW).to(torch.int32).contiguous()
-        ds = torch.empty_like(s)
+        acc = ds is not None
+        if ds is None:
+            ds = torch.empty_like(s)
         out = torch.empty(1, dtype=torch.float32, device=dev)
         ws = _workspace(dev, lib.sd_ifvd_sim_workspace_bytes(B, C, HW))
         rc = lib.sd_ifvd_sim_fwd_bwd(s.data_ptr(), t.data_ptr(), k.data_ptr(), ds.data_ptr(), out.data_ptr(), B, C, HW,
-                                     code, float(weight), float(grad_scale), ws.data_ptr(), ws.numel(),
+                                     code, float(weight), float(grad_scale), int(acc), ws.data_ptr(), ws.numel(),
                                      _stream_ptr(dev))
         _check(rc)
     return out[0], ds
+
+
+def ifvd_class_map(target, n_classes, h, w):
+    """(B, h*w) int32 class of every pixel from an integer label map (B, 1, Ht, Wt): nearest-resized to (h, w),
+    labels outside [0, n_classes) -> n_classes."""
+    lib = load()
+    if not target.is_cuda or target.dim() != 4 or target.shape[1] != 1 or target.is_floating_point():
+        raise SegDistillError('label map must be an integer CUDA tensor of shape (B, 1, H, W)')
+    dev = target.device
+    with _on(dev):
+        tg = target.to(torch.int64).contiguous()
+        B, _, Ht, Wt = tg.shape
+        cls = torch.empty(B, h * w, dtype=torch.int32, device=dev)
+        _check(lib.sd_ifvd_class_map(tg.data_ptr(), cls.data_ptr(), B, Ht, Wt, int(h), int(w), int(n_classes),
+                                     _stream_ptr(dev)))
+    return cls
 
 
 def cgd_corr(x_student, x_teacher, group=10, alpha=1.0, grad_scale=1.0):

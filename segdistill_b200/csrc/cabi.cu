@@ -607,9 +607,21 @@ size_t sd_ifvd_sim_workspace_bytes(int B, int C, int HW) {
     return sd::ifvd_workspace_layout(B, C, HW, sd::ifvd_pix_threads()).bytes;
 }
 
+int sd_ifvd_class_map(const int64_t* target, int32_t* cls, int B, int Ht, int Wt, int h, int w, int C, void* stream) {
+    if (!target || !cls) return SD_ERR_NULL;
+    if (B <= 0 || Ht <= 0 || Wt <= 0 || h <= 0 || w <= 0 || C <= 0) return SD_ERR_SHAPE;
+    DeviceInfo& dev = device_info();
+    if (dev.cc_major != 10) return SD_ERR_DEVICE;
+    cudaError_t e = sd::launch_ifvd_class_map(reinterpret_cast<const long long*>(target), cls, B, Ht, Wt, h, w, C,
+                                              static_cast<cudaStream_t>(stream));
+    g_launches += 1;
+    t_last_kernel = "ifvd_class_map_kernel";
+    return e == cudaSuccess ? SD_OK : (int)e;
+}
+
 int sd_ifvd_sim_fwd_bwd(const void* S, const void* T, const int32_t* cls, void* dS, float* loss, int B, int C, int HW,
-                        int dtype, float weight, float grad_scale, void* workspace, size_t workspace_bytes,
-                        void* stream) {
+                        int dtype, float weight, float grad_scale, int accumulate, void* workspace,
+                        size_t workspace_bytes, void* stream) {
     if (!S || !T || !cls || !dS || !loss || !workspace) return SD_ERR_NULL;
     if (dtype != SD_F32 && dtype != SD_BF16) return SD_ERR_DTYPE;
     if (B <= 0 || C <= 0 || HW <= 0 || B > 32767 || (long long)B * C * HW >= (1ll << 40)) return SD_ERR_SHAPE;
@@ -629,6 +641,7 @@ int sd_ifvd_sim_fwd_bwd(const void* S, const void* T, const int32_t* cls, void* 
     p.spart = reinterpret_cast<float*>(ws + w.off_spart);
     p.B = B; p.C = C; p.HW = HW;
     p.splits = w.splits;
+    p.accumulate = accumulate != 0;
     p.vec = HW % 4 == 0 && aligned16(S) && aligned16(T) && aligned16(workspace);
     const double npix = (double)B * (double)HW;
     p.gcoef = (float)((double)grad_scale * 2.0 * (double)weight / npix);

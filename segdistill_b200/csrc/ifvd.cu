@@ -289,8 +289,10 @@ __global__ void __launch_bounds__(kIfvdPixThreads* kIfvdSlices) ifvd_grad_kernel
     const int k = __ldg(p.cls + (size_t)b * HW + px);
     const T* s = static_cast<const T*>(p.S) + (size_t)b * C * HW + px;
     T* out = static_cast<T*>(p.dS) + (size_t)b * C * HW + px;
+    const bool acc = p.accumulate != 0;   // dS already holds another loss's gradient (IFVDLoss: the per-pixel KL)
     if (k >= C) {
-        for (int c = cbeg; c < cend; ++c) Elem<T>::store(out + (size_t)c * HW, 0.f);
+        if (!acc)
+            for (int c = cbeg; c < cend; ++c) Elem<T>::store(out + (size_t)c * HW, 0.f);
         return;
     }
     const size_t o = (size_t)b * HW + px, n = (size_t)p.B * HW;
@@ -305,8 +307,36 @@ __global__ void __launch_bounds__(kIfvdPixThreads* kIfvdSlices) ifvd_grad_kernel
     for (int c = cbeg; c < cend; ++c) {
         const float f = Elem<T>::load(s + (size_t)c * HW);
         const float z = __ldg(zs + c), u = __ldg(us + c);
-        Elem<T>::store(out + (size_t)c * HW, fmaf(ks, z, fmaf(cp, u, -a2 * f)));
+        const float g = fmaf(ks, z, fmaf(cp, u, -a2 * f));
+        Elem<T>::store(out + (size_t)c * HW, acc ? Elem<T>::load(out + (size_t)c * HW) + g : g);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// class map: losses.py:218-224.  nn.Upsample(size, mode='nearest') of the label map (ATen's nearest index:
+// identity, >> 1 for an exact doubling, else min(floor(dst * in/out), in - 1) in fp32), then the class index where the
+// label equals one of range(C), else C.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nearest_src(int dst, int in, int out, float scale) {
+    if (out == in) return dst;
+    if (out == 2 * in) return dst >> 1;
+    return min((int)floorf((float)dst * scale), in - 1);
+}
+__global__ void __launch_bounds__(256) ifvd_class_map_kernel(const long long* target, int* cls, int B, int Ht, int Wt,
+                                                             int h, int w, int C) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long long)B * h * w) return;
+    const int x = (int)(i % w), y = (int)((i / w) % h), b = (int)(i / ((long long)w * h));
+    const int sy = nearest_src(y, Ht, h, (float)Ht / (float)h), sx = nearest_src(x, Wt, w, (float)Wt / (float)w);
+    const long long lab = target[((size_t)b * Ht + sy) * Wt + sx];
+    cls[i] = lab >= 0 && lab < C ? (int)lab : C;
+}
+
+cudaError_t launch_ifvd_class_map(const long long* target, int* cls, int B, int Ht, int Wt, int h, int w, int C,
+                                  cudaStream_t stream) {
+    const long long n = (long long)B * h * w;
+    ifvd_class_map_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(target, cls, B, Ht, Wt, h, w, C);
+    return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256) ifvd_finalize_kernel(const float* part, int n, float scale, float* loss) {

@@ -47,6 +47,8 @@ cudaError_t launch_scale_grad2(void* dS, long long n, bool bf16, const float* g0
 
 // ifvd.cu
 cudaError_t launch_ifvd_sim(const IfvdParams& p, bool bf16, float loss_scale, cudaStream_t stream);
+cudaError_t launch_ifvd_class_map(const long long* target, int* cls, int B, int Ht, int Wt, int h, int w, int C,
+                                  cudaStream_t stream);
 int ifvd_pix_threads();
 int ifvd_max_channels();
 

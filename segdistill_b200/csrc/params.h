@@ -228,6 +228,7 @@ struct IfvdParams {
     int B, C, HW;
     int splits;         // pixel ranges (CTAs) per (sample, 32 channels) of the class-sum kernels
     int vec;            // HW % 4 == 0 and S, T 16-byte aligned: 4-pixel loads
+    int accumulate;     // dS += gradient instead of dS = gradient
     float gcoef;        // grad_scale * 2 * weight / (B*HW)
 };
 struct IfvdWorkspace {

@@ -174,6 +174,24 @@ class _IFVDSim(torch.autograd.Function):
         return _finish_backward(ctx, grad_output), None, None, None
 
 
+class _IFVD(torch.autograd.Function):
+    """Whole IFVDLoss (losses.py:213-237): the per-pixel KL kernel writes dS, the similarity term adds its gradient
+    to the same buffer - one gradient tensor, one backward node."""
+
+    @staticmethod
+    def forward(ctx, x_student, x_teacher, cls, weight, algo):
+        loss_pd, ds, _, _ = _cabi.kl_pixels(x_student, x_teacher, tau=1.0, alpha=1.0, algo=algo)
+        loss_sim, ds = _cabi.ifvd_sim(x_student, x_teacher, cls, weight=weight, ds=ds)
+        ctx.ds = ds if x_student.requires_grad else None
+        ctx.in_dtype, ctx.in_shape = x_student.dtype, x_student.shape
+        return loss_sim + loss_pd
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        return _finish_backward(ctx, grad_output), None, None, None, None
+
+
 class _CGDCorr(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_student, x_teacher, group, alpha):
@@ -241,6 +259,11 @@ def mse_loss(x_student, x_teacher, weight=1.0):
 def ifvd_sim_loss(x_student, x_teacher, cls, weight=10.0):
     """weight * mean over pixels of (cos(s, centre_s) - cos(t, centre_t))^2, centres per sample and class."""
     return _IFVDSim.apply(x_student, x_teacher, cls, float(weight))
+
+
+def ifvd_loss(x_student, x_teacher, cls, weight=10.0, algo='auto'):
+    """per-pixel KL (tau = alpha = 1) + weight * the class-centre similarity MSE, as one autograd node."""
+    return _IFVD.apply(x_student, x_teacher, cls, float(weight), _cabi.ALGOS[algo])
 
 
 def cgd_corr_loss(x_student, x_teacher, group=10, alpha=1.0):

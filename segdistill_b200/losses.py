@@ -22,6 +22,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _cabi
 from . import functional as SF
 
 __all__ = ['KLDLoss', 'PDLoss', 'CDLoss', 'CGDLoss', 'CGDLossWS', 'ATLoss', 'IFVDLoss',
@@ -264,10 +265,12 @@ class IFVDLoss(nn.Module):
         if feat_t.shape[2:] != feat_s.shape[2:]:
             feat_t = F.interpolate(feat_t, size=feat_s.shape[2:], mode='bilinear', align_corners=False)   # :204-209
         feat_t = feat_t.detach()
-        loss_pd = SF.kl_pixels_loss(feat_s, feat_t, tau=1.0, alpha=1.0, algo=self.algo)                    # :213-215
         b, c, h, w = feat_s.shape
-        cls = self._class_map(target, c, h, w)
-        return SF.ifvd_sim_loss(feat_s, feat_t, cls, 10.0) + loss_pd                                      # :226-237
+        if target.is_cuda and not target.is_floating_point():
+            cls = _cabi.ifvd_class_map(target, c, h, w)                                                    # :218-224
+        else:
+            cls = self._class_map(target, c, h, w).to(feat_s.device)
+        return SF.ifvd_loss(feat_s, feat_t, cls, 10.0, algo=self.algo)                                    # :213-237
 
 
 class FeatureMSELoss(nn.Module):

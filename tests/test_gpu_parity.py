@@ -778,6 +778,20 @@ def test_ifvd_similarity_term_bf16_and_upstream_scale():
                   grad_rtol=BF16_GRAD_RTOL)
 
 
+@pytest.mark.parametrize('label_hw,feat_hw', [((64, 64), (64, 64)), ((32, 24), (64, 48)), ((512, 512), (128, 128)),
+                                              ((50, 70), (33, 47)), ((20, 30), (33, 47))])
+def test_ifvd_class_map_kernel_equals_the_torch_restatement(label_hw, feat_hw):
+    """sd_ifvd_class_map vs nn.Upsample(nearest) + the class masks (losses.py:218-224): identity, exact doubling,
+    4x down, odd ratios both ways; labels outside range(C) (255, negative) -> C."""
+    g = torch.Generator().manual_seed(81)
+    target = torch.randint(-1, 23, (3, 1) + label_hw, generator=g)
+    target[0, 0, : label_hw[0] // 3] = 255
+    want = sd.IFVDLoss._class_map(target, 19, *feat_hw)
+    got = _cabi.ifvd_class_map(target.to(dev()), 19, *feat_hw)
+    assert got.dtype == torch.int32 and torch.equal(got.cpu(), want)
+    assert int((want == 19).sum()) > 0
+
+
 def test_ifvd_module_on_the_training_shape():
     """IFVDLoss on logits 2x150x128x128 with labels at 512x512 (the exp_tab5 *_IFVD situation) vs the oracle loop."""
     s, t = seeded_pair((2, 150, 128, 128), seed=75, scale=2.0)
@@ -789,8 +803,8 @@ def test_ifvd_module_on_the_training_shape():
     x = s.to(dev()).requires_grad_(True)
     before = _cabi.launch_count()
     loss = sd.IFVDLoss()(x, t.to(dev()), target.to(dev()), 0)
-    assert _cabi.launch_count() - before == 8          # one pixel-KL kernel + seven of the similarity term (class sums
-                                                       # over several pixel ranges + their fixed-order combine, twice)
+    assert _cabi.launch_count() - before == 9          # class map, one pixel-KL kernel, seven of the similarity term
+                                                       # (class sums over several pixel ranges + their combine, twice)
     loss.backward()
     _assert_close(loss.item(), x.grad.cpu(), ref.item(), xr.grad)
 
