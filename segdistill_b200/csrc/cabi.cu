@@ -642,7 +642,7 @@ int sd_ifvd_sim_fwd_bwd(const void* S, const void* T, const int32_t* cls, void* 
     p.B = B; p.C = C; p.HW = HW;
     p.splits = w.splits;
     p.accumulate = accumulate != 0;
-    p.vec = HW % 4 == 0 && aligned16(S) && aligned16(T) && aligned16(workspace);
+    p.vec = HW % (16 / elem_size(dtype)) == 0 && aligned16(S) && aligned16(T) && aligned16(workspace);
     const double npix = (double)B * (double)HW;
     p.gcoef = (float)((double)grad_scale * 2.0 * (double)weight / npix);
     cudaError_t e = sd::launch_ifvd_sim(p, dtype == SD_BF16, (float)((double)weight / npix),

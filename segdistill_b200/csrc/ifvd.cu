@@ -28,6 +28,8 @@
 //
 // eps handling follows ATen's cosine_similarity (x / max(|x|, 1e-8) for both arguments), including the zero
 // gradient through a clamped norm.
+#include <type_traits>
+
 #include "common.cuh"
 #include "launch.h"
 #include "params.h"
@@ -52,22 +54,33 @@ constexpr float kCentreEps = 1e-6f;    // losses.py:229-230
 // the bin.  No match/shuffle reductions, no atomics; every (channel, class) sum has a fixed order: pixels in order
 // inside a warp, warps in order inside a CTA, CTAs (`splits` pixel ranges) in order in ifvd_combine_kernel.
 // ------------------------------------------------------------------------------------------------
-constexpr int kTilePitch = 33;
+constexpr int kTileMaxPitch = 65;   // 64 pixel columns (bf16, 16-byte loads) + 1
 
-__device__ __forceinline__ void load4(const float* p, float* f) {
-    const float4 v = *reinterpret_cast<const float4*>(p);
-    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+template <int N>
+__device__ __forceinline__ void load_vec(const float* p, float* f) {   // N floats, 16-byte aligned
+#pragma unroll
+    for (int i = 0; i < N; i += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(p + i);
+        f[i] = v.x; f[i + 1] = v.y; f[i + 2] = v.z; f[i + 3] = v.w;
+    }
 }
-__device__ __forceinline__ void load4(const __nv_bfloat16* p, float* f) {
-    const uint2 v = *reinterpret_cast<const uint2*>(p);
-    Elem<__nv_bfloat16>::unpack2(v.x, f[0], f[1]);
-    Elem<__nv_bfloat16>::unpack2(v.y, f[2], f[3]);
+template <int N>
+__device__ __forceinline__ void load_vec(const __nv_bfloat16* p, float* f) {   // 8 bf16, 16-byte aligned
+    static_assert(N == 8, "bf16: one 16-byte load");
+    Elem<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(p), f);
 }
 
-// VEC (HW % 4 == 0): a lane fetches 4 consecutive pixels of a channel per load, a warp-load covers 4 channel rows
+// VEC (HW % EPL == 0, 16-byte aligned tensors): a lane fetches 16 bytes = EPL consecutive pixels of a channel per load,
+// 8 lanes cover a 128-byte piece of a channel row, a warp-load covers 4 channel rows; a step is 8*EPL pixels (32 fp32,
+// 64 bf16 - 64-byte pieces of a row were measured 2x slower per element).  Otherwise: scalar loads, 32 pixels per step.
 template <typename T, bool WEIGHTED, bool VEC>
 __global__ void __launch_bounds__(kIfvdWarps * 32, 1) ifvd_class_sums_kernel(const IfvdParams p) {
-    extern __shared__ float smem_f[];  // bins [kIfvdWarps][K1][32], tiles [kIfvdWarps][32][33]
+    constexpr int EPL = VEC ? 16 / (int)sizeof(T) : 1;   // pixels per lane and row-load
+    constexpr int PXS = VEC ? 8 * EPL : 32;              // pixels per step
+    constexpr int HALVES = PXS / 32;                     // 32-pixel walks per step
+    constexpr int PITCH = PXS + 1;
+    constexpr int NV = VEC ? 8 * EPL : 32;               // staged values per lane and step
+    extern __shared__ float smem_f[];  // bins [kIfvdWarps][K1][32], tiles [kIfvdWarps][32][kTileMaxPitch]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = p.C, HW = p.HW, K1 = C + 1;
     const int split = blockIdx.x, c0 = blockIdx.y * 32;
@@ -75,11 +88,11 @@ __global__ void __launch_bounds__(kIfvdWarps * 32, 1) ifvd_class_sums_kernel(con
     const bool second = !WEIGHTED && (blockIdx.z & 1);
 
     float* bins = smem_f + (size_t)warp * K1 * 32;
-    float* tile = smem_f + (size_t)kIfvdWarps * K1 * 32 + (size_t)warp * 32 * kTilePitch;
+    float* tile = smem_f + (size_t)kIfvdWarps * K1 * 32 + (size_t)warp * 32 * kTileMaxPitch;
     for (int i = lane; i < K1 * 32; i += 32) bins[i] = 0.f;
 
-    // this warp's run of 32-pixel steps
-    const int steps = (HW + 31) / 32;
+    // this warp's run of steps
+    const int steps = (HW + PXS - 1) / PXS;
     const int per_cta = (steps + p.splits - 1) / p.splits;
     const int per_warp = (per_cta + kIfvdWarps - 1) / kIfvdWarps;
     const int s0 = split * per_cta + warp * per_warp;
@@ -92,85 +105,107 @@ __global__ void __launch_bounds__(kIfvdWarps * 32, 1) ifvd_class_sums_kernel(con
 
     int cur = C;       // class of the run being summed in `acc` (C: the bin nobody reads)
     float acc = 0.f;
-    // one step = 32 pixels x 32 channels; the next step's global loads fly while this one is walked
-    float v[32], w[4] = {1.f, 1.f, 1.f, 1.f};
-    int kreg = C;
-    const int sr = lane >> 3, px4 = 4 * (lane & 7);  // VEC: sub-row and first pixel of this lane's loads
+    // one step = PXS pixels x 32 channels; the next step's global loads fly while this one is walked.  The loads land
+    // in registers RAW (no conversion, no arithmetic on them before the next step's shared-memory stores): a use right
+    // behind each load would make the in-order warp wait for every load in turn (bf16: 8 round trips per step).
+    using vec_t = typename Elem<T>::vec_t;
+    using raw_t = typename std::conditional<VEC, vec_t, T>::type;
+    constexpr int NRAW = VEC ? 8 : 32;
+    raw_t raw[NRAW];
+    float w[EPL], virt[EPL];   // weights of this lane's pixels; values of the virtual channel c == C
+    int kreg[HALVES];
+    const int sr = lane >> 3, pxl = EPL * (lane & 7);  // VEC: sub-row and first pixel of this lane's loads
+    const int rv = C - c0;                              // row of the virtual channel in this group (if 0 <= rv < 32)
     auto load_step = [&](int st) {
-        const int px = st * 32 + lane;
-        kreg = px < HW ? __ldg(cls + px) : C;
-        if (VEC) {
-            const int q0 = st * 32 + px4;
+#pragma unroll
+        for (int h = 0; h < HALVES; ++h) {
+            const int px = st * PXS + h * 32 + lane;
+            kreg[h] = px < HW ? __ldg(cls + px) : C;
+        }
+        if constexpr (VEC) {
+            const int q0 = st * PXS + pxl;
             const bool in = q0 < HW;
-            if (WEIGHTED) {
-                if (in) load4(a0 + q0, w);
-                else w[0] = w[1] = w[2] = w[3] = 0.f;
-            }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const int r = 4 * q + sr, c = c0 + r;
-                float* d = &v[4 * q];
-                d[0] = d[1] = d[2] = d[3] = 0.f;
-                if (in) {
-                    if (c < C) load4(feat + (size_t)r * HW + q0, d);
-                    else if (c == C) {
-                        if (WEIGHTED) load4(a1 + q0, d);
-                        else d[0] = d[1] = d[2] = d[3] = 1.f;
-                    }
-                }
+                const int r = 4 * q + sr;
+                raw[q] = vec_t{};
+                if (in && c0 + r < C) raw[q] = *reinterpret_cast<const vec_t*>(feat + (size_t)r * HW + q0);
+            }
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) {
+                w[e] = WEIGHTED ? 0.f : 1.f;
+                virt[e] = (!WEIGHTED && in) ? 1.f : 0.f;
+            }
+            if (WEIGHTED && in) {
+                load_vec<EPL>(a0 + q0, w);
+                if (rv >= 0 && rv < 32 && (rv & 3) == sr) load_vec<EPL>(a1 + q0, virt);
             }
         } else {
+            const int px = st * 32 + lane;
             const bool in = px < HW;
-            if (WEIGHTED) w[0] = in ? __ldg(a0 + px) : 0.f;
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
-                const int c = c0 + r;
-                v[r] = 0.f;
-                if (in) {
-                    if (c < C) v[r] = Elem<T>::load(feat + (size_t)r * HW + px);
-                    else if (c == C) v[r] = WEIGHTED ? __ldg(a1 + px) : 1.f;
-                }
+                raw[r] = T(0.f);
+                if (in && c0 + r < C) raw[r] = feat[(size_t)r * HW + px];
             }
+            w[0] = WEIGHTED ? (in ? __ldg(a0 + px) : 0.f) : 1.f;
+            virt[0] = in ? (WEIGHTED ? __ldg(a1 + px) : 1.f) : 0.f;
         }
     };
     if (s0 < s1) load_step(s0);
     __syncwarp();
     for (int st = s0; st < s1; ++st) {
-        if (VEC) {  // bank = (row + pixel) % 32 = (4q + sr + px4 + e) % 32: distinct over the warp
+        if constexpr (VEC) {  // bank = (row + pixel) % 32 = (4q + sr + pxl + e) % 32: distinct over the warp for EPL = 4, 2-way for 8
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int r = 4 * q + sr;
-                const bool scale = WEIGHTED && c0 + r < C;
+                float d[EPL];
+                Elem<T>::unpack(raw[q], d);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) tile[r * kTilePitch + px4 + e] = scale ? w[e] * v[4 * q + e] : v[4 * q + e];
+                for (int e = 0; e < EPL; ++e) {
+                    float val = WEIGHTED ? w[e] * d[e] : d[e];
+                    if (r == rv) val = virt[e];
+                    tile[r * PITCH + pxl + e] = val;
+                }
             }
         } else {
 #pragma unroll
-            for (int r = 0; r < 32; ++r) tile[r * kTilePitch + lane] = (WEIGHTED && c0 + r < C) ? w[0] * v[r] : v[r];
+            for (int r = 0; r < 32; ++r) {
+                float val = (float)raw[r];
+                if (WEIGHTED) val *= w[0];
+                if (r == rv) val = virt[0];
+                tile[r * PITCH + lane] = val;
+            }
         }
-        const int kcur = kreg;
+        int kstep[HALVES];
+#pragma unroll
+        for (int h = 0; h < HALVES; ++h) kstep[h] = kreg[h];
         __syncwarp();
         if (st + 1 < s1) load_step(st + 1);
-        float x[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = tile[lane * kTilePitch + j];
-        // bit j: pixel j starts a new run (its class differs from its predecessor's)
-        const int kprev = __shfl_up_sync(0xffffffffu, kcur, 1);
-        const unsigned chg = __ballot_sync(0xffffffffu, lane == 0 ? kcur != cur : kcur != kprev);
-        if (chg == 0u) {  // the whole step continues the current run (the usual case on label maps)
-            float t[8];
+        for (int h = 0; h < HALVES; ++h) {
+            const int kcur = kstep[h];
+            float x[32];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) t[q] = (x[4 * q] + x[4 * q + 1]) + (x[4 * q + 2] + x[4 * q + 3]);
-            acc += ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
-        } else {
+            for (int j = 0; j < 32; ++j) x[j] = tile[lane * PITCH + h * 32 + j];
+            // bit j: pixel j starts a new run (its class differs from its predecessor's)
+            const int kprev = __shfl_up_sync(0xffffffffu, kcur, 1);
+            const unsigned chg = __ballot_sync(0xffffffffu, lane == 0 ? kcur != cur : kcur != kprev);
+            if (chg == 0u) {  // the whole walk continues the current run (the usual case on label maps)
+                float t[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                if ((chg >> j) & 1u) {  // warp-uniform
-                    bins[cur * 32 + lane] += acc;
-                    acc = 0.f;
-                    cur = __shfl_sync(0xffffffffu, kcur, j);
+                for (int q = 0; q < 8; ++q) t[q] = (x[4 * q] + x[4 * q + 1]) + (x[4 * q + 2] + x[4 * q + 3]);
+                acc += ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if ((chg >> j) & 1u) {  // warp-uniform
+                        bins[cur * 32 + lane] += acc;
+                        acc = 0.f;
+                        cur = __shfl_sync(0xffffffffu, kcur, j);
+                    }
+                    acc += x[j];
                 }
-                acc += x[j];
             }
         }
         __syncwarp();
@@ -357,7 +392,7 @@ __global__ void __launch_bounds__(256) ifvd_finalize_kernel(const float* part, i
 template <typename T>
 static cudaError_t launch_ifvd_t(const IfvdParams& p, float loss_scale, cudaStream_t stream) {
     const int K1 = p.C + 1;
-    const size_t smem = (size_t)kIfvdWarps * (K1 * 32 + 32 * kTilePitch) * sizeof(float);
+    const size_t smem = (size_t)kIfvdWarps * (K1 * 32 + 32 * kTileMaxPitch) * sizeof(float);
     const bool vec = p.vec != 0;
     auto sums = vec ? ifvd_class_sums_kernel<T, false, true> : ifvd_class_sums_kernel<T, false, false>;
     auto wsums = vec ? ifvd_class_sums_kernel<T, true, true> : ifvd_class_sums_kernel<T, true, false>;
@@ -381,7 +416,7 @@ static cudaError_t launch_ifvd_t(const IfvdParams& p, float loss_scale, cudaStre
 }
 
 // class-sum bins (C+1 classes x 32 channels per warp) must fit the CTA's shared memory
-int ifvd_max_channels() { return (int)((227 * 1024 / sizeof(float) / kIfvdWarps - 32 * kTilePitch) / 32) - 1; }
+int ifvd_max_channels() { return (int)((227 * 1024 / sizeof(float) / kIfvdWarps - 32 * kTileMaxPitch) / 32) - 1; }
 
 int ifvd_pix_threads() { return kIfvdPixThreads; }
 

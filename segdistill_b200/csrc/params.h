@@ -227,7 +227,7 @@ struct IfvdParams {
     float* spart;       // [splits][2][B][C+1][C+1] class sums per pixel range (splits > 1)
     int B, C, HW;
     int splits;         // pixel ranges (CTAs) per (sample, 32 channels) of the class-sum kernels
-    int vec;            // HW % 4 == 0 and S, T 16-byte aligned: 4-pixel loads
+    int vec;            // 16-byte loads: HW a multiple of 16 / sizeof(element), S and T 16-byte aligned
     int accumulate;     // dS += gradient instead of dS = gradient
     float gcoef;        // grad_scale * 2 * weight / (B*HW)
 };
