@@ -641,13 +641,14 @@ int sd_ifvd_sim_fwd_bwd(const void* S, const void* T, const int32_t* cls, void* 
     p.spart = reinterpret_cast<float*>(ws + w.off_spart);
     p.B = B; p.C = C; p.HW = HW;
     p.splits = w.splits;
+    p.wsplits = w.wsplits;
     p.accumulate = accumulate != 0;
     p.vec = HW % (16 / elem_size(dtype)) == 0 && aligned16(S) && aligned16(T) && aligned16(workspace);
     const double npix = (double)B * (double)HW;
     p.gcoef = (float)((double)grad_scale * 2.0 * (double)weight / npix);
     cudaError_t e = sd::launch_ifvd_sim(p, dtype == SD_BF16, (float)((double)weight / npix),
                                         static_cast<cudaStream_t>(stream));
-    g_launches += w.splits > 1 ? 7 : 5;
+    g_launches += 5 + (w.splits > 1) + (w.wsplits > 1);
     t_last_kernel = "ifvd_sim (class sums, sim, weighted class sums, grad)";
     return e == cudaSuccess ? SD_OK : (int)e;
 }

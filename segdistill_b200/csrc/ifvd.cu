@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(kIfvdWarps * 32, 1) ifvd_class_sums_kernel(con
 
     // this warp's run of steps
     const int steps = (HW + PXS - 1) / PXS;
-    const int per_cta = (steps + p.splits - 1) / p.splits;
+    const int nsplit = WEIGHTED ? p.wsplits : p.splits;
+    const int per_cta = (steps + nsplit - 1) / nsplit;
     const int per_warp = (per_cta + kIfvdWarps - 1) / kIfvdWarps;
     const int s0 = split * per_cta + warp * per_warp;
     const int s1 = min(min(s0 + per_warp, (split + 1) * per_cta), steps);
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(kIfvdWarps * 32, 1) ifvd_class_sums_kernel(con
     __syncthreads();
 
     // warps summed in order; out[(tensor, b)][k][c]: one contiguous row of channels per class
-    float* out = (p.splits > 1 ? p.spart + (size_t)split * (WEIGHTED ? 1 : 2) * p.B * K1 * K1 : (WEIGHTED ? p.wsum : p.sums)) +
+    float* out = (nsplit > 1 ? p.spart + (size_t)split * (WEIGHTED ? 1 : 2) * p.B * K1 * K1 : (WEIGHTED ? p.wsum : p.sums)) +
                  ((size_t)(second ? p.B : 0) + b) * K1 * K1;
     const float* all = smem_f;
     for (int i = threadIdx.x; i < 32 * K1; i += kIfvdWarps * 32) {
@@ -400,7 +401,7 @@ static cudaError_t launch_ifvd_t(const IfvdParams& p, float loss_scale, cudaStre
     if (e == cudaSuccess) e = cudaFuncSetAttribute(wsums, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     const int groups = (K1 + 31) / 32;
-    const dim3 gsum(p.splits, groups, 2 * p.B), gwsum(p.splits, groups, p.B);
+    const dim3 gsum(p.splits, groups, 2 * p.B), gwsum(p.wsplits, groups, p.B);
     const dim3 gpix((p.HW + kIfvdPixThreads - 1) / kIfvdPixThreads, p.B, 1);
     const long long plane = (long long)p.B * K1 * K1;
     sums<<<gsum, kIfvdWarps * 32, smem, stream>>>(p);
@@ -408,8 +409,8 @@ static cudaError_t launch_ifvd_t(const IfvdParams& p, float loss_scale, cudaStre
         ifvd_combine_kernel<<<(unsigned)((2 * plane + 255) / 256), 256, 0, stream>>>(p.spart, p.sums, 2 * plane, p.splits);
     ifvd_sim_kernel<T><<<gpix, dim3(kIfvdPixThreads, kIfvdSlices), 0, stream>>>(p);
     wsums<<<gwsum, kIfvdWarps * 32, smem, stream>>>(p);
-    if (p.splits > 1)
-        ifvd_combine_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, stream>>>(p.spart, p.wsum, plane, p.splits);
+    if (p.wsplits > 1)
+        ifvd_combine_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, stream>>>(p.spart, p.wsum, plane, p.wsplits);
     ifvd_grad_kernel<T><<<gpix, dim3(kIfvdPixThreads, kIfvdSlices), 0, stream>>>(p);
     ifvd_finalize_kernel<<<1, 256, 0, stream>>>(p.part, (int)(gpix.x * gpix.y), loss_scale, p.loss);
     return cudaGetLastError();

@@ -224,9 +224,9 @@ struct IfvdParams {
     float* wsum;        // [B][C+1 classes][C+1]    gradient reaching the class sums of S: C channels + V_k
     float* pix;         // [4][B][HW]       per-pixel backward coefficients
     float* part;        // one loss partial per CTA of the per-pixel kernel
-    float* spart;       // [splits][2][B][C+1][C+1] class sums per pixel range (splits > 1)
+    float* spart;       // [splits][2][B][C+1][C+1] (plain) / [wsplits][B][C+1][C+1] (weighted) class sums per pixel range
     int B, C, HW;
-    int splits;         // pixel ranges (CTAs) per (sample, 32 channels) of the class-sum kernels
+    int splits, wsplits;  // pixel ranges (CTAs) per (sample, 32 channels, tensor) of the plain / weighted class-sum launch
     int vec;            // 16-byte loads: HW a multiple of 16 / sizeof(element), S and T 16-byte aligned
     int accumulate;     // dS += gradient instead of dS = gradient
     float gcoef;        // grad_scale * 2 * weight / (B*HW)
@@ -234,19 +234,29 @@ struct IfvdParams {
 struct IfvdWorkspace {
     size_t off_sums, off_wsum, off_pix, off_part, off_spart, bytes;
     long long nparts;
-    int splits;
+    int splits, wsplits;
 };
-// the class-sum CTAs own a whole SM (their bins fill its shared memory): as many pixel ranges as keep the plain launch
-// (S and T) within four waves of a 148-SM part, but no less than 8 warps x 2 steps of 32 pixels per CTA; a function
-// of the shape only, so that sd_ifvd_sim_workspace_bytes and the launch agree
-inline int ifvd_splits(long long B, long long C, long long HW) {
+// Pixel ranges per (sample, 32 channels, tensor) of a class-sum launch.  The CTAs own a whole SM (their bins fill its
+// shared memory), so the launch runs in waves of 148; a CTA costs its warps' steps of 32 pixels plus a fixed part
+// (zeroing and merging 8 x 151 x 32 bins, about three steps' worth).  Pick the count that minimises
+// waves x (steps per warp + 3), with at least two steps per warp; a function of the shape only, so that
+// sd_ifvd_sim_workspace_bytes and the launch agree.  `tensors`: 2 for the plain sums (S and T), 1 for the weighted.
+inline int ifvd_splits(long long B, long long C, long long HW, int tensors) {
     const long long groups = (C + 1 + 31) / 32;
-    const long long ctas = 2 * B * groups;
-    long long s = 592 / ctas;
-    const long long most = (HW + 511) / 512;
-    if (s > most) s = most;
-    if (s > 32) s = 32;
-    return s < 1 ? 1 : (int)s;
+    const long long base = tensors * B * groups;
+    const long long steps = (HW + 31) / 32;
+    long long best = 1, best_cost = -1;
+    for (long long s = 1; s <= 32; ++s) {
+        const long long per_cta = (steps + s - 1) / s;
+        if (s > 1 && per_cta < 16) break;
+        const long long waves = (base * s + 147) / 148;
+        const long long cost = waves * ((per_cta + 7) / 8 + 3);
+        if (best_cost < 0 || cost < best_cost) {
+            best = s;
+            best_cost = cost;
+        }
+    }
+    return (int)best;
 }
 inline IfvdWorkspace ifvd_workspace_layout(long long B, long long C, long long HW, long long pix_threads) {
     IfvdWorkspace w;
@@ -258,8 +268,10 @@ inline IfvdWorkspace ifvd_workspace_layout(long long B, long long C, long long H
     w.off_pix = o;   o = up(o + sizeof(float) * 4 * (size_t)B * (size_t)HW);   // 16-byte aligned: read as float4
     w.nparts = B * ((HW + pix_threads - 1) / pix_threads);
     w.off_part = o;  o += sizeof(float) * (size_t)w.nparts;
-    w.splits = ifvd_splits(B, C, HW);
-    w.off_spart = o; o += w.splits > 1 ? sizeof(float) * 2 * (size_t)w.splits * (size_t)B * K1 * K1 : 0;
+    w.splits = ifvd_splits(B, C, HW, 2);
+    w.wsplits = ifvd_splits(B, C, HW, 1);
+    const size_t slabs = (size_t)(2 * w.splits > w.wsplits ? 2 * w.splits : w.wsplits);   // both launches use the buffer in turn
+    w.off_spart = o; o += sizeof(float) * slabs * (size_t)B * K1 * K1;
     w.bytes = (o + 255) & ~(size_t)255;
     return w;
 }
