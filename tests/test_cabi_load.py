@@ -46,6 +46,12 @@ def test_workspace_sizes_are_positive_and_monotone(lib):
     assert lib.sd_kl_rows_workspace_bytes(0, 150, 4096, 1) == 0
     assert lib.sd_kl_pixels_workspace_bytes(16, 150, 16384) > 16 * 16384 * 4
     assert lib.sd_mse_workspace_bytes(1 << 20) > 0
+    # IFVD: class sums of S, T and the weighted pass (3 * B * 151^2 floats) + 4 floats per pixel, plus the
+    # per-pixel-range partial sums; grows with the batch, zero for an empty problem
+    small = lib.sd_ifvd_sim_workspace_bytes(2, 150, 16384)
+    assert small > 4 * (3 * 2 * 151 * 151 + 4 * 2 * 16384)
+    assert lib.sd_ifvd_sim_workspace_bytes(16, 150, 16384) > small
+    assert lib.sd_ifvd_sim_workspace_bytes(0, 150, 16384) == 0
 
 
 def test_argument_errors_are_reported_without_a_device(lib):
@@ -74,6 +80,13 @@ def test_argument_errors_are_reported_without_a_device(lib):
                                     p, 1 << 20, 0, None) == -1
     assert lib.sd_mse_fwd_bwd(p, p, p, p, 0, 0, 1.0, 1.0, p, 1 << 20, None) == -2
     assert lib.sd_scale_grad(None, 4, 0, p, None) == -1
+    # IFVD similarity term: NULL class map, bad dtype, empty shape, workspace too small; class map: NULL, bad size
+    assert lib.sd_ifvd_sim_fwd_bwd(p, p, None, p, p, 1, 2, 4, 0, 10.0, 1.0, 0, p, 1 << 20, None) == -1
+    assert lib.sd_ifvd_sim_fwd_bwd(p, p, p, p, p, 1, 2, 4, 5, 10.0, 1.0, 0, p, 1 << 20, None) == -3
+    assert lib.sd_ifvd_sim_fwd_bwd(p, p, p, p, p, 1, 0, 4, 0, 10.0, 1.0, 0, p, 1 << 20, None) == -2
+    assert lib.sd_ifvd_sim_fwd_bwd(p, p, p, p, p, 1, 2, 4, 0, 10.0, 1.0, 0, p, 16, None) == -5
+    assert lib.sd_ifvd_class_map(None, p, 1, 4, 4, 2, 2, 3, None) == -1
+    assert lib.sd_ifvd_class_map(p, p, 1, 4, 0, 2, 2, 3, None) == -2
 
 
 def test_no_device_means_loud_failure(lib):
