@@ -397,9 +397,13 @@ static cudaError_t launch_ifvd_t(const IfvdParams& p, float loss_scale, cudaStre
     const bool vec = p.vec != 0;
     auto sums = vec ? ifvd_class_sums_kernel<T, false, true> : ifvd_class_sums_kernel<T, false, false>;
     auto wsums = vec ? ifvd_class_sums_kernel<T, true, true> : ifvd_class_sums_kernel<T, true, false>;
-    cudaError_t e = cudaFuncSetAttribute(sums, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(wsums, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
+    static bool configured[2] = {false, false};  // per instantiation (T) and load width
+    if (!configured[vec]) {
+        cudaError_t e = cudaFuncSetAttribute(sums, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(wsums, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        configured[vec] = true;
+    }
     const int groups = (K1 + 31) / 32;
     const dim3 gsum(p.splits, groups, 2 * p.B), gwsum(p.wsplits, groups, p.B);
     const dim3 gpix((p.HW + kIfvdPixThreads - 1) / kIfvdPixThreads, p.B, 1);
