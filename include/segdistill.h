@@ -203,6 +203,9 @@ SD_API int sd_mse_fwd_bwd(const void* S, const void* T, void* dS, float* loss,
  *   written by sd_kl_pixels_fwd_bwd with the same grad_scale).
  */
 SD_API size_t sd_ifvd_sim_workspace_bytes(int B, int C, int HW);
+/* largest channel (= class) count the class-sum kernels take: their per-warp bins (C + 1 classes x 32 channel lanes)
+ * must fit one CTA's shared memory.  Larger C -> SD_ERR_UNSUPPORTED (the reference's Python loop, :222-230, takes any). */
+SD_API int sd_ifvd_max_channels(void);
 SD_API int sd_ifvd_sim_fwd_bwd(const void* S, const void* T, const int32_t* cls, void* dS, float* loss,
                         int B, int C, int HW, int dtype, float weight, float grad_scale, int accumulate,
                         void* workspace, size_t workspace_bytes, void* stream);

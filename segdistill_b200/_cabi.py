@@ -29,7 +29,8 @@ EXPORTS = (
     'sd_kl_rows_workspace_bytes', 'sd_kl_rows_fwd_bwd', 'sd_kl_rows_multi_fwd_bwd', 'sd_scale_grad2',
     'sd_kl_pixels_workspace_bytes', 'sd_kl_pixels_fwd_bwd',
     'sd_kl_rows_up_workspace_bytes', 'sd_kl_rows_up_fwd_bwd', 'sd_kl_pixels_up_workspace_bytes', 'sd_kl_pixels_up_fwd_bwd',
-    'sd_mse_workspace_bytes', 'sd_mse_fwd_bwd', 'sd_ifvd_sim_workspace_bytes', 'sd_ifvd_sim_fwd_bwd', 'sd_ifvd_class_map', 'sd_scale_grad',
+    'sd_mse_workspace_bytes', 'sd_mse_fwd_bwd', 'sd_ifvd_sim_workspace_bytes', 'sd_ifvd_sim_fwd_bwd', 'sd_ifvd_max_channels',
+    'sd_ifvd_class_map', 'sd_scale_grad',
     'sd_cgd_corr_workspace_bytes', 'sd_cgd_corr_fwd_bwd',
     'sd_launch_count', 'sd_last_kernel',
 )
@@ -97,6 +98,7 @@ def load():
         lib.sd_ifvd_sim_workspace_bytes.argtypes = [i32, i32, i32]
         lib.sd_ifvd_sim_fwd_bwd.restype = i32
         lib.sd_ifvd_sim_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, i32, vp, sz, vp]
+        lib.sd_ifvd_max_channels.restype = i32
         lib.sd_ifvd_class_map.restype = i32
         lib.sd_ifvd_class_map.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
         lib.sd_scale_grad.restype = i32
@@ -435,6 +437,11 @@ def ifvd_sim(x_student, x_teacher, cls, weight=10.0, grad_scale=1.0, ds=None):
                                      _stream_ptr(dev))
         _check(rc)
     return out[0], ds
+
+
+def ifvd_max_channels() -> int:
+    """Largest C the IFVD class-sum kernels take (their bins must fit one CTA's shared memory)."""
+    return int(load().sd_ifvd_max_channels())
 
 
 def ifvd_class_map(target, n_classes, h, w):

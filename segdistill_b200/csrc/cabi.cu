@@ -573,7 +573,7 @@ int sd_kl_pixels_up_fwd_bwd(const void* S, const void* T, void* dS, float* loss,
     if (!S || !T || !dS || !loss || !workspace) return SD_ERR_NULL;
     if (dtype != SD_F32 && dtype != SD_BF16) return SD_ERR_DTYPE;
     if (B <= 0 || C <= 0 || Hl <= 0 || Wl <= 0) return SD_ERR_SHAPE;
-    if (!(tau > 0.f)) return SD_ERR_VALUE;
+    if (!(tau > 0.f) || alpha == 0.f || grad_scale == 0.f) return SD_ERR_VALUE;   // (the kernel divides by their product)
     if (scale != 2 && scale != 4 && scale != 8) return SD_ERR_UNSUPPORTED;
     if ((long long)B * C * Hl * Wl >= (1ll << 40)) return SD_ERR_SHAPE;
     if (workspace_bytes < sd_kl_pixels_up_workspace_bytes(B, C, Hl, Wl, scale)) return SD_ERR_WORKSPACE;
@@ -589,6 +589,7 @@ int sd_kl_pixels_up_fwd_bwd(const void* S, const void* T, void* dS, float* loss,
     p.inv_Wl = 1.0f / (float)Wl;
     p.inv_tau = (float)(1.0 / (double)tau);
     p.coef = (float)((double)grad_scale * (double)alpha / (R * (double)tau));
+    p.inv_coef = (float)(R * (double)tau / ((double)grad_scale * (double)alpha));
     p.loss_scale = (float)((double)alpha / R);
     p.loss = loss;
     char* ws = static_cast<char*>(workspace);
@@ -606,6 +607,8 @@ size_t sd_ifvd_sim_workspace_bytes(int B, int C, int HW) {
     if (B <= 0 || C <= 0 || HW <= 0) return 0;
     return sd::ifvd_workspace_layout(B, C, HW, sd::ifvd_pix_threads()).bytes;
 }
+
+int sd_ifvd_max_channels(void) { return sd::ifvd_max_channels(); }
 
 int sd_ifvd_class_map(const int64_t* target, int32_t* cls, int B, int Ht, int Wt, int h, int w, int C, void* stream) {
     if (!target || !cls) return SD_ERR_NULL;

@@ -179,6 +179,46 @@ struct Elem<__nv_bfloat16> {
     static __device__ __forceinline__ void store(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
 
+// ---------------------------------------------------------------- KL without cancellation when S ~ T
+// KL(p||q) = sum p (t - s)/tau - (lse_t - lse_s).  With lse = M/tau + ln Z the difference of the two logarithms
+// loses everything below ulp(ln Z) ~ 1e-6 - as large as the whole KL of a nearly converged student (the reference's
+// own log_softmax chain, losses.py:108-111, is ~6e-4 accurate there).  Every kernel therefore ALSO accumulates
+//     dd = sum_i (et_i - es_i),   es_i = exp2(s_i c2 - sigma), et_i = exp2(t_i c2 - theta)
+// element by element (a sum of small terms when S ~ T, whatever the references sigma = fl(ms c2), theta = fl(mt c2)
+// are), and evaluates  lse_t - lse_s = (theta - sigma) ln 2 + log1p(dd / zs):  three terms of the size of the
+// differences t - s, each with fp32 relative accuracy.  When partial sums taken against different references are
+// merged, dd' = sum_k dd_k ft_k + zs_k (ft_k - fs_k) with the rescale factors fs_k = 2^(sigma_k - sigma'),
+// ft_k = 2^(theta_k - theta'); their difference comes from factor_diff below (exp2m1 of the small exponent gap), never
+// from subtracting two rounded factors.
+
+// 2^x - 1 for |x| <= 0.25, relative error ~1e-8 (Taylor in y = x ln 2, |y| <= 0.174)
+__device__ __forceinline__ float exp2m1_small(float x) {
+    const float y = x * kLn2;
+    float p = 1.f / 720.f;
+    p = fmaf(p, y, 1.f / 120.f);
+    p = fmaf(p, y, 1.f / 24.f);
+    p = fmaf(p, y, 1.f / 6.f);
+    p = fmaf(p, y, 0.5f);
+    p = fmaf(p, y, 1.f);
+    return p * y;
+}
+// ft - fs for rescale factors fs = 2^xs, ft = 2^xt, given x = xt - xs formed from the small differences
+// (theta_k - sigma_k) - (theta' - sigma') (each exact when S ~ T).  Away from x ~ 0 nothing cancels.
+__device__ __forceinline__ float factor_diff(float fs, float ft, float x) {
+    return fabsf(x) <= 0.25f ? fs * exp2m1_small(x) : ft - fs;
+}
+// exponent gap (theta_k - sigma_k) - (theta - sigma) of a part (ms_k, mt_k) merged into (ms, mt); the products are
+// rounded exactly as the kernels round the references of their exponentials (fmaf(x, c2, -fl(m c2)))
+__device__ __forceinline__ float ref_gap2(float ms, float mt, float c2) { return __fmul_rn(mt, c2) - __fmul_rn(ms, c2); }
+// 2^(fl(m_k c2) - fl(m c2)): rescale factor of sums taken against m_k to the reference m >= m_k
+__device__ __forceinline__ float ref_factor(float mk, float m, float c2) {
+    return fast_exp2(__fmul_rn(mk, c2) - __fmul_rn(m, c2));
+}
+// KL of one row from its merged statistics; gap2 = fl(mt c2) - fl(ms c2)
+__device__ __forceinline__ float kl_from_stats(float inv_tau, float gap2, float zs, float zt, float a, float dd) {
+    return inv_tau * a / zt - (gap2 * kLn2 + log1pf(dd / zs));
+}
+
 // softmax statistics of a piece of a row: max m and z = sum exp2((x - m)*c2)
 struct Stat {
     float m, z;

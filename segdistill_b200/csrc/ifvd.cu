@@ -397,12 +397,13 @@ static cudaError_t launch_ifvd_t(const IfvdParams& p, float loss_scale, cudaStre
     const bool vec = p.vec != 0;
     auto sums = vec ? ifvd_class_sums_kernel<T, false, true> : ifvd_class_sums_kernel<T, false, false>;
     auto wsums = vec ? ifvd_class_sums_kernel<T, true, true> : ifvd_class_sums_kernel<T, true, false>;
-    static bool configured[2] = {false, false};  // per instantiation (T) and load width
-    if (!configured[vec]) {
+    static std::atomic<bool> configured[kMaxDevices][2];  // per instantiation (T), device and load width
+    const int dev = device_slot();
+    if (!configured[dev][vec].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(sums, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(wsums, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        configured[vec] = true;
+        configured[dev][vec].store(true, std::memory_order_release);
     }
     const int groups = (K1 + 31) / 32;
     const dim3 gsum(p.splits, groups, 2 * p.B), gwsum(p.wsplits, groups, p.B);

@@ -174,12 +174,16 @@ kl_pixels_tma_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_cons
         }
 
         // ---- exponentials stay in registers; per-pixel partial sums
-        float zs[PXT], zt[PXT], ac[PXT];
+        // (dd = sum (et - es) term by term against the pixel's references: common.cuh, KL without cancellation)
+        float zs[PXT], zt[PXT], ac[PXT], dd[PXT], rs2[PXT], rt2[PXT];
 #pragma unroll
         for (int q = 0; q < PXT; ++q) {
             zs[q] = 0.f;
             zt[q] = 0.f;
             ac[q] = 0.f;
+            dd[q] = 0.f;
+            rs2[q] = __fmul_rn(mxs[q], c2);
+            rt2[q] = __fmul_rn(mxt[q], c2);
         }
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
@@ -188,11 +192,12 @@ kl_pixels_tma_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_cons
                 for (int q = 0; q < PXT; ++q) {
                     const int i = k * PXT + q;
                     const float d = t[i] - s[i];
-                    const float es = fast_exp2(fmaf(s[i], c2, -mxs[q] * c2));
-                    const float et = fast_exp2(fmaf(t[i], c2, -mxt[q] * c2));
+                    const float es = fast_exp2(fmaf(s[i], c2, -rs2[q]));
+                    const float et = fast_exp2(fmaf(t[i], c2, -rt2[q]));
                     zs[q] += es;
                     zt[q] += et;
                     ac[q] = fmaf(et, d, ac[q]);
+                    dd[q] += et - es;
                     s[i] = es;
                     t[i] = et;
                 }
@@ -200,24 +205,25 @@ kl_pixels_tma_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_cons
         }
 #pragma unroll
         for (int q = 0; q < PXT; ++q)
-            red_sum[(q * kPixCG + cg) * kPixCols + col] = make_float4(zs[q], zt[q], ac[q], 0.f);
+            red_sum[(q * kPixCG + cg) * kPixCols + col] = make_float4(zs[q], zt[q], ac[q], dd[q]);
         __syncthreads();
         float ks[PXT], kt[PXT], ga[PXT];
 #pragma unroll
         for (int q = 0; q < PXT; ++q) {
-            float Zs = 0.f, Zt = 0.f, A = 0.f;
+            float Zs = 0.f, Zt = 0.f, A = 0.f, DD = 0.f;
 #pragma unroll
             for (int g = 0; g < kPixCG; ++g) {
                 const float4 r = red_sum[(q * kPixCG + g) * kPixCols + col];
                 Zs += r.x;
                 Zt += r.y;
                 A += r.z;
+                DD += r.w;
             }
             ks[q] = p.coef / Zs;
             kt[q] = p.coef / Zt;
             ga[q] = AT ? p.at_gcoef * dm[q] : 0.f;
             if (cg == 0 && px + q < p.HW) {
-                const float kl = p.inv_tau * A / Zt - ((mxt[q] - mxs[q]) * p.inv_tau + (logf(Zt) - logf(Zs)));
+                const float kl = kl_from_stats(p.inv_tau, rt2[q] - rs2[q], Zs, Zt, A, DD);
                 p.row_kl[(size_t)b * p.HW + px + q] = kl;
                 acc_kl += kl;
                 if (AT) acc_at = fmaf(dm[q], dm[q], acc_at);
@@ -309,14 +315,16 @@ __global__ void __launch_bounds__(256) kl_pixels_generic(const PixParams p) {
             ss += a;
             st += bb;
         }
-        const float ms2 = ms * p.c2, mt2 = mt * p.c2;
-        float zs = 0.f, zt = 0.f, ac = 0.f;
+        const float ms2 = __fmul_rn(ms, p.c2), mt2 = __fmul_rn(mt, p.c2);
+        float zs = 0.f, zt = 0.f, ac = 0.f, dd = 0.f;
         for (int c = 0; c < p.C; ++c) {
             const float a = E::load(s + (size_t)c * p.HW), bb = E::load(t + (size_t)c * p.HW);
+            const float es = fast_exp2(fmaf(a, p.c2, -ms2));
             const float et = fast_exp2(fmaf(bb, p.c2, -mt2));
-            zs += fast_exp2(fmaf(a, p.c2, -ms2));
+            zs += es;
             zt += et;
             ac = fmaf(et, bb - a, ac);
+            dd += et - es;
         }
         const float dm = (ss - st) * p.inv_C;
         const float ks = p.coef / zs, kt = p.coef / zt;
@@ -327,7 +335,7 @@ __global__ void __launch_bounds__(256) kl_pixels_generic(const PixParams p) {
             const float et = fast_exp2(fmaf(bb, p.c2, -mt2));
             E::store(o + (size_t)c * p.HW, fmaf(es, ks, -et * kt) + ga);
         }
-        kl = p.inv_tau * ac / zt - ((mt - ms) * p.inv_tau + (logf(zt) - logf(zs)));
+        kl = kl_from_stats(p.inv_tau, mt2 - ms2, zs, zt, ac, dd);
         p.row_kl[r] = kl;
         if (AT) atsq = dm * dm;
     }

@@ -16,6 +16,7 @@
 //                           written once; 2 ex2 per element.
 //   kl_rows_generic_*       any alignment / any row length: three plain passes.
 #include "rows_common.cuh"
+#include "launch.h"
 
 namespace sd {
 
@@ -193,59 +194,65 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
         __syncthreads();
         if (tid == 0) issue_loads(nslots);
 
-        // ---- exponentials (kept in registers), thread-partial sums relative to (ms, mt)
-        float zs = 0.f, zt = 0.f, a = 0.f, sq = 0.f;
-        const float ms2 = ms * c2, mt2 = mt * c2;
+        // ---- exponentials (kept in registers), thread-partial sums relative to (ms, mt); dd = sum (et - es) term by
+        //      term (common.cuh: KL without cancellation).  Against thread-local maxima zs and zt lie in [1, 32], so
+        //      zs = zt - dd is as accurate as a sum of its own: one accumulator less in the loop
+        float zt = 0.f, dd = 0.f, a = 0.f, sq = 0.f;
+        const float ms2 = __fmul_rn(ms, c2), mt2 = __fmul_rn(mt, c2);
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
             const float d = t[i] - s[i];
             if (MSE) sq = fmaf(d, d, sq);
             const float es = fast_exp2(fmaf(s[i], c2, -ms2));
             const float et = fast_exp2(fmaf(t[i], c2, -mt2));
-            zs += es;
             zt += et;
+            dd += et - es;
             a = fmaf(et, d, a);
             if (!MSE) {
                 s[i] = es;
                 t[i] = et;
             }
         }
+        const float zs = zt - dd;
 
         // ---- warp: sums rescaled to the warp maxima
         const float msw = warp_max(ms), mtw = warp_max(mt);
         {
-            const float fs = fast_exp2((ms - msw) * c2);
-            const float ft = fast_exp2((mt - mtw) * c2);
+            const float fs = ref_factor(ms, msw, c2);
+            const float ft = ref_factor(mt, mtw, c2);
+            const float gx = (mt2 - ms2) - ref_gap2(msw, mtw, c2);
             const float wzs = warp_sum(zs * fs), wzt = warp_sum(zt * ft), wa = warp_sum(a * ft);
+            const float wdd = warp_sum(fmaf(zs, factor_diff(fs, ft, gx), dd * ft));
             const float wsq = MSE ? warp_sum(sq) : 0.f;
             if (lane == 0) {
                 float* my_red = red + (par * kWarps + warp) * kRedFloats;
                 reinterpret_cast<float4*>(my_red)[0] = make_float4(msw, mtw, wzs, wzt);
-                reinterpret_cast<float4*>(my_red)[1] = make_float4(wa, wsq, 0.f, 0.f);
+                reinterpret_cast<float4*>(my_red)[1] = make_float4(wa, wsq, wdd, 0.f);
             }
         }
         __syncthreads();
 
         // ---- CTA = row: every warp merges the 16 warp records (lanes l and l+16 mirror each other)
-        float Ms, Mt, Zs, Zt, A, SQ = 0.f;
+        float Ms, Mt, Zs, Zt, A, DD, SQ = 0.f;
         {
             const float* q = red + (par * kWarps + (lane & 15)) * kRedFloats;
             const float4 r0 = reinterpret_cast<const float4*>(q)[0];
             const float4 r1 = reinterpret_cast<const float4*>(q)[1];
             Ms = max16(r0.x);
             Mt = max16(r0.y);
-            const float fs = fast_exp2((r0.x - Ms) * c2);
-            const float ft = fast_exp2((r0.y - Mt) * c2);
+            const float fs = ref_factor(r0.x, Ms, c2);
+            const float ft = ref_factor(r0.y, Mt, c2);
+            const float gx = ref_gap2(r0.x, r0.y, c2) - ref_gap2(Ms, Mt, c2);
             Zs = sum16(r0.z * fs);
             Zt = sum16(r0.w * ft);
             A = sum16(r1.x * ft);
+            DD = sum16(fmaf(r0.z, factor_diff(fs, ft, gx), r1.z * ft));
             if (MSE) SQ = sum16(r1.y);
         }
         par ^= 1;
 
         if (tid == 0) {
-            // KL(p||q) = sum p (t - s)/tau - lse_t + lse_s
-            const float kl = p.l[0].inv_tau * A / Zt - ((Mt - Ms) * p.l[0].inv_tau + (logf(Zt) - logf(Zs)));
+            const float kl = kl_from_stats(p.l[0].inv_tau, ref_gap2(Ms, Mt, c2), Zs, Zt, A, DD);
             if (p.l[0].row_kl) p.l[0].row_kl[x.b * p.l[0].G + x.grp] = kl;
             ps.kl += kl;
             if (MSE) ps.sq += SQ;
@@ -254,8 +261,8 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
         // ---- gradient straight from registers
         float coef = p.l[0].coef;
         if (p.grad_out[0] != nullptr) coef *= __ldg(p.grad_out[0]);
-        const float ks = coef * fast_exp2((ms - Ms) * c2) / Zs;
-        const float kt = coef * fast_exp2((mt - Mt) * c2) / Zt;
+        const float ks = coef * ref_factor(ms, Ms, c2) / Zs;
+        const float kt = coef * ref_factor(mt, Mt, c2) / Zt;
         auto grad_vec = [&](int v, float* o) {
 #pragma unroll
             for (int q = 0; q < VE; ++q) {
@@ -459,38 +466,42 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_pack_kernel(const RowsPar
         __syncthreads();
         if (tid == 0) issue_loads(nslots);
 
-        float zs = 0.f, zt = 0.f, a = 0.f;
-        const float ms2 = ms * c2, mt2 = mt * c2;
+        float zt = 0.f, dd = 0.f, a = 0.f;       // zs = zt - dd: see kl_rows_tma_kernel
+        const float ms2 = __fmul_rn(ms, c2), mt2 = __fmul_rn(mt, c2);
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
             const float d = t[i] - s[i];
             if (MSE) my_sq = fmaf(d, d, my_sq);
             const float es = fast_exp2(fmaf(s[i], c2, -ms2));
             const float et = fast_exp2(fmaf(t[i], c2, -mt2));
-            zs += es;
             zt += et;
+            dd += et - es;
             a = fmaf(et, d, a);
             if (!MSE) {
                 s[i] = es;
                 t[i] = et;
             }
         }
+        const float zs = zt - dd;
         // ---- the row's lanes of this warp
         float Ms = ms, Mt = mt;
         for (int o = seg >> 1; o > 0; o >>= 1) {
             Ms = fmaxf(Ms, __shfl_xor_sync(0xffffffffu, Ms, o));
             Mt = fmaxf(Mt, __shfl_xor_sync(0xffffffffu, Mt, o));
         }
-        float Zs = zs * fast_exp2((ms - Ms) * c2), Zt, A;
+        float Zs, Zt, A, DD;
         {
-            const float ft = fast_exp2((mt - Mt) * c2);
+            const float fs = ref_factor(ms, Ms, c2), ft = ref_factor(mt, Mt, c2);
+            Zs = zs * fs;
             Zt = zt * ft;
             A = a * ft;
+            DD = fmaf(zs, factor_diff(fs, ft, (mt2 - ms2) - ref_gap2(Ms, Mt, c2)), dd * ft);
         }
         for (int o = seg >> 1; o > 0; o >>= 1) {
             Zs += __shfl_xor_sync(0xffffffffu, Zs, o);
             Zt += __shfl_xor_sync(0xffffffffu, Zt, o);
             A += __shfl_xor_sync(0xffffffffu, A, o);
+            DD += __shfl_xor_sync(0xffffffffu, DD, o);
         }
         // ---- the row's warps (rows wider than a warp): one exchange through shared memory
         if (tw > 1) {
@@ -498,33 +509,36 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_pack_kernel(const RowsPar
                 float* my_red = red + (par * kWarps + warp) * kRedFloats;
                 reinterpret_cast<float4*>(my_red)[0] = make_float4(Ms, Mt, Zs, Zt);
                 my_red[4] = A;
+                my_red[5] = DD;
             }
             __syncthreads();
             const float* rq = red + (par * kWarps + (warp / tw) * tw + (lane & (tw - 1))) * kRedFloats;
             const float4 r0 = reinterpret_cast<const float4*>(rq)[0];
-            const float r1 = rq[4];
+            const float r1 = rq[4], r2 = rq[5];
             float M2s = r0.x, M2t = r0.y;
             for (int o = tw >> 1; o > 0; o >>= 1) {
                 M2s = fmaxf(M2s, __shfl_xor_sync(0xffffffffu, M2s, o));
                 M2t = fmaxf(M2t, __shfl_xor_sync(0xffffffffu, M2t, o));
             }
-            const float fs = fast_exp2((r0.x - M2s) * c2), ft = fast_exp2((r0.y - M2t) * c2);
+            const float fs = ref_factor(r0.x, M2s, c2), ft = ref_factor(r0.y, M2t, c2);
             float z2s = r0.z * fs, z2t = r0.w * ft, a2 = r1 * ft;
+            float d2 = fmaf(r0.z, factor_diff(fs, ft, ref_gap2(r0.x, r0.y, c2) - ref_gap2(M2s, M2t, c2)), r2 * ft);
             for (int o = tw >> 1; o > 0; o >>= 1) {
                 z2s += __shfl_xor_sync(0xffffffffu, z2s, o);
                 z2t += __shfl_xor_sync(0xffffffffu, z2t, o);
                 a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+                d2 += __shfl_xor_sync(0xffffffffu, d2, o);
             }
             Ms = M2s;
             Mt = M2t;
             Zs = z2s;
             Zt = z2t;
             A = a2;
+            DD = d2;
             par ^= 1;
         }
         if (active && lt == 0) {
-            // KL(p||q) = sum p (t - s)/tau - lse_t + lse_s
-            const float kl = p.l[0].inv_tau * A / Zt - ((Mt - Ms) * p.l[0].inv_tau + (logf(Zt) - logf(Zs)));
+            const float kl = kl_from_stats(p.l[0].inv_tau, ref_gap2(Ms, Mt, c2), Zs, Zt, A, DD);
             if (p.l[0].row_kl) p.l[0].row_kl[u * RPU + q] = kl;
             my_kl += kl;
         }
@@ -532,8 +546,8 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_pack_kernel(const RowsPar
         if (active) {
             float coef = p.l[0].coef;
             if (p.grad_out[0] != nullptr) coef *= __ldg(p.grad_out[0]);
-            const float ks = coef * fast_exp2((ms - Ms) * c2) / Zs;
-            const float kt = coef * fast_exp2((mt - Mt) * c2) / Zt;
+            const float ks = coef * ref_factor(ms, Ms, c2) / Zs;
+            const float kt = coef * ref_factor(mt, Mt, c2) / Zt;
             vec_t* dst = reinterpret_cast<vec_t*>(static_cast<T*>(p.dS)) + (size_t)u * RPU * nvec_row + cv0;
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
@@ -661,7 +675,7 @@ __device__ __forceinline__ void block_max2(float& a, float& b, float* scratch /*
 template <typename T>
 __global__ void __launch_bounds__(kGenThreads) kl_rows_generic_stats(const RowsParams p) {
     using E = Elem<T>;
-    __shared__ float scratch[4 * 8];
+    __shared__ float scratch[5 * 8];
     const long long u = blockIdx.x;
     const GenUnit x = decode_gen(p, u);
     const float c2 = p.l[0].c2;
@@ -673,18 +687,20 @@ __global__ void __launch_bounds__(kGenThreads) kl_rows_generic_stats(const RowsP
         mt = fmaxf(mt, E::load(t + i));
     }
     block_max2(ms, mt, scratch);
-    const float ms2 = ms * c2, mt2 = mt * c2;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};  // zs, zt, a, sq
+    const float ms2 = __fmul_rn(ms, c2), mt2 = __fmul_rn(mt, c2);
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // zs, zt, a, sq, dd
     for (int i = threadIdx.x; i < x.n; i += kGenThreads) {
         const float a = E::load(s + i), b = E::load(t + i);
         const float d = b - a;
+        const float es = fast_exp2(fmaf(a, c2, -ms2));
         const float et = fast_exp2(fmaf(b, c2, -mt2));
-        acc[0] += fast_exp2(fmaf(a, c2, -ms2));
+        acc[0] += es;
         acc[1] += et;
         acc[2] = fmaf(et, d, acc[2]);
         acc[3] = fmaf(d, d, acc[3]);
+        acc[4] += et - es;
     }
-    block_sum<4>(acc, scratch);
+    block_sum<5>(acc, scratch);
     if (threadIdx.x == 0) {
         float* slot = p.unit_part + (size_t)u * kPartWords;
         slot[0] = ms;
@@ -693,6 +709,7 @@ __global__ void __launch_bounds__(kGenThreads) kl_rows_generic_stats(const RowsP
         slot[3] = acc[1];
         slot[4] = acc[2];
         slot[5] = acc[3];
+        slot[6] = acc[4];
     }
 }
 
@@ -714,7 +731,7 @@ __global__ void __launch_bounds__(kGenThreads) kl_rows_generic_grad(const RowsPa
         RowStat acc = rowstat_empty();
         for (int k = lane; k < nparts; k += 32) {
             const float* q = p.unit_part + (size_t)(u0 + k) * kPartWords;
-            acc = rowstat_merge(acc, RowStat{q[0], q[1], q[2], q[3], q[4]}, c2);
+            acc = rowstat_merge(acc, RowStat{q[0], q[1], q[2], q[3], q[4], q[6]}, c2);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -724,6 +741,7 @@ __global__ void __launch_bounds__(kGenThreads) kl_rows_generic_grad(const RowsPa
             other.mt = __shfl_xor_sync(0xffffffffu, acc.mt, o);
             other.zt = __shfl_xor_sync(0xffffffffu, acc.zt, o);
             other.a = __shfl_xor_sync(0xffffffffu, acc.a, o);
+            other.dd = __shfl_xor_sync(0xffffffffu, acc.dd, o);
             acc = rowstat_merge(acc, other, c2);
         }
         if (lane == 0) {
@@ -732,15 +750,16 @@ __global__ void __launch_bounds__(kGenThreads) kl_rows_generic_grad(const RowsPa
             row_stat[2] = acc.mt;
             row_stat[3] = acc.zt;
             row_stat[4] = acc.a;
+            row_stat[5] = acc.dd;
         }
     }
     __syncthreads();
     const float Ms = row_stat[0], Zs = row_stat[1], Mt = row_stat[2], Zt = row_stat[3], A = row_stat[4];
     if (threadIdx.x == 0 && u == u0) {
-        const float kl = p.l[0].inv_tau * A / Zt - ((Mt - Ms) * p.l[0].inv_tau + (logf(Zt) - logf(Zs)));
+        const float kl = kl_from_stats(p.l[0].inv_tau, ref_gap2(Ms, Mt, c2), Zs, Zt, A, row_stat[5]);
         p.l[0].row_kl[x.b * p.l[0].G + grp] = kl;
     }
-    const float ms2 = Ms * c2, mt2 = Mt * c2;
+    const float ms2 = __fmul_rn(Ms, c2), mt2 = __fmul_rn(Mt, c2);
     const float ks = p.l[0].coef / Zs, kt = p.l[0].coef / Zt;
     const T* s = static_cast<const T*>(p.S) + x.off;
     const T* t = static_cast<const T*>(p.T) + x.off;
@@ -787,11 +806,12 @@ __global__ void __launch_bounds__(1024) kl_rows_generic_finalize(const RowsParam
 template <typename T, bool MSE>
 static cudaError_t launch_tma_t(const RowsParams& p, int grid, cudaStream_t stream) {
     auto kern = kl_rows_tma_kernel<T, MSE>;
-    static bool configured = false;  // per instantiation
-    if (!configured) {
+    static std::atomic<bool> configured[kMaxDevices];  // per instantiation and device
+    const int dev = device_slot();
+    if (!configured[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmemBytes);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev].store(true, std::memory_order_release);
     }
     kern<<<grid, kThreads, kRowsSmemBytes, stream>>>(p);
     return cudaGetLastError();
@@ -811,11 +831,12 @@ int kl_rows_tma_chunk_capacity() { return kThreads * kDataRegs; }
 template <typename T, bool MSE>
 static cudaError_t launch_pack_t(const RowsParams& p, int grid, cudaStream_t stream) {
     auto kern = kl_rows_pack_kernel<T, MSE>;
-    static bool configured = false;  // per instantiation
-    if (!configured) {
+    static std::atomic<bool> configured[kMaxDevices];  // per instantiation and device
+    const int dev = device_slot();
+    if (!configured[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmemBytes);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev].store(true, std::memory_order_release);
     }
     kern<<<grid, kThreads, kRowsSmemBytes, stream>>>(p);
     return cudaGetLastError();

@@ -34,6 +34,7 @@
 // Geometry contract (cabi.cu): HW % 128 == 0, so every 32-vector row of a warp lies inside one piece of one
 // slice; slices are whole chunks.
 #include "rows_common.cuh"
+#include "launch.h"
 #ifndef SD_WAIT_NS
 #define SD_WAIT_NS 20000
 #endif
@@ -53,7 +54,7 @@ constexpr int kCRing = 6;                              // ring slots of 32 KB (S
 constexpr int kCSlots = 8;                             // TMEM chunk slots per park warp
 constexpr int kCSlotCols = 32;                         // ... of 32 columns: 4 vector-rows x (4 of S + 4 of T)
 constexpr int kCMaxPieces = kClusterMaxPieces;
-constexpr int kCRecFloats = 8;                         // ms, mt, {zs, zt, a} x 2
+constexpr int kCRecFloats = 12;                        // ms, mt, {zs, zt, a, dd} x 2, 2 x pad (three 16-byte words)
 constexpr int kCTmemCols = 512;
 static_assert(kCSlots * kCSlotCols * (kCParkWarps / 4) == kCTmemCols, "TMEM columns");
 static_assert(kClusterMaxChunks <= kCSlots, "a slice must fit the TMEM slots");
@@ -147,10 +148,11 @@ __device__ __forceinline__ float warp_max_uniform(float v) {
 
 // ---------------------------------------------------------------- statistics of a part of a row
 // NL losses share the raw maxima; sums are relative to them
+// (dd = sum (et - es), accumulated term by term: common.cuh, "KL without cancellation")
 template <int NL>
 struct PStat {
     float ms, mt;
-    float zs[NL], zt[NL], a[NL];
+    float zs[NL], zt[NL], a[NL], dd[NL];
 };
 template <int NL>
 __device__ __forceinline__ PStat<NL> pstat_empty() {
@@ -158,20 +160,33 @@ __device__ __forceinline__ PStat<NL> pstat_empty() {
     r.ms = kMaxFloor;
     r.mt = kMaxFloor;
 #pragma unroll
-    for (int k = 0; k < NL; ++k) r.zs[k] = r.zt[k] = r.a[k] = 0.f;
+    for (int k = 0; k < NL; ++k) r.zs[k] = r.zt[k] = r.a[k] = r.dd[k] = 0.f;
     return r;
 }
 // exp2((x - ref) * c2[k]) for every loss; R == 2: c2[0] == 2*c2[1], so e[0] = e[1]^2 (one ex2 for both)
 template <int NL, int R>
 __device__ __forceinline__ void exps(float x, float ref, const float (&c2)[NL], float (&e)[NL]) {
+    // (fl(x c2) - fl(ref c2), not (x - ref) c2: the per-element exponents are taken against fl(ref c2))
     if (NL == 1) {
-        e[0] = fast_exp2((x - ref) * c2[0]);
+        e[0] = ref_factor(x, ref, c2[0]);
     } else if (R == 2) {
-        e[NL - 1] = fast_exp2((x - ref) * c2[NL - 1]);
+        e[NL - 1] = ref_factor(x, ref, c2[NL - 1]);
         e[0] = e[NL - 1] * e[NL - 1];
     } else {
 #pragma unroll
-        for (int k = 0; k < NL; ++k) e[k] = fast_exp2((x - ref) * c2[k]);
+        for (int k = 0; k < NL; ++k) e[k] = ref_factor(x, ref, c2[k]);
+    }
+}
+// ft - fs per loss for sums taken against (ms, mt) that move to the references (Ms, Mt): see factor_diff
+template <int NL, int R>
+__device__ __forceinline__ void factor_diffs(float ms, float mt, float Ms, float Mt, const float (&c2)[NL],
+                                             const float (&fs)[NL], const float (&ft)[NL], float (&df)[NL]) {
+    if (NL == 2 && R == 2) {
+        df[NL - 1] = factor_diff(fs[NL - 1], ft[NL - 1], ref_gap2(ms, mt, c2[NL - 1]) - ref_gap2(Ms, Mt, c2[NL - 1]));
+        df[0] = df[NL - 1] * (ft[NL - 1] + fs[NL - 1]);      // fs[0] = fs[1]^2, ft[0] = ft[1]^2
+    } else {
+#pragma unroll
+        for (int k = 0; k < NL; ++k) df[k] = factor_diff(fs[k], ft[k], ref_gap2(ms, mt, c2[k]) - ref_gap2(Ms, Mt, c2[k]));
     }
 }
 // the same with the references pre-multiplied (ref2[k] = ref * c2[k]): one FFMA per exponent
@@ -199,14 +214,16 @@ __device__ __forceinline__ PStat<NL> pstat_reduce(const PStat<NL>& x, const floa
         r.ms = fmaxf(r.ms, __shfl_xor_sync(0xffffffffu, r.ms, o));
         r.mt = fmaxf(r.mt, __shfl_xor_sync(0xffffffffu, r.mt, o));
     }
-    float fs[NL], ft[NL];
+    float fs[NL], ft[NL], df[NL];
     exps<NL, R>(x.ms, r.ms, c2, fs);
     exps<NL, R>(x.mt, r.mt, c2, ft);
+    factor_diffs<NL, R>(x.ms, x.mt, r.ms, r.mt, c2, fs, ft, df);
 #pragma unroll
     for (int k = 0; k < NL; ++k) {
         r.zs[k] = x.zs[k] * fs[k];
         r.zt[k] = x.zt[k] * ft[k];
         r.a[k] = x.a[k] * ft[k];
+        r.dd[k] = fmaf(x.zs[k], df[k], x.dd[k] * ft[k]);
     }
 #pragma unroll
     for (int o = WIDTH >> 1; o > 0; o >>= 1) {
@@ -215,6 +232,7 @@ __device__ __forceinline__ PStat<NL> pstat_reduce(const PStat<NL>& x, const floa
             r.zs[k] += __shfl_xor_sync(0xffffffffu, r.zs[k], o);
             r.zt[k] += __shfl_xor_sync(0xffffffffu, r.zt[k], o);
             r.a[k] += __shfl_xor_sync(0xffffffffu, r.a[k], o);
+            r.dd[k] += __shfl_xor_sync(0xffffffffu, r.dd[k], o);
         }
     }
     return r;
@@ -230,26 +248,33 @@ __device__ __forceinline__ PStat<NL> pstat_merge(const PStat<NL>& x, const PStat
     exps<NL, R>(y.ms, r.ms, c2, fys);
     exps<NL, R>(x.mt, r.mt, c2, fxt);
     exps<NL, R>(y.mt, r.mt, c2, fyt);
+    float dfx[NL], dfy[NL];
+    factor_diffs<NL, R>(x.ms, x.mt, r.ms, r.mt, c2, fxs, fxt, dfx);
+    factor_diffs<NL, R>(y.ms, y.mt, r.ms, r.mt, c2, fys, fyt, dfy);
 #pragma unroll
     for (int k = 0; k < NL; ++k) {
         r.zs[k] = __fadd_rn(__fmul_rn(x.zs[k], fxs[k]), __fmul_rn(y.zs[k], fys[k]));
         r.zt[k] = __fadd_rn(__fmul_rn(x.zt[k], fxt[k]), __fmul_rn(y.zt[k], fyt[k]));
         r.a[k] = __fadd_rn(__fmul_rn(x.a[k], fxt[k]), __fmul_rn(y.a[k], fyt[k]));
+        r.dd[k] = __fadd_rn(fmaf(x.zs[k], dfx[k], __fmul_rn(x.dd[k], fxt[k])), fmaf(y.zs[k], dfy[k], __fmul_rn(y.dd[k], fyt[k])));
     }
     return r;
 }
+// record layout: {ms, mt, zs0, zt0} {a0, dd0, zs1, zt1} {a1, dd1, -, -}
 template <int NL>
-__device__ __forceinline__ PStat<NL> pstat_from(const float4& r0, const float4& r1) {
+__device__ __forceinline__ PStat<NL> pstat_from(const float4& r0, const float4& r1, const float4& r2) {
     PStat<NL> x;
     x.ms = r0.x;
     x.mt = r0.y;
     x.zs[0] = r0.z;
     x.zt[0] = r0.w;
     x.a[0] = r1.x;
+    x.dd[0] = r1.y;
     if (NL == 2) {
-        x.zs[NL - 1] = r1.y;
-        x.zt[NL - 1] = r1.z;
-        x.a[NL - 1] = r1.w;
+        x.zs[NL - 1] = r1.z;
+        x.zt[NL - 1] = r1.w;
+        x.a[NL - 1] = r2.x;
+        x.dd[NL - 1] = r2.y;
     }
     return x;
 }
@@ -274,9 +299,9 @@ __device__ __forceinline__ float warp_sum8_transposed(const float (&v)[8], int l
     t += __shfl_xor_sync(0xffffffffu, t, 1);
     return t;
 }
-__device__ __forceinline__ float kl_of_row(float inv_tau, float ms, float mt, float zs, float zt, float a) {
-    // KL(p||q) = sum p (t - s)/tau - lse_t + lse_s
-    return inv_tau * a / zt - ((mt - ms) * inv_tau + (logf(zt) - logf(zs)));
+__device__ __forceinline__ float kl_of_row(float inv_tau, float c2, float ms, float mt, float zs, float zt, float a, float dd) {
+    // KL(p||q) = sum p (t - s)/tau - (lse_t - lse_s), the difference of the log-sum-exps without cancellation
+    return kl_from_stats(inv_tau, ref_gap2(ms, mt, c2), zs, zt, a, dd);
 }
 
 // ---------------------------------------------------------------- geometry
@@ -308,7 +333,7 @@ struct SliceGeo {
     int r_first;           // first row of l[0] (within the super-row) that intersects it
     int n_pieces;          // rows of l[0] that intersect it
     int nchunks;
-    uint32_t xch_bytes;    // summaries all CTAs of the cluster push for this super-row (32 bytes a piece)
+    uint32_t xch_pieces;   // summaries all CTAs of the cluster push for this super-row
 };
 __device__ __forceinline__ int pieces_of(const ClusterGeom& g, int lv, int c) {
     const int cv0 = min(lv, c * g.slv), cv1 = min(lv, cv0 + g.slv);
@@ -328,7 +353,7 @@ __device__ __forceinline__ SliceGeo slice_geo(const ClusterGeom& g, int lv, int 
         total = 0;
         for (int c = 0; c < g.nc; ++c) total += pieces_of(g, lv, c);
     }
-    s.xch_bytes = (uint32_t)total * 32u;
+    s.xch_pieces = (uint32_t)total;
     return s;
 }
 // end of piece pc, in vectors of the slice
@@ -541,7 +566,7 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
             PStat<NL> x = pstat_empty<NL>();
             if (off >= 0) {
                 const float4* q = reinterpret_cast<const float4*>(base + off);
-                x = pstat_from<NL>(q[0], q[1]);
+                x = pstat_from<NL>(q[0], q[1], NL == 2 ? q[2] : make_float4(0.f, 0.f, 0.f, 0.f));
             }
             return x;
         };
@@ -556,8 +581,8 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
             const bool full = lv == lv_full;
             const SliceGeo s = full ? geo_full : slice_geo(g, lv, (int)rank);
             const StatPlan pl = full ? plan_full : make_plan(lv, s);
-            // this row's summaries: 32 bytes per piece of every CTA of the cluster will land in summ[par]
-            if (lane == 0) mbar_arrive_expect_tx(&sm.xch[par], s.xch_bytes);
+            // this row's summaries: 32 (one loss) / 48 bytes per piece of every CTA of the cluster will land in summ[par]
+            if (lane == 0) mbar_arrive_expect_tx(&sm.xch[par], s.xch_pieces * (NL == 2 ? 48u : 32u));
             mbar_wait(&sm.recbar[par], ph);
             SD_TICK(t1);
             // ---- 8 warp records -> one summary per piece, four pieces per pass (8 lanes each);
@@ -570,7 +595,8 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
                     const uint32_t off = (uint32_t)(((par * kClusterMaxSize) * kCMaxPieces + pc) * kCRecFloats * 4);
                     const uint32_t dst = push_dst + off, bar = push_bar + (uint32_t)par * 8u;
                     st_async_f4(dst, make_float4(st.ms, st.mt, st.zs[0], st.zt[0]), bar);
-                    st_async_f4(dst + 16, make_float4(st.a[0], st.zs[NL - 1], st.zt[NL - 1], st.a[NL - 1]), bar);
+                    st_async_f4(dst + 16, make_float4(st.a[0], st.dd[0], st.zs[NL - 1], st.zt[NL - 1]), bar);
+                    if (NL == 2) st_async_f4(dst + 32, make_float4(st.a[NL - 1], st.dd[NL - 1], 0.f, 0.f), bar);
                 }
             }
             SD_TICK(t2);
@@ -612,14 +638,14 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
             SD_TICK(t4);
             // ---- off the critical path: the KL terms of the rows this CTA accounts for
             if (NL == 2 && lane == 0 && rank == 0) {
-                const float kl = kl_of_row(p.l[K].inv_tau, sr.ms, sr.mt, sr.zs[K], sr.zt[K], sr.a[K]);
+                const float kl = kl_of_row(p.l[K].inv_tau, c2[K], sr.ms, sr.mt, sr.zs[K], sr.zt[K], sr.a[K], sr.dd[K]);
                 if (p.l[K].row_kl) p.l[K].row_kl[rc.b * p.l[K].G + rc.grp] = kl;
                 kl_acc[K] += kl;
             }
 #pragma unroll
             for (int q = 0; q < kPrPasses; ++q) {
                 if ((lane & 7) == 0 && pl.pr_row[q] >= 0 && (int)rank == pl.pr_ca[q]) {
-                    const float kl = kl_of_row(p.l[0].inv_tau, pr[q].ms, pr[q].mt, pr[q].zs[0], pr[q].zt[0], pr[q].a[0]);
+                    const float kl = kl_of_row(p.l[0].inv_tau, c2[0], pr[q].ms, pr[q].mt, pr[q].zs[0], pr[q].zt[0], pr[q].a[0], pr[q].dd[0]);
                     const int rowi = NL == 2 ? rc.b * p.l[0].G + rc.grp * p.l[NL - 1].m + pl.pr_row[q] : rc.b * p.l[0].G + rc.grp;
                     if (p.l[0].row_kl) p.l[0].row_kl[rowi] = kl;
                     kl_acc[0] += kl;
@@ -704,15 +730,16 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
 
         // a piece ends: the warp's record (maxima + 3 sums per loss)
         auto close_piece = [&]() {
-            float v[8] = {st.zs[0], st.zt[0], st.a[0], 0.f, 0.f, 0.f, 0.f, 0.f};
+            float v[8] = {st.zs[0], st.zt[0], st.a[0], st.dd[0], 0.f, 0.f, 0.f, 0.f};
             if (NL == 2) {
-                v[3] = st.zs[NL - 1];
-                v[4] = st.zt[NL - 1];
-                v[5] = st.a[NL - 1];
+                v[4] = st.zs[NL - 1];
+                v[5] = st.zt[NL - 1];
+                v[6] = st.a[NL - 1];
+                v[7] = st.dd[NL - 1];
             }
             const float tot = warp_sum8_transposed(v, lane);
             float* rec = sm.rec[itA & 1][pcA][pw];
-            if ((lane & 3) == 0 && lane < 4 * 3 * NL) rec[2 + (lane >> 2)] = tot;
+            if ((lane & 3) == 0 && lane < 4 * 4 * NL) rec[2 + (lane >> 2)] = tot;
             if (lane == 1) rec[0] = st.ms;
             if (lane == 2) rec[1] = st.mt;
             st = pstat_empty<NL>();
@@ -723,11 +750,13 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
         auto raise_refs = [&](float wms, float wmt) {
             const float nms = fmaxf(st.ms, wms), nmt = fmaxf(st.mt, wmt);
             if (nms != st.ms || nmt != st.mt) {      // warp-uniform
-                float rs[NL], rt[NL];
+                float rs[NL], rt[NL], df[NL];
                 exps<NL, R>(st.ms, nms, c2, rs);
                 exps<NL, R>(st.mt, nmt, c2, rt);
+                factor_diffs<NL, R>(st.ms, st.mt, nms, nmt, c2, rs, rt, df);
 #pragma unroll
                 for (int k = 0; k < NL; ++k) {
+                    st.dd[k] = fmaf(st.zs[k], df[k], st.dd[k] * rt[k]);
                     st.zs[k] *= rs[k];
                     st.zt[k] *= rt[k];
                     st.a[k] *= rt[k];
@@ -741,8 +770,8 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
             float refs2[NL], reft2[NL];
 #pragma unroll
             for (int k = 0; k < NL; ++k) {
-                refs2[k] = st.ms * c2[k];
-                reft2[k] = st.mt * c2[k];
+                refs2[k] = __fmul_rn(st.ms, c2[k]);
+                reft2[k] = __fmul_rn(st.mt, c2[k]);
             }
 #pragma unroll
             for (int i = 0; i < NE; ++i) {
@@ -756,6 +785,14 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
                         st.zs[k] += es[k];
                         st.zt[k] += et[k];
                         st.a[k] = fmaf(et[k], d, st.a[k]);
+                    }
+                    if (NL == 2 && R == 2) {
+                        const float dk = et[K] - es[K];          // et0 - es0 = (et1 - es1)(et1 + es1)
+                        st.dd[K] += dk;
+                        st.dd[0] = fmaf(dk, et[K] + es[K], st.dd[0]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < NL; ++k) st.dd[k] += et[k] - es[k];
                     }
                     if (kParkExp) {
                         fs[i] = es[K];
@@ -914,11 +951,11 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
                 }
                 if (kParkExp) {
                     // parked: e = exp2((x - ref) c2[K]); softmax_k = e^(c2[k]/c2[K]) * exp2((ref - M_k) c2[k]) / Z_k, ref <= M_k
-                    const float gsK = (NL == 2 ? fb.z : fa.z) * fast_exp2((ref_s - (NL == 2 ? fb.x : fa.x)) * c2[K]);
-                    const float gtK = (NL == 2 ? fb.w : fa.w) * fast_exp2((ref_t - (NL == 2 ? fb.y : fa.y)) * c2[K]);
+                    const float gsK = (NL == 2 ? fb.z : fa.z) * ref_factor(ref_s, NL == 2 ? fb.x : fa.x, c2[K]);
+                    const float gtK = (NL == 2 ? fb.w : fa.w) * ref_factor(ref_t, NL == 2 ? fb.y : fa.y, c2[K]);
                     if (NL == 2) {
-                        const float gs0 = fa.z * fast_exp2((ref_s - fa.x) * c2[0]);
-                        const float gt0 = fa.w * fast_exp2((ref_t - fa.y) * c2[0]);
+                        const float gs0 = fa.z * ref_factor(ref_s, fa.x, c2[0]);
+                        const float gt0 = fa.w * ref_factor(ref_t, fa.y, c2[0]);
 #pragma unroll
                         for (int q = 0; q < VE; ++q) o[q] = fs[q] * fmaf(fs[q], gs0, gsK) - ft[q] * fmaf(ft[q], gt0, gtK);
                     } else {
@@ -927,8 +964,8 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
                     }
                 } else {
                     // raw values parked: recompute against the row maxima
-                    const float rs0 = fa.x * c2[0], rt0 = fa.y * c2[0];
-                    const float rs1 = fb.x * c2[K], rt1 = fb.y * c2[K];
+                    const float rs0 = __fmul_rn(fa.x, c2[0]), rt0 = __fmul_rn(fa.y, c2[0]);
+                    const float rs1 = __fmul_rn(fb.x, c2[K]), rt1 = __fmul_rn(fb.y, c2[K]);
 #pragma unroll
                     for (int q = 0; q < VE; ++q) {
                         const float es0 = fast_exp2(fmaf(fs[q], c2[0], -rs0));
@@ -964,10 +1001,10 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
                 if (vA + (kCChunkRows - 1) * kCPark < pv1) {
                     if (kParkExp && NL == 2) {
                         // all vector-rows in one piece, parked against the same references: the four factors once
-                        const float gsK = fb.z * fast_exp2((rf[0] - fb.x) * c2[K]);
-                        const float gtK = fb.w * fast_exp2((rf[1] - fb.y) * c2[K]);
-                        const float gs0 = fa.z * fast_exp2((rf[0] - fa.x) * c2[0]);
-                        const float gt0 = fa.w * fast_exp2((rf[1] - fa.y) * c2[0]);
+                        const float gsK = fb.z * ref_factor(rf[0], fb.x, c2[K]);
+                        const float gtK = fb.w * ref_factor(rf[1], fb.y, c2[K]);
+                        const float gs0 = fa.z * ref_factor(rf[0], fa.x, c2[0]);
+                        const float gt0 = fa.w * ref_factor(rf[1], fa.y, c2[0]);
 #pragma unroll
                         for (int r = 0; r < kCChunkRows; ++r) {
                             float o[VE];
@@ -1028,13 +1065,15 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
 template <typename T, int NL, int R>
 static cudaError_t launch_cluster_t(const RowsParams& p, ClusterGeom g, int sms, cudaStream_t stream, bool probe_only) {
     auto kern = kl_rows_cluster_kernel<T, NL, R>;
-    static bool configured = false;      // per instantiation
-    static int max_clusters[kClusterMaxSize + 1] = {0};
-    if (!configured) {
+    static std::atomic<bool> configured[kMaxDevices];      // per instantiation and device
+    static std::atomic<int> max_clusters_dev[kMaxDevices][kClusterMaxSize + 1];
+    const int dev = device_slot();
+    if (!configured[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemBytes);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev].store(true, std::memory_order_release);
     }
+    std::atomic<int>* max_clusters = max_clusters_dev[dev];
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(kCThreads);
     cfg.dynamicSmemBytes = kClusterSmemBytes;

@@ -27,6 +27,7 @@
 // exponentials (4 ex2 per element and loss instead of 2).  Two CTAs per SM (<= 64 registers, a 3-stage
 // 84 KB ring each).  NL = 2 serves two losses with nested rows (CD + CGD on the same logits).
 #include "rows_common.cuh"
+#include "launch.h"
 
 namespace sd {
 
@@ -40,8 +41,9 @@ constexpr int kSSlotBytes = kSSlotVecs * 16;
 constexpr int kSStageBytes = 2 * kSSlotBytes;      // S + T
 constexpr int kSStages = 3;
 constexpr int kSBars = 2 * kSStages + 8;           // full, empty, part_ready[2], part_free[2], stat_ready[2], stat_free[2]
+constexpr int kSRec = 12;                          // warp record: ms, mt, {zs, zt, a, dd} x NL; [6]: sq (MSE, NL == 1)
 constexpr size_t kStreamSmemBytes = (size_t)kSStages * kSStageBytes + kSBars * sizeof(uint64_t) +
-                                    2 * 16 * kRedFloats * sizeof(float) + 2 * kMaxLosses * 8 * sizeof(float);
+                                    2 * 16 * kSRec * sizeof(float) + 2 * kMaxLosses * 8 * sizeof(float);
 
 template <typename T, int NL, bool MSE>
 __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const RowsParams p) {
@@ -59,8 +61,8 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
     uint64_t* part_free = part_ready + 2;      // [2] the control warp has read them
     uint64_t* stat_ready = part_free + 2;      // [2] row statistics of a phase-2 unit are in bcast
     uint64_t* stat_free = stat_ready + 2;      // [2] every consumer warp has read them
-    float* red = reinterpret_cast<float*>(full + kSBars);  // [2][16][kRedFloats]
-    float* bcast = red + 2 * 16 * kRedFloats;              // [2][kMaxLosses][8]
+    float* red = reinterpret_cast<float*>(full + kSBars);  // [2][16][kSRec]
+    float* bcast = red + 2 * 16 * kSRec;                   // [2][kMaxLosses][8]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -195,18 +197,20 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
                     RowStat acc = rowstat_empty();
                     for (int j = lane; j < rown; j += 32) {
                         const unsigned long long* q = p.pkt + (size_t)(rowu + j) * kPktWords + 6 * k;
-                        unsigned long long w[5];
+                        unsigned long long w[6];
                         unsigned spins = 0;
                         for (;;) {
                             bool ok = true;
 #pragma unroll
-                            for (int i = 0; i < 5; ++i) {
+                            for (int i = 0; i < 6; ++i) {
                                 w[i] = ld_relaxed_u64(q + i);
                                 ok = ok && (unsigned)(w[i] >> 32) == epoch;
                             }
                             if (ok) break;
                             if (++spins > kSpinLimit) {
-                                atomicExch(&p.ctrl[1], 1u);  // never expected: reported by the host wrapper
+                                // never expected (the launch is cooperative: every CTA is resident).  The flag makes
+                                // the last CTA report NaN losses instead of numbers built on a stale packet.
+                                atomicExch(&p.ctrl[1], 1u);
                                 break;
                             }
                             __nanosleep(64);
@@ -217,6 +221,7 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
                         r.mt = __uint_as_float((unsigned)w[2]);
                         r.zt = __uint_as_float((unsigned)w[3]);
                         r.a = __uint_as_float((unsigned)w[4]);
+                        r.dd = __uint_as_float((unsigned)w[5]);
                         acc = rowstat_merge(acc, r, p.l[k].c2);
                     }
 #pragma unroll
@@ -227,20 +232,20 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
                         other.mt = __shfl_xor_sync(0xffffffffu, acc.mt, o);
                         other.zt = __shfl_xor_sync(0xffffffffu, acc.zt, o);
                         other.a = __shfl_xor_sync(0xffffffffu, acc.a, o);
+                        other.dd = __shfl_xor_sync(0xffffffffu, acc.dd, o);
                         acc = rowstat_merge(acc, other, p.l[k].c2);
                     }
                     if (lane == 0) {
                         float coef = p.l[k].coef;
                         if (p.grad_out[k] != nullptr) coef *= __ldg(p.grad_out[k]);
                         float* b = bcast + (par2 * kMaxLosses + k) * 8;
-                        b[0] = acc.ms * p.l[k].c2;
+                        b[0] = __fmul_rn(acc.ms, p.l[k].c2);
                         b[1] = coef / acc.zs;
-                        b[2] = acc.mt * p.l[k].c2;
+                        b[2] = __fmul_rn(acc.mt, p.l[k].c2);
                         b[3] = coef / acc.zt;
                         if (u == rowu) {
-                            // KL(p||q) = sum p (t - s)/tau - lse_t + lse_s
-                            const float kl = p.l[k].inv_tau * acc.a / acc.zt -
-                                             ((acc.mt - acc.ms) * p.l[k].inv_tau + (logf(acc.zt) - logf(acc.zs)));
+                            const float kl = kl_from_stats(p.l[k].inv_tau, ref_gap2(acc.ms, acc.mt, p.l[k].c2), acc.zs, acc.zt,
+                                                           acc.a, acc.dd);
                             if (p.l[k].row_kl) p.l[k].row_kl[rowi] = kl;
                             cta_kl[k] += kl;
                         }
@@ -253,32 +258,38 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
             if (has1) {
                 // ---- merge the consumer warps' records of the phase-1 unit, publish its packet
                 mbar_wait(&part_ready[par1], ph1);
-                const float* q = red + (par1 * 16 + (lane < kSConsWarps ? lane : 0)) * kRedFloats;
+                const float* q = red + (par1 * 16 + (lane < kSConsWarps ? lane : 0)) * kSRec;
                 const float4 r0 = reinterpret_cast<const float4*>(q)[0];
                 const float4 r1 = reinterpret_cast<const float4*>(q)[1];
+                const float4 r2 = reinterpret_cast<const float4*>(q)[2];
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&part_free[par1]);
                 const bool live = lane < kSConsWarps;
-                const float rr[kRedFloats] = {live ? r0.x : -INFINITY, live ? r0.y : -INFINITY, live ? r0.z : 0.f,
-                                              live ? r0.w : 0.f,       live ? r1.x : 0.f,       live ? r1.y : 0.f,
-                                              live ? r1.z : 0.f,       live ? r1.w : 0.f};
-                const float Ms = warp_max(rr[0]);
-                const float Mt = warp_max(rr[1]);
+                const float rms = live ? r0.x : -INFINITY, rmt = live ? r0.y : -INFINITY;
+                // {zs, zt, a, dd} of loss k: r0.zw r1.xy, r1.zw r2.xy
+                const float rz[kMaxLosses][4] = {{r0.z, r0.w, r1.x, r1.y}, {r1.z, r1.w, r2.x, r2.y}};
+                const float Ms = warp_max(rms);
+                const float Mt = warp_max(rmt);
                 float val = 0.f;
 #pragma unroll
                 for (int k = 0; k < NL; ++k) {
-                    const float fs = live ? fast_exp2((rr[0] - Ms) * p.l[k].c2) : 0.f;
-                    const float ft = live ? fast_exp2((rr[1] - Mt) * p.l[k].c2) : 0.f;
-                    const float Zs = warp_sum(rr[2 + 3 * k] * fs);
-                    const float Zt = warp_sum(rr[3 + 3 * k] * ft);
-                    const float A = warp_sum(rr[4 + 3 * k] * ft);
+                    const float c2k = p.l[k].c2;
+                    const float fs = live ? ref_factor(rms, Ms, c2k) : 0.f;
+                    const float ft = live ? ref_factor(rmt, Mt, c2k) : 0.f;
+                    const float gx = live ? ref_gap2(rms, rmt, c2k) - ref_gap2(Ms, Mt, c2k) : 1.f;
+                    const float zsk = live ? rz[k][0] : 0.f;
+                    const float Zs = warp_sum(zsk * fs);
+                    const float Zt = warp_sum((live ? rz[k][1] : 0.f) * ft);
+                    const float A = warp_sum((live ? rz[k][2] : 0.f) * ft);
+                    const float DD = warp_sum(fmaf(zsk, factor_diff(fs, ft, gx), (live ? rz[k][3] : 0.f) * ft));
                     if (lane == 6 * k + 0) val = Ms;
                     if (lane == 6 * k + 1) val = Zs;
                     if (lane == 6 * k + 2) val = Mt;
                     if (lane == 6 * k + 3) val = Zt;
                     if (lane == 6 * k + 4) val = A;
+                    if (lane == 6 * k + 5) val = DD;
                 }
-                if (MSE) cta_sq += warp_sum(rr[5]);
+                if (MSE) cta_sq += warp_sum(live ? r1.z : 0.f);
                 if (lane < 6 * NL)
                     st_relaxed_u64(p.pkt + (size_t)c1.u * kPktWords + lane,
                                    ((unsigned long long)epoch << 32) | __float_as_uint(val));
@@ -312,8 +323,13 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
                 for (int k = 0; k <= NL; ++k) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
             }
             if (lane == 0) {
+                // a control warp that gave up waiting for a packet (ctrl[1]) built statistics on stale data: the
+                // losses of this launch are reported as NaN - visible to the caller without a synchronisation -
+                // and the flag stays set (the Python binding's workspace_error_flag() reads it)
+                const bool timed_out = __ldcg(&p.ctrl[1]) != 0u;
 #pragma unroll
-                for (int k = 0; k < NL; ++k) *p.l[k].loss = (float)((double)p.l[k].loss_scale * acc[k]);
+                for (int k = 0; k < NL; ++k)
+                    *p.l[k].loss = timed_out ? __int_as_float(0x7fc00000) : (float)((double)p.l[k].loss_scale * acc[k]);
                 if (MSE && p.mse_loss) *p.mse_loss = (float)((double)p.mse_scale * acc[NL]);
                 atomicAdd(&p.ctrl[2], 1u);
                 atomicExch(&p.ctrl[0], 0u);
@@ -377,15 +393,16 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
                 }
             }
             // pass B: exponentials against the local maxima, partial sums; the slots are handed back
-            float zs[NL], zt[NL], a[NL], sq = 0.f;
+            // (dd = sum (et - es) term by term, common.cuh; against thread-local maxima zs = zt - dd is exact enough)
+            float zt[NL], dd[NL], a[NL], sq = 0.f;
             float ms2[NL], mt2[NL];
 #pragma unroll
             for (int k = 0; k < NL; ++k) {
-                zs[k] = 0.f;
                 zt[k] = 0.f;
+                dd[k] = 0.f;
                 a[k] = 0.f;
-                ms2[k] = ms * p.l[k].c2;
-                mt2[k] = mt * p.l[k].c2;
+                ms2[k] = __fmul_rn(ms, p.l[k].c2);
+                mt2[k] = __fmul_rn(mt, p.l[k].c2);
             }
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
@@ -414,8 +431,8 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
                                 for (int k = 0; k < NL; ++k) {
                                     const float es = fast_exp2(fmaf(fs[q], p.l[k].c2, -ms2[k]));
                                     const float et = fast_exp2(fmaf(ft[q], p.l[k].c2, -mt2[k]));
-                                    zs[k] += es;
                                     zt[k] += et;
+                                    dd[k] += et - es;
                                     a[k] = fmaf(et, d, a[k]);
                                 }
                             }
@@ -428,26 +445,30 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
             }
             // warp record: raw maxima are common to all losses, sums are rescaled to them
             const float msw = warp_max(ms), mtw = warp_max(mt);
-            float rec[kRedFloats];
+            float rec[kSRec];
 #pragma unroll
-            for (int i = 0; i < kRedFloats; ++i) rec[i] = 0.f;
+            for (int i = 0; i < kSRec; ++i) rec[i] = 0.f;
             rec[0] = msw;
             rec[1] = mtw;
 #pragma unroll
             for (int k = 0; k < NL; ++k) {
-                const float fs = fast_exp2((ms - msw) * p.l[k].c2);
-                const float ft = fast_exp2((mt - mtw) * p.l[k].c2);
-                rec[2 + 3 * k] = warp_sum(zs[k] * fs);
-                rec[3 + 3 * k] = warp_sum(zt[k] * ft);
-                rec[4 + 3 * k] = warp_sum(a[k] * ft);
+                const float c2k = p.l[k].c2;
+                const float fs = ref_factor(ms, msw, c2k);
+                const float ft = ref_factor(mt, mtw, c2k);
+                const float zs = zt[k] - dd[k];
+                rec[2 + 4 * k] = warp_sum(zs * fs);
+                rec[3 + 4 * k] = warp_sum(zt[k] * ft);
+                rec[4 + 4 * k] = warp_sum(a[k] * ft);
+                rec[5 + 4 * k] = warp_sum(fmaf(zs, factor_diff(fs, ft, (mt2[k] - ms2[k]) - ref_gap2(msw, mtw, c2k)), dd[k] * ft));
             }
-            if (MSE) rec[5] = warp_sum(sq);
+            if (MSE) rec[6] = warp_sum(sq);
             const int par1 = step & 1;
             if (lane == 0) {
                 mbar_wait(&part_free[par1], ((uint32_t)(step >> 1) & 1u) ^ 1u);
-                float* my_red = red + (par1 * 16 + warp) * kRedFloats;
+                float* my_red = red + (par1 * 16 + warp) * kSRec;
                 reinterpret_cast<float4*>(my_red)[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
                 reinterpret_cast<float4*>(my_red)[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+                reinterpret_cast<float4*>(my_red)[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
                 mbar_arrive(&part_ready[par1]);
             }
             c1.advance(p, grid);
@@ -524,7 +545,8 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
 template <typename T, int NL, bool MSE>
 static cudaError_t launch_stream_t(const RowsParams& p, int sms, cudaStream_t stream) {
     auto kern = kl_rows_stream_kernel<T, NL, MSE>;
-    static int ctas_per_sm = 0;  // per instantiation
+    static std::atomic<int> ctas_per_sm_dev[kMaxDevices];  // per instantiation and device
+    std::atomic<int>& ctas_per_sm = ctas_per_sm_dev[device_slot()];
     if (ctas_per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamSmemBytes);
         if (e != cudaSuccess) return e;

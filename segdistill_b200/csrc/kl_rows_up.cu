@@ -23,6 +23,7 @@
 //
 // Deterministic (no floating-point atomics); fp32 arithmetic; dS has the dtype and the (low) resolution of S.
 #include "common.cuh"
+#include "launch.h"
 #include "params.h"
 
 namespace sd {
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_stats_kernel(const UpPa
         // between cells - the unit is redone below against the exact maximum.)
         ms = block_max(ms, red);
         mt = block_max(mt, red);
-        float zs, zt, acc;
+        float zs, zt, acc, dd;     // dd = sum (et - es) term by term (common.cuh: KL without cancellation)
         for (int attempt = 0;; ++attempt) {
             // sweep over the (small) strip: values -> exponents relative to the references (the redo reloads the raw
             // values: exponents thousands below the old reference have lost their low bits)
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_stats_kernel(const UpPa
             zs = 0.f;
             zt = 0.f;
             acc = 0.f;
+            dd = 0.f;
             const int ncell = (x.i1 - x.i0) * p.Wl;
             for (int c = threadIdx.x; c < ncell; c += kUpThreads) {
                 int i, j;
@@ -249,12 +251,14 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_stats_kernel(const UpPa
                         zs += es;
                         zt += et;
                         acc = fmaf(et, vt - vs, acc);
+                        dd += et - es;
                     }
                 }
             }
             zs = block_sum(zs, red);
             zt = block_sum(zt, red);
             acc = block_sum(acc, red);
+            dd = block_sum(dd, red);
             if (attempt > 0 || (zs >= 1e-20f && zt >= 1e-20f)) break;      // (uniform over the CTA)
             // ---- rare: EXACT maximum of the up-sampled values of my cells.  Between four cell centres the interpolant
             // is bilinear, and a bilinear patch takes its extremes at the corners of any axis-aligned rectangle of
@@ -305,7 +309,7 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_stats_kernel(const UpPa
         if (threadIdx.x == 0) {
             float4* rec = reinterpret_cast<float4*>(p.part + u * 8);
             rec[0] = make_float4(ms, mt, zs, zt);
-            rec[1] = make_float4(acc, 0.f, 0.f, 0.f);
+            rec[1] = make_float4(acc, dd, 0.f, 0.f);
         }
     }
 }
@@ -349,27 +353,31 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_grad_kernel(const UpPar
             ls = warp_max(ls);
             lt = warp_max(lt);
             const float ms = bs + ls * p.inv_c2, mt = bt + lt * p.inv_c2;     // used consistently from here on
-            float zs = 0.f, zt = 0.f, acc = 0.f;
+            float zs = 0.f, zt = 0.f, acc = 0.f, dd = 0.f;
+            const float gap = mt - ms;                                         // (exact when S ~ T)
             for (int r = lane; r < nrec; r += 32) {
                 const float4 q0 = *reinterpret_cast<const float4*>(p.part + (first + r) * 8);
-                const float a = p.part[(first + r) * 8 + 4];
+                const float2 q1 = *reinterpret_cast<const float2*>(p.part + (first + r) * 8 + 4);
                 const float fs = fast_exp2((q0.x - ms) * p.c2), ft = fast_exp2((q0.y - mt) * p.c2);
                 zs = fmaf(q0.z, fs, zs);
                 zt = fmaf(q0.w, ft, zt);
                 // a is sum et (t - s) against the unit's reference; (t - s) needs no shift, et scales like zt
-                acc = fmaf(a, ft, acc);
+                acc = fmaf(q1.x, ft, acc);
+                // zt ft - zs fs = dd ft + zs (ft - fs), the factor difference from the small exponent gap
+                dd = fmaf(q0.z, factor_diff(fs, ft, ((q0.y - q0.x) - gap) * p.c2), fmaf(q1.y, ft, dd));
             }
             zs = warp_sum(zs);
             zt = warp_sum(zt);
             acc = warp_sum(acc);
+            dd = warp_sum(dd);
             if (lane == 0) {
                 rowstat[0] = ms;
                 rowstat[1] = mt;
                 rowstat[2] = p.coef / zs;
                 rowstat[3] = p.coef / zt;
                 if (x.j == 0 && x.i0 == 0) {
-                    // KL(p||q) = sum p (t - s)/tau - lse_t + lse_s, once per row
-                    const float kl = p.inv_tau * acc / zt - ((mt - ms) * p.inv_tau + (logf(zt) - logf(zs)));
+                    // KL(p||q) = sum p (t - s)/tau - (lse_t - lse_s), once per row
+                    const float kl = kl_from_stats(p.inv_tau, gap * p.c2, zs, zt, acc, dd);
                     p.row_kl[x.b * p.G + x.grp] = kl;
                 }
             }
@@ -574,10 +582,12 @@ __global__ void __launch_bounds__(kPxThreads) kl_pixels_up_kernel(const UpParams
         for (int win = 0; win < NWIN; ++win) {
             if (NWIN > 1 && win != my_win) continue;          // (uniform over the CTA)
             const int ky0 = (win / (S / SB)) * SB, kx0 = (win % (S / SB)) * SB;
-            // ---------------- pass 1: per-pixel sums over the channels (reference = running maximum of the cell)
-            float zs[SB * SB], zt[SB * SB], ak[SB * SB];
+            // ---------------- pass 1: per-pixel sums over the channels (reference = running maximum of the cell).
+            // dd = sum (et - es) term by term (common.cuh: KL without cancellation); the sum p (t - s) term of the KL is
+            // collected in pass 2, where the probabilities exist (a scalar per thread instead of a register per pixel)
+            float zs[SB * SB], zt[SB * SB], dd[SB * SB];
 #pragma unroll
-            for (int q = 0; q < SB * SB; ++q) zs[q] = zt[q] = ak[q] = 0.f;
+            for (int q = 0; q < SB * SB; ++q) zs[q] = zt[q] = dd[q] = 0.f;
             float ref_s = kUpFloor, ref_t = kUpFloor;
             __syncthreads();
             load_chunk(0, 0);
@@ -602,24 +612,22 @@ __global__ void __launch_bounds__(kPxThreads) kl_pixels_up_kernel(const UpParams
 #pragma unroll
                             for (int e = 0; e < 3; ++e) mt = fmaxf(mt, a[d][e]);
                         up_hrows_win<S, SB>(a, kx0, ht);
-                        if (ms > ref_s) {
-                            const float f = fast_exp2((ref_s - ms) * p.c2);
-#pragma unroll
-                            for (int q = 0; q < SB * SB; ++q) zs[q] *= f;
-                            ref_s = ms;
-                        }
-                        if (mt > ref_t) {
-                            const float f = fast_exp2((ref_t - mt) * p.c2);
+                        if (ms > ref_s || mt > ref_t) {
+                            const float nrs = fmaxf(ref_s, ms), nrt = fmaxf(ref_t, mt);
+                            const float fs = ref_factor(ref_s, nrs, p.c2), ft = ref_factor(ref_t, nrt, p.c2);
+                            const float df = factor_diff(fs, ft, ref_gap2(ref_s, ref_t, p.c2) - ref_gap2(nrs, nrt, p.c2));
 #pragma unroll
                             for (int q = 0; q < SB * SB; ++q) {
-                                zt[q] *= f;
-                                ak[q] *= f;
+                                dd[q] = fmaf(zs[q], df, dd[q] * ft);
+                                zs[q] *= fs;
+                                zt[q] *= ft;
                             }
-                            ref_t = mt;
+                            ref_s = nrs;
+                            ref_t = nrt;
                         }
                         up_vdiff<SB>(hs, ds_);
                         up_vdiff<SB>(ht, dt_);
-                        const float rs2 = ref_s * p.c2, rt2 = ref_t * p.c2;
+                        const float rs2 = __fmul_rn(ref_s, p.c2), rt2 = __fmul_rn(ref_t, p.c2);
 #pragma unroll
                         for (int ky = 0; ky < SB; ++ky) {
 #pragma unroll
@@ -629,18 +637,20 @@ __global__ void __launch_bounds__(kPxThreads) kl_pixels_up_kernel(const UpParams
                                 const float es = fast_exp2(fmaf(vs, p.c2, -rs2)), et = fast_exp2(fmaf(vt, p.c2, -rt2));
                                 zs[ky * SB + kx] += es;
                                 zt[ky * SB + kx] += et;
-                                ak[ky * SB + kx] = fmaf(et, vt - vs, ak[ky * SB + kx]);
+                                dd[ky * SB + kx] += et - es;
                             }
                         }
                     }
                 }
             }
-            // KL of my pixels (owned cells only), then the sums become the gradient factors coef / Z
+            // the lse_t - lse_s part of the KL of my pixels (owned cells only), then the sums become the gradient
+            // factors coef / Z
             if (owned) {
+                const float gap = ref_gap2(ref_s, ref_t, p.c2) * kLn2;
 #pragma unroll
-                for (int q = 0; q < SB * SB; ++q)
-                    kl_acc += p.inv_tau * ak[q] / zt[q] - ((ref_t - ref_s) * p.inv_tau + (logf(zt[q]) - logf(zs[q])));
+                for (int q = 0; q < SB * SB; ++q) kl_acc -= gap + log1pf(dd[q] / zs[q]);
             }
+            float kl_a = 0.f;              // coef * sum over my pixels and the channels of p (t - s)
             if (in_map) {
 #pragma unroll
                 for (int q = 0; q < SB * SB; ++q) {
@@ -648,7 +658,7 @@ __global__ void __launch_bounds__(kPxThreads) kl_pixels_up_kernel(const UpParams
                     zt[q] = __fdividef(p.coef, zt[q]);
                 }
             }
-            const float rs2 = ref_s * p.c2, rt2 = ref_t * p.c2;
+            const float rs2 = __fmul_rn(ref_s, p.c2), rt2 = __fmul_rn(ref_t, p.c2);
 
             // ---------------- pass 2: per channel, window gradient -> nine contributions -> owned cells
             __syncthreads();
@@ -678,9 +688,12 @@ __global__ void __launch_bounds__(kPxThreads) kl_pixels_up_kernel(const UpParams
                             float tr[3] = {0.f, 0.f, 0.f};
 #pragma unroll
                             for (int kx = 0; kx < SB; ++kx) {
-                                const float es = fast_exp2(fmaf(up_value_win<S, SB>(hs, ds_, ky0 + ky, kx), p.c2, -rs2));
-                                const float et = fast_exp2(fmaf(up_value_win<S, SB>(ht, dt_, ky0 + ky, kx), p.c2, -rt2));
-                                const float gv = es * zs[ky * SB + kx] - et * zt[ky * SB + kx];
+                                const float vs = up_value_win<S, SB>(hs, ds_, ky0 + ky, kx);
+                                const float vt = up_value_win<S, SB>(ht, dt_, ky0 + ky, kx);
+                                const float es = fast_exp2(fmaf(vs, p.c2, -rs2));
+                                const float pt = fast_exp2(fmaf(vt, p.c2, -rt2)) * zt[ky * SB + kx];     // coef * p
+                                const float gv = fmaf(es, zs[ky * SB + kx], -pt);
+                                kl_a = fmaf(pt, vt - vs, kl_a);
                                 const int f = UpW<S>::first(kx0 + kx) + 1;
                                 const float w1 = UpW<S>::w1(kx0 + kx);
                                 tr[f] = fmaf(1.f - w1, gv, tr[f]);
@@ -742,6 +755,7 @@ __global__ void __launch_bounds__(kPxThreads) kl_pixels_up_kernel(const UpParams
                     }
                 }
             }
+            if (owned) kl_acc = fmaf(kl_a, p.inv_tau * p.inv_coef, kl_acc);
         }
     }
     // ---- loss: CTA partial, the last CTA sums the partials in a fixed order
@@ -823,17 +837,17 @@ static cudaError_t launch_up_t(const UpParams& p, int sms, cudaStream_t stream) 
     const size_t smem2 = up_smem_bytes(p.SR, p.Wl);
     auto k1 = kl_rows_up_stats_kernel<T, S>;
     auto k2 = kl_rows_up_grad_kernel<T, S>;
-    static bool configured = false;
-    static int occ1 = 1, occ2 = 1;
-    static size_t cfg1 = 0, cfg2 = 0;
-    if (!configured || smem1 > cfg1 || smem2 > cfg2) {
+    // the largest dynamic shared memory opted into so far, per instantiation and device
+    static std::atomic<size_t> cfg1_dev[kMaxDevices], cfg2_dev[kMaxDevices];
+    const int dev = device_slot();
+    int occ1 = 1, occ2 = 1;
+    if (smem1 > cfg1_dev[dev].load() || smem2 > cfg2_dev[dev].load()) {
         cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         if (e != cudaSuccess) return e;
-        cfg1 = smem1;
-        cfg2 = smem2;
-        configured = true;
+        if (smem1 > cfg1_dev[dev].load()) cfg1_dev[dev].store(smem1);
+        if (smem2 > cfg2_dev[dev].load()) cfg2_dev[dev].store(smem2);
     }
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k1, kUpThreads, smem1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k2, kUpThreads, smem2);

@@ -3,9 +3,21 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include "params.h"
 
 namespace sd {
+
+// Function attributes (the opt-in to > 48 KB of dynamic shared memory) and occupancy answers belong to a device
+// (context), not to the process: the launchers cache them per device ordinal - one process may drive several GPUs
+// (MMDataParallel, `with torch.cuda.device(...)`).  The cached values are idempotent, the flags atomic.
+constexpr int kMaxDevices = 64;
+inline int device_slot() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d < 0 || d >= kMaxDevices) ? 0 : d;
+}
 
 // kl_rows.cu
 cudaError_t launch_kl_rows_tma(const RowsParams& p, bool bf16, int grid, cudaStream_t stream);

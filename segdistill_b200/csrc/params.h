@@ -137,6 +137,7 @@ struct UpParams {
     int SR, NS;              // low-res rows per strip, strips per plane
     long long units;         // B*C*NS
     float c2, inv_c2, inv_tau, coef, loss_scale;
+    float inv_coef;          // pixel mode: 1 / coef (the KL's sum p (t - s) term is collected with the gradient weights)
     float inv_Wl;
     float* loss;
     float* row_kl;           // [R]

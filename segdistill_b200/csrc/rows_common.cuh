@@ -8,7 +8,7 @@
 namespace sd {
 
 constexpr unsigned kSpinLimit = 1u << 22;
-constexpr int kRedFloats = 8;                     // per-warp record: Ms, Mt, {Zs, Zt, A} x NL, (SQ)
+constexpr int kRedFloats = 8;                     // per-warp record of kl_rows.cu: Ms, Mt, Zs, Zt, A, SQ, DD
 constexpr float kPadValue = -1.0e30f;             // stands in for elements a partial chunk does not have
 constexpr float kMaxFloor = -1.0e29f;             // floor of a thread's local maximum: a thread that holds only
                                                   // padding then exponentiates to exact zeros (not to exp2 of
@@ -80,22 +80,28 @@ __device__ __forceinline__ size_t perm_elem_offset(const RowsParams& p, const Un
     return ((size_t)x.b * p.C + ch) * p.HW + pos;
 }
 
-// softmax statistics of a piece of a row: raw-value maxima (ms, mt) and sums relative to them
+// softmax statistics of a piece of a row: raw-value maxima (ms, mt), sums relative to them, and
+// dd = sum (et - es) accumulated term by term (common.cuh: KL without cancellation)
 struct RowStat {
-    float ms, zs, mt, zt, a;
+    float ms, zs, mt, zt, a, dd;
 };
-__device__ __forceinline__ RowStat rowstat_empty() { return RowStat{-INFINITY, 0.f, -INFINITY, 0.f, 0.f}; }
+__device__ __forceinline__ RowStat rowstat_empty() { return RowStat{-INFINITY, 0.f, -INFINITY, 0.f, 0.f, 0.f}; }
 __device__ __forceinline__ RowStat rowstat_merge(const RowStat& x, const RowStat& y, float c2) {
     RowStat r;
     r.ms = fmaxf(x.ms, y.ms);
     r.mt = fmaxf(x.mt, y.mt);
-    const float fxs = x.zs > 0.f ? fast_exp2((x.ms - r.ms) * c2) : 0.f;
-    const float fys = y.zs > 0.f ? fast_exp2((y.ms - r.ms) * c2) : 0.f;
-    const float fxt = x.zt > 0.f ? fast_exp2((x.mt - r.mt) * c2) : 0.f;
-    const float fyt = y.zt > 0.f ? fast_exp2((y.mt - r.mt) * c2) : 0.f;
+    const float fxs = x.zs > 0.f ? ref_factor(x.ms, r.ms, c2) : 0.f;
+    const float fys = y.zs > 0.f ? ref_factor(y.ms, r.ms, c2) : 0.f;
+    const float fxt = x.zt > 0.f ? ref_factor(x.mt, r.mt, c2) : 0.f;
+    const float fyt = y.zt > 0.f ? ref_factor(y.mt, r.mt, c2) : 0.f;
     r.zs = __fadd_rn(__fmul_rn(x.zs, fxs), __fmul_rn(y.zs, fys));
     r.zt = __fadd_rn(__fmul_rn(x.zt, fxt), __fmul_rn(y.zt, fyt));
     r.a = __fadd_rn(__fmul_rn(x.a, fxt), __fmul_rn(y.a, fyt));
+    // (an empty part has infinite references: its gap is NaN, factor_diff then takes the plain difference 0 - 0)
+    const float gr = ref_gap2(r.ms, r.mt, c2);
+    const float dx = fmaf(x.zs, factor_diff(fxs, fxt, ref_gap2(x.ms, x.mt, c2) - gr), __fmul_rn(x.dd, fxt));
+    const float dy = fmaf(y.zs, factor_diff(fys, fyt, ref_gap2(y.ms, y.mt, c2) - gr), __fmul_rn(y.dd, fyt));
+    r.dd = __fadd_rn(dx, dy);
     return r;
 }
 

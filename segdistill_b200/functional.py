@@ -15,11 +15,28 @@ from torch.autograd.function import once_differentiable
 from . import _cabi
 
 
-def _finish_backward(ctx, grad_output):
-    ds = ctx.ds
-    ctx.ds = None                      # drop our reference so autograd can adopt the buffer without a copy
-    if ds is None:
+def _keep(ctx, x_student, x_teacher, ds):
+    """Forward's bookkeeping: the gradient buffer the kernel already filled, and (only references) the inputs, so
+    that a SECOND backward through the same node can rebuild it."""
+    ctx.needs = x_student.requires_grad
+    ctx.ds = ds if ctx.needs else None
+    ctx.in_dtype, ctx.in_shape = x_student.dtype, x_student.shape
+    if ctx.needs:
+        ctx.save_for_backward(x_student, x_teacher)
+
+
+def _finish_backward(ctx, grad_output, recompute):
+    """dS * grad_output.  The first backward hands out the buffer forward filled (scaled in place; our reference is
+    dropped so autograd can adopt it without a copy).  A later backward through the same node - ``retain_graph=True``,
+    e.g. the reference trainer's ``log_grad`` mode, SD_structure.py:92-134 - finds it gone and re-runs the kernel on
+    the saved inputs (``recompute(x_student, x_teacher) -> dS``).  Without ``retain_graph`` the saved tensors are freed
+    and autograd raises its usual error."""
+    if not ctx.needs:
         return None
+    ds = ctx.ds
+    ctx.ds = None
+    if ds is None:
+        ds = recompute(*ctx.saved_tensors)
     _cabi.scale_grad_(ds, grad_output)
     if ds.dtype != ctx.in_dtype:
         ds = ds.to(ctx.in_dtype)
@@ -29,11 +46,9 @@ def _finish_backward(ctx, grad_output):
 class _KLRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_student, x_teacher, group, tau, alpha, perm, mse_weight, algo, bchw):
-        need_grad = x_student.requires_grad
-        loss, ds, _, mse = _cabi.kl_rows(x_student, x_teacher, group=group, tau=tau, alpha=alpha, perm=perm,
-                                         mse_weight=mse_weight, algo=algo, bchw=bchw)
-        ctx.ds = ds if need_grad else None
-        ctx.in_dtype, ctx.in_shape = x_student.dtype, x_student.shape
+        ctx.call = dict(group=group, tau=tau, alpha=alpha, perm=perm, mse_weight=mse_weight, algo=algo, bchw=bchw)
+        loss, ds, _, mse = _cabi.kl_rows(x_student, x_teacher, **ctx.call)
+        _keep(ctx, x_student, x_teacher, ds)
         if mse is not None:
             total = loss + mse
             ctx.mark_non_differentiable(loss, mse)
@@ -43,7 +58,7 @@ class _KLRows(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output, *unused):
-        return (_finish_backward(ctx, grad_output),) + (None,) * 8
+        return (_finish_backward(ctx, grad_output, lambda s, t: _cabi.kl_rows(s, t, **ctx.call)[1]),) + (None,) * 8
 
 
 class _KLRowsUp(torch.autograd.Function):
@@ -51,15 +66,16 @@ class _KLRowsUp(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_student, x_teacher, scale, group, tau, alpha, perm):
-        loss, ds, _ = _cabi.kl_rows_up(x_student, x_teacher, scale, group=group, tau=tau, alpha=alpha, perm=perm)
-        ctx.ds = ds if x_student.requires_grad else None
-        ctx.in_dtype, ctx.in_shape = x_student.dtype, x_student.shape
+        ctx.call = dict(group=group, tau=tau, alpha=alpha, perm=perm)
+        ctx.scale = scale
+        loss, ds, _ = _cabi.kl_rows_up(x_student, x_teacher, scale, **ctx.call)
+        _keep(ctx, x_student, x_teacher, ds)
         return loss
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
-        return (_finish_backward(ctx, grad_output),) + (None,) * 6
+        return (_finish_backward(ctx, grad_output, lambda s, t: _cabi.kl_rows_up(s, t, ctx.scale, **ctx.call)[1]),) + (None,) * 6
 
 
 class _KLPixelsUp(torch.autograd.Function):
@@ -67,15 +83,17 @@ class _KLPixelsUp(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_student, x_teacher, scale, tau, alpha):
+        ctx.call = (scale, tau, alpha)
         loss, ds = _cabi.kl_pixels_up(x_student, x_teacher, scale, tau=tau, alpha=alpha)
-        ctx.ds = ds if x_student.requires_grad else None
-        ctx.in_dtype, ctx.in_shape = x_student.dtype, x_student.shape
+        _keep(ctx, x_student, x_teacher, ds)
         return loss
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
-        return (_finish_backward(ctx, grad_output),) + (None,) * 4
+        scale, tau, alpha = ctx.call
+        return (_finish_backward(ctx, grad_output,
+                                 lambda s, t: _cabi.kl_pixels_up(s, t, scale, tau=tau, alpha=alpha)[1]),) + (None,) * 4
 
 
 PAIR_ALGO = 'auto'      # kernel of the fused two-loss launch: 'auto' | 'cluster' | 'stream' (tests force one)
@@ -94,22 +112,22 @@ class _KLRowsMulti(torch.autograd.Function):
     def forward(ctx, x_student, x_teacher, g0, tau0, alpha0, g1, tau1, alpha1):
         algo = _cabi.ALGOS[PAIR_ALGO]
         losses, ds = _cabi.kl_rows_multi(x_student, x_teacher, (g0, g1), (tau0, tau1), (alpha0, alpha1), algo=algo)
-        need_grad = x_student.requires_grad
-        ctx.ds = ds if need_grad else None
         ctx.cfg = ((g0, g1), (tau0, tau1), (alpha0, alpha1))
         ctx.algo = algo
-        ctx.in_dtype, ctx.in_shape = x_student.dtype, x_student.shape
-        if need_grad:
-            ctx.save_for_backward(x_student, x_teacher)
+        _keep(ctx, x_student, x_teacher, ds)
         return losses[0], losses[1]
 
     @staticmethod
     @once_differentiable
     def backward(ctx, go0, go1):
+        if not ctx.needs:
+            return (None,) * 8
         ds = ctx.ds
         ctx.ds = None
-        if ds is None:
-            return (None,) * 8
+        groups, taus, alphas = ctx.cfg
+        x_student, x_teacher = ctx.saved_tensors
+        if ds is None:       # a second backward through this node (retain_graph=True): rebuild dS for unit weights
+            ds = _cabi.kl_rows_multi(x_student, x_teacher, groups, taus, alphas, algo=ctx.algo)[1]
         dev = ds.device
         if go0 is go1 or (go0.data_ptr() == go1.data_ptr() and go0.device == go1.device):
             # the two terms entered one sum: a single upstream gradient, one in-place scaling launch
@@ -118,8 +136,6 @@ class _KLRowsMulti(torch.autograd.Function):
             go0 = go0.detach().to(device=dev, dtype=torch.float32).reshape(1)
             go1 = go1.detach().to(device=dev, dtype=torch.float32).reshape(1)
             flag = _cabi.scale_grad2_(ds, go0, go1)
-            x_student, x_teacher = ctx.saved_tensors
-            groups, taus, alphas = ctx.cfg
             _cabi.kl_rows_multi(x_student, x_teacher, groups, taus, alphas, grad_outputs=(go0, go1), run_if=flag,
                                 ds=ds, algo=ctx.algo)
         if ds.dtype != ctx.in_dtype:
@@ -130,10 +146,9 @@ class _KLRowsMulti(torch.autograd.Function):
 class _KLPixels(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_student, x_teacher, tau, alpha, at_weight, algo):
-        need_grad = x_student.requires_grad
-        loss, ds, _, at = _cabi.kl_pixels(x_student, x_teacher, tau=tau, alpha=alpha, at_weight=at_weight, algo=algo)
-        ctx.ds = ds if need_grad else None
-        ctx.in_dtype, ctx.in_shape = x_student.dtype, x_student.shape
+        ctx.call = dict(tau=tau, alpha=alpha, at_weight=at_weight, algo=algo)
+        loss, ds, _, at = _cabi.kl_pixels(x_student, x_teacher, **ctx.call)
+        _keep(ctx, x_student, x_teacher, ds)
         if at is not None:
             return loss + at
         return loss
@@ -141,21 +156,21 @@ class _KLPixels(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
-        return (_finish_backward(ctx, grad_output),) + (None,) * 5
+        return (_finish_backward(ctx, grad_output, lambda s, t: _cabi.kl_pixels(s, t, **ctx.call)[1]),) + (None,) * 5
 
 
 class _MSE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_student, x_teacher, weight):
+        ctx.weight = weight
         loss, ds = _cabi.mse(x_student, x_teacher, weight=weight)
-        ctx.ds = ds if x_student.requires_grad else None
-        ctx.in_dtype, ctx.in_shape = x_student.dtype, x_student.shape
+        _keep(ctx, x_student, x_teacher, ds)
         return loss
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
-        return _finish_backward(ctx, grad_output), None, None
+        return _finish_backward(ctx, grad_output, lambda s, t: _cabi.mse(s, t, weight=ctx.weight)[1]), None, None
 
 
 class _IFVDSim(torch.autograd.Function):
@@ -163,15 +178,16 @@ class _IFVDSim(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_student, x_teacher, cls, weight):
+        ctx.call = (cls, weight)
         loss, ds = _cabi.ifvd_sim(x_student, x_teacher, cls, weight=weight)
-        ctx.ds = ds if x_student.requires_grad else None
-        ctx.in_dtype, ctx.in_shape = x_student.dtype, x_student.shape
+        _keep(ctx, x_student, x_teacher, ds)
         return loss
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
-        return _finish_backward(ctx, grad_output), None, None, None
+        cls, weight = ctx.call
+        return _finish_backward(ctx, grad_output, lambda s, t: _cabi.ifvd_sim(s, t, cls, weight=weight)[1]), None, None, None
 
 
 class _IFVD(torch.autograd.Function):
@@ -180,30 +196,36 @@ class _IFVD(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_student, x_teacher, cls, weight, algo):
+        ctx.call = (cls, weight, algo)
         loss_pd, ds, _, _ = _cabi.kl_pixels(x_student, x_teacher, tau=1.0, alpha=1.0, algo=algo)
         loss_sim, ds = _cabi.ifvd_sim(x_student, x_teacher, cls, weight=weight, ds=ds)
-        ctx.ds = ds if x_student.requires_grad else None
-        ctx.in_dtype, ctx.in_shape = x_student.dtype, x_student.shape
+        _keep(ctx, x_student, x_teacher, ds)
         return loss_sim + loss_pd
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
-        return _finish_backward(ctx, grad_output), None, None, None, None
+        cls, weight, algo = ctx.call
+
+        def again(s, t):
+            ds = _cabi.kl_pixels(s, t, tau=1.0, alpha=1.0, algo=algo)[1]
+            return _cabi.ifvd_sim(s, t, cls, weight=weight, ds=ds)[1]
+        return _finish_backward(ctx, grad_output, again), None, None, None, None
 
 
 class _CGDCorr(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_student, x_teacher, group, alpha):
+        ctx.call = (group, alpha)
         loss, ds = _cabi.cgd_corr(x_student, x_teacher, group=group, alpha=alpha)
-        ctx.ds = ds if x_student.requires_grad else None
-        ctx.in_dtype, ctx.in_shape = x_student.dtype, x_student.shape
+        _keep(ctx, x_student, x_teacher, ds)
         return loss
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
-        return _finish_backward(ctx, grad_output), None, None, None
+        group, alpha = ctx.call
+        return _finish_backward(ctx, grad_output, lambda s, t: _cabi.cgd_corr(s, t, group=group, alpha=alpha)[1]), None, None, None
 
 
 class _ZeroLoss(torch.autograd.Function):

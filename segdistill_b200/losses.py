@@ -266,6 +266,9 @@ class IFVDLoss(nn.Module):
             feat_t = F.interpolate(feat_t, size=feat_s.shape[2:], mode='bilinear', align_corners=False)   # :204-209
         feat_t = feat_t.detach()
         b, c, h, w = feat_s.shape
+        if c > _cabi.ifvd_max_channels():      # before anything is launched (the KL kernel's work would be thrown away)
+            raise _cabi.SegDistillUnsupported(
+                f'IFVDLoss: C = {c} classes exceed the {_cabi.ifvd_max_channels()} the class-sum kernels hold per CTA')
         if target.is_cuda and not target.is_floating_point():
             cls = _cabi.ifvd_class_map(target, c, h, w)                                                    # :218-224
         else:

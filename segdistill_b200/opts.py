@@ -97,8 +97,10 @@ class DistillationLoss(nn.Module):
                 loss = results[i]
             else:
                 loss = crit(student_features[s_name], teacher_features[t_name], gt_semantic_seg, step)
-            cfg = entry['loss_config'][0] if isinstance(entry['loss_config'], tuple) else entry['loss_config']
-            info = cfg.get('transform_config', 'other') if isinstance(cfg, dict) else 'other'
+            # the reference indexes entry['loss_config'] ITSELF (:105-108, bare except): a tuple-wrapped config, or one
+            # without the key, is named 'other' - kept, so that log / checkpoint keys are the same
+            cfg = entry['loss_config']
+            info = cfg['transform_config'] if isinstance(cfg, dict) and 'transform_config' in cfg else 'other'
             out[f'loss_{s_name}<->{t_name}_{info}'] = loss
         return out
 

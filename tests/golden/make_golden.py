@@ -87,6 +87,14 @@ CASES = [
     ('cgdws_warm_n500',   'CGDLossWS', {}, {}, (1, 20, 4, 4), (4, 4), 500, 'float32'),
     ('cd_logits_x4',      'CDLoss',  {}, {}, (2, 6, 8, 8),   (8, 8),   1, 'float32*4'),
     ('cd_near_converged', 'CDLoss',  {}, {}, (2, 6, 16, 16), (16, 16), 1, 'near'),
+    # nearly converged student (KL ~ 5e-5: lse_t - lse_s cancels), the other layouts; every 'near' fixture also holds
+    # the reference run in float64 on the same inputs (loss_f64 / grad_f64)
+    ('cgd_near_converged', 'CGDLoss', {}, {}, (2, 20, 16, 16), (16, 16), 1, 'near'),
+    ('pd_near_converged',  'PDLoss',  {}, {}, (2, 6, 16, 16),  (16, 16), 1, 'near'),
+    ('cd_near_offset',     'CDLoss',  {}, {}, (2, 6, 16, 16),  (16, 16), 1, 'near+3'),
+    ('cd_near_64x64',      'CDLoss',  {}, {}, (1, 4, 64, 64),  (64, 64), 1, 'near'),
+    ('cgd_near_resize_4x', 'CGDLoss', dict(group_size=3), {}, (1, 6, 8, 8), (32, 32), 1, 'near'),
+    ('pd_near_resize_2x',  'PDLoss',  {}, {}, (1, 5, 8, 8),    (16, 16), 1, 'near'),
 ]
 
 
@@ -98,6 +106,8 @@ def _inputs(shape, kind, seed):
         s, t = s * 4, t * 4
     elif kind == 'near':
         t = s + 1e-2 * t
+    elif kind == 'near+3':                 # ... up to a constant offset, which a softmax does not see
+        t = s + 1e-2 * t + 3.0
     return s, t
 
 
@@ -122,10 +132,22 @@ def run_case(ref, case, seed):
     if sc and n_iter % sc['interval'] == 0:
         torch.set_rng_state(rng_state)
         perm = torch.randperm(shape[1]).numpy()
-    return dict(S=s.detach().numpy(), T=t.numpy(), gt_hw=np.array(gt_hw), n_iter=np.array(n_iter),
-                loss=np.array(loss.item(), dtype=np.float64), grad=s.grad.numpy(), perm=perm,
-                alpha_after=np.array(float(crit.alpha)), tau=np.array(float(crit.tau)),
-                cls=np.array(cls), kwargs=np.array(repr(kwargs)), manual_seed=np.array(1234 + seed))
+    rec = dict(S=s.detach().numpy(), T=t.numpy(), gt_hw=np.array(gt_hw), n_iter=np.array(n_iter),
+               loss=np.array(loss.item(), dtype=np.float64), grad=s.grad.numpy(), perm=perm,
+               alpha_after=np.array(float(crit.alpha)), tau=np.array(float(crit.tau)),
+               cls=np.array(cls), kwargs=np.array(repr(kwargs)), manual_seed=np.array(1234 + seed))
+    if kind.startswith('near'):
+        # the same reference code in float64: what the fp32 reference (and the CUDA path) is measured against
+        s64 = s.detach().double().requires_grad_(True)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            crit64 = getattr(ref, cls)(**kwargs)
+        torch.set_rng_state(rng_state)
+        with cuda_is_noop():
+            loss64 = crit64(s64, t.double(), gt, n_iter)
+        loss64.backward()
+        rec.update(loss_f64=np.array(loss64.item(), dtype=np.float64), grad_f64=s64.grad.numpy())
+    return rec
 
 
 def schedule_table(ref):

@@ -62,13 +62,99 @@ def test_golden_vectors(name, algo):
     loss, grad = _run(crit, torch.from_numpy(rec['S']), torch.from_numpy(rec['T']),
                       [int(v) for v in rec['gt_hw']], int(rec['n_iter']), algo, seed=int(rec['manual_seed']))
     if 'near' in name:
-        # S ~ T: KL ~ 5e-5; the fp32 reference itself is only ~6e-4 accurate here
-        f64_loss, f64_grad, _ = oracle.kld_closed_form_f64(rec['S'], rec['T'], 'channel', 1, 1.0, 1.0)
-        assert rel_err(loss, f64_loss) <= 5e-3
-        assert (grad.double().numpy() - f64_grad).__abs__().max() <= 1e-4 * np.abs(f64_grad).max() + 1e-9
+        # S ~ T, KL ~ 2..5e-5: lse_t - lse_s cancels.  The fixture holds the reference run in fp32 AND in float64; the
+        # fp32 reference is 6e-5 .. 1.2e-2 off its own float64 result here (losses.py:108-111: log_softmax values of
+        # magnitude ~ln(row length) subtracted).  The CUDA path must be at least as close to float64 as the reference
+        # (floor 1e-4), never worse than the 6e-4 the survey measured, and agree with the fp32 reference within the
+        # sum of the two errors.
+        f64_loss, f64_grad = float(rec['loss_f64']), rec['grad_f64']
+        ref_err = rel_err(float(rec['loss']), f64_loss)
+        our_err = rel_err(loss, f64_loss)
+        assert our_err <= max(min(ref_err, 6e-4), 1e-4), (name, algo, our_err, ref_err)
+        assert rel_err(loss, float(rec['loss'])) <= ref_err + our_err + 1e-7
+        gscale = np.abs(f64_grad).max()
+        ref_gerr = np.abs(rec['grad'] - f64_grad).max() / gscale
+        our_gerr = np.abs(grad.double().numpy() - f64_grad).max() / gscale
+        assert our_gerr <= max(ref_gerr, 1e-4), (name, algo, our_gerr, ref_gerr)       # north_star: gradients <= 1e-4
         return
     _assert_close(loss, grad, float(rec['loss']), rec['grad'])
     assert float(crit.alpha) == pytest.approx(float(rec['alpha_after']), rel=1e-12)
+
+
+def _near_pair(shape, seed, eps=1e-2, offset=0.0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    s = torch.randn(shape, generator=g)
+    t = s + eps * torch.randn(shape, generator=g) + offset
+    return s.to(dtype), t.to(dtype)
+
+
+def _check_near(loss, grad, f64_loss, f64_grad, tol=1e-4, gtol=1e-4):
+    assert rel_err(loss, f64_loss) <= tol, (loss, f64_loss, rel_err(loss, f64_loss))
+    f64_grad = np.asarray(f64_grad, dtype=np.float64).reshape(grad.shape)
+    assert np.abs(grad.double().numpy() - f64_grad).max() <= gtol * np.abs(f64_grad).max()
+
+
+@pytest.mark.parametrize('algo', ['tma', 'rows1', 'stream', 'cluster', 'generic'])
+@pytest.mark.parametrize('shape,g,tau,offset', [((2, 150, 64, 64), 1, 1.0, 0.0), ((2, 150, 64, 64), 10, 2.0, 0.0),
+                                                ((1, 20, 128, 128), 10, 2.0, 0.0), ((2, 7, 96, 96), 3, 4.0, 0.5),
+                                                ((4, 64, 16, 16), 1, 1.0, -2.0), ((1, 150, 32, 32), 150, 3.0, 0.0)])
+def test_near_converged_rows_every_kernel(shape, g, tau, offset, algo):
+    """KL ~ 5e-5 (teacher = student + 1e-2 noise): every row kernel must match float64 to 1e-4 - the reference's own
+    fp32 chain is 6e-4 .. 1e-2 off there (fixtures kld_*near*) - because lse_t - lse_s is evaluated from the
+    term-by-term difference of the exponentials, not from two rounded logarithms."""
+    s, t = _near_pair(shape, seed=5 + g, offset=offset)
+    f64_loss, f64_grad, _ = oracle.kld_closed_form_f64(s.numpy(), t.numpy(), 'channel', g, tau, 3.0)
+    try:
+        loss, grad = _run(sd.CGDLoss(group_size=g, alpha=3, tau=tau), s, t, shape[2:], 1, algo)
+    except _cabi.SegDistillUnsupported:
+        pytest.skip(f'{algo} does not take this layout')
+    _check_near(loss, grad, f64_loss, f64_grad)
+
+
+@pytest.mark.parametrize('algo', ['tma', 'generic'])
+@pytest.mark.parametrize('shape', [(2, 150, 64, 64), (1, 19, 33, 40), (2, 6, 16, 16)])
+def test_near_converged_pixels(shape, algo):
+    s, t = _near_pair(shape, seed=11, offset=0.25)
+    f64_loss, f64_grad, _ = oracle.kld_closed_form_f64(s.numpy(), t.numpy(), 'pixel', 1, 1.0, 1.0)
+    loss, grad = _run(sd.PDLoss(), s, t, shape[2:], 1, algo)
+    _check_near(loss, grad, f64_loss, f64_grad)
+
+
+@pytest.mark.parametrize('cls,kw,shape,scale', [('CGDLoss', dict(group_size=10, alpha=3, tau=2), (2, 20, 32, 32), 4),
+                                                ('CDLoss', {}, (1, 6, 24, 40), 2), ('CDLoss', {}, (1, 4, 16, 16), 8),
+                                                ('PDLoss', {}, (1, 19, 24, 24), 4), ('PDLoss', {}, (1, 6, 16, 16), 8),
+                                                ('PDLoss', {}, (2, 5, 20, 12), 2)])
+def test_near_converged_behind_the_fused_resize(cls, kw, shape, scale):
+    """The same through the kernels that up-sample on the fly; float64 truth = the oracle chain run in float64."""
+    s, t = _near_pair(shape, seed=13)
+    hw = (shape[2] * scale, shape[3] * scale)
+    x = s.double().requires_grad_(True)
+    gt = torch.zeros(shape[0], 1, *hw, dtype=torch.long)
+    ref = oracle.make_preset(cls, **kw)(x, t.double(), gt, 1)
+    ref.backward()
+    loss, grad = _run(getattr(sd, cls)(**kw), s, t, hw, 1)
+    assert _cabi.last_kernel() in ('kl_rows_up_kernel', 'kl_pixels_up_kernel', 'scale_grad_kernel')
+    _check_near(loss, grad, ref.item(), x.grad.numpy(), tol=2e-4)
+
+
+@pytest.mark.parametrize('pair_algo', ['cluster', 'stream'], indirect=True)
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_near_converged_two_losses_one_launch(pair_algo, dtype):
+    shape = (2, 150, 64, 64)
+    s, t = _near_pair(shape, seed=17, dtype=dtype)
+    ka, kb = dict(group_size=1, alpha=1, tau=1), dict(group_size=10, alpha=3, tau=2)
+    fa = oracle.kld_closed_form_f64(s.float().numpy(), t.float().numpy(), 'channel', 1, 1.0, 1.0)
+    fb = oracle.kld_closed_form_f64(s.float().numpy(), t.float().numpy(), 'channel', 10, 2.0, 3.0)
+    x = s.to(dev()).requires_grad_(True)
+    tg = t.to(dev())
+    la, lb = sd.KLDLoss.run_pair(sd.CGDLoss(**ka).plan(x, tg, None, 1), sd.CGDLoss(**kb).plan(x, tg, None, 1))
+    assert _cabi.last_kernel() == f'kl_rows_{pair_algo}_kernel(2 losses)'
+    (la + lb).backward()
+    torch.cuda.synchronize()
+    assert rel_err(la.item(), fa[0]) <= 1e-4 and rel_err(lb.item(), fb[0]) <= 1e-4
+    g64 = (fa[1] + fb[1]).reshape(shape)
+    gtol = BF16_GRAD_RTOL if dtype == torch.bfloat16 else 1e-4
+    assert np.abs(x.grad.double().cpu().numpy() - g64).max() <= gtol * np.abs(g64).max()
 
 
 def test_golden_atloss():
@@ -875,3 +961,78 @@ def test_fused_resize_pixel_mode_large_logit_steps():
         got = _run(sd.PDLoss(), s, t, hw, 1)
         assert np.isfinite(got[0]) and torch.isfinite(got[1]).all()
         _assert_close(*got, *ref, loss_rtol=2e-5, grad_rtol=1e-4)
+
+
+# ------------------------------------------------------------------ round 2: the benchmarked launch at its own shape
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_full_size_two_loss_launch_against_the_oracle(dtype):
+    """bench.py's step - CDLoss + CGDLoss(g=10, tau=2, alpha=3) on 16x150x128x128 through the dispatcher's two-loss
+    launch - against the oracle chain on the same tensors (CPU, fp32), not only through properties."""
+    s, t = seeded_pair(FULL, seed=0, dtype=dtype)
+    ra = _oracle_run('CDLoss', {}, s, t, FULL[2:], 1)
+    rb = _oracle_run('CGDLoss', dict(group_size=10, alpha=3, tau=2), s, t, FULL[2:], 1)
+    x = s.to(dev()).requires_grad_(True)
+    tg = t.to(dev())
+    la, lb = sd.KLDLoss.run_pair(sd.CDLoss().plan(x, tg, None, 1), sd.CGDLoss().plan(x, tg, None, 1))
+    assert _cabi.last_kernel() == 'kl_rows_cluster_kernel(2 losses)'
+    (la + lb).backward()
+    torch.cuda.synchronize()
+    lt = 2e-5 if dtype == torch.bfloat16 else LOSS_RTOL
+    gt_ = BF16_GRAD_RTOL if dtype == torch.bfloat16 else GRAD_RTOL
+    assert rel_err(la.item(), ra[0]) <= lt and rel_err(lb.item(), rb[0]) <= lt
+    ref_grad = ra[1] + rb[1]
+    assert (x.grad.float().cpu() - ref_grad).abs().max().item() <= gt_ * ref_grad.abs().max().item()
+
+
+def test_second_backward_with_retain_graph_on_the_device():
+    """log_grad mode of the reference trainer (SD_structure.py:92-134): backward(retain_graph=True), then the real one."""
+    s, t = seeded_pair((2, 20, 64, 64), seed=21)
+    ref_cd = _oracle_run('CDLoss', {}, s, t, (64, 64), 1)
+    ref_cgd = _oracle_run('CGDLoss', {}, s, t, (64, 64), 1)
+    ref_pd = _oracle_run('PDLoss', {}, s, t, (64, 64), 1)
+    tg = t.to(dev())
+    for crit, ref in ((sd.CDLoss(), ref_cd), (sd.PDLoss(), ref_pd)):
+        w = s.to(dev()).requires_grad_(True)
+        loss = crit(w * 1.0, tg, None, 1)
+        (g1,) = torch.autograd.grad(loss, w, retain_graph=True)
+        (g2,) = torch.autograd.grad(2.0 * loss, w, retain_graph=True)
+        loss.backward()
+        torch.cuda.synchronize()
+        for got, k in ((g1, 1.0), (g2, 2.0), (w.grad, 1.0)):
+            assert (got.cpu() - k * ref[1]).abs().max().item() <= GRAD_RTOL * k * ref[1].abs().max().item()
+    # the two-loss node
+    w = s.to(dev()).requires_grad_(True)
+    x = w * 1.0
+    la, lb = sd.KLDLoss.run_pair(sd.CDLoss().plan(x, tg, None, 1), sd.CGDLoss().plan(x, tg, None, 1))
+    (g1,) = torch.autograd.grad(la + lb, w, retain_graph=True)
+    (g2,) = torch.autograd.grad(la + 3.0 * lb, w, retain_graph=True)
+    (la + lb).backward()
+    torch.cuda.synchronize()
+    r1, r2 = ref_cd[1] + ref_cgd[1], ref_cd[1] + 3.0 * ref_cgd[1]
+    assert (g1.cpu() - r1).abs().max().item() <= GRAD_RTOL * r1.abs().max().item()
+    assert (g2.cpu() - r2).abs().max().item() <= GRAD_RTOL * r2.abs().max().item()
+    assert (w.grad.cpu() - r1).abs().max().item() <= GRAD_RTOL * r1.abs().max().item()
+
+
+def test_streaming_kernel_next_to_a_kernel_that_occupies_the_sms():
+    """The split-row kernel's CTAs read each other's packets: the launch is cooperative, so it starts only when the whole
+    grid can be resident - also while another stream keeps the SMs busy.  The result must be the oracle's and the
+    time-out flag must stay clear (a time-out would turn the loss into NaN)."""
+    shape = (2, 150, 64, 64)
+    s, t = seeded_pair(shape, seed=31)
+    ref = _oracle_run('CGDLoss', dict(group_size=10, alpha=3, tau=2), s, t, shape[2:], 1)
+    side = torch.cuda.Stream()
+    a = torch.randn(8192, 8192, device=dev())
+    x = s.to(dev())
+    tg = t.to(dev())
+    torch.cuda.synchronize()
+    for _ in range(3):
+        with torch.cuda.stream(side):
+            for _ in range(6):
+                a = torch.sin(a) * 1.0001          # ~1 ms each: every SM is taken while the loss kernel is queued
+        loss, ds, _, _ = _cabi.kl_rows(x, tg, group=10, tau=2.0, alpha=3.0, algo=_cabi.ALGOS['stream'])
+        assert _cabi.last_kernel() == 'kl_rows_stream_kernel'
+        torch.cuda.synchronize()
+        assert _cabi.workspace_error_flag() == 0
+        assert np.isfinite(loss.item())
+        _assert_close(loss.item(), ds.cpu(), *ref)

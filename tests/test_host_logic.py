@@ -79,15 +79,20 @@ def test_dispatcher_builds_and_names_like_the_reference():
          'loss_name': 'CGDLossWS', 'loss_config': {}},
         {'student_layer': 'a', 'teacher_layer': 'b', 'loss_name': 'KLDLoss',
          'loss_config': ({'alpha': 0, 'tau': 2, 'transform_config': {'loss_type': 'channel', 'group_size': 2}},)},
+        {'student_layer': 'a', 'teacher_layer': 'c', 'loss_name': 'KLDLoss',
+         'loss_config': {'alpha': 0, 'tau': 2, 'transform_config': {'loss_type': 'channel', 'group_size': 2}}},
     ]
     d = sd.DistillationLoss(cfg)
     assert isinstance(cfg[0]['criterion'], sd.CGDLossWS)
     x = torch.randn(1, 4, 2, 2)
     feats = {'decode_head.linear_pred': x, 'a': x}
-    featt = {'decode_head.linear_pred': x, 'b': x}
-    out = d(feats, featt, None, 0, None, None)       # both alphas are 0 -> no kernel needed on CPU
+    featt = {'decode_head.linear_pred': x, 'b': x, 'c': x}
+    out = d(feats, featt, None, 0, None, None)       # all alphas are 0 -> no kernel needed on CPU
+    # a tuple-wrapped loss_config is unwrapped for the constructor only (opts.py:81-82); the key lookup indexes the
+    # tuple itself and lands in the bare except (:105-108) -> 'other'
     assert list(out) == ['loss_decode_head.linear_pred<->decode_head.linear_pred_other',
-                         "loss_a<->b_{'loss_type': 'channel', 'group_size': 2}"]
+                         'loss_a<->b_other',
+                         "loss_a<->c_{'loss_type': 'channel', 'group_size': 2}"]
     with pytest.raises(NameError):
         sd.build_criterion('NoSuchLoss', {})
     with pytest.raises(TypeError):
@@ -193,3 +198,38 @@ def test_ifvd_class_map_equals_the_reference_masks():
         assert bool((cls[m] == i).all())
         covered |= m
     assert bool((cls[~covered] == c).all()) and int((~covered).sum()) > 0
+
+
+def test_second_backward_through_the_same_node_rebuilds_the_gradient(monkeypatch):
+    """retain_graph=True and two backward passes (the reference trainer's log_grad mode, SD_structure.py:92-134):
+    the first hands out the buffer forward filled, the second must re-run the kernel - never return None.
+    (The C ABI is mocked on the CPU: this is host logic.)"""
+    from segdistill_b200 import _cabi
+    from segdistill_b200 import functional as SF
+    calls = []
+
+    def fake_mse(s, t, weight=1.0, grad_scale=1.0):
+        calls.append('mse')
+        d = s.detach() - t.detach()
+        return weight * (d * d).mean(), 2.0 * weight * d / d.numel()
+
+    def fake_scale(ds, go):
+        return ds.mul_(go.detach().reshape(()).to(ds.dtype))
+
+    monkeypatch.setattr(_cabi, 'mse', fake_mse)
+    monkeypatch.setattr(_cabi, 'scale_grad_', fake_scale)
+    torch.manual_seed(3)
+    w = torch.randn(4, 5, requires_grad=True)
+    t = torch.randn(4, 5)
+    x = w * 2.0                                    # non-leaf student, as in training
+    loss = SF.mse_loss(x, t, 0.5)
+    want = 2.0 * 2.0 * 0.5 * (2.0 * w.detach() - t) / t.numel()
+    (g1,) = torch.autograd.grad(loss, w, retain_graph=True)
+    (g2,) = torch.autograd.grad(3.0 * loss, w, retain_graph=True)      # a different upstream weight
+    loss.backward()
+    assert torch.allclose(g1, want, rtol=1e-6, atol=1e-8)
+    assert torch.allclose(g2, 3.0 * want, rtol=1e-6, atol=1e-8)
+    assert torch.allclose(w.grad, want, rtol=1e-6, atol=1e-8)
+    assert calls == ['mse', 'mse', 'mse']          # forward + one re-run per extra backward
+    with pytest.raises(RuntimeError):              # graph freed: autograd's own error, not a silent None
+        loss.backward()

@@ -52,12 +52,17 @@ def test_closed_form_f64_matches_reference(name):
     perm = rec['perm'] if rec['perm'].size else None
     loss, grad, row_kl = oracle.kld_closed_form_f64(S, T, mode, g, float(rec['tau']),
                                                     float(rec['alpha_after']), perm)
-    tol = 2e-3 if 'near' in name else 5e-6      # the fp32 reference itself is ~6e-4 off near convergence
-    assert rel_err(rec['loss'], loss) <= tol
     scale = np.abs(grad).max()
-    # near convergence q - p cancels: the fp32 reference carries ~1e-5 of max|grad| there
-    gtol = 5e-5 if 'near' in name else 2e-6
-    assert np.abs(grad.reshape(rec['grad'].shape) - rec['grad']).max() <= gtol * scale
+    if 'near' in name:
+        # S ~ T: the fp32 reference is 6e-5 .. 1.2e-2 off here (lse_t - lse_s cancels); the fixture also holds the
+        # reference run in float64, which the closed form must reproduce
+        assert rel_err(rec['loss_f64'], loss) <= 1e-9
+        assert np.abs(grad.reshape(rec['grad'].shape) - rec['grad_f64']).max() <= 1e-9 * scale
+        assert rel_err(rec['loss'], loss) <= 2e-2
+        assert np.abs(grad.reshape(rec['grad'].shape) - rec['grad']).max() <= 1e-4 * scale
+    else:
+        assert rel_err(rec['loss'], loss) <= 5e-6
+        assert np.abs(grad.reshape(rec['grad'].shape) - rec['grad']).max() <= 2e-6 * scale
     assert row_kl.min() >= -1e-12
 
 
