@@ -11,6 +11,10 @@ dispatcher with two `distillation` entries hooking the same logits tensor (`deco
 HBM; `e2e` = same from pinned HOST buffers (H2D of S and T and D2H of the loss scalars inside the
 timed region).  Inputs
 (2 x 157 MB per GPU) exceed the 126 MB L2, so no L2 flush is needed between iterations.
+
+Every leg - the GPU arm, its `cpu_baseline`, its `gpu_aten_baseline`, and `--impl reference` - runs the SAME
+tensors: rank r's shard is drawn on the CPU from `torch.Generator().manual_seed(1234 + r)` (S first, then T).  The
+GPU arm checks its two loss values against the CPU leg's (1e-5) before it prints.
 """
 from __future__ import annotations
 
@@ -34,6 +38,19 @@ UNIT = 'Mpixel/s'
 WORKLOAD = ('cfg5 shard: CGDLoss(g=10,tau=2,alpha=3)+CDLoss fwd+bwd on logits %dx%dx%dx%d fp32 per GPU '
             '(global B=128 at 8 GPUs)' % (B_PER_GPU, C, H, W))
 FALLBACK_HBM_GBS = 6650.0
+# one dict for both arms (the driver compares them): what is computed, on which tensors
+CONFIG = {'workload': WORKLOAD, 'per_gpu_shape': [B_PER_GPU, C, H, W], 'losses': ['CGDLoss', 'CDLoss'],
+          'inputs': 'rank r: torch.Generator().manual_seed(1234 + r) on the CPU, S = randn, then T = randn, fp32',
+          'l2': 'inputs (2 x 157 MB per GPU) exceed the 126 MB L2; no flush'}
+
+
+def make_inputs(rank):
+    """The shard of `rank`, drawn on the CPU so that every leg (GPU, CPU port, ATen-on-GPU) sees the same numbers."""
+    import torch
+    g = torch.Generator().manual_seed(1234 + rank)
+    s = torch.randn(B_PER_GPU, C, H, W, generator=g)
+    t = torch.randn(B_PER_GPU, C, H, W, generator=g)
+    return s, t
 
 
 def parse_args():
@@ -44,6 +61,7 @@ def parse_args():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU oracle leg (profiling runs)')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-aten', action='store_true', help='skip the ATen-chain-on-GPU baseline leg')
     ap.add_argument('--extra', action='store_true', help='also time the other BASELINE configs (N=1 only)')
     ap.add_argument('--unfused', action='store_true', help='one launch per loss (no dispatcher batching)')
     ap.add_argument('--eager', action='store_true', help='time eager launches instead of replaying the captured step')
@@ -124,27 +142,53 @@ def profiled_traffic():
 
 
 # ------------------------------------------------------------------ CPU oracle legs
-def cpu_oracle_step_time(batch, steps, warmup, threads=None):
-    """Reference algorithm (oracle port of losses.py) on the host cores: CGD+CD fwd+bwd on `batch` samples."""
+def cpu_oracle_step_time(s, t, steps, warmup, threads=None):
+    """Reference algorithm (oracle port of losses.py) on the host cores: CGD+CD fwd+bwd on the shard (s, t).
+    Returns (seconds per timed step, (cgd loss, cd loss))."""
     import torch
     import oracle
     if threads:
         torch.set_num_threads(threads)
-    torch.manual_seed(0)
-    s = torch.randn(batch, C, H, W)
-    t = torch.randn(batch, C, H, W)
-    gt = torch.zeros(batch, 1, H, W, dtype=torch.long)
+    gt = torch.zeros(s.shape[0], 1, H, W, dtype=torch.long)
     crits = [oracle.make_preset('CGDLoss', **CGD), oracle.make_preset('CDLoss')]
     times = []
     for i in range(warmup + steps):
         x = s.clone().requires_grad_(True)
         t0 = time.perf_counter()
-        loss = crits[0](x, t, gt, 1) + crits[1](x, t, gt, 1)
-        loss.backward()
+        l_cgd, l_cd = crits[0](x, t, gt, 1), crits[1](x, t, gt, 1)
+        (l_cgd + l_cd).backward()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return times, float(loss.detach())
+    return times, (float(l_cgd.detach()), float(l_cd.detach()))
+
+
+def gpu_aten_step_time(crits_kwargs, s, t, gt, steps=5, warmup=2, loss_fn=None):
+    """The reference's ATen op chain (oracle port of losses.py:95-113 + autograd) on the SAME GPU: what the drop-in
+    replaces when the reference itself runs on a B200 ("the true kernel to beat").  CUDA events.
+    crits_kwargs: [(preset name, ctor kwargs)]; or loss_fn(x) -> scalar for a chain that is not a preset."""
+    import torch
+    import oracle
+    crits = [oracle.make_preset(name, **kw) for name, kw in (crits_kwargs or [])]
+    x = s.detach().clone().requires_grad_(True)
+
+    def step():
+        x.grad = None
+        total = loss_fn(x) if loss_fn is not None else None
+        for c in crits:
+            v = c(x, t, gt, 1)
+            total = v if total is None else total + v
+        total.backward()
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
 
 
 def run_reference_arm(args, rank):
@@ -155,20 +199,23 @@ def run_reference_arm(args, rank):
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_b = 2
-    times, _ = cpu_oracle_step_time(sample_b, args.steps, args.warmup)
+    s, t = make_inputs(0)                 # the whole shard of rank 0: the tensors the GPU arm runs
+    times, losses = cpu_oracle_step_time(s, t, args.steps, args.warmup)
     total = sum(times)
-    value = sample_b * H * W * len(times) / total / 1e6
+    value = B_PER_GPU * H * W * len(times) / total / 1e6
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'timing': 'host perf_counter, CPU only'},
+        'config': dict(CONFIG),
+        'timing': 'host perf_counter, CPU only, mean over the timed steps',
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-                         'sample': f'each step = CGD+CD fwd+bwd on {sample_b} of the {B_PER_GPU} samples '
-                                   f'({sample_b}x{C}x{H}x{W} fp32), oracle port of losses.py on torch CPU'},
+                         'sample': f'each step = CGD+CD fwd+bwd on the whole shard of rank 0 ({B_PER_GPU}x{C}x{H}x{W} fp32, '
+                                   f'the GPU arm\'s tensors), oracle port of losses.py on torch CPU, every host thread; '
+                                   f'the reference is Python on top of mmcv (absent): it cannot travel to the GPU box'},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
+        'loss_values': {'cgd': losses[0], 'cd': losses[1]},
     }
     print(json.dumps(line), flush=True)
 
@@ -206,9 +253,10 @@ def run_ours(args, rank, local_rank, world):
         _note(rank, 'process group up')
     assert _cabi.load().sd_device_check() == 0, 'not an sm_100 device'
 
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    S = torch.randn(B_PER_GPU, C, H, W, device=dev, generator=g).requires_grad_(True)
-    T = torch.randn(B_PER_GPU, C, H, W, device=dev, generator=g)
+    hS, hT = make_inputs(rank)                      # CPU, seeded: every leg runs these tensors
+    hS, hT = hS.pin_memory(), hT.pin_memory()
+    S = hS.to(dev).requires_grad_(True)
+    T = hT.to(dev)
     gt = torch.zeros(B_PER_GPU, 1, H, W, dtype=torch.long, device=dev)
     dl = sd.DistillationLoss([
         {'student_layer': 'decode_head.linear_pred', 'teacher_layer': 'decode_head.linear_pred',
@@ -216,8 +264,13 @@ def run_ours(args, rank, local_rank, world):
         {'student_layer': 'decode_head', 'teacher_layer': 'decode_head', 'loss_name': 'CDLoss', 'loss_config': {}}])
     dl.batch_pairs = not args.unfused
     numel = S.numel()
-    packed = torch.zeros(3, device=dev)
-    slots = [torch.zeros(3, device=dev) for _ in range(2)]      # N>1: what the collectives read (two steps in flight)
+    # N > 1: the path's only collective is the all-reduce of the loss scalars for logging.  The reference issues one
+    # per log variable per step (SD_structure.py:137-142); here every step appends its scalars to a device-resident
+    # ring (one 32-thread launch, captured with the step) and the ring is all-reduced ONCE per LOG_INTERVAL steps -
+    # the interval at which the reference's logger reads them (default_runtime.py:2-7).  No NCCL kernel sits between
+    # two steps' loss kernels; the flush of the steps timed here is inside the timed region.
+    LOG_INTERVAL = 50
+    logs = sdist.DeferredLogs(['loss_cgd', 'loss_cd'], interval=LOG_INTERVAL, device=dev) if world > 1 else None
 
     def feats(x):
         return {'decode_head.linear_pred': x, 'decode_head': x}
@@ -235,33 +288,21 @@ def run_ours(args, rank, local_rank, world):
         (l1 + l2).backward()
         if record:
             record[2].record()
-        if world > 1:
-            packed[0], packed[1] = l1.detach(), l2.detach()
+        if logs is not None:
+            logs.push([l1, l2])                # device-side append, no collective
         return l1, l2
 
-    pending = []
+    flushed = []
 
-    def reduce_scalars(slot=None):
-        """The path's only collective: the packed loss scalars of this step, all-reduced asynchronously so that the
-        next step's kernels do not queue behind it.  slot: the static buffer a captured step copied them to (replays
-        alternate between two graphs / slots); None: an eager step, a fresh copy is made."""
-        if world > 1:
-            buf = packed.clone() if slot is None else slots[slot]
-            pending.append((dist.all_reduce(buf, async_op=True), buf))
-            if len(pending) > 1:                       # before a slot is written again its collective has completed
-                pending.pop(0)[0].wait()
-
-    def drain_scalars():
-        while pending:
-            pending.pop(0)[0].wait()
+    def flush_logs():
+        """one all-reduce + one D2H for all the steps since the last flush"""
+        if logs is not None:
+            flushed.extend(logs.flush())
 
     def step(record=None):
-        r = compute(record)
-        reduce_scalars()
-        return r
+        return compute(record)
 
     def sync_all():
-        drain_scalars()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -293,20 +334,14 @@ def run_ours(args, rank, local_rank, world):
             sync_all()
             # capture on the stream the warm-up ran on: its zero-filled workspace exists already (a fresh
             # capture stream would put the one-time workspace allocation + fill into every replay).  The scalar
-            # all-reduce is launched after each replay, not captured; with N > 1 two graphs alternate, each ending
-            # with a copy of the packed scalars into its own slot for the collective to read.
-            graphs = []
-            for k in range(2 if world > 1 else 1):
-                g_ = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g_, stream=side):
-                    static_losses = compute()
-                    if world > 1:
-                        slots[k].copy_(packed)
-                graphs.append(g_)
-            graph, graph_note = graphs, 'CUDA graph replay of the captured module-API step'
+            # append of the step's loss scalars to the log ring (N > 1) is part of the captured step.
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_, stream=side):
+                static_losses = compute()
+            graph, graph_note = [g_], 'CUDA graph replay of the captured module-API step'
             for i in range(4):
-                graph[i % len(graph)].replay()
-                reduce_scalars(i % len(graph))
+                graph[0].replay()
+            flush_logs()
             sync_all()
             _note(rank, 'graph captured')
         except Exception as exc:          # capture is an optimisation, never a requirement
@@ -323,19 +358,26 @@ def run_ours(args, rank, local_rank, world):
     t_begin.record()
     for i in range(args.steps):
         l1, l2 = step(evs[i])
-    drain_scalars()
+        if logs is not None and (i + 1) % LOG_INTERVAL == 0:
+            flush_logs()
+    flush_logs()                             # (N > 1) the scalars of the timed steps are reduced inside the timed region
     t_end.record()
     sync_all()
     launches = _cabi.launch_count() - launches0
     eager_ms = t_begin.elapsed_time(t_end) / args.steps
+    if world > 1:
+        tt = torch.tensor([eager_ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        eager_ms = tt.item()
     if graph is not None:
         # timed region of the headline number: exactly K replays of the captured step
         per_step_launches = launches // args.steps
         t_begin.record()
         for i in range(args.steps):
-            graph[i % len(graph)].replay()
-            reduce_scalars(i % len(graph))
-        drain_scalars()                      # the timed region ends when the last collective has completed
+            graph[0].replay()
+            if logs is not None and (i + 1) % LOG_INTERVAL == 0:
+                flush_logs()
+        flush_logs()                         # the timed region ends when the steps' scalars have been reduced and read
         t_end.record()
         sync_all()
         l1, l2 = static_losses
@@ -379,8 +421,6 @@ def run_ours(args, rank, local_rank, world):
     # ---- e2e: pinned host buffers -> H2D -> modules -> D2H of the loss scalars, every step
     e2e = None
     if not args.no_e2e:
-        hS = torch.randn(B_PER_GPU, C, H, W).pin_memory()
-        hT = torch.randn(B_PER_GPU, C, H, W).pin_memory()
         dS_in = torch.empty_like(S).requires_grad_(True)
         dT_in = torch.empty_like(T)
 
@@ -390,9 +430,9 @@ def run_ours(args, rank, local_rank, world):
                 dS_in.copy_(hS, non_blocking=True)
                 dT_in.copy_(hT, non_blocking=True)
             losses = dl(feats(dS_in), feats(dT_in), gt, 1, None, None)
-            total, logs = sdist.parse_losses(losses)     # one packed all-reduce + ONE D2H read per step
+            total, log_vars = sdist.parse_losses(losses)     # one packed all-reduce + ONE D2H read per step
             total.backward()
-            return logs
+            return log_vars
 
         n_e2e = max(3, min(args.steps, 10))
         for _ in range(2):
@@ -412,24 +452,36 @@ def run_ours(args, rank, local_rank, world):
         e2e = {'value': world * B_PER_GPU * H * W / (ems / n_e2e * 1e-3) / 1e6, 'unit': UNIT,
                'h2d_bytes_per_step': 2 * numel * 4, 'd2h_bytes_per_step': 3 * 4, 'steps': n_e2e,
                'ms_per_step': ems / n_e2e}
-        del hS, hT, dS_in, dT_in
+        del dS_in, dT_in
 
     extra = None
     if args.extra and world == 1:
         extra = extra_configs(dev)
 
     # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample
-    cpu = None
+    cpu, loss_check, aten = None, None, None
+    gpu_losses = {'cgd': float(l1.detach()), 'cd': float(l2.detach())}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample_b = 8
-        times, _ = cpu_oracle_step_time(sample_b, steps=8, warmup=2, threads=cores)
-        best = min(times)
-        cpu = {'value': sample_b * H * W / best / 1e6, 'unit': UNIT, 'cores': torch.get_num_threads(),
+        times, cpu_losses = cpu_oracle_step_time(hS, hT, steps=4, warmup=1, threads=cores)
+        mean = sum(times) / len(times)
+        cpu = {'value': B_PER_GPU * H * W / mean / 1e6, 'unit': UNIT, 'cores': torch.get_num_threads(),
                'kind': 'port',
-               'sample': f'CGD+CD fwd+bwd on {sample_b} of the {B_PER_GPU} samples ({sample_b}x{C}x{H}x{W} fp32), '
-                         f'best of 8 after 2 warm-ups ({sum(times):.1f} s of CPU work), oracle port of losses.py on '
+               'sample': f'CGD+CD fwd+bwd on the whole shard ({B_PER_GPU}x{C}x{H}x{W} fp32, the tensors the GPU arm ran), '
+                         f'mean of 4 steps after 1 warm-up ({sum(times):.1f} s of CPU work), oracle port of losses.py on '
                          f'torch CPU, every host thread'}
+        # the benchmarked step computed the reference's numbers (north_star: loss rel. err <= 1e-5)
+        errs = {'cgd': abs(gpu_losses['cgd'] - cpu_losses[0]) / abs(cpu_losses[0]),
+                'cd': abs(gpu_losses['cd'] - cpu_losses[1]) / abs(cpu_losses[1])}
+        loss_check = {'cpu_port': {'cgd': cpu_losses[0], 'cd': cpu_losses[1]}, 'rel_err': errs, 'tol': 1e-5,
+                      'ok': max(errs.values()) <= 1e-5}
+        assert loss_check['ok'], f'benchmarked losses differ from the CPU port: {loss_check}'
+    if rank == 0 and world == 1 and not args.no_aten:
+        ms = gpu_aten_step_time([('CGDLoss', dict(CGD)), ('CDLoss', {})], S, T, gt)
+        aten = {'ms_per_step': ms, 'value': B_PER_GPU * H * W / (ms * 1e-3) / 1e6, 'unit': UNIT,
+                'what': 'the reference\'s op chain (oracle port of losses.py:95-113: div, log_softmax, softmax, kl_div, autograd '
+                        'backward) as ATen CUDA kernels on this GPU, same tensors, CUDA events, 5 steps after 2 warm-ups'}
+        torch.cuda.empty_cache()
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -442,11 +494,14 @@ def run_ours(args, rank, local_rank, world):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'per_gpu_shape': [B_PER_GPU, C, H, W], 'losses': ['CGDLoss', 'CDLoss'],
-                       'l2': 'inputs (2 x 157 MB per GPU) exceed the 126 MB L2; no flush',
-                       'timing': 'CUDA events on the launch stream, max over ranks',
-                       'launch': graph_note,
-                       'parallelism': f'batch-sharded x{world}, one scalar all-reduce per step'},
+            'config': dict(CONFIG),
+            'timing': 'CUDA events on the launch stream, max over ranks',
+            'launch': graph_note,
+            'parallelism': (f'batch-sharded x{world}; loss scalars appended to a device ring every step, one all-reduce per '
+                            f'{LOG_INTERVAL} steps (and at the end of the timed region)' if world > 1 else 'single GPU'),
+            # the same step driven eagerly through the module API (what mmcv's runner does), device-timed
+            'eager': {'ms_per_step': eager_ms, 'value': world * B_PER_GPU * H * W / (eager_ms * 1e-3) / 1e6, 'unit': UNIT},
+            'gpu_aten_baseline': aten, 'loss_check': loss_check,
             'melem_per_s': world * numel / (ms_per_step * 1e-3) / 1e6,
             'hbm_gbs_step': world * launches_per_step * cd_bytes / (ms_per_step * 1e-3) / 1e9,
             'kernel_ms': {'dominant_kernel': kern_ms, 'loss_kernels_fwd_eager': fwd_ms, 'backward_eager': bwd_ms,
@@ -457,8 +512,10 @@ def run_ours(args, rank, local_rank, world):
                          'algorithmic_bytes_per_launch': cd_bytes, 'traffic': profiled_traffic(),
                          'timing': 'CUDA events around back-to-back launches of the kernel on the launch stream'},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'cpu_baseline': cpu,
-            'loss_values': {'cgd': float(l1.detach()), 'cd': float(l2.detach())},
+            'loss_values': gpu_losses,
         }
+        if flushed:
+            line['reduced_log_sample'] = flushed[-1]
         if extra:
             line['extra'] = extra
         print(json.dumps(line), flush=True)
@@ -519,19 +576,35 @@ def extra_configs(dev):
         t = torch.randn(shape, device=dev).to(dtype)
         return s, t
 
+    import oracle
     peak, _ = measured_peak()
-    for name, crit, shape, dtype in (
-            ('cfg1_cd_2x150x64x64_f32', sd.CDLoss(), (2, 150, 64, 64), torch.float32),
-            ('cfg3_cd_16x150x128x128_bf16', sd.CDLoss(), (16, 150, 128, 128), torch.bfloat16),
-            ('cfg3_pd_16x150x128x128_bf16', sd.PDLoss(), (16, 150, 128, 128), torch.bfloat16),
-            ('cfg3_pd_16x150x128x128_f32', sd.PDLoss(), (16, 150, 128, 128), torch.float32),
-            ('cfg4_cd+mse_fused_16x512x64x64_f32', sd.CDMSELoss(alpha=1, tau=4), (16, 512, 64, 64), torch.float32),
-            ('cfg4_mse_16x512x64x64_f32', sd.FeatureMSELoss(), (16, 512, 64, 64), torch.float32)):
+
+    def aten_ms(presets, s, t, gt_hw=None, loss_fn=None):
+        """the reference's ATen chain for the same loss on this GPU (ms per fwd+bwd), or None when it does not fit"""
+        hw = gt_hw or tuple(s.shape[2:])
+        gt = torch.zeros(s.shape[0], 1, *hw, dtype=torch.long, device=dev)
+        try:
+            return gpu_aten_step_time(presets, s, t, gt, steps=3, warmup=1, loss_fn=loss_fn)
+        except torch.OutOfMemoryError:
+            return None
+        finally:
+            torch.cuda.empty_cache()
+
+    for name, crit, shape, dtype, presets in (
+            ('cfg1_cd_2x150x64x64_f32', sd.CDLoss(), (2, 150, 64, 64), torch.float32, [('CDLoss', {})]),
+            ('cfg3_cd_16x150x128x128_bf16', sd.CDLoss(), (16, 150, 128, 128), torch.bfloat16, [('CDLoss', {})]),
+            ('cfg3_pd_16x150x128x128_bf16', sd.PDLoss(), (16, 150, 128, 128), torch.bfloat16, [('PDLoss', {})]),
+            ('cfg3_pd_16x150x128x128_f32', sd.PDLoss(), (16, 150, 128, 128), torch.float32, [('PDLoss', {})]),
+            ('cfg4_cd+mse_fused_16x512x64x64_f32', sd.CDMSELoss(alpha=1, tau=4), (16, 512, 64, 64), torch.float32,
+             [('CGDLoss', dict(group_size=1, alpha=1, tau=4))]),
+            ('cfg4_mse_16x512x64x64_f32', sd.FeatureMSELoss(), (16, 512, 64, 64), torch.float32, [])):
         s, t = pair(shape, dtype)
         eager, ms = timeit(fwd_bwd(crit, s, t))
         nbytes = 3 * s.numel() * s.element_size()
+        mse_fn = (lambda x, t=t: oracle.mse_loss_torch(x, t, 1.0)) if 'mse' in name else None
         out[name] = {'ms': ms, 'ms_eager': eager, 'mpixel_s': shape[0] * shape[2] * shape[3] / ms / 1e3,
-                     'gbs': nbytes / ms / 1e6, 'frac_of_measured_peak': nbytes / ms / 1e6 / peak}
+                     'gbs': nbytes / ms / 1e6, 'frac_of_measured_peak': nbytes / ms / 1e6 / peak,
+                     'aten_chain_ms': aten_ms(presets, s, t, loss_fn=mse_fn)}
     stages = [(16, 32, 128, 128), (16, 64, 64, 64), (16, 160, 32, 32), (16, 256, 16, 16)]
     pairs = [pair(sh, torch.float32) for sh in stages]
     crit = sd.CGDLoss()
@@ -542,8 +615,10 @@ def extra_configs(dev):
             crit(s, t, None, 1).backward()
     eager, ms = timeit(cfg2)
     nbytes = sum(3 * s.numel() * 4 for s, _ in pairs)
+    aten2 = [aten_ms([('CGDLoss', {})], s, t) for s, t in pairs]
     out['cfg2_cgd_4stages_b16_f32'] = {'ms': ms, 'ms_eager': eager, 'mpixel_s': sum(s.shape[0] * s.shape[2] * s.shape[3] for s, _ in pairs) / ms / 1e3,
-                                       'gbs': nbytes / ms / 1e6, 'frac_of_measured_peak': nbytes / ms / 1e6 / peak}
+                                       'gbs': nbytes / ms / 1e6, 'frac_of_measured_peak': nbytes / ms / 1e6 / peak,
+                                       'aten_chain_ms': sum(aten2) if all(v is not None for v in aten2) else None}
     # the reference's real training path: logits at 1/4 resolution resized to the 512x512 labels;
     # fused = bilinear up-sampling inside the loss kernels, host = F.interpolate first (what the reference does)
     for name, cls, shape in (('f1_cgd_resize4_2x150x128x128_f32', sd.CGDLoss, (2, 150, 128, 128)),
@@ -565,6 +640,14 @@ def extra_configs(dev):
         rec['mpixel_s'] = shape[0] * 16 * shape[2] * shape[3] / rec['fused_ms'] / 1e3
         rec['upsampled_gelem_s'] = hi / rec['fused_ms'] / 1e6
         rec['speedup_vs_host_resize'] = rec['host_resize_ms'] / rec['fused_ms']
+        # these kernels regenerate every up-sampled value twice (statistics, gradient) and take its exponential for S and
+        # for T each time: 4 ex2 per up-sampled value.  The bound is the MUFU pipe (16 ex2 / clk / SM), not HBM.
+        mufu_peak = 148 * 16 * 1.965e9
+        rec['roofline'] = {'bound': 'mufu', 'ex2_per_upsampled_value': 4, 'achieved_gex2_s': 4 * hi / rec['fused_ms'] / 1e6,
+                           'peak_gex2_s': mufu_peak / 1e9, 'frac': 4 * hi / (rec['fused_ms'] * 1e-3) / mufu_peak,
+                           'peak_source': '148 SMs x 16 MUFU.EX2 / clk x 1.965 GHz (B300_MICROARCH.md; sm clock from MEASURED_PEAKS.json)'}
+        if shape[0] <= 2:                      # the reference chain on the resized maps (16x the elements): small batch only
+            rec['aten_chain_ms'] = aten_ms([(cls.__name__, {})], s, t, gt_hw=(4 * shape[2], 4 * shape[3]))
         out[name] = rec
     # IFVDLoss on the training shape: logits 2x150x128x128, labels 512x512 in 32-pixel blocks with an ignore band
     s, t = pair((2, 150, 128, 128), torch.float32)

@@ -225,6 +225,17 @@ SD_API int sd_scale_grad(void* dS, int64_t numel, int dtype, const float* grad_o
 SD_API int sd_scale_grad2(void* dS, int64_t numel, int dtype, const float* grad_output0, const float* grad_output1,
                    unsigned* nonuniform_flag, void* stream);
 
+/* ------------------------------------------------------------------ loss scalars for logging */
+/*
+ * mmseg/models/segmentors/SD_structure.py:137-142 all-reduces every log variable on every iteration (and blocks on
+ * .item()), although the logger reads them every 50 (local_configs/_base_/default_runtime.py:2-7).  Here the step's
+ * n scalars (device floats, e.g. the `loss` outputs of the calls above) are appended to a device-resident ring:
+ *   ring[(*cursor mod slots) * n + i] = values[i];  *cursor += 1
+ * - one 32-thread launch that a CUDA graph can capture (the slot is picked on the device) - and the host all-reduces
+ * the whole ring once per `slots` steps (segdistill_b200/dist.py: DeferredLogs).  ring: slots * n floats.
+ */
+SD_API int sd_log_push(const float* values, int n, float* ring, unsigned* cursor, int slots, void* stream);
+
 /* ------------------------------------------------------------------ CGD correlation (extension) */
 SD_API size_t sd_cgd_corr_workspace_bytes(int B, int C, int HW, int group);
 /*

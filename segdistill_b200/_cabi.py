@@ -31,7 +31,7 @@ EXPORTS = (
     'sd_kl_rows_up_workspace_bytes', 'sd_kl_rows_up_fwd_bwd', 'sd_kl_pixels_up_workspace_bytes', 'sd_kl_pixels_up_fwd_bwd',
     'sd_mse_workspace_bytes', 'sd_mse_fwd_bwd', 'sd_ifvd_sim_workspace_bytes', 'sd_ifvd_sim_fwd_bwd', 'sd_ifvd_max_channels',
     'sd_ifvd_class_map', 'sd_scale_grad',
-    'sd_cgd_corr_workspace_bytes', 'sd_cgd_corr_fwd_bwd',
+    'sd_cgd_corr_workspace_bytes', 'sd_cgd_corr_fwd_bwd', 'sd_log_push',
     'sd_launch_count', 'sd_last_kernel',
 )
 
@@ -107,6 +107,8 @@ def load():
         lib.sd_cgd_corr_workspace_bytes.argtypes = [i32, i32, i32, i32]
         lib.sd_cgd_corr_fwd_bwd.restype = i32
         lib.sd_cgd_corr_fwd_bwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp, sz, vp]
+        lib.sd_log_push.restype = i32
+        lib.sd_log_push.argtypes = [vp, i32, vp, vp, i32, vp]
         lib.sd_launch_count.restype = c.c_uint64
         lib.sd_last_kernel.restype = c.c_char_p
         if lib.sd_abi_version() != 1:
@@ -488,3 +490,15 @@ def scale_grad_(ds: torch.Tensor, grad_output: torch.Tensor):
         rc = lib.sd_scale_grad(ds.data_ptr(), ds.numel(), _dtype_code(ds), g.data_ptr(), _stream_ptr(ds.device))
         _check(rc)
     return ds
+
+
+def log_push(values: torch.Tensor, ring: torch.Tensor, cursor: torch.Tensor):
+    """ring[cursor % slots] = values; cursor += 1, on the device (capturable).  values: n contiguous fp32 on the GPU;
+    ring: (slots, n) fp32; cursor: one int32."""
+    lib = load()
+    n = values.numel()
+    if values.dtype != torch.float32 or not values.is_contiguous() or ring.dtype != torch.float32 or ring.shape[1] != n:
+        raise SegDistillError('log_push: values must be n contiguous fp32, ring (slots, n) fp32')
+    with _on(values.device):
+        _check(lib.sd_log_push(values.data_ptr(), n, ring.data_ptr(), cursor.data_ptr(), ring.shape[0],
+                               _stream_ptr(values.device)))

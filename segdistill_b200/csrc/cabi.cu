@@ -704,6 +704,17 @@ int sd_scale_grad(void* dS, int64_t numel, int dtype, const float* grad_output, 
     return e == cudaSuccess ? SD_OK : (int)e;
 }
 
+int sd_log_push(const float* values, int n, float* ring, unsigned* cursor, int slots, void* stream) {
+    if (!values || !ring || !cursor) return SD_ERR_NULL;
+    if (n <= 0 || slots <= 0) return SD_ERR_SHAPE;
+    DeviceInfo& dev = device_info();
+    if (dev.cc_major != 10) return SD_ERR_DEVICE;
+    cudaError_t e = sd::launch_log_push(values, n, ring, cursor, slots, static_cast<cudaStream_t>(stream));
+    g_launches += 1;
+    t_last_kernel = "log_push_kernel";
+    return e == cudaSuccess ? SD_OK : (int)e;
+}
+
 int sd_scale_grad2(void* dS, int64_t numel, int dtype, const float* grad_output0, const float* grad_output1,
                    unsigned* nonuniform_flag, void* stream) {
     if (!dS || !grad_output0 || !grad_output1 || !nonuniform_flag) return SD_ERR_NULL;

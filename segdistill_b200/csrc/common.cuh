@@ -180,16 +180,20 @@ struct Elem<__nv_bfloat16> {
 };
 
 // ---------------------------------------------------------------- KL without cancellation when S ~ T
-// KL(p||q) = sum p (t - s)/tau - (lse_t - lse_s).  With lse = M/tau + ln Z the difference of the two logarithms
-// loses everything below ulp(ln Z) ~ 1e-6 - as large as the whole KL of a nearly converged student (the reference's
-// own log_softmax chain, losses.py:108-111, is ~6e-4 accurate there).  Every kernel therefore ALSO accumulates
-//     dd = sum_i (et_i - es_i),   es_i = exp2(s_i c2 - sigma), et_i = exp2(t_i c2 - theta)
-// element by element (a sum of small terms when S ~ T, whatever the references sigma = fl(ms c2), theta = fl(mt c2)
-// are), and evaluates  lse_t - lse_s = (theta - sigma) ln 2 + log1p(dd / zs):  three terms of the size of the
-// differences t - s, each with fp32 relative accuracy.  When partial sums taken against different references are
-// merged, dd' = sum_k dd_k ft_k + zs_k (ft_k - fs_k) with the rescale factors fs_k = 2^(sigma_k - sigma'),
-// ft_k = 2^(theta_k - theta'); their difference comes from factor_diff below (exp2m1 of the small exponent gap), never
-// from subtracting two rounded factors.
+// With as_i = s_i c2 - sigma, at_i = t_i c2 - theta the exponents the kernels feed to ex2 (sigma = fl(ms c2),
+// theta = fl(mt c2) the references, c2 = log2(e)/tau), es_i = 2^as_i, et_i = 2^at_i, zs = sum es, zt = sum et:
+//     KL(p||q) = sum p_i ln(p_i / q_i) = ln2 * (sum et_i (at_i - as_i)) / zt  -  ln(zt / zs)
+// exactly - the references cancel algebraically, so a constant offset between teacher and student (which a softmax
+// does not see) never enters.  Both terms are of the size of the differences t - s; the KL of a nearly converged
+// student is their difference, of second order.  ln(zt) - ln(zs) from two rounded logarithms would lose everything
+// below ulp(ln z) ~ 1e-6 - as large as the whole KL there (the reference's own log_softmax chain, losses.py:108-111,
+// is 6e-4 .. 1e-2 off on such inputs, tests/golden/kld_*near*).  Every kernel therefore accumulates, next to zs, zt:
+//     a2 = sum et_i (at_i - as_i)          dd = sum (et_i - es_i)        (term by term: sums of small terms)
+// and evaluates ln(zt / zs) = log1p(dd / zs).  When partial sums taken against references (sigma_k, theta_k) are
+// merged into (sigma, theta), with fs_k = 2^(sigma_k - sigma), ft_k = 2^(theta_k - theta) and the shift
+// x_k = (theta_k - sigma_k) - (theta - sigma) = log2(ft_k / fs_k):
+//     a2 = sum_k ft_k (a2_k + zt_k x_k)     dd = sum_k dd_k ft_k + zs_k (ft_k - fs_k),   ft_k - fs_k = fs_k (2^x_k - 1)
+// x_k comes from compensated differences (exact), 2^x - 1 from a polynomial - never from subtracting rounded factors.
 
 // 2^x - 1 for |x| <= 0.25, relative error ~1e-8 (Taylor in y = x ln 2, |y| <= 0.174)
 __device__ __forceinline__ float exp2m1_small(float x) {
@@ -202,21 +206,39 @@ __device__ __forceinline__ float exp2m1_small(float x) {
     p = fmaf(p, y, 1.f);
     return p * y;
 }
-// ft - fs for rescale factors fs = 2^xs, ft = 2^xt, given x = xt - xs formed from the small differences
-// (theta_k - sigma_k) - (theta' - sigma') (each exact when S ~ T).  Away from x ~ 0 nothing cancels.
+// ft - fs for rescale factors fs = 2^xs, ft = 2^xt, given x = xt - xs.  Away from x ~ 0 nothing cancels.
 __device__ __forceinline__ float factor_diff(float fs, float ft, float x) {
     return fabsf(x) <= 0.25f ? fs * exp2m1_small(x) : ft - fs;
 }
-// exponent gap (theta_k - sigma_k) - (theta - sigma) of a part (ms_k, mt_k) merged into (ms, mt); the products are
-// rounded exactly as the kernels round the references of their exponentials (fmaf(x, c2, -fl(m c2)))
-__device__ __forceinline__ float ref_gap2(float ms, float mt, float c2) { return __fmul_rn(mt, c2) - __fmul_rn(ms, c2); }
+// a - b and its exact rounding error (Knuth's TwoSum on a + (-b))
+__device__ __forceinline__ float two_diff(float a, float b, float& err) {
+    const float d = __fsub_rn(a, b);
+    const float bb = __fsub_rn(d, a);
+    err = __fsub_rn(__fsub_rn(a, __fsub_rn(d, bb)), __fadd_rn(b, bb));
+    return d;
+}
+// the shift x_k = (theta_k - sigma_k) - (theta - sigma) of a part merged into new references, all four in the
+// exponent (log2) domain; exact up to one final rounding whatever offset separates teacher and student
+__device__ __forceinline__ float merge_shift2(float sk, float tk, float s, float t) {
+    float e1, e2;
+    const float d1 = two_diff(tk, sk, e1), d2 = two_diff(t, s, e2);
+    return __fadd_rn(__fsub_rn(d1, d2), __fsub_rn(e1, e2));
+}
+// the same from references in the value domain; the products are rounded exactly as the kernels round the
+// references of their exponentials (fmaf(x, c2, -fl(m c2)))
+__device__ __forceinline__ float merge_shift(float msk, float mtk, float ms, float mt, float c2) {
+    return merge_shift2(__fmul_rn(msk, c2), __fmul_rn(mtk, c2), __fmul_rn(ms, c2), __fmul_rn(mt, c2));
+}
 // 2^(fl(m_k c2) - fl(m c2)): rescale factor of sums taken against m_k to the reference m >= m_k
 __device__ __forceinline__ float ref_factor(float mk, float m, float c2) {
     return fast_exp2(__fmul_rn(mk, c2) - __fmul_rn(m, c2));
 }
-// KL of one row from its merged statistics; gap2 = fl(mt c2) - fl(ms c2)
-__device__ __forceinline__ float kl_from_stats(float inv_tau, float gap2, float zs, float zt, float a, float dd) {
-    return inv_tau * a / zt - (gap2 * kLn2 + log1pf(dd / zs));
+// KL of one row from its merged statistics.  log1p(dd / zs) needs zt / zs = 1 + dd / zs away from 0; where the two
+// sums differ by more than a factor 2 the plain logarithms are as good (nothing cancels there).
+__device__ __forceinline__ float kl_from_stats(float zs, float zt, float a2, float dd) {
+    const float r = dd / zs;
+    const float lse = fabsf(r) < 0.5f ? log1pf(r) : logf(zt) - logf(zs);
+    return kLn2 * a2 / zt - lse;
 }
 
 // softmax statistics of a piece of a row: max m and z = sum exp2((x - m)*c2)

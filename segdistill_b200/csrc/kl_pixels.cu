@@ -191,12 +191,12 @@ kl_pixels_tma_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_cons
 #pragma unroll
                 for (int q = 0; q < PXT; ++q) {
                     const int i = k * PXT + q;
-                    const float d = t[i] - s[i];
-                    const float es = fast_exp2(fmaf(s[i], c2, -rs2[q]));
-                    const float et = fast_exp2(fmaf(t[i], c2, -rt2[q]));
+                    const float as = fmaf(s[i], c2, -rs2[q]), at = fmaf(t[i], c2, -rt2[q]);
+                    const float es = fast_exp2(as);
+                    const float et = fast_exp2(at);
                     zs[q] += es;
                     zt[q] += et;
-                    ac[q] = fmaf(et, d, ac[q]);
+                    ac[q] = fmaf(et, at - as, ac[q]);
                     dd[q] += et - es;
                     s[i] = es;
                     t[i] = et;
@@ -223,7 +223,7 @@ kl_pixels_tma_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_cons
             kt[q] = p.coef / Zt;
             ga[q] = AT ? p.at_gcoef * dm[q] : 0.f;
             if (cg == 0 && px + q < p.HW) {
-                const float kl = kl_from_stats(p.inv_tau, rt2[q] - rs2[q], Zs, Zt, A, DD);
+                const float kl = kl_from_stats(Zs, Zt, A, DD);
                 p.row_kl[(size_t)b * p.HW + px + q] = kl;
                 acc_kl += kl;
                 if (AT) acc_at = fmaf(dm[q], dm[q], acc_at);
@@ -319,11 +319,12 @@ __global__ void __launch_bounds__(256) kl_pixels_generic(const PixParams p) {
         float zs = 0.f, zt = 0.f, ac = 0.f, dd = 0.f;
         for (int c = 0; c < p.C; ++c) {
             const float a = E::load(s + (size_t)c * p.HW), bb = E::load(t + (size_t)c * p.HW);
-            const float es = fast_exp2(fmaf(a, p.c2, -ms2));
-            const float et = fast_exp2(fmaf(bb, p.c2, -mt2));
+            const float as = fmaf(a, p.c2, -ms2), at = fmaf(bb, p.c2, -mt2);
+            const float es = fast_exp2(as);
+            const float et = fast_exp2(at);
             zs += es;
             zt += et;
-            ac = fmaf(et, bb - a, ac);
+            ac = fmaf(et, at - as, ac);
             dd += et - es;
         }
         const float dm = (ss - st) * p.inv_C;
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(256) kl_pixels_generic(const PixParams p) {
             const float et = fast_exp2(fmaf(bb, p.c2, -mt2));
             E::store(o + (size_t)c * p.HW, fmaf(es, ks, -et * kt) + ga);
         }
-        kl = kl_from_stats(p.inv_tau, mt2 - ms2, zs, zt, ac, dd);
+        kl = kl_from_stats(zs, zt, ac, dd);
         p.row_kl[r] = kl;
         if (AT) atsq = dm * dm;
     }

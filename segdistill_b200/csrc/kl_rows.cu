@@ -194,20 +194,23 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
         __syncthreads();
         if (tid == 0) issue_loads(nslots);
 
-        // ---- exponentials (kept in registers), thread-partial sums relative to (ms, mt); dd = sum (et - es) term by
-        //      term (common.cuh: KL without cancellation).  Against thread-local maxima zs and zt lie in [1, 32], so
-        //      zs = zt - dd is as accurate as a sum of its own: one accumulator less in the loop
+        // ---- exponentials (kept in registers), thread-partial sums relative to (ms, mt); a = sum et (at - as) and
+        //      dd = sum (et - es) term by term (common.cuh: KL without cancellation).  Against thread-local maxima zs
+        //      and zt lie in [1, 32], so zs = zt - dd is as accurate as a sum of its own: one accumulator less
         float zt = 0.f, dd = 0.f, a = 0.f, sq = 0.f;
         const float ms2 = __fmul_rn(ms, c2), mt2 = __fmul_rn(mt, c2);
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
-            const float d = t[i] - s[i];
-            if (MSE) sq = fmaf(d, d, sq);
-            const float es = fast_exp2(fmaf(s[i], c2, -ms2));
-            const float et = fast_exp2(fmaf(t[i], c2, -mt2));
+            if (MSE) {
+                const float d = t[i] - s[i];
+                sq = fmaf(d, d, sq);
+            }
+            const float as = fmaf(s[i], c2, -ms2), at = fmaf(t[i], c2, -mt2);
+            const float es = fast_exp2(as);
+            const float et = fast_exp2(at);
             zt += et;
             dd += et - es;
-            a = fmaf(et, d, a);
+            a = fmaf(et, at - as, a);
             if (!MSE) {
                 s[i] = es;
                 t[i] = et;
@@ -220,8 +223,8 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
         {
             const float fs = ref_factor(ms, msw, c2);
             const float ft = ref_factor(mt, mtw, c2);
-            const float gx = (mt2 - ms2) - ref_gap2(msw, mtw, c2);
-            const float wzs = warp_sum(zs * fs), wzt = warp_sum(zt * ft), wa = warp_sum(a * ft);
+            const float gx = merge_shift2(ms2, mt2, __fmul_rn(msw, c2), __fmul_rn(mtw, c2));
+            const float wzs = warp_sum(zs * fs), wzt = warp_sum(zt * ft), wa = warp_sum(fmaf(zt * ft, gx, a * ft));
             const float wdd = warp_sum(fmaf(zs, factor_diff(fs, ft, gx), dd * ft));
             const float wsq = MSE ? warp_sum(sq) : 0.f;
             if (lane == 0) {
@@ -242,17 +245,17 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
             Mt = max16(r0.y);
             const float fs = ref_factor(r0.x, Ms, c2);
             const float ft = ref_factor(r0.y, Mt, c2);
-            const float gx = ref_gap2(r0.x, r0.y, c2) - ref_gap2(Ms, Mt, c2);
+            const float gx = merge_shift(r0.x, r0.y, Ms, Mt, c2);
             Zs = sum16(r0.z * fs);
             Zt = sum16(r0.w * ft);
-            A = sum16(r1.x * ft);
+            A = sum16(fmaf(r0.w * ft, gx, r1.x * ft));
             DD = sum16(fmaf(r0.z, factor_diff(fs, ft, gx), r1.z * ft));
             if (MSE) SQ = sum16(r1.y);
         }
         par ^= 1;
 
         if (tid == 0) {
-            const float kl = kl_from_stats(p.l[0].inv_tau, ref_gap2(Ms, Mt, c2), Zs, Zt, A, DD);
+            const float kl = kl_from_stats(Zs, Zt, A, DD);
             if (p.l[0].row_kl) p.l[0].row_kl[x.b * p.l[0].G + x.grp] = kl;
             ps.kl += kl;
             if (MSE) ps.sq += SQ;
@@ -470,13 +473,16 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_pack_kernel(const RowsPar
         const float ms2 = __fmul_rn(ms, c2), mt2 = __fmul_rn(mt, c2);
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
-            const float d = t[i] - s[i];
-            if (MSE) my_sq = fmaf(d, d, my_sq);
-            const float es = fast_exp2(fmaf(s[i], c2, -ms2));
-            const float et = fast_exp2(fmaf(t[i], c2, -mt2));
+            if (MSE) {
+                const float d = t[i] - s[i];
+                my_sq = fmaf(d, d, my_sq);
+            }
+            const float as = fmaf(s[i], c2, -ms2), at = fmaf(t[i], c2, -mt2);
+            const float es = fast_exp2(as);
+            const float et = fast_exp2(at);
             zt += et;
             dd += et - es;
-            a = fmaf(et, d, a);
+            a = fmaf(et, at - as, a);
             if (!MSE) {
                 s[i] = es;
                 t[i] = et;
@@ -492,10 +498,11 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_pack_kernel(const RowsPar
         float Zs, Zt, A, DD;
         {
             const float fs = ref_factor(ms, Ms, c2), ft = ref_factor(mt, Mt, c2);
+            const float gx = merge_shift2(ms2, mt2, __fmul_rn(Ms, c2), __fmul_rn(Mt, c2));
             Zs = zs * fs;
             Zt = zt * ft;
-            A = a * ft;
-            DD = fmaf(zs, factor_diff(fs, ft, (mt2 - ms2) - ref_gap2(Ms, Mt, c2)), dd * ft);
+            A = fmaf(Zt, gx, a * ft);
+            DD = fmaf(zs, factor_diff(fs, ft, gx), dd * ft);
         }
         for (int o = seg >> 1; o > 0; o >>= 1) {
             Zs += __shfl_xor_sync(0xffffffffu, Zs, o);
@@ -521,8 +528,9 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_pack_kernel(const RowsPar
                 M2t = fmaxf(M2t, __shfl_xor_sync(0xffffffffu, M2t, o));
             }
             const float fs = ref_factor(r0.x, M2s, c2), ft = ref_factor(r0.y, M2t, c2);
-            float z2s = r0.z * fs, z2t = r0.w * ft, a2 = r1 * ft;
-            float d2 = fmaf(r0.z, factor_diff(fs, ft, ref_gap2(r0.x, r0.y, c2) - ref_gap2(M2s, M2t, c2)), r2 * ft);
+            const float gx = merge_shift(r0.x, r0.y, M2s, M2t, c2);
+            float z2s = r0.z * fs, z2t = r0.w * ft, a2 = fmaf(r0.w * ft, gx, r1 * ft);
+            float d2 = fmaf(r0.z, factor_diff(fs, ft, gx), r2 * ft);
             for (int o = tw >> 1; o > 0; o >>= 1) {
                 z2s += __shfl_xor_sync(0xffffffffu, z2s, o);
                 z2t += __shfl_xor_sync(0xffffffffu, z2t, o);
@@ -538,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_pack_kernel(const RowsPar
             par ^= 1;
         }
         if (active && lt == 0) {
-            const float kl = kl_from_stats(p.l[0].inv_tau, ref_gap2(Ms, Mt, c2), Zs, Zt, A, DD);
+            const float kl = kl_from_stats(Zs, Zt, A, DD);
             if (p.l[0].row_kl) p.l[0].row_kl[u * RPU + q] = kl;
             my_kl += kl;
         }
@@ -692,11 +700,12 @@ __global__ void __launch_bounds__(kGenThreads) kl_rows_generic_stats(const RowsP
     for (int i = threadIdx.x; i < x.n; i += kGenThreads) {
         const float a = E::load(s + i), b = E::load(t + i);
         const float d = b - a;
-        const float es = fast_exp2(fmaf(a, c2, -ms2));
-        const float et = fast_exp2(fmaf(b, c2, -mt2));
+        const float as = fmaf(a, c2, -ms2), at = fmaf(b, c2, -mt2);
+        const float es = fast_exp2(as);
+        const float et = fast_exp2(at);
         acc[0] += es;
         acc[1] += et;
-        acc[2] = fmaf(et, d, acc[2]);
+        acc[2] = fmaf(et, at - as, acc[2]);
         acc[3] = fmaf(d, d, acc[3]);
         acc[4] += et - es;
     }
@@ -756,7 +765,7 @@ __global__ void __launch_bounds__(kGenThreads) kl_rows_generic_grad(const RowsPa
     __syncthreads();
     const float Ms = row_stat[0], Zs = row_stat[1], Mt = row_stat[2], Zt = row_stat[3], A = row_stat[4];
     if (threadIdx.x == 0 && u == u0) {
-        const float kl = kl_from_stats(p.l[0].inv_tau, ref_gap2(Ms, Mt, c2), Zs, Zt, A, row_stat[5]);
+        const float kl = kl_from_stats(Zs, Zt, A, row_stat[5]);
         p.l[0].row_kl[x.b * p.l[0].G + grp] = kl;
     }
     const float ms2 = __fmul_rn(Ms, c2), mt2 = __fmul_rn(Mt, c2);

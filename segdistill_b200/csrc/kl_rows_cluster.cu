@@ -148,7 +148,9 @@ __device__ __forceinline__ float warp_max_uniform(float v) {
 
 // ---------------------------------------------------------------- statistics of a part of a row
 // NL losses share the raw maxima; sums are relative to them
-// (dd = sum (et - es), accumulated term by term: common.cuh, "KL without cancellation")
+// (a = sum et (at - as) and dd = sum (et - es), accumulated term by term: common.cuh, "KL without cancellation".
+// With R == 2 - one exponent for both losses, e[0] = e[1]^2 - a[0] is kept in units of the loss-1 exponent, i.e. it is
+// half the true sum, everywhere up to kl_of_row.)
 template <int NL>
 struct PStat {
     float ms, mt;
@@ -177,16 +179,48 @@ __device__ __forceinline__ void exps(float x, float ref, const float (&c2)[NL], 
         for (int k = 0; k < NL; ++k) e[k] = ref_factor(x, ref, c2[k]);
     }
 }
+// the same, returning the exponents too (arg[0] in units of the loss-1 exponent when R == 2)
+template <int NL, int R>
+__device__ __forceinline__ void exps_args(float x, const float (&ref2)[NL], const float (&c2)[NL], float (&arg)[NL],
+                                          float (&e)[NL]) {
+    if (NL == 1) {
+        arg[0] = fmaf(x, c2[0], -ref2[0]);
+        e[0] = fast_exp2(arg[0]);
+    } else if (R == 2) {
+        arg[NL - 1] = fmaf(x, c2[NL - 1], -ref2[NL - 1]);
+        arg[0] = arg[NL - 1];
+        e[NL - 1] = fast_exp2(arg[NL - 1]);
+        e[0] = e[NL - 1] * e[NL - 1];
+    } else {
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+            arg[k] = fmaf(x, c2[k], -ref2[k]);
+            e[k] = fast_exp2(arg[k]);
+        }
+    }
+}
+// shift of the exponent gap per loss when sums taken against (ms, mt) move to (Ms, Mt) (common.cuh: merge_shift), in
+// the units a[k] is kept in
+template <int NL, int R>
+__device__ __forceinline__ void shifts(float ms, float mt, float Ms, float Mt, const float (&c2)[NL], float (&x)[NL]) {
+    if (NL == 2 && R == 2) {
+        x[NL - 1] = merge_shift(ms, mt, Ms, Mt, c2[NL - 1]);
+        x[0] = x[NL - 1];
+    } else {
+#pragma unroll
+        for (int k = 0; k < NL; ++k) x[k] = merge_shift(ms, mt, Ms, Mt, c2[k]);
+    }
+}
 // ft - fs per loss for sums taken against (ms, mt) that move to the references (Ms, Mt): see factor_diff
 template <int NL, int R>
-__device__ __forceinline__ void factor_diffs(float ms, float mt, float Ms, float Mt, const float (&c2)[NL],
-                                             const float (&fs)[NL], const float (&ft)[NL], float (&df)[NL]) {
+__device__ __forceinline__ void factor_diffs(const float (&x)[NL], const float (&fs)[NL], const float (&ft)[NL],
+                                             float (&df)[NL]) {
     if (NL == 2 && R == 2) {
-        df[NL - 1] = factor_diff(fs[NL - 1], ft[NL - 1], ref_gap2(ms, mt, c2[NL - 1]) - ref_gap2(Ms, Mt, c2[NL - 1]));
+        df[NL - 1] = factor_diff(fs[NL - 1], ft[NL - 1], x[NL - 1]);
         df[0] = df[NL - 1] * (ft[NL - 1] + fs[NL - 1]);      // fs[0] = fs[1]^2, ft[0] = ft[1]^2
     } else {
 #pragma unroll
-        for (int k = 0; k < NL; ++k) df[k] = factor_diff(fs[k], ft[k], ref_gap2(ms, mt, c2[k]) - ref_gap2(Ms, Mt, c2[k]));
+        for (int k = 0; k < NL; ++k) df[k] = factor_diff(fs[k], ft[k], x[k]);
     }
 }
 // the same with the references pre-multiplied (ref2[k] = ref * c2[k]): one FFMA per exponent
@@ -214,15 +248,16 @@ __device__ __forceinline__ PStat<NL> pstat_reduce(const PStat<NL>& x, const floa
         r.ms = fmaxf(r.ms, __shfl_xor_sync(0xffffffffu, r.ms, o));
         r.mt = fmaxf(r.mt, __shfl_xor_sync(0xffffffffu, r.mt, o));
     }
-    float fs[NL], ft[NL], df[NL];
+    float fs[NL], ft[NL], df[NL], sh[NL];
     exps<NL, R>(x.ms, r.ms, c2, fs);
     exps<NL, R>(x.mt, r.mt, c2, ft);
-    factor_diffs<NL, R>(x.ms, x.mt, r.ms, r.mt, c2, fs, ft, df);
+    shifts<NL, R>(x.ms, x.mt, r.ms, r.mt, c2, sh);
+    factor_diffs<NL, R>(sh, fs, ft, df);
 #pragma unroll
     for (int k = 0; k < NL; ++k) {
         r.zs[k] = x.zs[k] * fs[k];
         r.zt[k] = x.zt[k] * ft[k];
-        r.a[k] = x.a[k] * ft[k];
+        r.a[k] = fmaf(r.zt[k], sh[k], x.a[k] * ft[k]);
         r.dd[k] = fmaf(x.zs[k], df[k], x.dd[k] * ft[k]);
     }
 #pragma unroll
@@ -248,14 +283,17 @@ __device__ __forceinline__ PStat<NL> pstat_merge(const PStat<NL>& x, const PStat
     exps<NL, R>(y.ms, r.ms, c2, fys);
     exps<NL, R>(x.mt, r.mt, c2, fxt);
     exps<NL, R>(y.mt, r.mt, c2, fyt);
-    float dfx[NL], dfy[NL];
-    factor_diffs<NL, R>(x.ms, x.mt, r.ms, r.mt, c2, fxs, fxt, dfx);
-    factor_diffs<NL, R>(y.ms, y.mt, r.ms, r.mt, c2, fys, fyt, dfy);
+    float dfx[NL], dfy[NL], shx[NL], shy[NL];
+    shifts<NL, R>(x.ms, x.mt, r.ms, r.mt, c2, shx);
+    shifts<NL, R>(y.ms, y.mt, r.ms, r.mt, c2, shy);
+    factor_diffs<NL, R>(shx, fxs, fxt, dfx);
+    factor_diffs<NL, R>(shy, fys, fyt, dfy);
 #pragma unroll
     for (int k = 0; k < NL; ++k) {
+        const float zx = __fmul_rn(x.zt[k], fxt[k]), zy = __fmul_rn(y.zt[k], fyt[k]);
         r.zs[k] = __fadd_rn(__fmul_rn(x.zs[k], fxs[k]), __fmul_rn(y.zs[k], fys[k]));
-        r.zt[k] = __fadd_rn(__fmul_rn(x.zt[k], fxt[k]), __fmul_rn(y.zt[k], fyt[k]));
-        r.a[k] = __fadd_rn(__fmul_rn(x.a[k], fxt[k]), __fmul_rn(y.a[k], fyt[k]));
+        r.zt[k] = __fadd_rn(zx, zy);
+        r.a[k] = __fadd_rn(fmaf(zx, shx[k], __fmul_rn(x.a[k], fxt[k])), fmaf(zy, shy[k], __fmul_rn(y.a[k], fyt[k])));
         r.dd[k] = __fadd_rn(fmaf(x.zs[k], dfx[k], __fmul_rn(x.dd[k], fxt[k])), fmaf(y.zs[k], dfy[k], __fmul_rn(y.dd[k], fyt[k])));
     }
     return r;
@@ -299,9 +337,9 @@ __device__ __forceinline__ float warp_sum8_transposed(const float (&v)[8], int l
     t += __shfl_xor_sync(0xffffffffu, t, 1);
     return t;
 }
-__device__ __forceinline__ float kl_of_row(float inv_tau, float c2, float ms, float mt, float zs, float zt, float a, float dd) {
-    // KL(p||q) = sum p (t - s)/tau - (lse_t - lse_s), the difference of the log-sum-exps without cancellation
-    return kl_from_stats(inv_tau, ref_gap2(ms, mt, c2), zs, zt, a, dd);
+// a_unit: 2 for loss 0 of a launch with R == 2 (its a is kept in units of the loss-1 exponent), else 1
+__device__ __forceinline__ float kl_of_row(float a_unit, float zs, float zt, float a, float dd) {
+    return kl_from_stats(zs, zt, a_unit * a, dd);
 }
 
 // ---------------------------------------------------------------- geometry
@@ -638,14 +676,14 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
             SD_TICK(t4);
             // ---- off the critical path: the KL terms of the rows this CTA accounts for
             if (NL == 2 && lane == 0 && rank == 0) {
-                const float kl = kl_of_row(p.l[K].inv_tau, c2[K], sr.ms, sr.mt, sr.zs[K], sr.zt[K], sr.a[K], sr.dd[K]);
+                const float kl = kl_of_row(1.f, sr.zs[K], sr.zt[K], sr.a[K], sr.dd[K]);
                 if (p.l[K].row_kl) p.l[K].row_kl[rc.b * p.l[K].G + rc.grp] = kl;
                 kl_acc[K] += kl;
             }
 #pragma unroll
             for (int q = 0; q < kPrPasses; ++q) {
                 if ((lane & 7) == 0 && pl.pr_row[q] >= 0 && (int)rank == pl.pr_ca[q]) {
-                    const float kl = kl_of_row(p.l[0].inv_tau, c2[0], pr[q].ms, pr[q].mt, pr[q].zs[0], pr[q].zt[0], pr[q].a[0], pr[q].dd[0]);
+                    const float kl = kl_of_row(NL == 2 && R == 2 ? 2.f : 1.f, pr[q].zs[0], pr[q].zt[0], pr[q].a[0], pr[q].dd[0]);
                     const int rowi = NL == 2 ? rc.b * p.l[0].G + rc.grp * p.l[NL - 1].m + pl.pr_row[q] : rc.b * p.l[0].G + rc.grp;
                     if (p.l[0].row_kl) p.l[0].row_kl[rowi] = kl;
                     kl_acc[0] += kl;
@@ -750,16 +788,17 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
         auto raise_refs = [&](float wms, float wmt) {
             const float nms = fmaxf(st.ms, wms), nmt = fmaxf(st.mt, wmt);
             if (nms != st.ms || nmt != st.mt) {      // warp-uniform
-                float rs[NL], rt[NL], df[NL];
+                float rs[NL], rt[NL], df[NL], sh[NL];
                 exps<NL, R>(st.ms, nms, c2, rs);
                 exps<NL, R>(st.mt, nmt, c2, rt);
-                factor_diffs<NL, R>(st.ms, st.mt, nms, nmt, c2, rs, rt, df);
+                shifts<NL, R>(st.ms, st.mt, nms, nmt, c2, sh);
+                factor_diffs<NL, R>(sh, rs, rt, df);
 #pragma unroll
                 for (int k = 0; k < NL; ++k) {
                     st.dd[k] = fmaf(st.zs[k], df[k], st.dd[k] * rt[k]);
                     st.zs[k] *= rs[k];
                     st.zt[k] *= rt[k];
-                    st.a[k] *= rt[k];
+                    st.a[k] = fmaf(st.zt[k], sh[k], st.a[k] * rt[k]);
                 }
                 st.ms = nms;
                 st.mt = nmt;
@@ -776,15 +815,14 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
 #pragma unroll
             for (int i = 0; i < NE; ++i) {
                 if (i < n) {
-                    const float d = ft[i] - fs[i];
-                    float es[NL], et[NL];
-                    exps<NL, R>(fs[i], refs2, c2, es);
-                    exps<NL, R>(ft[i], reft2, c2, et);
+                    float as[NL], at[NL], es[NL], et[NL];
+                    exps_args<NL, R>(fs[i], refs2, c2, as, es);
+                    exps_args<NL, R>(ft[i], reft2, c2, at, et);
 #pragma unroll
                     for (int k = 0; k < NL; ++k) {
                         st.zs[k] += es[k];
                         st.zt[k] += et[k];
-                        st.a[k] = fmaf(et[k], d, st.a[k]);
+                        st.a[k] = fmaf(et[k], at[k] - as[k], st.a[k]);
                     }
                     if (NL == 2 && R == 2) {
                         const float dk = et[K] - es[K];          // et0 - es0 = (et1 - es1)(et1 + es1)

@@ -244,8 +244,7 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
                         b[2] = __fmul_rn(acc.mt, p.l[k].c2);
                         b[3] = coef / acc.zt;
                         if (u == rowu) {
-                            const float kl = kl_from_stats(p.l[k].inv_tau, ref_gap2(acc.ms, acc.mt, p.l[k].c2), acc.zs, acc.zt,
-                                                           acc.a, acc.dd);
+                            const float kl = kl_from_stats(acc.zs, acc.zt, acc.a, acc.dd);
                             if (p.l[k].row_kl) p.l[k].row_kl[rowi] = kl;
                             cta_kl[k] += kl;
                         }
@@ -276,11 +275,11 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
                     const float c2k = p.l[k].c2;
                     const float fs = live ? ref_factor(rms, Ms, c2k) : 0.f;
                     const float ft = live ? ref_factor(rmt, Mt, c2k) : 0.f;
-                    const float gx = live ? ref_gap2(rms, rmt, c2k) - ref_gap2(Ms, Mt, c2k) : 1.f;
-                    const float zsk = live ? rz[k][0] : 0.f;
+                    const float gx = live ? merge_shift(rms, rmt, Ms, Mt, c2k) : 0.f;
+                    const float zsk = live ? rz[k][0] : 0.f, ztk = (live ? rz[k][1] : 0.f) * ft;
                     const float Zs = warp_sum(zsk * fs);
-                    const float Zt = warp_sum((live ? rz[k][1] : 0.f) * ft);
-                    const float A = warp_sum((live ? rz[k][2] : 0.f) * ft);
+                    const float Zt = warp_sum(ztk);
+                    const float A = warp_sum(fmaf(ztk, gx, (live ? rz[k][2] : 0.f) * ft));
                     const float DD = warp_sum(fmaf(zsk, factor_diff(fs, ft, gx), (live ? rz[k][3] : 0.f) * ft));
                     if (lane == 6 * k + 0) val = Ms;
                     if (lane == 6 * k + 1) val = Zs;
@@ -425,15 +424,18 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
                             E::unpack(vt[r], ft);
 #pragma unroll
                             for (int q = 0; q < VE; ++q) {
-                                const float d = ft[q] - fs[q];
-                                if (MSE) sq = fmaf(d, d, sq);
+                                if (MSE) {
+                                    const float d = ft[q] - fs[q];
+                                    sq = fmaf(d, d, sq);
+                                }
 #pragma unroll
                                 for (int k = 0; k < NL; ++k) {
-                                    const float es = fast_exp2(fmaf(fs[q], p.l[k].c2, -ms2[k]));
-                                    const float et = fast_exp2(fmaf(ft[q], p.l[k].c2, -mt2[k]));
+                                    const float as = fmaf(fs[q], p.l[k].c2, -ms2[k]), at = fmaf(ft[q], p.l[k].c2, -mt2[k]);
+                                    const float es = fast_exp2(as);
+                                    const float et = fast_exp2(at);
                                     zt[k] += et;
                                     dd[k] += et - es;
-                                    a[k] = fmaf(et, d, a[k]);
+                                    a[k] = fmaf(et, at - as, a[k]);
                                 }
                             }
                         }
@@ -456,10 +458,11 @@ __global__ void __launch_bounds__(kSThreads, 2) kl_rows_stream_kernel(const Rows
                 const float fs = ref_factor(ms, msw, c2k);
                 const float ft = ref_factor(mt, mtw, c2k);
                 const float zs = zt[k] - dd[k];
+                const float gx = merge_shift2(ms2[k], mt2[k], __fmul_rn(msw, c2k), __fmul_rn(mtw, c2k));
                 rec[2 + 4 * k] = warp_sum(zs * fs);
                 rec[3 + 4 * k] = warp_sum(zt[k] * ft);
-                rec[4 + 4 * k] = warp_sum(a[k] * ft);
-                rec[5 + 4 * k] = warp_sum(fmaf(zs, factor_diff(fs, ft, (mt2[k] - ms2[k]) - ref_gap2(msw, mtw, c2k)), dd[k] * ft));
+                rec[4 + 4 * k] = warp_sum(fmaf(zt[k] * ft, gx, a[k] * ft));
+                rec[5 + 4 * k] = warp_sum(fmaf(zs, factor_diff(fs, ft, gx), dd[k] * ft));
             }
             if (MSE) rec[6] = warp_sum(sq);
             const int par1 = step & 1;

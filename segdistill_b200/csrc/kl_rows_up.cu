@@ -304,8 +304,7 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_stats_kernel(const UpPa
             mt += et_max * p.inv_c2;          // true maximum serves: what matters is that it is used consistently)
             __syncthreads();
         }
-        // acc = sum et ((t - mt) - (s - ms)) c2  ->  sum et (t - s)
-        acc = acc * p.inv_c2 + (mt - ms) * zt;
+        // (acc = sum et (at - as) stays in the exponent domain: common.cuh, KL without cancellation)
         if (threadIdx.x == 0) {
             float4* rec = reinterpret_cast<float4*>(p.part + u * 8);
             rec[0] = make_float4(ms, mt, zs, zt);
@@ -354,17 +353,17 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_grad_kernel(const UpPar
             lt = warp_max(lt);
             const float ms = bs + ls * p.inv_c2, mt = bt + lt * p.inv_c2;     // used consistently from here on
             float zs = 0.f, zt = 0.f, acc = 0.f, dd = 0.f;
-            const float gap = mt - ms;                                         // (exact when S ~ T)
             for (int r = lane; r < nrec; r += 32) {
                 const float4 q0 = *reinterpret_cast<const float4*>(p.part + (first + r) * 8);
                 const float2 q1 = *reinterpret_cast<const float2*>(p.part + (first + r) * 8 + 4);
                 const float fs = fast_exp2((q0.x - ms) * p.c2), ft = fast_exp2((q0.y - mt) * p.c2);
+                // shift of the exponent gap from the unit's references to the row's (compensated: exact)
+                const float gx = merge_shift2(q0.x, q0.y, ms, mt) * p.c2;
+                const float ztf = q0.w * ft;
                 zs = fmaf(q0.z, fs, zs);
-                zt = fmaf(q0.w, ft, zt);
-                // a is sum et (t - s) against the unit's reference; (t - s) needs no shift, et scales like zt
-                acc = fmaf(q1.x, ft, acc);
-                // zt ft - zs fs = dd ft + zs (ft - fs), the factor difference from the small exponent gap
-                dd = fmaf(q0.z, factor_diff(fs, ft, ((q0.y - q0.x) - gap) * p.c2), fmaf(q1.y, ft, dd));
+                zt += ztf;
+                acc += fmaf(ztf, gx, q1.x * ft);                               // a2 = sum ft (a2_u + zt_u x_u)
+                dd += fmaf(q0.z, factor_diff(fs, ft, gx), q1.y * ft);          // zt ft - zs fs = dd ft + zs (ft - fs)
             }
             zs = warp_sum(zs);
             zt = warp_sum(zt);
@@ -377,7 +376,7 @@ __global__ void __launch_bounds__(kUpThreads) kl_rows_up_grad_kernel(const UpPar
                 rowstat[3] = p.coef / zt;
                 if (x.j == 0 && x.i0 == 0) {
                     // KL(p||q) = sum p (t - s)/tau - (lse_t - lse_s), once per row
-                    const float kl = kl_from_stats(p.inv_tau, gap * p.c2, zs, zt, acc, dd);
+                    const float kl = kl_from_stats(zs, zt, acc, dd);
                     p.row_kl[x.b * p.G + x.grp] = kl;
                 }
             }
@@ -615,7 +614,7 @@ __global__ void __launch_bounds__(kPxThreads) kl_pixels_up_kernel(const UpParams
                         if (ms > ref_s || mt > ref_t) {
                             const float nrs = fmaxf(ref_s, ms), nrt = fmaxf(ref_t, mt);
                             const float fs = ref_factor(ref_s, nrs, p.c2), ft = ref_factor(ref_t, nrt, p.c2);
-                            const float df = factor_diff(fs, ft, ref_gap2(ref_s, ref_t, p.c2) - ref_gap2(nrs, nrt, p.c2));
+                            const float df = factor_diff(fs, ft, merge_shift(ref_s, ref_t, nrs, nrt, p.c2));
 #pragma unroll
                             for (int q = 0; q < SB * SB; ++q) {
                                 dd[q] = fmaf(zs[q], df, dd[q] * ft);
@@ -643,14 +642,13 @@ __global__ void __launch_bounds__(kPxThreads) kl_pixels_up_kernel(const UpParams
                     }
                 }
             }
-            // the lse_t - lse_s part of the KL of my pixels (owned cells only), then the sums become the gradient
-            // factors coef / Z
+            // the ln(zt / zs) part of the KL of my pixels (owned cells only; kl_from_stats with a2 = 0), then the sums
+            // become the gradient factors coef / Z
             if (owned) {
-                const float gap = ref_gap2(ref_s, ref_t, p.c2) * kLn2;
 #pragma unroll
-                for (int q = 0; q < SB * SB; ++q) kl_acc -= gap + log1pf(dd[q] / zs[q]);
+                for (int q = 0; q < SB * SB; ++q) kl_acc += kl_from_stats(zs[q], zt[q], 0.f, dd[q]);
             }
-            float kl_a = 0.f;              // coef * sum over my pixels and the channels of p (t - s)
+            float kl_a = 0.f;              // coef * sum over my pixels and the channels of p (at - as), exponent domain
             if (in_map) {
 #pragma unroll
                 for (int q = 0; q < SB * SB; ++q) {
@@ -690,10 +688,11 @@ __global__ void __launch_bounds__(kPxThreads) kl_pixels_up_kernel(const UpParams
                             for (int kx = 0; kx < SB; ++kx) {
                                 const float vs = up_value_win<S, SB>(hs, ds_, ky0 + ky, kx);
                                 const float vt = up_value_win<S, SB>(ht, dt_, ky0 + ky, kx);
-                                const float es = fast_exp2(fmaf(vs, p.c2, -rs2));
-                                const float pt = fast_exp2(fmaf(vt, p.c2, -rt2)) * zt[ky * SB + kx];     // coef * p
+                                const float as = fmaf(vs, p.c2, -rs2), at = fmaf(vt, p.c2, -rt2);
+                                const float es = fast_exp2(as);
+                                const float pt = fast_exp2(at) * zt[ky * SB + kx];                       // coef * p
                                 const float gv = fmaf(es, zs[ky * SB + kx], -pt);
-                                kl_a = fmaf(pt, vt - vs, kl_a);
+                                kl_a = fmaf(pt, at - as, kl_a);
                                 const int f = UpW<S>::first(kx0 + kx) + 1;
                                 const float w1 = UpW<S>::w1(kx0 + kx);
                                 tr[f] = fmaf(1.f - w1, gv, tr[f]);
@@ -755,7 +754,7 @@ __global__ void __launch_bounds__(kPxThreads) kl_pixels_up_kernel(const UpParams
                     }
                 }
             }
-            if (owned) kl_acc = fmaf(kl_a, p.inv_tau * p.inv_coef, kl_acc);
+            if (owned) kl_acc = fmaf(kl_a, kLn2 * p.inv_coef, kl_acc);
         }
     }
     // ---- loss: CTA partial, the last CTA sums the partials in a fixed order

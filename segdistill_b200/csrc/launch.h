@@ -57,6 +57,8 @@ cudaError_t launch_scale_grad(void* dS, long long n, bool bf16, const float* g, 
 cudaError_t launch_scale_grad2(void* dS, long long n, bool bf16, const float* g0, const float* g1, unsigned* flag,
                                int grid, cudaStream_t stream);
 
+cudaError_t launch_log_push(const float* values, int n, float* ring, unsigned* cursor, int slots, cudaStream_t stream);
+
 // ifvd.cu
 cudaError_t launch_ifvd_sim(const IfvdParams& p, bool bf16, float loss_scale, cudaStream_t stream);
 cudaError_t launch_ifvd_class_map(const long long* target, int* cls, int B, int Ht, int Wt, int h, int w, int C,

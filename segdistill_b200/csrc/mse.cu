@@ -129,6 +129,23 @@ __global__ void __launch_bounds__(256) scale_grad2_kernel(T* __restrict__ x, lon
     for (long long i = done + gid; i < n; i += stride) E::store(x + i, E::load(x + i) * a);
 }
 
+// The step's loss scalars into slot (*cursor mod slots) of a device-resident ring, cursor += 1: one warp, capturable
+// in a CUDA graph (the slot is chosen on the device).  The ring is all-reduced once per `slots` steps instead of
+// one collective per step (segdistill_b200/dist.py: DeferredLogs).
+__global__ void log_push_kernel(const float* __restrict__ values, int n, float* __restrict__ ring,
+                                unsigned* __restrict__ cursor, unsigned slots) {
+    const unsigned c = *cursor;
+    float* dst = ring + (size_t)(c % slots) * n;
+    for (int i = threadIdx.x; i < n; i += 32) dst[i] = values[i];
+    __syncwarp();
+    if (threadIdx.x == 0) *cursor = c + 1u;
+}
+
+cudaError_t launch_log_push(const float* values, int n, float* ring, unsigned* cursor, int slots, cudaStream_t stream) {
+    log_push_kernel<<<1, 32, 0, stream>>>(values, n, ring, cursor, (unsigned)slots);
+    return cudaGetLastError();
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 cudaError_t launch_mse(const void* S, const void* T, void* dS, float* loss, float* partials, long long n, bool bf16,

@@ -80,8 +80,8 @@ __device__ __forceinline__ size_t perm_elem_offset(const RowsParams& p, const Un
     return ((size_t)x.b * p.C + ch) * p.HW + pos;
 }
 
-// softmax statistics of a piece of a row: raw-value maxima (ms, mt), sums relative to them, and
-// dd = sum (et - es) accumulated term by term (common.cuh: KL without cancellation)
+// softmax statistics of a piece of a row: raw-value maxima (ms, mt), sums relative to them, and the two sums the
+// KL is built from (common.cuh, "KL without cancellation"): a = sum et (at - as), dd = sum (et - es)
 struct RowStat {
     float ms, zs, mt, zt, a, dd;
 };
@@ -90,18 +90,18 @@ __device__ __forceinline__ RowStat rowstat_merge(const RowStat& x, const RowStat
     RowStat r;
     r.ms = fmaxf(x.ms, y.ms);
     r.mt = fmaxf(x.mt, y.mt);
+    const bool hx = x.zs > 0.f || x.zt > 0.f, hy = y.zs > 0.f || y.zt > 0.f;     // (an empty part has infinite references)
     const float fxs = x.zs > 0.f ? ref_factor(x.ms, r.ms, c2) : 0.f;
     const float fys = y.zs > 0.f ? ref_factor(y.ms, r.ms, c2) : 0.f;
     const float fxt = x.zt > 0.f ? ref_factor(x.mt, r.mt, c2) : 0.f;
     const float fyt = y.zt > 0.f ? ref_factor(y.mt, r.mt, c2) : 0.f;
+    const float gx = hx ? merge_shift(x.ms, x.mt, r.ms, r.mt, c2) : 0.f;
+    const float gy = hy ? merge_shift(y.ms, y.mt, r.ms, r.mt, c2) : 0.f;
     r.zs = __fadd_rn(__fmul_rn(x.zs, fxs), __fmul_rn(y.zs, fys));
     r.zt = __fadd_rn(__fmul_rn(x.zt, fxt), __fmul_rn(y.zt, fyt));
-    r.a = __fadd_rn(__fmul_rn(x.a, fxt), __fmul_rn(y.a, fyt));
-    // (an empty part has infinite references: its gap is NaN, factor_diff then takes the plain difference 0 - 0)
-    const float gr = ref_gap2(r.ms, r.mt, c2);
-    const float dx = fmaf(x.zs, factor_diff(fxs, fxt, ref_gap2(x.ms, x.mt, c2) - gr), __fmul_rn(x.dd, fxt));
-    const float dy = fmaf(y.zs, factor_diff(fys, fyt, ref_gap2(y.ms, y.mt, c2) - gr), __fmul_rn(y.dd, fyt));
-    r.dd = __fadd_rn(dx, dy);
+    r.a = __fadd_rn(fmaf(__fmul_rn(x.zt, fxt), gx, __fmul_rn(x.a, fxt)), fmaf(__fmul_rn(y.zt, fyt), gy, __fmul_rn(y.a, fyt)));
+    r.dd = __fadd_rn(fmaf(x.zs, factor_diff(fxs, fxt, gx), __fmul_rn(x.dd, fxt)),
+                     fmaf(y.zs, factor_diff(fys, fyt, gy), __fmul_rn(y.dd, fyt)));
     return r;
 }
 

@@ -44,3 +44,77 @@ def parse_losses(losses, group=None):
         dist.all_reduce(packed, group=group)
     host = packed.tolist()             # the single device->host synchronisation of the step
     return total, OrderedDict(zip(log_vars.keys(), host))
+
+
+def _as_vector(values):
+    """A list of 0-dim fp32 tensors as one vector: a view when they already sit next to each other in one buffer
+    (the outputs of a fused two-loss launch do), else a stacked copy."""
+    v0 = values[0]
+    try:
+        base = v0.untyped_storage().data_ptr()
+        adjacent = all(isinstance(v, torch.Tensor) and v.dim() == 0 and v.dtype == torch.float32 and
+                       v.untyped_storage().data_ptr() == base and v.storage_offset() == v0.storage_offset() + i
+                       for i, v in enumerate(values))
+    except Exception:
+        adjacent = False
+    if adjacent:
+        return v0.detach().as_strided((len(values),), (1,))
+    return torch.stack([v.detach().float().reshape(()) for v in values])
+
+
+class DeferredLogs:
+    """The loss scalars of the last ``interval`` steps, kept on the device; ONE all-reduce and ONE device->host
+    copy per ``interval`` steps instead of one collective (and one blocking ``.item()``) per log variable per step.
+
+    The reference reduces and reads every log variable on every iteration (``SD_structure.py:137-142``) although
+    its logger consumes them every 50 (``local_configs/_base_/default_runtime.py:2-7``, mmcv ``TextLoggerHook``
+    averages the buffered values of the interval).  Here a step only appends its scalars to a device-resident ring
+    - on the GPU one 32-thread launch (``sd_log_push``) that a CUDA graph captures along with the loss kernels, so
+    no NCCL kernel sits between two steps' loss kernels - and ``flush()`` returns, for every step since the last
+    flush, the same rank-averaged values ``parse_losses`` would have produced then.  The differentiable total never
+    needs a collective (every rank back-propagates its own shard's loss, as under the reference's DDP).
+    """
+
+    def __init__(self, names, interval=50, device=None, group=None):
+        self.names = list(names)
+        self.interval = int(interval)
+        self.group = group
+        self.device = torch.device('cpu') if device is None else torch.device(device)
+        self.ring = torch.zeros(self.interval, len(self.names), dtype=torch.float32, device=self.device)
+        self.cursor = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._flushed = 0                      # value of the cursor at the last flush
+
+    def push(self, values):
+        """Append one step's scalars (a tensor of ``len(names)`` fp32 values, or a list of 0-dim tensors) - no
+        synchronisation, no collective.  Inside a CUDA-graph capture this records the append into the graph."""
+        if not isinstance(values, torch.Tensor):
+            values = _as_vector(values)
+        values = values.detach()
+        if values.is_cuda:
+            from . import _cabi
+            _cabi.log_push(values.float().contiguous(), self.ring, self.cursor)
+        else:
+            slot = int(self.cursor.item()) % self.interval
+            self.ring[slot].copy_(values.float())
+            self.cursor += 1
+
+    def flush(self):
+        """All-reduce (mean over ranks) and read back the steps pushed since the last flush, oldest first: a list of
+        ``OrderedDict(name -> float)``; each gets ``'loss'`` = the sum of its entries whose name contains 'loss'
+        unless a variable of that name was pushed.  At most ``interval`` steps are retained."""
+        ring = self.ring.clone()
+        if dist.is_available() and dist.is_initialized():
+            ring /= dist.get_world_size(self.group)
+            dist.all_reduce(ring, group=self.group)
+        cur = int(self.cursor.item())          # the one synchronisation of the interval
+        host = ring.tolist()
+        n = min((cur - self._flushed) & 0x7fffffff, self.interval)
+        self._flushed = cur
+        out = []
+        for k in range(cur - n, cur):
+            row = host[k % self.interval]
+            rec = OrderedDict(zip(self.names, row))
+            if 'loss' not in rec:
+                rec['loss'] = sum(v for name, v in rec.items() if 'loss' in name)
+            out.append(rec)
+        return out

@@ -28,8 +28,17 @@ def _worker(rank, world, port, q):
         local = {k: c(s[lo:hi], t[lo:hi], gt[lo:hi], 1) for k, c in crits.items()}
         local['acc_dummy'] = torch.tensor(float(rank))
         total, logs = sdist.parse_losses(local)
+        # the deferred form: three steps appended locally, one all-reduce for all of them at the flush
+        dl = sdist.DeferredLogs(['loss_cgd', 'loss_cd', 'acc_dummy'], interval=4)
+        for step in range(3):
+            dl.push([local['loss_cgd'] * (step + 1), local['loss_cd'], local['acc_dummy']])
+        deferred = dl.flush()
+        assert dl.flush() == []
+        for step in range(6):                  # more steps than slots: the newest `interval` survive
+            dl.push([local['loss_cgd'] * (step + 1), local['loss_cd'], local['acc_dummy']])
+        wrapped = dl.flush()
         glob = {k: float(oracle.make_preset(k2)(s, t, gt, 1)) for k, k2 in (('loss_cgd', 'CGDLoss'), ('loss_cd', 'CDLoss'))}
-        q.put((rank, float(total), dict(logs), glob))
+        q.put((rank, float(total), dict(logs), glob, [dict(d) for d in deferred], [dict(d) for d in wrapped]))
     finally:
         dist.destroy_process_group()
 
@@ -56,3 +65,13 @@ def test_world2_packed_allreduce_matches_global_batch():
     assert logs0['acc_dummy'] == pytest.approx(0.5)
     assert logs0['loss'] == pytest.approx(glob['loss_cgd'] + glob['loss_cd'], rel=2e-6)
     assert res[0][1] != res[1][1]                           # the differentiable totals stay local
+    # DeferredLogs: the same rank-averaged values, one collective for the whole interval
+    d0, d1 = res[0][4], res[1][4]
+    assert d0 == d1 and len(d0) == 3
+    for step, rec in enumerate(d0):
+        assert rec['loss_cgd'] == pytest.approx((step + 1) * glob['loss_cgd'], rel=2e-6)
+        assert rec['loss_cd'] == pytest.approx(glob['loss_cd'], rel=2e-6)
+        assert rec['acc_dummy'] == pytest.approx(0.5)
+        assert rec['loss'] == pytest.approx(rec['loss_cgd'] + rec['loss_cd'], rel=1e-6)
+    w0 = res[0][5]
+    assert len(w0) == 4 and [round(r['loss_cgd'] / glob['loss_cgd']) for r in w0] == [3, 4, 5, 6]
