@@ -251,7 +251,25 @@ def kl_rows(x_student, x_teacher, group=1, tau=1.0, alpha=1.0, perm: Optional[to
     return out[0], ds, row_kl, (out[1] if mse_weight != 0 else None)
 
 
-_multi_arrays = {}
+_multi_calls = {}
+
+
+class _MultiCall:
+    """Everything of a two-loss launch that does not change from step to step (ctypes arrays, sizes, dtype code)."""
+    __slots__ = ('n', 'B', 'C', 'HW', 'code', 'g_arr', 't_arr', 'a_arr', 'l_arr', 'ws_bytes', 'fn')
+
+    def __init__(self, lib, shape, dtype, groups, taus, alphas):
+        c = ctypes
+        self.n = n = len(groups)
+        self.B, self.C = shape[0], shape[1]
+        self.HW = math.prod(shape[2:])
+        self.code = SD_F32 if dtype == torch.float32 else SD_BF16
+        self.g_arr = (c.c_int * n)(*[int(g) for g in groups])
+        self.t_arr = (c.c_float * n)(*[float(v) for v in taus])
+        self.a_arr = (c.c_float * n)(*[float(v) for v in alphas])
+        self.l_arr = (c.c_void_p * n)()
+        self.ws_bytes = lib.sd_kl_rows_workspace_bytes(self.B, self.C, self.HW, min(int(g) for g in groups))
+        self.fn = lib.sd_kl_rows_multi_fwd_bwd
 
 
 def kl_rows_multi(x_student, x_teacher, groups, taus, alphas, grad_outputs=None, run_if=None, ds=None,
@@ -260,35 +278,34 @@ def kl_rows_multi(x_student, x_teacher, groups, taus, alphas, grad_outputs=None,
 
     ``grad_outputs``/``run_if``/``ds`` serve the conditional backward re-run (see functional._KLRowsMulti).
     """
-    lib = load()
-    s, t, code = _prep_pair(x_student, x_teacher)
-    n = len(groups)
-    B, C = s.shape[0], s.shape[1]
-    HW = math.prod(s.shape[2:])
+    s, t = x_student, x_teacher
+    if (s.dtype is not torch.float32 and s.dtype is not torch.bfloat16) or t.dtype is not s.dtype or s.shape != t.shape \
+            or not s.is_cuda or t.device != s.device or not s.is_contiguous() or not t.is_contiguous():
+        s, t, _ = _prep_pair(x_student, x_teacher)          # conversions, checks with messages
+    else:
+        s, t = s.detach(), t.detach()
+    key = (s.shape, s.dtype, groups, taus, alphas) if type(groups) is tuple else (s.shape, s.dtype, tuple(groups), tuple(taus), tuple(alphas))
+    call = _multi_calls.get(key)
+    if call is None:
+        call = _multi_calls[key] = _MultiCall(load(), tuple(s.shape), s.dtype, groups, taus, alphas)
     dev = s.device
-    c = ctypes
+    n = call.n
     with _on(dev):
         if ds is None:
             ds = torch.empty_like(s)
         out = torch.empty(n, dtype=torch.float32, device=dev)
-        key = (tuple(groups), tuple(taus), tuple(alphas))
-        arrs = _multi_arrays.get(key)
-        if arrs is None:
-            arrs = _multi_arrays[key] = ((c.c_int * n)(*[int(g) for g in groups]),
-                                         (c.c_float * n)(*[float(v) for v in taus]),
-                                         (c.c_float * n)(*[float(v) for v in alphas]))
-        g_arr, t_arr, a_arr = arrs
         base = out.data_ptr()
-        l_arr = (c.c_void_p * n)(*[base + 4 * k for k in range(n)])
+        for k in range(n):
+            call.l_arr[k] = base + 4 * k
         go_arr = None
         if grad_outputs is not None:
-            go_arr = (c.c_void_p * n)(*[g.data_ptr() for g in grad_outputs])
-        ws = _workspace(dev, _rows_ws_bytes(lib, B, C, HW, min(int(g) for g in groups)))
-        rc = lib.sd_kl_rows_multi_fwd_bwd(
-            s.data_ptr(), t.data_ptr(), ds.data_ptr(), n, g_arr, t_arr, a_arr, l_arr, None, go_arr,
-            run_if.data_ptr() if run_if is not None else None,
-            B, C, HW, code, 1.0, ws.data_ptr(), ws.numel(), int(algo), _stream_ptr(dev))
-        _check(rc)
+            go_arr = (ctypes.c_void_p * n)(*[g.data_ptr() for g in grad_outputs])
+        ws = _workspace(dev, call.ws_bytes)
+        rc = call.fn(s.data_ptr(), t.data_ptr(), ds.data_ptr(), n, call.g_arr, call.t_arr, call.a_arr, call.l_arr, None,
+                     go_arr, run_if.data_ptr() if run_if is not None else None,
+                     call.B, call.C, call.HW, call.code, 1.0, ws.data_ptr(), ws.numel(), int(algo), _stream_ptr(dev))
+        if rc:
+            _check(rc)
     return out, ds
 
 
@@ -482,13 +499,15 @@ def cgd_corr(x_student, x_teacher, group=10, alpha=1.0, grad_scale=1.0):
 
 def scale_grad_(ds: torch.Tensor, grad_output: torch.Tensor):
     """In place ``ds *= grad_output`` on the device; a no-op launch when grad_output == 1."""
-    lib = load()
+    lib = _lib or load()
     g = grad_output
-    if g.device != ds.device or g.dtype != torch.float32 or g.numel() != 1 or g.requires_grad:
+    if g.device != ds.device or g.dtype is not torch.float32 or g.numel() != 1 or g.requires_grad:
         g = grad_output.detach().to(device=ds.device, dtype=torch.float32).reshape(1)
     with _on(ds.device):
-        rc = lib.sd_scale_grad(ds.data_ptr(), ds.numel(), _dtype_code(ds), g.data_ptr(), _stream_ptr(ds.device))
-        _check(rc)
+        rc = lib.sd_scale_grad(ds.data_ptr(), ds.numel(), SD_F32 if ds.dtype is torch.float32 else _dtype_code(ds),
+                               g.data_ptr(), _stream_ptr(ds.device))
+        if rc:
+            _check(rc)
     return ds
 
 

@@ -10,9 +10,19 @@ The teacher never receives a gradient (reference: frozen, run under ``no_grad``,
 from __future__ import annotations
 
 import torch
-from torch.autograd.function import once_differentiable
 
 from . import _cabi
+
+
+def once_differentiable(fn):
+    """The backward of these nodes launches kernels through the C ABI: it cannot be differentiated again.  torch's
+    ``once_differentiable`` enforces that by wrapping every call (~30 us of host time per backward); here the same
+    contract is one check: a backward that is itself being recorded (``create_graph=True``) raises."""
+    def backward(ctx, *grads):
+        if torch.is_grad_enabled():
+            raise RuntimeError('segdistill_b200 losses are differentiable once (their backward is a fused kernel)')
+        return fn(ctx, *grads)
+    return backward
 
 
 def _keep(ctx, x_student, x_teacher, ds):

@@ -48,8 +48,71 @@ class Extractor(nn.Module):
             (self.student_features if role == 'student' else self.teacher_features)[name] = output
 
 
+class _StepRecipe:
+    """What one dispatcher step launches, decided once per (shapes, dtypes, pairing) and replayed while it stays valid.
+
+    The slow path re-derives every step what cannot change between steps of a training run: which entries share their
+    tensors and fuse into one launch, which kernel serves them, the result keys.  A recipe records that for steps
+    whose host-side decisions are static - no alpha schedule (warm-up / early decay), no channel shuffle on this step,
+    no host-side resize - so that a step is: fetch the hooked tensors, check they still look the same, one autograd
+    node per launch.  Anything else (a shuffle step, a shape change, a stateful criterion) takes the slow path, which
+    is always correct."""
+
+    def __init__(self, sig, gt_hw, ops, keys, shuffle_intervals, batch_pairs):
+        self.sig, self.gt_hw, self.ops, self.keys = sig, gt_hw, ops, keys
+        self.shuffle_intervals, self.batch_pairs = shuffle_intervals, batch_pairs
+
+    def run(self, owner, student_features, teacher_features, gt, step):
+        if owner.batch_pairs != self.batch_pairs:
+            return None
+        for interval in self.shuffle_intervals:
+            if step % interval == 0:
+                return None                       # the reference draws a channel permutation on this step
+        if (None if gt is None else tuple(gt.shape[2:])) != self.gt_hw:
+            return None
+        xs, xt = [], []
+        for s_name, t_name, shape, dtype, device in self.sig:
+            a, b = student_features[s_name], teacher_features[t_name]
+            if a.shape != shape or a.dtype != dtype or a.device != device or b.shape != shape or b.dtype != dtype:
+                return None
+            xs.append(a)
+            xt.append(b)
+        results = [None] * len(self.sig)
+        for kind, idx, fn in self.ops:
+            if kind == 'pair':
+                i, j = idx
+                if xs[i] is not xs[j] or xt[i] is not xt[j]:
+                    return None
+                results[i], results[j] = fn(xs[i], xt[i])
+            else:
+                results[idx] = fn(xs[idx], xt[idx], gt, step)
+        return dict(zip(self.keys, results))
+
+
+def _static_kld_op(crit, plan):
+    """A planned KLD call as a function of the two maps alone, or None when the plan holds per-step host work."""
+    from . import functional as SF
+    if crit.warmup_config or crit.earlydecay_config or plan['perm'] is not None or crit.algo != 'auto':
+        return None
+    kind, tau, alpha, group, up = plan['kind'], plan['tau'], plan['alpha'], plan['group'], plan.get('upscale')
+    if crit.resize_config and not up and plan['student'].shape[2:] != plan['student_in'].shape[2:]:
+        return None                               # resized on the host: stays on the slow path
+    if alpha == 0:
+        return lambda xs, xt, gt, step: SF.zero_loss(xs)
+    if up and kind == 'pixel':
+        return lambda xs, xt, gt, step: SF.kl_pixels_up_loss(xs, xt, up, tau=tau, alpha=alpha)
+    if up:
+        return lambda xs, xt, gt, step: SF.kl_rows_up_loss(xs, xt, up, group=group, tau=tau, alpha=alpha)
+    if kind == 'pixel':
+        return lambda xs, xt, gt, step: SF.kl_pixels_loss(xs, xt, tau=tau, alpha=alpha)
+    if kind == 'channel':
+        return lambda xs, xt, gt, step: SF.kl_rows_loss(xs, xt, group=group, tau=tau, alpha=alpha)
+    return None
+
+
 class DistillationLoss(nn.Module):
     batch_pairs = True      # serve two KLD entries on the same tensors with one launch when possible
+    cache_steps = True      # replay the step's launch decisions while shapes / pairing stay the same (_StepRecipe)
 
     def __init__(self, distillation):
         super().__init__()
@@ -59,12 +122,20 @@ class DistillationLoss(nn.Module):
             entry['criterion'] = build_criterion(entry['loss_name'], entry['loss_config'])
             crits.append(entry['criterion'])
         self.criteria = nn.ModuleList(crits)
+        self._recipe = None
 
     def forward(self, student_features, teacher_features, gt_semantic_seg, step, student=None, teacher=None):
         """Same results and key names as the reference loop (:87-112).  One difference in HOW: the host-side
         half of every KLD criterion (schedules, resize, shuffle draw) runs first, in entry order, so that two
         entries hooking the very same tensors (e.g. CD + CGD on the logits) can be served by one two-loss
         kernel launch - one read of the maps, one write of the summed gradient."""
+        if self.cache_steps and self._recipe is not None:
+            try:
+                out = self._recipe.run(self, student_features, teacher_features, gt_semantic_seg, step)
+            except _losses._cabi.SegDistillUnsupported:      # (a pair the library declined: the slow path splits it)
+                out, self.cache_steps = None, False
+            if out is not None:
+                return out
         out = {}
         plans, resized = {}, {}
         for i, entry in enumerate(self.distillation):
@@ -73,7 +144,7 @@ class DistillationLoss(nn.Module):
                 continue
             plans[i] = crit.plan(student_features[entry['student_layer']], teacher_features[entry['teacher_layer']],
                                  gt_semantic_seg, step, resized)
-        results, pending = {}, list(plans)
+        results, pending, pairs = {}, list(plans), []
         while pending:
             i = pending.pop(0)
             mate = next((j for j in pending if _losses.KLDLoss.can_fuse(plans[i], plans[j])), None) \
@@ -82,6 +153,7 @@ class DistillationLoss(nn.Module):
                 results[i] = _losses.KLDLoss.run(plans[i])
             else:
                 pending.remove(mate)
+                pairs.append((i, mate))
                 results[i], results[mate] = _losses.KLDLoss.run_pair(plans[i], plans[mate])
         for i, entry in enumerate(self.distillation):
             s_name, t_name = entry['student_layer'], entry['teacher_layer']
@@ -102,7 +174,43 @@ class DistillationLoss(nn.Module):
             cfg = entry['loss_config']
             info = cfg['transform_config'] if isinstance(cfg, dict) and 'transform_config' in cfg else 'other'
             out[f'loss_{s_name}<->{t_name}_{info}'] = loss
+        if self.cache_steps:
+            self._recipe = self._build_recipe(student_features, teacher_features, gt_semantic_seg, plans, pairs, list(out))
         return out
+
+    def _build_recipe(self, student_features, teacher_features, gt, plans, pairs, keys):
+        """The step just run as a _StepRecipe, or None when some entry needs per-step host work."""
+        from . import functional as SF
+        sig, ops, intervals = [], [], []
+        paired = {i for pr in pairs for i in pr}
+        for i, entry in enumerate(self.distillation):
+            s_name, t_name, crit = entry['student_layer'], entry['teacher_layer'], entry['criterion']
+            if isinstance(s_name, list) or len(keys) != len(self.distillation):
+                return None
+            x = student_features[s_name]
+            sig.append((s_name, t_name, x.shape, x.dtype, x.device))
+            if not x.is_cuda:
+                return None
+            if isinstance(crit, _losses.KLDLoss):
+                if crit.shuffle_config:
+                    intervals.append(crit.shuffle_config['interval'])
+                if i in paired:
+                    if crit.warmup_config or crit.earlydecay_config:
+                        return None
+                    continue
+                plan = dict(plans[i], student_in=x)
+                fn = _static_kld_op(crit, plan)
+                if fn is None:
+                    return None
+                ops.append(('one', i, fn))
+            else:
+                ops.append(('one', i, lambda xs, xt, gt, step, crit=crit: crit(xs, xt, gt, step)))
+        for i, j in pairs:
+            pa, pb = plans[i], plans[j]
+            args = (int(pa['group']), float(pa['tau']), float(pa['alpha']), int(pb['group']), float(pb['tau']), float(pb['alpha']))
+            ops.append(('pair', (i, j), lambda xs, xt, args=args: SF._KLRowsMulti.apply(xs, xt, *args)))
+        gt_hw = None if gt is None else tuple(gt.shape[2:])
+        return _StepRecipe(sig, gt_hw, ops, keys, intervals, self.batch_pairs)
 
 
 class ExtractorMT(nn.Module):
