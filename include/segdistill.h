@@ -191,6 +191,28 @@ SD_API int sd_mse_fwd_bwd(const void* S, const void* T, void* dS, float* loss,
                    int64_t numel, int dtype, float weight, float grad_scale,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ student head: resize + cross-entropy + accuracy */
+/*
+ * BaseDecodeHead.losses, mmseg/models/decode_heads/decode_head.py:217-237, with the default CrossEntropyLoss
+ * (mmseg/models/losses/cross_entropy_loss.py:9-32, :138-198; weight_reduce_loss, losses/utils.py:25-56) and
+ * accuracy (mmseg/models/losses/accuracy.py:4-46, top-1), plus autograd's backward, in one pass:
+ *   x = bilinear_resize(logits, scale, align_corners=False)            (never materialised; scale 1, 2, 4 or 8)
+ *   nll(b,y,x) = -log_softmax_c(x)[label] * class_weight[label] * pixel_weight     (0 where label == ignore_index)
+ *   *loss = loss_weight * sum(nll) / denominator
+ *           denominator: number of label pixels B*Hs*Ws for reduction='mean' (ignored pixels count, as in the
+ *           reference's loss.mean()), avg_factor when given, 1 for reduction='sum'
+ *   *acc  = 100 * #{argmax_c x == label} / (B*Hs*Ws)                  (may be NULL)
+ *   dlogits = grad_scale * d loss / d logits, low resolution, dtype of logits.
+ * logits (B, C, Hl, Wl) contiguous; label (B, scale*Hl, scale*Wl) int64; class_weight float[C] or NULL; pixel_weight
+ * float (B, scale*Hl, scale*Wl) or NULL.  A label outside [0, C) that is not ignore_index contributes nothing (the
+ * reference's F.cross_entropy asserts on the device).  Deterministic.
+ */
+SD_API size_t sd_ce_up_workspace_bytes(int B, int C, int Hl, int Wl, int scale);
+SD_API int sd_ce_up_fwd_bwd(const void* logits, const int64_t* label, void* dlogits, float* loss, float* acc,
+                     const float* class_weight, const float* pixel_weight, int B, int C, int Hl, int Wl, int scale,
+                     int dtype, int64_t ignore_index, float loss_weight, double denominator, float grad_scale,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ IFVDLoss similarity term */
 /*
  * mmseg/models/distillation/losses.py:218-235 (IFVDLoss without its per-pixel KL, which is sd_kl_pixels_fwd_bwd):

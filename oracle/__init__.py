@@ -17,3 +17,4 @@ from .kld_oracle import (  # noqa: F401
     kld_loss_torch, kld_closed_form_f64, mse_loss_torch, at_loss_torch,
     alpha_schedule, OracleKLD, ORACLE_PRESETS, make_preset, corr_loss_torch, ifvd_loss_torch,
 )
+from .seg_loss_oracle import decode_head_losses_torch  # noqa: F401

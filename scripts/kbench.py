@@ -101,6 +101,25 @@ def main():
         'ifvd_sim_16x150x128_bf16': (L, torch.bfloat16, lambda s, t: _cabi.ifvd_sim(s, t, cls16)),
         'ifvd_sim_16x150x128_aten': (L, torch.float32, lambda s, t: torch_ifvd_sim(s, t, cls16)),
     })
+    # the student head's supervised loss: logits at 1/4 resolution, 512x512 labels
+    lab2 = torch.randint(0, 150, (2, 512, 512), device=dev)
+    lab16 = torch.randint(0, 150, (16, 512, 512), device=dev)
+
+    def torch_seg_loss(s, lab):
+        """decode_head.py:217-237 as ATen ops under autograd - what ce_up.cu replaced"""
+        import torch.nn.functional as F
+        x = s.detach().requires_grad_(True)
+        up = F.interpolate(x, size=lab.shape[1:], mode='bilinear', align_corners=False)
+        loss = F.cross_entropy(up, lab, reduction='none', ignore_index=255).mean()
+        (up.argmax(1) == lab).float().mean()
+        loss.backward()
+
+    cases.update({
+        'ce_up4_2x150x128_f32': (S2, torch.float32, lambda s, t: _cabi.ce_up(s, lab2, 4)),
+        'ce_up4_2x150x128_aten': (S2, torch.float32, lambda s, t: torch_seg_loss(s, lab2)),
+        'ce_up4_16x150x128_f32': (L, torch.float32, lambda s, t: _cabi.ce_up(s, lab16, 4)),
+        'ce_up4_16x150x128_bf16': (L, torch.bfloat16, lambda s, t: _cabi.ce_up(s, lab16, 4)),
+    })
     only = [x for x in a.only.split(',') if x]
     for name, (shape, dtype, fn) in cases.items():
         if only and name not in only:

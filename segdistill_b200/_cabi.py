@@ -31,7 +31,7 @@ EXPORTS = (
     'sd_kl_rows_up_workspace_bytes', 'sd_kl_rows_up_fwd_bwd', 'sd_kl_pixels_up_workspace_bytes', 'sd_kl_pixels_up_fwd_bwd',
     'sd_mse_workspace_bytes', 'sd_mse_fwd_bwd', 'sd_ifvd_sim_workspace_bytes', 'sd_ifvd_sim_fwd_bwd', 'sd_ifvd_max_channels',
     'sd_ifvd_class_map', 'sd_scale_grad',
-    'sd_cgd_corr_workspace_bytes', 'sd_cgd_corr_fwd_bwd', 'sd_log_push',
+    'sd_cgd_corr_workspace_bytes', 'sd_cgd_corr_fwd_bwd', 'sd_log_push', 'sd_ce_up_workspace_bytes', 'sd_ce_up_fwd_bwd',
     'sd_launch_count', 'sd_last_kernel',
 )
 
@@ -107,6 +107,11 @@ def load():
         lib.sd_cgd_corr_workspace_bytes.argtypes = [i32, i32, i32, i32]
         lib.sd_cgd_corr_fwd_bwd.restype = i32
         lib.sd_cgd_corr_fwd_bwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp, sz, vp]
+        lib.sd_ce_up_workspace_bytes.restype = sz
+        lib.sd_ce_up_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
+        lib.sd_ce_up_fwd_bwd.restype = i32
+        lib.sd_ce_up_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, f32, c.c_double, f32,
+                                         vp, sz, vp]
         lib.sd_log_push.restype = i32
         lib.sd_log_push.argtypes = [vp, i32, vp, vp, i32, vp]
         lib.sd_launch_count.restype = c.c_uint64
@@ -521,3 +526,45 @@ def log_push(values: torch.Tensor, ring: torch.Tensor, cursor: torch.Tensor):
     with _on(values.device):
         _check(lib.sd_log_push(values.data_ptr(), n, ring.data_ptr(), cursor.data_ptr(), ring.shape[0],
                                _stream_ptr(values.device)))
+
+
+CE_SCALES = (1, 2, 4, 8)
+
+
+def ce_up(logits, label, scale, class_weight=None, pixel_weight=None, ignore_index=255, loss_weight=1.0,
+          denominator=None, grad_scale=1.0):
+    """Cross-entropy + top-1 accuracy of ``logits`` up-sampled ``scale`` x (bilinear, align_corners=False) against
+    ``label`` (B, scale*Hl, scale*Wl), without materialising the up-sampled maps.  Returns (loss, acc, dlogits)."""
+    lib = load()
+    if not logits.is_cuda or logits.dim() != 4:
+        raise SegDistillError('ce_up expects 4-D CUDA logits (no CPU fallback)')
+    x = logits.detach()
+    if x.dtype == torch.float16:
+        x = x.float()
+    x = x.contiguous()
+    code = _dtype_code(x)
+    B, C, Hl, Wl = x.shape
+    dev = x.device
+    lab = label.reshape(B, Hl * scale, Wl * scale)
+    if lab.device != dev or lab.dtype != torch.int64 or not lab.is_contiguous():
+        lab = lab.to(device=dev, dtype=torch.int64).contiguous()
+    n_pix = B * Hl * Wl * scale * scale
+    with _on(dev):
+        dx = torch.empty_like(x)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        cw = None
+        if class_weight is not None:
+            cw = torch.as_tensor(class_weight, dtype=torch.float32, device=dev).contiguous()
+            if cw.numel() != C:
+                raise SegDistillError('class_weight must have C entries')
+        pw = None
+        if pixel_weight is not None:
+            pw = pixel_weight.to(device=dev, dtype=torch.float32).reshape(B, Hl * scale, Wl * scale).contiguous()
+        ws = _workspace(dev, lib.sd_ce_up_workspace_bytes(B, C, Hl, Wl, int(scale)))
+        rc = lib.sd_ce_up_fwd_bwd(x.data_ptr(), lab.data_ptr(), dx.data_ptr(), out.data_ptr(), out[1:].data_ptr(),
+                                  cw.data_ptr() if cw is not None else None, pw.data_ptr() if pw is not None else None,
+                                  B, C, Hl, Wl, int(scale), code, int(ignore_index), float(loss_weight),
+                                  float(n_pix if denominator is None else denominator), float(grad_scale),
+                                  ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        _check(rc)
+    return out[0], out[1], dx

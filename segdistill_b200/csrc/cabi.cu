@@ -602,6 +602,51 @@ int sd_kl_pixels_up_fwd_bwd(const void* S, const void* T, void* dS, float* loss,
     return e == cudaSuccess ? SD_OK : (int)e;
 }
 
+// ============================================================================ cross-entropy behind the resize
+size_t sd_ce_up_workspace_bytes(int B, int C, int Hl, int Wl, int scale) {
+    size_t n = sd::kArenaBytes + sizeof(float) * 2 * sd::kMaxGrid;
+    if (scale == 8 && B > 0 && C > 0 && Hl > 0 && Wl > 0)       // the four window planes of the gradient, fp32
+        n += sizeof(float) * 4 * (size_t)B * C * Hl * Wl;
+    return (n + 255) & ~(size_t)255;
+}
+
+int sd_ce_up_fwd_bwd(const void* logits, const int64_t* label, void* dlogits, float* loss, float* acc,
+                     const float* class_weight, const float* pixel_weight, int B, int C, int Hl, int Wl, int scale,
+                     int dtype, int64_t ignore_index, float loss_weight, double denominator, float grad_scale,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+    if (!logits || !label || !dlogits || !loss || !workspace) return SD_ERR_NULL;
+    if (dtype != SD_F32 && dtype != SD_BF16) return SD_ERR_DTYPE;
+    if (B <= 0 || C <= 0 || Hl <= 0 || Wl <= 0) return SD_ERR_SHAPE;
+    if (!(denominator > 0.0)) return SD_ERR_VALUE;
+    if (scale != 1 && scale != 2 && scale != 4 && scale != 8) return SD_ERR_UNSUPPORTED;
+    if ((long long)B * C * Hl * Wl >= (1ll << 40) || (long long)B * Hl * Wl * scale * scale >= (1ll << 40)) return SD_ERR_SHAPE;
+    if (workspace_bytes < sd_ce_up_workspace_bytes(B, C, Hl, Wl, scale)) return SD_ERR_WORKSPACE;
+    DeviceInfo& dev = device_info();
+    if (dev.cc_major != 10) return SD_ERR_DEVICE;
+    sd::CeParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.X = logits;
+    p.label = reinterpret_cast<const long long*>(label);
+    p.class_weight = class_weight;
+    p.pix_weight = pixel_weight;
+    p.dX = dlogits;
+    p.loss = loss;
+    p.acc = acc;
+    p.B = B; p.C = C; p.Hl = Hl; p.Wl = Wl; p.scale = scale;
+    p.ignore_index = ignore_index;
+    p.gscale = (float)((double)grad_scale * (double)loss_weight / denominator);
+    p.lscale = (float)((double)loss_weight / denominator);
+    p.acc_scale = (float)(100.0 / ((double)B * Hl * Wl * scale * scale));
+    char* ws = static_cast<char*>(workspace);
+    p.ctrl = reinterpret_cast<unsigned*>(ws);
+    p.part = reinterpret_cast<float*>(ws + sd::kArenaBytes);
+    p.wpart = reinterpret_cast<float*>(ws + sd::kArenaBytes + sizeof(float) * 2 * sd::kMaxGrid);
+    cudaError_t e = sd::launch_ce_up(p, dtype == SD_BF16, dev.sms, static_cast<cudaStream_t>(stream));
+    g_launches += scale == 8 ? 2 : 1;
+    t_last_kernel = "ce_up_kernel";
+    return e == cudaSuccess ? SD_OK : (int)e;
+}
+
 // ============================================================================ IFVD similarity term
 size_t sd_ifvd_sim_workspace_bytes(int B, int C, int HW) {
     if (B <= 0 || C <= 0 || HW <= 0) return 0;

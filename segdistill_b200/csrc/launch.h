@@ -36,6 +36,9 @@ cudaError_t launch_kl_rows_cluster(const RowsParams& p, const ClusterGeom& g, bo
 cudaError_t launch_kl_rows_up(const UpParams& p, bool bf16, int sms, cudaStream_t stream);
 cudaError_t launch_kl_pixels_up(const UpParams& p, bool bf16, int sms, cudaStream_t stream);   // p.part: [kMaxGrid] CTA partials
 
+// ce_up.cu
+cudaError_t launch_ce_up(const CeParams& p, bool bf16, int sms, cudaStream_t stream);
+
 // kl_pixels.cu   (mapS/mapT point at CUtensorMap objects)
 cudaError_t launch_kl_pixels_tma(const void* mapS, const void* mapT, const PixParams& p, bool bf16, int grid,
                                  size_t smem, cudaStream_t stream);

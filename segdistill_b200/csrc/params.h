@@ -170,6 +170,25 @@ inline UpWorkspace up_workspace_layout(long long B, long long C, long long Hl, l
     return w;
 }
 
+// ---------------------------------------------------------------- cross-entropy on bilinearly up-sampled logits (ce_up.cu)
+struct CeParams {
+    const void* X;               // logits (B, C, Hl, Wl)
+    const long long* label;      // (B, scale*Hl, scale*Wl) int64
+    const float* class_weight;   // [C] or null
+    const float* pix_weight;     // (B, scale*Hl, scale*Wl) or null
+    void* dX;                    // like X
+    float* loss;
+    float* acc;                  // top-1 accuracy in percent, or null
+    int B, C, Hl, Wl, scale;
+    long long ignore_index;
+    float gscale;                // grad_scale * loss_weight / denominator
+    float lscale;                // loss_weight / denominator
+    float acc_scale;             // 100 / number of label pixels
+    float* part;                 // [2][kMaxGrid] CTA partials: weighted nll, hit count
+    float* wpart;                // scale 8: [4][B*C*Hl*Wl] gradients of the four windows of a block
+    unsigned* ctrl;
+};
+
 // ---------------------------------------------------------------- pixels (PD / AT)
 struct PixParams {
     const void* S;

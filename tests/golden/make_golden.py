@@ -227,7 +227,92 @@ def ifvd_cases(ref):
     return out
 
 
+def load_reference_seg_losses(ref_root=REF):
+    """The reference's supervised-loss modules, unmodified, loaded by path: ``mmseg/models/losses/cross_entropy_loss.py``
+    (+ its ``utils.py``) and ``accuracy.py``, and ``resize`` from ``mmseg/ops/wrappers.py``.  ``import mmseg`` needs mmcv
+    (absent), so stub packages stand in for ``mmseg``, ``mmseg.models``, ``mmseg.models.losses`` and
+    ``mmseg.models.builder`` (whose ``LOSSES.register_module()`` - an mmcv Registry in the reference - is an identity
+    decorator here)."""
+    names = ['mmseg', 'mmseg.models', 'mmseg.models.builder', 'mmseg.models.losses', 'mmseg.models.losses.utils',
+             'mmseg.models.losses.cross_entropy_loss', 'mmseg.models.losses.accuracy']
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        for pkg in names[:4]:
+            m = types.ModuleType(pkg)
+            m.__path__ = []
+            sys.modules[pkg] = m
+
+        class _Registry:
+            def register_module(self, *a, **k):
+                return lambda cls: cls
+        sys.modules['mmseg.models.builder'].LOSSES = _Registry()
+        mods = {}
+        for short in ('utils', 'cross_entropy_loss', 'accuracy'):
+            full = 'mmseg.models.losses.' + short
+            spec = importlib.util.spec_from_file_location(full, os.path.join(ref_root, 'mmseg/models/losses', short + '.py'))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[full] = mod
+            spec.loader.exec_module(mod)
+            mods[short] = mod
+        wrappers = types.ModuleType('mmseg.ops.wrappers')
+        with open(os.path.join(ref_root, 'mmseg/ops/wrappers.py')) as f:
+            exec(compile(f.read(), 'mmseg/ops/wrappers.py', 'exec'), wrappers.__dict__)
+        return mods['cross_entropy_loss'].CrossEntropyLoss, mods['accuracy'].accuracy, wrappers.resize
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+# (case, logits shape, scale, CrossEntropyLoss kwargs, call kwargs, ignore band, label kind)
+SEG_CASES = [
+    ('x4_plain',        (2, 7, 6, 8),   4, {}, {}, True),
+    ('x1_same_size',    (2, 5, 9, 7),   1, {}, {}, True),
+    ('x2_class_weight', (1, 6, 8, 8),   2, dict(class_weight=[0.5, 1.0, 2.0, 1.5, 0.25, 3.0], loss_weight=0.4), {}, True),
+    ('x8_avg_factor',   (1, 4, 5, 6),   8, {}, dict(avg_factor=777.0), True),
+    ('x4_sum',          (1, 19, 4, 4),  4, dict(reduction='sum', loss_weight=0.01), {}, False),
+    ('x2_pixel_weight', (2, 3, 6, 6),   2, {}, 'weight', True),
+]
+
+
+def seg_loss_cases():
+    """BaseDecodeHead.losses (decode_head.py:217-237) with the reference's own resize, CrossEntropyLoss and accuracy,
+    called in that order; ignore_index=255, align_corners=False (BaseDecodeHead defaults, decode_head.py:52-54)."""
+    CE, accuracy, resize = load_reference_seg_losses()
+    out = {}
+    for n, (name, shape, scale, kw, call_kw, ignore_band) in enumerate(SEG_CASES):
+        g = torch.Generator().manual_seed(300 + n)
+        b, c, h, w = shape
+        logit = (torch.randn(shape, generator=g) * 2.0).requires_grad_(True)
+        label = torch.randint(0, c, (b, 1, h * scale, w * scale), generator=g)
+        if ignore_band:
+            label[:, :, : max(1, h * scale // 5), : w * scale // 2] = 255
+        weight = None
+        if call_kw == 'weight':
+            weight = torch.rand(b, h * scale, w * scale, generator=g)
+            call_kw = {}
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            seg_logit = resize(input=logit, size=label.shape[2:], mode='bilinear', align_corners=False)    # :221-225
+            seg_label = label.squeeze(1)                                                                  # :230
+            loss = CE(**kw)(seg_logit, seg_label, weight=weight, ignore_index=255, **call_kw)            # :231-235
+            acc = accuracy(seg_logit, seg_label)                                                          # :236
+        loss.backward()
+        out[name] = dict(logit=logit.detach().numpy(), label=label.numpy(), scale=np.array(scale),
+                         loss=np.array(loss.item(), dtype=np.float64), acc=np.array(float(acc), dtype=np.float64),
+                         grad=logit.grad.numpy(), ce_kwargs=np.array(repr(kw)), call_kwargs=np.array(repr(call_kw)),
+                         weight=(weight.numpy() if weight is not None else np.zeros(0, dtype=np.float32)))
+    return out
+
+
 def main():
+    if sys.argv[1:] == ['segloss']:            # add these fixtures without rewriting the others
+        for name, rec in seg_loss_cases().items():
+            np.savez_compressed(os.path.join(HERE, f'segloss_{name}.npz'), **rec)
+            print(f'segloss_{name:18s} loss={float(rec["loss"]):.9f} acc={float(rec["acc"]):.4f}')
+        return
     ref = load_reference_losses()
     if sys.argv[1:] == ['ifvd']:               # add this fixture without rewriting the others
         np.savez_compressed(os.path.join(HERE, 'ifvd_2x5x6x8.npz'), **ifvd_cases(ref))
@@ -240,6 +325,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'smoke_cfg1.npz'), **smoke_values(ref))
     np.savez_compressed(os.path.join(HERE, 'atloss_2x6x5x8.npz'), **at_cases(ref))
     np.savez_compressed(os.path.join(HERE, 'ifvd_2x5x6x8.npz'), **ifvd_cases(ref))
+    for name, rec in seg_loss_cases().items():
+        np.savez_compressed(os.path.join(HERE, f'segloss_{name}.npz'), **rec)
     print('torch', torch.__version__, 'reference', REF)
 
 

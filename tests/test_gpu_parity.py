@@ -1041,3 +1041,87 @@ def test_streaming_kernel_next_to_a_kernel_that_occupies_the_sms():
         assert _cabi.workspace_error_flag() == 0
         assert np.isfinite(loss.item())
         _assert_close(loss.item(), ds.cpu(), *ref)
+
+
+# ------------------------------------------------------------------ f4: resize + cross-entropy + accuracy of the student head
+def _seg_oracle(x, label, **kw):
+    xr = x.clone().float().requires_grad_(True)
+    out = oracle.decode_head_losses_torch(xr, label, **kw)
+    out['loss_seg'].backward()
+    return out['loss_seg'].item(), float(out['acc_seg']), xr.grad
+
+
+@pytest.mark.parametrize('name', golden_cases('segloss_'))
+def test_seg_loss_golden_vectors(name):
+    """decode_head.py:217-237 through the fused kernel against fixtures the unmodified reference modules produced."""
+    import ast
+    rec = load_golden(name)
+    kw = ast.literal_eval(str(rec['ce_kwargs']))
+    ckw = ast.literal_eval(str(rec['call_kwargs']))
+    x = torch.from_numpy(rec['logit']).to(dev()).requires_grad_(True)
+    label = torch.from_numpy(rec['label']).to(dev())
+    weight = torch.from_numpy(rec['weight']).to(dev()) if rec['weight'].size else None
+    crit = sd.CrossEntropyLoss(**kw)
+    loss = crit(x, label, weight=weight, ignore_index=255, **ckw)
+    assert _cabi.last_kernel() == 'ce_up_kernel'
+    loss.backward()
+    torch.cuda.synchronize()
+    _assert_close(loss.item(), x.grad.cpu(), float(rec['loss']), rec['grad'])
+    assert abs(crit.last_acc.item() - float(rec['acc'])) <= 1e-3
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('shape,scale', [((2, 150, 128, 128), 4), ((2, 150, 64, 64), 8), ((1, 19, 33, 47), 2),
+                                         ((2, 171, 40, 24), 1), ((1, 2, 1, 1), 4), ((3, 5, 15, 16), 4)])
+def test_seg_loss_fused_resize_ce_accuracy(shape, scale, dtype):
+    """The training shape (SegFormer logits at 1/4 resolution, 512x512 labels, 150 classes), PSPNet's 1/8, odd sizes, a
+    single cell, more classes than the pixel kernels hold in registers - against the oracle on the fp32 upcast."""
+    g = torch.Generator().manual_seed(41)
+    b, c, h, w = shape
+    x = (torch.randn(shape, generator=g) * 3.0).to(dtype)
+    label = torch.randint(0, c, (b, 1, h * scale, w * scale), generator=g)
+    label[:, :, : max(1, h * scale // 7)] = 255
+    cw = [0.5 + (k % 7) * 0.25 for k in range(c)]
+    ref = _seg_oracle(x, label, class_weight=cw, loss_weight=0.4)
+    y = x.to(dev()).requires_grad_(True)
+    out = sd.decode_head_losses(y, label.to(dev()), sd.CrossEntropyLoss(class_weight=cw, loss_weight=0.4))
+    assert _cabi.last_kernel() == 'ce_up_kernel'
+    out['loss_seg'].backward()
+    torch.cuda.synchronize()
+    if dtype == torch.bfloat16:
+        _assert_close(out['loss_seg'].item(), y.grad.float().cpu(), ref[0], ref[2], loss_rtol=2e-5, grad_rtol=BF16_GRAD_RTOL)
+    else:
+        _assert_close(out['loss_seg'].item(), y.grad.cpu(), ref[0], ref[2])
+    # accuracy: identical up to pixels whose two largest up-sampled logits tie within rounding
+    assert abs(out['acc_seg'].item() - ref[1]) <= 100.0 * 4 / label.numel() + 1e-3
+
+
+def test_seg_loss_edge_cases():
+    """Every pixel ignored (zero loss, zero gradient, zero accuracy); reduction='sum'; avg_factor; a non-integer resize
+    (host-side F.interpolate, then the kernel at scale 1); loss scale in backward; a second backward."""
+    g = torch.Generator().manual_seed(43)
+    x = torch.randn(2, 6, 10, 12, generator=g)
+    lab = torch.randint(0, 6, (2, 1, 40, 48), generator=g)
+    allign = torch.full_like(lab, 255)
+    y = x.to(dev()).requires_grad_(True)
+    out = sd.decode_head_losses(y, allign.to(dev()))
+    out['loss_seg'].backward()
+    assert out['loss_seg'].item() == 0.0 and out['acc_seg'].item() == 0.0 and y.grad.abs().max().item() == 0.0
+    for kw, ckw in ((dict(reduction='sum'), {}), ({}, dict(avg_factor=1234.5))):
+        ref = _seg_oracle(x, lab, reduction=kw.get('reduction', 'mean'), avg_factor=ckw.get('avg_factor'))
+        y = x.to(dev()).requires_grad_(True)
+        loss = sd.CrossEntropyLoss(**kw)(y, lab.to(dev()), ignore_index=255, **ckw)
+        loss.backward()
+        _assert_close(loss.item(), y.grad.cpu(), ref[0], ref[2])
+    lab3 = torch.randint(0, 6, (2, 1, 30, 36), generator=g)            # 3x: not a fused scale
+    ref = _seg_oracle(x, lab3)
+    y = x.to(dev()).requires_grad_(True)
+    out = sd.decode_head_losses(y, lab3.to(dev()))
+    (512.0 * out['loss_seg']).backward(retain_graph=True)
+    assert (y.grad.cpu() - 512.0 * ref[2]).abs().max().item() <= GRAD_RTOL * 512.0 * ref[2].abs().max().item()
+    y.grad = None
+    out['loss_seg'].backward()
+    _assert_close(out['loss_seg'].item(), y.grad.cpu(), ref[0], ref[2])
+    assert abs(out['acc_seg'].item() - ref[1]) <= 1e-3
+    with pytest.raises(_cabi.SegDistillUnsupported):
+        sd.CrossEntropyLoss(reduction='none')(y, lab3.to(dev()))

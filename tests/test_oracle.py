@@ -153,3 +153,22 @@ def test_ifvd_matches_reference():
     loss.backward()
     assert rel_err(loss.item(), z['loss']) <= 1e-6
     np.testing.assert_allclose(s.grad.numpy(), z['grad'], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize('name', golden_cases('segloss_'))
+def test_seg_loss_oracle_matches_reference(name):
+    """decode_head.py:217-237 + cross_entropy_loss.py + accuracy.py, generated by the unmodified reference modules."""
+    import ast
+    rec = load_golden(name)
+    kw = ast.literal_eval(str(rec['ce_kwargs']))
+    ckw = ast.literal_eval(str(rec['call_kwargs']))
+    x = torch.from_numpy(rec['logit']).requires_grad_(True)
+    label = torch.from_numpy(rec['label'])
+    weight = torch.from_numpy(rec['weight']) if rec['weight'].size else None
+    out = oracle.decode_head_losses_torch(x, label, class_weight=kw.get('class_weight'), loss_weight=kw.get('loss_weight', 1.0),
+                                          reduction=kw.get('reduction', 'mean'), avg_factor=ckw.get('avg_factor'),
+                                          seg_weight=weight)
+    out['loss_seg'].backward()
+    assert rel_err(out['loss_seg'].item(), rec['loss']) <= 1e-6
+    assert abs(float(out['acc_seg']) - float(rec['acc'])) <= 1e-4
+    assert np.abs(x.grad.numpy() - rec['grad']).max() <= 1e-6 * np.abs(rec['grad']).max()
