@@ -127,6 +127,51 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// maximum over the warp, identical bits in every lane (also orders the lanes: everybody contributed)
+__device__ __forceinline__ float warp_max_uniform(float v) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// sums of 8 values over the 32 lanes in 9 shuffles (halve the values a lane carries at every step, then two
+// plain steps); lane L returns the total of v[L >> 2].  Fixed order: deterministic.
+__device__ __forceinline__ float warp_sum8_transposed(const float (&v)[8], int lane) {
+    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+    float w[4], u[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float keep = b4 ? v[j + 4] : v[j], send = b4 ? v[j] : v[j + 4];
+        w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float keep = b3 ? w[j + 2] : w[j], send = b3 ? w[j] : w[j + 2];
+        u[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const float keep = b2 ? u[1] : u[0], send = b2 ? u[0] : u[1];
+    float t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    return t;
+}
+// the same for 4 values in 6 shuffles; lane L returns the total of v[L >> 3]
+__device__ __forceinline__ float warp_sum4_transposed(const float (&v)[4], int lane) {
+    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
+    float w[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float keep = b4 ? v[j + 2] : v[j], send = b4 ? v[j] : v[j + 2];
+        w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    const float keep = b3 ? w[1] : w[0], send = b3 ? w[0] : w[1];
+    float t = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    t += __shfl_xor_sync(0xffffffffu, t, 4);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    return t;
+}
+
 // ---------------------------------------------------------------- global memory, L2-coherent access
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
     uint32_t v;

@@ -218,39 +218,48 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
         }
         const float zs = zt - dd;
 
-        // ---- warp: sums rescaled to the warp maxima
-        const float msw = warp_max(ms), mtw = warp_max(mt);
+        // ---- warp: sums rescaled to the warp maxima (redux.sync for the maxima, transposed butterflies for the sums:
+        //      the reductions were 4 of the 27 instructions per element)
+        const float msw = warp_max_uniform(ms), mtw = warp_max_uniform(mt);
         {
             const float fs = ref_factor(ms, msw, c2);
             const float ft = ref_factor(mt, mtw, c2);
             const float gx = merge_shift2(ms2, mt2, __fmul_rn(msw, c2), __fmul_rn(mtw, c2));
-            const float wzs = warp_sum(zs * fs), wzt = warp_sum(zt * ft), wa = warp_sum(fmaf(zt * ft, gx, a * ft));
-            const float wdd = warp_sum(fmaf(zs, factor_diff(fs, ft, gx), dd * ft));
-            const float wsq = MSE ? warp_sum(sq) : 0.f;
-            if (lane == 0) {
-                float* my_red = red + (par * kWarps + warp) * kRedFloats;
-                reinterpret_cast<float4*>(my_red)[0] = make_float4(msw, mtw, wzs, wzt);
-                reinterpret_cast<float4*>(my_red)[1] = make_float4(wa, wsq, wdd, 0.f);
+            const float ztf = zt * ft;
+            float* my_red = red + (par * kWarps + warp) * kRedFloats;       // ms, mt, zs, zt, a, dd, sq, -
+            if (MSE) {
+                const float v[8] = {zs * fs, ztf, fmaf(ztf, gx, a * ft), fmaf(zs, factor_diff(fs, ft, gx), dd * ft), sq, 0.f, 0.f, 0.f};
+                const float tot = warp_sum8_transposed(v, lane);
+                if ((lane & 3) == 0 && lane < 20) my_red[2 + (lane >> 2)] = tot;
+            } else {
+                const float v[4] = {zs * fs, ztf, fmaf(ztf, gx, a * ft), fmaf(zs, factor_diff(fs, ft, gx), dd * ft)};
+                const float tot = warp_sum4_transposed(v, lane);
+                if ((lane & 7) == 0) my_red[2 + (lane >> 3)] = tot;
             }
+            if (lane == 1) my_red[0] = msw;
+            if (lane == 2) my_red[1] = mtw;
         }
         __syncthreads();
 
-        // ---- CTA = row: every warp merges the 16 warp records (lanes l and l+16 mirror each other)
-        float Ms, Mt, Zs, Zt, A, DD, SQ = 0.f;
+        // ---- CTA = row: every warp merges the 16 warp records (lanes l and l+16 mirror each other); the sums only
+        //      thread 0 needs (KL, MSE) are merged by warp 0 alone
+        float Ms, Mt, Zs, Zt, A = 0.f, DD = 0.f, SQ = 0.f;
         {
             const float* q = red + (par * kWarps + (lane & 15)) * kRedFloats;
             const float4 r0 = reinterpret_cast<const float4*>(q)[0];
             const float4 r1 = reinterpret_cast<const float4*>(q)[1];
-            Ms = max16(r0.x);
-            Mt = max16(r0.y);
+            Ms = warp_max_uniform(r0.x);
+            Mt = warp_max_uniform(r0.y);
             const float fs = ref_factor(r0.x, Ms, c2);
             const float ft = ref_factor(r0.y, Mt, c2);
-            const float gx = merge_shift(r0.x, r0.y, Ms, Mt, c2);
             Zs = sum16(r0.z * fs);
             Zt = sum16(r0.w * ft);
-            A = sum16(fmaf(r0.w * ft, gx, r1.x * ft));
-            DD = sum16(fmaf(r0.z, factor_diff(fs, ft, gx), r1.z * ft));
-            if (MSE) SQ = sum16(r1.y);
+            if (warp == 0) {
+                const float gx = merge_shift(r0.x, r0.y, Ms, Mt, c2);
+                A = sum16(fmaf(r0.w * ft, gx, r1.x * ft));
+                DD = sum16(fmaf(r0.z, factor_diff(fs, ft, gx), r1.y * ft));
+                if (MSE) SQ = sum16(r1.z);
+            }
         }
         par ^= 1;
 

@@ -139,13 +139,6 @@ __device__ __forceinline__ void tmem_wait_ld(Parked& x) {
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// maximum over the warp, identical bits in every lane (also orders the lanes: everybody contributed)
-__device__ __forceinline__ float warp_max_uniform(float v) {
-    float r;
-    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
-    return r;
-}
-
 // ---------------------------------------------------------------- statistics of a part of a row
 // NL losses share the raw maxima; sums are relative to them
 // (a = sum et (at - as) and dd = sum (et - es), accumulated term by term: common.cuh, "KL without cancellation".
@@ -315,27 +308,6 @@ __device__ __forceinline__ PStat<NL> pstat_from(const float4& r0, const float4& 
         x.dd[NL - 1] = r2.y;
     }
     return x;
-}
-// sums of 8 values over the 32 lanes in 9 shuffles (halve the values a lane carries at every step, then two
-// plain steps); lane L returns the total of v[L >> 2].  Fixed order: deterministic.
-__device__ __forceinline__ float warp_sum8_transposed(const float (&v)[8], int lane) {
-    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
-    float w[4], u[2];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float keep = b4 ? v[j + 4] : v[j], send = b4 ? v[j] : v[j + 4];
-        w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const float keep = b3 ? w[j + 2] : w[j], send = b3 ? w[j] : w[j + 2];
-        u[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    const float keep = b2 ? u[1] : u[0], send = b2 ? u[0] : u[1];
-    float t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    t += __shfl_xor_sync(0xffffffffu, t, 2);
-    t += __shfl_xor_sync(0xffffffffu, t, 1);
-    return t;
 }
 // a_unit: 2 for loss 0 of a launch with R == 2 (its a is kept in units of the loss-1 exponent), else 1
 __device__ __forceinline__ float kl_of_row(float a_unit, float zs, float zt, float a, float dd) {
@@ -818,17 +790,25 @@ __global__ void __launch_bounds__(kCThreads, 1) kl_rows_cluster_kernel(const Row
                     float as[NL], at[NL], es[NL], et[NL];
                     exps_args<NL, R>(fs[i], refs2, c2, as, es);
                     exps_args<NL, R>(ft[i], reft2, c2, at, et);
-#pragma unroll
-                    for (int k = 0; k < NL; ++k) {
-                        st.zs[k] += es[k];
-                        st.zt[k] += et[k];
-                        st.a[k] = fmaf(et[k], at[k] - as[k], st.a[k]);
-                    }
                     if (NL == 2 && R == 2) {
-                        const float dk = et[K] - es[K];          // et0 - es0 = (et1 - es1)(et1 + es1)
+                        // e0 = eK^2: the sums of loss 0 straight from the loss-K exponentials (one FFMA each)
+                        const float da = at[K] - as[K], dk = et[K] - es[K];
+                        st.zs[K] += es[K];
+                        st.zt[K] += et[K];
+                        st.zs[0] = fmaf(es[K], es[K], st.zs[0]);
+                        st.zt[0] = fmaf(et[K], et[K], st.zt[0]);
+                        const float w = et[K] * da;
+                        st.a[K] += w;
+                        st.a[0] = fmaf(et[K], w, st.a[0]);
                         st.dd[K] += dk;
-                        st.dd[0] = fmaf(dk, et[K] + es[K], st.dd[0]);
+                        st.dd[0] = fmaf(dk, et[K] + es[K], st.dd[0]);      // et0 - es0 = (eK_t - eK_s)(eK_t + eK_s)
                     } else {
+#pragma unroll
+                        for (int k = 0; k < NL; ++k) {
+                            st.zs[k] += es[k];
+                            st.zt[k] += et[k];
+                            st.a[k] = fmaf(et[k], at[k] - as[k], st.a[k]);
+                        }
 #pragma unroll
                         for (int k = 0; k < NL; ++k) st.dd[k] += et[k] - es[k];
                     }
