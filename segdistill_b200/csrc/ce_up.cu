@@ -17,23 +17,29 @@
 //
 // scale 1 (labels at logit resolution) runs the same code with a one-pixel block.  fp32 arithmetic; dX has the dtype
 // of the logits.
+#include <type_traits>
+
 #include "up_common.cuh"
 #include "launch.h"
 
 namespace sd {
 
+template <int NP>
 struct CeSmem {
     float st[2][kPxCh][kPxLoad * kPxLoad];   // [stage][channel][cell]
     float planes[2][9][kPxPlane];
     float red[kPxThreads / 32];
+    // exact redo (a pixel's sum vanished against the cell's reference - neighbouring cells more than ~87 apart): one
+    // reference per pixel, fl(max_c v * log2e); only the owning thread reads its column
+    float r2[NP][kPxThreads];
 };
 
 template <typename T, int S>
-__global__ void __launch_bounds__(kPxThreads) ce_up_kernel(const CeParams p) {
+__global__ void __launch_bounds__(kPxThreads, 2) ce_up_kernel(const CeParams p) {
     constexpr int SB = S > 4 ? 4 : S;              // window side
     constexpr int NWIN = (S / SB) * (S / SB);
     constexpr int NP = SB * SB;
-    __shared__ CeSmem sm;
+    __shared__ CeSmem<NP> sm;
     const int tid = threadIdx.x;
     const int ty = tid / kPxTile, tx = tid % kPxTile;
     const int tiles_x = (p.Wl + kPxOwn - 1) / kPxOwn, tiles_y = (p.Hl + kPxOwn - 1) / kPxOwn;
@@ -151,13 +157,50 @@ __global__ void __launch_bounds__(kPxThreads) ce_up_kernel(const CeParams p) {
                 }
             }
         }
+        // ---- a pixel whose sum vanished against the cell's reference: the CTA sums again, every pixel against its own
+        // maximum over the channels (best[], already known)
+        bool bad = false;
+        if (in_map) {
+#pragma unroll
+            for (int q = 0; q < NP; ++q) bad = bad || !(zs[q] >= 1e-30f && zs[q] < 3e38f);
+        }
+        const bool exact = __syncthreads_or(bad) != 0;
+        if (exact) {
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                sm.r2[q][tid] = __fmul_rn(best[q], kLog2e);
+                zs[q] = 0.f;
+            }
+            load_chunk(0, 0);
+            for (int ck = 0; ck < n_chunks; ++ck) {
+                __syncthreads();
+                if (ck + 1 < n_chunks) load_chunk((ck + 1) * kPxCh, (ck + 1) & 1);
+                const int nch = min(kPxCh, p.C - ck * kPxCh);
+                if (in_map) {
+                    for (int ch = 0; ch < nch; ++ch) {
+                        float a[3][3], hs[3][SB], dv[2][SB];
+                        nbhd(sm.st[ck & 1][ch], a);
+                        up_hrows_win<S, SB>(a, kx0, hs);
+                        up_vdiff<SB>(hs, dv);
+#pragma unroll
+                        for (int ky = 0; ky < SB; ++ky) {
+#pragma unroll
+                            for (int kx = 0; kx < SB; ++kx) {
+                                const int q = ky * SB + kx;
+                                zs[q] += fast_exp2(fmaf(up_value_win<S, SB>(hs, dv, ky0 + ky, kx), kLog2e, -sm.r2[q][tid]));
+                            }
+                        }
+                    }
+                }
+            }
+        }
         // loss and accuracy of my pixels (owned cells only); then the per-pixel gradient factors
         const float r2 = __fmul_rn(ref, kLog2e);
         if (owned) {
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
                 // -log softmax_y = ln Z + ref - v_y = ln2 (log2 Z - (v_y log2e - ref log2e))
-                const float nll = kLn2 * (log2f(zs[q]) - fmaf(vy[q], kLog2e, -r2));
+                const float nll = kLn2 * (log2f(zs[q]) - fmaf(vy[q], kLog2e, exact ? -sm.r2[q][tid] : -r2));
                 if (wq[q] != 0.f) loss_acc = fmaf(wq[q], nll, loss_acc);
                 if (lab[q] >= 0 && vy[q] >= best[q]) hit_acc += 1.f;
             }
@@ -170,92 +213,98 @@ __global__ void __launch_bounds__(kPxThreads) ce_up_kernel(const CeParams p) {
         }
 
         // ---------------- sweep 2: per channel, window gradient -> nine contributions -> owned cells
-        __syncthreads();
-        load_chunk(0, 0);
-        int cglob = 0;
-        for (int ck = 0; ck < n_chunks; ++ck) {
+        // (two compiled copies: the cell's reference in a register, or a reference per pixel from shared memory)
+        auto sweep2 = [&](auto exact_tag) {
+            constexpr bool EXACT = decltype(exact_tag)::value;
             __syncthreads();
-            if (ck + 1 < n_chunks) load_chunk((ck + 1) * kPxCh, (ck + 1) & 1);
-            const int nch = min(kPxCh, p.C - ck * kPxCh);
-            for (int ch = 0; ch < nch; ++ch, ++cglob) {
-                float* pl = sm.planes[cglob & 1][0];
-                if (in_map) {
-                    float a[3][3], hs[3][SB], dv[2][SB];
-                    nbhd(sm.st[ck & 1][ch], a);
-                    up_hrows_win<S, SB>(a, kx0, hs);
-                    up_vdiff<SB>(hs, dv);
-                    float m[3][3];
-#pragma unroll
-                    for (int d = 0; d < 3; ++d)
-#pragma unroll
-                        for (int e = 0; e < 3; ++e) m[d][e] = 0.f;
-#pragma unroll
-                    for (int ky = 0; ky < SB; ++ky) {
-                        float tr[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-                        for (int kx = 0; kx < SB; ++kx) {
-                            const int q = ky * SB + kx;
-                            const float es = fast_exp2(fmaf(up_value_win<S, SB>(hs, dv, ky0 + ky, kx), kLog2e, -r2));
-                            const float gv = fmaf(es, zs[q], cglob == lab[q] ? -best[q] : 0.f);   // coef (softmax_c - [c == y])
-                            const int f = UpW<S>::first(kx0 + kx) + 1;
-                            const float w1 = UpW<S>::w1(kx0 + kx);
-                            tr[f] = fmaf(1.f - w1, gv, tr[f]);
-                            tr[f + 1] = fmaf(w1, gv, tr[f + 1]);
-                        }
-                        const int f = UpW<S>::first(ky0 + ky) + 1;
-                        const float w1 = UpW<S>::w1(ky0 + ky);
-#pragma unroll
-                        for (int e = 0; e < 3; ++e) {
-                            m[f][e] = fmaf(1.f - w1, tr[e], m[f][e]);
-                            m[f + 1][e] = fmaf(w1, tr[e], m[f + 1][e]);
-                        }
-                    }
-                    // taps clamped at the border of the map fall onto the cell itself
-                    if (i == 0) {
-#pragma unroll
-                        for (int e = 0; e < 3; ++e) { m[1][e] += m[0][e]; m[0][e] = 0.f; }
-                    }
-                    if (i == p.Hl - 1) {
-#pragma unroll
-                        for (int e = 0; e < 3; ++e) { m[1][e] += m[2][e]; m[2][e] = 0.f; }
-                    }
-                    if (j == 0) {
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) { m[d][1] += m[d][0]; m[d][0] = 0.f; }
-                    }
-                    if (j == p.Wl - 1) {
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) { m[d][1] += m[d][2]; m[d][2] = 0.f; }
-                    }
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        const int ry = ty + d - 1;
-                        if (ry >= 0 && ry < kPxTile) {
-#pragma unroll
-                            for (int e = 0; e < 3; ++e) pl[(d * 3 + e) * kPxPlane + ry * (kPxTile + 2) + tx + e] = m[d][e];
-                        }
-                    }
-                }
+            load_chunk(0, 0);
+            int cglob = 0;
+            for (int ck = 0; ck < n_chunks; ++ck) {
                 __syncthreads();
-                if (owned) {
-                    // plane (d, e) at my position holds what cell (i - d + 1, j - e + 1) sent here
-                    const float* q = pl + ty * (kPxTile + 2) + tx + 1;
-                    const bool okd[3] = {i + 1 < p.Hl, true, i >= 1};
-                    const bool oke[3] = {j + 1 < p.Wl, true, j >= 1};
-                    float v = 0.f;
-#pragma unroll
-                    for (int d = 0; d < 3; ++d)
-#pragma unroll
-                        for (int e = 0; e < 3; ++e) {
-                            const float x = q[(d * 3 + e) * kPxPlane];
-                            v += (okd[d] && oke[e]) ? x : 0.f;
+                if (ck + 1 < n_chunks) load_chunk((ck + 1) * kPxCh, (ck + 1) & 1);
+                const int nch = min(kPxCh, p.C - ck * kPxCh);
+                for (int ch = 0; ch < nch; ++ch, ++cglob) {
+                    float* pl = sm.planes[cglob & 1][0];
+                    if (in_map) {
+                        float a[3][3], hs[3][SB], dv[2][SB];
+                        nbhd(sm.st[ck & 1][ch], a);
+                        up_hrows_win<S, SB>(a, kx0, hs);
+                        up_vdiff<SB>(hs, dv);
+                        float m[3][3];
+    #pragma unroll
+                        for (int d = 0; d < 3; ++d)
+    #pragma unroll
+                            for (int e = 0; e < 3; ++e) m[d][e] = 0.f;
+    #pragma unroll
+                        for (int ky = 0; ky < SB; ++ky) {
+                            float tr[3] = {0.f, 0.f, 0.f};
+    #pragma unroll
+                            for (int kx = 0; kx < SB; ++kx) {
+                                const int q = ky * SB + kx;
+                                const float es = fast_exp2(fmaf(up_value_win<S, SB>(hs, dv, ky0 + ky, kx), kLog2e, EXACT ? -sm.r2[q][tid] : -r2));
+                                const float gv = fmaf(es, zs[q], cglob == lab[q] ? -best[q] : 0.f);   // coef (softmax_c - [c == y])
+                                const int f = UpW<S>::first(kx0 + kx) + 1;
+                                const float w1 = UpW<S>::w1(kx0 + kx);
+                                tr[f] = fmaf(1.f - w1, gv, tr[f]);
+                                tr[f + 1] = fmaf(w1, gv, tr[f + 1]);
+                            }
+                            const int f = UpW<S>::first(ky0 + ky) + 1;
+                            const float w1 = UpW<S>::w1(ky0 + ky);
+    #pragma unroll
+                            for (int e = 0; e < 3; ++e) {
+                                m[f][e] = fmaf(1.f - w1, tr[e], m[f][e]);
+                                m[f + 1][e] = fmaf(w1, tr[e], m[f + 1][e]);
+                            }
                         }
-                    const size_t off = (size_t)cglob * plane_elems + (size_t)i * p.Wl + j;
-                    if (NWIN > 1) p.wpart[((size_t)win * p.B + b) * p.C * plane_elems + off] = v;
-                    else up_store<T>(gD + off, v);
+                        // taps clamped at the border of the map fall onto the cell itself
+                        if (i == 0) {
+    #pragma unroll
+                            for (int e = 0; e < 3; ++e) { m[1][e] += m[0][e]; m[0][e] = 0.f; }
+                        }
+                        if (i == p.Hl - 1) {
+    #pragma unroll
+                            for (int e = 0; e < 3; ++e) { m[1][e] += m[2][e]; m[2][e] = 0.f; }
+                        }
+                        if (j == 0) {
+    #pragma unroll
+                            for (int d = 0; d < 3; ++d) { m[d][1] += m[d][0]; m[d][0] = 0.f; }
+                        }
+                        if (j == p.Wl - 1) {
+    #pragma unroll
+                            for (int d = 0; d < 3; ++d) { m[d][1] += m[d][2]; m[d][2] = 0.f; }
+                        }
+    #pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            const int ry = ty + d - 1;
+                            if (ry >= 0 && ry < kPxTile) {
+    #pragma unroll
+                                for (int e = 0; e < 3; ++e) pl[(d * 3 + e) * kPxPlane + ry * (kPxTile + 2) + tx + e] = m[d][e];
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    if (owned) {
+                        // plane (d, e) at my position holds what cell (i - d + 1, j - e + 1) sent here
+                        const float* q = pl + ty * (kPxTile + 2) + tx + 1;
+                        const bool okd[3] = {i + 1 < p.Hl, true, i >= 1};
+                        const bool oke[3] = {j + 1 < p.Wl, true, j >= 1};
+                        float v = 0.f;
+    #pragma unroll
+                        for (int d = 0; d < 3; ++d)
+    #pragma unroll
+                            for (int e = 0; e < 3; ++e) {
+                                const float x = q[(d * 3 + e) * kPxPlane];
+                                v += (okd[d] && oke[e]) ? x : 0.f;
+                            }
+                        const size_t off = (size_t)cglob * plane_elems + (size_t)i * p.Wl + j;
+                        if (NWIN > 1) p.wpart[((size_t)win * p.B + b) * p.C * plane_elems + off] = v;
+                        else up_store<T>(gD + off, v);
+                    }
                 }
             }
-        }
+        };
+        if (exact) sweep2(std::true_type{});
+        else sweep2(std::false_type{});
         }   // windows
     }
     // ---- loss and hit count: CTA partials, the last CTA sums them in a fixed order

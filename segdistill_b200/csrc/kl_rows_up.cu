@@ -22,6 +22,8 @@
 //                          twice (L2-resident the second time) + dS once.
 //
 // Deterministic (no floating-point atomics); fp32 arithmetic; dS has the dtype and the (low) resolution of S.
+#include <type_traits>
+
 #include "up_common.cuh"
 #include "launch.h"
 
@@ -432,12 +434,23 @@ struct PxSmem {
     float planes[2][9][kPxPlane];
     float red[kPxThreads / 32];
 };
+// The fast path takes one reference per CELL (the maximum of its 3 x 3 neighbourhood over the channels).  When
+// neighbouring cells differ by more than ~87 tau somewhere, a pixel far below that reference underflows: its sums come
+// out 0.  The CTA then redoes the window EXACTLY: a sweep for the maximum of every up-sampled pixel over the channels,
+// and the two sweeps again with those per-pixel references - kept in (dynamic) shared memory, [S|T][pixel][thread], so
+// that the fast path's registers are untouched.  Slower (three sweeps, two shared-memory reads per value), rare.
+template <int NP>
+struct PxRefs {
+    float r2[2][NP][kPxThreads];               // fl(max * c2): the references of the exponents, as the sweeps use them
+};
 
 template <typename T, int S>
-__global__ void __launch_bounds__(kPxThreads) kl_pixels_up_kernel(const UpParams p) {
+__global__ void __launch_bounds__(kPxThreads, 2) kl_pixels_up_kernel(const UpParams p) {
     constexpr int SB = S > 4 ? 4 : S;              // window side
     constexpr int NWIN = (S / SB) * (S / SB);
     __shared__ PxSmem sm;
+    extern __shared__ __align__(16) unsigned char px_dyn[];
+    PxRefs<SB * SB>& refs = *reinterpret_cast<PxRefs<SB * SB>*>(px_dyn);
     const int tid = threadIdx.x;
     const int ty = tid / kPxTile, tx = tid % kPxTile;
     const int tiles_x = (p.Wl + kPxOwn - 1) / kPxOwn, tiles_y = (p.Hl + kPxOwn - 1) / kPxOwn;
@@ -549,6 +562,83 @@ __global__ void __launch_bounds__(kPxThreads) kl_pixels_up_kernel(const UpParams
                     }
                 }
             }
+            // ---------------- a pixel whose sums vanished against the cell's reference (or went non-finite): redo the
+            // window with one reference per pixel (uniform over the CTA; see PxRefs)
+            bool bad = false;
+            if (in_map) {
+#pragma unroll
+                for (int q = 0; q < SB * SB; ++q) bad = bad || !(zs[q] >= 1e-30f && zs[q] < 3e38f && zt[q] >= 1e-30f && zt[q] < 3e38f);
+            }
+            const bool exact = __syncthreads_or(bad) != 0;
+            if (exact) {
+                // sweep 0: the maximum of every pixel over the channels (zs / zt hold the maxima for now)
+#pragma unroll
+                for (int q = 0; q < SB * SB; ++q) zs[q] = zt[q] = -3.0e38f;
+                load_chunk(0, 0);
+                for (int ck = 0; ck < n_chunks; ++ck) {
+                    __syncthreads();
+                    if (ck + 1 < n_chunks) load_chunk((ck + 1) * kPxCh, (ck + 1) & 1);
+                    const int nch = min(kPxCh, p.C - ck * kPxCh);
+                    if (in_map) {
+                        for (int ch = 0; ch < nch; ++ch) {
+                            float a[3][3], hs[3][SB], ht[3][SB], ds_[2][SB], dt_[2][SB];
+                            nbhd(sm.st[ck & 1][0][ch], a);
+                            up_hrows_win<S, SB>(a, kx0, hs);
+                            nbhd(sm.st[ck & 1][1][ch], a);
+                            up_hrows_win<S, SB>(a, kx0, ht);
+                            up_vdiff<SB>(hs, ds_);
+                            up_vdiff<SB>(ht, dt_);
+#pragma unroll
+                            for (int ky = 0; ky < SB; ++ky) {
+#pragma unroll
+                                for (int kx = 0; kx < SB; ++kx) {
+                                    zs[ky * SB + kx] = fmaxf(zs[ky * SB + kx], up_value_win<S, SB>(hs, ds_, ky0 + ky, kx));
+                                    zt[ky * SB + kx] = fmaxf(zt[ky * SB + kx], up_value_win<S, SB>(ht, dt_, ky0 + ky, kx));
+                                }
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < SB * SB; ++q) {
+                    refs.r2[0][q][tid] = __fmul_rn(zs[q], p.c2);
+                    refs.r2[1][q][tid] = __fmul_rn(zt[q], p.c2);
+                    zs[q] = zt[q] = dd[q] = 0.f;
+                }
+                // sweep 1 again, against the per-pixel references (only this thread reads its column of refs)
+                __syncthreads();
+                load_chunk(0, 0);
+                for (int ck = 0; ck < n_chunks; ++ck) {
+                    __syncthreads();
+                    if (ck + 1 < n_chunks) load_chunk((ck + 1) * kPxCh, (ck + 1) & 1);
+                    const int nch = min(kPxCh, p.C - ck * kPxCh);
+                    if (in_map) {
+                        for (int ch = 0; ch < nch; ++ch) {
+                            float a[3][3], hs[3][SB], ht[3][SB], ds_[2][SB], dt_[2][SB];
+                            nbhd(sm.st[ck & 1][0][ch], a);
+                            up_hrows_win<S, SB>(a, kx0, hs);
+                            nbhd(sm.st[ck & 1][1][ch], a);
+                            up_hrows_win<S, SB>(a, kx0, ht);
+                            up_vdiff<SB>(hs, ds_);
+                            up_vdiff<SB>(ht, dt_);
+#pragma unroll
+                            for (int ky = 0; ky < SB; ++ky) {
+#pragma unroll
+                                for (int kx = 0; kx < SB; ++kx) {
+                                    const int q = ky * SB + kx;
+                                    const float vs = up_value_win<S, SB>(hs, ds_, ky0 + ky, kx);
+                                    const float vt = up_value_win<S, SB>(ht, dt_, ky0 + ky, kx);
+                                    const float es = fast_exp2(fmaf(vs, p.c2, -refs.r2[0][q][tid]));
+                                    const float et = fast_exp2(fmaf(vt, p.c2, -refs.r2[1][q][tid]));
+                                    zs[q] += es;
+                                    zt[q] += et;
+                                    dd[q] += et - es;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
             // the ln(zt / zs) part of the KL of my pixels (owned cells only; kl_from_stats with a2 = 0), then the sums
             // become the gradient factors coef / Z
             if (owned) {
@@ -566,101 +656,109 @@ __global__ void __launch_bounds__(kPxThreads) kl_pixels_up_kernel(const UpParams
             const float rs2 = __fmul_rn(ref_s, p.c2), rt2 = __fmul_rn(ref_t, p.c2);
 
             // ---------------- pass 2: per channel, window gradient -> nine contributions -> owned cells
-            __syncthreads();
-            load_chunk(0, 0);
-            int cglob = 0;
-            for (int ck = 0; ck < n_chunks; ++ck) {
+            // (two compiled copies: the fast one with the cell's references in registers, the exact one reading a
+            // reference per pixel from shared memory)
+            auto pass2 = [&](auto exact_tag) {
+                constexpr bool EXACT = decltype(exact_tag)::value;
                 __syncthreads();
-                if (ck + 1 < n_chunks) load_chunk((ck + 1) * kPxCh, (ck + 1) & 1);
-                const int nch = min(kPxCh, p.C - ck * kPxCh);
-                for (int ch = 0; ch < nch; ++ch, ++cglob) {
-                    float* pl = sm.planes[cglob & 1][0];
-                    if (in_map) {
-                        float a[3][3], hs[3][SB], ht[3][SB], ds_[2][SB], dt_[2][SB];
-                        nbhd(sm.st[ck & 1][0][ch], a);
-                        up_hrows_win<S, SB>(a, kx0, hs);
-                        nbhd(sm.st[ck & 1][1][ch], a);
-                        up_hrows_win<S, SB>(a, kx0, ht);
-                        up_vdiff<SB>(hs, ds_);
-                        up_vdiff<SB>(ht, dt_);
-                        float m[3][3];
-#pragma unroll
-                        for (int d = 0; d < 3; ++d)
-#pragma unroll
-                            for (int e = 0; e < 3; ++e) m[d][e] = 0.f;
-#pragma unroll
-                        for (int ky = 0; ky < SB; ++ky) {
-                            float tr[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-                            for (int kx = 0; kx < SB; ++kx) {
-                                const float vs = up_value_win<S, SB>(hs, ds_, ky0 + ky, kx);
-                                const float vt = up_value_win<S, SB>(ht, dt_, ky0 + ky, kx);
-                                const float as = fmaf(vs, p.c2, -rs2), at = fmaf(vt, p.c2, -rt2);
-                                const float es = fast_exp2(as);
-                                const float pt = fast_exp2(at) * zt[ky * SB + kx];                       // coef * p
-                                const float gv = fmaf(es, zs[ky * SB + kx], -pt);
-                                kl_a = fmaf(pt, at - as, kl_a);
-                                const int f = UpW<S>::first(kx0 + kx) + 1;
-                                const float w1 = UpW<S>::w1(kx0 + kx);
-                                tr[f] = fmaf(1.f - w1, gv, tr[f]);
-                                tr[f + 1] = fmaf(w1, gv, tr[f + 1]);
-                            }
-                            const int f = UpW<S>::first(ky0 + ky) + 1;
-                            const float w1 = UpW<S>::w1(ky0 + ky);
-#pragma unroll
-                            for (int e = 0; e < 3; ++e) {
-                                m[f][e] = fmaf(1.f - w1, tr[e], m[f][e]);
-                                m[f + 1][e] = fmaf(w1, tr[e], m[f + 1][e]);
-                            }
-                        }
-                        // taps clamped at the border of the map fall onto the cell itself
-                        if (i == 0) {
-#pragma unroll
-                            for (int e = 0; e < 3; ++e) { m[1][e] += m[0][e]; m[0][e] = 0.f; }
-                        }
-                        if (i == p.Hl - 1) {
-#pragma unroll
-                            for (int e = 0; e < 3; ++e) { m[1][e] += m[2][e]; m[2][e] = 0.f; }
-                        }
-                        if (j == 0) {
-#pragma unroll
-                            for (int d = 0; d < 3; ++d) { m[d][1] += m[d][0]; m[d][0] = 0.f; }
-                        }
-                        if (j == p.Wl - 1) {
-#pragma unroll
-                            for (int d = 0; d < 3; ++d) { m[d][1] += m[d][2]; m[d][2] = 0.f; }
-                        }
-                        // contribution (d, e) goes to tile cell (ty + d - 1, tx + e - 1): plane (d, e), row ty + d - 1,
-                        // padded column tx + e
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) {
-                            const int ry = ty + d - 1;
-                            if (ry >= 0 && ry < kPxTile) {
-#pragma unroll
-                                for (int e = 0; e < 3; ++e) pl[(d * 3 + e) * kPxPlane + ry * (kPxTile + 2) + tx + e] = m[d][e];
-                            }
-                        }
-                    }
+                load_chunk(0, 0);
+                int cglob = 0;
+                for (int ck = 0; ck < n_chunks; ++ck) {
                     __syncthreads();
-                    if (owned) {
-                        // plane (d, e) at my position holds what cell (i - d + 1, j - e + 1) sent here
-                        const float* q = pl + ty * (kPxTile + 2) + tx + 1;
-                        const bool okd[3] = {i + 1 < p.Hl, true, i >= 1};
-                        const bool oke[3] = {j + 1 < p.Wl, true, j >= 1};
-                        float v = 0.f;
-#pragma unroll
-                        for (int d = 0; d < 3; ++d)
-#pragma unroll
-                            for (int e = 0; e < 3; ++e) {
-                                const float x = q[(d * 3 + e) * kPxPlane];
-                                v += (okd[d] && oke[e]) ? x : 0.f;
+                    if (ck + 1 < n_chunks) load_chunk((ck + 1) * kPxCh, (ck + 1) & 1);
+                    const int nch = min(kPxCh, p.C - ck * kPxCh);
+                    for (int ch = 0; ch < nch; ++ch, ++cglob) {
+                        float* pl = sm.planes[cglob & 1][0];
+                        if (in_map) {
+                            float a[3][3], hs[3][SB], ht[3][SB], ds_[2][SB], dt_[2][SB];
+                            nbhd(sm.st[ck & 1][0][ch], a);
+                            up_hrows_win<S, SB>(a, kx0, hs);
+                            nbhd(sm.st[ck & 1][1][ch], a);
+                            up_hrows_win<S, SB>(a, kx0, ht);
+                            up_vdiff<SB>(hs, ds_);
+                            up_vdiff<SB>(ht, dt_);
+                            float m[3][3];
+    #pragma unroll
+                            for (int d = 0; d < 3; ++d)
+    #pragma unroll
+                                for (int e = 0; e < 3; ++e) m[d][e] = 0.f;
+    #pragma unroll
+                            for (int ky = 0; ky < SB; ++ky) {
+                                float tr[3] = {0.f, 0.f, 0.f};
+    #pragma unroll
+                                for (int kx = 0; kx < SB; ++kx) {
+                                    const float vs = up_value_win<S, SB>(hs, ds_, ky0 + ky, kx);
+                                    const float vt = up_value_win<S, SB>(ht, dt_, ky0 + ky, kx);
+                                    const float as = fmaf(vs, p.c2, EXACT ? -refs.r2[0][ky * SB + kx][tid] : -rs2);
+                                    const float at = fmaf(vt, p.c2, EXACT ? -refs.r2[1][ky * SB + kx][tid] : -rt2);
+                                    const float es = fast_exp2(as);
+                                    const float pt = fast_exp2(at) * zt[ky * SB + kx];                       // coef * p
+                                    const float gv = fmaf(es, zs[ky * SB + kx], -pt);
+                                    kl_a = fmaf(pt, at - as, kl_a);
+                                    const int f = UpW<S>::first(kx0 + kx) + 1;
+                                    const float w1 = UpW<S>::w1(kx0 + kx);
+                                    tr[f] = fmaf(1.f - w1, gv, tr[f]);
+                                    tr[f + 1] = fmaf(w1, gv, tr[f + 1]);
+                                }
+                                const int f = UpW<S>::first(ky0 + ky) + 1;
+                                const float w1 = UpW<S>::w1(ky0 + ky);
+    #pragma unroll
+                                for (int e = 0; e < 3; ++e) {
+                                    m[f][e] = fmaf(1.f - w1, tr[e], m[f][e]);
+                                    m[f + 1][e] = fmaf(w1, tr[e], m[f + 1][e]);
+                                }
                             }
-                        const size_t off = (size_t)(ck * kPxCh + ch) * plane_elems + (size_t)i * p.Wl + j;
-                        if (NWIN > 1) p.wpart[((size_t)win * p.B + b) * p.C * plane_elems + off] = v;
-                        else up_store<T>(gD + off, v);
+                            // taps clamped at the border of the map fall onto the cell itself
+                            if (i == 0) {
+    #pragma unroll
+                                for (int e = 0; e < 3; ++e) { m[1][e] += m[0][e]; m[0][e] = 0.f; }
+                            }
+                            if (i == p.Hl - 1) {
+    #pragma unroll
+                                for (int e = 0; e < 3; ++e) { m[1][e] += m[2][e]; m[2][e] = 0.f; }
+                            }
+                            if (j == 0) {
+    #pragma unroll
+                                for (int d = 0; d < 3; ++d) { m[d][1] += m[d][0]; m[d][0] = 0.f; }
+                            }
+                            if (j == p.Wl - 1) {
+    #pragma unroll
+                                for (int d = 0; d < 3; ++d) { m[d][1] += m[d][2]; m[d][2] = 0.f; }
+                            }
+                            // contribution (d, e) goes to tile cell (ty + d - 1, tx + e - 1): plane (d, e), row ty + d - 1,
+                            // padded column tx + e
+    #pragma unroll
+                            for (int d = 0; d < 3; ++d) {
+                                const int ry = ty + d - 1;
+                                if (ry >= 0 && ry < kPxTile) {
+    #pragma unroll
+                                    for (int e = 0; e < 3; ++e) pl[(d * 3 + e) * kPxPlane + ry * (kPxTile + 2) + tx + e] = m[d][e];
+                                }
+                            }
+                        }
+                        __syncthreads();
+                        if (owned) {
+                            // plane (d, e) at my position holds what cell (i - d + 1, j - e + 1) sent here
+                            const float* q = pl + ty * (kPxTile + 2) + tx + 1;
+                            const bool okd[3] = {i + 1 < p.Hl, true, i >= 1};
+                            const bool oke[3] = {j + 1 < p.Wl, true, j >= 1};
+                            float v = 0.f;
+    #pragma unroll
+                            for (int d = 0; d < 3; ++d)
+    #pragma unroll
+                                for (int e = 0; e < 3; ++e) {
+                                    const float x = q[(d * 3 + e) * kPxPlane];
+                                    v += (okd[d] && oke[e]) ? x : 0.f;
+                                }
+                            const size_t off = (size_t)(ck * kPxCh + ch) * plane_elems + (size_t)i * p.Wl + j;
+                            if (NWIN > 1) p.wpart[((size_t)win * p.B + b) * p.C * plane_elems + off] = v;
+                            else up_store<T>(gD + off, v);
+                        }
                     }
                 }
-            }
+            };
+            if (exact) pass2(std::true_type{});
+            else pass2(std::false_type{});
             if (owned) kl_acc = fmaf(kl_a, kLn2 * p.inv_coef, kl_acc);
         }
     }
@@ -706,8 +804,17 @@ __global__ void __launch_bounds__(256) up_sum_windows_kernel(const float* __rest
 template <typename T, int S>
 static cudaError_t launch_px_up_t(const UpParams& p, int sms, cudaStream_t stream, int* grid_out) {
     auto k = kl_pixels_up_kernel<T, S>;
+    constexpr int SB = S > 4 ? 4 : S;
+    const size_t dyn = sizeof(PxRefs<SB * SB>);           // per-pixel references of the exact redo
+    static std::atomic<bool> configured[kMaxDevices];
+    const int dev = device_slot();
+    if (!configured[dev].load(std::memory_order_acquire)) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return e;
+        configured[dev].store(true, std::memory_order_release);
+    }
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kPxThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kPxThreads, dyn);
     if (occ < 1) return cudaErrorLaunchOutOfResources;
     constexpr int nwin = S > 4 ? (S / 4) * (S / 4) : 1;
     const long long units = (long long)p.B * ((p.Hl + kPxOwn - 1) / kPxOwn) * ((p.Wl + kPxOwn - 1) / kPxOwn) * nwin;
@@ -715,7 +822,7 @@ static cudaError_t launch_px_up_t(const UpParams& p, int sms, cudaStream_t strea
     if (grid > units) grid = units;
     if (grid > kMaxGrid) grid = kMaxGrid;
     if (grid_out) *grid_out = (int)grid;
-    k<<<(unsigned)grid, kPxThreads, 0, stream>>>(p);
+    k<<<(unsigned)grid, kPxThreads, dyn, stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || nwin == 1) return e;
     const long long n = (long long)p.B * p.C * p.Hl * p.Wl;

@@ -954,18 +954,51 @@ def test_fused_resize_isolated_spikes_stay_finite():
 
 
 def test_fused_resize_pixel_mode_large_logit_steps():
-    """Pixel mode keeps one reference per low-resolution cell (the maximum over channels of its 3x3 neighbourhood): steps
-    of up to ~87*tau between neighbouring cells stay inside the fp32 exponent range (documented limit)."""
-    s, t = seeded_pair((1, 6, 12, 12), seed=48)
-    s[0, 1, 5, 7] += 60.0
-    t[0, 2, 9, 2] += 50.0
-    s[0, 3, 0, 0] -= 70.0
-    for scale in (2, 4, 8):
-        hw = (12 * scale, 12 * scale)
-        ref = _oracle_run('PDLoss', {}, s, t, hw, 1)
-        got = _run(sd.PDLoss(), s, t, hw, 1)
-        assert np.isfinite(got[0]) and torch.isfinite(got[1]).all()
-        _assert_close(*got, *ref, loss_rtol=2e-5, grad_rtol=1e-4)
+    """Pixel mode keeps one reference per low-resolution cell (the maximum over the channels of its 3x3 neighbourhood).
+    Steps of more than ~87*tau between neighbouring cells would underflow the sums of the pixels far below it: the CTA
+    detects that and redoes the window with one reference per up-sampled pixel (kl_rows_up.cu: PxRefs), so the result
+    stays the oracle's whatever the step - 60, 200 (the round-1 limit was ~87) or 5000 times tau, in S, in T or both."""
+    for k, (a, b, c) in enumerate(((60.0, 50.0, -70.0), (200.0, 150.0, -220.0), (5000.0, -3000.0, 4000.0))):
+        s, t = seeded_pair((1, 6, 12, 12), seed=48 + k)
+        s[0, 1, 5, 7] += a
+        t[0, 2, 9, 2] += b
+        s[0, 3, 0, 0] += c                # a corner cell: clamped taps
+        t[0, 3, 0, 1] -= c
+        for scale in (2, 4, 8):
+            hw = (12 * scale, 12 * scale)
+            ref = _oracle_run('PDLoss', {}, s, t, hw, 1)
+            got = _run(sd.PDLoss(), s, t, hw, 1)
+            assert _cabi.last_kernel() in ('kl_pixels_up_kernel', 'scale_grad_kernel')
+            assert np.isfinite(got[0]) and torch.isfinite(got[1]).all()
+            _assert_close(*got, *ref, loss_rtol=1e-5, grad_rtol=1e-4)
+    # the same with a temperature: a KLDLoss in pixel mode, tau = 4 (steps of 50 tau and 1250 tau)
+    s, t = seeded_pair((2, 5, 10, 9), seed=52)
+    s[1, 0, 3, 3] += 200.0
+    t[0, 4, 7, 2] += 5000.0
+    kw = dict(alpha=2.0, tau=4.0, resize_config={'mode': 'bilinear', 'align_corners': False},
+              transform_config={'loss_type': 'pixel'})
+    ref = _oracle_run('KLDLoss', kw, s, t, (40, 36), 1)
+    got = _run(sd.KLDLoss(**kw), s, t, (40, 36), 1)
+    _assert_close(*got, *ref, loss_rtol=1e-5, grad_rtol=1e-4)
+
+
+def test_seg_loss_large_logit_steps_between_cells():
+    """The cross-entropy kernel has the same per-cell reference and the same exact redo (ce_up.cu)."""
+    g = torch.Generator().manual_seed(61)
+    x = torch.randn(2, 7, 9, 11, generator=g)
+    x[0, 2, 4, 5] += 300.0
+    x[1, 6, 0, 0] += 6000.0
+    x[1, 1, 8, 10] -= 900.0
+    for scale in (1, 2, 4, 8):
+        lab = torch.randint(0, 7, (2, 1, 9 * scale, 11 * scale), generator=g)
+        lab[:, :, :2] = 255
+        ref = _seg_oracle(x, lab)
+        y = x.to(dev()).requires_grad_(True)
+        out = sd.decode_head_losses(y, lab.to(dev()))
+        out['loss_seg'].backward()
+        assert np.isfinite(out['loss_seg'].item()) and torch.isfinite(y.grad).all()
+        _assert_close(out['loss_seg'].item(), y.grad.cpu(), ref[0], ref[2], loss_rtol=1e-5, grad_rtol=1e-4)
+        assert abs(out['acc_seg'].item() - ref[1]) <= 100.0 * 2 / lab.numel() + 1e-3
 
 
 # ------------------------------------------------------------------ round 2: the benchmarked launch at its own shape
