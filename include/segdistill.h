@@ -139,6 +139,22 @@ SD_API int sd_kl_rows_multi_fwd_bwd(const void* S, const void* T, void* dS, int 
                              const unsigned* run_if, int B, int C, int HW, int dtype, float grad_scale,
                              void* workspace, size_t workspace_bytes, int algo, void* stream);
 
+/*
+ * The channel-mode losses of SEVERAL (student, teacher) pairs in ONE launch: one dispatcher step over a `distillation`
+ * list with more than one layer (mmseg/models/distillation/opts.py:87-112; the reference runs its whole op chain once per
+ * entry).  Pair k: maps S[k], T[k] of shape (B[k], C[k], HW[k]), rows of groups[k] channels, temperature taus[k], weight
+ * alphas[k]; *losses[k] and dS[k] exactly as sd_kl_rows_fwd_bwd computes them for that pair alone (same dtype for all
+ * pairs; n_pairs <= 8).  grad_output: NULL or one device scalar multiplied into every gradient.  The units of all
+ * pairs form one work list for a persistent cooperative grid (two-phase streaming kernel, rows of any length, ragged
+ * groups).  SD_ERR_UNSUPPORTED when a pair's rows are not 16-byte aligned (use the per-pair entry).
+ */
+SD_API size_t sd_kl_rows_group_workspace_bytes(int n_pairs, const int* B, const int* C, const int* HW, const int* groups,
+                                        int dtype);
+SD_API int sd_kl_rows_group_fwd_bwd(int n_pairs, const void* const* S, const void* const* T, void* const* dS,
+                             float* const* losses, const int* B, const int* C, const int* HW, const int* groups,
+                             const float* taus, const float* alphas, int dtype, float grad_scale,
+                             const float* grad_output, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ pixels (PD / AT) */
 SD_API size_t sd_kl_pixels_workspace_bytes(int B, int C, int HW);
 

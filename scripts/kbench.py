@@ -120,6 +120,19 @@ def main():
         'ce_up4_16x150x128_f32': (L, torch.float32, lambda s, t: _cabi.ce_up(s, lab16, 4)),
         'ce_up4_16x150x128_bf16': (L, torch.bfloat16, lambda s, t: _cabi.ce_up(s, lab16, 4)),
     })
+    # BASELINE config 2: CGD on the four MiT-B0 stage maps, one grouped launch vs four launches
+    st_shapes = [(16, 32, 128, 128), (16, 64, 64, 64), (16, 160, 32, 32), (16, 256, 16, 16)]
+    st = [pair(sh, torch.float32) for sh in st_shapes]
+    st_bytes = sum(3 * s.numel() * 4 for s, _ in st)
+
+    def cfg2_grouped(s, t):
+        _cabi.kl_rows_group([x for x, _ in st], [y for _, y in st], (10,) * 4, (2.0,) * 4, (3.0,) * 4)
+
+    def cfg2_separate(s, t):
+        for x, y in st:
+            _cabi.kl_rows(x, y, group=10, tau=2.0, alpha=3.0)
+    cases.update({'cfg2_grouped_f32': ((1, 1, 4, 4), torch.float32, cfg2_grouped),
+                  'cfg2_separate_f32': ((1, 1, 4, 4), torch.float32, cfg2_separate)})
     only = [x for x in a.only.split(',') if x]
     for name, (shape, dtype, fn) in cases.items():
         if only and name not in only:
@@ -135,7 +148,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / a.iters * 1e3
-        nbytes = 3 * s.numel() * s.element_size()
+        nbytes = st_bytes if name.startswith('cfg2_') else 3 * s.numel() * s.element_size()
         gbs = nbytes / us / 1e3
         print(f'{name:20s} {us:9.1f} us  {gbs:8.1f} GB/s  {gbs / pk:6.3f} of measured peak   [{_cabi.last_kernel()}]',
               flush=True)

@@ -32,6 +32,7 @@ EXPORTS = (
     'sd_mse_workspace_bytes', 'sd_mse_fwd_bwd', 'sd_ifvd_sim_workspace_bytes', 'sd_ifvd_sim_fwd_bwd', 'sd_ifvd_max_channels',
     'sd_ifvd_class_map', 'sd_scale_grad',
     'sd_cgd_corr_workspace_bytes', 'sd_cgd_corr_fwd_bwd', 'sd_log_push', 'sd_ce_up_workspace_bytes', 'sd_ce_up_fwd_bwd',
+    'sd_kl_rows_group_workspace_bytes', 'sd_kl_rows_group_fwd_bwd',
     'sd_launch_count', 'sd_last_kernel',
 )
 
@@ -112,6 +113,10 @@ def load():
         lib.sd_ce_up_fwd_bwd.restype = i32
         lib.sd_ce_up_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, f32, c.c_double, f32,
                                          vp, sz, vp]
+        lib.sd_kl_rows_group_workspace_bytes.restype = sz
+        lib.sd_kl_rows_group_workspace_bytes.argtypes = [i32, vp, vp, vp, vp, i32]
+        lib.sd_kl_rows_group_fwd_bwd.restype = i32
+        lib.sd_kl_rows_group_fwd_bwd.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, vp, vp, sz, vp]
         lib.sd_log_push.restype = i32
         lib.sd_log_push.argtypes = [vp, i32, vp, vp, i32, vp]
         lib.sd_launch_count.restype = c.c_uint64
@@ -568,3 +573,60 @@ def ce_up(logits, label, scale, class_weight=None, pixel_weight=None, ignore_ind
                                   ws.data_ptr(), ws.numel(), _stream_ptr(dev))
         _check(rc)
     return out[0], out[1], dx
+
+
+MAX_GROUP_PAIRS = 8
+_group_calls = {}
+
+
+class _GroupCall:
+    """The step-invariant half of a grouped launch: shapes, group sizes, temperatures, weights as ctypes arrays."""
+    __slots__ = ('n', 'code', 'B', 'C', 'HW', 'g', 'tau', 'alpha', 'S', 'T', 'D', 'L', 'ws_bytes', 'fn')
+
+    def __init__(self, lib, shapes, dtype, groups, taus, alphas):
+        c = ctypes
+        self.n = n = len(shapes)
+        self.code = SD_F32 if dtype == torch.float32 else SD_BF16
+        self.B = (c.c_int * n)(*[int(s[0]) for s in shapes])
+        self.C = (c.c_int * n)(*[int(s[1]) for s in shapes])
+        self.HW = (c.c_int * n)(*[int(math.prod(s[2:])) for s in shapes])
+        self.g = (c.c_int * n)(*[int(v) for v in groups])
+        self.tau = (c.c_float * n)(*[float(v) for v in taus])
+        self.alpha = (c.c_float * n)(*[float(v) for v in alphas])
+        self.S, self.T, self.D, self.L = ((c.c_void_p * n)() for _ in range(4))
+        self.ws_bytes = lib.sd_kl_rows_group_workspace_bytes(n, self.B, self.C, self.HW, self.g, self.code)
+        self.fn = lib.sd_kl_rows_group_fwd_bwd
+
+
+def kl_rows_group(students, teachers, groups, taus, alphas, grad_output=None):
+    """Channel-mode softmax-KL of several (student, teacher) pairs in one launch.  Returns (losses[n], [dS_k])."""
+    lib = load()
+    n = len(students)
+    if not 1 <= n <= MAX_GROUP_PAIRS:
+        raise SegDistillUnsupported(f'a grouped launch takes 1..{MAX_GROUP_PAIRS} pairs')
+    ss, ts = [], []
+    for a, b in zip(students, teachers):
+        s, t, _ = _prep_pair(a, b)
+        ss.append(s)
+        ts.append(t)
+    dtype, dev = ss[0].dtype, ss[0].device
+    if any(s.dtype != dtype or s.device != dev for s in ss):
+        raise SegDistillUnsupported('a grouped launch needs one dtype and one device')
+    key = (tuple(tuple(s.shape) for s in ss), dtype, tuple(groups), tuple(taus), tuple(alphas))
+    call = _group_calls.get(key)
+    if call is None:
+        call = _group_calls[key] = _GroupCall(lib, key[0], dtype, groups, taus, alphas)
+    if call.ws_bytes == 0:
+        raise SegDistillUnsupported('grouped launch: a pair\'s rows are not 16-byte aligned')
+    with _on(dev):
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+        dss = [torch.empty_like(s) for s in ss]
+        base = out.data_ptr()
+        for k in range(n):
+            call.S[k], call.T[k], call.D[k], call.L[k] = ss[k].data_ptr(), ts[k].data_ptr(), dss[k].data_ptr(), base + 4 * k
+        ws = _workspace(dev, call.ws_bytes)
+        rc = call.fn(n, call.S, call.T, call.D, call.L, call.B, call.C, call.HW, call.g, call.tau, call.alpha, call.code,
+                     1.0, grad_output.data_ptr() if grad_output is not None else None, ws.data_ptr(), ws.numel(),
+                     _stream_ptr(dev))
+        _check(rc)
+    return out, dss

@@ -417,6 +417,95 @@ int sd_kl_rows_multi_fwd_bwd(const void* S, const void* T, void* dS, int n_losse
     return rows_dispatch(c);
 }
 
+// ============================================================================ rows of several pairs, one launch
+namespace {
+
+// work decomposition of one pair for the grouped kernel; false: the layout cannot take the TMA path
+bool group_seg_geometry(sd::GroupSeg& s, int B, int C, int HW, int group, int es) {
+    if (group > C) group = C;
+    const int VE = 16 / es;
+    const int cap = sd::kl_rows_group_chunk_capacity();
+    s.B = B; s.C = C; s.HW = HW;
+    s.g = group;
+    s.G = (C + group - 1) / group;
+    s.G_full = C / group;
+    s.g_last = C % group;
+    const long long row_len = (long long)group * HW;
+    if (row_len >= (1ll << 31) || ((long long)HW * es) % 16 != 0) return false;
+    s.nch_full = s.G_full > 0 ? (int)((row_len + cap - 1) / cap) : 1;
+    long long ce = s.G_full > 0 ? (row_len + s.nch_full - 1) / s.nch_full : (long long)s.g_last * HW;
+    ce = (ce + VE - 1) / VE * VE;
+    if (ce > cap) ce = cap;
+    s.chunk_elems = (int)ce;
+    s.nch_last = s.g_last ? (int)(((long long)s.g_last * HW + ce - 1) / ce) : 0;
+    s.units_per_sample = s.G_full * s.nch_full + s.nch_last;
+    return true;
+}
+
+}  // namespace
+
+size_t sd_kl_rows_group_workspace_bytes(int n_pairs, const int* B, const int* C, const int* HW, const int* groups, int dtype) {
+    if (n_pairs < 1 || n_pairs > sd::kMaxSegs || !B || !C || !HW || !groups) return 0;
+    long long total = 0;
+    for (int k = 0; k < n_pairs; ++k) {
+        if (B[k] <= 0 || C[k] <= 0 || HW[k] <= 0 || groups[k] <= 0) return 0;
+        sd::GroupSeg s;
+        if (!group_seg_geometry(s, B[k], C[k], HW[k], groups[k], elem_size(dtype))) return 0;
+        total += (long long)B[k] * s.units_per_sample;
+    }
+    return sd::group_workspace_layout(total).bytes;
+}
+
+int sd_kl_rows_group_fwd_bwd(int n_pairs, const void* const* S, const void* const* T, void* const* dS,
+                             float* const* losses, const int* B, const int* C, const int* HW, const int* groups,
+                             const float* taus, const float* alphas, int dtype, float grad_scale,
+                             const float* grad_output, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!S || !T || !dS || !losses || !B || !C || !HW || !groups || !taus || !alphas || !workspace) return SD_ERR_NULL;
+    if (n_pairs < 1 || n_pairs > sd::kMaxSegs) return SD_ERR_VALUE;
+    if (dtype != SD_F32 && dtype != SD_BF16) return SD_ERR_DTYPE;
+    DeviceInfo& dev = device_info();
+    if (dev.cc_major != 10) return SD_ERR_DEVICE;
+    sd::GroupParams gp;
+    std::memset(&gp, 0, sizeof(gp));
+    gp.nseg = n_pairs;
+    long long total = 0;
+    int max_row_units = 1;
+    const int es = elem_size(dtype);
+    for (int k = 0; k < n_pairs; ++k) {
+        if (!S[k] || !T[k] || !dS[k] || !losses[k]) return SD_ERR_NULL;
+        if (B[k] <= 0 || C[k] <= 0 || HW[k] <= 0) return SD_ERR_SHAPE;
+        if (groups[k] < 1 || !(taus[k] > 0.f)) return SD_ERR_VALUE;
+        if ((long long)B[k] * C[k] * HW[k] >= (1ll << 40)) return SD_ERR_SHAPE;
+        sd::GroupSeg& s = gp.seg[k];
+        if (!aligned16(S[k]) || !aligned16(T[k]) || !aligned16(dS[k])) return SD_ERR_UNSUPPORTED;
+        if (!group_seg_geometry(s, B[k], C[k], HW[k], groups[k], es)) return SD_ERR_UNSUPPORTED;
+        s.S = S[k]; s.T = T[k]; s.dS = dS[k];
+        s.loss = losses[k];
+        s.row_kl = nullptr;
+        const double R = (double)B[k] * s.G;
+        s.c2 = (float)(1.4426950408889634 / (double)taus[k]);
+        s.coef = (float)((double)grad_scale * (double)alphas[k] / (R * (double)taus[k]));
+        s.loss_scale = (float)((double)alphas[k] / R);
+        s.unit0 = total;
+        total += (long long)B[k] * s.units_per_sample;
+        max_row_units = std::max(max_row_units, std::max(s.nch_full, s.nch_last));
+    }
+    if (total >= (1ll << 31)) return SD_ERR_SHAPE;
+    const sd::GroupWorkspace wl = sd::group_workspace_layout(total);
+    if (workspace_bytes < wl.bytes) return SD_ERR_WORKSPACE;
+    char* ws = static_cast<char*>(workspace);
+    gp.total_units = total;
+    gp.delay = stream_delay();
+    gp.grad_out = grad_output;
+    gp.ctrl = reinterpret_cast<unsigned*>(ws + wl.off_ctrl);
+    gp.cta_part = reinterpret_cast<float*>(ws + wl.off_cta);
+    gp.pkt = reinterpret_cast<unsigned long long*>(ws + wl.off_pkt);
+    cudaError_t e = sd::launch_kl_rows_group(gp, max_row_units, dtype == SD_BF16, dev.sms, static_cast<cudaStream_t>(stream));
+    g_launches += 1;
+    t_last_kernel = "kl_rows_group_kernel";
+    return e == cudaSuccess ? SD_OK : (int)e;
+}
+
 // ============================================================================ pixels
 size_t sd_kl_pixels_workspace_bytes(int B, int C, int HW) {
     if (B <= 0 || C <= 0 || HW <= 0) return 0;

@@ -28,6 +28,10 @@ cudaError_t launch_kl_rows_pack(const RowsParams& p, bool bf16, int grid, cudaSt
 cudaError_t launch_kl_rows_stream(const RowsParams& p, bool bf16, int sms, cudaStream_t stream);
 int kl_rows_stream_chunk_capacity();
 
+// kl_rows_group.cu
+cudaError_t launch_kl_rows_group(const GroupParams& gp, int max_row_units, bool bf16, int sms, cudaStream_t stream);
+int kl_rows_group_chunk_capacity();
+
 // kl_rows_cluster.cu   (probe_only: just answer whether a cluster of g.nc CTAs can be resident)
 cudaError_t launch_kl_rows_cluster(const RowsParams& p, const ClusterGeom& g, bool bf16, int sms, cudaStream_t stream,
                                    bool probe_only);

@@ -108,6 +108,44 @@ inline RowsWorkspace rows_workspace_layout(long long B, long long C, long long H
     return w;
 }
 
+// ---------------------------------------------------------------- rows of several (student, teacher) pairs, one launch
+constexpr int kMaxSegs = 8;            // pairs per grouped launch
+struct GroupSeg {
+    const void* S;
+    const void* T;
+    void* dS;
+    float* loss;
+    float* row_kl;         // [B*G] or null
+    int B, C, HW;
+    int g, G, G_full, g_last;          // channels per row, rows per sample, complete rows, channels of the ragged last row
+    int chunk_elems, nch_full, nch_last, units_per_sample;
+    long long unit0;       // first unit of this pair in the launch's work list
+    float c2, coef, loss_scale;
+};
+struct GroupParams {
+    int nseg;
+    int delay;
+    long long total_units;
+    const float* grad_out; // device scalar d(total)/d(losses) folded into the gradient, or null (= 1)
+    unsigned* ctrl;
+    float* cta_part;       // [kMaxSegs][kMaxGrid]
+    unsigned long long* pkt;   // [total units][kPktWords]
+    GroupSeg seg[kMaxSegs];
+};
+struct GroupWorkspace {
+    size_t off_ctrl, off_cta, off_pkt, bytes;
+};
+inline GroupWorkspace group_workspace_layout(long long total_units) {
+    GroupWorkspace w;
+    size_t o = 0;
+    w.off_ctrl = o;  o += kArenaBytes;
+    w.off_cta = o;   o += sizeof(float) * kMaxSegs * kMaxGrid;
+    o = (o + 127) & ~(size_t)127;
+    w.off_pkt = o;   o += sizeof(unsigned long long) * kPktWords * (size_t)total_units;
+    w.bytes = (o + 255) & ~(size_t)255;
+    return w;
+}
+
 // ---------------------------------------------------------------- rows, cluster-resident kernel
 constexpr int kClusterMaxSize = 8;     // portable cluster size
 constexpr int kClusterMaxChunks = 6;   // 4096-element chunks of a CTA's slice (TMEM: 20 columns per chunk and thread)

@@ -153,6 +153,47 @@ class _KLRowsMulti(torch.autograd.Function):
         return (ds.view(ctx.in_shape),) + (None,) * 7
 
 
+class _KLRowsGroup(torch.autograd.Function):
+    """The channel-mode KL losses of several (student, teacher) pairs from ONE launch (a dispatcher
+    step over several layers).  ``apply(cfg, s0, t0, s1, t1, ...)`` with cfg = (groups, taus, alphas) -> one loss per
+    pair; backward hands every student the gradient the launch wrote for it, times its upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, cfg, *maps):
+        students, teachers = maps[0::2], maps[1::2]
+        losses, dss = _cabi.kl_rows_group(students, teachers, *cfg)
+        ctx.cfg = cfg
+        ctx.needs = [s.requires_grad for s in students]
+        ctx.dss = dss if any(ctx.needs) else None
+        ctx.meta = [(s.dtype, s.shape) for s in students]
+        if any(ctx.needs):
+            ctx.save_for_backward(*maps)
+        return tuple(losses[k] for k in range(len(students)))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *grads):
+        n = len(ctx.meta)
+        if not any(ctx.needs):
+            return (None,) * (1 + 2 * n)
+        dss = ctx.dss
+        ctx.dss = None
+        if dss is None:                     # a second backward through this node (retain_graph=True): rebuild
+            maps = ctx.saved_tensors
+            dss = _cabi.kl_rows_group(maps[0::2], maps[1::2], *ctx.cfg)[1]
+        out = [None]
+        for k in range(n):
+            g = None
+            if ctx.needs[k]:
+                g = _cabi.scale_grad_(dss[k], grads[k])
+                dtype, shape = ctx.meta[k]
+                if g.dtype != dtype:
+                    g = g.to(dtype)
+                g = g.view(shape)
+            out += [g, None]
+        return tuple(out)
+
+
 class _KLPixels(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_student, x_teacher, tau, alpha, at_weight, algo):
@@ -277,6 +318,13 @@ def kl_rows_pair_loss(x_student, x_teacher, group0, tau0, alpha0, group1, tau1, 
     """Two channel-mode KL losses over the same pair in one pass; returns (loss0, loss1)."""
     return _KLRowsMulti.apply(x_student, x_teacher, int(group0), float(tau0), float(alpha0),
                               int(group1), float(tau1), float(alpha1))
+
+
+def kl_rows_group_loss(pairs, groups, taus, alphas):
+    """Channel-mode KL of several (student, teacher) pairs in one launch; returns a tuple of losses, one per pair."""
+    maps = [m for pair in pairs for m in pair]
+    cfg = (tuple(int(g) for g in groups), tuple(float(v) for v in taus), tuple(float(v) for v in alphas))
+    return _KLRowsGroup.apply(cfg, *maps)
 
 
 def kl_pixels_loss(x_student, x_teacher, tau=1.0, alpha=1.0, at_weight=0.0, algo='auto'):

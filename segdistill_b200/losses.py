@@ -181,6 +181,31 @@ class KLDLoss(nn.Module):
         except _cabi.SegDistillUnsupported:
             return KLDLoss.run(pa), KLDLoss.run(pb)
 
+    @staticmethod
+    def can_group(plan):
+        """A planned call that a grouped launch (several pairs, one kernel) can take: channel mode, no shuffle on this
+        step, a non-zero weight, no resize left to fuse, default kernel selection, 16-byte aligned rows."""
+        x = plan['student']
+        if plan['kind'] != 'channel' or plan.get('upscale') or plan['perm'] is not None or plan['alpha'] == 0:
+            return False
+        if plan['algo'] != 'auto' or x.dim() != 4 or not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16):
+            return False
+        if x.shape != plan['teacher'].shape:
+            return False
+        hw = x.shape[2] * x.shape[3]
+        return (hw * x.element_size()) % 16 == 0
+
+    @staticmethod
+    def run_group(plans):
+        """Losses of several groupable plans from ONE launch; falls back to one launch per plan when the library
+        declines (SD_ERR_UNSUPPORTED)."""
+        from . import _cabi
+        try:
+            return SF.kl_rows_group_loss([(p['student'], p['teacher']) for p in plans], [p['group'] for p in plans],
+                                         [p['tau'] for p in plans], [p['alpha'] for p in plans])
+        except _cabi.SegDistillUnsupported:
+            return tuple(KLDLoss.run(p) for p in plans)
+
     def forward(self, x_student, x_teacher, gt=None, n_iter=0):
         return self.run(self.plan(x_student, x_teacher, gt, n_iter))
 

@@ -84,6 +84,9 @@ class _StepRecipe:
                 if xs[i] is not xs[j] or xt[i] is not xt[j]:
                     return None
                 results[i], results[j] = fn(xs[i], xt[i])
+            elif kind == 'group':
+                for k, loss in zip(idx, fn([(xs[k], xt[k]) for k in idx])):
+                    results[k] = loss
             else:
                 results[idx] = fn(xs[idx], xt[idx], gt, step)
         return dict(zip(self.keys, results))
@@ -113,6 +116,8 @@ def _static_kld_op(crit, plan):
 class DistillationLoss(nn.Module):
     batch_pairs = True      # serve two KLD entries on the same tensors with one launch when possible
     cache_steps = True      # replay the step's launch decisions while shapes / pairing stay the same (_StepRecipe)
+    batch_groups = True     # serve the channel-mode entries on DIFFERENT tensors with one grouped launch ...
+    group_max_elements = 32 * 1024 * 1024   # ... while they are small: above this, one tuned launch per entry wins
 
     def __init__(self, distillation):
         super().__init__()
@@ -144,17 +149,31 @@ class DistillationLoss(nn.Module):
                 continue
             plans[i] = crit.plan(student_features[entry['student_layer']], teacher_features[entry['teacher_layer']],
                                  gt_semantic_seg, step, resized)
-        results, pending, pairs = {}, list(plans), []
+        results, pending, pairs, singles = {}, list(plans), [], []
         while pending:
             i = pending.pop(0)
             mate = next((j for j in pending if _losses.KLDLoss.can_fuse(plans[i], plans[j])), None) \
                 if self.batch_pairs else None
             if mate is None:
-                results[i] = _losses.KLDLoss.run(plans[i])
+                singles.append(i)
             else:
                 pending.remove(mate)
                 pairs.append((i, mate))
                 results[i], results[mate] = _losses.KLDLoss.run_pair(plans[i], plans[mate])
+        # entries on different tensors: one grouped launch for the channel-mode ones (same dtype / device), while small
+        group = [i for i in singles if _losses.KLDLoss.can_group(plans[i])] if self.batch_groups else []
+        if group:
+            x0 = plans[group[0]]['student']
+            group = [i for i in group if plans[i]['student'].dtype == x0.dtype and plans[i]['student'].device == x0.device]
+            group = group[:_losses._cabi.MAX_GROUP_PAIRS]
+        if len(group) < 2 or sum(plans[i]['student'].numel() for i in group) > self.group_max_elements:
+            group = []
+        if group:
+            for i, loss in zip(group, _losses.KLDLoss.run_group([plans[i] for i in group])):
+                results[i] = loss
+        for i in singles:
+            if i not in results:
+                results[i] = _losses.KLDLoss.run(plans[i])
         for i, entry in enumerate(self.distillation):
             s_name, t_name = entry['student_layer'], entry['teacher_layer']
             crit = entry['criterion']
@@ -175,14 +194,15 @@ class DistillationLoss(nn.Module):
             info = cfg['transform_config'] if isinstance(cfg, dict) and 'transform_config' in cfg else 'other'
             out[f'loss_{s_name}<->{t_name}_{info}'] = loss
         if self.cache_steps:
-            self._recipe = self._build_recipe(student_features, teacher_features, gt_semantic_seg, plans, pairs, list(out))
+            self._recipe = self._build_recipe(student_features, teacher_features, gt_semantic_seg, plans, pairs, list(out),
+                                              group)
         return out
 
-    def _build_recipe(self, student_features, teacher_features, gt, plans, pairs, keys):
+    def _build_recipe(self, student_features, teacher_features, gt, plans, pairs, keys, group=()):
         """The step just run as a _StepRecipe, or None when some entry needs per-step host work."""
         from . import functional as SF
         sig, ops, intervals = [], [], []
-        paired = {i for pr in pairs for i in pr}
+        paired = {i for pr in pairs for i in pr} | set(group)
         for i, entry in enumerate(self.distillation):
             s_name, t_name, crit = entry['student_layer'], entry['teacher_layer'], entry['criterion']
             if isinstance(s_name, list) or len(keys) != len(self.distillation):
@@ -209,6 +229,13 @@ class DistillationLoss(nn.Module):
             pa, pb = plans[i], plans[j]
             args = (int(pa['group']), float(pa['tau']), float(pa['alpha']), int(pb['group']), float(pb['tau']), float(pb['alpha']))
             ops.append(('pair', (i, j), lambda xs, xt, args=args: SF._KLRowsMulti.apply(xs, xt, *args)))
+        if group:
+            gp = [plans[i] for i in group]
+            if any(crit.resize_config and p['student'].shape[2:] != student_features[self.distillation[i]['student_layer']].shape[2:]
+                   for i, p, crit in ((i, plans[i], self.distillation[i]['criterion']) for i in group)):
+                return None                           # resized on the host: stays on the slow path
+            cfg = ([p['group'] for p in gp], [p['tau'] for p in gp], [p['alpha'] for p in gp])
+            ops.append(('group', tuple(group), lambda pairs_, cfg=cfg: SF.kl_rows_group_loss(pairs_, *cfg)))
         gt_hw = None if gt is None else tuple(gt.shape[2:])
         return _StepRecipe(sig, gt_hw, ops, keys, intervals, self.batch_pairs)
 

@@ -1158,3 +1158,85 @@ def test_seg_loss_edge_cases():
     assert abs(out['acc_seg'].item() - ref[1]) <= 1e-3
     with pytest.raises(_cabi.SegDistillUnsupported):
         sd.CrossEntropyLoss(reduction='none')(y, lab3.to(dev()))
+
+
+# ------------------------------------------------------------------ f3: several (student, teacher) pairs, one launch
+CFG2_STAGES = [(32, 128, 128), (64, 64, 64), (160, 32, 32), (256, 16, 16)]     # MiT-B0 stage maps (C, H, W), SURVEY 8d
+
+
+def _stage_pairs(batch, dtype=torch.float32, seed=70):
+    return [seeded_pair((batch,) + st, seed=seed + k, dtype=dtype) for k, st in enumerate(CFG2_STAGES)]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_grouped_launch_cfg2_four_stages_b16(dtype):
+    """BASELINE config 2 at its full batch: CGD (g = 10, ragged groups: 32, 64, 256 % 10 != 0) on the four stage maps in
+    ONE launch through the C ABI, against the oracle per pair."""
+    pairs = _stage_pairs(16, dtype)
+    kw = dict(group_size=10, alpha=3, tau=2)
+    refs = [_oracle_run('CGDLoss', kw, s, t, s.shape[2:], 1) for s, t in pairs]
+    ss = [s.to(dev()) for s, _ in pairs]
+    ts = [t.to(dev()) for _, t in pairs]
+    before = _cabi.launch_count()
+    losses, dss = _cabi.kl_rows_group(ss, ts, (10,) * 4, (2.0,) * 4, (3.0,) * 4)
+    assert _cabi.launch_count() - before == 1 and _cabi.last_kernel() == 'kl_rows_group_kernel'
+    torch.cuda.synchronize()
+    assert _cabi.workspace_error_flag() == 0
+    for k in range(4):
+        if dtype == torch.bfloat16:
+            _assert_close(losses[k].item(), dss[k].float().cpu(), *refs[k], loss_rtol=2e-5, grad_rtol=BF16_GRAD_RTOL)
+        else:
+            _assert_close(losses[k].item(), dss[k].cpu(), *refs[k])
+
+
+def test_grouped_launch_mixed_settings_and_near_converged():
+    """Pairs with different group sizes, temperatures, weights and row lengths (one split over many units, one of a
+    single short unit), one of them nearly converged - each must equal its own single-pair result."""
+    shapes = [(2, 20, 128, 128), (3, 7, 24, 20), (1, 150, 32, 32), (2, 6, 16, 16)]
+    cfgs = [(10, 2.0, 3.0), (3, 4.0, 1.0), (150, 3.0, 0.5), (1, 1.0, 1.0)]
+    pairs = [seeded_pair(sh, seed=80 + k) for k, sh in enumerate(shapes)]
+    pairs[3] = _near_pair(shapes[3], seed=83, offset=0.7)
+    ss = [s.to(dev()) for s, _ in pairs]
+    ts = [t.to(dev()) for _, t in pairs]
+    losses, dss = _cabi.kl_rows_group(ss, ts, [c[0] for c in cfgs], [c[1] for c in cfgs], [c[2] for c in cfgs])
+    torch.cuda.synchronize()
+    for k, ((s, t), (g, tau, alpha)) in enumerate(zip(pairs, cfgs)):
+        f64_loss, f64_grad, _ = oracle.kld_closed_form_f64(s.numpy(), t.numpy(), 'channel', g, tau, alpha)
+        if k == 3:
+            _check_near(losses[k].item(), dss[k].cpu(), f64_loss, f64_grad)
+        else:
+            assert rel_err(losses[k].item(), f64_loss) <= LOSS_RTOL
+            f64_grad = f64_grad.reshape(s.shape)
+            assert np.abs(dss[k].double().cpu().numpy() - f64_grad).max() <= GRAD_RTOL * np.abs(f64_grad).max()
+
+
+def test_dispatcher_groups_entries_on_different_layers():
+    """Four `distillation` entries on four different layers (opts.py:87-112): one grouped launch per step, the
+    reference's result keys, correct gradients with different upstream weights, also on the cached second step."""
+    pairs = _stage_pairs(4)
+    kw = dict(group_size=10, alpha=3, tau=2)
+    refs = [_oracle_run('CGDLoss', kw, s, t, s.shape[2:], 1) for s, t in pairs]
+    cfg = [{'student_layer': f'stage{k}', 'teacher_layer': f'stage{k}', 'loss_name': 'CGDLoss', 'loss_config': dict(kw)}
+           for k in range(4)]
+    d = sd.DistillationLoss(cfg)
+    tf = {f'stage{k}': t.to(dev()) for k, (_, t) in enumerate(pairs)}
+    w = [1.0, 2.0, 0.5, 3.0]
+    for step in (1, 2, 3):                       # step 1 plans, steps 2.. replay the recipe
+        xs = [s.to(dev()).requires_grad_(True) for s, _ in pairs]
+        before = _cabi.launch_count()
+        out = d({f'stage{k}': x for k, x in enumerate(xs)}, tf, None, step, None, None)
+        assert _cabi.launch_count() - before == 1 and _cabi.last_kernel() == 'kl_rows_group_kernel'
+        assert list(out) == [f"loss_stage{k}<->stage{k}_other" for k in range(4)]
+        sum(wk * v for wk, v in zip(w, out.values())).backward()
+        torch.cuda.synchronize()
+        for k in range(4):
+            assert rel_err(list(out.values())[k].item(), refs[k][0]) <= LOSS_RTOL
+            assert (xs[k].grad.cpu() - w[k] * refs[k][1]).abs().max().item() <= GRAD_RTOL * w[k] * refs[k][1].abs().max().item()
+    # switched off: one launch per entry, same numbers
+    d.batch_groups, d._recipe = False, None
+    xs = [s.to(dev()).requires_grad_(True) for s, _ in pairs]
+    before = _cabi.launch_count()
+    out = d({f'stage{k}': x for k, x in enumerate(xs)}, tf, None, 5, None, None)
+    assert _cabi.launch_count() - before == 4
+    for k in range(4):
+        assert rel_err(list(out.values())[k].item(), refs[k][0]) <= LOSS_RTOL
