@@ -292,18 +292,24 @@ def run_ours(args, rank, local_rank, world):
             logs.push([l1, l2])                # device-side append, no collective
         return l1, l2
 
-    flushed = []
+    flushed, in_flight = [], []
 
     def flush_logs():
-        """one all-reduce + one D2H for all the steps since the last flush"""
+        """one all-reduce + one (asynchronous) D2H for all the steps since the last flush; the launch stream is ordered
+        behind the collective, the host reads the values later (collect_logs)"""
         if logs is not None:
-            flushed.extend(logs.flush())
+            in_flight.append(logs.flush_start())
+
+    def collect_logs():
+        while in_flight:
+            flushed.extend(logs.flush_finish(in_flight.pop(0)))
 
     def step(record=None):
         return compute(record)
 
     def sync_all():
         torch.cuda.synchronize()
+        collect_logs()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()

@@ -83,6 +83,7 @@ class DeferredLogs:
         self.ring = torch.zeros(self.interval, len(self.names), dtype=torch.float32, device=self.device)
         self.cursor = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._flushed = 0                      # value of the cursor at the last flush
+        self._pool = []                        # pinned landing buffers of the asynchronous flushes
 
     def push(self, values):
         """Append one step's scalars (a tensor of ``len(names)`` fp32 values, or a list of 0-dim tensors) - no
@@ -98,16 +99,35 @@ class DeferredLogs:
             self.ring[slot].copy_(values.float())
             self.cursor += 1
 
-    def flush(self):
-        """All-reduce (mean over ranks) and read back the steps pushed since the last flush, oldest first: a list of
-        ``OrderedDict(name -> float)``; each gets ``'loss'`` = the sum of its entries whose name contains 'loss'
-        unless a variable of that name was pushed.  At most ``interval`` steps are retained."""
+    def flush_start(self):
+        """Enqueue the flush without waiting for it: one all-reduce of the ring (mean over ranks), then asynchronous
+        device->host copies of the ring and of the cursor into pinned buffers.  Returns a handle for ``flush_finish``.
+        The launch stream is ordered behind the collective, so a CUDA event recorded after this call times it."""
         ring = self.ring.clone()
         if dist.is_available() and dist.is_initialized():
             ring /= dist.get_world_size(self.group)
             dist.all_reduce(ring, group=self.group)
-        cur = int(self.cursor.item())          # the one synchronisation of the interval
+        if ring.is_cuda:
+            host = self._pool.pop() if self._pool else (torch.empty(ring.shape, dtype=ring.dtype).pin_memory(),
+                                                        torch.empty(1, dtype=torch.int32).pin_memory())
+            host[0].copy_(ring, non_blocking=True)
+            host[1].copy_(self.cursor, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+            return (host[0], host[1], done)
+        return (ring, self.cursor.clone(), None)
+
+    def flush_finish(self, handle):
+        """Wait for a started flush and return, oldest first, one ``OrderedDict(name -> float)`` per step pushed since
+        the previous flush (at most ``interval``); each gets ``'loss'`` = the sum of its entries whose name contains
+        'loss' unless a variable of that name was pushed."""
+        ring, cursor, done = handle
+        if done is not None:
+            done.synchronize()             # the one synchronisation of the interval
+        cur = int(cursor.item())
         host = ring.tolist()
+        if done is not None:
+            self._pool.append((ring, cursor))  # pinned landing buffers, reused by a later flush
         n = min((cur - self._flushed) & 0x7fffffff, self.interval)
         self._flushed = cur
         out = []
@@ -118,3 +138,7 @@ class DeferredLogs:
                 rec['loss'] = sum(v for name, v in rec.items() if 'loss' in name)
             out.append(rec)
         return out
+
+    def flush(self):
+        """``flush_finish(flush_start())``: all-reduce and read back the steps pushed since the last flush."""
+        return self.flush_finish(self.flush_start())
