@@ -292,8 +292,6 @@ def kl_rows_multi(x_student, x_teacher, groups, taus, alphas, grad_outputs=None,
     if (s.dtype is not torch.float32 and s.dtype is not torch.bfloat16) or t.dtype is not s.dtype or s.shape != t.shape \
             or not s.is_cuda or t.device != s.device or not s.is_contiguous() or not t.is_contiguous():
         s, t, _ = _prep_pair(x_student, x_teacher)          # conversions, checks with messages
-    else:
-        s, t = s.detach(), t.detach()
     key = (s.shape, s.dtype, groups, taus, alphas) if type(groups) is tuple else (s.shape, s.dtype, tuple(groups), tuple(taus), tuple(alphas))
     call = _multi_calls.get(key)
     if call is None:
@@ -302,7 +300,7 @@ def kl_rows_multi(x_student, x_teacher, groups, taus, alphas, grad_outputs=None,
     n = call.n
     with _on(dev):
         if ds is None:
-            ds = torch.empty_like(s)
+            ds = torch.empty(s.shape, dtype=s.dtype, device=dev)
         out = torch.empty(n, dtype=torch.float32, device=dev)
         base = out.data_ptr()
         for k in range(n):
@@ -310,10 +308,14 @@ def kl_rows_multi(x_student, x_teacher, groups, taus, alphas, grad_outputs=None,
         go_arr = None
         if grad_outputs is not None:
             go_arr = (ctypes.c_void_p * n)(*[g.data_ptr() for g in grad_outputs])
-        ws = _workspace(dev, call.ws_bytes)
+        idx = _dev_index(dev)
+        stream = _raw_stream(idx)
+        ws = _workspaces.get((idx, stream))
+        if ws is None or ws.numel() < call.ws_bytes:
+            ws = _workspace(dev, call.ws_bytes)
         rc = call.fn(s.data_ptr(), t.data_ptr(), ds.data_ptr(), n, call.g_arr, call.t_arr, call.a_arr, call.l_arr, None,
                      go_arr, run_if.data_ptr() if run_if is not None else None,
-                     call.B, call.C, call.HW, call.code, 1.0, ws.data_ptr(), ws.numel(), int(algo), _stream_ptr(dev))
+                     call.B, call.C, call.HW, call.code, 1.0, ws.data_ptr(), ws.numel(), int(algo), stream)
         if rc:
             _check(rc)
     return out, ds

@@ -121,11 +121,11 @@ class _KLRowsMulti(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_student, x_teacher, g0, tau0, alpha0, g1, tau1, alpha1):
         algo = _cabi.ALGOS[PAIR_ALGO]
-        losses, ds = _cabi.kl_rows_multi(x_student, x_teacher, (g0, g1), (tau0, tau1), (alpha0, alpha1), algo=algo)
-        ctx.cfg = ((g0, g1), (tau0, tau1), (alpha0, alpha1))
+        ctx.cfg = cfg = ((g0, g1), (tau0, tau1), (alpha0, alpha1))
+        losses, ds = _cabi.kl_rows_multi(x_student, x_teacher, *cfg, algo=algo)
         ctx.algo = algo
         _keep(ctx, x_student, x_teacher, ds)
-        return losses[0], losses[1]
+        return losses.unbind(0)
 
     @staticmethod
     @once_differentiable
@@ -135,14 +135,15 @@ class _KLRowsMulti(torch.autograd.Function):
         ds = ctx.ds
         ctx.ds = None
         groups, taus, alphas = ctx.cfg
-        x_student, x_teacher = ctx.saved_tensors
         if ds is None:       # a second backward through this node (retain_graph=True): rebuild dS for unit weights
+            x_student, x_teacher = ctx.saved_tensors
             ds = _cabi.kl_rows_multi(x_student, x_teacher, groups, taus, alphas, algo=ctx.algo)[1]
         dev = ds.device
         if go0 is go1 or (go0.data_ptr() == go1.data_ptr() and go0.device == go1.device):
             # the two terms entered one sum: a single upstream gradient, one in-place scaling launch
             _cabi.scale_grad_(ds, go0)
         else:
+            x_student, x_teacher = ctx.saved_tensors
             go0 = go0.detach().to(device=dev, dtype=torch.float32).reshape(1)
             go1 = go1.detach().to(device=dev, dtype=torch.float32).reshape(1)
             flag = _cabi.scale_grad2_(ds, go0, go1)
