@@ -67,16 +67,18 @@ extern "C" {
 /* algo: AUTO picks a TMA-staged kernel when the layout allows it (16-byte aligned rows): the
  * register-resident single pass for rows of up to 16384 elements (several whole rows per CTA pass when they
  * are short powers of two); for longer rows and for two fused
- * losses the cluster-resident single pass (rows that fit the shared memory of 8 CTAs), else the
+ * losses the grid-resident single pass (rows of up to 64 units spread over every SM, parked in tensor
+ * memory), else the cluster-resident single pass (rows that fit 8 CTAs), else the
  * streaming two-phase kernel; the plain multi-pass kernel otherwise.  TMA = AUTO without the generic
- * fallback; STREAM / CLUSTER force that kernel (rows only; CLUSTER answers SD_ERR_UNSUPPORTED when
- * the rows do not fit). */
+ * fallback; STREAM / CLUSTER / GRID force that kernel (rows only; CLUSTER and GRID answer
+ * SD_ERR_UNSUPPORTED when the rows do not fit). */
 #define SD_ALGO_AUTO    0
 #define SD_ALGO_GENERIC 1
 #define SD_ALGO_TMA     2
 #define SD_ALGO_STREAM  3
 #define SD_ALGO_CLUSTER 4
 #define SD_ALGO_ROWS1   5   /* one row per CTA pass even where several short rows could be packed (tests) */
+#define SD_ALGO_GRID    6   /* grid-resident single pass: long rows spread over all SMs (cooperative launch) */
 
 /* argument errors */
 #define SD_OK               0
@@ -129,8 +131,8 @@ SD_API int sd_kl_rows_fwd_bwd(const void* S, const void* T, void* dS,
  *   (device scalars) or 1 when grad_outputs (or the entry) is NULL.
  *   run_if: NULL, or a device word: the launch is a no-op when it reads 0 (conditional backward
  *   re-run after sd_scale_grad2 found non-uniform upstream gradients).
- * algo: SD_ALGO_AUTO (cluster-resident kernel when the rows fit, else the streaming kernel), or
- * SD_ALGO_CLUSTER / SD_ALGO_STREAM to force one.  TMA paths only: SD_ERR_UNSUPPORTED when the layout
+ * algo: SD_ALGO_AUTO (grid- or cluster-resident kernel when the rows fit, else the streaming kernel), or
+ * SD_ALGO_GRID / SD_ALGO_CLUSTER / SD_ALGO_STREAM to force one.  TMA paths only: SD_ERR_UNSUPPORTED when the layout
  * cannot take it (call the single-loss entry per loss).
  */
 SD_API int sd_kl_rows_multi_fwd_bwd(const void* S, const void* T, void* dS, int n_losses, const int* groups,

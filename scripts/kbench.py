@@ -49,6 +49,18 @@ def main():
         'cgd10_bf16_cluster': (L, torch.bfloat16, lambda s, t: _cabi.kl_rows(s, t, group=10, tau=2.0, alpha=3.0, algo=4)),
         'cd_f32_cluster': (L, torch.float32, lambda s, t: _cabi.kl_rows(s, t, group=1, algo=4)),
         'cd_bf16_cluster': (L, torch.bfloat16, lambda s, t: _cabi.kl_rows(s, t, group=1, algo=4)),
+        'fused_f32_cluster': (L, torch.float32,
+                              lambda s, t: _cabi.kl_rows_multi(s, t, (10, 1), (2.0, 1.0), (3.0, 1.0), algo=4)),
+        'fused_bf16_cluster': (L, torch.bfloat16,
+                               lambda s, t: _cabi.kl_rows_multi(s, t, (10, 1), (2.0, 1.0), (3.0, 1.0), algo=4)),
+        'fused_f32_grid': (L, torch.float32,
+                           lambda s, t: _cabi.kl_rows_multi(s, t, (10, 1), (2.0, 1.0), (3.0, 1.0), algo=6)),
+        'fused_bf16_grid': (L, torch.bfloat16,
+                            lambda s, t: _cabi.kl_rows_multi(s, t, (10, 1), (2.0, 1.0), (3.0, 1.0), algo=6)),
+        'cgd10_f32_grid': (L, torch.float32, lambda s, t: _cabi.kl_rows(s, t, group=10, tau=2.0, alpha=3.0, algo=6)),
+        'cgd10_bf16_grid': (L, torch.bfloat16, lambda s, t: _cabi.kl_rows(s, t, group=10, tau=2.0, alpha=3.0, algo=6)),
+        'cd_f32_grid': (L, torch.float32, lambda s, t: _cabi.kl_rows(s, t, group=1, algo=6)),
+        'cd_bf16_grid': (L, torch.bfloat16, lambda s, t: _cabi.kl_rows(s, t, group=1, algo=6)),
         'cgd10_f32_stream': (L, torch.float32, lambda s, t: _cabi.kl_rows(s, t, group=10, tau=2.0, alpha=3.0, algo=3)),
         'fused_f32_stream': (L, torch.float32,
                              lambda s, t: _cabi.kl_rows_multi(s, t, (10, 1), (2.0, 1.0), (3.0, 1.0), algo=3)),

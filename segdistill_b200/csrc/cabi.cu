@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <utility>
 
@@ -144,6 +145,50 @@ int stream_delay() {
     return d;
 }
 
+// grid-resident kernel: chunks per unit (SEGDISTILL_GRID_UNIT overrides; tuning knob) and whether AUTO prefers it to
+// the cluster-resident kernel (SEGDISTILL_PREFER_GRID=0: tuning / A-B knob)
+int grid_unit_chunks() {
+    static int n = 0;
+    if (n == 0) {
+        const char* e = std::getenv("SEGDISTILL_GRID_UNIT");
+        n = e ? std::atoi(e) : 4;
+        if (n < 1) n = 1;
+        if (n > sd::kGridUnitMaxChunks) n = sd::kGridUnitMaxChunks;
+    }
+    return n;
+}
+// active gather warps and back-off sleeps (ns) of the grid-resident kernel: SEGDISTILL_GRID_KNOBS="gather,fin,tma,stat"
+const int* grid_knobs() {
+    static int k[4] = {0, 0, 0, 0};
+    if (k[0] == 0) {
+        int v[4] = {3, 96, 32, 64};
+        const char* e = std::getenv("SEGDISTILL_GRID_KNOBS");
+        if (e) std::sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]);
+        if (v[0] < 1) v[0] = 1;
+        if (v[0] > 3) v[0] = 3;
+        for (int i = 1; i < 4; ++i) v[i] = v[i] < 0 ? 0 : (v[i] > 100000 ? 100000 : v[i]);
+        for (int i = 3; i >= 0; --i) k[i] = v[i];
+    }
+    return k;
+}
+// SEGDISTILL_GRID_FINE=0: no fine tail (every unit grid_unit_chunks() chunks; A-B knob)
+bool grid_fine_tail() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("SEGDISTILL_GRID_FINE");
+        v = e ? (std::atoi(e) != 0) : 1;
+    }
+    return v != 0;
+}
+bool prefer_grid() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("SEGDISTILL_PREFER_GRID");
+        v = e ? (std::atoi(e) != 0) : 1;
+    }
+    return v != 0;
+}
+
 struct RowsCall {
     const void* S;
     const void* T;
@@ -238,6 +283,7 @@ int rows_dispatch(RowsCall c) {
     p.cta_part = reinterpret_cast<float*>(ws + wl.off_cta);
     p.pkt = reinterpret_cast<unsigned long long*>(ws + wl.off_unit);
     p.unit_part = reinterpret_cast<float*>(ws + wl.off_unit);
+    p.dbg = reinterpret_cast<unsigned long long*>(ws + wl.off_rowkl);
 
     // TMA paths: rows must start on 16-byte boundaries.  Rows of one loss that fit one CTA's registers
     // (16384 elements) take the register-resident single pass, everything else the streaming kernel.
@@ -281,6 +327,70 @@ int rows_dispatch(RowsCall c) {
         }
     }
 
+    // grid-resident single pass (kl_rows_grid.cu): same layouts as the cluster kernel.  Units of up to grid_uc chunks of
+    // 4096 elements for as many whole rounds of the grid as the work list has, units of one chunk (or the smallest
+    // size that keeps a row within 64 units) for the rest - so that the last round is shared by every SM.  A row of
+    // any fused loss may span at most 64 units and no more than one round of the grid.
+    struct GridGeo {
+        long long nch_full, nch_last, ups, max_row_units;
+    };
+    const auto grid_geo = [&](int chunks) {
+        GridGeo g;
+        const long long cap = (long long)chunks * sd::kGridChunkElems;
+        g.nch_full = p.G_full > 0 ? (row_len + cap - 1) / cap : 0;
+        g.nch_last = p.g_last ? ((long long)p.g_last * HW + cap - 1) / cap : 0;
+        g.ups = p.G_full * g.nch_full + g.nch_last;
+        g.max_row_units = std::max(g.nch_full, g.nch_last);
+        for (int k = 1; k < c.nl; ++k) {
+            const long long m = p.l[k].m;
+            long long n = m * g.nch_full;
+            if (m > p.G_full) n = (long long)p.G_full * g.nch_full + g.nch_last;
+            g.max_row_units = std::max(g.max_row_units, n);
+        }
+        return g;
+    };
+    bool grid_ok = false;
+    const int grid_uc = grid_unit_chunks();
+    int grid_fc = grid_uc;                       // chunks per unit of the fine region (== grid_uc: no fine region)
+    GridGeo gc = {0, 0, 0, 0}, gf = {0, 0, 0, 0};
+    long long grid_units_coarse = 0, grid_total = 0, grid_max_row_units = 0;
+    int grid_split_b = B, grid_split_row = 0;
+    if (layout_ok && HW % 128 == 0 && !c.perm && c.mse_weight == 0.f) {
+        gc = grid_geo(grid_uc);
+        const long long all_coarse = (long long)B * gc.ups;
+        const long long sms = std::min<long long>(dev.sms, sd::kMaxGrid);
+        for (int fcand = 1; fcand < grid_uc && grid_fine_tail(); fcand *= 2) {
+            gf = grid_geo(fcand);
+            if (gf.max_row_units <= sd::kGridMaxRowUnits && gf.max_row_units <= sms) {
+                grid_fc = fcand;
+                break;
+            }
+        }
+        grid_units_coarse = all_coarse;
+        grid_total = all_coarse;
+        grid_max_row_units = gc.max_row_units;
+        if (grid_fc < grid_uc && all_coarse % sms != 0) {
+            // coarse units for floor(all / sms) whole rounds, cut back to a row boundary of the larger-group loss
+            const long long budget = all_coarse / sms * sms;
+            const int m = c.nl == 2 ? p.l[1].m : 1;
+            int sb = (int)(budget / gc.ups);
+            const long long rem = budget - (long long)sb * gc.ups;
+            int row = gc.nch_full > 0 ? (int)std::min<long long>(rem / gc.nch_full, p.G_full) : 0;
+            row = row / m * m;
+            grid_split_b = sb;
+            grid_split_row = row;
+            grid_units_coarse = (long long)sb * gc.ups + (long long)row * gc.nch_full;
+            const long long fine_first = (long long)row * gf.nch_full;
+            grid_total = grid_units_coarse + (gf.ups - fine_first) + (long long)(B - sb - 1) * gf.ups;
+            grid_max_row_units = grid_units_coarse > 0 ? std::max(gc.max_row_units, gf.max_row_units) : gf.max_row_units;
+        }
+        const long long grid = std::min<long long>(sms, grid_total);
+        // (rows of one unit gain nothing from the exchange: the register-resident kernels serve them)
+        if (grid_max_row_units <= sd::kGridMaxRowUnits && grid_max_row_units <= grid && row_len >= 2048 &&
+            grid_total < (1ll << 31))
+            grid_ok = sd::launch_kl_rows_grid(p, c.dtype == SD_BF16, dev.sms, nullptr, true) == cudaSuccess;
+    }
+
     // packed short rows: whole rows of 32 * TPR elements (TPR a power of two), contiguous in memory
     bool pack_ok = false;
     if (layout_ok && fits_regs && !c.perm && C % g0 == 0 && row_len % 32 == 0) {
@@ -294,15 +404,17 @@ int rows_dispatch(RowsCall c) {
         }
     }
 
-    enum { kGeneric, kRegs, kStream, kCluster, kPack } path;
+    enum { kGeneric, kRegs, kStream, kCluster, kPack, kGrid } path;
+    // (measured on B200: the grid-resident kernel beats the cluster-resident one - 148 SMs instead of 120 -, and that one
+    // the streaming kernel, for one loss and for two)
+    const auto long_rows = [&]() { return grid_ok && prefer_grid() ? kGrid : (cluster_ok ? kCluster : (grid_ok ? kGrid : kStream)); };
     switch (c.algo) {
         case SD_ALGO_AUTO:
-            path = !layout_ok ? kGeneric : (pack_ok ? kPack : fits_regs ? kRegs : (cluster_ok ? kCluster : kStream));
+            path = !layout_ok ? kGeneric : (pack_ok ? kPack : fits_regs ? kRegs : long_rows());
             break;
         case SD_ALGO_TMA:
             if (!layout_ok) return SD_ERR_UNSUPPORTED;
-            // (measured on B200: the cluster-resident kernel beats the streaming kernel for one loss and for two)
-            path = pack_ok ? kPack : fits_regs ? kRegs : (cluster_ok ? kCluster : kStream);
+            path = pack_ok ? kPack : fits_regs ? kRegs : long_rows();
             break;
         case SD_ALGO_ROWS1:
             if (!layout_ok || !fits_regs) return SD_ERR_UNSUPPORTED;
@@ -316,18 +428,29 @@ int rows_dispatch(RowsCall c) {
             if (!cluster_ok) return SD_ERR_UNSUPPORTED;
             path = kCluster;
             break;
+        case SD_ALGO_GRID:
+            if (!grid_ok) return SD_ERR_UNSUPPORTED;
+            path = kGrid;
+            break;
         case SD_ALGO_GENERIC: path = kGeneric; break;
         default: return SD_ERR_VALUE;
     }
     if (path == kGeneric && (c.nl > 1 || c.run_if || c.grad_out[0])) return SD_ERR_UNSUPPORTED;
 
     const int cap = path == kStream ? sd::kl_rows_stream_chunk_capacity() : sd::kl_rows_tma_chunk_capacity();
-    p.nch_full = p.G_full > 0 ? (int)((row_len + cap - 1) / cap) : 1;
-    long long ce = p.G_full > 0 ? (row_len + p.nch_full - 1) / p.nch_full : (long long)p.g_last * HW;
-    ce = (ce + VE - 1) / VE * VE;
-    if (ce > cap) ce = cap;
-    p.chunk_elems = (int)ce;
-    p.nch_last = p.g_last ? (int)(((long long)p.g_last * HW + ce - 1) / ce) : 0;
+    if (path == kGrid) {
+        // units of whole chunks; the last unit of a row may be shorter
+        p.nch_full = p.G_full > 0 ? (int)gc.nch_full : 1;
+        p.chunk_elems = grid_uc * sd::kGridChunkElems;
+        p.nch_last = (int)gc.nch_last;
+    } else {
+        p.nch_full = p.G_full > 0 ? (int)((row_len + cap - 1) / cap) : 1;
+        long long ce = p.G_full > 0 ? (row_len + p.nch_full - 1) / p.nch_full : (long long)p.g_last * HW;
+        ce = (ce + VE - 1) / VE * VE;
+        if (ce > cap) ce = cap;
+        p.chunk_elems = (int)ce;
+        p.nch_last = p.g_last ? (int)(((long long)p.g_last * HW + ce - 1) / ce) : 0;
+    }
     p.units_per_sample = p.G_full * p.nch_full + p.nch_last;
     p.total_units = (long long)B * p.units_per_sample;
     // the longest row of any fused loss, in units
@@ -338,9 +461,23 @@ int rows_dispatch(RowsCall c) {
         if (m > p.G_full) n = (long long)p.G_full * p.nch_full + p.nch_last;
         if (n > max_row_units) max_row_units = n;
     }
+    p.units_coarse = p.total_units;
+    p.split_b = B;
+    if (path == kGrid) {
+        p.total_units = grid_total;
+        p.units_coarse = grid_units_coarse;
+        p.split_b = grid_split_b;
+        p.split_row = grid_split_row;
+        p.f_chunk_elems = grid_fc * sd::kGridChunkElems;
+        p.f_nch_full = p.G_full > 0 ? (int)gf.nch_full : 1;
+        p.f_nch_last = (int)gf.nch_last;
+        p.f_units_per_sample = (int)gf.ups;
+        max_row_units = grid_max_row_units;
+    }
     if (max_row_units >= (1ll << 30)) return SD_ERR_SHAPE;
     p.max_row_units = (int)max_row_units;
     p.delay = stream_delay();
+    for (int i = 0; i < 4; ++i) p.grid_knobs[i] = grid_knobs()[i];
 
     cudaStream_t st = static_cast<cudaStream_t>(c.stream);
     cudaError_t e;
@@ -358,6 +495,10 @@ int rows_dispatch(RowsCall c) {
         e = sd::launch_kl_rows_cluster(p, cg, c.dtype == SD_BF16, dev.sms, st, false);
         g_launches += 1;
         t_last_kernel = c.nl == 2 ? "kl_rows_cluster_kernel(2 losses)" : "kl_rows_cluster_kernel";
+    } else if (path == kGrid) {
+        e = sd::launch_kl_rows_grid(p, c.dtype == SD_BF16, dev.sms, st, false);
+        g_launches += 1;
+        t_last_kernel = c.nl == 2 ? "kl_rows_grid_kernel(2 losses)" : "kl_rows_grid_kernel";
     } else if (path == kStream) {
         e = sd::launch_kl_rows_stream(p, c.dtype == SD_BF16, dev.sms, st);
         g_launches += 1;

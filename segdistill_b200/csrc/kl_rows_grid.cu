@@ -1,0 +1,877 @@
+// Row-wise softmax-KL for rows longer than one SM can hold, resident in the WHOLE GRID: one pass over HBM, no L2
+// re-read, every SM of the GPU busy.  One or two losses (CD + CGD on the same logits) per launch.
+//
+// Same mathematics as kl_rows.cu (mmseg/models/distillation/losses.py:50-58,:108-112 + backward).
+// kl_rows_cluster.cu keeps a long row (CGD, g = 10 channels of 128x128 logits: 1.3 MB of S and T) resident in a
+// thread-block cluster of 8 - but only 15 such clusters fit the GPU's GPCs: 120 of 148 SMs work.  Here the row is
+// spread over CTAs that need not be neighbours: the grid is launched cooperatively (one CTA per SM, all resident),
+// a UNIT is a run of 1 .. 4 chunks (4096 elements of S and of T each) of one row of the smaller-group loss (4 for
+// most of the work list, 1 for its tail: see "units" below), unit u belongs to CTA u % grid - the units of one row are worked on at the same time by different SMs - and the
+// softmax statistics of a unit travel as an epoch-tagged packet through global memory (L2), like in
+// kl_rows_stream.cu, instead of through distributed shared memory.  Between the statistics and the gradient a unit
+// is PARKED IN TENSOR MEMORY, as in the cluster kernel: 8 chunk slots per SM, so up to eight chunks are in flight
+// while the packets of the row-mates arrive - nobody waits for a neighbour in the steady state.
+//
+//   TMA warp     streams the CTA's units, chunk by chunk, through a 6 x 32 KB shared-memory ring; the same warp is the
+//                PUBLISHER: 8 warp records of a parked unit -> the unit's packet in global memory (both jobs polled).
+//   8 PARK warps (phase 1) chunk -> registers (16 elements of S and of T per thread), statistics of the unit against a
+//                warp-uniform running maximum, exponentials -> tensor memory (tcgen05.st); a unit that ends -> one
+//                warp record.
+//   8 GRADIENT   (phase 2) warp 8 + i retrieves what park warp i parked (tcgen05.ld) once the statistics of the
+//     warps      unit's rows are known: one multiply-add per element and loss, no second ex2; dS written once.
+//   3 gather     the packets of the row-mates of a unit (warp i: the CTA's units j % 3 == i), merged (row of the
+//     warps      smaller-group loss: the mates of that row only; row of the larger-group loss: all of them) -> the row
+//                statistics the gradient warps wait for; the KL terms of the rows whose first unit is the CTA's.
+//
+// Geometry contract (cabi.cu): HW % 128 == 0 (a warp's 32 consecutive 4-element vectors are all inside or all outside
+// a unit), units of whole chunks (the last unit of a row may be shorter), at most 64 units per row of any fused loss
+// and no more than the grid holds, no channel gather, no fused MSE.
+#include "rows_common.cuh"
+#include "park_common.cuh"
+#include "launch.h"
+
+namespace sd {
+
+constexpr int kGPark = 256;                            // park threads (warps 0..7); gradient threads: warps 8..15
+constexpr int kGParkWarps = kGPark / 32;
+constexpr int kGTmaWarp = 2 * kGParkWarps;             // warp 16
+constexpr int kGGatherWarps = 3;                       // warps 17..19: packets -> row statistics (warp i: units j % 3 == i)
+constexpr int kGThreads = 2 * kGPark + 32 + 32 * kGGatherWarps;   // 20 warps: the most that keep 96 registers per thread
+constexpr int kGChunkRows = 4;                         // 4-element vectors per park thread, chunk and tensor
+constexpr int kGChunkVecs = kGChunkRows * kGPark;      // 1024 vectors = 4096 elements per tensor
+constexpr int kGChunkBytes = kGChunkVecs * 16;         // fp32; bf16 chunks fill half a slot
+constexpr int kGRing = 6;                              // ring slots of 32 KB (S chunk + T chunk)
+constexpr int kGSlots = 8;                             // TMEM chunk slots per park warp
+constexpr int kGDepth = 8;                             // units between park and gradient (a unit is >= 1 chunk)
+constexpr int kGRecFloats = 12;                        // ms, mt, {zs, zt, a, dd} x 2, 2 x pad (three 16-byte words)
+constexpr int kGTmemCols = 512;
+constexpr int kGPktWords = 2 + 4 * kMaxLosses;         // words of a packet in use (same order as a warp record)
+static_assert(kGSlots * kCSlotCols * (kGParkWarps / 4) == kGTmemCols, "TMEM columns");
+static_assert(kGridUnitMaxChunks * 2 <= kGSlots, "two units must fit the TMEM slots (deadlock freedom)");
+static_assert(kGPktWords <= kPktWords, "packet size");
+static_assert(kGChunkVecs * 4 == kGridChunkElems, "chunk size");
+
+struct GridSmem {
+    unsigned char ring[kGRing][2][kGChunkBytes];
+    uint64_t full[kGRing], empty[kGRing];
+    uint64_t recbar[kGDepth];                             // 8 park warps: "my record of this unit is written"
+    uint64_t finbar[kGDepth];                             // stats warp: "the row statistics of this unit are written"
+    uint64_t tfree[kGParkWarps][kGSlots];                 // gradient warp -> its park warp: "this TMEM slot is read"
+    float rec[kGDepth][kGParkWarps][kGRecFloats];         // warp records of the units in flight
+    float fin[kGDepth][2][4];                             // {Ms, Mt, coef/Zs, coef/Zt} of the unit's row of l[0], of l[1]
+    float refs[kGParkWarps][kGSlots][2];                  // references {ms, mt} a parked chunk was taken against
+    float klpart[kGGatherWarps][kMaxLosses];              // KL sums of the gather warps
+#ifdef SD_GRID_TIMING
+    long long stamp[kGDepth];                             // clock at which park warp 0 finished the unit
+#endif
+    uint32_t tmem_base;
+};
+constexpr size_t kGridSmemBytes = sizeof(GridSmem);
+
+// waits that normally last a microsecond or more: poll, then sleep - a polling warp takes issue slots from the park warps
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned sleep_ns) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(sleep_ns);
+}
+__device__ __forceinline__ void ld_relaxed_v2u64(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+
+
+// ---------------------------------------------------------------- units: a coarse region, then a fine one
+// The work list is cut into units of p.chunk_elems elements (up to 4 chunks) - few unit boundaries, few packets -
+// except for its tail, which is cut into units of p.f_chunk_elems (one chunk): the grid's last round is then shared
+// by all SMs instead of leaving most of them idle, and the last gradient after the last exchange is short.  The
+// regions meet at a row boundary of the larger-group loss (sample p.split_b, row p.split_row of l[0]).
+struct GridRegion {
+    int chunk_elems, nch_full, nch_last, ups;
+};
+__device__ __forceinline__ GridRegion grid_region(const RowsParams& p, bool fine) {
+    GridRegion g;
+    g.chunk_elems = fine ? p.f_chunk_elems : p.chunk_elems;
+    g.nch_full = fine ? p.f_nch_full : p.nch_full;
+    g.nch_last = fine ? p.f_nch_last : p.nch_last;
+    g.ups = fine ? p.f_units_per_sample : p.units_per_sample;
+    return g;
+}
+// first unit (within the sample) of l[0] row j; j == number of rows gives the end
+__device__ __forceinline__ int grid_unit_start(const RowsParams& p, const GridRegion& g, int j) {
+    return j <= p.G_full ? j * g.nch_full : g.ups;
+}
+struct GUnit {
+    int b, grp, ck, nch;   // sample, row of l[0], unit within the row, units of the row
+    int r;                 // unit within the sample
+    int e0, len;           // first element within the row, elements
+    bool fine;
+};
+__device__ __forceinline__ GUnit grid_decode(const RowsParams& p, long long u) {
+    GUnit x;
+    x.fine = u >= p.units_coarse;
+    const GridRegion g = grid_region(p, x.fine);
+    int r;
+    if (!x.fine) {
+        x.b = (int)(u / g.ups);
+        r = (int)(u - (long long)x.b * g.ups);
+    } else {
+        long long v = u - p.units_coarse;
+        const int first = grid_unit_start(p, g, p.split_row);   // the fine units of sample split_b start here
+        const int part = g.ups - first;
+        if (v < part) {
+            x.b = p.split_b;
+            r = first + (int)v;
+        } else {
+            v -= part;
+            const int q = (int)(v / g.ups);
+            x.b = p.split_b + 1 + q;
+            r = (int)(v - (long long)q * g.ups);
+        }
+    }
+    x.r = r;
+    const int full_units = p.G_full * g.nch_full;
+    int g_real;
+    if (r < full_units) {
+        x.grp = g.nch_full == 1 ? r : r / g.nch_full;
+        x.ck = r - x.grp * g.nch_full;
+        x.nch = g.nch_full;
+        g_real = p.l[0].g;
+    } else {
+        x.grp = p.G_full;
+        x.ck = r - full_units;
+        x.nch = g.nch_last;
+        g_real = p.g_last;
+    }
+    x.e0 = x.ck * g.chunk_elems;
+    x.len = min(g.chunk_elems, g_real * p.HW - x.e0);
+    return x;
+}
+// index in the work list of unit r of sample b, in the region `fine`
+__device__ __forceinline__ long long grid_unit_index(const RowsParams& p, const GridRegion& g, bool fine, int b, int r) {
+    if (!fine) return (long long)b * g.ups + r;
+    const int first = grid_unit_start(p, g, p.split_row);
+    if (b == p.split_b) return p.units_coarse + (r - first);
+    return p.units_coarse + (g.ups - first) + (long long)(b - p.split_b - 1) * g.ups + r;
+}
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// cycle counters per CTA (scripts/grid_timing.py; build with SD_NVCC_EXTRA=-DSD_GRID_TIMING)
+#ifdef SD_GRID_TIMING
+#define GT_DECL(n) long long gt_acc[n] = {}
+#define GT_TICK(var) const long long var = clock64()
+#define GT_ACC(slot, a, b) gt_acc[slot] += (b) - (a)
+#define GT_OUT(first, n) do { for (int gi = 0; gi < (n); ++gi) p.dbg[blockIdx.x * 16 + (first) + gi] = (unsigned long long)gt_acc[gi]; } while (0)
+#else
+#define GT_DECL(n)
+#define GT_TICK(var)
+#define GT_ACC(slot, a, b)
+#define GT_OUT(first, n)
+#endif
+
+// R: 0 = independent exponentials per loss, 2 = l[1].tau == 2 * l[0].tau (one ex2 serves both).
+// With one loss, or with R == 2, phase 1 parks the EXPONENTIALS (relative to the warp's running maximum at that
+// moment, kept in shared memory): phase 2 is then a multiply-add per element, no ex2.  Otherwise the raw values are
+// parked and phase 2 recomputes.
+template <typename T, int NL, int R>
+__global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsParams p) {
+    using V = Vec4<T>;
+    using vec_t = typename V::type;
+    constexpr int VE = 4;
+    constexpr int NE = kGChunkRows * VE;        // elements per thread, chunk and tensor
+    constexpr bool kParkExp = NL == 1 || R == 2;
+    constexpr int K = NL - 1;                   // the loss whose exponential comes out of the MUFU
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    GridSmem& sm = *reinterpret_cast<GridSmem*>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+
+    if (p.run_if != nullptr && *p.run_if == 0u) return;  // cancelled backward re-run (uniform over the grid)
+#ifdef SD_GRID_TIMING
+    if (tid == 0) p.dbg[blockIdx.x * 16 + 11] = global_ns();
+#endif
+
+    if (tid == 0) {
+        for (int c = 0; c < kGRing; ++c) {
+            mbar_init(&sm.full[c], 1);
+            mbar_init(&sm.empty[c], kGParkWarps);
+        }
+        for (int q = 0; q < kGDepth; ++q) {
+            mbar_init(&sm.recbar[q], kGParkWarps);
+            mbar_init(&sm.finbar[q], 1);
+        }
+        for (int w = 0; w < kGParkWarps; ++w)
+            for (int q = 0; q < kGSlots; ++q) mbar_init(&sm.tfree[w][q], 1);
+        fence_barrier_init();
+    }
+    if (warp == kGTmaWarp) tmem_alloc(&sm.tmem_base, kGTmemCols);
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    const uint32_t tmem_base = sm.tmem_base;
+
+    const int grid = (int)gridDim.x;
+    const int n_units = blockIdx.x < p.total_units ? (int)((p.total_units - blockIdx.x + grid - 1) / grid) : 0;
+
+    float c2[NL];
+#pragma unroll
+    for (int k = 0; k < NL; ++k) c2[k] = p.l[k].c2;
+    const int n_gather = p.grid_knobs[0];          // active gather warps (1 .. kGGatherWarps)
+    const unsigned ns_fin = (unsigned)p.grid_knobs[1], ns_tma = (unsigned)p.grid_knobs[2], ns_stat = (unsigned)p.grid_knobs[3];
+
+    if (warp == kGTmaWarp) {
+        // =====================================================================================
+        // TMA + publisher warp.  Lane 0 streams this CTA's units, chunk by chunk, into the ring as slots drain; the
+        // warp turns the 8 warp records of a parked unit into its packet in global memory as soon as they are
+        // written.  Neither job ever waits for the other (or for another CTA): both are polled.
+        // =====================================================================================
+        // tag of this launch's packets: the workspace's launch counter (bumped by the last CTA to finish, i.e. after
+        // every CTA has read it) + 1, so a packet left by any earlier launch never validates
+        const unsigned long long tag = (unsigned long long)(__ldcg(&p.ctrl[2]) + 1u) << 32;
+        const uint64_t pol = l2_policy_evict_first();
+        int slot = 0;
+        uint32_t phase = 0;
+        int jt = 0, c = 0, jp = 0;  // unit being streamed and its chunk, unit to publish next
+        size_t base = 0;
+        int nvs = 0;
+        if (n_units > 0) {
+            const GUnit x = grid_decode(p, blockIdx.x);
+            base = ((size_t)x.b * p.C + (size_t)x.grp * p.l[0].g) * p.HW + (size_t)x.e0;
+            nvs = x.len / VE;
+        }
+        while (jp < n_units) {
+            int ev = 0;
+            if (lane == 0) {
+                if (jt < n_units && mbar_try_wait(&sm.empty[slot], phase ^ 1u)) ev |= 1;
+                if (mbar_try_wait(&sm.recbar[jp & (kGDepth - 1)], (uint32_t)(jp >> 3) & 1u)) ev |= 2;
+            }
+            ev = __shfl_sync(0xffffffffu, ev, 0);
+            if (ev & 1) {
+                if (lane == 0) {
+                    const int nv = min(kGChunkVecs, nvs - c * kGChunkVecs);
+                    const uint32_t bytes = (uint32_t)nv * (uint32_t)sizeof(vec_t);
+                    mbar_arrive_expect_tx(&sm.full[slot], 2u * bytes);
+                    const size_t off = (base + (size_t)c * kGChunkVecs * VE) * sizeof(T);
+                    tma_bulk_g2s(sm.ring[slot][0], static_cast<const char*>(p.S) + off, bytes, &sm.full[slot], pol);
+                    tma_bulk_g2s(sm.ring[slot][1], static_cast<const char*>(p.T) + off, bytes, &sm.full[slot], pol);
+                }
+                if (++slot == kGRing) {
+                    slot = 0;
+                    phase ^= 1u;
+                }
+                if (++c * kGChunkVecs >= nvs) {
+                    c = 0;
+                    ++jt;
+                    if (jt < n_units) {
+                        const GUnit x = grid_decode(p, (long long)blockIdx.x + (long long)jt * grid);
+                        base = ((size_t)x.b * p.C + (size_t)x.grp * p.l[0].g) * p.HW + (size_t)x.e0;
+                        nvs = x.len / VE;
+                    }
+                }
+            }
+            if (ev & 2) {
+                const float4* q = reinterpret_cast<const float4*>(sm.rec[jp & (kGDepth - 1)][lane & 7]);
+                PStat<NL> st = pstat_from<NL>(q[0], q[1], NL == 2 ? q[2] : make_float4(0.f, 0.f, 0.f, 0.f));
+                st = pstat_reduce<NL, R, 8>(st, c2);
+                float val = st.ms;
+                if (lane == 1) val = st.mt;
+                if (lane == 2) val = st.zs[0];
+                if (lane == 3) val = st.zt[0];
+                if (lane == 4) val = st.a[0];
+                if (lane == 5) val = st.dd[0];
+                if (NL == 2) {
+                    if (lane == 6) val = st.zs[K];
+                    if (lane == 7) val = st.zt[K];
+                    if (lane == 8) val = st.a[K];
+                    if (lane == 9) val = st.dd[K];
+                }
+                if (lane < 2 + 4 * NL)
+                    st_relaxed_u64(p.pkt + ((size_t)blockIdx.x + (size_t)jp * grid) * kPktWords + lane,
+                                   tag | (unsigned long long)__float_as_uint(val));
+                ++jp;
+            }
+            if (ev == 0) __nanosleep(ns_tma);
+        }
+        // TMEM is released after every consumer of this CTA is through with it
+        bar_sync(3, kGThreads);
+        tmem_dealloc(tmem_base, kGTmemCols);
+        return;
+    }
+
+    if (warp > kGTmaWarp) {
+        // =====================================================================================
+        // gather warps: packets of a unit's row-mates (all CTAs) -> row statistics for the gradient warps; warp i takes
+        // the units j % kGGatherWarps == i of this CTA
+        // =====================================================================================
+        const int gw = warp - kGTmaWarp - 1;
+        const unsigned epoch = __ldcg(&p.ctrl[2]) + 1u;
+        float kl_acc[NL];
+        float coef[NL];
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+            kl_acc[k] = 0.f;
+            coef[k] = p.l[k].coef;
+            if (p.grad_out[k] != nullptr) coef[k] *= __ldg(p.grad_out[k]);
+        }
+        GT_DECL(6);
+        for (int j = gw < n_gather ? gw : n_units; j < n_units; j += n_gather) {
+            // ---- the packets of the row-mates of unit j: units [rowu, rowu + rown); its row of l[0] is the mates
+            //      [i0, i0 + n0)
+            const long long u = (long long)blockIdx.x + (long long)j * grid;
+            const GUnit x = grid_decode(p, u);
+            const GridRegion rg = grid_region(p, x.fine);
+            long long rowu;
+            int rown, i0, n0, rk = 0;
+            if (NL == 2) {
+                const int m = p.l[K].m;
+                rk = x.grp / m;
+                const int j0 = rk * m, j1 = min(j0 + m, p.l[0].G);
+                const int us = grid_unit_start(p, rg, j0);
+                rown = grid_unit_start(p, rg, j1) - us;
+                rowu = grid_unit_index(p, rg, x.fine, x.b, us);
+                i0 = (int)(u - x.ck - rowu);
+                n0 = x.nch;
+            } else {
+                rowu = u - x.ck;
+                rown = x.nch;
+                i0 = 0;
+                n0 = rown;
+            }
+            // (my own packet is among them: nothing can be complete before my CTA's park warps are through the unit)
+            GT_TICK(g0);
+            mbar_wait_backoff(&sm.recbar[j & (kGDepth - 1)], (uint32_t)(j >> 3) & 1u, ns_stat);
+            GT_TICK(g1);
+            GT_ACC(0, g0, g1);
+            PStat<NL> mate[2];
+            unsigned spins = 0;
+            for (;;) {
+                bool ok = true;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int idx = lane + 32 * h;
+                    mate[h] = pstat_empty<NL>();
+                    if (idx < rown) {
+                        const unsigned long long* q = p.pkt + (size_t)(rowu + idx) * kPktWords;
+                        unsigned long long w[2 + 4 * NL];
+#pragma unroll
+                        for (int i = 0; i < 1 + 2 * NL; ++i) ld_relaxed_v2u64(q + 2 * i, w[2 * i], w[2 * i + 1]);
+#pragma unroll
+                        for (int i = 0; i < 2 + 4 * NL; ++i) ok = ok && (unsigned)(w[i] >> 32) == epoch;
+                        mate[h].ms = __uint_as_float((unsigned)w[0]);
+                        mate[h].mt = __uint_as_float((unsigned)w[1]);
+                        mate[h].zs[0] = __uint_as_float((unsigned)w[2]);
+                        mate[h].zt[0] = __uint_as_float((unsigned)w[3]);
+                        mate[h].a[0] = __uint_as_float((unsigned)w[4]);
+                        mate[h].dd[0] = __uint_as_float((unsigned)w[5]);
+                        if (NL == 2) {
+                            mate[h].zs[K] = __uint_as_float((unsigned)w[2 + 4 * K]);
+                            mate[h].zt[K] = __uint_as_float((unsigned)w[3 + 4 * K]);
+                            mate[h].a[K] = __uint_as_float((unsigned)w[4 + 4 * K]);
+                            mate[h].dd[K] = __uint_as_float((unsigned)w[5 + 4 * K]);
+                        }
+                    }
+                }
+                if (__all_sync(0xffffffffu, ok)) break;
+                if (++spins > kSpinLimit) {
+                    // never expected (the launch is cooperative: every CTA is resident).  The flag makes the last CTA
+                    // report NaN losses instead of numbers built on a stale packet.
+                    if (lane == 0) atomicExch(&p.ctrl[1], 1u);
+                    break;
+                }
+                __nanosleep(ns_stat);
+            }
+            GT_TICK(g2);
+            GT_ACC(1, g1, g2);
+            const int d = j & (kGDepth - 1);
+            // ---- on the critical path (the gradient warps wait for it): maxima and the sums Zs, Zt of the unit's rows,
+            //      nothing else - plain (max, sum exp) merges, one redux / butterfly each
+            const bool in0[2] = {NL == 1 || (lane >= i0 && lane < i0 + n0), NL == 1 || (lane + 32 >= i0 && lane + 32 < i0 + n0)};
+            {
+                const float MsK = warp_max_uniform(fmaxf(mate[0].ms, mate[1].ms));
+                const float MtK = warp_max_uniform(fmaxf(mate[0].mt, mate[1].mt));
+                float zsK = mate[0].zs[K] * ref_factor(mate[0].ms, MsK, c2[K]);
+                float ztK = mate[0].zt[K] * ref_factor(mate[0].mt, MtK, c2[K]);
+                if (rown > 32) {
+                    zsK = fmaf(mate[1].zs[K], ref_factor(mate[1].ms, MsK, c2[K]), zsK);
+                    ztK = fmaf(mate[1].zt[K], ref_factor(mate[1].mt, MtK, c2[K]), ztK);
+                }
+                float Ms0 = MsK, Mt0 = MtK, zs0 = 0.f, zt0 = 0.f;
+                if (NL == 2) {
+                    Ms0 = warp_max_uniform(fmaxf(in0[0] ? mate[0].ms : kMaxFloor, in0[1] ? mate[1].ms : kMaxFloor));
+                    Mt0 = warp_max_uniform(fmaxf(in0[0] ? mate[0].mt : kMaxFloor, in0[1] ? mate[1].mt : kMaxFloor));
+                    zs0 = in0[0] ? mate[0].zs[0] * ref_factor(mate[0].ms, Ms0, c2[0]) : 0.f;
+                    zt0 = in0[0] ? mate[0].zt[0] * ref_factor(mate[0].mt, Mt0, c2[0]) : 0.f;
+                    if (rown > 32 && in0[1]) {
+                        zs0 = fmaf(mate[1].zs[0], ref_factor(mate[1].ms, Ms0, c2[0]), zs0);
+                        zt0 = fmaf(mate[1].zt[0], ref_factor(mate[1].mt, Mt0, c2[0]), zt0);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    zsK += __shfl_xor_sync(0xffffffffu, zsK, o);
+                    ztK += __shfl_xor_sync(0xffffffffu, ztK, o);
+                    if (NL == 2) {
+                        zs0 += __shfl_xor_sync(0xffffffffu, zs0, o);
+                        zt0 += __shfl_xor_sync(0xffffffffu, zt0, o);
+                    }
+                }
+                if (lane == 0) {
+                    if (NL == 2) {
+                        *reinterpret_cast<float4*>(sm.fin[d][0]) = make_float4(Ms0, Mt0, __fdividef(coef[0], zs0), __fdividef(coef[0], zt0));
+                        *reinterpret_cast<float4*>(sm.fin[d][1]) = make_float4(MsK, MtK, __fdividef(coef[K], zsK), __fdividef(coef[K], ztK));
+                    } else {
+                        *reinterpret_cast<float4*>(sm.fin[d][0]) = make_float4(MsK, MtK, __fdividef(coef[0], zsK), __fdividef(coef[0], ztK));
+                    }
+                }
+                __syncwarp();
+#ifdef SD_GRID_TIMING
+                gt_acc[4] += clock64() - sm.stamp[d];     // park warp 0 through the unit -> row statistics ready
+#endif
+                if (lane == 0) mbar_arrive(&sm.finbar[d]);
+            }
+            GT_TICK(g3);
+            GT_ACC(2, g2, g3);
+            // ---- off the critical path: the KL terms of the rows whose first unit is mine, from the complete statistics
+            //      (compensated merges of the a and dd sums: common.cuh)
+            const bool own0 = x.ck == 0, ownK = NL == 2 && u == rowu;
+            if (own0 || ownK) {
+                PStat<NL> pr, sr = pstat_empty<NL>();
+                if (NL == 2) {
+                    PStat<NL> all = mate[0], mine[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) mine[h] = in0[h] ? mate[h] : pstat_empty<NL>();
+                    if (rown > 32) {
+                        all = pstat_merge<NL, R>(mate[0], mate[1], c2);
+                        mine[0] = pstat_merge<NL, R>(mine[0], mine[1], c2);
+                    }
+                    if (ownK) sr = pstat_reduce<NL, R, 32>(all, c2);
+                    pr = pstat_reduce<NL, R, 32>(mine[0], c2);
+                } else {
+                    PStat<NL> all = mate[0];
+                    if (rown > 32) all = pstat_merge<NL, R>(mate[0], mate[1], c2);
+                    pr = pstat_reduce<NL, R, 32>(all, c2);
+                }
+                if (lane == 0) {
+                    if (own0) {
+                        const float kl = kl_of_row(NL == 2 && R == 2 ? 2.f : 1.f, pr.zs[0], pr.zt[0], pr.a[0], pr.dd[0]);
+                        if (p.l[0].row_kl) p.l[0].row_kl[x.b * p.l[0].G + x.grp] = kl;
+                        kl_acc[0] += kl;
+                    }
+                    if (ownK) {
+                        const float kl = kl_of_row(1.f, sr.zs[K], sr.zt[K], sr.a[K], sr.dd[K]);
+                        if (p.l[K].row_kl) p.l[K].row_kl[x.b * p.l[K].G + rk] = kl;
+                        kl_acc[K] += kl;
+                    }
+                }
+            }
+            GT_TICK(g4);
+            GT_ACC(3, g3, g4);
+#ifdef SD_GRID_TIMING
+            gt_acc[5] += 1;
+#endif
+        }
+#ifdef SD_GRID_TIMING
+        if (gw == 0 && lane == 0) GT_OUT(5, 6);
+#endif
+        // ---- loss: this CTA's partial = the gather warps' sums in warp order; the last CTA sums the partials in a fixed order
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < NL; ++k) sm.klpart[gw][k] = kl_acc[k];
+        }
+        // every consumer is through with TMEM (the TMA warp frees it); every gather warp's partial is written
+        bar_sync(3, kGThreads);
+        if (gw != 0) return;
+#ifdef SD_GRID_TIMING
+        if (lane == 0) p.dbg[blockIdx.x * 16 + 15] = global_ns();
+#endif
+        unsigned ticket = 0;
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < NL; ++k) {
+                float acc = sm.klpart[0][k];
+#pragma unroll
+                for (int w = 1; w < kGGatherWarps; ++w) acc += sm.klpart[w][k];
+                __stcg(&p.cta_part[k * kMaxGrid + blockIdx.x], acc);
+            }
+            __threadfence();
+            ticket = atomicAdd(&p.ctrl[0], 1u);
+        }
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            double acc[NL];
+#pragma unroll
+            for (int k = 0; k < NL; ++k) acc[k] = 0.0;
+            for (int i = lane; i < (int)gridDim.x; i += 32) {
+#pragma unroll
+                for (int k = 0; k < NL; ++k) acc[k] += (double)__ldcg(&p.cta_part[k * kMaxGrid + i]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int k = 0; k < NL; ++k) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
+            }
+            if (lane == 0) {
+                const bool timed_out = __ldcg(&p.ctrl[1]) != 0u;
+#pragma unroll
+                for (int k = 0; k < NL; ++k)
+                    *p.l[k].loss = timed_out ? __int_as_float(0x7fc00000) : (float)((double)p.l[k].loss_scale * acc[k]);
+                atomicAdd(&p.ctrl[2], 1u);
+                atomicExch(&p.ctrl[0], 0u);
+            }
+        }
+        return;
+    }
+
+    // =========================================================================================
+    // park warps 0..7 and gradient warps 8..15: warp 8 + i retrieves what warp i parked
+    // =========================================================================================
+    const int pw = warp & (kGParkWarps - 1);
+    const int ptid = tid & (kGPark - 1);
+    // the pair's TMEM window: lane quarter of both warps, 256 columns, 8 chunk slots of 32
+    const uint32_t tmem_mine = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((pw >> 2) * 256);
+    const int wv = pw * 32;            // the pair's vector-rows of a chunk start here, + 256 r (r < 4)
+
+    if (warp < kGParkWarps) {
+        // ------------------------------------------------ phase 1: statistics, park the unit
+        PStat<NL> st = pstat_empty<NL>();  // statistics of the unit so far: maxima identical in every lane, sums per lane
+        uint32_t q = 0;                    // chunks parked so far -> TMEM slot
+        GT_DECL(8);
+        GT_TICK(gt_start);
+        int slot = 0;
+        uint32_t phase = 0;
+
+        // the running maxima move to (at least) wms, wmt: rescale the sums (rarely needed after the first chunks)
+        auto raise_refs = [&](float wms, float wmt) {
+            const float nms = fmaxf(st.ms, wms), nmt = fmaxf(st.mt, wmt);
+            if (nms != st.ms || nmt != st.mt) {      // warp-uniform
+                float rs[NL], rt[NL], df[NL], sh[NL];
+                exps<NL, R>(st.ms, nms, c2, rs);
+                exps<NL, R>(st.mt, nmt, c2, rt);
+                shifts<NL, R>(st.ms, st.mt, nms, nmt, c2, sh);
+                factor_diffs<NL, R>(sh, rs, rt, df);
+#pragma unroll
+                for (int k = 0; k < NL; ++k) {
+                    st.dd[k] = fmaf(st.zs[k], df[k], st.dd[k] * rt[k]);
+                    st.zs[k] *= rs[k];
+                    st.zt[k] *= rt[k];
+                    st.a[k] = fmaf(st.zt[k], sh[k], st.a[k] * rt[k]);
+                }
+                st.ms = nms;
+                st.mt = nmt;
+            }
+        };
+        // N elements into the statistics of the unit; what gets parked replaces them in fs / ft
+        auto accumulate = [&](float* fs, float* ft, int n) {
+            float refs2[NL], reft2[NL];
+#pragma unroll
+            for (int k = 0; k < NL; ++k) {
+                refs2[k] = __fmul_rn(st.ms, c2[k]);
+                reft2[k] = __fmul_rn(st.mt, c2[k]);
+            }
+#pragma unroll
+            for (int i = 0; i < NE; ++i) {
+                if (i < n) {
+                    float as[NL], at[NL], es[NL], et[NL];
+                    exps_args<NL, R>(fs[i], refs2, c2, as, es);
+                    exps_args<NL, R>(ft[i], reft2, c2, at, et);
+                    if (NL == 2 && R == 2) {
+                        // e0 = eK^2: the sums of loss 0 straight from the loss-K exponentials (one FFMA each)
+                        const float da = at[K] - as[K], dk = et[K] - es[K];
+                        st.zs[K] += es[K];
+                        st.zt[K] += et[K];
+                        st.zs[0] = fmaf(es[K], es[K], st.zs[0]);
+                        st.zt[0] = fmaf(et[K], et[K], st.zt[0]);
+                        const float w = et[K] * da;
+                        st.a[K] += w;
+                        st.a[0] = fmaf(et[K], w, st.a[0]);
+                        st.dd[K] += dk;
+                        st.dd[0] = fmaf(dk, et[K] + es[K], st.dd[0]);      // et0 - es0 = (eK_t - eK_s)(eK_t + eK_s)
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < NL; ++k) {
+                            st.zs[k] += es[k];
+                            st.zt[k] += et[k];
+                            st.a[k] = fmaf(et[k], at[k] - as[k], st.a[k]);
+                        }
+#pragma unroll
+                        for (int k = 0; k < NL; ++k) st.dd[k] += et[k] - es[k];
+                    }
+                    if (kParkExp) {
+                        fs[i] = es[K];
+                        ft[i] = et[K];
+                    }
+                }
+            }
+        };
+
+        for (int j = 0; j < n_units; ++j) {
+            GT_TICK(d0);
+            const GUnit x = grid_decode(p, (long long)blockIdx.x + (long long)j * grid);
+            const int nvs = x.len / VE;
+            const int nchunks = (nvs + kGChunkVecs - 1) / kGChunkVecs;
+            st = pstat_empty<NL>();
+            GT_TICK(d1);
+            GT_ACC(3, d0, d1);
+            for (int c = 0; c < nchunks; ++c, ++q) {
+                // ---- one chunk: ring -> registers -> statistics -> TMEM
+                const uint32_t ts = q & (uint32_t)(kGSlots - 1);
+                if (q >= (uint32_t)kGSlots) {
+                    // the slot's previous chunk has been retrieved by my gradient warp
+                    GT_TICK(w0);
+                    mbar_wait(&sm.tfree[pw][ts], ((q >> 3) - 1u) & 1u);
+                    GT_TICK(w1);
+                    GT_ACC(0, w0, w1);
+                    tmem_fence_after_sync();
+                }
+                GT_TICK(w2);
+                mbar_wait(&sm.full[slot], phase);
+                GT_TICK(w3);
+                GT_ACC(1, w2, w3);
+#ifdef SD_GRID_TIMING
+                if (tid == 0 && q == 0) p.dbg[blockIdx.x * 16 + 12] = global_ns();
+#endif
+                const vec_t* bs = reinterpret_cast<const vec_t*>(sm.ring[slot][0]);
+                const vec_t* bt = reinterpret_cast<const vec_t*>(sm.ring[slot][1]);
+                float fs[NE], ft[NE];
+#pragma unroll
+                for (int r = 0; r < kGChunkRows; ++r) {
+                    V::unpack(bs[r * kGPark + ptid], &fs[r * VE]);
+                    V::unpack(bt[r * kGPark + ptid], &ft[r * VE]);
+                }
+                float mxs[kGChunkRows], mxt[kGChunkRows];
+#pragma unroll
+                for (int r = 0; r < kGChunkRows; ++r) {
+                    mxs[r] = fmaxf(fmaxf(fs[r * VE], fs[r * VE + 1]), fmaxf(fs[r * VE + 2], fs[r * VE + 3]));
+                    mxt[r] = fmaxf(fmaxf(ft[r * VE], ft[r * VE + 1]), fmaxf(ft[r * VE + 2], ft[r * VE + 3]));
+                }
+                const int vA = c * kGChunkVecs + wv;      // my first vector-row, in vectors of the unit; + 256 r
+                if (vA + (kGChunkRows - 1) * kGPark < nvs) {
+                    // ---- all my vector-rows lie inside the unit (the common case)
+                    const float wms = warp_max_uniform(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])));
+                    const float wmt = warp_max_uniform(fmaxf(fmaxf(mxt[0], mxt[1]), fmaxf(mxt[2], mxt[3])));
+                    // every lane's shared-memory reads went into the maxima: the slot may go back to the TMA warp
+                    if (lane == 0) mbar_arrive(&sm.empty[slot]);
+                    GT_TICK(r0);
+                    raise_refs(wms, wmt);
+                    GT_TICK(r1);
+                    GT_ACC(4, r0, r1);
+                    accumulate(fs, ft, NE);
+                    GT_TICK(r2);
+                    GT_ACC(5, r1, r2);
+                } else {
+                    // ---- the unit ends in this chunk: only the vector-rows inside it count
+                    float ms_ = kMaxFloor, mt_ = kMaxFloor;
+#pragma unroll
+                    for (int r = 0; r < kGChunkRows; ++r) {
+                        if (vA + r * kGPark < nvs) {
+                            ms_ = fmaxf(ms_, mxs[r]);
+                            mt_ = fmaxf(mt_, mxt[r]);
+                        }
+                    }
+                    const float wms = warp_max_uniform(ms_);
+                    const float wmt = warp_max_uniform(mt_);
+                    if (lane == 0) mbar_arrive(&sm.empty[slot]);
+                    raise_refs(wms, wmt);
+#pragma unroll
+                    for (int r = 0; r < kGChunkRows; ++r)
+                        if (vA + r * kGPark < nvs) accumulate(&fs[r * VE], &ft[r * VE], VE);
+                }
+                // ---- park: registers -> TMEM; the references once per warp
+                Parked pk;
+#pragma unroll
+                for (int r = 0; r < kGChunkRows; ++r) {
+#pragma unroll
+                    for (int e = 0; e < VE; ++e) {
+                        pk.w[r * 8 + e] = __float_as_uint(fs[r * VE + e]);
+                        pk.w[r * 8 + 4 + e] = __float_as_uint(ft[r * VE + e]);
+                    }
+                }
+                GT_TICK(s0);
+                tmem_st32(tmem_mine + ts * kCSlotCols, pk);
+                if (kParkExp && lane == 0) *reinterpret_cast<float2*>(sm.refs[pw][ts]) = make_float2(st.ms, st.mt);
+                GT_TICK(s1);
+                GT_ACC(6, s0, s1);
+                if (++slot == kGRing) {
+                    slot = 0;
+                    phase ^= 1u;
+                }
+            }
+            // ---- the unit is parked: the warp's record (maxima + 4 sums per loss, transposed butterfly); what I
+            //      stored in TMEM is complete and ordered before the arrival the gradient warps (transitively) wait on
+            GT_TICK(c0);
+            {
+                float v[8] = {st.zs[0], st.zt[0], st.a[0], st.dd[0], 0.f, 0.f, 0.f, 0.f};
+                if (NL == 2) {
+                    v[4] = st.zs[NL - 1];
+                    v[5] = st.zt[NL - 1];
+                    v[6] = st.a[NL - 1];
+                    v[7] = st.dd[NL - 1];
+                }
+                const float tot = warp_sum8_transposed(v, lane);
+                float* rec = sm.rec[j & (kGDepth - 1)][pw];
+                if ((lane & 3) == 0 && lane < 4 * 4 * NL) rec[2 + (lane >> 2)] = tot;
+                if (lane == 1) rec[0] = st.ms;
+                if (lane == 2) rec[1] = st.mt;
+            }
+            tmem_wait_st();
+            tmem_fence_before_sync();
+            __syncwarp();
+#ifdef SD_GRID_TIMING
+            if (tid == 0) sm.stamp[j & (kGDepth - 1)] = clock64();
+            gt_acc[7] += clock64() - c0;
+#endif
+            if (lane == 0) mbar_arrive(&sm.recbar[j & (kGDepth - 1)]);
+        }
+#ifdef SD_GRID_TIMING
+        if (tid == 0) {
+            gt_acc[2] = clock64() - gt_start;
+            GT_OUT(0, 3);
+            p.dbg[blockIdx.x * 16 + 13] = global_ns();
+        }
+#endif
+    } else {
+        // ------------------------------------------------ phase 2: gradient from the parked unit
+        uint32_t q = 0;                    // chunks retrieved so far -> TMEM slot
+        GT_DECL(2);
+        GT_TICK(gt_start);
+        for (int j = 0; j < n_units; ++j) {
+            const GUnit x = grid_decode(p, (long long)blockIdx.x + (long long)j * grid);
+            const int nvs = x.len / VE;
+            const int n = (nvs + kGChunkVecs - 1) / kGChunkVecs;
+            const int d = j & (kGDepth - 1);
+            GT_TICK(w0);
+            mbar_wait_backoff(&sm.finbar[d], (uint32_t)(j >> 3) & 1u, ns_fin);
+            GT_TICK(w1);
+            GT_ACC(0, w0, w1);
+            tmem_fence_after_sync();
+            T* out = static_cast<T*>(p.dS) + ((size_t)x.b * p.C + (size_t)x.grp * p.l[0].g) * p.HW + (size_t)x.e0;
+            const float4 fa = *reinterpret_cast<const float4*>(sm.fin[d][0]);                 // row of l[0]
+            const float4 fb = NL == 2 ? *reinterpret_cast<const float4*>(sm.fin[d][1]) : fa;   // row of l[1]
+            auto grad_chunk = [&](int c, const Parked& pk, uint32_t ts) {
+                float2 rf = make_float2(0.f, 0.f);
+                if (kParkExp) rf = *reinterpret_cast<const float2*>(sm.refs[pw][ts]);
+                // the parked values are in registers, the references too: the slot may be parked into again
+                __syncwarp();
+                tmem_fence_before_sync();
+                if (lane == 0) mbar_arrive(&sm.tfree[pw][ts]);
+                const int vA = c * kGChunkVecs + wv;
+                float gsK = 0.f, gtK = 0.f, gs0 = 0.f, gt0 = 0.f, rs0 = 0.f, rt0 = 0.f, rs1 = 0.f, rt1 = 0.f;
+                if (kParkExp) {
+                    // parked: e = exp2((x - ref) c2[K]); softmax_k = e^(c2[k]/c2[K]) * exp2((ref - M_k) c2[k]) / Z_k, ref <= M_k
+                    gsK = fb.z * ref_factor(rf.x, fb.x, c2[K]);
+                    gtK = fb.w * ref_factor(rf.y, fb.y, c2[K]);
+                    if (NL == 2) {
+                        gs0 = fa.z * ref_factor(rf.x, fa.x, c2[0]);
+                        gt0 = fa.w * ref_factor(rf.y, fa.y, c2[0]);
+                    }
+                } else {
+                    // raw values parked: recompute against the row maxima
+                    rs0 = __fmul_rn(fa.x, c2[0]);
+                    rt0 = __fmul_rn(fa.y, c2[0]);
+                    rs1 = __fmul_rn(fb.x, c2[K]);
+                    rt1 = __fmul_rn(fb.y, c2[K]);
+                }
+#pragma unroll
+                for (int r = 0; r < kGChunkRows; ++r) {
+                    if (vA + r * kGPark < nvs) {
+                        float o[VE];
+#pragma unroll
+                        for (int e = 0; e < VE; ++e) {
+                            const float vs = __uint_as_float(pk.w[r * 8 + e]), vt = __uint_as_float(pk.w[r * 8 + 4 + e]);
+                            if (kParkExp && NL == 2) {
+                                o[e] = vs * fmaf(vs, gs0, gsK) - vt * fmaf(vt, gt0, gtK);
+                            } else if (kParkExp) {
+                                o[e] = fmaf(vs, gsK, -vt * gtK);
+                            } else {
+                                const float es0 = fast_exp2(fmaf(vs, c2[0], -rs0));
+                                const float et0 = fast_exp2(fmaf(vt, c2[0], -rt0));
+                                const float es1 = fast_exp2(fmaf(vs, c2[K], -rs1));
+                                const float et1 = fast_exp2(fmaf(vt, c2[K], -rt1));
+                                o[e] = fmaf(es0, fa.z, es1 * fb.z) - fmaf(et0, fa.w, et1 * fb.w);
+                            }
+                        }
+                        V::store(out + (size_t)(vA + r * kGPark + lane) * VE, o);
+                    }
+                }
+            };
+            // parked chunks in flight from TMEM, one ahead of the arithmetic, in two register sets
+            Parked pa, pb;
+            tmem_ld32(tmem_mine + (q & (uint32_t)(kGSlots - 1)) * kCSlotCols, pa);
+            for (int c = 0; c < n; c += 2) {
+                const uint32_t t0_ = (q + (uint32_t)c) & (uint32_t)(kGSlots - 1), t1_ = (t0_ + 1) & (uint32_t)(kGSlots - 1),
+                               t2_ = (t0_ + 2) & (uint32_t)(kGSlots - 1);
+                tmem_wait_ld(pa);
+                if (c + 1 < n) tmem_ld32(tmem_mine + t1_ * kCSlotCols, pb);
+                grad_chunk(c, pa, t0_);
+                if (c + 1 < n) {
+                    tmem_wait_ld(pb);
+                    if (c + 2 < n) tmem_ld32(tmem_mine + t2_ * kCSlotCols, pa);
+                    grad_chunk(c + 1, pb, t1_);
+                }
+            }
+            q += (uint32_t)n;
+        }
+#ifdef SD_GRID_TIMING
+        if (tid == kGPark) {
+            gt_acc[1] = clock64() - gt_start;
+            GT_OUT(3, 2);
+            p.dbg[blockIdx.x * 16 + 14] = global_ns();
+        }
+#endif
+    }
+    // every consumer is through with TMEM (the TMA warp frees it)
+    bar_sync(3, kGThreads);
+}
+
+// ====================================================================================================
+template <typename T, int NL, int R>
+static cudaError_t launch_grid_t(const RowsParams& p, int sms, cudaStream_t stream, bool probe_only) {
+    auto kern = kl_rows_grid_kernel<T, NL, R>;
+    static std::atomic<int> ctas_per_sm_dev[kMaxDevices];  // per instantiation and device; -1: cannot run
+    std::atomic<int>& ctas_per_sm = ctas_per_sm_dev[device_slot()];
+    if (ctas_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGridSmemBytes);
+        if (e != cudaSuccess) return e;
+        int n = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kGThreads, kGridSmemBytes);
+        if (e != cudaSuccess) return e;
+        ctas_per_sm = n >= 1 ? 1 : -1;
+    }
+    if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
+    if (probe_only) return cudaSuccess;
+    long long grid = sms;                      // one CTA per SM: each allocates all of its SM's tensor memory
+    if (grid > p.total_units) grid = p.total_units;
+    if (grid > kMaxGrid) grid = kMaxGrid;
+    if (p.max_row_units > grid) return cudaErrorInvalidConfiguration;   // (cabi.cu checks against the SM count first)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kGThreads);
+    cfg.dynamicSmemBytes = kGridSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;  // every CTA must be resident: they read each other's packets
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+cudaError_t launch_kl_rows_grid(const RowsParams& p, bool bf16, int sms, cudaStream_t stream, bool probe_only) {
+    if (p.nl == 2) {
+        // tau[1] == 2 * tau[0]: one exponential serves both losses
+        const bool sq = p.l[0].c2 == 2.f * p.l[1].c2;
+        if (sq)
+            return bf16 ? launch_grid_t<__nv_bfloat16, 2, 2>(p, sms, stream, probe_only)
+                        : launch_grid_t<float, 2, 2>(p, sms, stream, probe_only);
+        return bf16 ? launch_grid_t<__nv_bfloat16, 2, 0>(p, sms, stream, probe_only)
+                    : launch_grid_t<float, 2, 0>(p, sms, stream, probe_only);
+    }
+    return bf16 ? launch_grid_t<__nv_bfloat16, 1, 0>(p, sms, stream, probe_only)
+                : launch_grid_t<float, 1, 0>(p, sms, stream, probe_only);
+}
+
+}  // namespace sd

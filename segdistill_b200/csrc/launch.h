@@ -36,6 +36,9 @@ int kl_rows_group_chunk_capacity();
 cudaError_t launch_kl_rows_cluster(const RowsParams& p, const ClusterGeom& g, bool bf16, int sms, cudaStream_t stream,
                                    bool probe_only);
 
+// kl_rows_grid.cu   (probe_only: just answer whether the kernel can be resident on this device)
+cudaError_t launch_kl_rows_grid(const RowsParams& p, bool bf16, int sms, cudaStream_t stream, bool probe_only);
+
 // kl_rows_up.cu
 cudaError_t launch_kl_rows_up(const UpParams& p, bool bf16, int sms, cudaStream_t stream);
 cudaError_t launch_kl_pixels_up(const UpParams& p, bool bf16, int sms, cudaStream_t stream);   // p.part: [kMaxGrid] CTA partials

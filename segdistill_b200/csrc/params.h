@@ -20,7 +20,10 @@ constexpr int kGenericChunk = 4096;  // elements of one channel plane per generi
 constexpr int kPartWords = 8;        // floats per published unit partial (generic kernels)
 constexpr int kMaxLosses = 2;        // softmax-KL losses fused over one (S, T) pair in one pass
 constexpr int kPktWords = 16;        // 8-byte {value, epoch} words per unit packet (6 per loss, padded)
-constexpr int kChunkCapMin = 7168;   // smallest chunk capacity of the TMA kernels (streaming kernel: 448 x 16)
+constexpr int kChunkCapMin = 4096;   // smallest unit of the TMA kernels (grid-resident kernel: one 4096-element chunk)
+constexpr int kGridChunkElems = 4096;     // grid-resident kernel (kl_rows_grid.cu): elements per chunk and tensor ...
+constexpr int kGridUnitMaxChunks = 4;     // ... and chunks per unit at most (two units must fit the 8 TMEM chunk slots)
+constexpr int kGridMaxRowUnits = 64;      // ... units of the longest row of any fused loss (two packets per lane of the stats warp)
 
 // one softmax-KL loss over rows of `g` consecutive (gathered) channels x HW
 struct RowLoss {
@@ -59,6 +62,12 @@ struct RowsParams {
     long long total_units;
     int max_row_units;    // units of the longest row of any fused loss
     int delay;            // streaming kernel: phase 2 trails phase 1 by this many units
+    // grid-resident kernel: units [0, units_coarse) are cut as above (chunk_elems ...), the rest - rows from row split_row of
+    // l[0] in sample split_b on - into finer units
+    long long units_coarse;
+    int split_b, split_row;
+    int f_chunk_elems, f_nch_full, f_nch_last, f_units_per_sample;
+    int grid_knobs[4];    // grid-resident kernel: active gather warps, sleep (ns) of the waits for row statistics / ring slots / packets
     // packed short rows (kl_rows_pack_kernel): a unit is pack_rows whole rows, pack_tpr threads each
     int pack_tpr;         // threads per row (8..256, power of two); row length = 32 * pack_tpr
     int pack_rows;        // rows per unit = 512 / pack_tpr
@@ -74,6 +83,7 @@ struct RowsParams {
     float* cta_part;            // [kMaxLosses + 1][kMaxGrid]
     unsigned long long* pkt;    // [TMA units][kPktWords]
     float* unit_part;           // [generic units][kPartWords]
+    unsigned long long* dbg;    // timing builds (-DSD_GRID_TIMING): 16 counters per CTA, in the row_kl region of the workspace
 };
 
 inline long long tma_units_upper(long long B, long long C, long long HW, long long g) {

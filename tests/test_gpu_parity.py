@@ -45,6 +45,17 @@ def _run(crit, s_cpu, t_cpu, gt_hw=None, n_iter=1, algo='auto', seed=None):
     return loss.detach().float().cpu().item(), s.grad.detach().float().cpu()
 
 
+def _run_forced(crit, s_cpu, t_cpu, gt_hw=None, n_iter=1, algo='auto', seed=None):
+    """_run with a forced kernel; the grid-resident kernel answers SD_ERR_UNSUPPORTED for layouts it does not take
+    (rows of more than 64 units, HW % 128 != 0, channel shuffle, ...): those cases are skipped for it."""
+    try:
+        return _run(crit, s_cpu, t_cpu, gt_hw, n_iter, algo, seed)
+    except _cabi.SegDistillUnsupported:
+        if algo != 'grid':
+            raise
+        pytest.skip('the grid-resident kernel does not take this layout')
+
+
 def _assert_close(loss, grad, ref_loss, ref_grad, loss_rtol=LOSS_RTOL, grad_rtol=GRAD_RTOL):
     assert rel_err(loss, ref_loss) <= loss_rtol, (loss, ref_loss)
     ref_grad = torch.as_tensor(ref_grad, dtype=torch.float32)
@@ -92,7 +103,7 @@ def _check_near(loss, grad, f64_loss, f64_grad, tol=1e-4, gtol=1e-4):
     assert np.abs(grad.double().numpy() - f64_grad).max() <= gtol * np.abs(f64_grad).max()
 
 
-@pytest.mark.parametrize('algo', ['tma', 'rows1', 'stream', 'cluster', 'generic'])
+@pytest.mark.parametrize('algo', ['tma', 'rows1', 'stream', 'cluster', 'grid', 'generic'])
 @pytest.mark.parametrize('shape,g,tau,offset', [((2, 150, 64, 64), 1, 1.0, 0.0), ((2, 150, 64, 64), 10, 2.0, 0.0),
                                                 ((1, 20, 128, 128), 10, 2.0, 0.0), ((2, 7, 96, 96), 3, 4.0, 0.5),
                                                 ((4, 64, 16, 16), 1, 1.0, -2.0), ((1, 150, 32, 32), 150, 3.0, 0.0)])
@@ -135,7 +146,7 @@ def test_near_converged_behind_the_fused_resize(cls, kw, shape, scale):
     _check_near(loss, grad, ref.item(), x.grad.numpy(), tol=2e-4)
 
 
-@pytest.mark.parametrize('pair_algo', ['cluster', 'stream'], indirect=True)
+@pytest.mark.parametrize('pair_algo', ['grid', 'cluster', 'stream'], indirect=True)
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_near_converged_two_losses_one_launch(pair_algo, dtype):
     shape = (2, 150, 64, 64)
@@ -146,7 +157,7 @@ def test_near_converged_two_losses_one_launch(pair_algo, dtype):
     x = s.to(dev()).requires_grad_(True)
     tg = t.to(dev())
     la, lb = sd.KLDLoss.run_pair(sd.CGDLoss(**ka).plan(x, tg, None, 1), sd.CGDLoss(**kb).plan(x, tg, None, 1))
-    assert _cabi.last_kernel() == f'kl_rows_{pair_algo}_kernel(2 losses)'
+    _expect_pair_kernel(pair_algo)
     (la + lb).backward()
     torch.cuda.synchronize()
     assert rel_err(la.item(), fa[0]) <= 1e-4 and rel_err(lb.item(), fb[0]) <= 1e-4
@@ -198,6 +209,25 @@ def test_cluster_resident_rows(g, shape, dtype):
     ref = _oracle_run('CGDLoss', kw, s, t, shape[2:], 1)
     got = _run(sd.CGDLoss(**kw), s, t, shape[2:], 1, 'cluster')
     assert _cabi.last_kernel() in ('kl_rows_cluster_kernel', 'scale_grad_kernel')
+    if dtype == torch.bfloat16:
+        _assert_close(*got, *ref, loss_rtol=2e-5, grad_rtol=BF16_GRAD_RTOL)
+    else:
+        _assert_close(*got, *ref)
+
+
+@pytest.mark.parametrize('g,shape', [(1, CFG1), (3, CFG1), (10, CFG1), (30, CFG1), (10, (1, 25, 128, 128)), (3, (2, 7, 96, 96)),
+                                     (5, (3, 12, 80, 80)), (1, (3, 5, 128, 128)), (2, (1, 9, 48, 48)), (4, (2, 10, 16, 32)),
+                                     (10, (5, 150, 128, 128))])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_grid_resident_rows(g, shape, dtype):
+    """Rows spread over the cooperative grid, parked in tensor memory, statistics exchanged as packets through L2
+    (kl_rows_grid.cu): rows of one unit and of many, complete and ragged groups (25 % 10, 7 % 3, 9 % 2 != 0), units that
+    end inside a chunk (96x96, 80x80, 48x48, 16x32), more units than SMs (5x150x128x128: 1500)."""
+    s, t = seeded_pair(shape, seed=g, dtype=dtype)
+    kw = dict(group_size=g, alpha=3, tau=2)
+    ref = _oracle_run('CGDLoss', kw, s, t, shape[2:], 1)
+    got = _run(sd.CGDLoss(**kw), s, t, shape[2:], 1, 'grid')
+    assert _cabi.last_kernel() in ('kl_rows_grid_kernel', 'scale_grad_kernel')
     if dtype == torch.bfloat16:
         _assert_close(*got, *ref, loss_rtol=2e-5, grad_rtol=BF16_GRAD_RTOL)
     else:
@@ -418,6 +448,14 @@ PAIR_CASES = [
 ]
 
 
+def _expect_pair_kernel(pair_algo):
+    """The forced two-loss kernel ran (run_pair falls back to two launches when the library declines a layout: the
+    grid-resident kernel does for rows of more than 64 units - such a case is skipped for it)."""
+    if pair_algo == 'grid' and _cabi.last_kernel() != 'kl_rows_grid_kernel(2 losses)':
+        pytest.skip('the grid-resident kernel does not take this layout')
+    assert _cabi.last_kernel() == f'kl_rows_{pair_algo}_kernel(2 losses)'
+
+
 @pytest.fixture
 def pair_algo(request):
     SF.PAIR_ALGO = request.param
@@ -425,7 +463,7 @@ def pair_algo(request):
     SF.PAIR_ALGO = 'auto'
 
 
-@pytest.mark.parametrize('pair_algo', ['cluster', 'stream'], indirect=True)
+@pytest.mark.parametrize('pair_algo', ['grid', 'cluster', 'stream'], indirect=True)
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('case', range(len(PAIR_CASES)))
 def test_two_losses_one_launch(case, dtype, pair_algo):
@@ -439,7 +477,7 @@ def test_two_losses_one_launch(case, dtype, pair_algo):
     pa, pb = ca.plan(x, tg, None, 1), cb.plan(x, tg, None, 1)
     assert sd.KLDLoss.can_fuse(pa, pb)
     la, lb = sd.KLDLoss.run_pair(pa, pb)
-    assert _cabi.last_kernel() == f'kl_rows_{pair_algo}_kernel(2 losses)'
+    _expect_pair_kernel(pair_algo)
     (la + lb).backward()
     torch.cuda.synchronize()
     assert _cabi.workspace_error_flag() == 0
@@ -449,7 +487,7 @@ def test_two_losses_one_launch(case, dtype, pair_algo):
     _assert_close(la.item() + lb.item(), x.grad.float().cpu(), ra[0] + rb[0], ra[1] + rb[1], loss_rtol=lt, grad_rtol=gt_)
 
 
-@pytest.mark.parametrize('pair_algo', ['cluster', 'stream'], indirect=True)
+@pytest.mark.parametrize('pair_algo', ['grid', 'cluster', 'stream'], indirect=True)
 @pytest.mark.parametrize('w', [(512.0, 512.0), (2.0, 5.0), (1.0, 0.0)])
 def test_two_losses_upstream_gradients(w, pair_algo):
     """Equal upstream gradients scale dS in place; different ones trigger the conditional re-run."""
@@ -479,7 +517,7 @@ def test_dispatcher_batches_entries_on_the_same_tensors():
     before = _cabi.launch_count()
     out = d({'decode_head.linear_pred': x, 'decode_head': x}, {'decode_head.linear_pred': tg, 'decode_head': tg},
             gt, 1, None, None)
-    assert _cabi.launch_count() - before == 1 and _cabi.last_kernel() == 'kl_rows_cluster_kernel(2 losses)'
+    assert _cabi.launch_count() - before == 1 and _cabi.last_kernel() in ('kl_rows_grid_kernel(2 losses)', 'kl_rows_cluster_kernel(2 losses)')
     assert list(out) == ['loss_decode_head.linear_pred<->decode_head.linear_pred_other',
                          'loss_decode_head<->decode_head_other']
     sum(out.values()).backward()
@@ -1012,7 +1050,7 @@ def test_full_size_two_loss_launch_against_the_oracle(dtype):
     x = s.to(dev()).requires_grad_(True)
     tg = t.to(dev())
     la, lb = sd.KLDLoss.run_pair(sd.CDLoss().plan(x, tg, None, 1), sd.CGDLoss().plan(x, tg, None, 1))
-    assert _cabi.last_kernel() == 'kl_rows_cluster_kernel(2 losses)'
+    assert _cabi.last_kernel() in ('kl_rows_grid_kernel(2 losses)', 'kl_rows_cluster_kernel(2 losses)')
     (la + lb).backward()
     torch.cuda.synchronize()
     lt = 2e-5 if dtype == torch.bfloat16 else LOSS_RTOL
