@@ -194,11 +194,55 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
     if (tid == 0) p.dbg[blockIdx.x * 16 + 11] = global_ns();
 #endif
 
-    if (tid == 0) {
-        for (int c = 0; c < kGRing; ++c) {
-            mbar_init(&sm.full[c], 1);
-            mbar_init(&sm.empty[c], kGParkWarps);
+    const int grid = (int)gridDim.x;
+    const int n_units = blockIdx.x < p.total_units ? (int)((p.total_units - blockIdx.x + grid - 1) / grid) : 0;
+
+    // ---- prologue.  The TMA warp sets up the ring's barriers itself and has the first chunks on their way before the
+    //      rest of the CTA is set up (barriers of the other hand-offs, tensor-memory allocation).
+    struct Stream {                  // the TMA warp's position in the CTA's work list (identical in every lane)
+        int slot;
+        uint32_t phase;
+        int jt, c;                   // unit being streamed and its chunk
+        size_t base;                 // first element of that unit
+        int nvs;                     // its length in vectors
+    } ts_ = {0, 0u, 0, 0, 0, 0};
+    const uint64_t pol = l2_policy_evict_first();
+    auto stream_unit = [&](int j) {
+        const GUnit x = grid_decode(p, (long long)blockIdx.x + (long long)j * grid);
+        ts_.base = ((size_t)x.b * p.C + (size_t)x.grp * p.l[0].g) * p.HW + (size_t)x.e0;
+        ts_.nvs = x.len / VE;
+    };
+    // the next chunk of the work list into ring slot ts_.slot (the caller knows it is free)
+    auto stream_chunk = [&]() {
+        if (lane == 0) {
+            const int nv = min(kGChunkVecs, ts_.nvs - ts_.c * kGChunkVecs);
+            const uint32_t bytes = (uint32_t)nv * (uint32_t)sizeof(vec_t);
+            mbar_arrive_expect_tx(&sm.full[ts_.slot], 2u * bytes);
+            const size_t off = (ts_.base + (size_t)ts_.c * kGChunkVecs * VE) * sizeof(T);
+            tma_bulk_g2s(sm.ring[ts_.slot][0], static_cast<const char*>(p.S) + off, bytes, &sm.full[ts_.slot], pol);
+            tma_bulk_g2s(sm.ring[ts_.slot][1], static_cast<const char*>(p.T) + off, bytes, &sm.full[ts_.slot], pol);
         }
+        if (++ts_.slot == kGRing) {
+            ts_.slot = 0;
+            ts_.phase ^= 1u;
+        }
+        if (++ts_.c * kGChunkVecs >= ts_.nvs) {
+            ts_.c = 0;
+            if (++ts_.jt < n_units) stream_unit(ts_.jt);
+        }
+    };
+    if (warp == kGTmaWarp) {
+        if (lane == 0) {
+            for (int c = 0; c < kGRing; ++c) {
+                mbar_init(&sm.full[c], 1);
+                mbar_init(&sm.empty[c], kGParkWarps);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        if (n_units > 0) stream_unit(0);
+        for (int i = 0; i < kGRing && ts_.jt < n_units; ++i) stream_chunk();     // every slot is free
+    } else if (tid == 0) {
         for (int q = 0; q < kGDepth; ++q) {
             mbar_init(&sm.recbar[q], kGParkWarps);
             mbar_init(&sm.finbar[q], 1);
@@ -206,15 +250,13 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
         for (int w = 0; w < kGParkWarps; ++w)
             for (int q = 0; q < kGSlots; ++q) mbar_init(&sm.tfree[w][q], 1);
         fence_barrier_init();
+    } else if (warp == kGTmaWarp + 1) {
+        tmem_alloc(&sm.tmem_base, kGTmemCols);       // (gather warp 0 also frees it)
     }
-    if (warp == kGTmaWarp) tmem_alloc(&sm.tmem_base, kGTmemCols);
     tmem_fence_before_sync();
     __syncthreads();
     tmem_fence_after_sync();
     const uint32_t tmem_base = sm.tmem_base;
-
-    const int grid = (int)gridDim.x;
-    const int n_units = blockIdx.x < p.total_units ? (int)((p.total_units - blockIdx.x + grid - 1) / grid) : 0;
 
     float c2[NL];
 #pragma unroll
@@ -231,47 +273,15 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
         // tag of this launch's packets: the workspace's launch counter (bumped by the last CTA to finish, i.e. after
         // every CTA has read it) + 1, so a packet left by any earlier launch never validates
         const unsigned long long tag = (unsigned long long)(__ldcg(&p.ctrl[2]) + 1u) << 32;
-        const uint64_t pol = l2_policy_evict_first();
-        int slot = 0;
-        uint32_t phase = 0;
-        int jt = 0, c = 0, jp = 0;  // unit being streamed and its chunk, unit to publish next
-        size_t base = 0;
-        int nvs = 0;
-        if (n_units > 0) {
-            const GUnit x = grid_decode(p, blockIdx.x);
-            base = ((size_t)x.b * p.C + (size_t)x.grp * p.l[0].g) * p.HW + (size_t)x.e0;
-            nvs = x.len / VE;
-        }
+        int jp = 0;                 // unit to publish next
         while (jp < n_units) {
             int ev = 0;
             if (lane == 0) {
-                if (jt < n_units && mbar_try_wait(&sm.empty[slot], phase ^ 1u)) ev |= 1;
+                if (ts_.jt < n_units && mbar_try_wait(&sm.empty[ts_.slot], ts_.phase ^ 1u)) ev |= 1;
                 if (mbar_try_wait(&sm.recbar[jp & (kGDepth - 1)], (uint32_t)(jp >> 3) & 1u)) ev |= 2;
             }
             ev = __shfl_sync(0xffffffffu, ev, 0);
-            if (ev & 1) {
-                if (lane == 0) {
-                    const int nv = min(kGChunkVecs, nvs - c * kGChunkVecs);
-                    const uint32_t bytes = (uint32_t)nv * (uint32_t)sizeof(vec_t);
-                    mbar_arrive_expect_tx(&sm.full[slot], 2u * bytes);
-                    const size_t off = (base + (size_t)c * kGChunkVecs * VE) * sizeof(T);
-                    tma_bulk_g2s(sm.ring[slot][0], static_cast<const char*>(p.S) + off, bytes, &sm.full[slot], pol);
-                    tma_bulk_g2s(sm.ring[slot][1], static_cast<const char*>(p.T) + off, bytes, &sm.full[slot], pol);
-                }
-                if (++slot == kGRing) {
-                    slot = 0;
-                    phase ^= 1u;
-                }
-                if (++c * kGChunkVecs >= nvs) {
-                    c = 0;
-                    ++jt;
-                    if (jt < n_units) {
-                        const GUnit x = grid_decode(p, (long long)blockIdx.x + (long long)jt * grid);
-                        base = ((size_t)x.b * p.C + (size_t)x.grp * p.l[0].g) * p.HW + (size_t)x.e0;
-                        nvs = x.len / VE;
-                    }
-                }
-            }
+            if (ev & 1) stream_chunk();
             if (ev & 2) {
                 const float4* q = reinterpret_cast<const float4*>(sm.rec[jp & (kGDepth - 1)][lane & 7]);
                 PStat<NL> st = pstat_from<NL>(q[0], q[1], NL == 2 ? q[2] : make_float4(0.f, 0.f, 0.f, 0.f));
@@ -295,9 +305,7 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
             }
             if (ev == 0) __nanosleep(ns_tma);
         }
-        // TMEM is released after every consumer of this CTA is through with it
         bar_sync(3, kGThreads);
-        tmem_dealloc(tmem_base, kGTmemCols);
         return;
     }
 
@@ -481,9 +489,10 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
 #pragma unroll
             for (int k = 0; k < NL; ++k) sm.klpart[gw][k] = kl_acc[k];
         }
-        // every consumer is through with TMEM (the TMA warp frees it); every gather warp's partial is written
+        // every consumer is through with TMEM (gather warp 0 frees it); every gather warp's partial is written
         bar_sync(3, kGThreads);
         if (gw != 0) return;
+        tmem_dealloc(tmem_base, kGTmemCols);
 #ifdef SD_GRID_TIMING
         if (lane == 0) p.dbg[blockIdx.x * 16 + 15] = global_ns();
 #endif
@@ -823,7 +832,7 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
         }
 #endif
     }
-    // every consumer is through with TMEM (the TMA warp frees it)
+    // every consumer is through with TMEM (gather warp 0 frees it)
     bar_sync(3, kGThreads);
 }
 
