@@ -103,26 +103,28 @@ struct GUnit {
     int e0, len;           // first element within the row, elements
     bool fine;
 };
-__device__ __forceinline__ GUnit grid_decode(const RowsParams& p, long long u) {
+__device__ __forceinline__ GUnit grid_decode(const RowsParams& p, long long u64) {
+    // (cabi.cu: fewer than 2^31 units - 32-bit divisions)
     GUnit x;
-    x.fine = u >= p.units_coarse;
+    const unsigned u = (unsigned)u64, uc = (unsigned)p.units_coarse;
+    x.fine = u >= uc;
     const GridRegion g = grid_region(p, x.fine);
     int r;
     if (!x.fine) {
-        x.b = (int)(u / g.ups);
-        r = (int)(u - (long long)x.b * g.ups);
+        x.b = (int)(u / (unsigned)g.ups);
+        r = (int)(u - (unsigned)x.b * (unsigned)g.ups);
     } else {
-        long long v = u - p.units_coarse;
+        unsigned v = u - uc;
         const int first = grid_unit_start(p, g, p.split_row);   // the fine units of sample split_b start here
-        const int part = g.ups - first;
+        const unsigned part = (unsigned)(g.ups - first);
         if (v < part) {
             x.b = p.split_b;
             r = first + (int)v;
         } else {
             v -= part;
-            const int q = (int)(v / g.ups);
-            x.b = p.split_b + 1 + q;
-            r = (int)(v - (long long)q * g.ups);
+            const unsigned q = v / (unsigned)g.ups;
+            x.b = p.split_b + 1 + (int)q;
+            r = (int)(v - q * (unsigned)g.ups);
         }
     }
     x.r = r;
