@@ -279,8 +279,8 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
         while (jp < n_units) {
             int ev = 0;
             if (lane == 0) {
-                if (ts_.jt < n_units && mbar_try_wait(&sm.empty[ts_.slot], ts_.phase ^ 1u)) ev |= 1;
-                if (mbar_try_wait(&sm.recbar[jp & (kGDepth - 1)], (uint32_t)(jp >> 3) & 1u)) ev |= 2;
+                if (ts_.jt < n_units && mbar_test_wait(&sm.empty[ts_.slot], ts_.phase ^ 1u)) ev |= 1;
+                if (mbar_test_wait(&sm.recbar[jp & (kGDepth - 1)], (uint32_t)(jp >> 3) & 1u)) ev |= 2;
             }
             ev = __shfl_sync(0xffffffffu, ev, 0);
             if (ev & 1) stream_chunk();
@@ -486,18 +486,17 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
 #ifdef SD_GRID_TIMING
         if (gw == 0 && lane == 0) GT_OUT(5, 6);
 #endif
-        // ---- loss: this CTA's partial = the gather warps' sums in warp order; the last CTA sums the partials in a fixed order
+        // ---- loss: this CTA's partial = the gather warps' sums in warp order; the last CTA sums the partials in a fixed
+        //      order.  All of it happens while the gradient warps are still busy with the last unit.
         if (lane == 0) {
 #pragma unroll
             for (int k = 0; k < NL; ++k) sm.klpart[gw][k] = kl_acc[k];
         }
-        // every consumer is through with TMEM (gather warp 0 frees it); every gather warp's partial is written
-        bar_sync(3, kGThreads);
-        if (gw != 0) return;
-        tmem_dealloc(tmem_base, kGTmemCols);
-#ifdef SD_GRID_TIMING
-        if (lane == 0) p.dbg[blockIdx.x * 16 + 15] = global_ns();
-#endif
+        bar_sync(4, 32 * kGGatherWarps);        // every gather warp's partial is written
+        if (gw != 0) {
+            bar_sync(3, kGThreads);
+            return;
+        }
         unsigned ticket = 0;
         if (lane == 0) {
 #pragma unroll
@@ -534,6 +533,12 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
                 atomicExch(&p.ctrl[0], 0u);
             }
         }
+        // every consumer is through with TMEM: this warp allocated it, this warp frees it
+        bar_sync(3, kGThreads);
+        tmem_dealloc(tmem_base, kGTmemCols);
+#ifdef SD_GRID_TIMING
+        if (lane == 0) p.dbg[blockIdx.x * 16 + 15] = global_ns();
+#endif
         return;
     }
 
