@@ -1,6 +1,6 @@
 #!/bin/bash
-# End-of-round record on the GPU box: tests, smoke, both bench arms, --extra, kernel table, ncu launch list,
-# memcheck of the IFVD tests and one full ncu capture of the IFVD class-sum kernel.  Everything lands in gpurun_out/.
+# End-of-round record on the GPU box: tests, smoke, both bench arms, --extra, kernel table, ncu launch list and one
+# full ncu capture of the dominant kernel inside the bench command.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,driver_version --format=csv,noheader > gpurun_out/gpu.txt
 python -m pytest tests -m gpu -x -q > gpurun_out/tests.log 2>&1; echo "tests rc=$?" > gpurun_out/summary.txt
@@ -11,9 +11,7 @@ python bench.py --extra > gpurun_out/bench_extra.log 2> /dev/null
 python scripts/kbench.py > gpurun_out/kbench.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 > gpurun_out/launches_run.log 2>&1
-timeout 300 compute-sanitizer --tool memcheck python -m pytest tests -m gpu -x -q -k ifvd > gpurun_out/memcheck_ifvd.log 2>&1
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:ifvd_class_sums -c 2 -f -o gpurun_out/prof_ifvd_sums \
-    python scripts/kbench.py --iters 1 --only ifvd_sim_2x150x128_f32 > gpurun_out/ncu_ifvd.log 2>&1
-tail -2 gpurun_out/tests.log; cat gpurun_out/summary.txt; tail -4 gpurun_out/memcheck_ifvd.log
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:kl_rows_grid -s 3 -c 1 -f -o gpurun_out/prof_bench_r02 \
+    python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e > gpurun_out/ncu_bench.log 2>&1
+tail -2 gpurun_out/tests.log; cat gpurun_out/summary.txt
 tail -1 gpurun_out/bench.log | cut -c1-300
-grep ifvd gpurun_out/kbench.log
