@@ -180,6 +180,11 @@ bool grid_fine_tail() {
     }
     return v != 0;
 }
+// SEGDISTILL_GROUP_GRID=0: launches over several pairs keep the two-phase kernel (A-B knob, tests of that kernel)
+bool group_prefers_grid() {
+    const char* e = std::getenv("SEGDISTILL_GROUP_GRID");
+    return e ? (std::atoi(e) != 0) : true;
+}
 bool prefer_grid() {
     static int v = -1;
     if (v < 0) {
@@ -641,6 +646,40 @@ int sd_kl_rows_group_fwd_bwd(int n_pairs, const void* const* S, const void* cons
     gp.ctrl = reinterpret_cast<unsigned*>(ws + wl.off_ctrl);
     gp.cta_part = reinterpret_cast<float*>(ws + wl.off_cta);
     gp.pkt = reinterpret_cast<unsigned long long*>(ws + wl.off_pkt);
+
+    // The grid-resident kernel (kl_rows_grid.cu: every pair's units parked in tensor memory, one pass over HBM) takes
+    // the work list when every map has HW % 128 == 0 and no row spans more than 64 units (of up to 4 chunks of 4096
+    // elements) or more than the grid holds; it needs no more packets than the two-phase kernel's work list has.
+    if (group_prefers_grid()) {
+        sd::GroupParams gg = gp;
+        const int uc = grid_unit_chunks();
+        const long long cap = (long long)uc * sd::kGridChunkElems;
+        long long gtotal = 0, gmax = 1;
+        bool ok = true;
+        for (int k = 0; k < n_pairs && ok; ++k) {
+            sd::GroupSeg& s = gg.seg[k];
+            const long long row_len = (long long)s.g * s.HW;
+            ok = s.HW % 128 == 0;
+            s.chunk_elems = (int)cap;
+            s.nch_full = s.G_full > 0 ? (int)((row_len + cap - 1) / cap) : 1;
+            s.nch_last = s.g_last ? (int)(((long long)s.g_last * s.HW + cap - 1) / cap) : 0;
+            s.units_per_sample = s.G_full * s.nch_full + s.nch_last;
+            s.unit0 = gtotal;
+            gtotal += (long long)s.B * s.units_per_sample;
+            gmax = std::max<long long>(gmax, std::max(s.G_full > 0 ? s.nch_full : 0, s.nch_last));
+        }
+        const long long grid = std::min<long long>(std::min<long long>(dev.sms, gtotal), sd::kMaxGrid);
+        if (ok && gtotal <= total && gmax <= sd::kGridMaxRowUnits && gmax <= grid) {
+            gg.total_units = gtotal;
+            cudaError_t e = sd::launch_kl_rows_grid_group(gg, (int)gmax, grid_knobs(), dtype == SD_BF16, dev.sms,
+                                                          static_cast<cudaStream_t>(stream), false);
+            if (e != cudaErrorLaunchOutOfResources) {
+                g_launches += 1;
+                t_last_kernel = "kl_rows_grid_kernel(group)";
+                return e == cudaSuccess ? SD_OK : (int)e;
+            }
+        }
+    }
     cudaError_t e = sd::launch_kl_rows_group(gp, max_row_units, dtype == SD_BF16, dev.sms, static_cast<cudaStream_t>(stream));
     g_launches += 1;
     t_last_kernel = "kl_rows_group_kernel";

@@ -61,6 +61,7 @@ struct GridSmem {
     float fin[kGDepth][2][4];                             // {Ms, Mt, coef/Zs, coef/Zt} of the unit's row of l[0], of l[1]
     float refs[kGParkWarps][kGSlots][2];                  // references {ms, mt} a parked chunk was taken against
     float klpart[kGGatherWarps][kMaxLosses];              // KL sums of the gather warps
+    float klseg[kGGatherWarps][kMaxSegs];                 // ... per pair (launches over several pairs)
 #ifdef SD_GRID_TIMING
     long long stamp[kGDepth];                             // clock at which park warp 0 finished the unit
 #endif
@@ -153,6 +154,42 @@ __device__ __forceinline__ long long grid_unit_index(const RowsParams& p, const 
     return p.units_coarse + (g.ups - first) + (long long)(b - p.split_b - 1) * g.ups + r;
 }
 
+
+// ---------------------------------------------------------------- several (student, teacher) pairs, one work list
+// MULTI launches (sd_kl_rows_group_fwd_bwd): one loss per pair, every pair cut into coarse units only; the units of
+// pair k are [seg[k].unit0, seg[k + 1].unit0).  `seg` = index of the pair.
+__device__ __forceinline__ GUnit grid_decode_multi(const GroupParams& gp, long long u64, int& seg) {
+    const unsigned u = (unsigned)u64;
+    int k = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxSegs; ++i)
+        if (i < gp.nseg && u >= (unsigned)gp.seg[i].unit0) k = i;
+    seg = k;
+    const GroupSeg& sg = gp.seg[k];
+    const unsigned v = u - (unsigned)sg.unit0;
+    GUnit x;
+    x.fine = false;
+    x.b = (int)(v / (unsigned)sg.units_per_sample);
+    const int r = (int)(v - (unsigned)x.b * (unsigned)sg.units_per_sample);
+    x.r = r;
+    const int full_units = sg.G_full * sg.nch_full;
+    int g_real;
+    if (r < full_units) {
+        x.grp = sg.nch_full == 1 ? r : r / sg.nch_full;
+        x.ck = r - x.grp * sg.nch_full;
+        x.nch = sg.nch_full;
+        g_real = sg.g;
+    } else {
+        x.grp = sg.G_full;
+        x.ck = r - full_units;
+        x.nch = sg.nch_last;
+        g_real = sg.g_last;
+    }
+    x.e0 = x.ck * sg.chunk_elems;
+    x.len = min(sg.chunk_elems, g_real * sg.HW - x.e0);
+    return x;
+}
+
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -175,8 +212,9 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // With one loss, or with R == 2, phase 1 parks the EXPONENTIALS (relative to the warp's running maximum at that
 // moment, kept in shared memory): phase 2 is then a multiply-add per element, no ex2.  Otherwise the raw values are
 // parked and phase 2 recomputes.
-template <typename T, int NL, int R>
-__global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsParams p) {
+template <typename T, int NL, int R, bool MULTI>
+__global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsParams p, const GroupParams gp) {
+    static_assert(!MULTI || (NL == 1 && R == 0), "several pairs: one loss each");
     using V = Vec4<T>;
     using vec_t = typename V::type;
     constexpr int VE = 4;
@@ -199,6 +237,17 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
     const int grid = (int)gridDim.x;
     const int n_units = blockIdx.x < p.total_units ? (int)((p.total_units - blockIdx.x + grid - 1) / grid) : 0;
 
+    // a unit of the work list, the pair it belongs to, where it starts in that pair's tensors
+    auto unit_at = [&](long long u, int& seg) {
+        if (MULTI) return grid_decode_multi(gp, u, seg);
+        seg = 0;
+        return grid_decode(p, u);
+    };
+    auto elem_base = [&](const GUnit& x, int seg) {
+        if (MULTI) return ((size_t)x.b * gp.seg[seg].C + (size_t)x.grp * gp.seg[seg].g) * gp.seg[seg].HW + (size_t)x.e0;
+        return ((size_t)x.b * p.C + (size_t)x.grp * p.l[0].g) * p.HW + (size_t)x.e0;
+    };
+
     // ---- prologue.  The TMA warp sets up the ring's barriers itself and has the first chunks on their way before the
     //      rest of the CTA is set up (barriers of the other hand-offs, tensor-memory allocation).
     struct Stream {                  // the TMA warp's position in the CTA's work list (identical in every lane)
@@ -207,12 +256,19 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
         int jt, c;                   // unit being streamed and its chunk
         size_t base;                 // first element of that unit
         int nvs;                     // its length in vectors
-    } ts_ = {0, 0u, 0, 0, 0, 0};
+        const char* pS;              // the pair's tensors
+        const char* pT;
+    } ts_ = {0, 0u, 0, 0, 0, 0, static_cast<const char*>(p.S), static_cast<const char*>(p.T)};
     const uint64_t pol = l2_policy_evict_first();
     auto stream_unit = [&](int j) {
-        const GUnit x = grid_decode(p, (long long)blockIdx.x + (long long)j * grid);
-        ts_.base = ((size_t)x.b * p.C + (size_t)x.grp * p.l[0].g) * p.HW + (size_t)x.e0;
+        int seg;
+        const GUnit x = unit_at((long long)blockIdx.x + (long long)j * grid, seg);
+        ts_.base = elem_base(x, seg);
         ts_.nvs = x.len / VE;
+        if (MULTI) {
+            ts_.pS = static_cast<const char*>(gp.seg[seg].S);
+            ts_.pT = static_cast<const char*>(gp.seg[seg].T);
+        }
     };
     // the next chunk of the work list into ring slot ts_.slot (the caller knows it is free)
     auto stream_chunk = [&]() {
@@ -221,8 +277,8 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
             const uint32_t bytes = (uint32_t)nv * (uint32_t)sizeof(vec_t);
             mbar_arrive_expect_tx(&sm.full[ts_.slot], 2u * bytes);
             const size_t off = (ts_.base + (size_t)ts_.c * kGChunkVecs * VE) * sizeof(T);
-            tma_bulk_g2s(sm.ring[ts_.slot][0], static_cast<const char*>(p.S) + off, bytes, &sm.full[ts_.slot], pol);
-            tma_bulk_g2s(sm.ring[ts_.slot][1], static_cast<const char*>(p.T) + off, bytes, &sm.full[ts_.slot], pol);
+            tma_bulk_g2s(sm.ring[ts_.slot][0], ts_.pS + off, bytes, &sm.full[ts_.slot], pol);
+            tma_bulk_g2s(sm.ring[ts_.slot][1], ts_.pT + off, bytes, &sm.full[ts_.slot], pol);
         }
         if (++ts_.slot == kGRing) {
             ts_.slot = 0;
@@ -262,7 +318,7 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
 
     float c2[NL];
 #pragma unroll
-    for (int k = 0; k < NL; ++k) c2[k] = p.l[k].c2;
+    for (int k = 0; k < NL; ++k) c2[k] = MULTI ? gp.seg[0].c2 : p.l[k].c2;      // (MULTI: set per unit)
     const int n_gather = p.grid_knobs[0];          // active gather warps (1 .. kGGatherWarps)
     const unsigned ns_fin = (unsigned)p.grid_knobs[1], ns_tma = (unsigned)p.grid_knobs[2], ns_stat = (unsigned)p.grid_knobs[3];
 
@@ -285,6 +341,11 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
             ev = __shfl_sync(0xffffffffu, ev, 0);
             if (ev & 1) stream_chunk();
             if (ev & 2) {
+                if (MULTI) {
+                    int seg;
+                    unit_at((long long)blockIdx.x + (long long)jp * grid, seg);
+                    c2[0] = gp.seg[seg].c2;
+                }
                 const float4* q = reinterpret_cast<const float4*>(sm.rec[jp & (kGDepth - 1)][lane & 7]);
                 PStat<NL> st = pstat_from<NL>(q[0], q[1], NL == 2 ? q[2] : make_float4(0.f, 0.f, 0.f, 0.f));
                 st = pstat_reduce<NL, R, 8>(st, c2);
@@ -326,13 +387,24 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
             coef[k] = p.l[k].coef;
             if (p.grad_out[k] != nullptr) coef[k] *= __ldg(p.grad_out[k]);
         }
+        float gscale = 1.f;        // MULTI: d(total)/d(losses), one scalar for the launch
+        if (MULTI) {
+            if (gp.grad_out != nullptr) gscale = __ldg(gp.grad_out);
+            if (lane < kMaxSegs) sm.klseg[gw][lane] = 0.f;
+            __syncwarp();
+        }
         GT_DECL(6);
         for (int j = gw < n_gather ? gw : n_units; j < n_units; j += n_gather) {
             // ---- the packets of the row-mates of unit j: units [rowu, rowu + rown); its row of l[0] is the mates
             //      [i0, i0 + n0)
             const long long u = (long long)blockIdx.x + (long long)j * grid;
-            const GUnit x = grid_decode(p, u);
+            int seg;
+            const GUnit x = unit_at(u, seg);
             const GridRegion rg = grid_region(p, x.fine);
+            if (MULTI) {
+                c2[0] = gp.seg[seg].c2;
+                coef[0] = gp.seg[seg].coef * gscale;
+            }
             long long rowu;
             int rown, i0, n0, rk = 0;
             if (NL == 2) {
@@ -467,8 +539,13 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
                 if (lane == 0) {
                     if (own0) {
                         const float kl = kl_of_row(NL == 2 && R == 2 ? 2.f : 1.f, pr.zs[0], pr.zt[0], pr.a[0], pr.dd[0]);
-                        if (p.l[0].row_kl) p.l[0].row_kl[x.b * p.l[0].G + x.grp] = kl;
-                        kl_acc[0] += kl;
+                        if (MULTI) {
+                            if (gp.seg[seg].row_kl) gp.seg[seg].row_kl[x.b * gp.seg[seg].G + x.grp] = kl;
+                            sm.klseg[gw][seg] += kl;
+                        } else {
+                            if (p.l[0].row_kl) p.l[0].row_kl[x.b * p.l[0].G + x.grp] = kl;
+                            kl_acc[0] += kl;
+                        }
                     }
                     if (ownK) {
                         const float kl = kl_of_row(1.f, sr.zs[K], sr.zt[K], sr.a[K], sr.dd[K]);
@@ -498,19 +575,47 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
             return;
         }
         unsigned ticket = 0;
+        if (MULTI && lane < gp.nseg) {
+            float acc = sm.klseg[0][lane];
+#pragma unroll
+            for (int w = 1; w < kGGatherWarps; ++w) acc += sm.klseg[w][lane];
+            __stcg(&p.cta_part[lane * kMaxGrid + blockIdx.x], acc);
+        }
+        if (MULTI) {
+            __threadfence();
+            __syncwarp();
+        }
         if (lane == 0) {
+            if (!MULTI) {
 #pragma unroll
-            for (int k = 0; k < NL; ++k) {
-                float acc = sm.klpart[0][k];
+                for (int k = 0; k < NL; ++k) {
+                    float acc = sm.klpart[0][k];
 #pragma unroll
-                for (int w = 1; w < kGGatherWarps; ++w) acc += sm.klpart[w][k];
-                __stcg(&p.cta_part[k * kMaxGrid + blockIdx.x], acc);
+                    for (int w = 1; w < kGGatherWarps; ++w) acc += sm.klpart[w][k];
+                    __stcg(&p.cta_part[k * kMaxGrid + blockIdx.x], acc);
+                }
             }
             __threadfence();
             ticket = atomicAdd(&p.ctrl[0], 1u);
         }
         ticket = __shfl_sync(0xffffffffu, ticket, 0);
-        if (ticket == gridDim.x - 1) {
+        if (MULTI && ticket == gridDim.x - 1) {
+            // the last CTA sums every pair's partials in a fixed order
+            __threadfence();
+            const bool timed_out = __ldcg(&p.ctrl[1]) != 0u;
+            for (int k = 0; k < gp.nseg; ++k) {
+                double acc = 0.0;
+                for (int i = lane; i < (int)gridDim.x; i += 32) acc += (double)__ldcg(&p.cta_part[k * kMaxGrid + i]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+                if (lane == 0)
+                    *gp.seg[k].loss = timed_out ? __int_as_float(0x7fc00000) : (float)((double)gp.seg[k].loss_scale * acc);
+            }
+            if (lane == 0) {
+                atomicAdd(&p.ctrl[2], 1u);
+                atomicExch(&p.ctrl[0], 0u);
+            }
+        } else if (ticket == gridDim.x - 1) {
             __threadfence();
             double acc[NL];
 #pragma unroll
@@ -626,7 +731,9 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
 
         for (int j = 0; j < n_units; ++j) {
             GT_TICK(d0);
-            const GUnit x = grid_decode(p, (long long)blockIdx.x + (long long)j * grid);
+            int seg;
+            const GUnit x = unit_at((long long)blockIdx.x + (long long)j * grid, seg);
+            if (MULTI) c2[0] = gp.seg[seg].c2;
             const int nvs = x.len / VE;
             const int nchunks = (nvs + kGChunkVecs - 1) / kGChunkVecs;
             st = pstat_empty<NL>();
@@ -755,7 +862,9 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
         GT_DECL(2);
         GT_TICK(gt_start);
         for (int j = 0; j < n_units; ++j) {
-            const GUnit x = grid_decode(p, (long long)blockIdx.x + (long long)j * grid);
+            int seg;
+            const GUnit x = unit_at((long long)blockIdx.x + (long long)j * grid, seg);
+            if (MULTI) c2[0] = gp.seg[seg].c2;
             const int nvs = x.len / VE;
             const int n = (nvs + kGChunkVecs - 1) / kGChunkVecs;
             const int d = j & (kGDepth - 1);
@@ -764,7 +873,7 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
             GT_TICK(w1);
             GT_ACC(0, w0, w1);
             tmem_fence_after_sync();
-            T* out = static_cast<T*>(p.dS) + ((size_t)x.b * p.C + (size_t)x.grp * p.l[0].g) * p.HW + (size_t)x.e0;
+            T* out = static_cast<T*>(MULTI ? gp.seg[seg].dS : p.dS) + elem_base(x, seg);
             const float4 fa = *reinterpret_cast<const float4*>(sm.fin[d][0]);                 // row of l[0]
             const float4 fb = NL == 2 ? *reinterpret_cast<const float4*>(sm.fin[d][1]) : fa;   // row of l[1]
             auto grad_chunk = [&](int c, const Parked& pk, uint32_t ts) {
@@ -844,9 +953,9 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
 }
 
 // ====================================================================================================
-template <typename T, int NL, int R>
-static cudaError_t launch_grid_t(const RowsParams& p, int sms, cudaStream_t stream, bool probe_only) {
-    auto kern = kl_rows_grid_kernel<T, NL, R>;
+template <typename T, int NL, int R, bool MULTI>
+static cudaError_t launch_grid_t(const RowsParams& p, const GroupParams& gp, int sms, cudaStream_t stream, bool probe_only) {
+    auto kern = kl_rows_grid_kernel<T, NL, R, MULTI>;
     static std::atomic<int> ctas_per_sm_dev[kMaxDevices];  // per instantiation and device; -1: cannot run
     std::atomic<int>& ctas_per_sm = ctas_per_sm_dev[device_slot()];
     if (ctas_per_sm == 0) {
@@ -873,21 +982,39 @@ static cudaError_t launch_grid_t(const RowsParams& p, int sms, cudaStream_t stre
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, p);
+    return cudaLaunchKernelEx(&cfg, kern, p, gp);
 }
 
 cudaError_t launch_kl_rows_grid(const RowsParams& p, bool bf16, int sms, cudaStream_t stream, bool probe_only) {
+    static const GroupParams none = {};
     if (p.nl == 2) {
         // tau[1] == 2 * tau[0]: one exponential serves both losses
         const bool sq = p.l[0].c2 == 2.f * p.l[1].c2;
         if (sq)
-            return bf16 ? launch_grid_t<__nv_bfloat16, 2, 2>(p, sms, stream, probe_only)
-                        : launch_grid_t<float, 2, 2>(p, sms, stream, probe_only);
-        return bf16 ? launch_grid_t<__nv_bfloat16, 2, 0>(p, sms, stream, probe_only)
-                    : launch_grid_t<float, 2, 0>(p, sms, stream, probe_only);
+            return bf16 ? launch_grid_t<__nv_bfloat16, 2, 2, false>(p, none, sms, stream, probe_only)
+                        : launch_grid_t<float, 2, 2, false>(p, none, sms, stream, probe_only);
+        return bf16 ? launch_grid_t<__nv_bfloat16, 2, 0, false>(p, none, sms, stream, probe_only)
+                    : launch_grid_t<float, 2, 0, false>(p, none, sms, stream, probe_only);
     }
-    return bf16 ? launch_grid_t<__nv_bfloat16, 1, 0>(p, sms, stream, probe_only)
-                : launch_grid_t<float, 1, 0>(p, sms, stream, probe_only);
+    return bf16 ? launch_grid_t<__nv_bfloat16, 1, 0, false>(p, none, sms, stream, probe_only)
+                : launch_grid_t<float, 1, 0, false>(p, none, sms, stream, probe_only);
+}
+
+// several pairs, one loss each: gp.seg[] cut into units of whole chunks (chunk_elems a multiple of 4096, at most 4 chunks),
+// gp.total_units / ctrl / cta_part / pkt / grad_out filled; knobs: grid_knobs as in RowsParams
+cudaError_t launch_kl_rows_grid_group(const GroupParams& gp, int max_row_units, const int* knobs, bool bf16, int sms,
+                                      cudaStream_t stream, bool probe_only) {
+    RowsParams p = {};
+    p.nl = 1;
+    p.total_units = gp.total_units;
+    p.units_coarse = gp.total_units;
+    p.max_row_units = max_row_units;
+    p.ctrl = gp.ctrl;
+    p.cta_part = gp.cta_part;
+    p.pkt = gp.pkt;
+    for (int i = 0; i < 4; ++i) p.grid_knobs[i] = knobs[i];
+    return bf16 ? launch_grid_t<__nv_bfloat16, 1, 0, true>(p, gp, sms, stream, probe_only)
+                : launch_grid_t<float, 1, 0, true>(p, gp, sms, stream, probe_only);
 }
 
 }  // namespace sd

@@ -38,6 +38,8 @@ cudaError_t launch_kl_rows_cluster(const RowsParams& p, const ClusterGeom& g, bo
 
 // kl_rows_grid.cu   (probe_only: just answer whether the kernel can be resident on this device)
 cudaError_t launch_kl_rows_grid(const RowsParams& p, bool bf16, int sms, cudaStream_t stream, bool probe_only);
+cudaError_t launch_kl_rows_grid_group(const GroupParams& gp, int max_row_units, const int* knobs, bool bf16, int sms,
+                                      cudaStream_t stream, bool probe_only);
 
 // kl_rows_up.cu
 cudaError_t launch_kl_rows_up(const UpParams& p, bool bf16, int sms, cudaStream_t stream);

@@ -1206,8 +1206,16 @@ def _stage_pairs(batch, dtype=torch.float32, seed=70):
     return [seeded_pair((batch,) + st, seed=seed + k, dtype=dtype) for k, st in enumerate(CFG2_STAGES)]
 
 
+@pytest.fixture(params=['grid', 'two-phase'])
+def group_kernel(request, monkeypatch):
+    """Launches over several pairs: the grid-resident kernel (default where every map has HW % 128 == 0) or the
+    two-phase streaming kernel (SEGDISTILL_GROUP_GRID=0)."""
+    monkeypatch.setenv('SEGDISTILL_GROUP_GRID', '1' if request.param == 'grid' else '0')
+    return 'kl_rows_grid_kernel(group)' if request.param == 'grid' else 'kl_rows_group_kernel'
+
+
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
-def test_grouped_launch_cfg2_four_stages_b16(dtype):
+def test_grouped_launch_cfg2_four_stages_b16(dtype, group_kernel):
     """BASELINE config 2 at its full batch: CGD (g = 10, ragged groups: 32, 64, 256 % 10 != 0) on the four stage maps in
     ONE launch through the C ABI, against the oracle per pair."""
     pairs = _stage_pairs(16, dtype)
@@ -1217,7 +1225,7 @@ def test_grouped_launch_cfg2_four_stages_b16(dtype):
     ts = [t.to(dev()) for _, t in pairs]
     before = _cabi.launch_count()
     losses, dss = _cabi.kl_rows_group(ss, ts, (10,) * 4, (2.0,) * 4, (3.0,) * 4)
-    assert _cabi.launch_count() - before == 1 and _cabi.last_kernel() == 'kl_rows_group_kernel'
+    assert _cabi.launch_count() - before == 1 and _cabi.last_kernel() == group_kernel
     torch.cuda.synchronize()
     assert _cabi.workspace_error_flag() == 0
     for k in range(4):
@@ -1227,17 +1235,21 @@ def test_grouped_launch_cfg2_four_stages_b16(dtype):
             _assert_close(losses[k].item(), dss[k].cpu(), *refs[k])
 
 
-def test_grouped_launch_mixed_settings_and_near_converged():
+@pytest.mark.parametrize('hw2', [(24, 20), (24, 32)])
+def test_grouped_launch_mixed_settings_and_near_converged(hw2, group_kernel):
     """Pairs with different group sizes, temperatures, weights and row lengths (one split over many units, one of a
-    single short unit), one of them nearly converged - each must equal its own single-pair result."""
-    shapes = [(2, 20, 128, 128), (3, 7, 24, 20), (1, 150, 32, 32), (2, 6, 16, 16)]
+    single short unit), one of them nearly converged - each must equal its own single-pair result.  (24x20: a map the
+    grid-resident kernel does not take - the launch falls back to the two-phase kernel; 24x32: it takes all four.)"""
+    shapes = [(2, 20, 128, 128), (3, 7) + hw2, (1, 150, 32, 32), (2, 6, 16, 16)]
     cfgs = [(10, 2.0, 3.0), (3, 4.0, 1.0), (150, 3.0, 0.5), (1, 1.0, 1.0)]
     pairs = [seeded_pair(sh, seed=80 + k) for k, sh in enumerate(shapes)]
     pairs[3] = _near_pair(shapes[3], seed=83, offset=0.7)
     ss = [s.to(dev()) for s, _ in pairs]
     ts = [t.to(dev()) for _, t in pairs]
     losses, dss = _cabi.kl_rows_group(ss, ts, [c[0] for c in cfgs], [c[1] for c in cfgs], [c[2] for c in cfgs])
+    assert _cabi.last_kernel() == (group_kernel if hw2 == (24, 32) else 'kl_rows_group_kernel')
     torch.cuda.synchronize()
+    assert _cabi.workspace_error_flag() == 0
     for k, ((s, t), (g, tau, alpha)) in enumerate(zip(pairs, cfgs)):
         f64_loss, f64_grad, _ = oracle.kld_closed_form_f64(s.numpy(), t.numpy(), 'channel', g, tau, alpha)
         if k == 3:
@@ -1248,7 +1260,7 @@ def test_grouped_launch_mixed_settings_and_near_converged():
             assert np.abs(dss[k].double().cpu().numpy() - f64_grad).max() <= GRAD_RTOL * np.abs(f64_grad).max()
 
 
-def test_dispatcher_groups_entries_on_different_layers():
+def test_dispatcher_groups_entries_on_different_layers(group_kernel):
     """Four `distillation` entries on four different layers (opts.py:87-112): one grouped launch per step, the
     reference's result keys, correct gradients with different upstream weights, also on the cached second step."""
     pairs = _stage_pairs(4)
@@ -1263,7 +1275,7 @@ def test_dispatcher_groups_entries_on_different_layers():
         xs = [s.to(dev()).requires_grad_(True) for s, _ in pairs]
         before = _cabi.launch_count()
         out = d({f'stage{k}': x for k, x in enumerate(xs)}, tf, None, step, None, None)
-        assert _cabi.launch_count() - before == 1 and _cabi.last_kernel() == 'kl_rows_group_kernel'
+        assert _cabi.launch_count() - before == 1 and _cabi.last_kernel() == group_kernel
         assert list(out) == [f"loss_stage{k}<->stage{k}_other" for k in range(4)]
         sum(wk * v for wk, v in zip(w, out.values())).backward()
         torch.cuda.synchronize()
