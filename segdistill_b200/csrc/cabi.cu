@@ -164,8 +164,7 @@ const int* grid_knobs() {
         int v[4] = {3, 96, 32, 64};
         const char* e = std::getenv("SEGDISTILL_GRID_KNOBS");
         if (e) std::sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]);
-        if (v[0] < 1) v[0] = 1;
-        if (v[0] > 3) v[0] = 3;
+        if ((v[0] & 255) < 1 || (v[0] & 255) > 3) v[0] = (v[0] & ~255) | 3;    // (bits 8..: park warps, 8 or 16)
         for (int i = 1; i < 4; ++i) v[i] = v[i] < 0 ? 0 : (v[i] > 100000 ? 100000 : v[i]);
         for (int i = 3; i >= 0; --i) k[i] = v[i];
     }

@@ -30,15 +30,13 @@
 #include "park_common.cuh"
 #include "launch.h"
 
+#include <type_traits>
+
 namespace sd {
 
-constexpr int kGPark = 256;                            // park threads (warps 0..7); gradient threads: warps 8..15
-constexpr int kGParkWarps = kGPark / 32;
-constexpr int kGTmaWarp = 2 * kGParkWarps;             // warp 16
-constexpr int kGGatherWarps = 3;                       // warps 17..19: packets -> row statistics (warp i: units j % 3 == i)
-constexpr int kGThreads = 2 * kGPark + 32 + 32 * kGGatherWarps;   // 20 warps: the most that keep 96 registers per thread
-constexpr int kGChunkRows = 4;                         // 4-element vectors per park thread, chunk and tensor
-constexpr int kGChunkVecs = kGChunkRows * kGPark;      // 1024 vectors = 4096 elements per tensor
+constexpr int kGGradWarps = 8;                         // gradient warps (two per TMEM lane quarter)
+constexpr int kGGatherWarps = 3;                       // packets -> row statistics (warp i: units j % 3 == i)
+constexpr int kGChunkVecs = 1024;                      // 4-element vectors per chunk and tensor = 4096 elements
 constexpr int kGChunkBytes = kGChunkVecs * 16;         // fp32; bf16 chunks fill half a slot
 constexpr int kGRing = 6;                              // ring slots of 32 KB (S chunk + T chunk)
 constexpr int kGSlots = 8;                             // TMEM chunk slots per park warp
@@ -46,20 +44,35 @@ constexpr int kGDepth = 8;                             // units between park and
 constexpr int kGRecFloats = 12;                        // ms, mt, {zs, zt, a, dd} x 2, 2 x pad (three 16-byte words)
 constexpr int kGTmemCols = 512;
 constexpr int kGPktWords = 2 + 4 * kMaxLosses;         // words of a packet in use (same order as a warp record)
-static_assert(kGSlots * kCSlotCols * (kGParkWarps / 4) == kGTmemCols, "TMEM columns");
 static_assert(kGridUnitMaxChunks * 2 <= kGSlots, "two units must fit the TMEM slots (deadlock freedom)");
 static_assert(kGPktWords <= kPktWords, "packet size");
 static_assert(kGChunkVecs * 4 == kGridChunkElems, "chunk size");
 
+// PW park warps (8: 16 element pairs per thread and chunk, 96 registers per thread; 16: 8 pairs, 72 registers - four
+// park warps per scheduler instead of two), 8 gradient warps (each serves PW / 8 park warps of its TMEM lane quarter),
+// the TMA + publisher warp, 3 gather warps
+template <int PW>
+struct GridCfg {
+    static constexpr int kParkWarps = PW;
+    static constexpr int kPark = 32 * PW;                          // park threads (warps 0 .. PW - 1)
+    static constexpr int kChunkRows = kGChunkVecs / kPark;         // 4-element vectors per park thread, chunk and tensor
+    static constexpr int kSlotCols = 8 * kChunkRows;               // TMEM columns of a parked chunk per thread
+    static constexpr int kWarpCols = kGSlots * kSlotCols;          // ... of a park warp
+    static constexpr int kTmaWarp = PW + kGGradWarps;
+    static constexpr int kThreads = 32 * (PW + kGGradWarps + 1 + kGGatherWarps);
+    static_assert(kWarpCols * (PW / 4) == kGTmemCols, "TMEM columns");
+};
+
+template <int PW>
 struct GridSmem {
     unsigned char ring[kGRing][2][kGChunkBytes];
     uint64_t full[kGRing], empty[kGRing];
-    uint64_t recbar[kGDepth];                             // 8 park warps: "my record of this unit is written"
-    uint64_t finbar[kGDepth];                             // stats warp: "the row statistics of this unit are written"
-    uint64_t tfree[kGParkWarps][kGSlots];                 // gradient warp -> its park warp: "this TMEM slot is read"
-    float rec[kGDepth][kGParkWarps][kGRecFloats];         // warp records of the units in flight
+    uint64_t recbar[kGDepth];                             // park warps: "my record of this unit is written"
+    uint64_t finbar[kGDepth];                             // gather warp: "the row statistics of this unit are written"
+    uint64_t tfree[PW][kGSlots];                          // gradient warp -> park warp: "this TMEM slot is read"
+    float rec[kGDepth][PW][kGRecFloats];                  // warp records of the units in flight
     float fin[kGDepth][2][4];                             // {Ms, Mt, coef/Zs, coef/Zt} of the unit's row of l[0], of l[1]
-    float refs[kGParkWarps][kGSlots][2];                  // references {ms, mt} a parked chunk was taken against
+    float refs[PW][kGSlots][2];                           // references {ms, mt} a parked chunk was taken against
     float klpart[kGGatherWarps][kMaxLosses];              // KL sums of the gather warps
     float klseg[kGGatherWarps][kMaxSegs];                 // ... per pair (launches over several pairs)
 #ifdef SD_GRID_TIMING
@@ -67,7 +80,6 @@ struct GridSmem {
 #endif
     uint32_t tmem_base;
 };
-constexpr size_t kGridSmemBytes = sizeof(GridSmem);
 
 // waits that normally last a microsecond or more: poll, then sleep - a polling warp takes issue slots from the park warps
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned sleep_ns) {
@@ -158,7 +170,8 @@ __device__ __forceinline__ long long grid_unit_index(const RowsParams& p, const 
 // ---------------------------------------------------------------- several (student, teacher) pairs, one work list
 // MULTI launches (sd_kl_rows_group_fwd_bwd): one loss per pair, every pair cut into coarse units only; the units of
 // pair k are [seg[k].unit0, seg[k + 1].unit0).  `seg` = index of the pair.
-__device__ __forceinline__ GUnit grid_decode_multi(const GroupParams& gp, long long u64, int& seg) {
+template <typename Pairs>
+__device__ __forceinline__ GUnit grid_decode_multi(const Pairs& gp, long long u64, int& seg) {
     const unsigned u = (unsigned)u64;
     int k = 0;
 #pragma unroll
@@ -212,9 +225,23 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // With one loss, or with R == 2, phase 1 parks the EXPONENTIALS (relative to the warp's running maximum at that
 // moment, kept in shared memory): phase 2 is then a multiply-add per element, no ex2.  Otherwise the raw values are
 // parked and phase 2 recomputes.
-template <typename T, int NL, int R, bool MULTI>
-__global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsParams p, const GroupParams gp) {
+// what a launch over one pair passes instead of the pairs' table (never read: every use is behind `if (MULTI)`)
+struct NoPairs {
+    int nseg;
+    const float* grad_out;
+    GroupSeg seg[1];
+};
+template <bool MULTI>
+using PairTable = typename std::conditional<MULTI, GroupParams, NoPairs>::type;
+
+template <typename T, int NL, int R, bool MULTI, int PW>
+__global__ void __launch_bounds__(GridCfg<PW>::kThreads, 1) kl_rows_grid_kernel(const RowsParams p, const PairTable<MULTI> gp) {
     static_assert(!MULTI || (NL == 1 && R == 0), "several pairs: one loss each");
+    using Cfg = GridCfg<PW>;
+    constexpr int kGParkWarps = Cfg::kParkWarps, kGPark = Cfg::kPark, kGChunkRows = Cfg::kChunkRows;
+    constexpr int kSlotCols = Cfg::kSlotCols, kGTmaWarp = Cfg::kTmaWarp, kGThreads = Cfg::kThreads;
+    constexpr int NSRC = PW / kGGradWarps;      // park warps a gradient warp serves
+    using ParkedT = typename std::conditional<PW == 8, Parked, Parked16>::type;
     using V = Vec4<T>;
     using vec_t = typename V::type;
     constexpr int VE = 4;
@@ -223,7 +250,7 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
     constexpr int K = NL - 1;                   // the loss whose exponential comes out of the MUFU
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    GridSmem& sm = *reinterpret_cast<GridSmem*>(smem_raw);
+    GridSmem<PW>& sm = *reinterpret_cast<GridSmem<PW>*>(smem_raw);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -346,9 +373,9 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
                     unit_at((long long)blockIdx.x + (long long)jp * grid, seg);
                     c2[0] = gp.seg[seg].c2;
                 }
-                const float4* q = reinterpret_cast<const float4*>(sm.rec[jp & (kGDepth - 1)][lane & 7]);
+                const float4* q = reinterpret_cast<const float4*>(sm.rec[jp & (kGDepth - 1)][lane & (PW - 1)]);
                 PStat<NL> st = pstat_from<NL>(q[0], q[1], NL == 2 ? q[2] : make_float4(0.f, 0.f, 0.f, 0.f));
-                st = pstat_reduce<NL, R, 8>(st, c2);
+                st = pstat_reduce<NL, R, PW>(st, c2);
                 float val = st.ms;
                 if (lane == 1) val = st.mt;
                 if (lane == 2) val = st.zs[0];
@@ -650,11 +677,16 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
     // =========================================================================================
     // park warps 0..7 and gradient warps 8..15: warp 8 + i retrieves what warp i parked
     // =========================================================================================
-    const int pw = warp & (kGParkWarps - 1);
-    const int ptid = tid & (kGPark - 1);
-    // the pair's TMEM window: lane quarter of both warps, 256 columns, 8 chunk slots of 32
-    const uint32_t tmem_mine = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((pw >> 2) * 256);
-    const int wv = pw * 32;            // the pair's vector-rows of a chunk start here, + 256 r (r < 4)
+    // TMEM window of park warp w: the lane quarter of the warp (w & 3 - a warp can only reach its own quarter),
+    // Cfg::kWarpCols columns from (w >> 2) * Cfg::kWarpCols: 8 chunk slots of kSlotCols.  A gradient warp reads the
+    // windows of the NSRC park warps of its quarter it is paired with.
+    auto tmem_of = [&](int w) {
+        return tmem_base + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)((w >> 2) * Cfg::kWarpCols);
+    };
+    const int pw = warp;               // (park warps) my index
+    const int ptid = tid;              // (park warps) my index among the park threads
+    const uint32_t tmem_mine = tmem_of(warp);
+    const int wv = pw * 32;            // (park warps) my vector-rows of a chunk start here, + kGPark r
 
     if (warp < kGParkWarps) {
         // ------------------------------------------------ phase 1: statistics, park the unit
@@ -774,8 +806,14 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
                 const int vA = c * kGChunkVecs + wv;      // my first vector-row, in vectors of the unit; + 256 r
                 if (vA + (kGChunkRows - 1) * kGPark < nvs) {
                     // ---- all my vector-rows lie inside the unit (the common case)
-                    const float wms = warp_max_uniform(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])));
-                    const float wmt = warp_max_uniform(fmaxf(fmaxf(mxt[0], mxt[1]), fmaxf(mxt[2], mxt[3])));
+                    float ms_ = mxs[0], mt_ = mxt[0];
+#pragma unroll
+                    for (int r = 1; r < kGChunkRows; ++r) {
+                        ms_ = fmaxf(ms_, mxs[r]);
+                        mt_ = fmaxf(mt_, mxt[r]);
+                    }
+                    const float wms = warp_max_uniform(ms_);
+                    const float wmt = warp_max_uniform(mt_);
                     // every lane's shared-memory reads went into the maxima: the slot may go back to the TMA warp
                     if (lane == 0) mbar_arrive(&sm.empty[slot]);
                     GT_TICK(r0);
@@ -804,7 +842,7 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
                         if (vA + r * kGPark < nvs) accumulate(&fs[r * VE], &ft[r * VE], VE);
                 }
                 // ---- park: registers -> TMEM; the references once per warp
-                Parked pk;
+                ParkedT pk;
 #pragma unroll
                 for (int r = 0; r < kGChunkRows; ++r) {
 #pragma unroll
@@ -814,7 +852,8 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
                     }
                 }
                 GT_TICK(s0);
-                tmem_st32(tmem_mine + ts * kCSlotCols, pk);
+                if constexpr (PW == 8) tmem_st32(tmem_mine + ts * kSlotCols, pk);
+                else tmem_st16(tmem_mine + ts * kSlotCols, pk);
                 if (kParkExp && lane == 0) *reinterpret_cast<float2*>(sm.refs[pw][ts]) = make_float2(st.ms, st.mt);
                 GT_TICK(s1);
                 GT_ACC(6, s0, s1);
@@ -858,6 +897,10 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
 #endif
     } else {
         // ------------------------------------------------ phase 2: gradient from the parked unit
+        // gradient warp g reads the park warps src0 + 4 s (s < NSRC) of its lane quarter: consecutive TMEM windows
+        const int gq = warp - kGParkWarps;
+        const int src0 = (gq & 3) + 4 * (NSRC * (gq >> 2));
+        const uint32_t tmem_src0 = tmem_of(src0);
         uint32_t q = 0;                    // chunks retrieved so far -> TMEM slot
         GT_DECL(2);
         GT_TICK(gt_start);
@@ -876,14 +919,15 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
             T* out = static_cast<T*>(MULTI ? gp.seg[seg].dS : p.dS) + elem_base(x, seg);
             const float4 fa = *reinterpret_cast<const float4*>(sm.fin[d][0]);                 // row of l[0]
             const float4 fb = NL == 2 ? *reinterpret_cast<const float4*>(sm.fin[d][1]) : fa;   // row of l[1]
-            auto grad_chunk = [&](int c, const Parked& pk, uint32_t ts) {
+            // one parked chunk of park warp `src`: values (+ the references they were taken against) -> gradient
+            auto grad_chunk = [&](int c, const ParkedT& pk, uint32_t ts, int src) {
                 float2 rf = make_float2(0.f, 0.f);
-                if (kParkExp) rf = *reinterpret_cast<const float2*>(sm.refs[pw][ts]);
+                if (kParkExp) rf = *reinterpret_cast<const float2*>(sm.refs[src][ts]);
                 // the parked values are in registers, the references too: the slot may be parked into again
                 __syncwarp();
                 tmem_fence_before_sync();
-                if (lane == 0) mbar_arrive(&sm.tfree[pw][ts]);
-                const int vA = c * kGChunkVecs + wv;
+                if (lane == 0) mbar_arrive(&sm.tfree[src][ts]);
+                const int vA = c * kGChunkVecs + src * 32;
                 float gsK = 0.f, gtK = 0.f, gs0 = 0.f, gt0 = 0.f, rs0 = 0.f, rt0 = 0.f, rs1 = 0.f, rt1 = 0.f;
                 if (kParkExp) {
                     // parked: e = exp2((x - ref) c2[K]); softmax_k = e^(c2[k]/c2[K]) * exp2((ref - M_k) c2[k]) / Z_k, ref <= M_k
@@ -923,19 +967,32 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
                     }
                 }
             };
-            // parked chunks in flight from TMEM, one ahead of the arithmetic, in two register sets
-            Parked pa, pb;
-            tmem_ld32(tmem_mine + (q & (uint32_t)(kGSlots - 1)) * kCSlotCols, pa);
-            for (int c = 0; c < n; c += 2) {
-                const uint32_t t0_ = (q + (uint32_t)c) & (uint32_t)(kGSlots - 1), t1_ = (t0_ + 1) & (uint32_t)(kGSlots - 1),
-                               t2_ = (t0_ + 2) & (uint32_t)(kGSlots - 1);
-                tmem_wait_ld(pa);
-                if (c + 1 < n) tmem_ld32(tmem_mine + t1_ * kCSlotCols, pb);
-                grad_chunk(c, pa, t0_);
-                if (c + 1 < n) {
-                    tmem_wait_ld(pb);
-                    if (c + 2 < n) tmem_ld32(tmem_mine + t2_ * kCSlotCols, pa);
-                    grad_chunk(c + 1, pb, t1_);
+            if constexpr (PW == 8) {
+                // parked chunks in flight from TMEM, one ahead of the arithmetic, in two register sets
+                Parked pa, pb;
+                tmem_ld32(tmem_src0 + (q & (uint32_t)(kGSlots - 1)) * kSlotCols, pa);
+                for (int c = 0; c < n; c += 2) {
+                    const uint32_t t0_ = (q + (uint32_t)c) & (uint32_t)(kGSlots - 1), t1_ = (t0_ + 1) & (uint32_t)(kGSlots - 1),
+                                   t2_ = (t0_ + 2) & (uint32_t)(kGSlots - 1);
+                    tmem_wait_ld(pa);
+                    if (c + 1 < n) tmem_ld32(tmem_src0 + t1_ * kSlotCols, pb);
+                    grad_chunk(c, pa, t0_, src0);
+                    if (c + 1 < n) {
+                        tmem_wait_ld(pb);
+                        if (c + 2 < n) tmem_ld32(tmem_src0 + t2_ * kSlotCols, pa);
+                        grad_chunk(c + 1, pb, t1_, src0);
+                    }
+                }
+            } else {
+                // two park warps per gradient warp: both halves of a chunk in one round trip to TMEM
+                for (int c = 0; c < n; ++c) {
+                    const uint32_t ts = (q + (uint32_t)c) & (uint32_t)(kGSlots - 1);
+                    Parked16 pa, pb;
+                    tmem_ld16(tmem_src0 + ts * kSlotCols, pa);
+                    tmem_ld16(tmem_src0 + Cfg::kWarpCols + ts * kSlotCols, pb);
+                    tmem_wait_ld(pa, pb);
+                    grad_chunk(c, pa, ts, src0);
+                    grad_chunk(c, pb, ts, src0 + 4);
                 }
             }
             q += (uint32_t)n;
@@ -953,9 +1010,11 @@ __global__ void __launch_bounds__(kGThreads, 1) kl_rows_grid_kernel(const RowsPa
 }
 
 // ====================================================================================================
-template <typename T, int NL, int R, bool MULTI>
-static cudaError_t launch_grid_t(const RowsParams& p, const GroupParams& gp, int sms, cudaStream_t stream, bool probe_only) {
-    auto kern = kl_rows_grid_kernel<T, NL, R, MULTI>;
+template <typename T, int NL, int R, bool MULTI, int PW>
+static cudaError_t launch_grid_pw(const RowsParams& p, const PairTable<MULTI>& gp, int sms, cudaStream_t stream, bool probe_only) {
+    auto kern = kl_rows_grid_kernel<T, NL, R, MULTI, PW>;
+    constexpr int kGThreads = GridCfg<PW>::kThreads;
+    constexpr size_t kGridSmemBytes = sizeof(GridSmem<PW>);
     static std::atomic<int> ctas_per_sm_dev[kMaxDevices];  // per instantiation and device; -1: cannot run
     std::atomic<int>& ctas_per_sm = ctas_per_sm_dev[device_slot()];
     if (ctas_per_sm == 0) {
@@ -985,8 +1044,22 @@ static cudaError_t launch_grid_t(const RowsParams& p, const GroupParams& gp, int
     return cudaLaunchKernelEx(&cfg, kern, p, gp);
 }
 
+// Park warps per CTA: 8.  The 16-warp variant (8 element pairs per thread and chunk, 72 registers, four park warps per
+// scheduler) is correct and measured no faster - bf16 fused 83.5 vs 80.3 us, fp32 the same: with 8 park warps busy 92 %
+// of the time the SM is bound by its instruction throughput, not by latency.  -DSD_GRID_PW16 builds it in
+// (SEGDISTILL_GRID_KNOBS=4099,... selects it: bits 8.. of the first knob).
+template <typename T, int NL, int R, bool MULTI>
+static cudaError_t launch_grid_t(const RowsParams& p, const PairTable<MULTI>& gp, int sms, cudaStream_t stream, bool probe_only) {
+    RowsParams q = p;
+    q.grid_knobs[0] &= 255;
+#ifdef SD_GRID_PW16
+    if ((p.grid_knobs[0] >> 8) == 16) return launch_grid_pw<T, NL, R, MULTI, 16>(q, gp, sms, stream, probe_only);
+#endif
+    return launch_grid_pw<T, NL, R, MULTI, 8>(q, gp, sms, stream, probe_only);
+}
+
 cudaError_t launch_kl_rows_grid(const RowsParams& p, bool bf16, int sms, cudaStream_t stream, bool probe_only) {
-    static const GroupParams none = {};
+    static const NoPairs none = {};
     if (p.nl == 2) {
         // tau[1] == 2 * tau[0]: one exponential serves both losses
         const bool sq = p.l[0].c2 == 2.f * p.l[1].c2;

@@ -71,6 +71,30 @@ __device__ __forceinline__ void tmem_wait_ld(Parked& x) {
                  :
                  : "memory");
 }
+
+// 16-column variants (kl_rows_grid.cu with 16 park warps: 8 element pairs per thread and chunk)
+struct Parked16 {
+    uint32_t w[16];
+};
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const Parked16& x) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(x.w[0]), "r"(x.w[1]), "r"(x.w[2]), "r"(x.w[3]), "r"(x.w[4]), "r"(x.w[5]), "r"(x.w[6]), "r"(x.w[7]), "r"(x.w[8]), "r"(x.w[9]), "r"(x.w[10]), "r"(x.w[11]), "r"(x.w[12]), "r"(x.w[13]), "r"(x.w[14]), "r"(x.w[15])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, Parked16& x) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(x.w[0]), "=r"(x.w[1]), "=r"(x.w[2]), "=r"(x.w[3]), "=r"(x.w[4]), "=r"(x.w[5]), "=r"(x.w[6]), "=r"(x.w[7]), "=r"(x.w[8]), "=r"(x.w[9]), "=r"(x.w[10]), "=r"(x.w[11]), "=r"(x.w[12]), "=r"(x.w[13]), "=r"(x.w[14]), "=r"(x.w[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+// (the loaded registers of both halves are operands of the wait: nothing may read or copy them before it)
+__device__ __forceinline__ void tmem_wait_ld(Parked16& a, Parked16& b) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a.w[0]), "+r"(a.w[1]), "+r"(a.w[2]), "+r"(a.w[3]), "+r"(a.w[4]), "+r"(a.w[5]), "+r"(a.w[6]), "+r"(a.w[7]), "+r"(a.w[8]), "+r"(a.w[9]), "+r"(a.w[10]), "+r"(a.w[11]), "+r"(a.w[12]), "+r"(a.w[13]), "+r"(a.w[14]), "+r"(a.w[15]),
+                   "+r"(b.w[0]), "+r"(b.w[1]), "+r"(b.w[2]), "+r"(b.w[3]), "+r"(b.w[4]), "+r"(b.w[5]), "+r"(b.w[6]), "+r"(b.w[7]), "+r"(b.w[8]), "+r"(b.w[9]), "+r"(b.w[10]), "+r"(b.w[11]), "+r"(b.w[12]), "+r"(b.w[13]), "+r"(b.w[14]), "+r"(b.w[15])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- statistics of a part of a row
