@@ -130,6 +130,44 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
+
+// ---------------------------------------------------------------- two fp32 per instruction (sm_100: FFMA2 / FADD2 / FMUL2)
+// The packed forms deliver the same 128 results per clock and SM as the scalar ones but take ONE issue slot for two
+// results (scripts/probe/ffma2_bench.cu) - what the issue-bound kernels are short of.  IEEE round-to-nearest per
+// element, like the scalar instructions.  A value pair lives in an aligned 64-bit register pair.
+struct F2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ F2 f2_make(float lo, float hi) {
+    F2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ F2 f2_dup(float x) { return f2_make(x, x); }
+__device__ __forceinline__ void f2_split(const F2& x, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x.v));
+}
+__device__ __forceinline__ float f2_sum(const F2& x) {
+    float lo, hi;
+    f2_split(x, lo, hi);
+    return lo + hi;
+}
+__device__ __forceinline__ F2 f2_fma(const F2& a, const F2& b, const F2& c) {
+    F2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+__device__ __forceinline__ F2 f2_add(const F2& a, const F2& b) {
+    F2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ F2 f2_mul(const F2& a, const F2& b) {
+    F2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

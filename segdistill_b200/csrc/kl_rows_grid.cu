@@ -717,47 +717,69 @@ __global__ void __launch_bounds__(GridCfg<PW>::kThreads, 1) kl_rows_grid_kernel(
                 st.mt = nmt;
             }
         };
-        // N elements into the statistics of the unit; what gets parked replaces them in fs / ft
+        // N (even) elements into the statistics of the unit; what gets parked replaces them in fs / ft.  Two elements
+        // per instruction (FFMA2 / FADD2 / FMUL2, common.cuh): every sum runs as two partial sums per lane.
         auto accumulate = [&](float* fs, float* ft, int n) {
-            float refs2[NL], reft2[NL];
+            const F2 neg1 = f2_dup(-1.f);
+            F2 C2[NL], NRS[NL], NRT[NL], ZS[NL], ZT[NL], A[NL], DD[NL];
 #pragma unroll
             for (int k = 0; k < NL; ++k) {
-                refs2[k] = __fmul_rn(st.ms, c2[k]);
-                reft2[k] = __fmul_rn(st.mt, c2[k]);
+                C2[k] = f2_dup(c2[k]);
+                NRS[k] = f2_dup(-__fmul_rn(st.ms, c2[k]));
+                NRT[k] = f2_dup(-__fmul_rn(st.mt, c2[k]));
+                ZS[k] = f2_make(st.zs[k], 0.f);
+                ZT[k] = f2_make(st.zt[k], 0.f);
+                A[k] = f2_make(st.a[k], 0.f);
+                DD[k] = f2_make(st.dd[k], 0.f);
             }
+            auto ex2x2 = [](const F2& x) {
+                float lo, hi;
+                f2_split(x, lo, hi);
+                return f2_make(fast_exp2(lo), fast_exp2(hi));
+            };
 #pragma unroll
-            for (int i = 0; i < NE; ++i) {
+            for (int i = 0; i < NE; i += 2) {
                 if (i < n) {
-                    float as[NL], at[NL], es[NL], et[NL];
-                    exps_args<NL, R>(fs[i], refs2, c2, as, es);
-                    exps_args<NL, R>(ft[i], reft2, c2, at, et);
+                    const F2 s2 = f2_make(fs[i], fs[i + 1]), t2 = f2_make(ft[i], ft[i + 1]);
                     if (NL == 2 && R == 2) {
-                        // e0 = eK^2: the sums of loss 0 straight from the loss-K exponentials (one FFMA each)
-                        const float da = at[K] - as[K], dk = et[K] - es[K];
-                        st.zs[K] += es[K];
-                        st.zt[K] += et[K];
-                        st.zs[0] = fmaf(es[K], es[K], st.zs[0]);
-                        st.zt[0] = fmaf(et[K], et[K], st.zt[0]);
-                        const float w = et[K] * da;
-                        st.a[K] += w;
-                        st.a[0] = fmaf(et[K], w, st.a[0]);
-                        st.dd[K] += dk;
-                        st.dd[0] = fmaf(dk, et[K] + es[K], st.dd[0]);      // et0 - es0 = (eK_t - eK_s)(eK_t + eK_s)
+                        // e0 = eK^2: the sums of loss 0 straight from the loss-K exponentials (one FFMA2 each)
+                        const F2 as2 = f2_fma(s2, C2[K], NRS[K]), at2 = f2_fma(t2, C2[K], NRT[K]);
+                        const F2 es2 = ex2x2(as2), et2 = ex2x2(at2);
+                        const F2 da = f2_fma(as2, neg1, at2), dk = f2_fma(es2, neg1, et2);
+                        ZS[K] = f2_add(ZS[K], es2);
+                        ZT[K] = f2_add(ZT[K], et2);
+                        ZS[0] = f2_fma(es2, es2, ZS[0]);
+                        ZT[0] = f2_fma(et2, et2, ZT[0]);
+                        const F2 w = f2_mul(et2, da);
+                        A[K] = f2_add(A[K], w);
+                        A[0] = f2_fma(et2, w, A[0]);
+                        DD[K] = f2_add(DD[K], dk);
+                        DD[0] = f2_fma(dk, f2_add(et2, es2), DD[0]);     // et0 - es0 = (eK_t - eK_s)(eK_t + eK_s)
+                        f2_split(es2, fs[i], fs[i + 1]);
+                        f2_split(et2, ft[i], ft[i + 1]);
                     } else {
 #pragma unroll
                         for (int k = 0; k < NL; ++k) {
-                            st.zs[k] += es[k];
-                            st.zt[k] += et[k];
-                            st.a[k] = fmaf(et[k], at[k] - as[k], st.a[k]);
+                            const F2 as2 = f2_fma(s2, C2[k], NRS[k]), at2 = f2_fma(t2, C2[k], NRT[k]);
+                            const F2 es2 = ex2x2(as2), et2 = ex2x2(at2);
+                            ZS[k] = f2_add(ZS[k], es2);
+                            ZT[k] = f2_add(ZT[k], et2);
+                            A[k] = f2_fma(et2, f2_fma(as2, neg1, at2), A[k]);
+                            DD[k] = f2_add(DD[k], f2_fma(es2, neg1, et2));
+                            if (kParkExp && k == K) {
+                                f2_split(es2, fs[i], fs[i + 1]);
+                                f2_split(et2, ft[i], ft[i + 1]);
+                            }
                         }
-#pragma unroll
-                        for (int k = 0; k < NL; ++k) st.dd[k] += et[k] - es[k];
-                    }
-                    if (kParkExp) {
-                        fs[i] = es[K];
-                        ft[i] = et[K];
                     }
                 }
+            }
+#pragma unroll
+            for (int k = 0; k < NL; ++k) {
+                st.zs[k] = f2_sum(ZS[k]);
+                st.zt[k] = f2_sum(ZT[k]);
+                st.a[k] = f2_sum(A[k]);
+                st.dd[k] = f2_sum(DD[k]);
             }
         };
 
@@ -944,23 +966,33 @@ __global__ void __launch_bounds__(GridCfg<PW>::kThreads, 1) kl_rows_grid_kernel(
                     rs1 = __fmul_rn(fb.x, c2[K]);
                     rt1 = __fmul_rn(fb.y, c2[K]);
                 }
+                const F2 GSK = f2_dup(gsK), NGTK = f2_dup(-gtK), GS0 = f2_dup(gs0), NGT0 = f2_dup(-gt0);
 #pragma unroll
                 for (int r = 0; r < kGChunkRows; ++r) {
                     if (vA + r * kGPark < nvs) {
                         float o[VE];
 #pragma unroll
-                        for (int e = 0; e < VE; ++e) {
-                            const float vs = __uint_as_float(pk.w[r * 8 + e]), vt = __uint_as_float(pk.w[r * 8 + 4 + e]);
+                        for (int e = 0; e < VE; e += 2) {
+                            const float vs0 = __uint_as_float(pk.w[r * 8 + e]), vs1 = __uint_as_float(pk.w[r * 8 + e + 1]);
+                            const float vt0 = __uint_as_float(pk.w[r * 8 + 4 + e]), vt1 = __uint_as_float(pk.w[r * 8 + 4 + e + 1]);
                             if (kParkExp && NL == 2) {
-                                o[e] = vs * fmaf(vs, gs0, gsK) - vt * fmaf(vt, gt0, gtK);
+                                // vs (vs gs0 + gsK) - vt (vt gt0 + gtK), two elements per instruction
+                                const F2 vs = f2_make(vs0, vs1), vt = f2_make(vt0, vt1);
+                                const F2 u = f2_mul(vt, f2_fma(vt, NGT0, NGTK));
+                                f2_split(f2_fma(vs, f2_fma(vs, GS0, GSK), u), o[e], o[e + 1]);
                             } else if (kParkExp) {
-                                o[e] = fmaf(vs, gsK, -vt * gtK);
+                                const F2 vs = f2_make(vs0, vs1), vt = f2_make(vt0, vt1);
+                                f2_split(f2_fma(vs, GSK, f2_mul(vt, NGTK)), o[e], o[e + 1]);
                             } else {
-                                const float es0 = fast_exp2(fmaf(vs, c2[0], -rs0));
-                                const float et0 = fast_exp2(fmaf(vt, c2[0], -rt0));
-                                const float es1 = fast_exp2(fmaf(vs, c2[K], -rs1));
-                                const float et1 = fast_exp2(fmaf(vt, c2[K], -rt1));
-                                o[e] = fmaf(es0, fa.z, es1 * fb.z) - fmaf(et0, fa.w, et1 * fb.w);
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    const float vs = h ? vs1 : vs0, vt = h ? vt1 : vt0;
+                                    const float es0 = fast_exp2(fmaf(vs, c2[0], -rs0));
+                                    const float et0 = fast_exp2(fmaf(vt, c2[0], -rt0));
+                                    const float es1 = fast_exp2(fmaf(vs, c2[K], -rs1));
+                                    const float et1 = fast_exp2(fmaf(vt, c2[K], -rt1));
+                                    o[e + h] = fmaf(es0, fa.z, es1 * fb.z) - fmaf(et0, fa.w, et1 * fb.w);
+                                }
                             }
                         }
                         V::store(out + (size_t)(vA + r * kGPark + lane) * VE, o);
