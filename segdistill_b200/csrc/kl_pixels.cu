@@ -185,21 +185,51 @@ kl_pixels_tma_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_cons
             rs2[q] = __fmul_rn(mxs[q], c2);
             rt2[q] = __fmul_rn(mxt[q], c2);
         }
+        if constexpr (PXT == 2) {
+            // bf16: the thread's two pixels side by side, two fp32 per instruction (FFMA2 / FADD2, common.cuh) - the
+            // bf16 kernel is bound by instruction issue, not by HBM
+            const F2 C2 = f2_dup(c2), NRS = f2_make(-rs2[0], -rs2[1]), NRT = f2_make(-rt2[0], -rt2[1]), neg1 = f2_dup(-1.f);
+            F2 ZS = f2_dup(0.f), ZT = f2_dup(0.f), AC = f2_dup(0.f), DD = f2_dup(0.f);
 #pragma unroll
-        for (int k = 0; k < CPT; ++k) {
-            if ((EXACT && k < CPT - 1) || cg + kPixCG * k < p.C) {
+            for (int k = 0; k < CPT; ++k) {
+                if ((EXACT && k < CPT - 1) || cg + kPixCG * k < p.C) {
+                    const int i = k * PXT;
+                    const F2 as2 = f2_fma(f2_make(s[i], s[i + 1]), C2, NRS), at2 = f2_fma(f2_make(t[i], t[i + 1]), C2, NRT);
+                    float as0, as1, at0, at1;
+                    f2_split(as2, as0, as1);
+                    f2_split(at2, at0, at1);
+                    s[i] = fast_exp2(as0);
+                    s[i + 1] = fast_exp2(as1);
+                    t[i] = fast_exp2(at0);
+                    t[i + 1] = fast_exp2(at1);
+                    const F2 es2 = f2_make(s[i], s[i + 1]), et2 = f2_make(t[i], t[i + 1]);
+                    ZS = f2_add(ZS, es2);
+                    ZT = f2_add(ZT, et2);
+                    AC = f2_fma(et2, f2_fma(as2, neg1, at2), AC);
+                    DD = f2_add(DD, f2_fma(es2, neg1, et2));
+                }
+            }
+            f2_split(ZS, zs[0], zs[PXT - 1]);
+            f2_split(ZT, zt[0], zt[PXT - 1]);
+            f2_split(AC, ac[0], ac[PXT - 1]);
+            f2_split(DD, dd[0], dd[PXT - 1]);
+        } else {
 #pragma unroll
-                for (int q = 0; q < PXT; ++q) {
-                    const int i = k * PXT + q;
-                    const float as = fmaf(s[i], c2, -rs2[q]), at = fmaf(t[i], c2, -rt2[q]);
-                    const float es = fast_exp2(as);
-                    const float et = fast_exp2(at);
-                    zs[q] += es;
-                    zt[q] += et;
-                    ac[q] = fmaf(et, at - as, ac[q]);
-                    dd[q] += et - es;
-                    s[i] = es;
-                    t[i] = et;
+            for (int k = 0; k < CPT; ++k) {
+                if ((EXACT && k < CPT - 1) || cg + kPixCG * k < p.C) {
+#pragma unroll
+                    for (int q = 0; q < PXT; ++q) {
+                        const int i = k * PXT + q;
+                        const float as = fmaf(s[i], c2, -rs2[q]), at = fmaf(t[i], c2, -rt2[q]);
+                        const float es = fast_exp2(as);
+                        const float et = fast_exp2(at);
+                        zs[q] += es;
+                        zt[q] += et;
+                        ac[q] = fmaf(et, at - as, ac[q]);
+                        dd[q] += et - es;
+                        s[i] = es;
+                        t[i] = et;
+                    }
                 }
             }
         }
@@ -239,8 +269,13 @@ kl_pixels_tma_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_cons
                 const int c = cg + kPixCG * k;
                 if ((EXACT && k < CPT - 1) || c < p.C) {
                     float o[PXT];
+                    if constexpr (PXT == 2) {
+                        const F2 u = f2_fma(f2_make(t[k * PXT], t[k * PXT + 1]), f2_make(-kt[0], -kt[PXT - 1]), f2_make(ga[0], ga[PXT - 1]));
+                        f2_split(f2_fma(f2_make(s[k * PXT], s[k * PXT + 1]), f2_make(ks[0], ks[PXT - 1]), u), o[0], o[PXT - 1]);
+                    } else {
 #pragma unroll
-                    for (int q = 0; q < PXT; ++q) o[q] = fmaf(s[k * PXT + q], ks[q], -t[k * PXT + q] * kt[q]) + ga[q];
+                        for (int q = 0; q < PXT; ++q) o[q] = fmaf(s[k * PXT + q], ks[q], -t[k * PXT + q] * kt[q]) + ga[q];
+                    }
                     out[(size_t)c * cstride] = PixTraits<T>::pack(o);
                 }
             }
