@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/tests.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/tests.log
-timeout 100 python scripts/kbench.py --only cd_f32,cd_bf16,pd_f32,pd_bf16,fused_f32,fused_bf16 2>&1
+timeout 120 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "occupies_the_sms or two_streams" > gpurun_out/tests_grid.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/tests_grid.log

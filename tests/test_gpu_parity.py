@@ -1090,8 +1090,9 @@ def test_second_backward_with_retain_graph_on_the_device():
     assert (w.grad.cpu() - r1).abs().max().item() <= GRAD_RTOL * r1.abs().max().item()
 
 
-def test_streaming_kernel_next_to_a_kernel_that_occupies_the_sms():
-    """The split-row kernel's CTAs read each other's packets: the launch is cooperative, so it starts only when the whole
+@pytest.mark.parametrize('algo', ['stream', 'grid'])
+def test_split_row_kernels_next_to_a_kernel_that_occupies_the_sms(algo):
+    """The split-row kernels' CTAs read each other's packets: the launch is cooperative, so it starts only when the whole
     grid can be resident - also while another stream keeps the SMs busy.  The result must be the oracle's and the
     time-out flag must stay clear (a time-out would turn the loss into NaN)."""
     shape = (2, 150, 64, 64)
@@ -1106,12 +1107,43 @@ def test_streaming_kernel_next_to_a_kernel_that_occupies_the_sms():
         with torch.cuda.stream(side):
             for _ in range(6):
                 a = torch.sin(a) * 1.0001          # ~1 ms each: every SM is taken while the loss kernel is queued
-        loss, ds, _, _ = _cabi.kl_rows(x, tg, group=10, tau=2.0, alpha=3.0, algo=_cabi.ALGOS['stream'])
-        assert _cabi.last_kernel() == 'kl_rows_stream_kernel'
+        loss, ds, _, _ = _cabi.kl_rows(x, tg, group=10, tau=2.0, alpha=3.0, algo=_cabi.ALGOS[algo])
+        assert _cabi.last_kernel() == f'kl_rows_{algo}_kernel'
         torch.cuda.synchronize()
         assert _cabi.workspace_error_flag() == 0
         assert np.isfinite(loss.item())
         _assert_close(loss.item(), ds.cpu(), *ref)
+
+
+def test_grid_resident_kernels_on_two_streams_at_once():
+    """Two launches of the grid-resident kernel queued on two streams (each with its own workspace): a cooperative launch
+    takes the whole GPU or waits, so the two never hold half of it each (the classic deadlock of CTAs that wait for
+    CTAs that cannot become resident).  Both results must be the oracle's."""
+    shape = (4, 150, 128, 128)
+    s, t = seeded_pair(shape, seed=37)
+    ra = _oracle_run('CDLoss', {}, s, t, shape[2:], 1)
+    rb = _oracle_run('CGDLoss', dict(group_size=10, alpha=3, tau=2), s, t, shape[2:], 1)
+    x, tg = s.to(dev()), t.to(dev())
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    outs = []
+    for rep in range(4):
+        for k, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                if k == 0:
+                    outs.append(_cabi.kl_rows_multi(x, tg, (10, 1), (2.0, 1.0), (3.0, 1.0), algo=_cabi.ALGOS['grid']))
+                else:
+                    outs.append(_cabi.kl_rows(x, tg, group=10, tau=2.0, alpha=3.0, algo=_cabi.ALGOS['grid'])[:2])
+    torch.cuda.synchronize()
+    assert _cabi.workspace_error_flag() == 0
+    for k, (losses, ds) in enumerate(outs):
+        if k % 2 == 0:
+            assert rel_err(losses[0].item(), rb[0]) <= LOSS_RTOL and rel_err(losses[1].item(), ra[0]) <= LOSS_RTOL
+            ref_grad = ra[1] + rb[1]
+        else:
+            assert rel_err(losses.item(), rb[0]) <= LOSS_RTOL
+            ref_grad = rb[1]
+        assert (ds.cpu() - ref_grad).abs().max().item() <= GRAD_RTOL * ref_grad.abs().max().item()
 
 
 # ------------------------------------------------------------------ f4: resize + cross-entropy + accuracy of the student head
