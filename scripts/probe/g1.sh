@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-timeout 120 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "occupies_the_sms or two_streams" > gpurun_out/tests_grid.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/tests_grid.log
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/tests.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/tests.log
+timeout 100 python scripts/kbench.py --only fused_f32,fused_bf16,cgd10_f32,cgd10_bf16,cfg2_grouped_f32,cgd150_f32 2>&1

@@ -170,14 +170,15 @@ const int* grid_knobs() {
     }
     return k;
 }
-// SEGDISTILL_GRID_FINE=0: no fine tail (every unit grid_unit_chunks() chunks; A-B knob)
-bool grid_fine_tail() {
+// SEGDISTILL_GRID_FINE=0: no fine tail (every unit grid_unit_chunks() chunks), 2: a fine tail whatever the size (A-B knob)
+int grid_fine_tail() {
     static int v = -1;
     if (v < 0) {
         const char* e = std::getenv("SEGDISTILL_GRID_FINE");
-        v = e ? (std::atoi(e) != 0) : 1;
+        v = e ? std::atoi(e) : 1;
+        if (v < 0) v = 0;
     }
-    return v != 0;
+    return v;
 }
 // SEGDISTILL_GROUP_GRID=0: launches over several pairs keep the two-phase kernel (A-B knob, tests of that kernel)
 bool group_prefers_grid() {
@@ -373,7 +374,10 @@ int rows_dispatch(RowsCall c) {
         grid_units_coarse = all_coarse;
         grid_total = all_coarse;
         grid_max_row_units = gc.max_row_units;
-        if (grid_fc < grid_uc && all_coarse % sms != 0) {
+        // (measured at 16 rounds - 16x150x128x128 - the fine tail costs ~1 us: its units wait for 40 row-mates each; it
+        //  pays where the last round is a large part of the work list.  SEGDISTILL_GRID_FINE=2 forces it)
+        const bool few_rounds = all_coarse < 8 * sms || grid_fine_tail() > 1;
+        if (grid_fc < grid_uc && all_coarse % sms != 0 && few_rounds) {
             // coarse units for floor(all / sms) whole rounds, cut back to a row boundary of the larger-group loss
             const long long budget = all_coarse / sms * sms;
             const int m = c.nl == 2 ? p.l[1].m : 1;
