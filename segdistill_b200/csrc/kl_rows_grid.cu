@@ -5,8 +5,8 @@
 // kl_rows_cluster.cu keeps a long row (CGD, g = 10 channels of 128x128 logits: 1.3 MB of S and T) resident in a
 // thread-block cluster of 8 - but only 15 such clusters fit the GPU's GPCs: 120 of 148 SMs work.  Here the row is
 // spread over CTAs that need not be neighbours: the grid is launched cooperatively (one CTA per SM, all resident),
-// a UNIT is a run of 1 .. 4 chunks (4096 elements of S and of T each) of one row of the smaller-group loss (4 for
-// most of the work list, 1 for its tail: see "units" below), unit u belongs to CTA u % grid - the units of one row are worked on at the same time by different SMs - and the
+// a UNIT is a run of 1 .. 4 chunks (4096 elements of S and of T each) of one row of the smaller-group loss (4; for
+// short work lists 1 for the tail: see "units" below), unit u belongs to CTA u % grid - the units of one row are worked on at the same time by different SMs - and the
 // softmax statistics of a unit travel as an epoch-tagged packet through global memory (L2), like in
 // kl_rows_stream.cu, instead of through distributed shared memory.  Between the statistics and the gradient a unit
 // is PARKED IN TENSOR MEMORY, as in the cluster kernel: 8 chunk slots per SM, so up to eight chunks are in flight
@@ -91,9 +91,10 @@ __device__ __forceinline__ void ld_relaxed_v2u64(const unsigned long long* p, un
 
 
 // ---------------------------------------------------------------- units: a coarse region, then a fine one
-// The work list is cut into units of p.chunk_elems elements (up to 4 chunks) - few unit boundaries, few packets -
-// except for its tail, which is cut into units of p.f_chunk_elems (one chunk): the grid's last round is then shared
-// by all SMs instead of leaving most of them idle, and the last gradient after the last exchange is short.  The
+// The work list is cut into units of p.chunk_elems elements (up to 4 chunks) - few unit boundaries, few packets.
+// Where it is short (fewer than 8 rounds of the grid; cabi.cu) its tail - everything after the last whole round - is
+// cut into units of p.f_chunk_elems (one chunk): the grid's last round is then shared by all SMs instead of leaving
+// most of them idle.  (At 16 rounds the fine tail measured 1 us slower: its units wait for 40 row-mates each.)  The
 // regions meet at a row boundary of the larger-group loss (sample p.split_b, row p.split_row of l[0]).
 struct GridRegion {
     int chunk_elems, nch_full, nch_last, ups;
