@@ -271,6 +271,7 @@ def run_ours(args, rank, local_rank, world):
     # two steps' loss kernels; the flush of the steps timed here is inside the timed region.
     LOG_INTERVAL = 50
     logs = sdist.DeferredLogs(['loss_cgd', 'loss_cd'], interval=LOG_INTERVAL, device=dev) if world > 1 else None
+    log_stream = torch.cuda.Stream() if world > 1 else None
 
     def feats(x):
         return {'decode_head.linear_pred': x, 'decode_head': x}
@@ -285,11 +286,13 @@ def run_ours(args, rank, local_rank, world):
             record[1].record()
             _cabi.last_kernel_of_step = _cabi.last_kernel()
         l1, l2 = out.values()
+        if logs is not None:
+            logs.push([l1, l2], stream=log_stream)     # device-side append, no collective; beside the backward's kernels
         (l1 + l2).backward()
+        if logs is not None:
+            logs.join()
         if record:
             record[2].record()
-        if logs is not None:
-            logs.push([l1, l2])                # device-side append, no collective
         return l1, l2
 
     flushed, in_flight = [], []

@@ -85,24 +85,42 @@ class DeferredLogs:
         self._flushed = 0                      # value of the cursor at the last flush
         self._pool = []                        # pinned landing buffers of the asynchronous flushes
 
-    def push(self, values):
+    def push(self, values, stream=None):
         """Append one step's scalars (a tensor of ``len(names)`` fp32 values, or a list of 0-dim tensors) - no
-        synchronisation, no collective.  Inside a CUDA-graph capture this records the append into the graph."""
+        synchronisation, no collective.  Inside a CUDA-graph capture this records the append into the graph.
+
+        ``stream``: a side stream for the append (CUDA only).  The append is ordered behind the work queued so far on the
+        current stream and the caller joins with ``join()`` later - typically after ``backward()``, so that the
+        one-warp launch runs next to the backward's kernels instead of between two steps' loss kernels."""
         if not isinstance(values, torch.Tensor):
             values = _as_vector(values)
         values = values.detach()
         if values.is_cuda:
             from . import _cabi
-            _cabi.log_push(values.float().contiguous(), self.ring, self.cursor)
+            if stream is not None:
+                stream.wait_stream(torch.cuda.current_stream(values.device))
+                with torch.cuda.stream(stream):
+                    _cabi.log_push(values.float().contiguous(), self.ring, self.cursor)
+                self._side = stream
+            else:
+                _cabi.log_push(values.float().contiguous(), self.ring, self.cursor)
         else:
             slot = int(self.cursor.item()) % self.interval
             self.ring[slot].copy_(values.float())
             self.cursor += 1
 
+    def join(self):
+        """Order the current stream behind an append that ``push(..., stream=side)`` queued on a side stream."""
+        side = getattr(self, '_side', None)
+        if side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self._side = None
+
     def flush_start(self):
         """Enqueue the flush without waiting for it: one all-reduce of the ring (mean over ranks), then asynchronous
         device->host copies of the ring and of the cursor into pinned buffers.  Returns a handle for ``flush_finish``.
         The launch stream is ordered behind the collective, so a CUDA event recorded after this call times it."""
+        self.join()
         ring = self.ring.clone()
         if dist.is_available() and dist.is_initialized():
             ring /= dist.get_world_size(self.group)
