@@ -147,8 +147,10 @@ SD_API int sd_kl_rows_multi_fwd_bwd(const void* S, const void* T, void* dS, int 
  * entry).  Pair k: maps S[k], T[k] of shape (B[k], C[k], HW[k]), rows of groups[k] channels, temperature taus[k], weight
  * alphas[k]; *losses[k] and dS[k] exactly as sd_kl_rows_fwd_bwd computes them for that pair alone (same dtype for all
  * pairs; n_pairs <= 8).  grad_output: NULL or one device scalar multiplied into every gradient.  The units of all
- * pairs form one work list for a persistent cooperative grid (two-phase streaming kernel, rows of any length, ragged
- * groups).  SD_ERR_UNSUPPORTED when a pair's rows are not 16-byte aligned (use the per-pair entry).
+ * pairs form one work list for a persistent cooperative grid: the grid-resident single pass (units parked in tensor
+ * memory) when every map has HW % 128 == 0 and no row spans more than 64 units of 16384 elements, else the two-phase
+ * streaming kernel (rows of any length); ragged groups either way.  SD_ERR_UNSUPPORTED when a pair's rows are not
+ * 16-byte aligned (use the per-pair entry).
  */
 SD_API size_t sd_kl_rows_group_workspace_bytes(int n_pairs, const int* B, const int* C, const int* HW, const int* groups,
                                         int dtype);
