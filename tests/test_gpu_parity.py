@@ -1060,6 +1060,32 @@ def test_full_size_two_loss_launch_against_the_oracle(dtype):
     assert (x.grad.float().cpu() - ref_grad).abs().max().item() <= gt_ * ref_grad.abs().max().item()
 
 
+@pytest.mark.parametrize('cls', ['CDLoss', 'PDLoss'])
+def test_cfg3_full_batch_bf16_against_the_oracle(cls):
+    """BASELINE config 3 at its own size: CD and the per-pixel logit KL on 16x150x128x128 bf16 against the oracle chain on
+    the fp32 upcast of the same bf16 values (CPU)."""
+    s, t = seeded_pair(FULL, seed=3, dtype=torch.bfloat16)
+    ref = _oracle_run(cls, {}, s, t, FULL[2:], 1)
+    got = _run(getattr(sd, cls)(), s, t, FULL[2:], 1)
+    _assert_close(*got, *ref, loss_rtol=2e-5, grad_rtol=BF16_GRAD_RTOL)
+
+
+def test_cfg4_full_batch_cd_plus_feature_mse_against_the_oracle():
+    """BASELINE config 4 at its own size: CWD (tau = 4) + feature MSE on 16x512x64x64 fp32 in the fused single pass,
+    against the oracle chain (CPU)."""
+    shape = (16, 512, 64, 64)
+    s, t = seeded_pair(shape, seed=12)
+    x = s.clone().requires_grad_(True)
+    ref_kl = oracle.OracleKLD(alpha=3, tau=4, transform_config={'loss_type': 'channel', 'group_size': 1})(x, t, None, 1)
+    ref_mse = oracle.mse_loss_torch(x, t, 0.7)
+    (ref_kl + ref_mse).backward()
+    crit = sd.CDMSELoss(alpha=3, tau=4, mse_weight=0.7)
+    loss, grad = _run(crit, s, t)
+    _assert_close(loss, grad, (ref_kl + ref_mse).item(), x.grad)
+    assert rel_err(crit.last_parts[0].item(), ref_kl.item()) <= LOSS_RTOL
+    assert rel_err(crit.last_parts[1].item(), ref_mse.item()) <= LOSS_RTOL
+
+
 def test_second_backward_with_retain_graph_on_the_device():
     """log_grad mode of the reference trainer (SD_structure.py:92-134): backward(retain_graph=True), then the real one."""
     s, t = seeded_pair((2, 20, 64, 64), seed=21)
