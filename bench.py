@@ -441,30 +441,49 @@ def run_ours(args, rank, local_rank, world):
     value = world * B_PER_GPU * H * W / (ms_per_step * 1e-3) / 1e6
 
     _note(rank, f'timed region done: {elapsed_ms / args.steps:.4f} ms per step')
-    # ---- e2e: pinned host buffers -> H2D -> modules -> D2H of the loss scalars, every step
+    # ---- e2e: pinned host buffers -> H2D -> modules -> D2H of the loss scalars, every step.  The inputs are double-buffered:
+    #      the H2D copies of step k + 1 run on a copy stream while step k's kernels run and its result is read (what a
+    #      training loop with a prefetching loader does); every step's copies and its result read are inside the timed
+    #      region, n copies for n steps.
     e2e = None
     if not args.no_e2e:
-        dS_in = torch.empty_like(S).requires_grad_(True)
-        dT_in = torch.empty_like(T)
+        bufs = [(torch.empty_like(S).requires_grad_(True), torch.empty_like(T)) for _ in range(2)]
+        copy_stream = torch.cuda.Stream()
+        ready = [torch.cuda.Event() for _ in range(2)]      # the buffer pair holds the step's inputs
+        free = [torch.cuda.Event() for _ in range(2)]       # the step that used the buffer pair is through with it
 
-        def e2e_step():
+        def start_copy(i):
+            k = i & 1
+            copy_stream.wait_event(free[k])                 # (never recorded yet: returns at once)
+            with torch.cuda.stream(copy_stream), torch.no_grad():
+                bufs[k][0].copy_(hS, non_blocking=True)
+                bufs[k][1].copy_(hT, non_blocking=True)
+                ready[k].record(copy_stream)
+
+        def e2e_step(i, prefetch):
+            k = i & 1
+            dS_in, dT_in = bufs[k]
             dS_in.grad = None
-            with torch.no_grad():
-                dS_in.copy_(hS, non_blocking=True)
-                dT_in.copy_(hT, non_blocking=True)
+            torch.cuda.current_stream().wait_event(ready[k])
+            if prefetch:
+                start_copy(i + 1)
             losses = dl(feats(dS_in), feats(dT_in), gt, 1, None, None)
             total, log_vars = sdist.parse_losses(losses)     # one packed all-reduce + ONE D2H read per step
             total.backward()
+            free[k].record()
             return log_vars
 
-        n_e2e = max(3, min(args.steps, 10))
-        for _ in range(2):
-            e2e_step()
+        def e2e_run(n):
+            start_copy(0)
+            for i in range(n):
+                e2e_step(i, i + 1 < n)
+
+        n_e2e = max(4, min(args.steps, 10))
+        e2e_run(2)
         sync_all()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(n_e2e):
-            e2e_step()
+        e2e_run(n_e2e)
         b.record()
         sync_all()
         ems = a.elapsed_time(b)
@@ -474,8 +493,10 @@ def run_ours(args, rank, local_rank, world):
             ems = tt.item()
         e2e = {'value': world * B_PER_GPU * H * W / (ems / n_e2e * 1e-3) / 1e6, 'unit': UNIT,
                'h2d_bytes_per_step': 2 * numel * 4, 'd2h_bytes_per_step': 3 * 4, 'steps': n_e2e,
-               'ms_per_step': ems / n_e2e}
-        del dS_in, dT_in
+               'ms_per_step': ems / n_e2e,
+               'pipelining': 'inputs double-buffered: the H2D of step k+1 (copy stream) overlaps the kernels and the result '
+                             'read of step k; every step copies its own inputs and reads its own result inside the timed region'}
+        del bufs
 
     extra = None
     if args.extra and world == 1:
