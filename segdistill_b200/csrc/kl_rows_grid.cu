@@ -6,7 +6,8 @@
 // thread-block cluster of 8 - but only 15 such clusters fit the GPU's GPCs: 120 of 148 SMs work.  Here the row is
 // spread over CTAs that need not be neighbours: the grid is launched cooperatively (one CTA per SM, all resident),
 // a UNIT is a run of 1 .. 4 chunks (4096 elements of S and of T each) of one row of the smaller-group loss (4; for
-// short work lists 1 for the tail: see "units" below), unit u belongs to CTA u % grid - the units of one row are worked on at the same time by different SMs - and the
+// short work lists 1 for the tail: see "units" below), unit u belongs to CTA u % grid - the units of one row are
+// worked on at the same time by different SMs - and the
 // softmax statistics of a unit travel as an epoch-tagged packet through global memory (L2), like in
 // kl_rows_stream.cu, instead of through distributed shared memory.  Between the statistics and the gradient a unit
 // is PARKED IN TENSOR MEMORY, as in the cluster kernel: 8 chunk slots per SM, so up to eight chunks are in flight
@@ -22,6 +23,10 @@
 //   3 gather     the packets of the row-mates of a unit (warp i: the CTA's units j % 3 == i), merged (row of the
 //     warps      smaller-group loss: the mates of that row only; row of the larger-group loss: all of them) -> the row
 //                statistics the gradient warps wait for; the KL terms of the rows whose first unit is the CTA's.
+//
+// The same kernel walks the work list of SEVERAL (student, teacher) pairs (template parameter MULTI,
+// sd_kl_rows_group_fwd_bwd: one loss per pair, temperature / weight / tensors per unit).  The sums of the park warps
+// and the gradient use two fp32 per instruction (FFMA2 / FADD2 / FMUL2, common.cuh).
 //
 // Geometry contract (cabi.cu): HW % 128 == 0 (a warp's 32 consecutive 4-element vectors are all inside or all outside
 // a unit), units of whole chunks (the last unit of a row may be shorter), at most 64 units per row of any fused loss
