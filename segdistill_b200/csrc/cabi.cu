@@ -185,6 +185,14 @@ bool group_prefers_grid() {
     const char* e = std::getenv("SEGDISTILL_GROUP_GRID");
     return e ? (std::atoi(e) != 0) : true;
 }
+int pix_cols_bf16() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = std::getenv("SEGDISTILL_PIX_COLS");
+        v = e && std::atoi(e) == 64 ? 64 : 32;
+    }
+    return v;
+}
 bool prefer_grid() {
     static int v = -1;
     if (v < 0) {
@@ -735,14 +743,17 @@ int sd_kl_pixels_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl, 
     p.cta_part = reinterpret_cast<float*>(ws + wl.off_cta);
     p.nparts = (int)wl.nparts;
 
-    const int tile_px = sd::kl_pixels_tile_pixels(bf16);
+    // bf16: tiles of 32 thread columns (64 pixels), 256 threads, two CTAs per SM (SEGDISTILL_PIX_COLS=64: the one-CTA layout)
+    const int cols = bf16 ? pix_cols_bf16() : 64;
+    const int tile_px = sd::kl_pixels_tile_pixels(bf16, cols);
     p.tiles_per_sample = (HW + tile_px - 1) / tile_px;
     p.total_tiles = (long long)B * p.tiles_per_sample;
-    p.stage_bytes = (unsigned)C * 256u;
-    // ring depth: as many stages as fit next to the reduction scratch (at most 4)
+    p.stage_bytes = (unsigned)C * (unsigned)cols * 4u;
+    // ring depth: as many stages as fit next to the reduction scratch (at most 4), in the CTA's share of the SM
+    const size_t smem_cap = cols == 32 ? 112u * 1024u : 227u * 1024u;
     int nstages = 0;
     for (int n = 4; n >= 1; --n) {
-        if (sd::pix_tma_smem_bytes(C, bf16 ? 2 : 1, n) <= 227u * 1024u) {
+        if (sd::pix_tma_smem_bytes(C, bf16 ? 2 : 1, n, cols) <= smem_cap) {
             nstages = n;
             break;
         }
@@ -770,8 +781,9 @@ int sd_kl_pixels_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl, 
         alignas(64) CUtensorMap mS, mT;
         if (!encode_pixel_map(&mS, S, B, C, HW, dtype, tile_px) || !encode_pixel_map(&mT, T, B, C, HW, dtype, tile_px))
             return (int)cudaErrorInvalidValue;
-        int grid = (int)(p.total_tiles < dev.sms ? p.total_tiles : dev.sms);
-        e = sd::launch_kl_pixels_tma(&mS, &mT, p, bf16, grid, sd::pix_tma_smem_bytes(C, bf16 ? 2 : 1, nstages), st);
+        const long long ctas = (long long)dev.sms * (cols == 32 ? 2 : 1);
+        int grid = (int)(p.total_tiles < ctas ? p.total_tiles : ctas);
+        e = sd::launch_kl_pixels_tma(&mS, &mT, p, bf16, cols, grid, sd::pix_tma_smem_bytes(C, bf16 ? 2 : 1, nstages, cols), st);
         g_launches += 1;
         t_last_kernel = "kl_pixels_tma_kernel";
     } else {

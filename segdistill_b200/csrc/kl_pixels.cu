@@ -41,18 +41,21 @@ struct PixTraits<__nv_bfloat16> {
     static __device__ __forceinline__ uint32_t pack(const float* f) { return Elem<__nv_bfloat16>::pack2(f[0], f[1]); }
 };
 
-size_t pix_tma_smem_bytes(int C, int pxt, int nstages) {
-    return (size_t)nstages * 2 * (size_t)C * kPixRowBytes          // ring
-           + 2 * (size_t)kPixCG * kPixCols * pxt * sizeof(float4)  // red_max, red_sum
+// cols: thread columns of a tile - 64 (512 threads, one CTA per SM) or 32 (256 threads, two CTAs per SM: their phases
+// - loads, maxima, exponentials, gradient - overlap; the bf16 kernel is not HBM-bound)
+size_t pix_tma_smem_bytes(int C, int pxt, int nstages, int cols) {
+    return (size_t)nstages * 2 * (size_t)C * cols * 4              // ring
+           + 2 * (size_t)kPixCG * cols * pxt * sizeof(float4)      // red_max, red_sum
            + 128;                                                  // barriers
 }
 
 // EXACT: C > 8 * (CPT - 1), i.e. only the last of a thread's CPT channel slots can be missing - the channel guards
 // of the other slots fold away at compile time (C = 150 with CPT = 19; the guards were a quarter of the instructions)
-template <typename T, int CPT, bool AT, bool EXACT>
-__global__ void __launch_bounds__(kPixThreads, 1)
+template <typename T, int CPT, bool AT, bool EXACT, int COLS>
+__global__ void __launch_bounds__(COLS * kPixCG, COLS == 32 ? 2 : 1)
 kl_pixels_tma_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUtensorMap mapT,
                      const PixParams p) {
+    constexpr int kPixCols = COLS;     // (shadows the default: this instantiation's thread columns)
     constexpr int PXT = PixTraits<T>::PXT;
     constexpr int P = kPixCols * PXT;  // pixels per tile
 
@@ -98,7 +101,7 @@ kl_pixels_tma_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_cons
     // ============================ compute ============================
     const int tid = threadIdx.x;
     const int col = tid & (kPixCols - 1);
-    const int cg = tid >> 6;
+    const int cg = tid / kPixCols;
     const float c2 = p.c2;
     float s[CPT * PXT], t[CPT * PXT];
     float acc_kl = 0.f, acc_at = 0.f;  // cg == 0 threads only, in tile order
@@ -298,8 +301,8 @@ kl_pixels_tma_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_cons
     if (tid < 32) {
         unsigned ticket = 0;
         if (lane == 0) {
-            __stcg(&p.cta_part[blockIdx.x], scratch[0] + scratch[2]);
-            __stcg(&p.cta_part[p.nparts + blockIdx.x], scratch[1] + scratch[3]);
+            __stcg(&p.cta_part[blockIdx.x], scratch[0] + (kPixCols == 64 ? scratch[2] : 0.f));
+            __stcg(&p.cta_part[p.nparts + blockIdx.x], scratch[1] + (kPixCols == 64 ? scratch[3] : 0.f));
             __threadfence();
             ticket = atomicAdd(&p.ctrl[0], 1u);
         }
@@ -424,50 +427,55 @@ __global__ void __launch_bounds__(1024) kl_pixels_generic_finalize(const PixPara
 // ====================================================================================================
 // host launchers
 // ====================================================================================================
-template <typename T, int CPT, bool AT>
+template <typename T, int CPT, bool AT, int COLS>
 static cudaError_t launch_pix_tma_t(const CUtensorMap& mS, const CUtensorMap& mT, const PixParams& p, int grid,
                                     size_t smem, cudaStream_t stream) {
     const bool exact = p.C > kPixCG * (CPT - 1);
     cudaError_t e;
     if (exact) {
-        auto kern = kl_pixels_tma_kernel<T, CPT, AT, true>;
+        auto kern = kl_pixels_tma_kernel<T, CPT, AT, true, COLS>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kern<<<grid, kPixThreads, smem, stream>>>(mS, mT, p);
+        kern<<<grid, COLS * kPixCG, smem, stream>>>(mS, mT, p);
     } else {
-        auto kern = kl_pixels_tma_kernel<T, CPT, AT, false>;
+        auto kern = kl_pixels_tma_kernel<T, CPT, AT, false, COLS>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kern<<<grid, kPixThreads, smem, stream>>>(mS, mT, p);
+        kern<<<grid, COLS * kPixCG, smem, stream>>>(mS, mT, p);
     }
     return cudaGetLastError();
 }
 
-template <typename T, bool AT>
+template <typename T, bool AT, int COLS>
 static cudaError_t launch_pix_tma_c(const CUtensorMap& mS, const CUtensorMap& mT, const PixParams& p, int grid,
                                     size_t smem, cudaStream_t stream) {
-    if (p.C <= 3 * kPixCG) return launch_pix_tma_t<T, 3, AT>(mS, mT, p, grid, smem, stream);
-    if (p.C <= 8 * kPixCG) return launch_pix_tma_t<T, 8, AT>(mS, mT, p, grid, smem, stream);
-    if (p.C <= 19 * kPixCG) return launch_pix_tma_t<T, 19, AT>(mS, mT, p, grid, smem, stream);
-    if (sizeof(T) == 4 && p.C <= 32 * kPixCG) return launch_pix_tma_t<T, (sizeof(T) == 4 ? 32 : 19), AT>(mS, mT, p, grid, smem, stream);
+    if (p.C <= 3 * kPixCG) return launch_pix_tma_t<T, 3, AT, COLS>(mS, mT, p, grid, smem, stream);
+    if (p.C <= 8 * kPixCG) return launch_pix_tma_t<T, 8, AT, COLS>(mS, mT, p, grid, smem, stream);
+    if (p.C <= 19 * kPixCG) return launch_pix_tma_t<T, 19, AT, COLS>(mS, mT, p, grid, smem, stream);
+    if (sizeof(T) == 4 && p.C <= 32 * kPixCG) return launch_pix_tma_t<T, (sizeof(T) == 4 ? 32 : 19), AT, COLS>(mS, mT, p, grid, smem, stream);
     return cudaErrorInvalidValue;
 }
 
 // largest channel count the TMA kernel holds in registers
 int kl_pixels_tma_max_channels(bool bf16) { return (bf16 ? 19 : 32) * kPixCG; }
-int kl_pixels_tile_pixels(bool bf16) { return kPixCols * (bf16 ? 2 : 1); }
+int kl_pixels_tile_pixels(bool bf16, int cols) { return cols * (bf16 ? 2 : 1); }
 
-cudaError_t launch_kl_pixels_tma(const void* mapS, const void* mapT, const PixParams& p, bool bf16, int grid,
+cudaError_t launch_kl_pixels_tma(const void* mapS, const void* mapT, const PixParams& p, bool bf16, int cols, int grid,
                                  size_t smem, cudaStream_t stream) {
     const CUtensorMap& mS = *static_cast<const CUtensorMap*>(mapS);
     const CUtensorMap& mT = *static_cast<const CUtensorMap*>(mapT);
     const bool at = p.at_gcoef != 0.f || p.at_loss != nullptr;
-    if (bf16) {
-        return at ? launch_pix_tma_c<__nv_bfloat16, true>(mS, mT, p, grid, smem, stream)
-                  : launch_pix_tma_c<__nv_bfloat16, false>(mS, mT, p, grid, smem, stream);
+    if (bf16 && cols == 32) {
+        return at ? launch_pix_tma_c<__nv_bfloat16, true, 32>(mS, mT, p, grid, smem, stream)
+                  : launch_pix_tma_c<__nv_bfloat16, false, 32>(mS, mT, p, grid, smem, stream);
     }
-    return at ? launch_pix_tma_c<float, true>(mS, mT, p, grid, smem, stream)
-              : launch_pix_tma_c<float, false>(mS, mT, p, grid, smem, stream);
+    if (cols != 64) return cudaErrorInvalidValue;
+    if (bf16) {
+        return at ? launch_pix_tma_c<__nv_bfloat16, true, 64>(mS, mT, p, grid, smem, stream)
+                  : launch_pix_tma_c<__nv_bfloat16, false, 64>(mS, mT, p, grid, smem, stream);
+    }
+    return at ? launch_pix_tma_c<float, true, 64>(mS, mT, p, grid, smem, stream)
+              : launch_pix_tma_c<float, false, 64>(mS, mT, p, grid, smem, stream);
 }
 
 cudaError_t launch_kl_pixels_generic(const PixParams& p, bool bf16, cudaStream_t stream) {

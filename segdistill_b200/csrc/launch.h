@@ -49,12 +49,12 @@ cudaError_t launch_kl_pixels_up(const UpParams& p, bool bf16, int sms, cudaStrea
 cudaError_t launch_ce_up(const CeParams& p, bool bf16, int sms, cudaStream_t stream);
 
 // kl_pixels.cu   (mapS/mapT point at CUtensorMap objects)
-cudaError_t launch_kl_pixels_tma(const void* mapS, const void* mapT, const PixParams& p, bool bf16, int grid,
+cudaError_t launch_kl_pixels_tma(const void* mapS, const void* mapT, const PixParams& p, bool bf16, int cols, int grid,
                                  size_t smem, cudaStream_t stream);
 cudaError_t launch_kl_pixels_generic(const PixParams& p, bool bf16, cudaStream_t stream);
-size_t pix_tma_smem_bytes(int C, int pxt, int nstages);
+size_t pix_tma_smem_bytes(int C, int pxt, int nstages, int cols);   // cols: 64 (one CTA per SM) or 32 (bf16: two)
 int kl_pixels_tma_max_channels(bool bf16);
-int kl_pixels_tile_pixels(bool bf16);
+int kl_pixels_tile_pixels(bool bf16, int cols);
 
 // corr_gemm.cu   (maps: CUtensorMap[4] built by cabi.cu with the box rows cgd_corr_geometry reports)
 size_t cgd_corr_workspace_bytes(int B, int C, int HW, int group);
