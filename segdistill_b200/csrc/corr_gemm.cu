@@ -252,7 +252,7 @@ corr_gram_kernel(const __grid_constant__ CUtensorMap mapS0, const __grid_constan
 // ====================================================================================================
 // K2: sum the splits, keep the block-diagonal, loss, A operand of K3
 // ====================================================================================================
-constexpr int kMaskPerCta = 512;    // Gram entries per CTA of K2
+constexpr int kMaskPerCta = 2048;   // Gram entries per CTA of K2
 
 template <bool BF16>
 __global__ void __launch_bounds__(256) corr_mask_kernel(const CorrParams p) {
@@ -265,26 +265,52 @@ __global__ void __launch_bounds__(256) corr_mask_kernel(const CorrParams p) {
     const float* part = p.partial + (size_t)blk * p.ksplit * (size_t)M * p.CBp;
     unsigned char* dm = p.dmask + (size_t)blk * p.dmask_bytes;
     constexpr int ES = BF16 ? 2 : 4;
-    constexpr int CH = 16 / ES;                                    // elements per 16-byte chunk
+    constexpr int CH = 16 / ES;                                    // elements per 16-byte chunk of the A operand
     const size_t tile_bytes = (size_t)(p.CBp / CH) * 2048;         // A operand of one 128-row tile
     double acc = 0.0;
-    const int end = min(M * p.CBp, (chunk + 1) * kMaskPerCta);
-    for (int idx = chunk * kMaskPerCta + threadIdx.x; idx < end; idx += 256) {
-        const int i = idx / p.CBp, j = idx - i * p.CBp;
-        float e = 0.f;
-#pragma unroll 4
-        for (int s = 0; s < p.ksplit; ++s) e += __ldcs(&part[(size_t)s * M * p.CBp + idx]);   // fixed order
-        const bool keep = i < c_real && j < c_real && i / p.g == j / p.g;
-        const float d = keep ? e * p.inv_hw : 0.f;
-        acc += (double)d * (double)d;
+    // one thread = one 16-byte chunk of the operand = CH consecutive columns of one row (CBp % 16 == 0: never straddles)
+    const int vend = min(M * p.CBp, (chunk + 1) * kMaskPerCta) / CH;
+    for (int v = chunk * (kMaskPerCta / CH) + threadIdx.x; v < vend; v += 256) {
+        const int idx = v * CH;
+        const int i = idx / p.CBp, j0 = idx - i * p.CBp;
+        float e[CH];
+#pragma unroll
+        for (int q = 0; q < CH; ++q) e[q] = 0.f;
+        for (int s = 0; s < p.ksplit; ++s) {                        // fixed order
+            const float4* src = reinterpret_cast<const float4*>(part + (size_t)s * M * p.CBp + idx);
+#pragma unroll
+            for (int q = 0; q < CH / 4; ++q) {
+                const float4 x = __ldcs(src + q);
+                e[4 * q] += x.x;
+                e[4 * q + 1] += x.y;
+                e[4 * q + 2] += x.z;
+                e[4 * q + 3] += x.w;
+            }
+        }
+        float a[CH];
+        const int gi = i / p.g;
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+            const int j = j0 + q;
+            const bool keep = i < c_real && j < c_real && gi == j / p.g;
+            const float d = keep ? e[q] * p.inv_hw : 0.f;
+            acc += (double)d * (double)d;
+            a[q] = p.dcoef * d;
+        }
         // canonical K-major layout without swizzle: 8-row x 16-byte core matrices; row groups 128 bytes apart
         // (SBO), 16-byte K chunks 2048 bytes apart (LBO); one such operand per 128-row tile
         const int m = i >> 7, r = i & 127;
-        const size_t off = (size_t)m * tile_bytes + (size_t)(j / CH) * 2048 + (size_t)(r >> 3) * 128 + (size_t)(r & 7) * 16 +
-                           (size_t)(j % CH) * ES;
-        const float a = p.dcoef * d;
-        if (BF16) *reinterpret_cast<__nv_bfloat16*>(dm + off) = __float2bfloat16_rn(a);
-        else *reinterpret_cast<float*>(dm + off) = a;
+        const size_t off = (size_t)m * tile_bytes + (size_t)(j0 / CH) * 2048 + (size_t)(r >> 3) * 128 + (size_t)(r & 7) * 16;
+        if (BF16) {
+            uint4 w;
+            w.x = Elem<__nv_bfloat16>::pack2(a[0], a[1]);
+            w.y = Elem<__nv_bfloat16>::pack2(a[2], a[3]);
+            w.z = Elem<__nv_bfloat16>::pack2(a[CH - 4], a[CH - 3]);
+            w.w = Elem<__nv_bfloat16>::pack2(a[CH - 2], a[CH - 1]);
+            *reinterpret_cast<uint4*>(dm + off) = w;
+        } else {
+            *reinterpret_cast<float4*>(dm + off) = make_float4(a[0], a[1], a[2], a[3]);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
@@ -518,8 +544,9 @@ static CorrPlan corr_plan(int B, int C, int HW, int group, int dtype) {
     p.rows0 = p.CBp < 128 ? p.CBp : 128;
     p.rows1 = p.MT == 2 ? p.CBp - 128 : 0;
     const int nk = (HW + p.kbox - 1) / p.kbox;
-    // K1: about one wave of CTAs (every split costs a partial Gram in the workspace), at least 4 K steps each
-    int want = (kPlanSMs + p.nblocks - 1) / p.nblocks;
+    // K1: ONE wave of CTAs, never a second, partly filled one (two 128-row tiles: 198 KB of stages, one CTA per SM; one
+    // tile: two CTAs per SM); every split costs a partial Gram in the workspace; at least 4 K steps each
+    int want = kPlanSMs * (p.MT == 1 ? 2 : 1) / p.nblocks;
     p.ksplit = want < 1 ? 1 : (want > nk / 4 ? (nk / 4 > 0 ? nk / 4 : 1) : want);
     if (p.ksplit > 16) p.ksplit = 16;
     p.dmask_bytes = p.MT * (p.CBp * es / 16) * 2048;
@@ -528,7 +555,7 @@ static CorrPlan corr_plan(int B, int C, int HW, int group, int dtype) {
     const int a_tile = ((p.CBp * es / 16) * 2048 + 1023) & ~1023;
     while (p.gboxes > 1 && a_tile + 2 * p.gboxes * p.MT * kGTileBytes > 200 * 1024) --p.gboxes;
     const int nt = (HW + p.gboxes * p.kbox - 1) / (p.gboxes * p.kbox);
-    int want3 = (2 * kPlanSMs + p.nblocks * p.MT - 1) / (p.nblocks * p.MT);   // about two waves
+    int want3 = 2 * kPlanSMs / (p.nblocks * p.MT);                            // two waves (one CTA per SM), not a third
     p.nsplit = want3 < 1 ? 1 : (want3 > nt ? nt : want3);
     if (p.nsplit > 64) p.nsplit = 64;
     size_t o = kArenaBytes;
