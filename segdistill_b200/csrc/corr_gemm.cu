@@ -289,10 +289,15 @@ __global__ void __launch_bounds__(256) corr_mask_kernel(const CorrParams p) {
         }
         float a[CH];
         const int gi = i / p.g;
+        int gj = j0 / p.g, rem = j0 - gj * p.g;                     // group of column j0 + q, walked without divisions
 #pragma unroll
         for (int q = 0; q < CH; ++q) {
             const int j = j0 + q;
-            const bool keep = i < c_real && j < c_real && gi == j / p.g;
+            const bool keep = i < c_real && j < c_real && gi == gj;
+            if (++rem == p.g) {
+                rem = 0;
+                ++gj;
+            }
             const float d = keep ? e[q] * p.inv_hw : 0.f;
             acc += (double)d * (double)d;
             a[q] = p.dcoef * d;
