@@ -573,6 +573,7 @@ def extra_configs(dev):
     """Other BASELINE configs (parity-test cases, timed for information only)."""
     import torch
     import segdistill_b200 as sd
+    from segdistill_b200 import _cabi
     out = {}
 
     def timeit(fn, n=20):

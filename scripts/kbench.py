@@ -150,8 +150,12 @@ def main():
         if only and name not in only:
             continue
         s, t = pair(shape, dtype)
-        for _ in range(5):
-            fn(s, t)
+        try:
+            for _ in range(5):
+                fn(s, t)
+        except _cabi.SegDistillUnsupported:
+            print(f'{name:20s} (the forced kernel does not take this layout)', flush=True)
+            continue
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

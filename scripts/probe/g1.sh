@@ -1,2 +1,4 @@
 mkdir -p gpurun_out
-timeout 1100 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 200 -k "not full_size and not full_batch and not b16 and not properties and not cfg3 and not occupies and not two_streams" > gpurun_out/memcheck_all.log 2>&1; echo "memcheck rc=$?"; tail -5 gpurun_out/memcheck_all.log
+timeout 500 python -m pytest tests -x -q -m gpu > gpurun_out/tests.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/tests.log
+timeout 300 python bench.py --extra --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_extra.log 2> gpurun_out/bench_extra.err; echo "extra rc=$?"; tail -c 400 gpurun_out/bench_extra.err
+timeout 300 python scripts/kbench.py > gpurun_out/kbench.log 2>&1; echo "kbench rc=$?"; tail -3 gpurun_out/kbench.log

@@ -318,13 +318,14 @@ int rows_dispatch(RowsCall c) {
         const long long lv = (long long)g_big * hwv;
         const long long rv0 = (long long)g0 * hwv;
         const long long slice_cap = (long long)sd::kClusterMaxChunks * sd::kClusterChunkVecs;
-        // (from 2 CTAs on: the summaries travel by st.async into the cluster's shared memory, which a one-CTA "cluster"
-        //  does not have - compute-sanitizer rejects it; rows that fit one CTA's tensor memory take the grid-resident kernel)
-        for (int nc = 2; nc <= sd::kClusterMaxSize && !cluster_ok; nc *= 2) {
+        // The smallest power-of-two cluster whose slices fit.  Rows that fit ONE CTA are not for this kernel (its summaries
+        // travel by st.async into the cluster's shared memory, which a one-CTA "cluster" does not have: compute-sanitizer
+        // rejects it) - the grid-resident kernel serves them.
+        for (int nc = 1; nc <= sd::kClusterMaxSize && !cluster_ok; nc *= 2) {
             long long slv = (lv + nc - 1) / nc;
             slv = (slv + sd::kClusterChunkVecs - 1) / sd::kClusterChunkVecs * sd::kClusterChunkVecs;
             if (slv > slice_cap) continue;
-            if (lv <= (long long)(nc - 1) * slv) break;           // a CTA of the cluster would never own a slice
+            if (nc == 1) break;
             if (rv0 < 512) break;
             if (slv / rv0 + 2 > sd::kClusterMaxPieces) continue;  // more, shorter slices
             cg.nc = nc;
