@@ -261,6 +261,10 @@ SD_API int sd_ifvd_class_map(const int64_t* target, int32_t* cls, int B, int Ht,
 /* ------------------------------------------------------------------ backward helper */
 /* dS *= *grad_output (a device scalar); exits without touching dS when it equals 1. */
 SD_API int sd_scale_grad(void* dS, int64_t numel, int dtype, const float* grad_output, void* stream);
+/* The same for the n_tensors <= 8 gradients of a grouped launch (sd_kl_rows_group_fwd_bwd; opts.py:87-112 sums the entries'
+ * losses, so every layer's gradient meets its own upstream factor in backward): dS[k] *= *grad_outputs[k], one launch. */
+SD_API int sd_scale_grad_group(int n_tensors, void* const* dS, const int64_t* numel, int dtype,
+                               const float* const* grad_outputs, void* stream);
 
 /* Two upstream gradients for one fused two-loss dS: if *grad_output0 == *grad_output1, dS *= that value
  * and *nonuniform_flag = 0; else dS is left alone and *nonuniform_flag = 1 (see run_if above). */

@@ -32,7 +32,7 @@ EXPORTS = (
     'sd_mse_workspace_bytes', 'sd_mse_fwd_bwd', 'sd_ifvd_sim_workspace_bytes', 'sd_ifvd_sim_fwd_bwd', 'sd_ifvd_max_channels',
     'sd_ifvd_class_map', 'sd_scale_grad',
     'sd_cgd_corr_workspace_bytes', 'sd_cgd_corr_fwd_bwd', 'sd_log_push', 'sd_ce_up_workspace_bytes', 'sd_ce_up_fwd_bwd',
-    'sd_kl_rows_group_workspace_bytes', 'sd_kl_rows_group_fwd_bwd',
+    'sd_kl_rows_group_workspace_bytes', 'sd_kl_rows_group_fwd_bwd', 'sd_scale_grad_group',
     'sd_launch_count', 'sd_last_kernel',
 )
 
@@ -104,6 +104,8 @@ def load():
         lib.sd_ifvd_class_map.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
         lib.sd_scale_grad.restype = i32
         lib.sd_scale_grad.argtypes = [vp, i64, i32, vp, vp]
+        lib.sd_scale_grad_group.restype = i32
+        lib.sd_scale_grad_group.argtypes = [i32, vp, vp, i32, vp, vp]
         lib.sd_cgd_corr_workspace_bytes.restype = sz
         lib.sd_cgd_corr_workspace_bytes.argtypes = [i32, i32, i32, i32]
         lib.sd_cgd_corr_fwd_bwd.restype = i32
@@ -521,6 +523,27 @@ def scale_grad_(ds: torch.Tensor, grad_output: torch.Tensor):
         if rc:
             _check(rc)
     return ds
+
+
+def scale_grad_group_(dss, grad_outputs):
+    """In place ``dss[k] *= grad_outputs[k]`` for the (same-dtype, same-device) gradients of a grouped launch: ONE launch,
+    a no-op per tensor whose factor is 1."""
+    lib = _lib or load()
+    n = len(dss)
+    dev = dss[0].device
+    gs = []
+    for g in grad_outputs:
+        if g.device != dev or g.dtype is not torch.float32 or g.numel() != 1 or g.requires_grad:
+            g = g.detach().to(device=dev, dtype=torch.float32).reshape(1)
+        gs.append(g)
+    ptrs = (ctypes.c_void_p * n)(*[d.data_ptr() for d in dss])
+    gptr = (ctypes.c_void_p * n)(*[g.data_ptr() for g in gs])
+    numel = (ctypes.c_int64 * n)(*[d.numel() for d in dss])
+    with _on(dev):
+        rc = lib.sd_scale_grad_group(n, ptrs, numel, _dtype_code(dss[0]), gptr, _stream_ptr(dev))
+        if rc:
+            _check(rc)
+    return dss
 
 
 def log_push(values: torch.Tensor, ring: torch.Tensor, cursor: torch.Tensor):

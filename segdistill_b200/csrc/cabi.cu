@@ -1019,6 +1019,33 @@ int sd_mse_fwd_bwd(const void* S, const void* T, void* dS, float* loss, int64_t 
     return e == cudaSuccess ? SD_OK : (int)e;
 }
 
+int sd_scale_grad_group(int n_tensors, void* const* dS, const int64_t* numel, int dtype, const float* const* grad_outputs,
+                        void* stream) {
+    if (!dS || !numel || !grad_outputs) return SD_ERR_NULL;
+    if (n_tensors < 1 || n_tensors > sd::kMaxSegs) return SD_ERR_VALUE;
+    if (dtype != SD_F32 && dtype != SD_BF16) return SD_ERR_DTYPE;
+    DeviceInfo& dev = device_info();
+    if (dev.cc_major != 10) return SD_ERR_DEVICE;
+    long long nn[sd::kMaxSegs], most = 0;
+    for (int k = 0; k < n_tensors; ++k) {
+        if (!dS[k] || !grad_outputs[k]) return SD_ERR_NULL;
+        if (numel[k] <= 0) return SD_ERR_SHAPE;
+        nn[k] = numel[k];
+        most = std::max(most, nn[k]);
+    }
+    const int VE = 16 / elem_size(dtype);
+    long long want = (most / VE + 255) / 256;
+    if (want < 1) want = 1;
+    int grid = dev.sms * 8 / n_tensors;
+    if (grid < 1) grid = 1;
+    if (want < grid) grid = (int)want;
+    cudaError_t e = sd::launch_scale_grad_group(n_tensors, dS, nn, dtype == SD_BF16, grad_outputs, grid,
+                                                static_cast<cudaStream_t>(stream));
+    g_launches += 1;
+    t_last_kernel = "scale_grad_group_kernel";
+    return e == cudaSuccess ? SD_OK : (int)e;
+}
+
 int sd_scale_grad(void* dS, int64_t numel, int dtype, const float* grad_output, void* stream) {
     if (!dS || !grad_output) return SD_ERR_NULL;
     if (dtype != SD_F32 && dtype != SD_BF16) return SD_ERR_DTYPE;

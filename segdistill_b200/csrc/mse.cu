@@ -97,6 +97,54 @@ __global__ void __launch_bounds__(256) scale_grad_kernel(T* __restrict__ x, long
     for (long long i = done + gid; i < n; i += stride) E::store(x + i, E::load(x + i) * gv);
 }
 
+// The same for the tensors of a grouped launch (sd_kl_rows_group_fwd_bwd): tensor k = blockIdx.y, dS[k] *= *g[k]; ONE launch
+// for all of them (a dispatcher step over several layers otherwise pays one launch per layer in its backward).
+struct ScaleGroup {
+    void* x[kMaxSegs];
+    const float* g[kMaxSegs];
+    long long n[kMaxSegs];
+};
+template <typename T>
+__global__ void __launch_bounds__(256) scale_grad_group_kernel(const ScaleGroup a) {
+    using E = Elem<T>;
+    using vec_t = typename E::vec_t;
+    constexpr int VE = E::kVec;
+    const int k = blockIdx.y;
+    const float gv = *a.g[k];
+    if (gv == 1.0f) return;
+    T* x = static_cast<T*>(a.x[k]);
+    const long long n = a.n[k];
+    const long long stride = (long long)gridDim.x * 256;
+    const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+    long long done = 0;
+    if ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+        const long long nvec = n / VE;
+        vec_t* vx = reinterpret_cast<vec_t*>(x);
+        for (long long i = gid; i < nvec; i += stride) {
+            float v[VE];
+            E::unpack(vx[i], v);
+#pragma unroll
+            for (int q = 0; q < VE; ++q) v[q] *= gv;
+            vx[i] = E::pack(v);
+        }
+        done = nvec * VE;
+    }
+    for (long long i = done + gid; i < n; i += stride) E::store(x + i, E::load(x + i) * gv);
+}
+cudaError_t launch_scale_grad_group(int n_tensors, void* const* dS, const long long* numel, bool bf16, const float* const* g,
+                                    int grid, cudaStream_t stream) {
+    ScaleGroup a = {};
+    for (int k = 0; k < n_tensors; ++k) {
+        a.x[k] = dS[k];
+        a.g[k] = g[k];
+        a.n[k] = numel[k];
+    }
+    const dim3 gr((unsigned)grid, (unsigned)n_tensors);
+    if (bf16) scale_grad_group_kernel<__nv_bfloat16><<<gr, 256, 0, stream>>>(a);
+    else scale_grad_group_kernel<float><<<gr, 256, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
 // Backward of a fused two-loss launch: dS was computed for d(total)/d(loss_k) == 1.  When the two
 // upstream gradients are equal (the loss terms enter the total as a plain sum, possibly times one
 // loss scale) dS is scaled in place and *flag = 0; otherwise *flag = 1 and the caller's conditional

@@ -182,11 +182,13 @@ class _KLRowsGroup(torch.autograd.Function):
         if dss is None:                     # a second backward through this node (retain_graph=True): rebuild
             maps = ctx.saved_tensors
             dss = _cabi.kl_rows_group(maps[0::2], maps[1::2], *ctx.cfg)[1]
+        live = [k for k in range(n) if ctx.needs[k]]
+        _cabi.scale_grad_group_([dss[k] for k in live], [grads[k] for k in live])      # one launch for every layer
         out = [None]
         for k in range(n):
             g = None
             if ctx.needs[k]:
-                g = _cabi.scale_grad_(dss[k], grads[k])
+                g = dss[k]
                 dtype, shape = ctx.meta[k]
                 if g.dtype != dtype:
                     g = g.to(dtype)
