@@ -193,6 +193,16 @@ int pix_cols_bf16() {
     }
     return v;
 }
+// bf16 rows of exactly the register capacity: kl_rows_rm_kernel (row-maximum references, pipelined loads);
+// SEGDISTILL_ROWS_RM=0 keeps kl_rows_tma_kernel
+bool rows_rm() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("SEGDISTILL_ROWS_RM");
+        v = e ? (std::atoi(e) != 0) : 1;
+    }
+    return v != 0;
+}
 bool prefer_grid() {
     static int v = -1;
     if (v < 0) {
@@ -508,9 +518,16 @@ int rows_dispatch(RowsCall c) {
         t_last_kernel = "kl_rows_pack_kernel";
     } else if (path == kRegs) {
         int grid = (int)(p.total_units < dev.sms ? p.total_units : dev.sms);
-        e = sd::launch_kl_rows_tma(p, c.dtype == SD_BF16, grid, st);
+        const bool mse = p.mse_gcoef != 0.f || p.mse_loss != nullptr;
+        const bool whole_rows = p.g_last == 0 && p.nch_full == 1 && row_len == sd::kl_rows_tma_chunk_capacity();
+        if (c.dtype == SD_BF16 && !mse && whole_rows && rows_rm()) {
+            e = sd::launch_kl_rows_rm(p, grid, st);
+            t_last_kernel = "kl_rows_rm_kernel";
+        } else {
+            e = sd::launch_kl_rows_tma(p, c.dtype == SD_BF16, grid, st);
+            t_last_kernel = "kl_rows_tma_kernel";
+        }
         g_launches += 1;
-        t_last_kernel = "kl_rows_tma_kernel";
     } else if (path == kCluster) {
         e = sd::launch_kl_rows_cluster(p, cg, c.dtype == SD_BF16, dev.sms, st, false);
         g_launches += 1;

@@ -49,6 +49,106 @@ __device__ __forceinline__ uint32_t packed_max4(uint32_t m, const uint4& v) {
 }
 __device__ __forceinline__ uint32_t packed_max4(uint32_t m, const float4&) { return m; }
 
+// ================================ TMA issue (thread 0 only) ================================
+// Slots are refilled in ring order.  `free_slots` counts slots every thread has drained: a unit's
+// slots are released by the CTA barrier that follows its ring->register copy.  The state lives in
+// shared memory: only thread 0 touches it, and the 16 compute warps need all 128 registers.
+template <typename T>
+__device__ __forceinline__ void rows_issue_loads(const RowsParams& p, ProducerState& ps, unsigned char* smem, uint64_t* full,
+                                                 int newly_free) {
+    constexpr int VE = Elem<T>::kVec;
+    int free_slots = ps.free_slots + newly_free, v0 = ps.v0, pstage = ps.stage;
+    while (free_slots > 0 && ps.cur.u < p.total_units) {
+        const Unit x = decode_unit(p, ps.cur.b, ps.cur.r);
+        const int nvec = x.len / VE;
+        const int nv = min(kSlotVecs, nvec - v0);
+        const uint32_t bytes = (uint32_t)nv * 16u;
+        mbar_arrive_expect_tx(&full[pstage], 2u * bytes);
+        unsigned char* dst_s = smem + (size_t)pstage * kStageBytes;
+        unsigned char* dst_t = dst_s + kSlotBytes;
+        const int e = x.e0 + v0 * VE;
+        if (p.perm == nullptr) {
+            const size_t off = (((size_t)x.b * p.C + (size_t)x.grp * p.l[0].g) * p.HW + e) * sizeof(T);
+            tma_bulk_g2s(dst_s, static_cast<const char*>(p.S) + off, bytes, &full[pstage], ps.pol);
+            tma_bulk_g2s(dst_t, static_cast<const char*>(p.T) + off, bytes, &full[pstage], ps.pol);
+        } else {
+            // gathered channels: one copy per channel segment
+            int remaining = nv * VE;
+            int cur = e;
+            uint32_t doff = 0;
+            while (remaining > 0) {
+                const int j = cur / p.HW;
+                const int pos = cur - j * p.HW;
+                const int n = min(remaining, p.HW - pos);
+                const size_t off = perm_elem_offset(p, x, cur) * sizeof(T);
+                const uint32_t nb = (uint32_t)n * (uint32_t)sizeof(T);
+                tma_bulk_g2s(dst_s + doff, static_cast<const char*>(p.S) + off, nb, &full[pstage], ps.pol);
+                tma_bulk_g2s(dst_t + doff, static_cast<const char*>(p.T) + off, nb, &full[pstage], ps.pol);
+                doff += nb;
+                cur += n;
+                remaining -= n;
+            }
+        }
+        v0 += kSlotVecs;
+        if (v0 >= nvec) {
+            v0 = 0;
+            ps.cur.advance(p, (int)gridDim.x);
+        }
+        if (++pstage == kStages) pstage = 0;
+        --free_slots;
+    }
+    ps.free_slots = free_slots;
+    ps.v0 = v0;
+    ps.stage = pstage;
+}
+
+// ================================ loss: per-CTA partials, last CTA sums them in a fixed order ================================
+template <bool MSE>
+__device__ __forceinline__ void rows_finish_loss(const RowsParams& p, const ProducerState& ps, int warp, int lane) {
+    if (warp == 0) {
+        unsigned ticket = 0;
+        if (lane == 0) {
+            __stcg(&p.cta_part[blockIdx.x], ps.kl);
+            __stcg(&p.cta_part[kMaxLosses * kMaxGrid + blockIdx.x], ps.sq);
+            __threadfence();
+            ticket = atomicAdd(&p.ctrl[0], 1u);
+        }
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            double kl = 0.0, sq = 0.0;
+            for (int i = lane; i < (int)gridDim.x; i += 32) {
+                kl += (double)__ldcg(&p.cta_part[i]);
+                sq += (double)__ldcg(&p.cta_part[kMaxLosses * kMaxGrid + i]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                kl += __shfl_down_sync(0xffffffffu, kl, o);
+                sq += __shfl_down_sync(0xffffffffu, sq, o);
+            }
+            if (lane == 0) {
+                *p.l[0].loss = (float)((double)p.l[0].loss_scale * kl);
+                if (MSE && p.mse_loss) *p.mse_loss = (float)((double)p.mse_scale * sq);
+                atomicExch(&p.ctrl[0], 0u);
+            }
+        }
+    }
+}
+
+// per-phase cycle counters of threads 0 and 480 (scripts/rows_timing.py; build with SD_NVCC_EXTRA=-DSD_ROWS_TIMING)
+#ifdef SD_ROWS_TIMING
+#define SD_RT_DECL long long rt_acc[6] = {0, 0, 0, 0, 0, 0}, rt_last = 0, rt_rows = 0, rt_begin = clock64();
+#define SD_RT_START rt_last = clock64(); ++rt_rows;
+#define SD_RT_MARK(k) { const long long rt_now = clock64(); rt_acc[k] += rt_now - rt_last; rt_last = rt_now; }
+#define SD_RT_WRITE if (tid == 0 || tid == 480) { unsigned long long* d = p.dbg + blockIdx.x * 16 + (tid ? 8 : 0); \
+    for (int k = 0; k < 6; ++k) d[k] = rt_acc[k]; d[6] = rt_rows; d[7] = clock64() - rt_begin; }
+#else
+#define SD_RT_DECL
+#define SD_RT_START
+#define SD_RT_MARK(k)
+#define SD_RT_WRITE
+#endif
+
 template <typename T, bool MSE>
 __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsParams p) {
     using E = Elem<T>;
@@ -81,55 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
     }
     __syncthreads();
 
-    // ================================ TMA issue (thread 0 only) ================================
-    // Slots are refilled in ring order.  `free_slots` counts slots every thread has drained: a unit's
-    // slots are released by the CTA barrier that follows its ring->register copy.  The state lives in
-    // shared memory: only thread 0 touches it, and the 16 compute warps need all 128 registers.
-    auto issue_loads = [&](int newly_free) {
-        int free_slots = ps.free_slots + newly_free, v0 = ps.v0, pstage = ps.stage;
-        while (free_slots > 0 && ps.cur.u < p.total_units) {
-            const Unit x = decode_unit(p, ps.cur.b, ps.cur.r);
-            const int nvec = x.len / VE;
-            const int nv = min(kSlotVecs, nvec - v0);
-            const uint32_t bytes = (uint32_t)nv * 16u;
-            mbar_arrive_expect_tx(&full[pstage], 2u * bytes);
-            unsigned char* dst_s = smem + (size_t)pstage * kStageBytes;
-            unsigned char* dst_t = dst_s + kSlotBytes;
-            const int e = x.e0 + v0 * VE;
-            if (p.perm == nullptr) {
-                const size_t off = (((size_t)x.b * p.C + (size_t)x.grp * p.l[0].g) * p.HW + e) * sizeof(T);
-                tma_bulk_g2s(dst_s, static_cast<const char*>(p.S) + off, bytes, &full[pstage], ps.pol);
-                tma_bulk_g2s(dst_t, static_cast<const char*>(p.T) + off, bytes, &full[pstage], ps.pol);
-            } else {
-                // gathered channels: one copy per channel segment
-                int remaining = nv * VE;
-                int cur = e;
-                uint32_t doff = 0;
-                while (remaining > 0) {
-                    const int j = cur / p.HW;
-                    const int pos = cur - j * p.HW;
-                    const int n = min(remaining, p.HW - pos);
-                    const size_t off = perm_elem_offset(p, x, cur) * sizeof(T);
-                    const uint32_t nb = (uint32_t)n * (uint32_t)sizeof(T);
-                    tma_bulk_g2s(dst_s + doff, static_cast<const char*>(p.S) + off, nb, &full[pstage], ps.pol);
-                    tma_bulk_g2s(dst_t + doff, static_cast<const char*>(p.T) + off, nb, &full[pstage], ps.pol);
-                    doff += nb;
-                    cur += n;
-                    remaining -= n;
-                }
-            }
-            v0 += kSlotVecs;
-            if (v0 >= nvec) {
-                v0 = 0;
-                ps.cur.advance(p, (int)gridDim.x);
-            }
-            if (++pstage == kStages) pstage = 0;
-            --free_slots;
-        }
-        ps.free_slots = free_slots;
-        ps.v0 = v0;
-        ps.stage = pstage;
-    };
+    auto issue_loads = [&](int newly_free) { rows_issue_loads<T>(p, ps, smem, full, newly_free); };
     if (tid == 0) issue_loads(0);
 
     // ================================ 16 warps, chunk lives in registers ================================
@@ -140,7 +192,9 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
     int par = 0;
 
     UnitCursor cur;
+    SD_RT_DECL
     for (cur.init(p, blockIdx.x); cur.u < p.total_units; cur.advance(p, (int)gridDim.x)) {
+        SD_RT_START
         const Unit x = decode_unit(p, cur.b, cur.r);
         const int nvec = x.len / VE;
         const bool whole = nvec == NV * kThreads;  // every thread holds NV vectors
@@ -217,8 +271,10 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
 
         // every thread holds its elements in registers (the maxima consumed every shared-memory read):
         // hand the unit's slots back to the TMA thread now, so the next loads fly during the exponentials
+        SD_RT_MARK(0)
         __syncthreads();
         if (tid == 0) issue_loads(nslots);
+        SD_RT_MARK(1)
 
         // ---- exponentials (kept in registers), thread-partial sums relative to (ms, mt); a = sum et (at - as) and
         //      dd = sum (et - es) term by term (common.cuh: KL without cancellation).  Against thread-local maxima zs
@@ -278,6 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
             }
         }
         const float zs = zt - dd;
+        SD_RT_MARK(2)
 
         // ---- warp: sums rescaled to the warp maxima (redux.sync for the maxima, transposed butterflies for the sums:
         //      the reductions were 4 of the 27 instructions per element)
@@ -300,6 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
             if (lane == 1) my_red[0] = msw;
             if (lane == 2) my_red[1] = mtw;
         }
+        SD_RT_MARK(3)
         __syncthreads();
 
         // ---- CTA = row: every warp merges the 16 warp records (lanes l and l+16 mirror each other); the sums only
@@ -331,6 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
             if (MSE) ps.sq += SQ;
         }
 
+        SD_RT_MARK(4)
         // ---- gradient straight from registers
         float coef = p.l[0].coef;
         if (p.grad_out[0] != nullptr) coef *= __ldg(p.grad_out[0]);
@@ -387,37 +446,196 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
                 }
             }
         }
+        SD_RT_MARK(5)
     }
+    SD_RT_WRITE
 
-    // ================================ loss: per-CTA partials, last CTA sums them in a fixed order ================================
-    if (warp == 0) {
-        unsigned ticket = 0;
-        if (lane == 0) {
-            __stcg(&p.cta_part[blockIdx.x], ps.kl);
-            __stcg(&p.cta_part[kMaxLosses * kMaxGrid + blockIdx.x], ps.sq);
-            __threadfence();
-            ticket = atomicAdd(&p.ctrl[0], 1u);
-        }
-        ticket = __shfl_sync(0xffffffffu, ticket, 0);
-        if (ticket == gridDim.x - 1) {
-            __threadfence();
-            double kl = 0.0, sq = 0.0;
-            for (int i = lane; i < (int)gridDim.x; i += 32) {
-                kl += (double)__ldcg(&p.cta_part[i]);
-                sq += (double)__ldcg(&p.cta_part[kMaxLosses * kMaxGrid + i]);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                kl += __shfl_down_sync(0xffffffffu, kl, o);
-                sq += __shfl_down_sync(0xffffffffu, sq, o);
-            }
-            if (lane == 0) {
-                *p.l[0].loss = (float)((double)p.l[0].loss_scale * kl);
-                if (MSE && p.mse_loss) *p.mse_loss = (float)((double)p.mse_scale * sq);
-                atomicExch(&p.ctrl[0], 0u);
-            }
-        }
+    rows_finish_loss<MSE>(p, ps, warp, lane);
+}
+
+// ====================================================================================================
+// bf16 rows of exactly 16384 elements: references = the ROW maxima, next row's loads inside the gradient sweep
+// ====================================================================================================
+// The bf16 launch of kl_rows_tma_kernel is not HBM-bound: its phases (ring -> registers with the bf16 -> fp32 unpack on
+// the ALU pipe, exponentials on the MUFU pipe, the reductions' shuffle chains, the gradient) run one after the other
+// between two CTA barriers, each on a different pipe (scripts/rows_timing.py: 1300 + 700 + 2100 + 1200 + 750 cycles per
+// row).  Here
+//   * a row stays PACKED (16 + 16 registers) from the ring until the exponentials, so the unpack runs next to the MUFU
+//     instructions instead of before them;
+//   * the barrier that hands the ring slots back also publishes the warps' maxima: every thread exponentiates against
+//     the ROW maxima, so the sums of threads and warps simply add - no rescale factors (ex2), no merge shifts;
+//   * the next row's ring -> register copy (and its packed maxima) is interleaved with the gradient of this one: the
+//     registers of the exponentials free up vector by vector.
+// Same statistics as everywhere (common.cuh, KL without cancellation): zs, zt, a2 = sum et (at - as), dd = sum (et - es).
+__global__ void __launch_bounds__(kThreads, 1) kl_rows_rm_kernel(const RowsParams p) {
+    using T = __nv_bfloat16;
+    using E = Elem<T>;
+    constexpr int VE = E::kVec;
+    constexpr int EPT = kDataRegs;
+    constexpr int NV = EPT / VE;                 // 4 vectors per thread and tensor
+    constexpr int NW = EPT / 2;                  // 16 packed words per thread and tensor
+    constexpr uint32_t kNegInf2 = 0xff80ff80u;   // (-inf, -inf)
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
+    float* red = reinterpret_cast<float*>(full + kStages + 1);      // [2][kWarps][kRedFloats]: ms, mt, -, -, zs, zt, a, dd
+    ProducerState& ps = *reinterpret_cast<ProducerState*>(red + 2 * kWarps * kRedFloats);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        fence_barrier_init();
+        ps.cur.init(p, blockIdx.x);
+        ps.v0 = 0;
+        ps.stage = 0;
+        ps.free_slots = kStages;
+        ps.pol = l2_policy_evict_first();
+        ps.kl = 0.f;
+        ps.sq = 0.f;
     }
+    __syncthreads();
+    if (tid == 0) rows_issue_loads<T>(p, ps, smem, full, 0);
+
+    const float c2 = p.l[0].c2;
+    uint32_t rs[NW], rt[NW];                     // the row at the head of the ring, packed
+    uint32_t pms = kNegInf2, pmt = kNegInf2;     // its packed maxima
+    int stage = 0;
+    uint32_t phase = 0;
+    int par = 0;
+
+    // vector v of the row at the head of the ring -> registers (v is a compile-time constant after unrolling)
+    auto load_vec = [&](int v) {
+        if (v % kSlotVecRows == 0) mbar_wait(&full[stage], phase);
+        const uint4* bs = reinterpret_cast<const uint4*>(smem + (size_t)stage * kStageBytes);
+        const uint4* bt = reinterpret_cast<const uint4*>(smem + (size_t)stage * kStageBytes + kSlotBytes);
+        const int r = v % kSlotVecRows;
+        const uint4 vs = bs[r * kThreads + tid], vt = bt[r * kThreads + tid];
+        pms = packed_max4(pms, vs);
+        pmt = packed_max4(pmt, vt);
+        rs[4 * v + 0] = vs.x; rs[4 * v + 1] = vs.y; rs[4 * v + 2] = vs.z; rs[4 * v + 3] = vs.w;
+        rt[4 * v + 0] = vt.x; rt[4 * v + 1] = vt.y; rt[4 * v + 2] = vt.z; rt[4 * v + 3] = vt.w;
+        if (r == kSlotVecRows - 1 && ++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+        }
+    };
+
+    UnitCursor cur;
+    cur.init(p, blockIdx.x);
+    bool have = cur.u < p.total_units;
+    if (have) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) load_vec(v);
+    }
+    SD_RT_DECL
+    while (have) {
+        SD_RT_START
+        const Unit x = decode_unit(p, cur.b, cur.r);
+        cur.advance(p, (int)gridDim.x);
+        const bool next = cur.u < p.total_units;
+
+        // ---- warp maxima -> shared memory; the barrier also says: every thread has drained this row's slots
+        float* my_red = red + (par * kWarps + warp) * kRedFloats;
+        {
+            float lo, hi;
+            E::unpack2(pms, lo, hi);
+            const float msw = warp_max_uniform(fmaxf(lo, hi));
+            E::unpack2(pmt, lo, hi);
+            const float mtw = warp_max_uniform(fmaxf(lo, hi));
+            if (lane == 0) *reinterpret_cast<float2*>(my_red) = make_float2(msw, mtw);
+        }
+        SD_RT_MARK(0)
+        __syncthreads();
+        if (tid == 0) rows_issue_loads<T>(p, ps, smem, full, NV / kSlotVecRows);
+        SD_RT_MARK(1)
+        const float2 wm = *reinterpret_cast<const float2*>(red + (par * kWarps + (lane & 15)) * kRedFloats);
+        const float sig = __fmul_rn(warp_max_uniform(wm.x), c2), th = __fmul_rn(warp_max_uniform(wm.y), c2);
+
+        // ---- exponentials against the row maxima (kept in registers), the thread's four sums
+        float es[EPT], et[EPT];
+        float v4[4];
+        {
+            const F2 C2 = f2_dup(c2), NS = f2_dup(-sig), NT = f2_dup(-th), neg1 = f2_dup(-1.f);
+            F2 ZS = f2_dup(0.f), ZT = f2_dup(0.f), DD = f2_dup(0.f), A = f2_dup(0.f);
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                float s0, s1, t0, t1;
+                E::unpack2(rs[w], s0, s1);
+                E::unpack2(rt[w], t0, t1);
+                const F2 as2 = f2_fma(f2_make(s0, s1), C2, NS), at2 = f2_fma(f2_make(t0, t1), C2, NT);
+                float as0, as1, at0, at1;
+                f2_split(as2, as0, as1);
+                f2_split(at2, at0, at1);
+                const float es0 = fast_exp2(as0), es1 = fast_exp2(as1), et0 = fast_exp2(at0), et1 = fast_exp2(at1);
+                const F2 es2 = f2_make(es0, es1), et2 = f2_make(et0, et1);
+                ZS = f2_add(ZS, es2);
+                ZT = f2_add(ZT, et2);
+                DD = f2_add(DD, f2_fma(es2, neg1, et2));
+                A = f2_fma(et2, f2_fma(as2, neg1, at2), A);
+                es[2 * w] = es0;
+                es[2 * w + 1] = es1;
+                et[2 * w] = et0;
+                et[2 * w + 1] = et1;
+            }
+            v4[0] = f2_sum(ZS);
+            v4[1] = f2_sum(ZT);
+            v4[2] = f2_sum(A);
+            v4[3] = f2_sum(DD);
+        }
+        SD_RT_MARK(2)
+        {
+            const float tot = warp_sum4_transposed(v4, lane);
+            if ((lane & 7) == 0) my_red[4 + (lane >> 3)] = tot;
+        }
+        SD_RT_MARK(3)
+        __syncthreads();
+
+        // ---- CTA = row: the 16 warp records add up (lanes l and l+16 mirror each other)
+        const float4 r4 = *reinterpret_cast<const float4*>(red + (par * kWarps + (lane & 15)) * kRedFloats + 4);
+        const float Zs = sum16(r4.x), Zt = sum16(r4.y);
+        if (warp == 0) {
+            const float A = sum16(r4.z), DD = sum16(r4.w);
+            if (tid == 0) {
+                const float kl = kl_from_stats(Zs, Zt, A, DD);
+                if (p.l[0].row_kl) p.l[0].row_kl[x.b * p.l[0].G + x.grp] = kl;
+                ps.kl += kl;
+            }
+        }
+        par ^= 1;
+        SD_RT_MARK(4)
+
+        // ---- gradient straight from registers; behind every vector the same vector of the next row comes in
+        float coef = p.l[0].coef;
+        if (p.grad_out[0] != nullptr) coef *= __ldg(p.grad_out[0]);
+        const F2 KS = f2_dup(coef / Zs), NKT = f2_dup(-coef / Zt);
+        T* out = static_cast<T*>(p.dS);
+        uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)x.b * p.C + (size_t)x.grp * p.l[0].g) * p.HW + x.e0) + tid;
+        pms = kNegInf2;
+        pmt = kNegInf2;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            float o[VE];
+#pragma unroll
+            for (int q = 0; q < VE; q += 2) {
+                const int i = v * VE + q;
+                f2_split(f2_fma(f2_make(es[i], es[i + 1]), KS, f2_mul(f2_make(et[i], et[i + 1]), NKT)), o[q], o[q + 1]);
+            }
+            if (p.perm == nullptr) {
+                dst[v * kThreads] = E::pack(o);
+            } else {
+                *reinterpret_cast<uint4*>(out + perm_elem_offset(p, x, x.e0 + (v * kThreads + tid) * VE)) = E::pack(o);
+            }
+            if (next) load_vec(v);
+        }
+        have = next;
+        SD_RT_MARK(5)
+    }
+    SD_RT_WRITE
+
+    rows_finish_loss<false>(p, ps, warp, lane);
 }
 
 // ====================================================================================================
@@ -910,6 +1128,20 @@ cudaError_t launch_kl_rows_tma(const RowsParams& p, bool bf16, int grid, cudaStr
                    : launch_tma_t<__nv_bfloat16, false>(p, grid, stream);
     }
     return mse ? launch_tma_t<float, true>(p, grid, stream) : launch_tma_t<float, false>(p, grid, stream);
+}
+
+// bf16 rows of exactly kl_rows_tma_chunk_capacity() elements (the caller checks: every unit is a whole row)
+cudaError_t launch_kl_rows_rm(const RowsParams& p, int grid, cudaStream_t stream) {
+    auto kern = kl_rows_rm_kernel;
+    static std::atomic<bool> configured[kMaxDevices];
+    const int dev = device_slot();
+    if (!configured[dev].load(std::memory_order_acquire)) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmemBytes);
+        if (e != cudaSuccess) return e;
+        configured[dev].store(true, std::memory_order_release);
+    }
+    kern<<<grid, kThreads, kRowsSmemBytes, stream>>>(p);
+    return cudaGetLastError();
 }
 
 int kl_rows_tma_chunk_capacity() { return kThreads * kDataRegs; }

@@ -22,6 +22,7 @@ inline int device_slot() {
 // kl_rows.cu
 cudaError_t launch_kl_rows_tma(const RowsParams& p, bool bf16, int grid, cudaStream_t stream);
 cudaError_t launch_kl_rows_generic(const RowsParams& p, bool bf16, cudaStream_t stream);
+cudaError_t launch_kl_rows_rm(const RowsParams& p, int grid, cudaStream_t stream);
 int kl_rows_tma_chunk_capacity();
 cudaError_t launch_kl_rows_pack(const RowsParams& p, bool bf16, int grid, cudaStream_t stream);
 // kl_rows_stream.cu
