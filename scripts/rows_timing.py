@@ -28,6 +28,8 @@ off = 256 + 4 * 3 * 1024
 n_cta = 148
 v = ws[off:off + n_cta * 16 * 8].view(torch.int64).view(n_cta, 16).cpu().double()
 names = ['ring->regs+max', 'barrier 1 (+issue)', 'exponentials', 'warp reduce', 'barrier 2 + merge', 'gradient + stores']
+if _cabi.last_kernel() == 'kl_rows_rm_kernel':
+    names = ['wait next row', 'exponentials + loads', 'warp reduce, publish', 'barrier (+issue)', 'merge', 'gradient + stores']
 for base, who in ((0, 'thread 0'), (8, 'thread 480')):
     rows = v[:, base + 6].clamp(min=1)
     print(f'-- {who}: rows per CTA {rows.mean():.1f}, total cycles {v[:, base + 7].mean():.0f}')

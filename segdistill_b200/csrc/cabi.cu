@@ -519,7 +519,8 @@ int rows_dispatch(RowsCall c) {
     } else if (path == kRegs) {
         int grid = (int)(p.total_units < dev.sms ? p.total_units : dev.sms);
         const bool mse = p.mse_gcoef != 0.f || p.mse_loss != nullptr;
-        const bool whole_rows = p.g_last == 0 && p.nch_full == 1 && row_len == sd::kl_rows_tma_chunk_capacity();
+        const bool whole_rows = p.g_last == 0 && p.nch_full == 1 && row_len == sd::kl_rows_tma_chunk_capacity() &&
+                                p.total_units < (1ll << 31);
         if (c.dtype == SD_BF16 && !mse && whole_rows && rows_rm()) {
             e = sd::launch_kl_rows_rm(p, grid, st);
             t_last_kernel = "kl_rows_rm_kernel";

@@ -101,6 +101,18 @@ __device__ __forceinline__ void tma_tile3d_g2s(void* dst_smem, const void* tmap,
         ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(l2_policy)
         : "memory");
 }
+// ---------------------------------------------------------------- TMA: 1-D bulk copy shared -> global
+// The writes of the calling thread('s warp, after __syncwarp) to `src_smem` must be made visible to the async proxy
+// first (fence_proxy_async_smem).  Completion is tracked per thread in bulk groups.
+__device__ __forceinline__ void tma_bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of the thread's groups have READ their shared-memory source (it may be overwritten)
+__device__ __forceinline__ void tma_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed
+__device__ __forceinline__ void tma_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
 }
 
 // ====================================================================================================
-// bf16 rows of exactly 16384 elements: references = the ROW maxima, next row's loads inside the gradient sweep
+// bf16 rows of exactly 16384 elements: references = the ROW maxima, ONE CTA barrier per row
 // ====================================================================================================
 // The bf16 launch of kl_rows_tma_kernel is not HBM-bound: its phases (ring -> registers with the bf16 -> fp32 unpack on
 // the ALU pipe, exponentials on the MUFU pipe, the reductions' shuffle chains, the gradient) run one after the other
@@ -462,11 +462,57 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
 // row).  Here
 //   * a row stays PACKED (16 + 16 registers) from the ring until the exponentials, so the unpack runs next to the MUFU
 //     instructions instead of before them;
-//   * the barrier that hands the ring slots back also publishes the warps' maxima: every thread exponentiates against
-//     the ROW maxima, so the sums of threads and warps simply add - no rescale factors (ex2), no merge shifts;
-//   * the next row's ring -> register copy (and its packed maxima) is interleaved with the gradient of this one: the
-//     registers of the exponentials free up vector by vector.
+//   * row r+1 comes out of the ring (packed, with its packed maxima) DURING the exponentials of row r - shared-memory
+//     loads under the MUFU instructions - and its warp maxima are published together with row r's warp sums: the one
+//     barrier of row r gives every thread the sums of row r and the maxima of row r+1.  Every thread exponentiates
+//     against the ROW maxima, so the sums of threads and warps simply add - no rescale factors (ex2), no merge shifts;
+//   * ring stages are whole rows (3 x 64 KB): one mbarrier wait and two bulk copies per row;
+//   * the gradient leaves through shared memory and one 2 KB bulk store per warp (cp.async.bulk shared -> global):
+//     128-bit global stores from 512 threads back up the queue that shared-memory loads, shuffles and MUFU
+//     instructions share, and every phase behind the gradient sweep waited for them.  A warp holds 2 KB of
+//     consecutive row elements (vector = warp * 128 + v * 32 + lane), so no CTA barrier is involved.
 // Same statistics as everywhere (common.cuh, KL without cancellation): zs, zt, a2 = sum et (at - as), dd = sum (et - es).
+constexpr int kRmStages = 3;
+constexpr int kRmRowBytes = kThreads * kDataRegs * 2;            // one tensor's row: 32 KB
+constexpr int kRmStageBytes = 2 * kRmRowBytes;                   // S + T
+struct RmProducer {
+    long long u_next;      // next unit this CTA loads
+    int stage;             // ... into this stage
+    uint64_t pol;
+    float kl;
+};
+constexpr int kRmWarpVecs = kDataRegs / 8 * 32;                  // 16-byte vectors of a row one warp holds (contiguous: 2 KB)
+constexpr size_t kRmSmemBytes = (size_t)kRmStages * kRmStageBytes + kRmRowBytes + (kRmStages + 1) * sizeof(uint64_t) +
+                                2 * kWarps * kRedFloats * sizeof(float) + sizeof(RmProducer);
+
+// thread 0: one row into the stage at the producer's head (a no-op behind the CTA's last row)
+__device__ __forceinline__ void rm_issue_row(const RowsParams& p, RmProducer& ps, unsigned char* smem, uint64_t* full) {
+    const long long u = ps.u_next;
+    if (u >= p.total_units) return;
+    const int st = ps.stage;
+    unsigned char* dst_s = smem + (size_t)st * kRmStageBytes;
+    unsigned char* dst_t = dst_s + kRmRowBytes;
+    mbar_arrive_expect_tx(&full[st], (uint32_t)kRmStageBytes);
+    if (p.perm == nullptr) {
+        // whole rows, C % g == 0: row u starts u rows into the tensor
+        const size_t off = (size_t)u * kRmRowBytes;
+        tma_bulk_g2s(dst_s, static_cast<const char*>(p.S) + off, kRmRowBytes, &full[st], ps.pol);
+        tma_bulk_g2s(dst_t, static_cast<const char*>(p.T) + off, kRmRowBytes, &full[st], ps.pol);
+    } else {
+        // gathered channels: one copy per channel
+        const int G = p.l[0].G, g = p.l[0].g;
+        const int b = (int)(u / G), grp = (int)(u - (long long)b * G);
+        const uint32_t nb = (uint32_t)p.HW * 2u;
+        for (int j = 0; j < g; ++j) {
+            const size_t off = (((size_t)b * p.C + p.perm[grp * g + j]) * p.HW) * 2u;
+            tma_bulk_g2s(dst_s + (size_t)j * nb, static_cast<const char*>(p.S) + off, nb, &full[st], ps.pol);
+            tma_bulk_g2s(dst_t + (size_t)j * nb, static_cast<const char*>(p.T) + off, nb, &full[st], ps.pol);
+        }
+    }
+    ps.u_next = u + gridDim.x;
+    ps.stage = st + 1 == kRmStages ? 0 : st + 1;
+}
+
 __global__ void __launch_bounds__(kThreads, 1) kl_rows_rm_kernel(const RowsParams p) {
     using T = __nv_bfloat16;
     using E = Elem<T>;
@@ -477,30 +523,29 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_rm_kernel(const RowsParam
     constexpr uint32_t kNegInf2 = 0xff80ff80u;   // (-inf, -inf)
 
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
-    float* red = reinterpret_cast<float*>(full + kStages + 1);      // [2][kWarps][kRedFloats]: ms, mt, -, -, zs, zt, a, dd
-    ProducerState& ps = *reinterpret_cast<ProducerState*>(red + 2 * kWarps * kRedFloats);
+    uint4* out_stage = reinterpret_cast<uint4*>(smem + (size_t)kRmStages * kRmStageBytes);       // the row's gradient
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kRmStages * kRmStageBytes + kRmRowBytes);
+    float* red = reinterpret_cast<float*>(full + kRmStages + 1);    // [2][kWarps][kRedFloats]: zs, zt, a, dd, ms', mt', -, -
+    RmProducer& ps = *reinterpret_cast<RmProducer*>(red + 2 * kWarps * kRedFloats);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < kRmStages; ++s) mbar_init(&full[s], 1);
         fence_barrier_init();
-        ps.cur.init(p, blockIdx.x);
-        ps.v0 = 0;
+        ps.u_next = blockIdx.x;
         ps.stage = 0;
-        ps.free_slots = kStages;
         ps.pol = l2_policy_evict_first();
         ps.kl = 0.f;
-        ps.sq = 0.f;
+        for (int s = 0; s < kRmStages; ++s) rm_issue_row(p, ps, smem, full);
     }
     __syncthreads();
-    if (tid == 0) rows_issue_loads<T>(p, ps, smem, full, 0);
 
     const float c2 = p.l[0].c2;
-    uint32_t rs[NW], rt[NW];                     // the row at the head of the ring, packed
+    const int G = p.l[0].G;
+    uint32_t rs[NW], rt[NW];                     // the row that is exponentiated next, packed
     uint32_t pms = kNegInf2, pmt = kNegInf2;     // its packed maxima
     int stage = 0;
     uint32_t phase = 0;
@@ -508,55 +553,65 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_rm_kernel(const RowsParam
 
     // vector v of the row at the head of the ring -> registers (v is a compile-time constant after unrolling)
     auto load_vec = [&](int v) {
-        if (v % kSlotVecRows == 0) mbar_wait(&full[stage], phase);
-        const uint4* bs = reinterpret_cast<const uint4*>(smem + (size_t)stage * kStageBytes);
-        const uint4* bt = reinterpret_cast<const uint4*>(smem + (size_t)stage * kStageBytes + kSlotBytes);
-        const int r = v % kSlotVecRows;
-        const uint4 vs = bs[r * kThreads + tid], vt = bt[r * kThreads + tid];
+        const uint4* bs = reinterpret_cast<const uint4*>(smem + (size_t)stage * kRmStageBytes);
+        const uint4* bt = reinterpret_cast<const uint4*>(smem + (size_t)stage * kRmStageBytes + kRmRowBytes);
+        const uint4 vs = bs[warp * kRmWarpVecs + v * 32 + lane], vt = bt[warp * kRmWarpVecs + v * 32 + lane];
         pms = packed_max4(pms, vs);
         pmt = packed_max4(pmt, vt);
         rs[4 * v + 0] = vs.x; rs[4 * v + 1] = vs.y; rs[4 * v + 2] = vs.z; rs[4 * v + 3] = vs.w;
         rt[4 * v + 0] = vt.x; rt[4 * v + 1] = vt.y; rt[4 * v + 2] = vt.z; rt[4 * v + 3] = vt.w;
-        if (r == kSlotVecRows - 1 && ++stage == kStages) {
+    };
+    auto next_stage = [&]() {
+        if (++stage == kRmStages) {
             stage = 0;
             phase ^= 1u;
         }
     };
+    // the warp's maxima of the row in (pms, pmt) -> its record
+    auto publish_max = [&](float* rec) {
+        float lo, hi;
+        E::unpack2(pms, lo, hi);
+        const float msw = warp_max_uniform(fmaxf(lo, hi));
+        E::unpack2(pmt, lo, hi);
+        const float mtw = warp_max_uniform(fmaxf(lo, hi));
+        if (lane == 0) *reinterpret_cast<float2*>(rec + 4) = make_float2(msw, mtw);
+    };
+    // the row maxima from the 16 records, as references of the exponents
+    auto read_refs = [&](const float* recs, float& sig, float& th) {
+        const float2 wm = *reinterpret_cast<const float2*>(recs + (lane & 15) * kRedFloats + 4);
+        sig = __fmul_rn(warp_max_uniform(wm.x), c2);
+        th = __fmul_rn(warp_max_uniform(wm.y), c2);
+    };
 
-    UnitCursor cur;
-    cur.init(p, blockIdx.x);
-    bool have = cur.u < p.total_units;
-    if (have) {
+    const unsigned total = (unsigned)p.total_units;     // rows of the launch (< 2^31: checked by the caller)
+    unsigned u = blockIdx.x;
+    bool have = u < total;
+    float sig = 0.f, th = 0.f;
+    if (have) {                                  // (uniform over the CTA)
+        mbar_wait(&full[stage], phase);
 #pragma unroll
         for (int v = 0; v < NV; ++v) load_vec(v);
+        next_stage();
+        publish_max(red + (par * kWarps + warp) * kRedFloats);
+        __syncthreads();
+        if (tid == 0) rm_issue_row(p, ps, smem, full);
+        read_refs(red + par * kWarps * kRedFloats, sig, th);
+        par ^= 1;
     }
     SD_RT_DECL
     while (have) {
         SD_RT_START
-        const Unit x = decode_unit(p, cur.b, cur.r);
-        cur.advance(p, (int)gridDim.x);
-        const bool next = cur.u < p.total_units;
-
-        // ---- warp maxima -> shared memory; the barrier also says: every thread has drained this row's slots
-        float* my_red = red + (par * kWarps + warp) * kRedFloats;
-        {
-            float lo, hi;
-            E::unpack2(pms, lo, hi);
-            const float msw = warp_max_uniform(fmaxf(lo, hi));
-            E::unpack2(pmt, lo, hi);
-            const float mtw = warp_max_uniform(fmaxf(lo, hi));
-            if (lane == 0) *reinterpret_cast<float2*>(my_red) = make_float2(msw, mtw);
-        }
+        const unsigned un = u + gridDim.x;
+        const bool next = un < total;
+        if (next) mbar_wait(&full[stage], phase);
         SD_RT_MARK(0)
-        __syncthreads();
-        if (tid == 0) rows_issue_loads<T>(p, ps, smem, full, NV / kSlotVecRows);
-        SD_RT_MARK(1)
-        const float2 wm = *reinterpret_cast<const float2*>(red + (par * kWarps + (lane & 15)) * kRedFloats);
-        const float sig = __fmul_rn(warp_max_uniform(wm.x), c2), th = __fmul_rn(warp_max_uniform(wm.y), c2);
 
-        // ---- exponentials against the row maxima (kept in registers), the thread's four sums
+        // ---- exponentials against the row maxima (kept in registers), the thread's four sums; behind every
+        //      vector of this row the same vector of the next row comes out of the ring
         float es[EPT], et[EPT];
         float v4[4];
+        pms = kNegInf2;
+        pmt = kNegInf2;
         {
             const F2 C2 = f2_dup(c2), NS = f2_dup(-sig), NT = f2_dup(-th), neg1 = f2_dup(-1.f);
             F2 ZS = f2_dup(0.f), ZT = f2_dup(0.f), DD = f2_dup(0.f), A = f2_dup(0.f);
@@ -579,42 +634,49 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_rm_kernel(const RowsParam
                 es[2 * w + 1] = es1;
                 et[2 * w] = et0;
                 et[2 * w + 1] = et1;
+                if ((w & 3) == 3 && next) load_vec(w >> 2);
             }
             v4[0] = f2_sum(ZS);
             v4[1] = f2_sum(ZT);
             v4[2] = f2_sum(A);
             v4[3] = f2_sum(DD);
         }
-        SD_RT_MARK(2)
+        SD_RT_MARK(1)
+        float* my_red = red + (par * kWarps + warp) * kRedFloats;
         {
             const float tot = warp_sum4_transposed(v4, lane);
-            if ((lane & 7) == 0) my_red[4 + (lane >> 3)] = tot;
+            if ((lane & 7) == 0) my_red[lane >> 3] = tot;
         }
+        if (next) {
+            next_stage();
+            publish_max(my_red);
+        }
+        SD_RT_MARK(2)
+        __syncthreads();          // row u: sums complete; row un: maxima complete, its stage drained
+        if (tid == 0 && next) rm_issue_row(p, ps, smem, full);
         SD_RT_MARK(3)
-        __syncthreads();
 
         // ---- CTA = row: the 16 warp records add up (lanes l and l+16 mirror each other)
-        const float4 r4 = *reinterpret_cast<const float4*>(red + (par * kWarps + (lane & 15)) * kRedFloats + 4);
+        const float* recs = red + par * kWarps * kRedFloats;
+        const float4 r4 = *reinterpret_cast<const float4*>(recs + (lane & 15) * kRedFloats);
         const float Zs = sum16(r4.x), Zt = sum16(r4.y);
         if (warp == 0) {
             const float A = sum16(r4.z), DD = sum16(r4.w);
             if (tid == 0) {
                 const float kl = kl_from_stats(Zs, Zt, A, DD);
-                if (p.l[0].row_kl) p.l[0].row_kl[x.b * p.l[0].G + x.grp] = kl;
+                if (p.l[0].row_kl) p.l[0].row_kl[u] = kl;
                 ps.kl += kl;
             }
         }
-        par ^= 1;
         SD_RT_MARK(4)
 
-        // ---- gradient straight from registers; behind every vector the same vector of the next row comes in
+        // ---- gradient from registers into the warp's 2 KB of the staging row, from there by one bulk store
         float coef = p.l[0].coef;
         if (p.grad_out[0] != nullptr) coef *= __ldg(p.grad_out[0]);
-        const F2 KS = f2_dup(coef / Zs), NKT = f2_dup(-coef / Zt);
-        T* out = static_cast<T*>(p.dS);
-        uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)x.b * p.C + (size_t)x.grp * p.l[0].g) * p.HW + x.e0) + tid;
-        pms = kNegInf2;
-        pmt = kNegInf2;
+        const F2 KS = f2_dup(__fdividef(coef, Zs)), NKT = f2_dup(-__fdividef(coef, Zt));     // (bf16 results)
+        uint4* my_out = out_stage + warp * kRmWarpVecs;
+        if (lane == 0) tma_bulk_wait_read0();        // the previous row's store has read the staging row
+        __syncwarp();
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             float o[VE];
@@ -623,19 +685,60 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_rm_kernel(const RowsParam
                 const int i = v * VE + q;
                 f2_split(f2_fma(f2_make(es[i], es[i + 1]), KS, f2_mul(f2_make(et[i], et[i + 1]), NKT)), o[q], o[q + 1]);
             }
-            if (p.perm == nullptr) {
-                dst[v * kThreads] = E::pack(o);
-            } else {
-                *reinterpret_cast<uint4*>(out + perm_elem_offset(p, x, x.e0 + (v * kThreads + tid) * VE)) = E::pack(o);
-            }
-            if (next) load_vec(v);
+            my_out[v * 32 + lane] = E::pack(o);
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            T* out = static_cast<T*>(p.dS);
+            constexpr int kWarpElems = kRmWarpVecs * VE;             // 1024 consecutive row elements
+            if (p.perm == nullptr) {
+                tma_bulk_s2g(out + (size_t)u * (kThreads * EPT) + warp * kWarpElems, my_out, kWarpElems * 2);
+            } else {
+                // gathered channels: one store per channel piece
+                const unsigned b = u / (unsigned)G, grp = u - b * (unsigned)G;
+                int e = warp * kWarpElems, left = kWarpElems;
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(my_out);
+                while (left > 0) {
+                    const int j = e / p.HW, pos = e - j * p.HW, n = min(left, p.HW - pos);
+                    tma_bulk_s2g(out + ((size_t)b * p.C + p.perm[grp * p.l[0].g + j]) * p.HW + pos, src, (uint32_t)n * 2u);
+                    src += (size_t)n * 2;
+                    e += n;
+                    left -= n;
+                }
+            }
+            tma_bulk_commit();
+        }
+        if (next) read_refs(recs, sig, th);
+        par ^= 1;
+        u = un;
         have = next;
         SD_RT_MARK(5)
     }
     SD_RT_WRITE
+    if (lane == 0) tma_bulk_wait0();             // the warp's last store is complete
 
-    rows_finish_loss<false>(p, ps, warp, lane);
+    // ---- loss: per-CTA partials, last CTA sums them in a fixed order
+    if (warp == 0) {
+        unsigned ticket = 0;
+        if (lane == 0) {
+            __stcg(&p.cta_part[blockIdx.x], ps.kl);
+            __threadfence();
+            ticket = atomicAdd(&p.ctrl[0], 1u);
+        }
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            double kl = 0.0;
+            for (int i = lane; i < (int)gridDim.x; i += 32) kl += (double)__ldcg(&p.cta_part[i]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) kl += __shfl_down_sync(0xffffffffu, kl, o);
+            if (lane == 0) {
+                *p.l[0].loss = (float)((double)p.l[0].loss_scale * kl);
+                atomicExch(&p.ctrl[0], 0u);
+            }
+        }
+    }
 }
 
 // ====================================================================================================
@@ -1136,14 +1239,13 @@ cudaError_t launch_kl_rows_rm(const RowsParams& p, int grid, cudaStream_t stream
     static std::atomic<bool> configured[kMaxDevices];
     const int dev = device_slot();
     if (!configured[dev].load(std::memory_order_acquire)) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRmSmemBytes);
         if (e != cudaSuccess) return e;
         configured[dev].store(true, std::memory_order_release);
     }
-    kern<<<grid, kThreads, kRowsSmemBytes, stream>>>(p);
+    kern<<<grid, kThreads, kRmSmemBytes, stream>>>(p);
     return cudaGetLastError();
 }
-
 int kl_rows_tma_chunk_capacity() { return kThreads * kDataRegs; }
 
 template <typename T, bool MSE>

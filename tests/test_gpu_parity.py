@@ -278,6 +278,45 @@ def test_cfg3_quarter_batch_bf16(cls, algo):
     _assert_close(*got, *ref, loss_rtol=2e-5, grad_rtol=BF16_GRAD_RTOL)
 
 
+@pytest.mark.parametrize('shape,g,tau,n_iter', [((3, 150, 128, 128), 1, 1.0, 1),    # 450 rows: three rounds of the grid, the ring wraps
+                                                ((2, 2, 128, 128), 1, 4.0, 1),      # fewer rows than SMs
+                                                ((2, 8, 64, 64), 4, 2.0, 1),        # rows of four 64 x 64 channels
+                                                ((2, 8, 64, 64), 4, 2.0, 3000),     # ... gathered (shuffle step)
+                                                ((3, 128, 16, 16), 64, 2.0, 3000),  # gathered: four channel pieces per warp
+                                                ((2, 32, 32, 32), 16, 1.0, 1)])
+def test_bf16_rows_of_register_capacity_row_maxima_kernel(shape, g, tau, n_iter):
+    """kl_rows_rm_kernel (bf16 rows of exactly 16384 elements: row-maximum references, one CTA barrier per row, gradient
+    through shared memory and bulk stores) against the oracle on the fp32 upcast of the same bf16 values."""
+    s, t = seeded_pair(shape, seed=31 + g, dtype=torch.bfloat16)
+    kw = dict(group_size=g, alpha=3, tau=tau)
+    perm = None
+    if n_iter % 1000 == 0:
+        torch.manual_seed(77)
+        perm = torch.randperm(shape[1])
+    ref = _oracle_run('CGDLoss', kw, s, t, shape[2:], n_iter, perm=perm)
+    crit = sd.CGDLoss(**kw)
+    got = _run(crit, s, t, shape[2:], n_iter, 'auto', seed=77)
+    assert _cabi.last_kernel() == 'kl_rows_rm_kernel'
+    if perm is not None:
+        assert torch.equal(crit.last_perm, perm)
+    _assert_close(*got, *ref, loss_rtol=2e-5, grad_rtol=BF16_GRAD_RTOL)
+    # S ~ T (KL ~ 5e-5) with a constant offset between the maps: float64 closed form.  With one pair of references per
+    # row (instead of one per thread) the two first-order terms whose difference is the KL are ~300x the KL itself:
+    # measured 3e-5 on average, up to 1.1e-4 on launches of a handful of rows (scripts/probe/rm_near_err.py; the
+    # thread-local references of kl_rows_tma_kernel: 1.5e-5 / 3.7e-5; the reference's own fp32 chain: 6e-4 .. 1e-2)
+    sn, tn = _near_pair(shape, seed=7, offset=0.5, dtype=torch.bfloat16)
+    f64_loss, f64_grad, _ = oracle.kld_closed_form_f64(sn.float().numpy(), tn.float().numpy(), 'channel', g, tau, 3.0)
+    loss, grad = _run(sd.CGDLoss(**kw), sn, tn, shape[2:], 1, 'auto')
+    assert _cabi.last_kernel() == 'kl_rows_rm_kernel'
+    _check_near(loss, grad, f64_loss, f64_grad, tol=3e-4, gtol=BF16_GRAD_RTOL)
+    # the upstream gradient is folded into dS on the device
+    x = s.to(dev()).requires_grad_(True)
+    (2.5 * sd.CGDLoss(**kw)(x, t.to(dev()), None, 1)).backward()
+    y = s.to(dev()).requires_grad_(True)
+    sd.CGDLoss(**kw)(y, t.to(dev()), None, 1).backward()
+    assert (x.grad.float() - 2.5 * y.grad.float()).abs().max().item() <= 2.0 ** -7 * (2.5 * y.grad.float()).abs().max().item()
+
+
 @pytest.mark.parametrize('algo', ['tma', 'generic'])
 @pytest.mark.parametrize('cls', ['CDLoss', 'PDLoss'])
 def test_cfg3_quarter_batch_fp32(cls, algo):
