@@ -58,7 +58,7 @@ PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
 }
 
 // (B, C, HW) view of an NCHW map; box = (tile pixels, C, 1); out-of-range pixels read as zero
-bool encode_pixel_map(CUtensorMap* m, const void* base, int B, int C, int HW, int dtype, int tile_px) {
+bool encode_pixel_map(CUtensorMap* m, const void* base, int B, int C, int HW, int dtype, int tile_px, bool swizzle128 = false) {
     auto enc = tensor_map_encoder();
     if (!enc) return false;
     const cuuint64_t es = (cuuint64_t)elem_size(dtype);
@@ -68,8 +68,8 @@ bool encode_pixel_map(CUtensorMap* m, const void* base, int B, int C, int HW, in
     cuuint32_t estr[3] = {1u, 1u, 1u};
     const CUresult r = enc(m, dtype == SD_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                            const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
@@ -199,6 +199,15 @@ bool rows_rm() {
     static int v = -1;
     if (v < 0) {
         const char* e = std::getenv("SEGDISTILL_ROWS_RM");
+        v = e ? (std::atoi(e) != 0) : 1;
+    }
+    return v != 0;
+}
+// bf16 PD (no AT term): kl_pixels_warp_kernel (every warp on its own); SEGDISTILL_PIX_WARP=0 keeps kl_pixels_tma_kernel
+bool pix_warp() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("SEGDISTILL_PIX_WARP");
         v = e ? (std::atoi(e) != 0) : 1;
     }
     return v != 0;
@@ -799,7 +808,20 @@ int sd_kl_pixels_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl, 
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
-    if (use_tma) {
+    const bool at_term = p.at_gcoef != 0.f || p.at_loss != nullptr;
+    if (use_tma && bf16 && !at_term && C <= 256 && pix_warp() && sd::pix_warp_smem_bytes(C) <= 227u * 1024u) {
+        alignas(64) CUtensorMap mS, mT, mD;
+        const int tpx = sd::kl_pixels_warp_tile_pixels();
+        if (!encode_pixel_map(&mS, S, B, C, HW, dtype, tpx, true) || !encode_pixel_map(&mT, T, B, C, HW, dtype, tpx, true) ||
+            !encode_pixel_map(&mD, dS, B, C, HW, dtype, tpx, true))
+            return (int)cudaErrorInvalidValue;
+        p.tiles_per_sample = (HW + tpx - 1) / tpx;
+        p.total_tiles = (long long)B * p.tiles_per_sample;
+        int grid = (int)(p.total_tiles < dev.sms ? p.total_tiles : dev.sms);
+        e = sd::launch_kl_pixels_warp(&mS, &mT, &mD, p, grid, st);
+        g_launches += 1;
+        t_last_kernel = "kl_pixels_warp_kernel";
+    } else if (use_tma) {
         alignas(64) CUtensorMap mS, mT;
         if (!encode_pixel_map(&mS, S, B, C, HW, dtype, tile_px) || !encode_pixel_map(&mT, T, B, C, HW, dtype, tile_px))
             return (int)cudaErrorInvalidValue;

@@ -108,6 +108,11 @@ __device__ __forceinline__ void tma_bulk_s2g(void* dst_gmem, const void* src_sme
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
 }
+// TMA: 3-D tiled tensor copy shared -> global (elements outside the tensor are not written); bulk-group completion
+__device__ __forceinline__ void tma_tile3d_s2g(const void* tmap, int c0, int c1, int c2, const void* src_smem) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src_smem)) : "memory");
+}
 __device__ __forceinline__ void tma_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all of the thread's groups have READ their shared-memory source (it may be overwritten)
 __device__ __forceinline__ void tma_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
