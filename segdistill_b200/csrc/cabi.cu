@@ -794,9 +794,15 @@ int sd_kl_pixels_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl, 
     const bool tma_ok = layout_ok && nstages >= 1 && C <= sd::kl_pixels_tma_max_channels(bf16) && C <= 256 &&
                         tensor_map_encoder() != nullptr;
 
+    // bf16 PD: the kernel with one warp per pixel column takes up to 256 channels
+    const bool at_term = p.at_gcoef != 0.f || p.at_loss != nullptr;
+    const int tpx_w = sd::kl_pixels_warp_tile_pixels();
+    const bool warp_ok = layout_ok && bf16 && !at_term && C <= 256 && sd::pix_warp_stages(C) >= 2 && pix_warp() &&
+                         tensor_map_encoder() != nullptr && (long long)B * ((HW + tpx_w - 1) / tpx_w) < (1ll << 31);
+
     bool use_tma;
     if (algo == SD_ALGO_TMA) {
-        if (!tma_ok) return SD_ERR_UNSUPPORTED;
+        if (!tma_ok && !warp_ok) return SD_ERR_UNSUPPORTED;
         use_tma = true;
     } else if (algo == SD_ALGO_GENERIC) {
         use_tma = false;
@@ -808,8 +814,7 @@ int sd_kl_pixels_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl, 
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
-    const bool at_term = p.at_gcoef != 0.f || p.at_loss != nullptr;
-    if (use_tma && bf16 && !at_term && C <= 256 && pix_warp() && sd::pix_warp_smem_bytes(C) <= 227u * 1024u) {
+    if (warp_ok && (algo == SD_ALGO_AUTO || algo == SD_ALGO_TMA)) {
         alignas(64) CUtensorMap mS, mT, mD;
         const int tpx = sd::kl_pixels_warp_tile_pixels();
         if (!encode_pixel_map(&mS, S, B, C, HW, dtype, tpx, true) || !encode_pixel_map(&mT, T, B, C, HW, dtype, tpx, true) ||
@@ -817,6 +822,7 @@ int sd_kl_pixels_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl, 
             return (int)cudaErrorInvalidValue;
         p.tiles_per_sample = (HW + tpx - 1) / tpx;
         p.total_tiles = (long long)B * p.tiles_per_sample;
+        p.nstages = sd::pix_warp_stages(C);
         int grid = (int)(p.total_tiles < dev.sms ? p.total_tiles : dev.sms);
         e = sd::launch_kl_pixels_warp(&mS, &mT, &mD, p, grid, st);
         g_launches += 1;

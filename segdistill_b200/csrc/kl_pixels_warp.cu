@@ -25,14 +25,19 @@ namespace sd {
 constexpr int kPwWarps = 16;                       // compute warps = 4-pixel columns of a tile
 constexpr int kPwThreads = 32 * (kPwWarps + 1);    // + the producer warp
 constexpr int kPwTilePx = 4 * kPwWarps;            // 64 pixels = 128 bytes of bf16
-constexpr int kPwStages = 5;
+constexpr int kPwStages = 5;                       // ring stages at most (p.nstages: as many as fit, C = 150: 5, C = 256: 3)
 constexpr uint32_t kNegInf2 = 0xff80ff80u;
 
 // bytes of one tensor's tile in a stage: C rows of 128 bytes, padded to the swizzle atom (1024 bytes)
 __host__ __device__ inline unsigned pw_tile_bytes(int C) { return ((unsigned)C * 128u + 1023u) & ~1023u; }
-size_t pix_warp_smem_bytes(int C) {
-    return 1024 /* alignment slack */ + (size_t)kPwStages * 2 * pw_tile_bytes(C) + 2 * kPwStages * sizeof(uint64_t) +
+size_t pix_warp_smem_bytes(int C, int nstages) {
+    return 1024 /* alignment slack */ + (size_t)nstages * 2 * pw_tile_bytes(C) + 2 * kPwStages * sizeof(uint64_t) +
            kPwWarps * sizeof(float);
+}
+int pix_warp_stages(int C) {
+    for (int n = kPwStages; n >= 2; --n)
+        if (pix_warp_smem_bytes(C, n) <= 227u * 1024u) return n;
+    return 0;
 }
 
 // the 16 per-thread sums v[4 p + {zs, zt, a, dd}] of a column's 4 pixels over the 32 lanes in 16 shuffles: lanes L and
@@ -71,7 +76,8 @@ kl_pixels_warp_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_con
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const unsigned tile_bytes = pw_tile_bytes(p.C);
     const unsigned stage_bytes = 2 * tile_bytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kPwStages * stage_bytes);
+    const int nst = p.nstages;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)nst * stage_bytes);
     uint64_t* done = full + kPwStages;
     float* warp_kl = reinterpret_cast<float*>(done + kPwStages);
 
@@ -80,7 +86,7 @@ kl_pixels_warp_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_con
     const int warp = tid >> 5;
 
     if (tid == 0) {
-        for (int s = 0; s < kPwStages; ++s) {
+        for (int s = 0; s < nst; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&done[s], kPwWarps);
         }
@@ -106,15 +112,15 @@ kl_pixels_warp_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_con
             const uint64_t pol = l2_policy_evict_first();
             int st = 0;
             uint32_t par = 1;                  // parity of the stage's previous use
-            for (int k = 0; k < my_tiles + kPwStages; ++k, ++st) {
-                if (st == kPwStages) {
+            for (int k = 0; k < my_tiles + nst; ++k, ++st) {
+                if (st == nst) {
                     st = 0;
                     par ^= 1u;
                 }
                 unsigned char* dst = smem + (size_t)st * stage_bytes;
-                if (k >= kPwStages) {
-                    // tile k - kPwStages lived here: its gradient is complete when the 16 warps have arrived
-                    const int kp = k - kPwStages;
+                if (k >= nst) {
+                    // tile k - nst lived here: its gradient is complete when the 16 warps have arrived
+                    const int kp = k - nst;
                     mbar_wait_sleep<200>(&done[st], par);
                     int b, px0;
                     tile_coords(kp, b, px0);
@@ -158,7 +164,7 @@ kl_pixels_warp_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_con
             }
         };
         for (int k = 0; k < my_tiles; ++k, ++st) {
-            if (st == kPwStages) {
+            if (st == nst) {
                 st = 0;
                 par ^= 1u;
             }
@@ -306,7 +312,7 @@ template <int CPT>
 static cudaError_t launch_pw_t(const CUtensorMap& mS, const CUtensorMap& mT, const CUtensorMap& mD, const PixParams& p, int grid,
                                cudaStream_t stream) {
     auto kern = kl_pixels_warp_kernel<CPT>;
-    const size_t smem = pix_warp_smem_bytes(p.C);
+    const size_t smem = pix_warp_smem_bytes(p.C, p.nstages);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kPwThreads, smem, stream>>>(mS, mT, mD, p);

@@ -57,7 +57,7 @@ cudaError_t launch_kl_pixels_generic(const PixParams& p, bool bf16, cudaStream_t
 cudaError_t launch_kl_pixels_warp(const void* mapS, const void* mapT, const void* mapD, const PixParams& p, int grid,
                                   cudaStream_t stream);
 int kl_pixels_warp_tile_pixels();
-size_t pix_warp_smem_bytes(int C);
+int pix_warp_stages(int C);    // ring stages that fit next to C channels (0: none)
 size_t pix_tma_smem_bytes(int C, int pxt, int nstages, int cols);   // cols: 64 (one CTA per SM) or 32 (bf16: two)
 int kl_pixels_tma_max_channels(bool bf16);
 int kl_pixels_tile_pixels(bool bf16, int cols);

@@ -398,6 +398,39 @@ def test_pixel_kernel_channel_counts(C):
     _assert_close(*gotb, *refb, loss_rtol=2e-5, grad_rtol=BF16_GRAD_RTOL)
 
 
+@pytest.mark.parametrize('shape,tau', [((2, 150, 64, 64), 1.0),      # 128 tiles: fewer than SMs
+                                       ((6, 150, 128, 128), 2.0),    # 1536 tiles: ten rounds, the 5-stage ring wraps twice
+                                       ((3, 19, 24, 40), 1.0),       # HW = 960: the last tile of a sample is clipped
+                                       ((2, 33, 8, 8), 4.0),         # HW = 64 = one tile; second channel slot of one lane only
+                                       ((1, 256, 16, 24), 1.0),      # eight channels per lane
+                                       ((2, 97, 40, 8), 1.0)])
+def test_bf16_pixel_kernel_one_warp_per_pixel_column(shape, tau):
+    """kl_pixels_warp_kernel (bf16 PD: lane = channel, warp reductions, swizzled tiles, in-place gradient + tensor
+    store) against the oracle on the fp32 upcast of the same bf16 values, per-pixel KL against the float64 closed form,
+    and a nearly converged pair with an offset."""
+    s, t = seeded_pair(shape, seed=41 + shape[1], scale=2.0, dtype=torch.bfloat16)
+    kw = dict(alpha=2, tau=tau)
+    ref = _oracle_run('KLDLoss', dict(transform_config={'loss_type': 'pixel'}, **kw), s, t, shape[2:], 1)
+    crit = sd.KLDLoss(transform_config={'loss_type': 'pixel'}, **kw)
+    got = _run(crit, s, t, shape[2:], 1)
+    assert _cabi.last_kernel() == 'kl_pixels_warp_kernel'
+    _assert_close(*got, *ref, loss_rtol=2e-5, grad_rtol=BF16_GRAD_RTOL)
+    # per-pixel KL through the C ABI
+    _, _, row64 = oracle.kld_closed_form_f64(s.float().numpy(), t.float().numpy(), 'pixel', 1, tau, 2.0)
+    loss1, ds1, rows, _ = _cabi.kl_pixels(s.to(dev()), t.to(dev()), tau=tau, alpha=2.0, want_row_kl=True)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(rows.cpu().numpy(), np.asarray(row64).reshape(-1), rtol=2e-5, atol=1e-7)
+    # twice the same bits
+    loss2, ds2, _, _ = _cabi.kl_pixels(s.to(dev()), t.to(dev()), tau=tau, alpha=2.0)
+    torch.cuda.synchronize()
+    assert torch.equal(ds2, ds1) and loss2.item() == loss1.item()
+    sn, tn = _near_pair(shape, seed=9, offset=-1.0, dtype=torch.bfloat16)
+    f64_loss, f64_grad, _ = oracle.kld_closed_form_f64(sn.float().numpy(), tn.float().numpy(), 'pixel', 1, tau, 2.0)
+    loss, grad = _run(sd.KLDLoss(transform_config={'loss_type': 'pixel'}, **kw), sn, tn, shape[2:], 1)
+    # (tau = 4 on 128 pixels: KL ~ 6e-6, the first-order terms that cancel are 1e3 x larger: 1.7e-4 measured)
+    _check_near(loss, grad, f64_loss, f64_grad, tol=1e-4 if f64_loss > 2e-5 else 4e-4, gtol=BF16_GRAD_RTOL)
+
+
 def test_resize_to_label_size_is_honoured():
     s, t = seeded_pair((2, 12, 16, 16), seed=8)
     for cls in ('CDLoss', 'PDLoss', 'CGDLoss'):
