@@ -35,6 +35,7 @@ struct ProducerState {
     int v0, stage, free_slots;
     uint64_t pol;
     float kl, sq;
+    float q[32][6];        // warp 0: {zs, zt, a2, dd, row} of up to 32 rows awaiting their KL, the lane's KL sum
 };
 constexpr size_t kRowsSmemBytes = (size_t)kStages * kStageBytes + (kStages + 1) * sizeof(uint64_t) +
                                   2 * kWarps * kRedFloats * sizeof(float) + sizeof(ProducerState);
@@ -192,6 +193,8 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
     int par = 0;
 
     UnitCursor cur;
+    int nrow = 0;
+    if (warp == 0) ps.q[lane][5] = 0.f;
     SD_RT_DECL
     for (cur.init(p, blockIdx.x); cur.u < p.total_units; cur.advance(p, (int)gridDim.x)) {
         SD_RT_START
@@ -382,12 +385,28 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
         }
         par ^= 1;
 
-        if (tid == 0) {
-            const float kl = kl_from_stats(Zs, Zt, A, DD);
-            if (p.l[0].row_kl) p.l[0].row_kl[x.b * p.l[0].G + x.grp] = kl;
-            ps.kl += kl;
-            if (MSE) ps.sq += SQ;
+        if (warp == 0) {
+            // lane (row count & 31) of warp 0 keeps the row's statistics: the logarithms of kl_from_stats run once per
+            // 32 rows with all lanes busy (~70 instructions that the other 15 warps would wait for behind the barrier)
+            if (lane == (nrow & 31)) {
+                ps.q[lane][0] = Zs;
+                ps.q[lane][1] = Zt;
+                ps.q[lane][2] = A;
+                ps.q[lane][3] = DD;
+                ps.q[lane][4] = __int_as_float(x.b * p.l[0].G + x.grp);
+            }
+            if (MSE && lane == 0) ps.sq += SQ;
+            if ((nrow & 31) == 31 || cur.u + (long long)gridDim.x >= p.total_units) {
+                __syncwarp();
+                if (lane <= (nrow & 31)) {
+                    const float kl = kl_from_stats(ps.q[lane][0], ps.q[lane][1], ps.q[lane][2], ps.q[lane][3]);
+                    if (p.l[0].row_kl) p.l[0].row_kl[__float_as_int(ps.q[lane][4])] = kl;
+                    ps.q[lane][5] += kl;
+                }
+                __syncwarp();
+            }
         }
+        ++nrow;
 
         SD_RT_MARK(4)
         // ---- gradient straight from registers
@@ -450,6 +469,11 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
     }
     SD_RT_WRITE
 
+    if (warp == 0) {
+        const float cta_kl = warp_sum(ps.q[lane][5]);
+        if (lane == 0) ps.kl = cta_kl;
+        __syncwarp();
+    }
     rows_finish_loss<MSE>(p, ps, warp, lane);
 }
 
@@ -479,7 +503,7 @@ struct RmProducer {
     long long u_next;      // next unit this CTA loads
     int stage;             // ... into this stage
     uint64_t pol;
-    float kl;
+    float q[32][6];        // warp 0: {zs, zt, a2, dd, row} of up to 32 rows awaiting their KL, the lane's KL sum
 };
 constexpr int kRmWarpVecs = kDataRegs / 8 * 32;                  // 16-byte vectors of a row one warp holds (contiguous: 2 KB)
 constexpr size_t kRmSmemBytes = (size_t)kRmStages * kRmStageBytes + kRmRowBytes + (kRmStages + 1) * sizeof(uint64_t) +
@@ -538,7 +562,6 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_rm_kernel(const RowsParam
         ps.u_next = blockIdx.x;
         ps.stage = 0;
         ps.pol = l2_policy_evict_first();
-        ps.kl = 0.f;
         for (int s = 0; s < kRmStages; ++s) rm_issue_row(p, ps, smem, full);
     }
     __syncthreads();
@@ -598,6 +621,18 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_rm_kernel(const RowsParam
         read_refs(red + par * kWarps * kRedFloats, sig, th);
         par ^= 1;
     }
+    // warp 0: statistics of up to 32 rows, one per lane (shared memory: the compute warps need all their registers)
+    int nrow = 0;
+    if (warp == 0) ps.q[lane][5] = 0.f;
+    auto flush_kl = [&](int last) {              // rows (last & ~31) .. last of this CTA
+        __syncwarp();
+        if (lane <= (last & 31)) {
+            const float kl = kl_from_stats(ps.q[lane][0], ps.q[lane][1], ps.q[lane][2], ps.q[lane][3]);
+            if (p.l[0].row_kl) p.l[0].row_kl[__float_as_uint(ps.q[lane][4])] = kl;
+            ps.q[lane][5] += kl;
+        }
+        __syncwarp();
+    };
     SD_RT_DECL
     while (have) {
         SD_RT_START
@@ -661,13 +696,19 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_rm_kernel(const RowsParam
         const float4 r4 = *reinterpret_cast<const float4*>(recs + (lane & 15) * kRedFloats);
         const float Zs = sum16(r4.x), Zt = sum16(r4.y);
         if (warp == 0) {
+            // lane (row count & 31) of warp 0 keeps the row's statistics: the logarithms of kl_from_stats run once per
+            // 32 rows with all lanes busy (~70 instructions that the other 15 warps would wait for behind every barrier)
             const float A = sum16(r4.z), DD = sum16(r4.w);
-            if (tid == 0) {
-                const float kl = kl_from_stats(Zs, Zt, A, DD);
-                if (p.l[0].row_kl) p.l[0].row_kl[u] = kl;
-                ps.kl += kl;
+            if (lane == (nrow & 31)) {
+                ps.q[lane][0] = Zs;
+                ps.q[lane][1] = Zt;
+                ps.q[lane][2] = A;
+                ps.q[lane][3] = DD;
+                ps.q[lane][4] = __uint_as_float(u);
             }
+            if ((nrow & 31) == 31 || !next) flush_kl(nrow);
         }
+        ++nrow;
         SD_RT_MARK(4)
 
         // ---- gradient from registers into the warp's 2 KB of the staging row, from there by one bulk store
@@ -720,9 +761,10 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_rm_kernel(const RowsParam
 
     // ---- loss: per-CTA partials, last CTA sums them in a fixed order
     if (warp == 0) {
+        const float cta_kl = warp_sum(ps.q[lane][5]);
         unsigned ticket = 0;
         if (lane == 0) {
-            __stcg(&p.cta_part[blockIdx.x], ps.kl);
+            __stcg(&p.cta_part[blockIdx.x], cta_kl);
             __threadfence();
             ticket = atomicAdd(&p.ctrl[0], 1u);
         }
