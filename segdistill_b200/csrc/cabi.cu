@@ -1082,7 +1082,7 @@ int sd_scale_grad_group(int n_tensors, void* const* dS, const int64_t* numel, in
     const int VE = 16 / elem_size(dtype);
     long long want = (most / VE + 255) / 256;
     if (want < 1) want = 1;
-    int grid = dev.sms * 8 / n_tensors;
+    int grid = dev.sms * 4 / n_tensors;
     if (grid < 1) grid = 1;
     if (want < grid) grid = (int)want;
     cudaError_t e = sd::launch_scale_grad_group(n_tensors, dS, nn, dtype == SD_BF16, grad_outputs, grid,
@@ -1101,7 +1101,7 @@ int sd_scale_grad(void* dS, int64_t numel, int dtype, const float* grad_output, 
     const int VE = 16 / elem_size(dtype);
     long long want = (numel / VE + 255) / 256;
     if (want < 1) want = 1;
-    int grid = dev.sms * 8;
+    int grid = dev.sms * 2;      // (scale_span: the usual launch has nothing to scale, it only starts and ends)
     if (want < grid) grid = (int)want;
     cudaError_t e = sd::launch_scale_grad(dS, numel, dtype == SD_BF16, grad_output, grid,
                                           static_cast<cudaStream_t>(stream));
@@ -1131,7 +1131,7 @@ int sd_scale_grad2(void* dS, int64_t numel, int dtype, const float* grad_output0
     const int VE = 16 / elem_size(dtype);
     long long want = (numel / VE + 255) / 256;
     if (want < 1) want = 1;
-    int grid = dev.sms * 8;
+    int grid = dev.sms * 2;      // (scale_span: the usual launch has nothing to scale, it only starts and ends)
     if (want < grid) grid = (int)want;
     cudaError_t e = sd::launch_scale_grad2(dS, numel, dtype == SD_BF16, grad_output0, grad_output1, nonuniform_flag,
                                            grid, static_cast<cudaStream_t>(stream));

@@ -72,20 +72,34 @@ __global__ void __launch_bounds__(1024) mse_finalize(const float* __restrict__ p
     }
 }
 
-template <typename T, bool VEC>
-__global__ void __launch_bounds__(256) scale_grad_kernel(T* __restrict__ x, long long n, const float* __restrict__ g) {
+// x[0 .. n) *= gv by the whole grid.  The grids are small (two CTAs per SM: the usual launch finds gv == 1 and only has
+// to start and end - 1184 CTAs took 3 us to do that, 296 take half), so a thread keeps four 16-byte vectors in flight.
+template <typename T>
+__device__ __forceinline__ void scale_span(T* __restrict__ x, long long n, float gv, bool vec) {
     using E = Elem<T>;
     using vec_t = typename E::vec_t;
     constexpr int VE = E::kVec;
-    const float gv = *g;
-    if (gv == 1.0f) return;  // the usual case: loss enters the total as a plain sum
     const long long stride = (long long)gridDim.x * 256;
     const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
     long long done = 0;
-    if (VEC) {
+    if (vec) {
         const long long nvec = n / VE;
         vec_t* vx = reinterpret_cast<vec_t*>(x);
-        for (long long i = gid; i < nvec; i += stride) {
+        long long i = gid;
+        for (; i + 3 * stride < nvec; i += 4 * stride) {
+            vec_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = vx[i + u * stride];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float a[VE];
+                E::unpack(v[u], a);
+#pragma unroll
+                for (int k = 0; k < VE; ++k) a[k] *= gv;
+                vx[i + u * stride] = E::pack(a);
+            }
+        }
+        for (; i < nvec; i += stride) {
             float a[VE];
             E::unpack(vx[i], a);
 #pragma unroll
@@ -97,6 +111,13 @@ __global__ void __launch_bounds__(256) scale_grad_kernel(T* __restrict__ x, long
     for (long long i = done + gid; i < n; i += stride) E::store(x + i, E::load(x + i) * gv);
 }
 
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) scale_grad_kernel(T* __restrict__ x, long long n, const float* __restrict__ g) {
+    const float gv = *g;
+    if (gv == 1.0f) return;  // the usual case: loss enters the total as a plain sum
+    scale_span<T>(x, n, gv, VEC);
+}
+
 // The same for the tensors of a grouped launch (sd_kl_rows_group_fwd_bwd): tensor k = blockIdx.y, dS[k] *= *g[k]; ONE launch
 // for all of them (a dispatcher step over several layers otherwise pays one launch per layer in its backward).
 struct ScaleGroup {
@@ -106,30 +127,11 @@ struct ScaleGroup {
 };
 template <typename T>
 __global__ void __launch_bounds__(256) scale_grad_group_kernel(const ScaleGroup a) {
-    using E = Elem<T>;
-    using vec_t = typename E::vec_t;
-    constexpr int VE = E::kVec;
     const int k = blockIdx.y;
     const float gv = *a.g[k];
     if (gv == 1.0f) return;
     T* x = static_cast<T*>(a.x[k]);
-    const long long n = a.n[k];
-    const long long stride = (long long)gridDim.x * 256;
-    const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
-    long long done = 0;
-    if ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
-        const long long nvec = n / VE;
-        vec_t* vx = reinterpret_cast<vec_t*>(x);
-        for (long long i = gid; i < nvec; i += stride) {
-            float v[VE];
-            E::unpack(vx[i], v);
-#pragma unroll
-            for (int q = 0; q < VE; ++q) v[q] *= gv;
-            vx[i] = E::pack(v);
-        }
-        done = nvec * VE;
-    }
-    for (long long i = done + gid; i < n; i += stride) E::store(x + i, E::load(x + i) * gv);
+    scale_span<T>(x, a.n[k], gv, (reinterpret_cast<uintptr_t>(x) & 15u) == 0);
 }
 cudaError_t launch_scale_grad_group(int n_tensors, void* const* dS, const long long* numel, bool bf16, const float* const* g,
                                     int grid, cudaStream_t stream) {
@@ -152,29 +154,11 @@ cudaError_t launch_scale_grad_group(int n_tensors, void* const* dS, const long l
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) scale_grad2_kernel(T* __restrict__ x, long long n, const float* __restrict__ g0,
                                                           const float* __restrict__ g1, unsigned* __restrict__ flag) {
-    using E = Elem<T>;
-    using vec_t = typename E::vec_t;
-    constexpr int VE = E::kVec;
     const float a = *g0, b = *g1;
     const bool uniform = a == b;
     if (blockIdx.x == 0 && threadIdx.x == 0) *flag = uniform ? 0u : 1u;
     if (!uniform || a == 1.0f) return;
-    const long long stride = (long long)gridDim.x * 256;
-    const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
-    long long done = 0;
-    if (VEC) {
-        const long long nvec = n / VE;
-        vec_t* vx = reinterpret_cast<vec_t*>(x);
-        for (long long i = gid; i < nvec; i += stride) {
-            float v[VE];
-            E::unpack(vx[i], v);
-#pragma unroll
-            for (int k = 0; k < VE; ++k) v[k] *= a;
-            vx[i] = E::pack(v);
-        }
-        done = nvec * VE;
-    }
-    for (long long i = done + gid; i < n; i += stride) E::store(x + i, E::load(x + i) * a);
+    scale_span<T>(x, n, a, VEC);
 }
 
 // The step's loss scalars into slot (*cursor mod slots) of a device-resident ring, cursor += 1: one warp, capturable
