@@ -415,6 +415,10 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
         const float ks = coef * ref_factor(ms, Ms, c2) / Zs;
         const float kt = coef * ref_factor(mt, Mt, c2) / Zt;
         const F2 KS = f2_dup(ks), NKT = f2_dup(-kt);
+        // (MSE: the exponents are computed again; as common subexpressions with the statistics loop they were all kept
+        //  alive across the reductions, i.e. spilled - see kl_rows_pack_kernel)
+        float ms2g = ms2, mt2g = mt2;
+        if (MSE) asm volatile("" : "+f"(ms2g), "+f"(mt2g));
         auto grad_vec = [&](int v, float* o) {
 #pragma unroll
             for (int q = 0; q < VE; q += 2) {
@@ -422,8 +426,8 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_tma_kernel(const RowsPara
                 if (MSE) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const float es = fast_exp2(fmaf(s[i + h], c2, -ms2));
-                        const float et = fast_exp2(fmaf(t[i + h], c2, -mt2));
+                        const float es = fast_exp2(fmaf(s[i + h], c2, -ms2g));
+                        const float et = fast_exp2(fmaf(t[i + h], c2, -mt2g));
                         o[q + h] = fmaf(es, ks, -et * kt) + p.mse_gcoef * (s[i + h] - t[i + h]);
                     }
                 } else if constexpr (kPacked) {
@@ -996,6 +1000,11 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_pack_kernel(const RowsPar
             if (p.grad_out[0] != nullptr) coef *= __ldg(p.grad_out[0]);
             const float ks = coef * ref_factor(ms, Ms, c2) / Zs;
             const float kt = coef * ref_factor(mt, Mt, c2) / Zt;
+            // (MSE: the exponents are computed again below; seen as the same expressions as in the statistics loop they
+            //  were all kept alive across the reductions - spilled to local memory, which this kernel's shared-memory
+            //  carve-out leaves no L1 for)
+            float ms2g = ms2, mt2g = mt2;
+            if (MSE) asm volatile("" : "+f"(ms2g), "+f"(mt2g));
             vec_t* dst = reinterpret_cast<vec_t*>(static_cast<T*>(p.dS)) + (size_t)u * RPU * nvec_row + cv0;
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
@@ -1004,8 +1013,8 @@ __global__ void __launch_bounds__(kThreads, 1) kl_rows_pack_kernel(const RowsPar
                 for (int k = 0; k < VE; ++k) {
                     const int i = j * VE + k;
                     if (MSE) {
-                        const float es = fast_exp2(fmaf(s[i], c2, -ms2));
-                        const float et = fast_exp2(fmaf(t[i], c2, -mt2));
+                        const float es = fast_exp2(fmaf(s[i], c2, -ms2g));
+                        const float et = fast_exp2(fmaf(t[i], c2, -mt2g));
                         o[k] = fmaf(es, ks, -et * kt) + p.mse_gcoef * (s[i] - t[i]);
                     } else {
                         o[k] = fmaf(s[i], ks, -t[i] * kt);
