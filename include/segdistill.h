@@ -79,6 +79,7 @@ extern "C" {
 #define SD_ALGO_CLUSTER 4
 #define SD_ALGO_ROWS1   5   /* one row per CTA pass even where several short rows could be packed (tests) */
 #define SD_ALGO_GRID    6   /* grid-resident single pass: long rows spread over all SMs (cooperative launch) */
+#define SD_ALGO_WARP    7   /* sd_kl_pixels_fwd_bwd: one warp per pixel column (kl_pixels_warp_kernel; AUTO takes it for bf16) */
 
 /* argument errors */
 #define SD_OK               0

@@ -19,9 +19,9 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, 'libsegdistill_sm100.so')
 
 SD_F32, SD_BF16 = 0, 1
-ALGO_AUTO, ALGO_GENERIC, ALGO_TMA, ALGO_STREAM, ALGO_CLUSTER, ALGO_ROWS1, ALGO_GRID = 0, 1, 2, 3, 4, 5, 6
+ALGO_AUTO, ALGO_GENERIC, ALGO_TMA, ALGO_STREAM, ALGO_CLUSTER, ALGO_ROWS1, ALGO_GRID, ALGO_WARP = 0, 1, 2, 3, 4, 5, 6, 7
 ALGOS = {'auto': ALGO_AUTO, 'generic': ALGO_GENERIC, 'tma': ALGO_TMA, 'stream': ALGO_STREAM,
-         'cluster': ALGO_CLUSTER, 'rows1': ALGO_ROWS1, 'grid': ALGO_GRID}
+         'cluster': ALGO_CLUSTER, 'rows1': ALGO_ROWS1, 'grid': ALGO_GRID, 'warp': ALGO_WARP}
 
 # every symbol include/segdistill.h declares (tests check the library exports all of them)
 EXPORTS = (

@@ -203,14 +203,15 @@ bool rows_rm() {
     }
     return v != 0;
 }
-// bf16 PD (no AT term): kl_pixels_warp_kernel (every warp on its own); SEGDISTILL_PIX_WARP=0 keeps kl_pixels_tma_kernel
-bool pix_warp() {
+// PD (no AT term): kl_pixels_warp_kernel (every warp on its own).  SEGDISTILL_PIX_WARP: 0 = kl_pixels_tma_kernel always,
+// 1 = bf16 launches, 2 = fp32 launches too
+int pix_warp() {
     static int v = -1;
     if (v < 0) {
         const char* e = std::getenv("SEGDISTILL_PIX_WARP");
-        v = e ? (std::atoi(e) != 0) : 1;
+        v = e ? std::atoi(e) : 1;
     }
-    return v != 0;
+    return v;
 }
 bool prefer_grid() {
     static int v = -1;
@@ -796,9 +797,12 @@ int sd_kl_pixels_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl, 
 
     // bf16 PD: the kernel with one warp per pixel column takes up to 256 channels
     const bool at_term = p.at_gcoef != 0.f || p.at_loss != nullptr;
-    const int tpx_w = sd::kl_pixels_warp_tile_pixels();
-    const bool warp_ok = layout_ok && bf16 && !at_term && C <= 256 && sd::pix_warp_stages(C) >= 2 && pix_warp() &&
-                         tensor_map_encoder() != nullptr && (long long)B * ((HW + tpx_w - 1) / tpx_w) < (1ll << 31);
+    const int tpx_w = sd::kl_pixels_warp_tile_pixels(bf16);
+    const bool warp_can = layout_ok && !at_term && C <= 256 && sd::pix_warp_stages(C) >= 2 && tensor_map_encoder() != nullptr &&
+                          (long long)B * ((HW + tpx_w - 1) / tpx_w) < (1ll << 31);
+    // (fp32 launches are HBM-bound on kl_pixels_tma_kernel and 3 % slower here - 32-pixel tiles, twice as many: bf16 only)
+    const bool warp_ok = warp_can && (algo == SD_ALGO_WARP || (pix_warp() >= (bf16 ? 1 : 2) &&
+                                                               (algo == SD_ALGO_AUTO || algo == SD_ALGO_TMA)));
 
     bool use_tma;
     if (algo == SD_ALGO_TMA) {
@@ -808,15 +812,18 @@ int sd_kl_pixels_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl, 
         use_tma = false;
     } else if (algo == SD_ALGO_AUTO) {
         use_tma = tma_ok;
+    } else if (algo == SD_ALGO_WARP) {
+        if (!warp_can) return SD_ERR_UNSUPPORTED;
+        use_tma = false;
     } else {
         return SD_ERR_VALUE;
     }
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
-    if (warp_ok && (algo == SD_ALGO_AUTO || algo == SD_ALGO_TMA)) {
+    if (warp_ok) {
         alignas(64) CUtensorMap mS, mT, mD;
-        const int tpx = sd::kl_pixels_warp_tile_pixels();
+        const int tpx = tpx_w;
         if (!encode_pixel_map(&mS, S, B, C, HW, dtype, tpx, true) || !encode_pixel_map(&mT, T, B, C, HW, dtype, tpx, true) ||
             !encode_pixel_map(&mD, dS, B, C, HW, dtype, tpx, true))
             return (int)cudaErrorInvalidValue;
@@ -824,7 +831,7 @@ int sd_kl_pixels_fwd_bwd(const void* S, const void* T, void* dS, float* row_kl, 
         p.total_tiles = (long long)B * p.tiles_per_sample;
         p.nstages = sd::pix_warp_stages(C);
         int grid = (int)(p.total_tiles < dev.sms ? p.total_tiles : dev.sms);
-        e = sd::launch_kl_pixels_warp(&mS, &mT, &mD, p, grid, st);
+        e = sd::launch_kl_pixels_warp(&mS, &mT, &mD, p, bf16, grid, st);
         g_launches += 1;
         t_last_kernel = "kl_pixels_warp_kernel";
     } else if (use_tma) {

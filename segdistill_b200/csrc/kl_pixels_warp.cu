@@ -24,7 +24,6 @@ namespace sd {
 
 constexpr int kPwWarps = 16;                       // compute warps = 4-pixel columns of a tile
 constexpr int kPwThreads = 32 * (kPwWarps + 1);    // + the producer warp
-constexpr int kPwTilePx = 4 * kPwWarps;            // 64 pixels = 128 bytes of bf16
 constexpr int kPwStages = 5;                       // ring stages at most (p.nstages: as many as fit, C = 150: 5, C = 256: 3)
 constexpr uint32_t kNegInf2 = 0xff80ff80u;
 
@@ -66,12 +65,57 @@ __device__ __forceinline__ float warp_sum16_transposed(const float (&v)[16], int
     return t;
 }
 
+// what differs between the element types: pixels of a lane's 8-byte column (4 bf16 / 2 fp32), i.e. H = 2 / 1 pixel pairs
+template <typename T>
+struct PwTraits;
+template <>
+struct PwTraits<__nv_bfloat16> {
+    static constexpr int kPairs = 2;
+    static __device__ __forceinline__ void pair(const uint2& w, int h, float& a, float& b) {
+        Elem<__nv_bfloat16>::unpack2(h ? w.y : w.x, a, b);
+    }
+    // running maxima of the column's pixels, packed like the data
+    static __device__ __forceinline__ uint2 max_init() { return make_uint2(kNegInf2, kNegInf2); }
+    static __device__ __forceinline__ void max_acc(uint2& m, const uint2& w) {
+        asm("max.bf16x2 %0, %1, %2;" : "=r"(m.x) : "r"(m.x), "r"(w.x));
+        asm("max.bf16x2 %0, %1, %2;" : "=r"(m.y) : "r"(m.y), "r"(w.y));
+    }
+    static __device__ __forceinline__ void store_pair(uint2& o, int h, float a, float b) {
+        (h ? o.y : o.x) = Elem<__nv_bfloat16>::pack2(a, b);
+    }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }   // (bf16 results)
+};
+template <>
+struct PwTraits<float> {
+    static constexpr int kPairs = 1;
+    static __device__ __forceinline__ void pair(const uint2& w, int, float& a, float& b) {
+        a = __uint_as_float(w.x);
+        b = __uint_as_float(w.y);
+    }
+    static __device__ __forceinline__ uint2 max_init() { return make_uint2(0xff800000u, 0xff800000u); }
+    static __device__ __forceinline__ void max_acc(uint2& m, const uint2& w) {
+        m.x = __float_as_uint(fmaxf(__uint_as_float(m.x), __uint_as_float(w.x)));
+        m.y = __float_as_uint(fmaxf(__uint_as_float(m.y), __uint_as_float(w.y)));
+    }
+    static __device__ __forceinline__ void store_pair(uint2& o, int, float a, float b) {
+        o.x = __float_as_uint(a);
+        o.y = __float_as_uint(b);
+    }
+    static __device__ __forceinline__ float div(float a, float b) { return a / b; }
+};
+
 // CPT = channels per lane = ceil(C / 32); only the last slot of a lane can be missing (C > 32 (CPT - 1))
-template <int CPT>
+template <typename T, int CPT>
 __global__ void __launch_bounds__(kPwThreads, 1)
 kl_pixels_warp_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUtensorMap mapT,
                       const __grid_constant__ CUtensorMap mapD, const PixParams p) {
-    using E = Elem<__nv_bfloat16>;
+    using W = PwTraits<T>;
+    constexpr int H = W::kPairs;               // pixel pairs of a column
+    constexpr int PXW = 2 * H;                 // pixels of a column
+    constexpr int NVAL = 4 * PXW;              // sums of a column: v[4 px + {zs, zt, a, dd}]
+    constexpr int SH = NVAL == 16 ? 1 : 2;     // the transposed reduction leaves value L >> SH on lane L
+    constexpr int LPP = 4 << SH;               // lanes per pixel (8 / 16): as many tiles share one evaluation of the logarithms
+    constexpr int kTilePx = PXW * kPwWarps;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const unsigned tile_bytes = pw_tile_bytes(p.C);
@@ -100,7 +144,7 @@ kl_pixels_warp_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_con
     auto tile_coords = [&](int k, int& b, int& px0) {
         const unsigned tile = blockIdx.x + (unsigned)k * gridDim.x;
         b = (int)(tile / tps);
-        px0 = (int)(tile - (unsigned)b * tps) * kPwTilePx;
+        px0 = (int)(tile - (unsigned)b * tps) * kTilePx;
     };
 
     if (warp == kPwWarps) {
@@ -145,17 +189,17 @@ kl_pixels_warp_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_con
         const unsigned col_off = (unsigned)lane * 128u + ((((unsigned)warp >> 1) ^ ((unsigned)lane & 7u)) << 4) + ((unsigned)warp & 1u) * 8u;
         const bool last_ok = lane + 32 * (CPT - 1) < p.C;
         float acc_kl = 0.f;
-        // the four statistics of one pixel, collected over eight tiles: lane 8 px + i keeps pixel px of the column in
-        // tile (k & ~7) + i; the logarithms of kl_from_stats then run once per eight tiles with all lanes busy
+        // the four statistics of one pixel, collected over LPP tiles: lane LPP px + i keeps pixel px of the column in
+        // tile (k & ~(LPP - 1)) + i; the logarithms of kl_from_stats then run once per LPP tiles with all lanes busy
         float q_zs = 1.f, q_zt = 1.f, q_a = 0.f, q_dd = 0.f;
         int st = 0;
         uint32_t par = 0;
-        auto flush_kl = [&](int k_last) {      // tiles (k_last & ~7) .. k_last
-            const int kk = (k_last & ~7) + (lane & 7);
+        auto flush_kl = [&](int k_last) {      // tiles (k_last & ~(LPP - 1)) .. k_last
+            const int kk = (k_last & ~(LPP - 1)) + (lane & (LPP - 1));
             if (kk <= k_last) {
                 int b, px0;
                 tile_coords(kk, b, px0);
-                const int px = px0 + 4 * warp + (lane >> 3);
+                const int px = px0 + PXW * warp + lane / LPP;
                 if (px < p.HW) {
                     const float kl = kl_from_stats(q_zs, q_zt, q_a, q_dd);
                     p.row_kl[(size_t)b * p.HW + px] = kl;
@@ -172,50 +216,45 @@ kl_pixels_warp_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_con
             unsigned char* ts = smem + (size_t)st * stage_bytes + col_off;
             const unsigned char* tt = ts + tile_bytes;
 
-            // ---- my channels of the column, packed; packed maxima over them
+            // ---- my channels of the column as they lie in the tile; maxima over them
             uint2 rs[CPT], rt[CPT];
-            uint2 ms2 = make_uint2(kNegInf2, kNegInf2), mt2 = ms2;
+            uint2 ms2 = W::max_init(), mt2 = W::max_init();
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 if (j < CPT - 1 || last_ok) {
                     rs[j] = *reinterpret_cast<const uint2*>(ts + j * 4096);
                     rt[j] = *reinterpret_cast<const uint2*>(tt + j * 4096);
-                    asm("max.bf16x2 %0, %1, %2;" : "=r"(ms2.x) : "r"(ms2.x), "r"(rs[j].x));
-                    asm("max.bf16x2 %0, %1, %2;" : "=r"(ms2.y) : "r"(ms2.y), "r"(rs[j].y));
-                    asm("max.bf16x2 %0, %1, %2;" : "=r"(mt2.x) : "r"(mt2.x), "r"(rt[j].x));
-                    asm("max.bf16x2 %0, %1, %2;" : "=r"(mt2.y) : "r"(mt2.y), "r"(rt[j].y));
+                    W::max_acc(ms2, rs[j]);
+                    W::max_acc(mt2, rt[j]);
                 }
             }
             // ---- pixel maxima over the 32 lanes -> references of the exponents
-            F2 NS[2], NT[2];
-            {
-                float a0, a1, a2, a3;
-                E::unpack2(ms2.x, a0, a1);
-                E::unpack2(ms2.y, a2, a3);
-                NS[0] = f2_make(-__fmul_rn(warp_max_uniform(a0), c2), -__fmul_rn(warp_max_uniform(a1), c2));
-                NS[1] = f2_make(-__fmul_rn(warp_max_uniform(a2), c2), -__fmul_rn(warp_max_uniform(a3), c2));
-                E::unpack2(mt2.x, a0, a1);
-                E::unpack2(mt2.y, a2, a3);
-                NT[0] = f2_make(-__fmul_rn(warp_max_uniform(a0), c2), -__fmul_rn(warp_max_uniform(a1), c2));
-                NT[1] = f2_make(-__fmul_rn(warp_max_uniform(a2), c2), -__fmul_rn(warp_max_uniform(a3), c2));
+            F2 NS[H], NT[H];
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                float a0, a1;
+                W::pair(ms2, h, a0, a1);
+                NS[h] = f2_make(-__fmul_rn(warp_max_uniform(a0), c2), -__fmul_rn(warp_max_uniform(a1), c2));
+                W::pair(mt2, h, a0, a1);
+                NT[h] = f2_make(-__fmul_rn(warp_max_uniform(a0), c2), -__fmul_rn(warp_max_uniform(a1), c2));
             }
 
             // ---- exponentials (kept in registers) and the thread's sums per pixel pair
-            F2 es[CPT][2], et[CPT][2];
-            float v[16];
+            F2 es[CPT][H], et[CPT][H];
+            float v[NVAL];
             {
                 const F2 C2 = f2_dup(c2), neg1 = f2_dup(-1.f);
-                F2 ZS[2], ZT[2], A[2], DD[2];
+                F2 ZS[H], ZT[H], A[H], DD[H];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) ZS[h] = ZT[h] = A[h] = DD[h] = f2_dup(0.f);
+                for (int h = 0; h < H; ++h) ZS[h] = ZT[h] = A[h] = DD[h] = f2_dup(0.f);
 #pragma unroll
                 for (int j = 0; j < CPT; ++j) {
                     if (j < CPT - 1 || last_ok) {
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
+                        for (int h = 0; h < H; ++h) {
                             float s0, s1, t0, t1;
-                            E::unpack2(h ? rs[j].y : rs[j].x, s0, s1);
-                            E::unpack2(h ? rt[j].y : rt[j].x, t0, t1);
+                            W::pair(rs[j], h, s0, s1);
+                            W::pair(rt[j], h, t0, t1);
                             const F2 as2 = f2_fma(f2_make(s0, s1), C2, NS[h]), at2 = f2_fma(f2_make(t0, t1), C2, NT[h]);
                             float as0, as1, at0, at1;
                             f2_split(as2, as0, as1);
@@ -228,50 +267,56 @@ kl_pixels_warp_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_con
                             A[h] = f2_fma(et[j][h], f2_fma(as2, neg1, at2), A[h]);
                         }
                     } else {
-                        es[j][0] = es[j][1] = et[j][0] = et[j][1] = f2_dup(0.f);
+#pragma unroll
+                        for (int h = 0; h < H; ++h) es[j][h] = et[j][h] = f2_dup(0.f);
                     }
                 }
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {          // pixel 2 h + {0, 1}: v[4 px + {zs, zt, a, dd}]
+                for (int h = 0; h < H; ++h) {          // pixel 2 h + {0, 1}: v[4 px + {zs, zt, a, dd}]
                     f2_split(ZS[h], v[8 * h + 0], v[8 * h + 4]);
                     f2_split(ZT[h], v[8 * h + 1], v[8 * h + 5]);
                     f2_split(A[h], v[8 * h + 2], v[8 * h + 6]);
                     f2_split(DD[h], v[8 * h + 3], v[8 * h + 7]);
                 }
             }
-            // ---- column sums: lanes L, L ^ 1 hold value L >> 1 = 4 px + stat
-            const float tot = warp_sum16_transposed(v, lane);
-            // the statistics of pixel px (lanes 8 px + {0, 2, 4, 6}) -> lane 8 px + (k & 7)
+            // ---- column sums: lane L holds value L >> SH = 4 px + stat
+            float tot;
+            if constexpr (NVAL == 16) tot = warp_sum16_transposed(v, lane);
+            else tot = warp_sum8_transposed(v, lane);
+            // the statistics of pixel px (lanes LPP px + {0, 1, 2, 3} << SH) -> lane LPP px + (k & (LPP - 1))
             {
-                const int src = lane & 24;
-                const float zs = __shfl_sync(0xffffffffu, tot, src), zt = __shfl_sync(0xffffffffu, tot, src + 2),
-                            a = __shfl_sync(0xffffffffu, tot, src + 4), dd = __shfl_sync(0xffffffffu, tot, src + 6);
-                if ((lane & 7) == (k & 7)) {
+                const int src = lane & ~(LPP - 1);
+                const float zs = __shfl_sync(0xffffffffu, tot, src), zt = __shfl_sync(0xffffffffu, tot, src + (1 << SH)),
+                            a = __shfl_sync(0xffffffffu, tot, src + (2 << SH)), dd = __shfl_sync(0xffffffffu, tot, src + (3 << SH));
+                if ((lane & (LPP - 1)) == (k & (LPP - 1))) {
                     q_zs = zs;
                     q_zt = zt;
                     q_a = a;
                     q_dd = dd;
                 }
-                if ((k & 7) == 7 || k == my_tiles - 1) flush_kl(k);
+                if ((k & (LPP - 1)) == LPP - 1 || k == my_tiles - 1) flush_kl(k);
             }
-            // gradient factors: lanes holding zs / zt divide, everybody fetches the four pixels' pairs
-            const float kq = __fdividef(p.coef, tot);         // (bf16 results)
-            F2 KS[2], NKT[2];
-            KS[0] = f2_make(__shfl_sync(0xffffffffu, kq, 0), __shfl_sync(0xffffffffu, kq, 8));
-            KS[1] = f2_make(__shfl_sync(0xffffffffu, kq, 16), __shfl_sync(0xffffffffu, kq, 24));
-            NKT[0] = f2_make(-__shfl_sync(0xffffffffu, kq, 2), -__shfl_sync(0xffffffffu, kq, 10));
-            NKT[1] = f2_make(-__shfl_sync(0xffffffffu, kq, 18), -__shfl_sync(0xffffffffu, kq, 26));
+            // gradient factors: lanes holding zs / zt divide, everybody fetches the pixels' pairs
+            const float kq = W::div(p.coef, tot);
+            F2 KS[H], NKT[H];
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                KS[h] = f2_make(__shfl_sync(0xffffffffu, kq, (2 * h) * LPP), __shfl_sync(0xffffffffu, kq, (2 * h + 1) * LPP));
+                NKT[h] = f2_make(-__shfl_sync(0xffffffffu, kq, (2 * h) * LPP + (1 << SH)),
+                                 -__shfl_sync(0xffffffffu, kq, (2 * h + 1) * LPP + (1 << SH)));
+            }
 
             // ---- gradient in place over my column of the S tile
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 if (j < CPT - 1 || last_ok) {
                     uint2 o;
-                    float o0, o1;
-                    f2_split(f2_fma(es[j][0], KS[0], f2_mul(et[j][0], NKT[0])), o0, o1);
-                    o.x = E::pack2(o0, o1);
-                    f2_split(f2_fma(es[j][1], KS[1], f2_mul(et[j][1], NKT[1])), o0, o1);
-                    o.y = E::pack2(o0, o1);
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
+                        float o0, o1;
+                        f2_split(f2_fma(es[j][h], KS[h], f2_mul(et[j][h], NKT[h])), o0, o1);
+                        W::store_pair(o, h, o0, o1);
+                    }
                     *reinterpret_cast<uint2*>(ts + j * 4096) = o;
                 }
             }
@@ -308,10 +353,10 @@ kl_pixels_warp_kernel(const __grid_constant__ CUtensorMap mapS, const __grid_con
     }
 }
 
-template <int CPT>
+template <typename T, int CPT>
 static cudaError_t launch_pw_t(const CUtensorMap& mS, const CUtensorMap& mT, const CUtensorMap& mD, const PixParams& p, int grid,
                                cudaStream_t stream) {
-    auto kern = kl_pixels_warp_kernel<CPT>;
+    auto kern = kl_pixels_warp_kernel<T, CPT>;
     const size_t smem = pix_warp_smem_bytes(p.C, p.nstages);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -319,25 +364,31 @@ static cudaError_t launch_pw_t(const CUtensorMap& mS, const CUtensorMap& mT, con
     return cudaGetLastError();
 }
 
-int kl_pixels_warp_tile_pixels() { return kPwTilePx; }
+int kl_pixels_warp_tile_pixels(bool bf16) { return (bf16 ? 4 : 2) * kPwWarps; }
 
-// bf16, no AT term, C <= 256, maps encoded with 128-byte swizzle and boxes of (64 pixels, C, 1)
-cudaError_t launch_kl_pixels_warp(const void* mapS, const void* mapT, const void* mapD, const PixParams& p, int grid,
+template <typename T>
+static cudaError_t launch_pw_c(const CUtensorMap& mS, const CUtensorMap& mT, const CUtensorMap& mD, const PixParams& p, int grid,
+                               cudaStream_t stream) {
+    switch ((p.C + 31) / 32) {
+        case 1: return launch_pw_t<T, 1>(mS, mT, mD, p, grid, stream);
+        case 2: return launch_pw_t<T, 2>(mS, mT, mD, p, grid, stream);
+        case 3: return launch_pw_t<T, 3>(mS, mT, mD, p, grid, stream);
+        case 4: return launch_pw_t<T, 4>(mS, mT, mD, p, grid, stream);
+        case 5: return launch_pw_t<T, 5>(mS, mT, mD, p, grid, stream);
+        case 6: return launch_pw_t<T, 6>(mS, mT, mD, p, grid, stream);
+        case 7: return launch_pw_t<T, 7>(mS, mT, mD, p, grid, stream);
+        case 8: return launch_pw_t<T, 8>(mS, mT, mD, p, grid, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// no AT term, C <= 256, maps encoded with 128-byte swizzle and boxes of (128 bytes of pixels, C, 1)
+cudaError_t launch_kl_pixels_warp(const void* mapS, const void* mapT, const void* mapD, const PixParams& p, bool bf16, int grid,
                                   cudaStream_t stream) {
     const CUtensorMap& mS = *static_cast<const CUtensorMap*>(mapS);
     const CUtensorMap& mT = *static_cast<const CUtensorMap*>(mapT);
     const CUtensorMap& mD = *static_cast<const CUtensorMap*>(mapD);
-    switch ((p.C + 31) / 32) {
-        case 1: return launch_pw_t<1>(mS, mT, mD, p, grid, stream);
-        case 2: return launch_pw_t<2>(mS, mT, mD, p, grid, stream);
-        case 3: return launch_pw_t<3>(mS, mT, mD, p, grid, stream);
-        case 4: return launch_pw_t<4>(mS, mT, mD, p, grid, stream);
-        case 5: return launch_pw_t<5>(mS, mT, mD, p, grid, stream);
-        case 6: return launch_pw_t<6>(mS, mT, mD, p, grid, stream);
-        case 7: return launch_pw_t<7>(mS, mT, mD, p, grid, stream);
-        case 8: return launch_pw_t<8>(mS, mT, mD, p, grid, stream);
-        default: return cudaErrorInvalidValue;
-    }
+    return bf16 ? launch_pw_c<__nv_bfloat16>(mS, mT, mD, p, grid, stream) : launch_pw_c<float>(mS, mT, mD, p, grid, stream);
 }
 
 }  // namespace sd

@@ -53,10 +53,10 @@ cudaError_t launch_ce_up(const CeParams& p, bool bf16, int sms, cudaStream_t str
 cudaError_t launch_kl_pixels_tma(const void* mapS, const void* mapT, const PixParams& p, bool bf16, int cols, int grid,
                                  size_t smem, cudaStream_t stream);
 cudaError_t launch_kl_pixels_generic(const PixParams& p, bool bf16, cudaStream_t stream);
-// kl_pixels_warp.cu   (bf16, no AT term, C <= 256; maps with 128-byte swizzle and boxes of (64 pixels, C, 1))
-cudaError_t launch_kl_pixels_warp(const void* mapS, const void* mapT, const void* mapD, const PixParams& p, int grid,
+// kl_pixels_warp.cu   (no AT term, C <= 256; maps with 128-byte swizzle and boxes of (128 bytes of pixels, C, 1))
+cudaError_t launch_kl_pixels_warp(const void* mapS, const void* mapT, const void* mapD, const PixParams& p, bool bf16, int grid,
                                   cudaStream_t stream);
-int kl_pixels_warp_tile_pixels();
+int kl_pixels_warp_tile_pixels(bool bf16);
 int pix_warp_stages(int C);    // ring stages that fit next to C channels (0: none)
 size_t pix_tma_smem_bytes(int C, int pxt, int nstages, int cols);   // cols: 64 (one CTA per SM) or 32 (bf16: two)
 int kl_pixels_tma_max_channels(bool bf16);

@@ -429,6 +429,15 @@ def test_bf16_pixel_kernel_one_warp_per_pixel_column(shape, tau):
     loss, grad = _run(sd.KLDLoss(transform_config={'loss_type': 'pixel'}, **kw), sn, tn, shape[2:], 1)
     # (tau = 4 on 128 pixels: KL ~ 6e-6, the first-order terms that cancel are 1e3 x larger: 1.7e-4 measured)
     _check_near(loss, grad, f64_loss, f64_grad, tol=1e-4 if f64_loss > 2e-5 else 4e-4, gtol=BF16_GRAD_RTOL)
+    # the same kernel on fp32 maps (SD_ALGO_WARP; AUTO keeps kl_pixels_tma_kernel there): 32-pixel tiles, 2 pixels per lane
+    sf, tf = seeded_pair(shape, seed=43 + shape[1], scale=2.0)
+    f64_loss, f64_grad, row64 = oracle.kld_closed_form_f64(sf.numpy(), tf.numpy(), 'pixel', 1, tau, 2.0)
+    lossf, dsf, rowsf, _ = _cabi.kl_pixels(sf.to(dev()), tf.to(dev()), tau=tau, alpha=2.0, algo=_cabi.ALGO_WARP, want_row_kl=True)
+    torch.cuda.synchronize()
+    assert _cabi.last_kernel() == 'kl_pixels_warp_kernel'
+    np.testing.assert_allclose(rowsf.cpu().numpy(), np.asarray(row64).reshape(-1), rtol=2e-5, atol=1e-7)
+    assert rel_err(lossf.item(), f64_loss) <= 2e-6
+    assert np.abs(dsf.cpu().numpy() - f64_grad).max() <= 2e-6 * np.abs(f64_grad).max()
 
 
 def test_resize_to_label_size_is_honoured():
