@@ -62,6 +62,9 @@ def main():
         'cd_f32_grid': (L, torch.float32, lambda s, t: _cabi.kl_rows(s, t, group=1, algo=6)),
         'cd_bf16_grid': (L, torch.bfloat16, lambda s, t: _cabi.kl_rows(s, t, group=1, algo=6)),
         'cgd10_f32_stream': (L, torch.float32, lambda s, t: _cabi.kl_rows(s, t, group=10, tau=2.0, alpha=3.0, algo=3)),
+        'cgd10_bf16_stream': (L, torch.bfloat16, lambda s, t: _cabi.kl_rows(s, t, group=10, tau=2.0, alpha=3.0, algo=3)),
+        'fused_bf16_stream': (L, torch.bfloat16,
+                              lambda s, t: _cabi.kl_rows_multi(s, t, (10, 1), (2.0, 1.0), (3.0, 1.0), algo=3)),
         'fused_f32_stream': (L, torch.float32,
                              lambda s, t: _cabi.kl_rows_multi(s, t, (10, 1), (2.0, 1.0), (3.0, 1.0), algo=3)),
         'corr10_f32': (L, torch.float32, lambda s, t: _cabi.cgd_corr(s, t, group=10)),
