@@ -309,6 +309,14 @@ def test_bf16_rows_of_register_capacity_row_maxima_kernel(shape, g, tau, n_iter)
     loss, grad = _run(sd.CGDLoss(**kw), sn, tn, shape[2:], 1, 'auto')
     assert _cabi.last_kernel() == 'kl_rows_rm_kernel'
     _check_near(loss, grad, f64_loss, f64_grad, tol=3e-4, gtol=BF16_GRAD_RTOL)
+    # per-row KL through the C ABI (the logarithms are evaluated for 32 rows at a time), twice the same bits
+    _, _, row64 = oracle.kld_closed_form_f64(s.float().numpy(), t.float().numpy(), 'channel', g, tau, 3.0)
+    loss1, ds1, rows, _ = _cabi.kl_rows(s.to(dev()), t.to(dev()), group=g, tau=tau, alpha=3.0, want_row_kl=True)
+    loss2, ds2, _, _ = _cabi.kl_rows(s.to(dev()), t.to(dev()), group=g, tau=tau, alpha=3.0)
+    torch.cuda.synchronize()
+    assert _cabi.last_kernel() == 'kl_rows_rm_kernel'
+    np.testing.assert_allclose(rows.cpu().numpy(), np.asarray(row64).reshape(-1), rtol=2e-5, atol=1e-7)
+    assert torch.equal(ds2, ds1) and loss2.item() == loss1.item()
     # the upstream gradient is folded into dS on the device
     x = s.to(dev()).requires_grad_(True)
     (2.5 * sd.CGDLoss(**kw)(x, t.to(dev()), None, 1)).backward()
