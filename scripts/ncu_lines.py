@@ -73,6 +73,10 @@ def main():
     cands = [fn for fn in table if re.sub(r'\s+', '', demangle(fn).replace('void ', '').replace('sd::', '').split('(')[0]) == key.replace('sd::', '')]
     cands = [fn for fn in cands if len(table[fn]) == len(rows)] or cands
     if not cands:
+        # template arguments print differently in ncu and c++filt (bools, dependent types): same base name, same length
+        base = key.replace('sd::', '').split('<')[0]
+        cands = [fn for fn in table if base in fn and len(table[fn]) == len(rows)]
+    if not cands:
         print('no cubin function matches', kname)
         return
     fn = cands[0]

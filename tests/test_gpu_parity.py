@@ -411,7 +411,9 @@ def test_pixel_kernel_channel_counts(C):
                                        ((3, 19, 24, 40), 1.0),       # HW = 960: the last tile of a sample is clipped
                                        ((2, 33, 8, 8), 4.0),         # HW = 64 = one tile; second channel slot of one lane only
                                        ((1, 256, 16, 24), 1.0),      # eight channels per lane
-                                       ((2, 97, 40, 8), 1.0)])
+                                       ((2, 97, 40, 8), 1.0),
+                                       ((2, 19, 4, 4), 1.0),         # HW = 16: a tile wider than the map
+                                       ((3, 8, 2, 4), 2.0)])         # HW = 8
 def test_bf16_pixel_kernel_one_warp_per_pixel_column(shape, tau):
     """kl_pixels_warp_kernel (bf16 PD: lane = channel, warp reductions, swizzled tiles, in-place gradient + tensor
     store) against the oracle on the fp32 upcast of the same bf16 values, per-pixel KL against the float64 closed form,
@@ -435,8 +437,10 @@ def test_bf16_pixel_kernel_one_warp_per_pixel_column(shape, tau):
     sn, tn = _near_pair(shape, seed=9, offset=-1.0, dtype=torch.bfloat16)
     f64_loss, f64_grad, _ = oracle.kld_closed_form_f64(sn.float().numpy(), tn.float().numpy(), 'pixel', 1, tau, 2.0)
     loss, grad = _run(sd.KLDLoss(transform_config={'loss_type': 'pixel'}, **kw), sn, tn, shape[2:], 1)
-    # (tau = 4 on 128 pixels: KL ~ 6e-6, the first-order terms that cancel are 1e3 x larger: 1.7e-4 measured)
-    _check_near(loss, grad, f64_loss, f64_grad, tol=1e-4 if f64_loss > 2e-5 else 4e-4, gtol=BF16_GRAD_RTOL)
+    # (a few dozen pixels, or tau = 4 on 128 pixels with KL ~ 6e-6: the first-order terms that cancel are up to 1e3 x
+    #  larger than the KL and nothing averages out: 1.7e-4 .. 1.9e-4 measured - the same references as kl_pixels_tma_kernel)
+    many = shape[0] * shape[2] * shape[3] >= 1024
+    _check_near(loss, grad, f64_loss, f64_grad, tol=1e-4 if (f64_loss > 2e-5 and many) else 4e-4, gtol=BF16_GRAD_RTOL)
     # the same kernel on fp32 maps (SD_ALGO_WARP; AUTO keeps kl_pixels_tma_kernel there): 32-pixel tiles, 2 pixels per lane
     sf, tf = seeded_pair(shape, seed=43 + shape[1], scale=2.0)
     f64_loss, f64_grad, row64 = oracle.kld_closed_form_f64(sf.numpy(), tf.numpy(), 'pixel', 1, tau, 2.0)
