@@ -266,7 +266,8 @@ def run_ours(args, rank, local_rank, world):
     numel = S.numel()
     # N > 1: the path's only collective is the all-reduce of the loss scalars for logging.  The reference issues one
     # per log variable per step (SD_structure.py:137-142); here every step appends its scalars to a device-resident
-    # ring (one 32-thread launch, captured with the step) and the ring is all-reduced ONCE per LOG_INTERVAL steps -
+    # ring (no launch of its own: the append rides on the backward's scaling launch, sd_scale_grad_log; captured with
+    # the step) and the ring is all-reduced ONCE per LOG_INTERVAL steps -
     # the interval at which the reference's logger reads them (default_runtime.py:2-7).  No NCCL kernel sits between
     # two steps' loss kernels; the flush of the steps timed here is inside the timed region.
     LOG_INTERVAL = 50
@@ -287,7 +288,8 @@ def run_ours(args, rank, local_rank, world):
             _cabi.last_kernel_of_step = _cabi.last_kernel()
         l1, l2 = out.values()
         if logs is not None:
-            logs.push([l1, l2], stream=log_stream)     # device-side append, no collective; beside the backward's kernels
+            logs.push([l1, l2], in_backward=True)      # device-side append, no collective, no launch of its own: it rides
+                                                       # on the backward's scaling launch (sd_scale_grad_log)
         (l1 + l2).backward()
         if logs is not None:
             logs.join()

@@ -262,6 +262,12 @@ SD_API int sd_ifvd_class_map(const int64_t* target, int32_t* cls, int B, int Ht,
 /* ------------------------------------------------------------------ backward helper */
 /* dS *= *grad_output (a device scalar); exits without touching dS when it equals 1. */
 SD_API int sd_scale_grad(void* dS, int64_t numel, int dtype, const float* grad_output, void* stream);
+/* The same launch also appends the step's n loss scalars `values` (device) to the log ring - what sd_log_push does
+ * with a launch of its own: ring[(*cursor mod slots)][0..n) = values, *cursor += 1.  The append does not depend on
+ * grad_output.  Replaces the per-variable all_reduce + .item() of SD_structure.py:137-142 together with sd_log_push
+ * (segdistill_b200/dist.py: DeferredLogs). */
+SD_API int sd_scale_grad_log(void* dS, int64_t numel, int dtype, const float* grad_output, const float* values, int n,
+                             float* ring, unsigned* cursor, int slots, void* stream);
 /* The same for the n_tensors <= 8 gradients of a grouped launch (sd_kl_rows_group_fwd_bwd; opts.py:87-112 sums the entries'
  * losses, so every layer's gradient meets its own upstream factor in backward): dS[k] *= *grad_outputs[k], one launch. */
 SD_API int sd_scale_grad_group(int n_tensors, void* const* dS, const int64_t* numel, int dtype,

@@ -30,7 +30,7 @@ EXPORTS = (
     'sd_kl_pixels_workspace_bytes', 'sd_kl_pixels_fwd_bwd',
     'sd_kl_rows_up_workspace_bytes', 'sd_kl_rows_up_fwd_bwd', 'sd_kl_pixels_up_workspace_bytes', 'sd_kl_pixels_up_fwd_bwd',
     'sd_mse_workspace_bytes', 'sd_mse_fwd_bwd', 'sd_ifvd_sim_workspace_bytes', 'sd_ifvd_sim_fwd_bwd', 'sd_ifvd_max_channels',
-    'sd_ifvd_class_map', 'sd_scale_grad',
+    'sd_ifvd_class_map', 'sd_scale_grad', 'sd_scale_grad_log',
     'sd_cgd_corr_workspace_bytes', 'sd_cgd_corr_fwd_bwd', 'sd_log_push', 'sd_ce_up_workspace_bytes', 'sd_ce_up_fwd_bwd',
     'sd_kl_rows_group_workspace_bytes', 'sd_kl_rows_group_fwd_bwd', 'sd_scale_grad_group',
     'sd_launch_count', 'sd_last_kernel',
@@ -104,6 +104,8 @@ def load():
         lib.sd_ifvd_class_map.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
         lib.sd_scale_grad.restype = i32
         lib.sd_scale_grad.argtypes = [vp, i64, i32, vp, vp]
+        lib.sd_scale_grad_log.restype = i32
+        lib.sd_scale_grad_log.argtypes = [vp, i64, i32, vp, vp, i32, vp, vp, i32, vp]
         lib.sd_scale_grad_group.restype = i32
         lib.sd_scale_grad_group.argtypes = [i32, vp, vp, i32, vp, vp]
         lib.sd_cgd_corr_workspace_bytes.restype = sz
@@ -511,15 +513,29 @@ def cgd_corr(x_student, x_teacher, group=10, alpha=1.0, grad_scale=1.0):
     return out[0], ds
 
 
+# A step's log append that waits for a launch to ride on (dist.DeferredLogs.push(..., in_backward=True)):
+# (values, ring, cursor) or None.  The next scaling launch of a backward on the same device takes it.
+pending_log = None
+
+
 def scale_grad_(ds: torch.Tensor, grad_output: torch.Tensor):
-    """In place ``ds *= grad_output`` on the device; a no-op launch when grad_output == 1."""
+    """In place ``ds *= grad_output`` on the device; a no-op launch when grad_output == 1.  Carries a pending log
+    append (``pending_log``) when there is one for this device."""
+    global pending_log
     lib = _lib or load()
     g = grad_output
     if g.device != ds.device or g.dtype is not torch.float32 or g.numel() != 1 or g.requires_grad:
         g = grad_output.detach().to(device=ds.device, dtype=torch.float32).reshape(1)
+    dt = SD_F32 if ds.dtype is torch.float32 else _dtype_code(ds)
     with _on(ds.device):
-        rc = lib.sd_scale_grad(ds.data_ptr(), ds.numel(), SD_F32 if ds.dtype is torch.float32 else _dtype_code(ds),
-                               g.data_ptr(), _stream_ptr(ds.device))
+        log = pending_log
+        if log is not None and log[0].device == ds.device:
+            pending_log = None
+            values, ring, cursor = log
+            rc = lib.sd_scale_grad_log(ds.data_ptr(), ds.numel(), dt, g.data_ptr(), values.data_ptr(), values.numel(),
+                                       ring.data_ptr(), cursor.data_ptr(), ring.shape[0], _stream_ptr(ds.device))
+        else:
+            rc = lib.sd_scale_grad(ds.data_ptr(), ds.numel(), dt, g.data_ptr(), _stream_ptr(ds.device))
         if rc:
             _check(rc)
     return ds

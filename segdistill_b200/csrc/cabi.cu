@@ -1099,7 +1099,8 @@ int sd_scale_grad_group(int n_tensors, void* const* dS, const int64_t* numel, in
     return e == cudaSuccess ? SD_OK : (int)e;
 }
 
-int sd_scale_grad(void* dS, int64_t numel, int dtype, const float* grad_output, void* stream) {
+static int scale_grad_impl(void* dS, int64_t numel, int dtype, const float* grad_output, const float* log_values, int log_n,
+                           float* log_ring, unsigned* log_cursor, int log_slots, void* stream) {
     if (!dS || !grad_output) return SD_ERR_NULL;
     if (dtype != SD_F32 && dtype != SD_BF16) return SD_ERR_DTYPE;
     if (numel <= 0) return SD_ERR_SHAPE;
@@ -1110,11 +1111,22 @@ int sd_scale_grad(void* dS, int64_t numel, int dtype, const float* grad_output, 
     if (want < 1) want = 1;
     int grid = dev.sms * 2;      // (scale_span: the usual launch has nothing to scale, it only starts and ends)
     if (want < grid) grid = (int)want;
-    cudaError_t e = sd::launch_scale_grad(dS, numel, dtype == SD_BF16, grad_output, grid,
-                                          static_cast<cudaStream_t>(stream));
+    cudaError_t e = sd::launch_scale_grad(dS, numel, dtype == SD_BF16, grad_output, grid, static_cast<cudaStream_t>(stream),
+                                          log_values, log_n, log_ring, log_cursor, log_slots);
     g_launches += 1;
     t_last_kernel = "scale_grad_kernel";
     return e == cudaSuccess ? SD_OK : (int)e;
+}
+
+int sd_scale_grad(void* dS, int64_t numel, int dtype, const float* grad_output, void* stream) {
+    return scale_grad_impl(dS, numel, dtype, grad_output, nullptr, 0, nullptr, nullptr, 0, stream);
+}
+
+int sd_scale_grad_log(void* dS, int64_t numel, int dtype, const float* grad_output, const float* values, int n, float* ring,
+                      unsigned* cursor, int slots, void* stream) {
+    if (!values || !ring || !cursor) return SD_ERR_NULL;
+    if (n <= 0 || slots <= 0) return SD_ERR_SHAPE;
+    return scale_grad_impl(dS, numel, dtype, grad_output, values, n, ring, cursor, slots, stream);
 }
 
 int sd_log_push(const float* values, int n, float* ring, unsigned* cursor, int slots, void* stream) {

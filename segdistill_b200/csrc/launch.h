@@ -71,7 +71,8 @@ cudaError_t launch_cgd_corr(void* dS, float* loss, int B, int C, int HW, int gro
 // mse.cu
 cudaError_t launch_mse(const void* S, const void* T, void* dS, float* loss, float* partials, long long n, bool bf16,
                        float gcoef, float scale, int grid, cudaStream_t stream);
-cudaError_t launch_scale_grad(void* dS, long long n, bool bf16, const float* g, int grid, cudaStream_t stream);
+cudaError_t launch_scale_grad(void* dS, long long n, bool bf16, const float* g, int grid, cudaStream_t stream,
+                              const float* log_values, int log_n, float* log_ring, unsigned* log_cursor, int log_slots);
 cudaError_t launch_scale_grad_group(int n_tensors, void* const* dS, const long long* numel, bool bf16, const float* const* g,
                                     int grid, cudaStream_t stream);
 cudaError_t launch_scale_grad2(void* dS, long long n, bool bf16, const float* g0, const float* g1, unsigned* flag,

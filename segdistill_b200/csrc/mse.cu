@@ -111,8 +111,28 @@ __device__ __forceinline__ void scale_span(T* __restrict__ x, long long n, float
     for (long long i = done + gid; i < n; i += stride) E::store(x + i, E::load(x + i) * gv);
 }
 
+// the step's loss scalars into slot (*cursor mod slots) of the device-resident log ring, cursor += 1 (one warp)
+struct LogSink {
+    const float* values;   // null: nothing to append
+    int n;
+    float* ring;
+    unsigned* cursor;
+    unsigned slots;
+};
+__device__ __forceinline__ void log_append(const LogSink& k) {
+    const unsigned c = *k.cursor;
+    float* dst = k.ring + (size_t)(c % k.slots) * k.n;
+    for (int i = threadIdx.x; i < k.n; i += 32) dst[i] = k.values[i];
+    __syncwarp();
+    if (threadIdx.x == 0) *k.cursor = c + 1u;
+}
+
+// (sink: the backward's scaling launch can carry the step's log append - sd_scale_grad_log -, so that a step under
+//  DeferredLogs holds no launch of its own for it)
 template <typename T, bool VEC>
-__global__ void __launch_bounds__(256) scale_grad_kernel(T* __restrict__ x, long long n, const float* __restrict__ g) {
+__global__ void __launch_bounds__(256) scale_grad_kernel(T* __restrict__ x, long long n, const float* __restrict__ g,
+                                                         const LogSink sink) {
+    if (sink.values != nullptr && blockIdx.x == 0 && threadIdx.x < 32) log_append(sink);
     const float gv = *g;
     if (gv == 1.0f) return;  // the usual case: loss enters the total as a plain sum
     scale_span<T>(x, n, gv, VEC);
@@ -166,11 +186,7 @@ __global__ void __launch_bounds__(256) scale_grad2_kernel(T* __restrict__ x, lon
 // one collective per step (segdistill_b200/dist.py: DeferredLogs).
 __global__ void log_push_kernel(const float* __restrict__ values, int n, float* __restrict__ ring,
                                 unsigned* __restrict__ cursor, unsigned slots) {
-    const unsigned c = *cursor;
-    float* dst = ring + (size_t)(c % slots) * n;
-    for (int i = threadIdx.x; i < n; i += 32) dst[i] = values[i];
-    __syncwarp();
-    if (threadIdx.x == 0) *cursor = c + 1u;
+    log_append(LogSink{values, n, ring, cursor, slots});
 }
 
 cudaError_t launch_log_push(const float* values, int n, float* ring, unsigned* cursor, int slots, cudaStream_t stream) {
@@ -200,16 +216,18 @@ cudaError_t launch_mse(const void* S, const void* T, void* dS, float* loss, floa
     return cudaGetLastError();
 }
 
-cudaError_t launch_scale_grad(void* dS, long long n, bool bf16, const float* g, int grid, cudaStream_t stream) {
+cudaError_t launch_scale_grad(void* dS, long long n, bool bf16, const float* g, int grid, cudaStream_t stream,
+                              const float* log_values, int log_n, float* log_ring, unsigned* log_cursor, int log_slots) {
+    const LogSink sink{log_values, log_n, log_ring, log_cursor, (unsigned)(log_slots > 0 ? log_slots : 1)};
     const bool vec = aligned16(dS);
     if (bf16) {
         auto x = static_cast<__nv_bfloat16*>(dS);
-        if (vec) scale_grad_kernel<__nv_bfloat16, true><<<grid, 256, 0, stream>>>(x, n, g);
-        else scale_grad_kernel<__nv_bfloat16, false><<<grid, 256, 0, stream>>>(x, n, g);
+        if (vec) scale_grad_kernel<__nv_bfloat16, true><<<grid, 256, 0, stream>>>(x, n, g, sink);
+        else scale_grad_kernel<__nv_bfloat16, false><<<grid, 256, 0, stream>>>(x, n, g, sink);
     } else {
         auto x = static_cast<float*>(dS);
-        if (vec) scale_grad_kernel<float, true><<<grid, 256, 0, stream>>>(x, n, g);
-        else scale_grad_kernel<float, false><<<grid, 256, 0, stream>>>(x, n, g);
+        if (vec) scale_grad_kernel<float, true><<<grid, 256, 0, stream>>>(x, n, g, sink);
+        else scale_grad_kernel<float, false><<<grid, 256, 0, stream>>>(x, n, g, sink);
     }
     return cudaGetLastError();
 }

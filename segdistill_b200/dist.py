@@ -85,9 +85,14 @@ class DeferredLogs:
         self._flushed = 0                      # value of the cursor at the last flush
         self._pool = []                        # pinned landing buffers of the asynchronous flushes
 
-    def push(self, values, stream=None):
+    def push(self, values, stream=None, in_backward=False):
         """Append one step's scalars (a tensor of ``len(names)`` fp32 values, or a list of 0-dim tensors) - no
         synchronisation, no collective.  Inside a CUDA-graph capture this records the append into the graph.
+
+        ``in_backward`` (CUDA only): do not launch anything now; the append rides on the scaling launch of the step's
+        backward (``sd_scale_grad_log``: the launch every backward through a loss node makes anyway), so the step holds
+        no launch and no stream fork for its logging.  ``join()`` - call it after ``backward()`` - appends with a launch
+        of its own if no backward took the append (a step without gradients, a grouped or a two-factor backward).
 
         ``stream``: a side stream for the append (CUDA only).  The append is ordered behind the work queued so far on the
         current stream and the caller joins with ``join()`` later - typically after ``backward()``, so that the
@@ -97,6 +102,11 @@ class DeferredLogs:
         values = values.detach()
         if values.is_cuda:
             from . import _cabi
+            if in_backward:
+                if _cabi.pending_log is not None:
+                    self.join()                                   # (an append nobody took: it must keep its place in the ring)
+                _cabi.pending_log = (values.float().contiguous(), self.ring, self.cursor)
+                return
             if stream is not None:
                 stream.wait_stream(torch.cuda.current_stream(values.device))
                 with torch.cuda.stream(stream):
@@ -115,6 +125,12 @@ class DeferredLogs:
         if side is not None:
             torch.cuda.current_stream(self.device).wait_stream(side)
             self._side = None
+        if self.device.type == 'cuda':
+            from . import _cabi
+            log = _cabi.pending_log
+            if log is not None and log[1] is self.ring:           # push(in_backward=True) that no backward took
+                _cabi.pending_log = None
+                _cabi.log_push(log[0], self.ring, self.cursor)
 
     def flush_start(self):
         """Enqueue the flush without waiting for it: one all-reduce of the ring (mean over ranks), then asynchronous

@@ -635,6 +635,63 @@ def test_dispatcher_batches_entries_on_the_same_tensors():
     _assert_close(sum(v.item() for v in out2.values()), x2.grad.cpu(), r1s[0] + r2[0], r1s[1] + r2[1])
 
 
+def test_deferred_logs_on_the_device_and_the_append_that_rides_on_the_backward():
+    """dist.DeferredLogs on the GPU: the per-step append as its own launch (sd_log_push), on a side stream, and carried
+    by the backward's scaling launch (sd_scale_grad_log: no launch of its own); an append no backward took is made by
+    join(); the ring keeps the order of the steps."""
+    from segdistill_b200 import dist as sdist
+    logs = sdist.DeferredLogs(['loss_cgd', 'loss_cd'], interval=8, device=dev())
+    dl = sd.DistillationLoss([
+        {'student_layer': 'a', 'teacher_layer': 'a', 'loss_name': 'CGDLoss', 'loss_config': {}},
+        {'student_layer': 'b', 'teacher_layer': 'b', 'loss_name': 'CDLoss', 'loss_config': {}}])
+    want = []
+    side = torch.cuda.Stream()
+    for step in range(7):
+        s, t = seeded_pair((1, 20, 128, 128), seed=100 + step)
+        x = s.to(dev()).requires_grad_(True)
+        tt = t.to(dev())
+        out = dl({'a': x, 'b': x}, {'a': tt, 'b': tt}, None, 1)
+        l1, l2 = out.values()
+        mode = step % 4
+        before = _cabi.launch_count()
+        if mode == 0:                                  # rides on the backward
+            logs.push([l1, l2], in_backward=True)
+            (l1 + l2).backward()
+            assert _cabi.pending_log is None           # (sd_last_kernel is per thread: the backward ran on autograd's)
+            logs.join()
+            assert _cabi.launch_count() - before == 1  # the scaling launch alone
+        elif mode == 1:                                # nobody takes it: join() appends
+            logs.push([l1, l2], in_backward=True)
+            logs.join()
+            assert _cabi.last_kernel() == 'log_push_kernel' and _cabi.pending_log is None
+        elif mode == 2:                                # own launch on a side stream
+            logs.push([l1, l2], stream=side)
+            (l1 + l2).backward()
+            logs.join()
+        else:                                          # own launch
+            logs.push([l1, l2])
+            (3.0 * (l1 + l2)).backward()               # (a real scaling next to it)
+        want.append((l1.item(), l2.item()))
+    recs = logs.flush()
+    assert len(recs) == 7
+    for rec, (a, b) in zip(recs, want):
+        assert rec['loss_cgd'] == a and rec['loss_cd'] == b and rec['loss'] == pytest.approx(a + b, rel=1e-6)
+    # the scaling itself is untouched by the append: gradient of 3 x the loss
+    s, t = seeded_pair((1, 20, 128, 128), seed=200)
+    x = s.to(dev()).requires_grad_(True)
+    tt = t.to(dev())
+    l1, l2 = dl({'a': x, 'b': x}, {'a': tt, 'b': tt}, None, 1).values()
+    logs.push([l1, l2], in_backward=True)
+    (3.0 * (l1 + l2)).backward()
+    logs.join()
+    y = s.to(dev()).requires_grad_(True)
+    m1, m2 = dl({'a': y, 'b': y}, {'a': tt, 'b': tt}, None, 1).values()
+    (m1 + m2).backward()
+    torch.cuda.synchronize()
+    assert (x.grad - 3.0 * y.grad).abs().max().item() <= 1e-6 * (3.0 * y.grad).abs().max().item()
+    assert logs.flush()[-1]['loss_cd'] == l2.item()
+
+
 def test_c_abi_error_codes_on_device():
     lib = _cabi.load()
     assert lib.sd_device_check() == 0
