@@ -402,9 +402,12 @@ def run_ours(args, rank, local_rank, world):
             graph[0].replay()
             if logs is not None and (i + 1) % LOG_INTERVAL == 0:
                 flush_logs()
+        t_flush = torch.cuda.Event(enable_timing=True)
+        t_flush.record()
         flush_logs()                         # the timed region ends when the steps' scalars have been reduced and read
         t_end.record()
         sync_all()
+        final_flush_ms = t_flush.elapsed_time(t_end) if logs is not None else None
         l1, l2 = static_losses
         launches = per_step_launches * args.steps
     elapsed_ms = t_begin.elapsed_time(t_end)
@@ -419,7 +422,16 @@ def run_ours(args, rank, local_rank, world):
                 compute()
         torch.cuda.synchronize()
     clocks = sampler.stop(window=(t_load0, time.perf_counter())) if rank == 0 else None
+    per_rank = None
     if world > 1:
+        # every rank's own device time of the region (and of its K steps without the closing flush): the spread between
+        # the GPUs of the box is part of the max-over-ranks figure
+        steps_only = t_begin.elapsed_time(t_flush) if graph is not None else elapsed_ms
+        mine = torch.tensor([elapsed_ms, steps_only], device=dev)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_rank = {'region_ms_per_step': [round(t[0].item() / args.steps, 6) for t in every],
+                    'steps_only_ms_per_step': [round(t[1].item() / args.steps, 6) for t in every]}
         tt = torch.tensor([elapsed_ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         elapsed_ms = tt.item()
@@ -563,6 +575,13 @@ def run_ours(args, rank, local_rank, world):
         }
         if flushed:
             line['reduced_log_sample'] = flushed[-1]
+        if graph is not None and final_flush_ms is not None:
+            # rank 0's device time of the flush that closes the timed region (all-reduce of the ring + its read-back,
+            # the wait for the slowest rank included): the part of ms_per_step x steps that is not the steps themselves
+            line['log_flush'] = {'final_flush_ms': final_flush_ms, 'per_step_ms_at_this_K': final_flush_ms / args.steps,
+                                 'interval_steps': LOG_INTERVAL}
+        if per_rank is not None:
+            line['per_rank'] = per_rank
         if extra:
             line['extra'] = extra
         print(json.dumps(line), flush=True)

@@ -8,6 +8,7 @@ all-reduce (NCCL over NVLink on the B200 box, gloo in the CPU tests), one device
 """
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 
 import torch
@@ -80,8 +81,12 @@ class DeferredLogs:
         self.interval = int(interval)
         self.group = group
         self.device = torch.device('cpu') if device is None else torch.device(device)
-        self.ring = torch.zeros(self.interval, len(self.names), dtype=torch.float32, device=self.device)
-        self.cursor = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # one allocation: the ring's slots*n floats followed by the cursor (an int32 in the last word), so that a flush
+        # reads both back with ONE device->host copy
+        n = len(self.names)
+        self._buf = torch.zeros(self.interval * n + 1, dtype=torch.float32, device=self.device)
+        self.ring = self._buf[:self.interval * n].view(self.interval, n)
+        self.cursor = self._buf[self.interval * n:].view(torch.int32)
         self._flushed = 0                      # value of the cursor at the last flush
         self._pool = []                        # pinned landing buffers of the asynchronous flushes
 
@@ -133,35 +138,46 @@ class DeferredLogs:
                 _cabi.log_push(log[0], self.ring, self.cursor)
 
     def flush_start(self):
-        """Enqueue the flush without waiting for it: one all-reduce of the ring (mean over ranks), then asynchronous
-        device->host copies of the ring and of the cursor into pinned buffers.  Returns a handle for ``flush_finish``.
-        The launch stream is ordered behind the collective, so a CUDA event recorded after this call times it."""
+        """Enqueue the flush without waiting for it: one all-reduce of the ring (mean over ranks), then ONE asynchronous
+        device->host copy of ring + cursor into a pinned buffer.  Returns a handle for ``flush_finish``.
+        The launch stream is ordered behind the collective, so a CUDA event recorded after this call times it.
+
+        On NCCL the ring is averaged in place (``ReduceOp.AVG``: no clone, no divide - every row a flush reduces is
+        either read by that flush or overwritten before a later one reads it; rows reduced a second time hold the same
+        value on every rank already).  Other backends (gloo has no AVG) reduce a copy."""
         self.join()
-        ring = self.ring.clone()
-        if dist.is_available() and dist.is_initialized():
-            ring /= dist.get_world_size(self.group)
+        distributed = dist.is_available() and dist.is_initialized()
+        world = dist.get_world_size(self.group) if distributed else 1
+        if (distributed and world > 1 and self._buf.is_cuda and dist.get_backend(self.group) == 'nccl'
+                and os.environ.get('SD_LOG_FLUSH_COPY', '0') != '1'):
+            dist.all_reduce(self.ring, op=dist.ReduceOp.AVG, group=self.group)
+            buf = self._buf
+        elif distributed and world > 1:
+            buf = self._buf.clone()
+            ring = buf[:-1]
+            ring /= world
             dist.all_reduce(ring, group=self.group)
-        if ring.is_cuda:
-            host = self._pool.pop() if self._pool else (torch.empty(ring.shape, dtype=ring.dtype).pin_memory(),
-                                                        torch.empty(1, dtype=torch.int32).pin_memory())
-            host[0].copy_(ring, non_blocking=True)
-            host[1].copy_(self.cursor, non_blocking=True)
+        else:                              # nothing to reduce: the copy below is ordered on the stream (CUDA)
+            buf = self._buf if self._buf.is_cuda else self._buf.clone()
+        if buf.is_cuda:
+            host = self._pool.pop() if self._pool else torch.empty(buf.shape, dtype=buf.dtype).pin_memory()
+            host.copy_(buf, non_blocking=True)
             done = torch.cuda.Event()
             done.record()
-            return (host[0], host[1], done)
-        return (ring, self.cursor.clone(), None)
+            return (host, done)
+        return (buf, None)
 
     def flush_finish(self, handle):
         """Wait for a started flush and return, oldest first, one ``OrderedDict(name -> float)`` per step pushed since
         the previous flush (at most ``interval``); each gets ``'loss'`` = the sum of its entries whose name contains
         'loss' unless a variable of that name was pushed."""
-        ring, cursor, done = handle
+        buf, done = handle
         if done is not None:
             done.synchronize()             # the one synchronisation of the interval
-        cur = int(cursor.item())
-        host = ring.tolist()
+        cur = int(buf[-1:].view(torch.int32).item())
+        host = buf[:-1].view(self.interval, len(self.names)).tolist()
         if done is not None:
-            self._pool.append((ring, cursor))  # pinned landing buffers, reused by a later flush
+            self._pool.append(buf)         # pinned landing buffer, reused by a later flush
         n = min((cur - self._flushed) & 0x7fffffff, self.interval)
         self._flushed = cur
         out = []
