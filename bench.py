@@ -436,7 +436,8 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         elapsed_ms = tt.item()
     assert _cabi.workspace_error_flag() == 0
-    fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)     # the loss kernel(s) of one eager step (+ host gaps)
+    fwd_ms = statistics.median(e[0].elapsed_time(e[1]) for e in evs)   # the loss kernel(s) of one eager step (+ host gaps);
+    # median over the K steps: one poll of the clock sampler inside a step's window is milliseconds
     # the dominant kernel alone: the same fused launch through the C ABI, back to back on this stream
     kern_ms = None
     if dl.batch_pairs:
@@ -450,7 +451,7 @@ def run_ours(args, rank, local_rank, world):
             kb.record()
             torch.cuda.synchronize()
             kern_ms = ka.elapsed_time(kb) / args.steps
-    bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+    bwd_ms = statistics.median(e[1].elapsed_time(e[2]) for e in evs)
     ms_per_step = elapsed_ms / args.steps
     value = world * B_PER_GPU * H * W / (ms_per_step * 1e-3) / 1e6
 

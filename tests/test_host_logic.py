@@ -158,6 +158,25 @@ def test_parse_losses_single_process():
     assert logs == {'loss_seg': 1.5, 'acc': 80.0, 'loss_kd': 0.75, 'loss': 2.25}
 
 
+def test_deferred_logs_single_process_ring_wraps_and_reads_back_in_one_buffer():
+    """dist.DeferredLogs without a process group: the ring and its cursor are ONE allocation (a flush reads both back
+    with one copy), a flush returns the steps since the previous one oldest first, at most ``interval`` of them, and
+    'loss' = the sum of the entries whose name contains 'loss' (SD_structure.py:121-122)."""
+    dl = sdist.DeferredLogs(['loss_a', 'loss_b', 'acc'], interval=4)
+    assert dl.ring.untyped_storage().data_ptr() == dl.cursor.untyped_storage().data_ptr()
+    assert dl.cursor.dtype == torch.int32 and dl.ring.shape == (4, 3)
+    assert dl.flush() == []
+    for i in range(6):                                 # six steps into four slots: the two oldest are overwritten
+        dl.push(torch.tensor([float(i), 0.5, 10.0 + i]))
+    recs = dl.flush()
+    assert [r['loss_a'] for r in recs] == [2.0, 3.0, 4.0, 5.0]
+    assert all(r['loss'] == r['loss_a'] + 0.5 and r['acc'] == 10.0 + r['loss_a'] for r in recs)
+    dl.push([torch.tensor(7.0), torch.tensor(1.0), torch.tensor(0.25)])    # a list of 0-dim tensors
+    assert dl.flush() == [{'loss_a': 7.0, 'loss_b': 1.0, 'acc': 0.25, 'loss': 8.0}]
+    assert dl.flush() == []
+    assert int(dl.cursor.item()) == 7
+
+
 def test_autograd_adopts_the_gradient_buffer_without_copy():
     """The pattern functional._finish_backward relies on: dropping ctx's reference lets autograd keep dS."""
     holder = {}
