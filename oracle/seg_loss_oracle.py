@@ -14,7 +14,6 @@ tests/test_oracle.py checks this restatement against them.
 """
 from __future__ import annotations
 
-import torch
 import torch.nn.functional as F
 
 
