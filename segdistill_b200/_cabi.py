@@ -185,6 +185,7 @@ def _dev_index(device: torch.device) -> int:
 
 # ---------------------------------------------------------------- workspaces
 _workspaces = {}
+_retired_workspaces = []    # outgrown workspaces stay allocated: a captured CUDA graph may hold their address
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
@@ -193,6 +194,8 @@ def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
     key = (idx, _raw_stream(idx))
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            _retired_workspaces.append(ws)
         ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
